@@ -1,0 +1,1211 @@
+// rv_core.cuh — per-read logic of the pileup path: read filters, CIGAR rewrite rules, CIGAR walk.
+//
+// Written from scratch as table/array code (no strings, no regex, no hash maps) so it runs one read
+// per GPU thread; every function cites the reference lines whose behaviour it reproduces
+// (LeiHaoa/RabbitVar: src/parseCigar.cpp, src/cigarModifier.cpp, include/VariationUtils.h).
+// Functions are __host__ __device__ so tests/ can also single-step them on the CPU; the product only
+// ever launches them from kernels (rv_kernels.cu) — there is no CPU execution path in the library.
+#pragma once
+#include "../../../include/rabbitvar_b200.h"
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define RV_HD __host__ __device__ __forceinline__
+#define RV_HDN __host__ __device__
+#else
+#define RV_HD inline
+#define RV_HDN inline
+#endif
+
+namespace rvk {
+
+enum { OP_M = 0, OP_I = 1, OP_D = 2, OP_N = 3, OP_S = 4, OP_H = 5, OP_P = 6, OP_EQ = 7, OP_X = 8, OP_B = 9 };
+static const int RV_MAX_OPS = 48;
+static const int CONF_LOWQUAL = 10;  // include/Configuration.h:14-27
+
+RV_HD int c_op(uint32_t c) { return (int)(c & 0xf); }
+RV_HD int c_len(uint32_t c) { return (int)(c >> 4); }
+RV_HD uint32_t c_make(int len, int op) { return ((uint32_t)len << 4) | (uint32_t)op; }
+
+// Reference window of the region (RecordPreprocessor::makeReference, recordPreprocessor.cpp:41-78):
+// a position "exists" iff it lies in [lo, hi]; the bases themselves are a flat contig slice.
+struct RefView {
+  const char* bases;
+  int32_t base_pos;  // reference position of bases[0]
+  int64_t n;
+  int32_t lo, hi;
+  RV_HD bool has(int p) const { return p >= lo && p <= hi && p >= base_pos && (int64_t)(p - base_pos) < n; }
+  // value of ref[p] as the reference's operator[] returns it: '\0' for a missing key
+  RV_HD char at(int p) const { return has(p) ? bases[p - base_pos] : (char)0; }
+};
+
+RV_HD char nt16_char(int nib) {
+  // seq_nt16_str "=ACMGRSVTWYHKDBN" packed 4 chars per word would also do; a switch keeps it in registers
+  switch (nib) {
+    case 1: return 'A'; case 2: return 'C'; case 4: return 'G'; case 8: return 'T'; case 15: return 'N';
+    case 0: return '='; case 3: return 'M'; case 5: return 'R'; case 6: return 'S'; case 7: return 'V';
+    case 9: return 'W'; case 10: return 'Y'; case 11: return 'H'; case 12: return 'K'; case 13: return 'D';
+    default: return 'B';
+  }
+}
+RV_HD int allele_of(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
+RV_HD bool is_atgc(char c) { return c == 'A' || c == 'T' || c == 'G' || c == 'C'; }
+
+struct ReadView {
+  const uint8_t* seq4;
+  const uint8_t* qual;
+  int lseq;
+  RV_HD char base(int i) const {
+    if (i < 0 || i >= lseq) return (char)0;
+    int b = seq4[i >> 1];
+    return nt16_char((i & 1) ? (b & 15) : (b >> 4));
+  }
+  RV_HD int q(int i) const { return (i < 0 || i >= lseq) ? 0 : (int)qual[i]; }
+};
+
+struct Cigar {
+  uint32_t op[RV_MAX_OPS];
+  int n;
+  bool overflow;
+  RV_HD void replace(int at, int count, const uint32_t* nw, int nnew) {
+    int tail = n - (at + count);
+    int nn = at + nnew + tail;
+    if (nn > RV_MAX_OPS) { overflow = true; return; }
+    if (nnew > count) for (int k = tail - 1; k >= 0; --k) op[at + nnew + k] = op[at + count + k];
+    else if (nnew < count) for (int k = 0; k < tail; ++k) op[at + nnew + k] = op[at + count + k];
+    for (int k = 0; k < nnew; ++k) op[at + k] = nw[k];
+    n = nn;
+  }
+};
+
+// Small fixed-capacity key builder (allele description strings, include/Variant.h:24-33).
+struct Key {
+  char c[52];
+  int n;
+  bool trunc;
+  RV_HD void clear() { n = 0; trunc = false; }
+  RV_HD void push(char ch) { if (n < 52) c[n++] = ch; else trunc = true; }
+  RV_HD void push_int(int v) {
+    char tmp[12];
+    int k = 0;
+    if (v == 0) tmp[k++] = '0';
+    bool neg = v < 0;
+    unsigned u = neg ? (unsigned)(-v) : (unsigned)v;
+    while (u) { tmp[k++] = (char)('0' + u % 10); u /= 10; }
+    if (neg) push('-');
+    while (k) push(tmp[--k]);
+  }
+  RV_HD void insert_at(int idx, char ch) {  // std::string::insert(idx, 1, ch); idx <= n assumed
+    if (idx > n) idx = n;
+    if (n >= 52) { trunc = true; return; }
+    for (int k = n; k > idx; --k) c[k] = c[k - 1];
+    c[idx] = ch;
+    n++;
+  }
+  RV_HD void erase_first(char ch) {  // replaceFirst(s, ch, "")
+    for (int k = 0; k < n; ++k)
+      if (c[k] == ch) { for (int j = k; j + 1 < n; ++j) c[j] = c[j + 1]; n--; return; }
+  }
+  RV_HD void prepend(const char* s, int len) {
+    if (n + len > 52) { trunc = true; return; }
+    for (int k = n - 1; k >= 0; --k) c[k + len] = c[k];
+    for (int k = 0; k < len; ++k) c[k] = s[k];
+    n += len;
+  }
+  RV_HD bool contains(char ch) const { for (int k = 0; k < n; ++k) if (c[k] == ch) return true; return false; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// CigarModifier::modifyCigar (src/cigarModifier.cpp:219-410) on op arrays.
+// ------------------------------------------------------------------------------------------------
+struct ModCtx {
+  Cigar* cg;
+  int position;
+  const ReadView* rd;
+  const RefView* ref;
+  bool unsupported;
+};
+
+// sums used by the helpers: ALIGNED_LENGTH_MND "(\d+)[MND]" and SOFT_CLIPPED "(\d+)[MIS]" over a prefix
+RV_HD int sum_mnd(const Cigar& c, int upto) {
+  int s = 0;
+  for (int k = 0; k < upto; ++k) { int o = c_op(c.op[k]); if (o == OP_M || o == OP_N || o == OP_D) s += c_len(c.op[k]); }
+  return s;
+}
+RV_HD int sum_mis(const Cigar& c, int upto) {
+  int s = 0;
+  for (int k = 0; k < upto; ++k) { int o = c_op(c.op[k]); if (o == OP_M || o == OP_I || o == OP_S) s += c_len(c.op[k]); }
+  return s;
+}
+RV_HD bool has_eq(const RefView& r, int p, char ch) { return r.has(p) && r.at(p) == ch; }   // isHasAndEquals
+RV_HD bool has_ne(const RefView& r, int p, char ch) { return r.has(p) && r.at(p) != ch; }   // isHasAndNotEquals
+
+// distinct reference bases collected in a std::set<char> — we only need "more than one distinct"
+struct BaseSet {
+  unsigned mask;
+  RV_HD BaseSet() : mask(0) {}
+  RV_HD void add(char ch) { mask |= 1u << ((unsigned char)ch & 31); }  // A,C,G,T,N map to distinct bits
+  RV_HD int size() const { int s = 0; for (unsigned m = mask; m; m &= m - 1) ++s; return s; }
+};
+
+// backward walk shared by captureMisSoftly3Mismatches / captureMisSoftlyMS (:546-562, :639-655):
+// rn = 1 + index of the last mismatch seen before 3 consecutive matches, scanning from the M end.
+RV_HD int tail_mismatch_walk(const ModCtx& m, int mch, int refoff, int rdoff) {
+  int rn = 0, rrn = 0, rmch = 0;
+  while (rrn < mch && rn < mch) {
+    if (!m.ref->has(refoff - rrn - 1)) break;
+    if (rrn < rdoff) {
+      if (m.ref->at(refoff - rrn - 1) != m.rd->base(rdoff - rrn - 1)) { rn = rrn + 1; rmch = 0; }
+      else rmch++;
+    }
+    rrn++;
+    if (rmch >= 3) break;
+  }
+  return rn;
+}
+// forward walk shared by combineBeginDigM / combineDigSDigM (:418-433, :499-514)
+RV_HD int head_mismatch_walk(const ModCtx& m, int mch, int position, int soft) {
+  int rn = 0, rrn = 0, rmch = 0;
+  while (rrn < mch && rn < mch) {
+    if (!m.ref->has(position + rrn)) break;
+    if (has_ne(*m.ref, position + rrn, m.rd->base(soft + rrn))) { rn = rrn + 1; rmch = 0; }
+    else if (has_eq(*m.ref, position + rrn, m.rd->base(soft + rrn))) rmch++;
+    rrn++;
+    if (rmch >= 3) break;
+  }
+  return rn;
+}
+
+// tail "...(m)M(s)S$" : captureMisSoftlyMS, cigarModifier.cpp:574-668
+RV_HD void capture_mis_softly_ms(ModCtx& m) {
+  Cigar& c = *m.cg;
+  int im = c.n - 2;
+  int mch = c_len(c.op[im]), soft = c_len(c.op[im + 1]);
+  int refoff = m.position + mch + sum_mnd(c, im);
+  int rdoff = mch + sum_mis(c, im);
+  int rn = 0;
+  while (rn < soft && has_eq(*m.ref, refoff + rn, m.rd->base(rdoff + rn)) && m.rd->q(rdoff + rn) > CONF_LOWQUAL) rn++;
+  if (rn > 0) {
+    mch += rn;
+    soft -= rn;
+    rn = 0;
+  }
+  if (soft > 0) {
+    BaseSet RN;
+    while (rn + 1 < soft && has_eq(*m.ref, refoff + rn + 1, m.rd->base(rdoff + rn + 1)) &&
+           m.rd->q(rdoff + rn + 1) > CONF_LOWQUAL) {
+      rn++;
+      if (m.ref->has(refoff + rn + 1)) RN.add(m.ref->at(refoff + rn + 1));
+    }
+    if (rn > 4 && RN.size() > 1) {
+      mch += rn + 1;
+      soft -= rn + 1;
+    }
+    if (rn == 0) {
+      rn = tail_mismatch_walk(m, mch, refoff, rdoff);
+      if (rn > 0 && rn < mch) {
+        soft += rn;
+        mch -= rn;
+      }
+    }
+  }
+  uint32_t nw[2];
+  int k = 0;
+  nw[k++] = c_make(mch, OP_M);
+  if (soft > 0) nw[k++] = c_make(soft, OP_S);
+  c.replace(im, 2, nw, k);
+}
+
+// tail "...(m)M$" : captureMisSoftly3Mismatches, cigarModifier.cpp:529-568
+RV_HD void capture_mis_softly_3mm(ModCtx& m) {
+  Cigar& c = *m.cg;
+  int im = c.n - 1;
+  int mch = c_len(c.op[im]);
+  int refoff = m.position + mch + sum_mnd(c, im);
+  int rdoff = mch + sum_mis(c, im);
+  int rn = tail_mismatch_walk(m, mch, refoff, rdoff);
+  mch -= rn;
+  if (rn > 0 && rn <= 3) {
+    uint32_t nw[2] = {c_make(mch, OP_M), c_make(rn, OP_S)};
+    c.replace(im, 1, nw, 2);
+  }
+}
+
+// head "^(s)S(m)M" : combineDigSDigM, cigarModifier.cpp:445-523
+RV_HD void combine_digs_digm(ModCtx& m) {
+  Cigar& c = *m.cg;
+  int soft = c_len(c.op[0]), mch = c_len(c.op[1]);
+  int rn = 0;
+  while (rn < soft && has_eq(*m.ref, m.position - rn - 1, m.rd->base(soft - rn - 1)) &&
+         m.rd->q(soft - rn - 1) > CONF_LOWQUAL)
+    rn++;
+  if (rn > 0) {
+    mch += rn;
+    soft -= rn;
+    m.position -= rn;
+    rn = 0;
+  }
+  if (soft > 0) {
+    BaseSet RN;
+    while (rn + 1 < soft && has_eq(*m.ref, m.position - rn - 2, m.rd->base(soft - rn - 2)) &&
+           m.rd->q(soft - rn - 2) > CONF_LOWQUAL) {
+      rn++;
+      if (m.ref->has(m.position - rn - 2)) RN.add(m.ref->at(m.position - rn - 2));
+    }
+    if ((rn > 4 && RN.size() > 1) || has_eq(*m.ref, m.position - 1, m.rd->base(soft - 1))) {
+      mch += rn + 1;
+      soft -= rn + 1;
+      m.position -= rn + 1;
+    }
+    if (rn == 0) {
+      rn = head_mismatch_walk(m, mch, m.position, soft);
+      if (rn > 0 && rn < mch) {
+        soft += rn;
+        mch -= rn;
+        m.position += rn;
+      }
+    }
+  }
+  uint32_t nw[2];
+  int k = 0;
+  if (soft > 0) nw[k++] = c_make(soft, OP_S);
+  nw[k++] = c_make(mch, OP_M);
+  c.replace(0, 2, nw, k);
+}
+
+// head "^(m)M" : combineBeginDigM, cigarModifier.cpp:412-439
+RV_HD void combine_begin_digm(ModCtx& m) {
+  Cigar& c = *m.cg;
+  int mch = c_len(c.op[0]);
+  int rn = head_mismatch_walk(m, mch, m.position, 0);
+  if (rn > 0 && rn <= 3) {
+    mch -= rn;
+    uint32_t nw[2] = {c_make(rn, OP_S), c_make(mch, OP_M)};
+    c.replace(0, 1, nw, 2);
+    m.position += rn;
+  }
+}
+
+RV_HD bool is_id(int o) { return o == OP_I || o == OP_D; }
+RV_HD bool one_digit(int len) { return len >= 0 && len <= 9; }
+
+// shared tail of threeIndels / threeDeletions / twoDeletionsInsertionToComplex (:771-800, :846-858, :907-918)
+RV_HD int build_complex(uint32_t* nw, int RDOFF, int dlen, int tslen, int rm, bool three_indels) {
+  int k = 0;
+  if (tslen <= 0) {
+    dlen -= tslen;
+    rm += tslen;
+    if (three_indels) {
+      if (dlen == 0) {
+        RDOFF = RDOFF + rm;
+        nw[k++] = c_make(RDOFF, OP_M);
+        return k;
+      } else if (dlen < 0) {
+        tslen = -dlen;
+        rm += dlen;
+        if (rm < 0) {
+          RDOFF = RDOFF + rm;
+          nw[k++] = c_make(RDOFF, OP_M);
+          nw[k++] = c_make(tslen, OP_I);
+        } else {
+          nw[k++] = c_make(RDOFF, OP_M);
+          nw[k++] = c_make(tslen, OP_I);
+          nw[k++] = c_make(rm, OP_M);
+        }
+        return k;
+      }
+    }
+    nw[k++] = c_make(RDOFF, OP_M);
+    nw[k++] = c_make(dlen, OP_D);
+    nw[k++] = c_make(rm, OP_M);
+  } else {
+    nw[k++] = c_make(RDOFF, OP_M);
+    if (three_indels && dlen == 0) {
+      nw[k++] = c_make(tslen, OP_I);
+      nw[k++] = c_make(rm, OP_M);
+    } else if (three_indels && dlen < 0) {
+      rm += dlen;
+      nw[k++] = c_make(tslen, OP_I);
+      nw[k++] = c_make(rm, OP_M);
+    } else {
+      nw[k++] = c_make(dlen, OP_D);
+      nw[k++] = c_make(tslen, OP_I);
+      nw[k++] = c_make(rm, OP_M);
+    }
+  }
+  return k;
+}
+
+// Returns true when the CIGAR (or position) was rewritten; `position` is updated only then
+// (parseCigar.cpp:559-567).
+RV_HDN bool modify_cigar(Cigar& cg, int& position_io, const ReadView& rd, const RefView& ref, int indel,
+                         bool* unsupported) {
+  Cigar orig;
+  orig.n = cg.n;
+  orig.overflow = false;
+  for (int k = 0; k < cg.n; ++k) orig.op[k] = cg.op[k];
+  ModCtx m;
+  m.cg = &cg;
+  m.position = position_io;
+  m.rd = &rd;
+  m.ref = &ref;
+  m.unsupported = false;
+  // :247-256 — a leading D advances a local pointer without shrinking n_cigar (reads one op past the
+  // end): refused.  A leading I is rewritten to D.  The two trailing tests compare a whole CIGAR word
+  // with an opcode and never fire.
+  if (c_op(cg.op[0]) == OP_D) { *unsupported = true; return false; }
+  if (c_op(cg.op[0]) == OP_I) cg.op[0] = c_make(c_len(cg.op[0]), OP_D);
+
+  bool flag = true;
+  int guard = 0;
+  while (flag && indel > 0) {
+    if (++guard > 64) { *unsupported = true; break; }
+    flag = false;
+    Cigar& c = cg;
+    // ^(\d+)S(\d+)([ID])  :263-272
+    if (c.n >= 2 && c_op(c.op[0]) == OP_S && is_id(c_op(c.op[1]))) {
+      int s = c_len(c.op[0]), l = c_len(c.op[1]);
+      bool ins = c_op(c.op[1]) == OP_I;
+      m.position += ins ? 0 : l;
+      uint32_t nw = c_make(s + (ins ? l : 0), OP_S);
+      c.replace(0, 2, &nw, 1);
+      flag = true;
+    }
+    // (\d+)([ID])(\d+)S$  :274-279
+    if (c.n >= 2 && c_op(c.op[c.n - 1]) == OP_S && is_id(c_op(c.op[c.n - 2]))) {
+      int s = c_len(c.op[c.n - 1]), l = c_len(c.op[c.n - 2]);
+      bool ins = c_op(c.op[c.n - 2]) == OP_I;
+      uint32_t nw = c_make(s + (ins ? l : 0), OP_S);
+      c.replace(c.n - 2, 2, &nw, 1);
+      flag = true;
+    }
+    // ^(\d+)S(\d+)M(\d+)([ID])  :281-290
+    if (c.n >= 3 && c_op(c.op[0]) == OP_S && c_op(c.op[1]) == OP_M && is_id(c_op(c.op[2]))) {
+      int tmid = c_len(c.op[1]);
+      if (tmid <= 10) {
+        int s = c_len(c.op[0]), l = c_len(c.op[2]);
+        bool ins = c_op(c.op[2]) == OP_I;
+        m.position += tmid + (ins ? 0 : l);
+        uint32_t nw = c_make(s + tmid + (ins ? l : 0), OP_S);
+        c.replace(0, 3, &nw, 1);
+        flag = true;
+      }
+    }
+    // (\d+)([ID])(\d+)M(\d+)S$  :292-306
+    if (c.n >= 3 && c_op(c.op[c.n - 1]) == OP_S && c_op(c.op[c.n - 2]) == OP_M && is_id(c_op(c.op[c.n - 3]))) {
+      int tmid = c_len(c.op[c.n - 2]);
+      if (tmid <= 10) {
+        int s = c_len(c.op[c.n - 1]), l = c_len(c.op[c.n - 3]);
+        bool ins = c_op(c.op[c.n - 3]) == OP_I;
+        uint32_t nw = c_make(s + tmid + (ins ? l : 0), OP_S);
+        c.replace(c.n - 3, 3, &nw, 1);
+        flag = true;
+      }
+    }
+    // ^(\d)M(\d+)([ID])(\d+)M  -> beginDigitMNumberIorDNumberM  :309-312, :975-1000
+    if (c.n >= 3 && c_op(c.op[0]) == OP_M && one_digit(c_len(c.op[0])) && is_id(c_op(c.op[1])) &&
+        c_op(c.op[2]) == OP_M) {
+      int tmid = c_len(c.op[0]), l = c_len(c.op[1]), mlen = c_len(c.op[2]);
+      bool ins = c_op(c.op[1]) == OP_I;
+      int tslen = tmid + (ins ? l : 0);
+      m.position += tmid + (ins ? 0 : l);
+      int tn = 0;
+      while (tn < mlen && has_ne(ref, m.position + tn, rd.base(tslen + tn))) tn++;
+      tslen += tn;
+      mlen -= tn;
+      m.position += tn;
+      uint32_t nw[2] = {c_make(tslen, OP_S), c_make(mlen, OP_M)};
+      c.replace(0, 3, nw, 2);
+      flag = true;
+    }
+    // (\d+)([ID])(\d)M$  :313-319
+    if (c.n >= 2 && c_op(c.op[c.n - 1]) == OP_M && one_digit(c_len(c.op[c.n - 1])) && is_id(c_op(c.op[c.n - 2]))) {
+      int tmid = c_len(c.op[c.n - 1]), l = c_len(c.op[c.n - 2]);
+      bool ins = c_op(c.op[c.n - 2]) == OP_I;
+      uint32_t nw = c_make(tmid + (ins ? l : 0), OP_S);
+      c.replace(c.n - 2, 2, &nw, 1);
+      flag = true;
+    }
+    // :321-331 — three searches on the same string, then at most one rewrite.
+    //   D_M_D_DD_M_D_I_D_M_D_DD : ^(.*?)(\d+)M(\d+)D(\d+)M(\d+)I(\d+)M(\d+)D(\d+)M
+    //   threeDeletionsPattern   : ^(.*?)(\d+)M(\d+)D(\d+)M(\d+)D(\d+)M(\d+)D(\d+)M
+    //   threeIndelsPattern      : ^(.*?)(\d+)M(\d+)([DI])(\d+)M(\d+)([DI])(\d+)M(\d+)([DI])(\d+)M
+    // The lazy prefix makes each search return its left-most occurrence.
+    {
+      int i_mdmimdm = -1, i_3del = -1, i_3indel = -1;
+      for (int k = 0; k + 7 <= c.n; ++k) {
+        bool seven = c_op(c.op[k]) == OP_M && c_op(c.op[k + 2]) == OP_M && c_op(c.op[k + 4]) == OP_M &&
+                     c_op(c.op[k + 6]) == OP_M && is_id(c_op(c.op[k + 1])) && is_id(c_op(c.op[k + 3])) &&
+                     is_id(c_op(c.op[k + 5]));
+        if (!seven) continue;
+        int o1 = c_op(c.op[k + 1]), o3 = c_op(c.op[k + 3]), o5 = c_op(c.op[k + 5]);
+        if (i_3indel < 0) i_3indel = k;
+        if (i_3del < 0 && o1 == OP_D && o3 == OP_D && o5 == OP_D) i_3del = k;
+        if (i_mdmimdm < 0 && o1 == OP_D && o3 == OP_I && o5 == OP_D) i_mdmimdm = k;
+      }
+      int at = -1, kind = 0;
+      if (i_mdmimdm >= 0) { at = i_mdmimdm; kind = 1; }
+      else if (i_3del >= 0) { at = i_3del; kind = 2; }
+      else if (i_3indel >= 0) { at = i_3indel; kind = 3; }
+      if (at >= 0) {
+        int g[8];
+        for (int k = 0; k < 7; ++k) g[k + 1] = c_len(c.op[at + k]);  // g[1]..g[7] = the seven lengths
+        int o1 = c_op(c.op[at + 1]), o3 = c_op(c.op[at + 3]), o5 = c_op(c.op[at + 5]);
+        int mid = g[3] + g[5];
+        int tslen, dlen;
+        if (kind == 1) {         // twoDeletionsInsertionToComplex :877-921
+          tslen = g[3] + g[4] + g[5];
+          dlen = g[2] + g[3] + g[5] + g[6];
+        } else if (kind == 2) {  // threeDeletions :815-862
+          tslen = g[3] + g[5];
+          dlen = g[2] + g[3] + g[4] + g[5] + g[6];
+        } else {                 // threeIndels :738-806
+          tslen = mid + (o1 == OP_I ? g[2] : 0) + (o3 == OP_I ? g[4] : 0) + (o5 == OP_I ? g[6] : 0);
+          dlen = mid + (o1 == OP_D ? g[2] : 0) + (o3 == OP_D ? g[4] : 0) + (o5 == OP_D ? g[6] : 0);
+        }
+        int refoff = m.position + g[1] + sum_mnd(c, at);
+        int rdoff = g[1] + sum_mis(c, at);
+        int RDOFF = g[1];
+        int rm = g[7];
+        int rn = 0;
+        while (rdoff + rn < rd.lseq && has_eq(ref, refoff + rn, rd.base(rdoff + rn))) rn++;
+        RDOFF += rn;
+        dlen -= rn;
+        tslen -= rn;
+        if (mid <= 15) {
+          uint32_t nw[4];
+          int k = build_complex(nw, RDOFF, dlen, tslen, rm, kind == 3);
+          // the replacement regex is un-anchored and format_first_only: it rewrites the FIRST
+          // occurrence of the seven-op shape, which for kinds 2/3 is `at` by construction; for kind 1
+          // the prim pattern (M D M I M D M) first occurrence is `at` as well.
+          for (int j = 0; j < k; ++j)
+            if ((int32_t)(nw[j] >> 4) < 0 || (nw[j] >> 4) > 0x0fffffff) m.unsupported = true;
+          c.replace(at, 7, nw, k);
+          flag = true;
+        }
+      }
+    }
+    // (\d+)D(\d+)M(\d+)([DI])(\d+I)?  -> combineToCloseToCorrect  :333-336, :717-741
+    for (int k = 0; k + 3 <= c.n; ++k) {
+      if (c_op(c.op[k]) == OP_D && c_op(c.op[k + 1]) == OP_M && is_id(c_op(c.op[k + 2]))) {
+        int g1 = c_len(c.op[k]), g2 = c_len(c.op[k + 1]), g3 = c_len(c.op[k + 2]);
+        if (g2 <= 15) {
+          bool opI = c_op(c.op[k + 2]) == OP_I;
+          int dlen = g1 + g2, ilen = g2, used = 3;
+          bool trailing_i = k + 3 < c.n && c_op(c.op[k + 3]) == OP_I;
+          if (opI) ilen += g3;
+          else {
+            dlen += g3;
+            if (trailing_i) ilen += c_len(c.op[k + 3]);
+          }
+          if (trailing_i) used = 4;  // the optional group is part of the match that gets replaced
+          uint32_t nw[2] = {c_make(dlen, OP_D), c_make(ilen, OP_I)};
+          c.replace(k, used, nw, 2);
+          flag = true;
+        }
+        break;  // regex_search only ever sees the left-most occurrence
+      }
+    }
+    // (\D)(\d+)I(\d+)M(\d+)([DI])(\d+I)?  -> combineToCloseToOne  :338-341, :675-705
+    for (int k = 1; k + 3 <= c.n; ++k) {
+      if (c_op(c.op[k]) == OP_I && c_op(c.op[k + 1]) == OP_M && is_id(c_op(c.op[k + 2]))) {
+        int prev = c_op(c.op[k - 1]);
+        if (prev != OP_D && prev != OP_H) {
+          int g2 = c_len(c.op[k]), g3 = c_len(c.op[k + 1]), g4 = c_len(c.op[k + 2]);
+          if (g3 <= 15) {
+            bool opI = c_op(c.op[k + 2]) == OP_I;
+            int dlen = g3, ilen = g2 + g3, used = 3;
+            bool trailing_i = k + 3 < c.n && c_op(c.op[k + 3]) == OP_I;
+            if (opI) ilen += g4;
+            else {
+              dlen += g4;
+              if (trailing_i) ilen += c_len(c.op[k + 3]);
+            }
+            if (trailing_i) used = 4;
+            uint32_t nw[2] = {c_make(dlen, OP_D), c_make(ilen, OP_I)};
+            c.replace(k, used, nw, 2);
+            flag = true;
+          }
+        }
+        break;
+      }
+    }
+    // (\d+)D(\d+)D :342-348 and (\d+)I(\d+)I :349-355 (first occurrence only)
+    for (int k = 0; k + 2 <= c.n; ++k)
+      if (c_op(c.op[k]) == OP_D && c_op(c.op[k + 1]) == OP_D) {
+        uint32_t nw = c_make(c_len(c.op[k]) + c_len(c.op[k + 1]), OP_D);
+        c.replace(k, 2, &nw, 1);
+        flag = true;
+        break;
+      }
+    for (int k = 0; k + 2 <= c.n; ++k)
+      if (c_op(c.op[k]) == OP_I && c_op(c.op[k + 1]) == OP_I) {
+        uint32_t nw = c_make(c_len(c.op[k]) + c_len(c.op[k + 1]), OP_I);
+        c.replace(k, 2, &nw, 1);
+        flag = true;
+        break;
+      }
+  }
+  // :365-377
+  if (cg.n >= 2 && c_op(cg.op[cg.n - 1]) == OP_S && c_op(cg.op[cg.n - 2]) == OP_M) capture_mis_softly_ms(m);
+  else if (cg.n >= 1 && c_op(cg.op[cg.n - 1]) == OP_M) capture_mis_softly_3mm(m);
+  if (cg.n >= 2 && c_op(cg.op[0]) == OP_S && c_op(cg.op[1]) == OP_M) combine_digs_digm(m);
+  else if (cg.n >= 1 && c_op(cg.op[0]) == OP_M) combine_begin_digm(m);
+
+  if (m.unsupported || cg.overflow) *unsupported = true;
+  // :380-401 — "changed" is a comparison of the rendered strings
+  bool same = cg.n == orig.n;
+  for (int k = 0; same && k < cg.n; ++k) same = cg.op[k] == orig.op[k];
+  if (same) return false;
+  position_io = m.position;
+  return true;
+}
+
+// CigarParser::cleanupCigar, parseCigar.cpp:1858-1892
+RV_HD void cleanup_cigar(Cigar& c) {
+  bool no_match_yet = true;
+  for (int k = 0; k < c.n && no_match_yet; ++k) {
+    int o = c_op(c.op[k]);
+    if (o == OP_I) c.op[k] = c_make(c_len(c.op[k]), OP_S);
+    else if (o == OP_H) {}
+    else if (o == OP_M || o == OP_EQ || o == OP_X) no_match_yet = false;
+  }
+  no_match_yet = true;
+  for (int k = c.n - 1; k >= 0 && no_match_yet; --k) {
+    int o = c_op(c.op[k]);
+    if (o == OP_I) c.op[k] = c_make(c_len(c.op[k]), OP_S);
+    else if (o == OP_H) {}
+    else if (o == OP_M || o == OP_EQ || o == OP_X) no_match_yet = false;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CigarParser::parseCigar, parseCigar.cpp:497-974, with its helpers.
+// Sink concept:
+//   void single(int pos, int allele, bool dir, int tp, int q, int mapq, int nm)   M-path obs, single base key
+//   void adj(int pos, int allele, int sign, bool dir, int tp, int q, int mapq, int nm)  addCnt / subtraction
+//   void cov(int pos)                                                               refCoverage[pos]++
+//   void event(const rv_event&)
+//   void max_read_len(int tlen)
+//   void kept(int aligned_bases) ; void unsupported()
+// ------------------------------------------------------------------------------------------------
+struct WalkState {
+  int start, rp, re, offset, clen;  // start, readPositionIncluding/ExcludingSoftClipped, offset, cigar_element_length
+  int seq_no;
+};
+
+template <class Sink>
+RV_HD void emit_event(Sink& s, WalkState& w, int region_idx, uint32_t read_idx, int kind, int pos, const Key* key,
+                      int flags, bool dir, int tp, int qsum, int qcnt, int mapq, int nm, int aux0, int aux1, int aux2) {
+  rv_event e;
+  e.region = region_idx;
+  e.pos = pos;
+  e.read_idx = read_idx;
+  e.seq_no = (uint16_t)w.seq_no++;
+  e.kind = (uint8_t)kind;
+  e.flags = (uint8_t)(flags | ((key && key->trunc) ? RV_EVF_KEY_TRUNC : 0));
+  e.tp = tp;
+  e.nm = nm;
+  e.qsum = qsum;
+  e.qcnt = qcnt;
+  e.dir = dir ? 1 : 0;
+  e.mapq = (uint8_t)mapq;
+  e.keylen = (uint8_t)(key ? key->n : 0);
+  e.pad = 0;
+  e.aux0 = aux0;
+  e.aux1 = aux1;
+  e.aux2 = aux2;
+  for (int k = 0; k < 52; ++k) e.key[k] = (key && k < key->n) ? key->c[k] : (char)0;
+  s.event(e);
+}
+
+RV_HD bool key_is_mnp(const Key& k) {  // isBEGIN_ATGC_AMP_ATGCs_END, parseCigar.cpp:480-495
+  if (k.n > 2 && k.c[1] == '&' && is_atgc(k.c[0])) {
+    for (int i = 2; i < k.n; ++i) if (!is_atgc(k.c[i])) return false;
+    return true;
+  }
+  return false;
+}
+
+// the look-ahead scan shared by findOffset (:208-256) and the in-line copies in process_insertion
+// (:1367-1389) / process_deletion (:1576-1595,:1622-1644,:1659-1680).  `n_break_ref` selects the variant
+// that also stops on a reference 'N'.  Returns offset, writes nmoff increment.
+RV_HD int lookahead_offset(const rv_params& P, const ReadView& rd, const RefView& ref, int ref_pos, int read_pos,
+                           int mlen, int n_break_mode, int* tnm) {
+  int offset = 0, vsn = 0;
+  *tnm = 0;
+  for (int vi = 0; vsn <= P.vext && vi < mlen; vi++) {
+    char ch = rd.base(read_pos + vi);
+    if (ch == 'N') break;
+    if ((double)rd.q(read_pos + vi) < P.goodq) break;
+    if (n_break_mode == 1 && has_eq(ref, ref_pos + vi, 'N')) break;  // :1582 (before the has() test)
+    if (ref.has(ref_pos + vi)) {
+      char rc = ref.at(ref_pos + vi);
+      if (n_break_mode == 2 && rc == 'N') break;                     // :1635, :1671
+      if (ch != rc) { offset = vi + 1; (*tnm)++; vsn = 0; }
+      else vsn++;
+    }
+  }
+  return offset;
+}
+
+template <class Sink>
+RV_HDN void process_read(const rv_params& P, const rv_region& R, int region_idx, const rv_read& rdh,
+                         const uint8_t* pool, const RefView& ref, uint32_t read_idx, Sink& sink) {
+  const uint8_t* var = pool + (size_t)rdh.data_off16 * 16;
+  const uint32_t* cig_in = (const uint32_t*)var;
+  ReadView rd;
+  rd.seq4 = var + 4 * (size_t)rdh.n_cigar;
+  rd.lseq = rdh.l_seq;
+  rd.qual = rd.seq4 + ((rdh.l_seq + 1) >> 1);
+
+  // ---- RecordPreprocessor::next_record filters, recordPreprocessor.cpp:121-146 -------------------
+  if ((rdh.flag & P.samfilter) != 0) return;
+  if ((int)rdh.mapq < P.mapping_quality) return;
+  if (rdh.l_seq == 1) return;
+  // ---- parseCigar.cpp:505-534 ---------------------------------------------------------------------
+  int n_cigar = rdh.n_cigar;
+  if (n_cigar <= 0) return;
+  if (n_cigar > RV_MAX_OPS - 8) { sink.unsupported(); return; }
+  Cigar cg;
+  cg.n = n_cigar;
+  cg.overflow = false;
+  int indel = 0;
+  for (int k = 0; k < n_cigar; ++k) {
+    cg.op[k] = cig_in[k];
+    int o = c_op(cig_in[k]);
+    if (o == OP_I || o == OP_D) indel += c_len(cig_in[k]);
+    if (o == OP_P || o == OP_B) { sink.unsupported(); return; }  // Appendix A-23
+  }
+  int nm = 0;
+  if (rdh.nm >= 0) {
+    nm = (int)rdh.nm - indel;
+    if (nm > P.mismatch) return;
+  } else {
+    if (rdh.flag & 4) return;
+    nm = 0;
+  }
+  const bool dir = (rdh.flag & 16) != 0;
+  const int mapq = rdh.mapq;
+  int position = rdh.pos;
+  // ---- CigarModifier, parseCigar.cpp:547-574 -------------------------------------------------------
+  if (P.local_realign) {
+    bool unsup = false;
+    modify_cigar(cg, position, rd, ref, indel, &unsup);
+    if (unsup) { sink.unsupported(); return; }
+  }
+  cleanup_cigar(cg);
+  n_cigar = cg.n;
+  WalkState w;
+  w.start = position;
+  w.offset = 0;
+  w.rp = 0;
+  w.re = 0;
+  w.seq_no = 0;
+  // :584-588
+  if (c_op(cg.op[0]) == OP_S && c_len(cg.op[0]) >= 10 && c_op(cg.op[n_cigar - 1]) == OP_S &&
+      c_len(cg.op[n_cigar - 1]) >= 10)
+    return;
+  // :591-601 (only M and I count; '=' / 'X' do not — literal)
+  int rlen = 0, tlen = 0, aligned = 0;
+  for (int k = 0; k < n_cigar; ++k) {
+    int o = c_op(cg.op[k]), l = c_len(cg.op[k]);
+    if (o == OP_M || o == OP_I) rlen += l;
+    if (o == OP_M || o == OP_I || o == OP_S) tlen += l;
+    if (o == OP_M || o == OP_EQ || o == OP_X) aligned += l;
+  }
+  if (P.minmatch != 0 && rlen < P.minmatch) return;
+  sink.max_read_len(tlen);
+  if (rdh.flag & 2048) return;  // :603
+  sink.kept(aligned);
+  const int mate_start = rdh.mpos;
+  const bool paired_same = (rdh.flag & 1) && rdh.mate_same_tid;
+
+  bool need_break = true;
+  for (int ci = 0; ci < n_cigar; ++ci) {
+    // :630-634 / skipOverlappingReads :182-206 — only evaluated before the first op
+    if (need_break) {
+      bool skip = false;
+      if (P.uniq_u && paired_same && !dir && w.start >= mate_start) skip = true;
+      if (!skip && P.uniq_un && (rdh.flag & 1) && paired_same) {
+        // isReadsOverlap :196-206 ; getReferenceLength/getAlignmentEnd of the record (original span)
+        int ref_len = rdh.end_pos - (rdh.pos - 1);
+        bool ov;
+        if (position >= mate_start) ov = w.start >= mate_start && w.start <= mate_start + ref_len - 1;
+        else ov = w.start >= mate_start && mate_start <= rdh.end_pos;
+        if (ov) skip = true;
+      }
+      if (skip) break;
+    }
+    need_break = false;
+    int c_operator = c_op(cg.op[ci]);
+    w.clen = c_len(cg.op[ci]);
+    if ((ci == 0 || ci == n_cigar - 1) && c_operator == OP_I) c_operator = OP_S;
+
+    if (c_operator == OP_N) {  // processNotMatched :1733-1753 — splice bookkeeping refused (A-16)
+      sink.unsupported();
+      w.start += w.clen;
+      w.offset = 0;
+      continue;
+    }
+    if (c_operator == OP_S) {
+      // ---- process_softclip :1112-1301 -----------------------------------------------------------
+      if (ci == 0) {
+        while (w.clen - 1 >= 0 && w.start - 1 > 0 && w.start - 1 <= R.chr_len &&
+               has_eq(ref, w.start - 1, rd.base(w.clen - 1)) && rd.q(w.clen - 1) > 10) {
+          char rc = ref.at(w.start - 1);
+          int al = allele_of(rc);
+          if (al >= 0) sink.adj(w.start - 1, al, +1, dir, w.clen, rd.q(w.clen - 1), mapq, nm);
+          else sink.unsupported();
+          sink.cov(w.start - 1);
+          w.start--;
+          w.clen--;
+        }
+        if (w.clen > 0) {
+          int qsum = 0, nhi = 0, nlo = 0;
+          for (int si = w.clen - 1; si >= 0; si--) {
+            if (rd.base(si) == 'N') break;
+            int bq = rd.q(si);
+            if (bq <= 12) nlo++;
+            if (nlo > 1) break;
+            qsum += bq;
+            nhi++;
+          }
+          if (nhi >= 1 && nhi > nlo && w.start >= R.start && w.start <= R.end)
+            emit_event(sink, w, region_idx, read_idx, RV_EV_SC5, w.start, (const Key*)0, 0, dir, w.clen, qsum, nhi,
+                       mapq, nm, w.clen, nhi, w.clen - 1);
+        }
+        w.clen = c_len(cg.op[ci]);
+      } else if (ci == n_cigar - 1) {
+        while (w.rp < rdh.l_seq && has_eq(ref, w.start, rd.base(w.rp)) && rd.q(w.rp) > 10) {
+          char rc = ref.at(w.start);
+          int al = allele_of(rc);
+          if (al >= 0) sink.adj(w.start, al, +1, dir, tlen - w.re, rd.q(w.rp), mapq, nm);
+          else sink.unsupported();
+          sink.cov(w.start);
+          w.rp++;
+          w.start++;
+          w.clen--;
+          w.re++;
+        }
+        if (w.rp < rdh.l_seq) {
+          int qsum = 0, nhi = 0, nlo = 0;
+          for (int si = 0; si < w.clen; si++) {
+            if (rd.base(w.rp + si) == 'N') break;
+            int bq = rd.q(w.rp + si);
+            if (bq <= 12) nlo++;
+            if (nlo > 1) break;
+            qsum += bq;
+            nhi++;
+          }
+          if (nhi >= 1 && nhi > nlo && w.start >= R.start && w.start <= R.end)
+            emit_event(sink, w, region_idx, read_idx, RV_EV_SC3, w.start, (const Key*)0, 0, dir, w.clen, qsum, nhi,
+                       mapq, nm, w.clen, nhi, w.rp);
+        }
+      }
+      w.rp += w.clen;
+      w.offset = 0;
+      w.start = position;
+      continue;
+    }
+    if (c_operator == OP_H) { w.offset = 0; continue; }
+
+    if (c_operator == OP_I) {
+      // ---- process_insertion :1303-1523 ----------------------------------------------------------
+      w.offset = 0;
+      if ((n_cigar > ci + 1 && c_op(cg.op[ci + 1]) == OP_N) || (ci > 0 && c_op(cg.op[ci - 1]) == OP_N)) {
+        w.rp += w.clen;
+        continue;
+      }
+      Key key;
+      key.clear();
+      for (int k = 0; k < w.clen; ++k) key.push(rd.base(w.rp + k));
+      int qsum = 0, qcnt = 0;
+      for (int k = w.rp; k < w.rp + w.clen; ++k) qsum += rd.q(k);
+      qcnt += w.clen;
+      Key ss;
+      ss.clear();
+      int multoffs = 0, multoffp = 0, nmoff = 0;
+      // isInsertionOrDeletionWithNextMatched :1816-1824 (reads cigar[ci+3] with only ci+2 guaranteed: A-6)
+      bool combo = P.local_realign && n_cigar > ci + 2 && c_len(cg.op[ci + 1]) <= P.vext &&
+                   c_op(cg.op[ci + 1]) == OP_M && is_id(c_op(cg.op[ci + 2]));
+      if (combo) {
+        if (ci + 3 >= n_cigar) { sink.unsupported(); return; }
+        combo = !is_id(c_op(cg.op[ci + 3]));
+      }
+      if (combo) {
+        int mLen = c_len(cg.op[ci + 1]), indelLen = c_len(cg.op[ci + 2]);
+        int begin = w.rp + w.clen;
+        bool next_ins = c_op(cg.op[ci + 2]) == OP_I;
+        // appendSegments(..., isInsertion = true) :1756-1815
+        key.push('#');
+        for (int k = 0; k < mLen; ++k) { key.push(rd.base(begin + k)); qsum += rd.q(begin + k); }
+        key.push('^');
+        if (next_ins) {
+          for (int k = 0; k < indelLen; ++k) { key.push(rd.base(begin + mLen + k)); qsum += rd.q(begin + mLen + k); }
+          qcnt += indelLen;
+        } else {
+          key.push_int(indelLen);
+          qsum += rd.q(begin + mLen);
+          qcnt += 1;
+        }
+        multoffs += mLen + (next_ins ? 0 : indelLen);
+        multoffp += mLen + (next_ins ? indelLen : 0);
+        int ci6 = n_cigar > ci + 3 ? c_len(cg.op[ci + 3]) : 0;
+        if (ci6 != 0 && c_op(cg.op[ci + 3]) == OP_M) {
+          // findOffset :208-256 (coverage of the offset bases is incremented without a region test)
+          int tnm;
+          int rpos = w.start + multoffs, qpos = w.rp + w.clen + multoffp;
+          int off = lookahead_offset(P, rd, ref, rpos, qpos, ci6, 0, &tnm);
+          if (off > 0) {
+            for (int k = 0; k < off; ++k) { ss.push(rd.base(qpos + k)); qsum += rd.q(qpos + k); sink.cov(rpos + k); }
+          }
+          w.offset = off;
+          qcnt += off;
+          // note: findOffset's mismatch count is NOT added to nmoff on this path (:1348-1355)
+        }
+        ci += 2;
+      } else if (P.local_realign && n_cigar > ci + 1 && c_op(cg.op[ci + 1]) == OP_M) {  // isNextMatched :1837
+        int tnm;
+        int qpos = w.rp + w.clen;
+        int off = lookahead_offset(P, rd, ref, w.start, qpos, c_len(cg.op[ci + 1]), 0, &tnm);
+        w.offset = off;
+        nmoff += tnm;
+        if (off != 0) {
+          for (int k = 0; k < off; ++k) { ss.push(rd.base(qpos + k)); qsum += rd.q(qpos + k); sink.cov(w.start + k); }
+          qcnt += off;
+        }
+      }
+      if (w.offset > 0) {
+        key.push('&');
+        for (int k = 0; k < ss.n; ++k) key.push(ss.c[k]);
+      }
+      if (w.start - 1 >= R.start && w.start - 1 <= R.end && !key.contains('N')) {
+        int inspos = w.start - 1;
+        bool all_atgc = key.n > 0;
+        for (int k = 0; k < key.n; ++k) all_atgc = all_atgc && is_atgc(key.c[k]);
+        if (all_atgc) {
+          // adjInsPos, include/VariationUtils.h:99-113
+          int n = 1, len = key.n, bi = w.start - 1;
+          while (ref.at(bi) == key.c[len - n]) {
+            n++;
+            if (n > len) n = 1;
+            bi--;
+          }
+          if (w.rp - 1 - (w.start - 1 - bi) > 0) {
+            inspos = bi;
+            if (n > 1) {  // rotate: last n-1 chars first
+              Key t;
+              t.clear();
+              for (int k = len - (n - 1); k < len; ++k) t.push(key.c[k]);
+              for (int k = 0; k < len - (n - 1); ++k) t.push(key.c[k]);
+              key = t;
+            }
+          }
+        }
+        key.prepend("+", 1);
+        int tp = w.re < rlen - w.re ? w.re + 1 : rlen - w.re;
+        emit_event(sink, w, region_idx, read_idx, RV_EV_IN, inspos, &key, RV_EVF_PINS, dir, tp, qsum, qcnt, mapq,
+                   nm - nmoff, 0, 0, 0);
+        // :1471-1490 — take the anchor base's observation back from the reference allele
+        int index = w.rp - 1 - (w.start - 1 - inspos);
+        if (inspos > position && has_eq(ref, inspos, rd.base(index))) {
+          int al = allele_of(rd.base(index));
+          if (al >= 0) sink.adj(inspos, al, -1, dir, tp, rd.q(index), mapq, nm - nmoff);
+          else sink.unsupported();
+        }
+        // :1497-1515 — insertion right behind a leading S/H: one extra reference observation
+        if (ci == 1 && (c_op(cg.op[0]) == OP_S || c_op(cg.op[0]) == OP_H)) {
+          Key rk;
+          rk.clear();
+          rk.push(ref.at(inspos));
+          emit_event(sink, w, region_idx, read_idx, RV_EV_TTREF, inspos, &rk, 0, dir, tp, qsum, qcnt, mapq,
+                     nm - nmoff, 0, 0, 0);
+          sink.cov(inspos);
+        }
+      }
+      w.rp += w.clen + w.offset + multoffp;
+      w.re += w.clen + w.offset + multoffp;
+      w.start += w.offset + multoffs;
+      continue;
+    }
+
+    if (c_operator == OP_D) {
+      // ---- process_deletion :1525-1727 -----------------------------------------------------------
+      w.offset = 0;
+      if (ci + 1 >= n_cigar) { sink.unsupported(); return; }  // reads cigar[ci+1] unconditionally (A-6)
+      if (c_op(cg.op[ci + 1]) == OP_N || (ci > 1 && c_op(cg.op[ci - 1]) == OP_N)) {
+        w.rp += w.clen;
+        continue;
+      }
+      Key key;
+      key.clear();
+      key.push('-');
+      key.push_int(w.clen);
+      Key app;
+      app.clear();
+      int q_before = rd.q(w.rp - 1);
+      int qsum = 0, qcnt = 0;
+      int multoffs = 0, multoffp = 0, nmoff = 0;
+      bool combo = P.local_realign && n_cigar > ci + 2 && c_len(cg.op[ci + 1]) <= P.vext &&
+                   c_op(cg.op[ci + 1]) == OP_M && is_id(c_op(cg.op[ci + 2]));
+      if (combo) {
+        if (ci + 3 >= n_cigar) { sink.unsupported(); return; }
+        combo = !is_id(c_op(cg.op[ci + 3]));
+      }
+      if (combo) {
+        int mLen = c_len(cg.op[ci + 1]), indelLen = c_len(cg.op[ci + 2]);
+        int begin = w.rp;
+        bool next_ins = c_op(cg.op[ci + 2]) == OP_I;
+        // appendSegments(..., isInsertion = false)
+        key.push('#');
+        for (int k = 0; k < mLen; ++k) { key.push(rd.base(begin + k)); qsum += rd.q(begin + k); }
+        key.push('^');
+        if (next_ins) {
+          for (int k = 0; k < indelLen; ++k) { key.push(rd.base(begin + mLen + k)); qsum += rd.q(begin + mLen + k); }
+          qcnt += indelLen;
+        } else {
+          key.push_int(indelLen);
+        }
+        multoffs += mLen + (next_ins ? 0 : indelLen);
+        multoffp += mLen + (next_ins ? indelLen : 0);
+        // isNextAfterNumMatched(ci, 3): n_cigar > ci+3 && op[ci+1] == M  (:1084-1087 tests ci+1, literal)
+        if (n_cigar > ci + 3 && c_op(cg.op[ci + 1]) == OP_M) {
+          int tn = w.rp + multoffp, ts = w.start + multoffs + w.clen;
+          int tnm;
+          int off = lookahead_offset(P, rd, ref, ts, tn, c_len(cg.op[ci + 3]), 1, &tnm);
+          w.offset = off;
+          nmoff += tnm;
+          if (off != 0) {
+            for (int k = 0; k < off; ++k) { app.push(rd.base(tn + k)); qsum += rd.q(tn + k); }
+            qcnt += off;
+          }
+        }
+        ci += 2;
+      } else if (P.local_realign && n_cigar > ci + 1 && c_op(cg.op[ci + 1]) == OP_I) {  // isNextInsertion :163
+        int insLen = c_len(cg.op[ci + 1]);
+        key.push('^');
+        for (int k = 0; k < insLen; ++k) { key.push(rd.base(w.rp + k)); qsum += rd.q(w.rp + k); }
+        qcnt += insLen;
+        multoffp += insLen;
+        if (n_cigar > ci + 2 && c_op(cg.op[ci + 1]) == OP_M) {  // isNextAfterNumMatched(ci, 2): never true here
+          int mLen = c_len(cg.op[ci + 2]);
+          int tn = w.rp + multoffp, ts = w.start + w.clen;
+          int tnm;
+          int off = lookahead_offset(P, rd, ref, ts, tn, mLen, 2, &tnm);
+          w.offset = off;
+          nmoff += tnm;
+          if (off != 0) {
+            for (int k = 0; k < off; ++k) { app.push(rd.base(tn + k)); qsum += rd.q(tn + k); }
+            qcnt += off;
+          }
+        }
+        ci += 1;
+      } else if (P.local_realign && n_cigar > ci + 1 && c_op(cg.op[ci + 1]) == OP_M) {  // isNextMatched
+        int mLen = c_len(cg.op[ci + 1]);
+        int tnm;
+        int off = lookahead_offset(P, rd, ref, w.start + w.clen, w.rp, mLen, 2, &tnm);
+        w.offset = off;
+        nmoff += tnm;
+        if (off != 0) {
+          for (int k = 0; k < off; ++k) { app.push(rd.base(w.rp + k)); qsum += rd.q(w.rp + k); }
+          qcnt += off;
+        }
+      }
+      if (w.offset > 0) {
+        key.push('&');
+        for (int k = 0; k < app.n; ++k) key.push(app.c[k]);
+      }
+      // :1697-1713
+      if (w.rp + w.offset >= rdh.l_seq) {
+        qsum += q_before;
+        qcnt += 1;
+      } else {
+        int q_after = rd.q(w.rp + w.offset);
+        qsum += q_before > q_after ? q_before : q_after;
+        qcnt += 1;
+      }
+      if (w.start >= R.start && w.start <= R.end) {
+        // addVariationForDeletion :1036-1082
+        int tp = w.re < rlen - w.re ? w.re + 1 : rlen - w.re;
+        emit_event(sink, w, region_idx, read_idx, RV_EV_NI, w.start, &key, RV_EVF_PDEL, dir, tp, qsum, qcnt, mapq,
+                   nm - nmoff, 0, 0, 0);
+        for (int k = 0; k < w.clen; ++k) sink.cov(w.start + k);
+      }
+      w.start += w.clen + w.offset + multoffs;
+      w.rp += w.offset + multoffp;
+      w.re += w.offset + multoffp;
+      continue;
+    }
+
+    // ---- match part :675-959 ------------------------------------------------------------------------
+    int nmoff = 0, moffset = 0;
+    for (int i = w.offset; i < w.clen; i++) {
+      bool trim = false;
+      if (P.trim_bases_after != 0) trim = !dir ? (w.rp > P.trim_bases_after) : (tlen - w.rp > P.trim_bases_after);
+      const char ch1 = rd.base(w.rp);
+      if (ch1 == 'N') {
+        w.start++;
+        w.rp++;
+        w.re++;
+        continue;
+      }
+      int q = rd.q(w.rp);  // running SUM of qualities (a double in the reference; integer-valued)
+      int qbases = 1, qibases = 0;
+      Key s;
+      s.clear();
+      s.push(ch1);
+      Key ss;
+      ss.clear();
+      bool start_with_deletion = false;
+      while ((w.start + 1) >= R.start && (w.start + 1) <= R.end && (i + 1) < w.clen && (double)q >= P.goodq &&
+             has_ne(ref, w.start, rd.base(w.rp)) && ref.at(w.start) != 'N') {
+        if ((double)rd.q(w.rp + 1) < P.goodq + 5) break;
+        char nuc = rd.base(w.rp + 1);
+        if (nuc == 'N') break;
+        if (has_eq(ref, w.start + 1, 'N')) break;
+        if (ref.at(w.start + 1) != nuc) {
+          ss.push(nuc);
+          q += rd.q(w.rp + 1);
+          qbases++;
+          w.rp++;
+          w.re++;
+          i++;
+          w.start++;
+          nmoff++;
+        } else {
+          int ssn = 0;
+          for (int ssi = 1; ssi <= P.vext; ssi++) {
+            if (i + 1 + ssi >= w.clen) break;
+            if (w.rp + 1 + ssi < rd.lseq && has_ne(ref, w.start + 1 + ssi, rd.base(w.rp + 1 + ssi))) {
+              ssn = ssi + 1;
+              break;
+            }
+          }
+          if (ssn == 0) break;
+          if ((double)rd.q(w.rp + ssn) < P.goodq + 5) break;
+          for (int ssi = 1; ssi <= ssn; ssi++) {
+            ss.push(rd.base(w.rp + ssi));
+            q += rd.q(w.rp + ssi);
+            qbases++;
+          }
+          w.rp += ssn;
+          w.re += ssn;
+          i += ssn;
+          w.start += ssn;
+        }
+      }
+      if (ss.n > 0) {
+        s.push('&');
+        for (int k = 0; k < ss.n; ++k) s.push(ss.c[k]);
+      }
+      int ddlen = 0;
+      bool near_end = P.local_realign && w.clen - i <= P.vext && ci + 1 < n_cigar && ref.has(w.start) &&
+                      (ss.n > 0 || rd.base(w.rp) != ref.at(w.start)) && (double)rd.q(w.rp) >= P.goodq;
+      if (near_end && c_op(cg.op[ci + 1]) == OP_D) {
+        // :779-846
+        while (i + 1 < w.clen) {
+          s.push(rd.base(w.rp + 1));
+          q += rd.q(w.rp + 1);
+          qbases++;
+          i++;
+          w.rp++;
+          w.re++;
+          w.start++;
+        }
+        s.erase_first('&');
+        Key pre;
+        pre.clear();
+        pre.push('-');
+        pre.push_int(c_len(cg.op[ci + 1]));
+        pre.push('&');
+        s.prepend(pre.c, pre.n);
+        start_with_deletion = true;
+        ddlen = c_len(cg.op[ci + 1]);
+        ci += 1;
+        if (n_cigar > ci + 1 && c_op(cg.op[ci + 1]) == OP_I) {
+          int next_len = c_len(cg.op[ci + 1]);
+          s.push('^');
+          for (int k = 0; k < next_len; ++k) s.push(rd.base(w.rp + 1 + k));
+          for (int qi = 1; qi <= next_len; qi++) {
+            q += rd.q(w.rp + 1 + qi);  // literal: starts one base late (:819-824)
+            qibases++;
+          }
+          w.rp += next_len;
+          w.re += next_len;
+          ci += 1;
+        }
+        // isNextAfterNumMatched(ci, 1) reads the RECORD's cigar (same memory) at ci+1
+        if (n_cigar > ci + 1 && c_op(cg.op[ci + 1]) == OP_M) {
+          int tnm;
+          int rpos = w.start + ddlen + 1, qpos = w.rp + 1;
+          int off = lookahead_offset(P, rd, ref, rpos, qpos, c_len(cg.op[ci + 1]), 0, &tnm);
+          if (off > 0) for (int k = 0; k < off; ++k) sink.cov(rpos + k);
+          if (off != 0) {
+            moffset = off;
+            nmoff += tnm;
+            s.push('&');
+            for (int k = 0; k < off; ++k) s.push(rd.base(qpos + k));
+            // the offset bases' qualities are never added (qualitySequence stays empty, A-7)
+          }
+        }
+      } else if (near_end && c_op(cg.op[ci + 1]) == OP_I) {
+        // :847-882
+        while (i + 1 < w.clen) {
+          s.push(rd.base(w.rp + 1));
+          q += rd.q(w.rp + 1);
+          qbases++;
+          i++;
+          w.rp++;
+          w.re++;
+          w.start++;
+        }
+        s.erase_first('&');
+        int next_len = c_len(cg.op[ci + 1]);
+        for (int k = 0; k < next_len; ++k) s.push(rd.base(w.rp + 1 + k));
+        s.insert_at(next_len, '&');
+        s.prepend("+", 1);
+        for (int qi = 1; qi <= next_len; qi++) {
+          q += rd.q(w.rp + 1 + qi);
+          qibases++;
+        }
+        w.rp += next_len;
+        w.re += next_len;
+        ci += 1;
+        qibases--;
+        qbases++;
+      }
+      if (!trim) {
+        const int pos = w.start - qbases + 1;
+        if (pos >= R.start && pos <= R.end) {
+          int tp = w.re < rlen - w.re ? w.re + 1 : rlen - w.re;
+          if (s.n == 1) {
+            int al = allele_of(ch1);
+            if (al >= 0) sink.single(pos, al, dir, tp, q, mapq, nm - nmoff);
+            else sink.unsupported();
+          } else {
+            int fl = (key_is_mnp(s) ? RV_EVF_MNP : 0) | (start_with_deletion ? RV_EVF_PDEL : 0);
+            emit_event(sink, w, region_idx, read_idx, RV_EV_NI, pos, &s, fl, dir, tp, q, qbases + qibases, mapq,
+                       nm - nmoff, 0, 0, 0);
+          }
+          for (int qi = 1; qi <= qbases; qi++) sink.cov(w.start - qi + 1);
+          if (start_with_deletion)
+            for (int qi = 1; qi < ddlen; qi++) sink.cov(w.start + qi);
+        }
+      }
+      if (start_with_deletion) w.start += ddlen;
+      w.start++;
+      w.rp++;
+      w.re++;
+    }
+    if (moffset != 0) {
+      w.offset = moffset;
+      w.rp += moffset;
+      w.start += moffset;
+      w.re += moffset;
+    }
+    if (w.start > R.end) break;
+  }
+}
+
+}  // namespace rvk

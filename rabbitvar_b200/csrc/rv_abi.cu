@@ -1,0 +1,817 @@
+// rv_abi.cu — CUDA kernels (sm_100a) and the C ABI of rabbitvar_b200 (include/rabbitvar_b200.h).
+//
+// Data layout in HBM (per context):
+//   reads   : rv_read[max_reads] (32 B fixed headers) + byte pool (cigar | 4-bit seq | qual per read)
+//   ref     : 1 B / reference base, flat contig slice
+//   counts  : position-major dense tables, [position][allele A,C,G,T][8 x u32] = 128 B / position
+//   cov     : u32 coverage / position
+//   events  : rv_event[max_events] appended through one global atomic cursor
+//   patch   : rv_patch_entry[] + u32 patch_first[position] (0 = none, else index+1) + group sizes
+//   variants: rv_variant[max_variants] appended through one global atomic cursor
+// Regions of a batch own disjoint slices [tab_off, tab_off + len + 2*halo) of counts/cov.
+#include "../../include/rabbitvar_b200.h"
+#include "kernels/rv_core.cuh"
+#include "kernels/rv_score.cuh"
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+using namespace rvk;
+
+// ------------------------------------------------------------------------------------------------
+// device-side views
+// ------------------------------------------------------------------------------------------------
+struct DevRegion {
+  rv_region r;
+  int64_t tab_off;    // first table position index of this region
+  int32_t first_pos;  // reference position of table index tab_off
+  int32_t n_pos;
+  int64_t item_base;  // first (region, read) work item of this region
+};
+
+struct DevStats {
+  unsigned long long n_items, n_kept, n_bases, n_events, n_overflow, n_unsupported, n_variants, n_score_unsupported;
+};
+
+struct PileupArgs {
+  rv_params P;
+  const DevRegion* regions;
+  int n_regions;
+  int64_t n_items;
+  const rv_read* reads;
+  const uint8_t* pool;
+  const char* ref;
+  int32_t ref_start;
+  int64_t ref_n;
+  uint32_t* counts;
+  uint32_t* cov;
+  rv_event* events;
+  unsigned long long max_events;
+  int32_t* max_rl;
+  DevStats* stats;
+};
+
+struct DeviceSink {
+  const PileupArgs* a;
+  const DevRegion* dr;
+  uint32_t* counts;  // region slice
+  uint32_t* covtab;
+  double goodq;
+  int kept_bases, n_kept, n_unsup, n_over, n_ev;
+  __device__ __forceinline__ bool idx_of(int pos, int* idx) {
+    int i = pos - dr->first_pos;
+    if (i < 0 || i >= dr->n_pos) { n_over++; return false; }
+    *idx = i;
+    return true;
+  }
+  __device__ __forceinline__ void single(int pos, int allele, bool dir, int tp, int q, int mapq, int nm) {
+    int i;
+    if (!idx_of(pos, &i)) return;
+    uint32_t* row = counts + ((size_t)i * 4 + allele) * RV_ROW_U32;
+    atomicAdd(row + (dir ? RV_F_REV : RV_F_FWD), 1u);
+    atomicAdd(row + RV_F_SUM_TP, (uint32_t)tp);
+    atomicAdd(row + RV_F_SUM_Q, (uint32_t)q);
+    atomicAdd(row + RV_F_SUM_MAPQ, (uint32_t)mapq);
+    if (nm) atomicAdd(row + RV_F_SUM_NM, (uint32_t)nm);
+    if ((double)q >= goodq) atomicAdd(row + RV_F_HI, 1u);
+    // pstd/qstd: "two observations differ" == "some observation differs from the first one recorded"
+    uint32_t mine = ((uint32_t)tp & 0xffffu) | (((uint32_t)q & 0xffu) << 16) | (1u << 31);
+    uint32_t old = atomicCAS(row + RV_F_STD, 0u, mine);
+    if (old != 0u) {
+      uint32_t bits = 0;
+      if ((old & 0xffffu) != ((uint32_t)tp & 0xffffu)) bits |= 1u << 24;
+      if (((old >> 16) & 0xffu) != ((uint32_t)q & 0xffu)) bits |= 1u << 25;
+      if (bits & ~old) atomicOr(row + RV_F_STD, bits);
+    }
+  }
+  __device__ __forceinline__ void adj(int pos, int allele, int sign, bool dir, int tp, int q, int mapq, int nm) {
+    int i;
+    if (!idx_of(pos, &i)) return;
+    uint32_t* row = counts + ((size_t)i * 4 + allele) * RV_ROW_U32;
+    atomicAdd(row + (dir ? RV_F_REV : RV_F_FWD), (uint32_t)sign);
+    atomicAdd(row + RV_F_SUM_TP, (uint32_t)(sign * tp));
+    atomicAdd(row + RV_F_SUM_Q, (uint32_t)(sign * q));
+    atomicAdd(row + RV_F_SUM_MAPQ, (uint32_t)(sign * mapq));
+    if (nm) atomicAdd(row + RV_F_SUM_NM, (uint32_t)(sign * nm));
+    if ((double)q >= goodq) atomicAdd(row + RV_F_HI, (uint32_t)sign);
+    atomicOr(row + RV_F_STD, 1u << 30);  // key exists even if it nets to zero
+  }
+  __device__ __forceinline__ void cov(int pos) {
+    int i;
+    if (!idx_of(pos, &i)) return;
+    atomicAdd(covtab + i, 1u);
+  }
+  __device__ __forceinline__ void event(const rv_event& e) {
+    unsigned long long slot = atomicAdd(&a->stats->n_events, 1ull);
+    if (slot >= a->max_events) { n_over++; return; }
+    a->events[slot] = e;
+    n_ev++;
+  }
+  __device__ __forceinline__ void max_read_len(int tlen) { atomicMax(a->max_rl + (dr - a->regions), tlen); }
+  __device__ __forceinline__ void kept(int aligned) { kept_bases += aligned; n_kept++; }
+  __device__ __forceinline__ void unsupported() { n_unsup++; }
+};
+
+__device__ __forceinline__ int find_region(const DevRegion* regs, int n, int64_t item) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (regs[mid].item_base <= item) lo = mid;
+    else hi = mid - 1;
+  }
+  return lo;
+}
+
+// One (region, read) pair per thread: read filters, CIGAR rewrite, CIGAR walk, accumulation.
+__global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
+  int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long kept = 0, bases = 0, unsup = 0, over = 0;
+  if (item < a.n_items) {
+    int ri = find_region(a.regions, a.n_regions, item);
+    const DevRegion* dr = a.regions + ri;
+    int64_t read_idx = dr->r.read_lo + (item - dr->item_base);
+    const rv_read rd = a.reads[read_idx];
+    // htslib iterator overlap test (sam_itr_next): pos0 < end && endpos > beg0
+    if (rd.pos - 1 < dr->r.end && rd.end_pos > dr->r.start - 1) {
+      RefView ref;
+      ref.bases = a.ref;
+      ref.base_pos = a.ref_start;
+      ref.n = a.ref_n;
+      ref.lo = dr->r.ref_lo;
+      ref.hi = dr->r.ref_hi;
+      DeviceSink s;
+      s.a = &a;
+      s.dr = dr;
+      s.counts = a.counts + (size_t)dr->tab_off * RV_POS_U32;
+      s.covtab = a.cov + dr->tab_off;
+      s.goodq = a.P.goodq;
+      s.kept_bases = s.n_kept = s.n_unsup = s.n_over = s.n_ev = 0;
+      process_read(a.P, dr->r, ri, rd, a.pool, ref, (uint32_t)read_idx, s);
+      kept = s.n_kept;
+      bases = s.kept_bases;
+      unsup = s.n_unsup;
+      over = s.n_over;
+    }
+  }
+  // block-level reduction of the statistics, one atomic per block and counter
+  __shared__ unsigned long long sh[4];
+  if (threadIdx.x < 4) sh[threadIdx.x] = 0;
+  __syncthreads();
+  for (int off = 16; off > 0; off >>= 1) {
+    kept += __shfl_down_sync(0xffffffffu, kept, off);
+    bases += __shfl_down_sync(0xffffffffu, bases, off);
+    unsup += __shfl_down_sync(0xffffffffu, unsup, off);
+    over += __shfl_down_sync(0xffffffffu, over, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (kept) atomicAdd(&sh[0], kept);
+    if (bases) atomicAdd(&sh[1], bases);
+    if (unsup) atomicAdd(&sh[2], unsup);
+    if (over) atomicAdd(&sh[3], over);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (sh[0]) atomicAdd(&a.stats->n_kept, sh[0]);
+    if (sh[1]) atomicAdd(&a.stats->n_bases, sh[1]);
+    if (sh[2]) atomicAdd(&a.stats->n_unsupported, sh[2]);
+    if (sh[3]) atomicAdd(&a.stats->n_overflow, sh[3]);
+  }
+}
+
+struct ScoreArgs {
+  rv_params P;
+  const DevRegion* regions;
+  int n_regions;
+  int64_t n_positions;  // total table positions
+  const char* ref;
+  int32_t ref_start;
+  int64_t ref_n;
+  const uint32_t* counts;
+  const uint32_t* cov;
+  const rv_patch_entry* patch;
+  const uint32_t* patch_first;
+  const uint8_t* patch_count;
+  rv_variant* variants;
+  unsigned long long max_variants;
+  const double* lgt;
+  int lgt_n;
+  DevStats* stats;
+};
+
+struct DeviceEmit {
+  const ScoreArgs* a;
+  __device__ __forceinline__ void emit(const rv_variant& v) {
+    unsigned long long slot = atomicAdd(&a->stats->n_variants, 1ull);
+    if (slot < a->max_variants) a->variants[slot] = v;
+  }
+};
+
+__device__ __forceinline__ int find_region_by_tab(const DevRegion* regs, int n, int64_t t) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (regs[mid].tab_off <= t) lo = mid;
+    else hi = mid - 1;
+  }
+  return lo;
+}
+
+// One table position per thread (ToVarsBuilder::process): gathers the position's keys, scores them,
+// applies the frequency cut and appends the survivors.  Only positions inside the region are scored
+// (simpleMode.cpp:155-159 drops the rest at output time).
+__global__ void __launch_bounds__(128) rv_score_kernel(ScoreArgs a) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.n_positions) return;
+  int ri = find_region_by_tab(a.regions, a.n_regions, t);
+  const DevRegion* dr = a.regions + ri;
+  int i = (int)(t - dr->tab_off);
+  int pos = dr->first_pos + i;
+  if (pos < dr->r.start || pos > dr->r.end) return;
+  const uint32_t* rows = a.counts + (size_t)t * RV_POS_U32;
+  uint32_t pf = a.patch_first ? a.patch_first[t] : 0u;
+  int pn = pf ? (int)a.patch_count[t] : 0;
+  // cheap early-out: nothing recorded here at all
+  bool any = pf != 0;
+  if (!any) {
+    const uint4* r4 = (const uint4*)rows;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      uint4 v = r4[k];
+      any = any || (v.x | v.y | v.z | v.w);
+    }
+  }
+  if (!any) return;
+  RefView ref;
+  ref.bases = a.ref;
+  ref.base_pos = a.ref_start;
+  ref.n = a.ref_n;
+  ref.lo = dr->r.ref_lo;
+  ref.hi = dr->r.ref_hi;
+  bool has_next = i + 1 < dr->n_pos;
+  LgTable L;
+  L.t = a.lgt;
+  L.n = a.lgt_n;
+  DeviceEmit em;
+  em.a = &a;
+  int unsup = 0;
+  score_position(a.P, dr->r, ri, pos, ref, rows, a.cov[t], has_next, rows + RV_POS_U32, has_next ? a.cov[t + 1] : 0u,
+                 a.patch, pf ? (int)(pf - 1) : 0, pn, L, em, &unsup);
+  if (unsup) atomicAdd(&a.stats->n_score_unsupported, (unsigned long long)unsup);
+}
+
+__global__ void rv_lgamma_table_kernel(double* t, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) t[i] = lgamma((double)i + 1.0);
+}
+
+__global__ void rv_fisher_kernel(const int32_t* tables, int64_t n, double* out, const double* lgt, int lgt_n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  LgTable L;
+  L.t = lgt;
+  L.n = lgt_n;
+  double l, r, two;
+  fisher_exact(L, tables[4 * i], tables[4 * i + 1], tables[4 * i + 2], tables[4 * i + 3], &l, &r, &two);
+  out[3 * i] = l;
+  out[3 * i + 1] = r;
+  out[3 * i + 2] = two;
+}
+
+// scatter of patch groups / coverage overrides / dense-row overrides
+__global__ void rv_patch_scatter_kernel(const int64_t* grp_tab, const uint32_t* grp_first, const uint8_t* grp_n, int64_t n,
+                                        uint32_t* patch_first, uint8_t* patch_count) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  patch_first[grp_tab[i]] = grp_first[i] + 1u;
+  patch_count[grp_tab[i]] = grp_n[i];
+}
+__global__ void rv_cov_scatter_kernel(const int64_t* tab, const int32_t* val, int64_t n, uint32_t* cov) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cov[tab[i]] = (uint32_t)val[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side of the ABI
+// ------------------------------------------------------------------------------------------------
+struct rv_ctx {
+  int device;
+  rv_params P;
+  rv_limits L;
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+  std::string err;
+  int64_t launches;
+  // device buffers
+  rv_read* d_reads;
+  uint8_t* d_pool;
+  char* d_ref;
+  int32_t ref_start;
+  int64_t ref_n;
+  uint32_t* d_counts;
+  uint32_t* d_cov;
+  rv_event* d_events;
+  rv_variant* d_variants;
+  rv_patch_entry* d_patch;
+  uint32_t* d_patch_first;
+  uint8_t* d_patch_count;
+  DevRegion* d_regions;
+  int32_t* d_max_rl;
+  DevStats* d_stats;
+  double* d_lgt;
+  int lgt_n;
+  // batch state
+  const rv_read* reads_dev_view;  // d_reads or a caller-provided device pointer
+  const uint8_t* pool_dev_view;
+  int64_t n_reads;
+  std::vector<DevRegion> regions;
+  int64_t n_positions, n_items;
+  bool have_patch;
+  // host mirrors (pinned)
+  uint32_t* h_counts;
+  uint32_t* h_cov;
+  size_t h_tab_cap;
+  bool tables_fetched;
+  rv_event* h_events;
+  size_t h_events_cap;
+  rv_variant* h_variants;
+  size_t h_variants_cap;
+  int32_t* h_max_rl;
+  DevStats h_stats;
+  float pileup_ms, score_ms;
+};
+
+static int fail(rv_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(ctx, RV_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
+  } while (0)
+
+extern "C" {
+
+int rv_abi_version(void) { return RV_ABI_VERSION; }
+
+int rv_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+void rv_default_params(rv_params* p) {
+  memset(p, 0, sizeof(*p));
+  p->goodq = 22.5;
+  p->freq = 0.01;
+  p->lofreq = 0.05;
+  p->qratio = 1.5;
+  p->mapq = 0;
+  p->bias = 0.05;
+  p->vext = 2;
+  p->mismatch = 8;
+  p->minr = 2;
+  p->min_bias_reads = 2;
+  p->read_pos_filter = 5;
+  p->minmatch = 0;
+  p->trim_bases_after = 0;
+  p->indelsize = 50;
+  p->mapping_quality = 0;
+  p->samfilter = 0x504;
+  p->local_realign = 1;
+}
+
+void rv_default_limits(rv_limits* l) {
+  memset(l, 0, sizeof(*l));
+  l->max_reads = 1 << 20;
+  l->max_read_bytes = (int64_t)(1 << 20) * 256;
+  l->max_positions = 4 << 20;
+  l->max_regions = 8192;
+  l->halo = 512;
+  l->max_events = 1 << 20;
+  l->max_variants = 1 << 20;
+  l->max_patch = 1 << 20;
+  l->max_ref_bases = 64 << 20;
+}
+
+const char* rv_last_error(const rv_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits* limits) {
+  if (!out || !params || !limits) return RV_ERR_ARG;
+  *out = NULL;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return RV_ERR_CUDA;
+  rv_ctx* ctx = new rv_ctx();
+  memset((void*)&ctx->h_stats, 0, sizeof(ctx->h_stats));
+  ctx->device = device;
+  ctx->P = *params;
+  ctx->L = *limits;
+  ctx->launches = 0;
+  ctx->d_reads = NULL; ctx->d_pool = NULL; ctx->d_ref = NULL; ctx->d_counts = NULL; ctx->d_cov = NULL;
+  ctx->d_events = NULL; ctx->d_variants = NULL; ctx->d_patch = NULL; ctx->d_patch_first = NULL;
+  ctx->d_patch_count = NULL; ctx->d_regions = NULL; ctx->d_max_rl = NULL; ctx->d_stats = NULL; ctx->d_lgt = NULL;
+  ctx->h_counts = NULL; ctx->h_cov = NULL; ctx->h_tab_cap = 0; ctx->h_events = NULL; ctx->h_events_cap = 0;
+  ctx->h_variants = NULL; ctx->h_variants_cap = 0; ctx->h_max_rl = NULL;
+  ctx->n_reads = 0; ctx->n_positions = 0; ctx->n_items = 0; ctx->have_patch = false; ctx->tables_fetched = false;
+  ctx->ref_start = 1; ctx->ref_n = 0; ctx->pileup_ms = ctx->score_ms = 0;
+  ctx->reads_dev_view = NULL; ctx->pool_dev_view = NULL;
+  *out = ctx;  // returned even on failure so the caller can read rv_last_error, then rv_destroy
+  CK(cudaSetDevice(device));
+  CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&ctx->ev0));
+  CK(cudaEventCreate(&ctx->ev1));
+  const rv_limits& L = ctx->L;
+  CK(cudaMalloc(&ctx->d_reads, sizeof(rv_read) * (size_t)L.max_reads));
+  CK(cudaMalloc(&ctx->d_pool, (size_t)L.max_read_bytes));
+  CK(cudaMalloc(&ctx->d_ref, (size_t)L.max_ref_bases));
+  CK(cudaMalloc(&ctx->d_counts, sizeof(uint32_t) * RV_POS_U32 * (size_t)(L.max_positions + 1)));
+  CK(cudaMalloc(&ctx->d_cov, sizeof(uint32_t) * (size_t)(L.max_positions + 1)));
+  CK(cudaMalloc(&ctx->d_events, sizeof(rv_event) * (size_t)L.max_events));
+  CK(cudaMalloc(&ctx->d_variants, sizeof(rv_variant) * (size_t)L.max_variants));
+  CK(cudaMalloc(&ctx->d_patch, sizeof(rv_patch_entry) * (size_t)L.max_patch));
+  CK(cudaMalloc(&ctx->d_patch_first, sizeof(uint32_t) * (size_t)(L.max_positions + 1)));
+  CK(cudaMalloc(&ctx->d_patch_count, (size_t)(L.max_positions + 1)));
+  CK(cudaMalloc(&ctx->d_regions, sizeof(DevRegion) * (size_t)L.max_regions));
+  CK(cudaMalloc(&ctx->d_max_rl, sizeof(int32_t) * (size_t)L.max_regions));
+  CK(cudaMalloc(&ctx->d_stats, sizeof(DevStats)));
+  CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->stream));
+  ctx->lgt_n = 1 << 20;
+  CK(cudaMalloc(&ctx->d_lgt, sizeof(double) * (size_t)ctx->lgt_n));
+  rv_lgamma_table_kernel<<<(ctx->lgt_n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_lgt, ctx->lgt_n);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMallocHost(&ctx->h_max_rl, sizeof(int32_t) * (size_t)L.max_regions));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RV_OK;
+}
+
+void rv_destroy(rv_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaFree(ctx->d_reads); cudaFree(ctx->d_pool); cudaFree(ctx->d_ref); cudaFree(ctx->d_counts); cudaFree(ctx->d_cov);
+  cudaFree(ctx->d_events); cudaFree(ctx->d_variants); cudaFree(ctx->d_patch); cudaFree(ctx->d_patch_first);
+  cudaFree(ctx->d_patch_count); cudaFree(ctx->d_regions); cudaFree(ctx->d_max_rl); cudaFree(ctx->d_stats);
+  cudaFree(ctx->d_lgt);
+  if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+  if (ctx->h_cov) cudaFreeHost(ctx->h_cov);
+  if (ctx->h_events) cudaFreeHost(ctx->h_events);
+  if (ctx->h_variants) cudaFreeHost(ctx->h_variants);
+  if (ctx->h_max_rl) cudaFreeHost(ctx->h_max_rl);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  delete ctx;
+}
+
+int rv_sync(rv_ctx* ctx) {
+  if (!ctx) return RV_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RV_OK;
+}
+
+int rv_set_reference(rv_ctx* ctx, int32_t ref_start, int64_t n, const char* bases) {
+  if (!ctx || !bases || n < 0) return RV_ERR_ARG;
+  if (n > ctx->L.max_ref_bases) return fail(ctx, RV_ERR_OVERFLOW, "reference larger than limits.max_ref_bases");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->d_ref, bases, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->ref_start = ref_start;
+  ctx->ref_n = n;
+  return RV_OK;
+}
+
+int rv_push_reads(rv_ctx* ctx, const rv_read_batch* b) {
+  if (!ctx || !b || b->n_reads < 0) return RV_ERR_ARG;
+  if (b->n_reads > ctx->L.max_reads) return fail(ctx, RV_ERR_OVERFLOW, "batch has more reads than limits.max_reads");
+  if (b->pool_bytes > ctx->L.max_read_bytes) return fail(ctx, RV_ERR_OVERFLOW, "batch pool larger than limits.max_read_bytes");
+  CK(cudaSetDevice(ctx->device));
+  if (b->n_reads) CK(cudaMemcpyAsync(ctx->d_reads, b->reads, sizeof(rv_read) * (size_t)b->n_reads, cudaMemcpyHostToDevice, ctx->stream));
+  if (b->pool_bytes) CK(cudaMemcpyAsync(ctx->d_pool, b->pool, (size_t)b->pool_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->reads_dev_view = ctx->d_reads;
+  ctx->pool_dev_view = ctx->d_pool;
+  ctx->n_reads = b->n_reads;
+  return RV_OK;
+}
+
+int rv_push_reads_device(rv_ctx* ctx, const rv_read_batch* b) {
+  if (!ctx || !b || b->n_reads < 0) return RV_ERR_ARG;
+  ctx->reads_dev_view = b->reads;
+  ctx->pool_dev_view = b->pool;
+  ctx->n_reads = b->n_reads;
+  return RV_OK;
+}
+
+int rv_set_regions(rv_ctx* ctx, const rv_region* regs, int32_t n) {
+  if (!ctx || (!regs && n) || n < 0) return RV_ERR_ARG;
+  if (n > ctx->L.max_regions) return fail(ctx, RV_ERR_OVERFLOW, "more regions than limits.max_regions");
+  CK(cudaSetDevice(ctx->device));
+  ctx->regions.resize(n);
+  int64_t tab = 0, items = 0;
+  for (int i = 0; i < n; ++i) {
+    DevRegion& d = ctx->regions[i];
+    d.r = regs[i];
+    if (d.r.end < d.r.start || d.r.read_hi < d.r.read_lo || d.r.read_hi > ctx->n_reads)
+      return fail(ctx, RV_ERR_ARG, "bad region " + std::to_string(i));
+    d.first_pos = d.r.start - ctx->L.halo;
+    d.n_pos = d.r.end - d.r.start + 1 + 2 * ctx->L.halo;
+    d.tab_off = tab;
+    d.item_base = items;
+    tab += d.n_pos;
+    items += d.r.read_hi - d.r.read_lo;
+    ctx->h_max_rl[i] = d.r.max_read_len_in;
+  }
+  if (tab > ctx->L.max_positions) return fail(ctx, RV_ERR_OVERFLOW, "regions need more table positions than limits.max_positions");
+  ctx->n_positions = tab;
+  ctx->n_items = items;
+  ctx->have_patch = false;
+  ctx->tables_fetched = false;
+  if (n) {
+    CK(cudaMemcpyAsync(ctx->d_regions, ctx->regions.data(), sizeof(DevRegion) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_max_rl, ctx->h_max_rl, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    // the async copies above read host vectors: make sure they are consumed before the caller can mutate them
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return RV_OK;
+}
+
+int rv_pileup(rv_ctx* ctx) {
+  if (!ctx) return RV_ERR_ARG;
+  if (ctx->regions.empty()) return fail(ctx, RV_ERR_STATE, "rv_set_regions has not been called");
+  if (!ctx->reads_dev_view) return fail(ctx, RV_ERR_STATE, "rv_push_reads has not been called");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_counts, 0, sizeof(uint32_t) * RV_POS_U32 * (size_t)(ctx->n_positions + 1), ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_cov, 0, sizeof(uint32_t) * (size_t)(ctx->n_positions + 1), ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->stream));
+  PileupArgs a;
+  a.P = ctx->P;
+  a.regions = ctx->d_regions;
+  a.n_regions = (int)ctx->regions.size();
+  a.n_items = ctx->n_items;
+  a.reads = ctx->reads_dev_view;
+  a.pool = ctx->pool_dev_view;
+  a.ref = ctx->d_ref;
+  a.ref_start = ctx->ref_start;
+  a.ref_n = ctx->ref_n;
+  a.counts = ctx->d_counts;
+  a.cov = ctx->d_cov;
+  a.events = ctx->d_events;
+  a.max_events = (unsigned long long)ctx->L.max_events;
+  a.max_rl = ctx->d_max_rl;
+  a.stats = ctx->d_stats;
+  if (ctx->n_items > 0) {
+    unsigned grid = (unsigned)((ctx->n_items + 127) / 128);
+    rv_pileup_kernel<<<grid, 128, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaMemcpyAsync(&ctx->h_stats, ctx->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_max_rl, ctx->d_max_rl, sizeof(int32_t) * ctx->regions.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaEventElapsedTime(&ctx->pileup_ms, ctx->ev0, ctx->ev1));
+  ctx->h_stats.n_items = (unsigned long long)ctx->n_items;
+  ctx->have_patch = false;
+  ctx->tables_fetched = false;
+  if (ctx->h_stats.n_overflow) return fail(ctx, RV_ERR_OVERFLOW, "pileup dropped observations (halo/event buffer too small)");
+  return RV_OK;
+}
+
+int rv_get_pileup_stats(rv_ctx* ctx, rv_pileup_stats* o) {
+  if (!ctx || !o) return RV_ERR_ARG;
+  o->n_items = (int64_t)ctx->h_stats.n_items;
+  o->n_reads_kept = (int64_t)ctx->h_stats.n_kept;
+  o->n_aligned_bases = (int64_t)ctx->h_stats.n_bases;
+  o->n_events = (int64_t)ctx->h_stats.n_events;
+  o->n_overflow = (int64_t)ctx->h_stats.n_overflow;
+  o->n_unsupported = (int64_t)ctx->h_stats.n_unsupported;
+  return RV_OK;
+}
+
+int rv_fetch_max_read_len(rv_ctx* ctx, const int32_t** out, int32_t* n) {
+  if (!ctx || !out || !n) return RV_ERR_ARG;
+  *out = ctx->h_max_rl;
+  *n = (int32_t)ctx->regions.size();
+  return RV_OK;
+}
+
+int rv_fetch_tables(rv_ctx* ctx, int32_t region, const uint32_t** counts, const uint32_t** cov, int32_t* first_pos,
+                    int32_t* n_pos) {
+  if (!ctx || region < 0 || region >= (int)ctx->regions.size()) return RV_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->tables_fetched) {
+    size_t need = (size_t)ctx->n_positions;
+    if (need > ctx->h_tab_cap) {
+      if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+      if (ctx->h_cov) cudaFreeHost(ctx->h_cov);
+      ctx->h_counts = NULL; ctx->h_cov = NULL;
+      CK(cudaMallocHost(&ctx->h_counts, sizeof(uint32_t) * RV_POS_U32 * need));
+      CK(cudaMallocHost(&ctx->h_cov, sizeof(uint32_t) * need));
+      ctx->h_tab_cap = need;
+    }
+    CK(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, sizeof(uint32_t) * RV_POS_U32 * need, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_cov, ctx->d_cov, sizeof(uint32_t) * need, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->tables_fetched = true;
+  }
+  const DevRegion& d = ctx->regions[region];
+  if (counts) *counts = ctx->h_counts + (size_t)d.tab_off * RV_POS_U32;
+  if (cov) *cov = ctx->h_cov + d.tab_off;
+  if (first_pos) *first_pos = d.first_pos;
+  if (n_pos) *n_pos = d.n_pos;
+  return RV_OK;
+}
+
+int rv_fetch_events(rv_ctx* ctx, const rv_event** events, int64_t* n_events) {
+  if (!ctx || !events || !n_events) return RV_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  size_t n = (size_t)std::min<unsigned long long>(ctx->h_stats.n_events, (unsigned long long)ctx->L.max_events);
+  if (n > ctx->h_events_cap) {
+    if (ctx->h_events) cudaFreeHost(ctx->h_events);
+    ctx->h_events = NULL;
+    CK(cudaMallocHost(&ctx->h_events, sizeof(rv_event) * n));
+    ctx->h_events_cap = n;
+  }
+  if (n) {
+    CK(cudaMemcpyAsync(ctx->h_events, ctx->d_events, sizeof(rv_event) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    // restore BAM order: (region, read, order inside the read)
+    std::sort(ctx->h_events, ctx->h_events + n, [](const rv_event& a, const rv_event& b) {
+      if (a.region != b.region) return a.region < b.region;
+      if (a.read_idx != b.read_idx) return a.read_idx < b.read_idx;
+      return a.seq_no < b.seq_no;
+    });
+  }
+  *events = ctx->h_events;
+  *n_events = (int64_t)n;
+  return RV_OK;
+}
+
+int rv_apply_patch(rv_ctx* ctx, const rv_patch_entry* entries, int64_t n_entries, const int32_t* cov_region,
+                   const int32_t* cov_pos, const int32_t* cov_val, int64_t n_cov) {
+  if (!ctx || n_entries < 0 || n_cov < 0) return RV_ERR_ARG;
+  if (n_entries > ctx->L.max_patch) return fail(ctx, RV_ERR_OVERFLOW, "more patch entries than limits.max_patch");
+  CK(cudaSetDevice(ctx->device));
+  // entries must be grouped by (region, pos); groups are located here and scattered on the device
+  std::vector<int64_t> grp_tab;
+  std::vector<uint32_t> grp_first;
+  std::vector<uint8_t> grp_n;
+  for (int64_t i = 0; i < n_entries;) {
+    int64_t j = i;
+    while (j < n_entries && entries[j].region == entries[i].region && entries[j].pos == entries[i].pos) ++j;
+    int r = entries[i].region;
+    if (r < 0 || r >= (int)ctx->regions.size()) return fail(ctx, RV_ERR_ARG, "patch entry with bad region");
+    const DevRegion& d = ctx->regions[r];
+    int idx = entries[i].pos - d.first_pos;
+    if (idx >= 0 && idx < d.n_pos) {
+      if (j - i > 255) return fail(ctx, RV_ERR_OVERFLOW, "more than 255 keys at one position");
+      grp_tab.push_back(d.tab_off + idx);
+      grp_first.push_back((uint32_t)i);
+      grp_n.push_back((uint8_t)(j - i));
+    }
+    i = j;
+  }
+  CK(cudaMemsetAsync(ctx->d_patch_first, 0, sizeof(uint32_t) * (size_t)(ctx->n_positions + 1), ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_patch_count, 0, (size_t)(ctx->n_positions + 1), ctx->stream));
+  if (n_entries) CK(cudaMemcpyAsync(ctx->d_patch, entries, sizeof(rv_patch_entry) * (size_t)n_entries, cudaMemcpyHostToDevice, ctx->stream));
+  int64_t ng = (int64_t)grp_tab.size();
+  void* scratch = NULL;
+  size_t sbytes = (size_t)ng * (8 + 4 + 1) + (size_t)n_cov * (8 + 4) + 64;
+  CK(cudaMalloc(&scratch, sbytes));
+  uint8_t* sp = (uint8_t*)scratch;
+  int64_t* d_tab = (int64_t*)sp; sp += 8 * (size_t)ng;
+  int64_t* d_ctab = (int64_t*)sp; sp += 8 * (size_t)n_cov;
+  uint32_t* d_first = (uint32_t*)sp; sp += 4 * (size_t)ng;
+  int32_t* d_cval = (int32_t*)sp; sp += 4 * (size_t)n_cov;
+  uint8_t* d_n = sp;
+  std::vector<int64_t> ctab((size_t)n_cov);
+  std::vector<int32_t> cval((size_t)n_cov);
+  int64_t nc = 0;
+  for (int64_t i = 0; i < n_cov; ++i) {
+    int r = cov_region[i];
+    if (r < 0 || r >= (int)ctx->regions.size()) { cudaFree(scratch); return fail(ctx, RV_ERR_ARG, "coverage patch with bad region"); }
+    const DevRegion& d = ctx->regions[r];
+    int idx = cov_pos[i] - d.first_pos;
+    if (idx < 0 || idx >= d.n_pos) continue;
+    ctab[nc] = d.tab_off + idx;
+    cval[nc] = cov_val[i];
+    nc++;
+  }
+  if (ng) {
+    cudaMemcpyAsync(d_tab, grp_tab.data(), 8 * (size_t)ng, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_first, grp_first.data(), 4 * (size_t)ng, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_n, grp_n.data(), (size_t)ng, cudaMemcpyHostToDevice, ctx->stream);
+    rv_patch_scatter_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, ctx->stream>>>(d_tab, d_first, d_n, ng, ctx->d_patch_first, ctx->d_patch_count);
+    ctx->launches++;
+  }
+  if (nc) {
+    cudaMemcpyAsync(d_ctab, ctab.data(), 8 * (size_t)nc, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_cval, cval.data(), 4 * (size_t)nc, cudaMemcpyHostToDevice, ctx->stream);
+    rv_cov_scatter_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, ctx->stream>>>(d_ctab, d_cval, nc, ctx->d_cov);
+    ctx->launches++;
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(scratch);
+  if (e != cudaSuccess) return fail(ctx, RV_ERR_CUDA, std::string("rv_apply_patch: ") + cudaGetErrorString(e));
+  ctx->have_patch = true;
+  ctx->tables_fetched = false;
+  return RV_OK;
+}
+
+int rv_score(rv_ctx* ctx) {
+  if (!ctx) return RV_ERR_ARG;
+  if (ctx->regions.empty()) return fail(ctx, RV_ERR_STATE, "rv_set_regions has not been called");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  CK(cudaMemsetAsync(&ctx->d_stats->n_variants, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  ScoreArgs a;
+  a.P = ctx->P;
+  a.regions = ctx->d_regions;
+  a.n_regions = (int)ctx->regions.size();
+  a.n_positions = ctx->n_positions;
+  a.ref = ctx->d_ref;
+  a.ref_start = ctx->ref_start;
+  a.ref_n = ctx->ref_n;
+  a.counts = ctx->d_counts;
+  a.cov = ctx->d_cov;
+  a.patch = ctx->d_patch;
+  a.patch_first = ctx->have_patch ? ctx->d_patch_first : NULL;
+  a.patch_count = ctx->d_patch_count;
+  a.variants = ctx->d_variants;
+  a.max_variants = (unsigned long long)ctx->L.max_variants;
+  a.lgt = ctx->d_lgt;
+  a.lgt_n = ctx->lgt_n;
+  a.stats = ctx->d_stats;
+  if (ctx->n_positions > 0) {
+    unsigned grid = (unsigned)((ctx->n_positions + 127) / 128);
+    rv_score_kernel<<<grid, 128, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaMemcpyAsync(&ctx->h_stats.n_variants, &ctx->d_stats->n_variants, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaEventElapsedTime(&ctx->score_ms, ctx->ev0, ctx->ev1));
+  if (ctx->h_stats.n_variants > (unsigned long long)ctx->L.max_variants)
+    return fail(ctx, RV_ERR_OVERFLOW, "more variants than limits.max_variants");
+  return RV_OK;
+}
+
+int rv_fetch_variants(rv_ctx* ctx, const rv_variant** variants, int64_t* n_variants) {
+  if (!ctx || !variants || !n_variants) return RV_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  size_t n = (size_t)ctx->h_stats.n_variants;
+  if (n > ctx->h_variants_cap) {
+    if (ctx->h_variants) cudaFreeHost(ctx->h_variants);
+    ctx->h_variants = NULL;
+    CK(cudaMallocHost(&ctx->h_variants, sizeof(rv_variant) * n));
+    ctx->h_variants_cap = n;
+  }
+  if (n) {
+    CK(cudaMemcpyAsync(ctx->h_variants, ctx->d_variants, sizeof(rv_variant) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::sort(ctx->h_variants, ctx->h_variants + n, [](const rv_variant& a, const rv_variant& b) {
+      if (a.region != b.region) return a.region < b.region;
+      if (a.pos != b.pos) return a.pos < b.pos;
+      return a.rank < b.rank;
+    });
+  }
+  *variants = ctx->h_variants;
+  *n_variants = (int64_t)n;
+  return RV_OK;
+}
+
+int rv_fisher_exact(rv_ctx* ctx, const int32_t* tables, int64_t n, double* out) {
+  if (!ctx || (!tables && n) || (!out && n) || n < 0) return RV_ERR_ARG;
+  if (n == 0) return RV_OK;
+  CK(cudaSetDevice(ctx->device));
+  int32_t* d_t = NULL;
+  double* d_o = NULL;
+  CK(cudaMalloc(&d_t, sizeof(int32_t) * 4 * (size_t)n));
+  cudaError_t e = cudaMalloc(&d_o, sizeof(double) * 3 * (size_t)n);
+  if (e != cudaSuccess) { cudaFree(d_t); return fail(ctx, RV_ERR_NOMEM, "rv_fisher_exact: out of device memory"); }
+  cudaMemcpyAsync(d_t, tables, sizeof(int32_t) * 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+  rv_fisher_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d_t, n, d_o, ctx->d_lgt, ctx->lgt_n);
+  ctx->launches++;
+  cudaMemcpyAsync(out, d_o, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+  e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_t);
+  cudaFree(d_o);
+  if (e != cudaSuccess) return fail(ctx, RV_ERR_CUDA, std::string("rv_fisher_exact: ") + cudaGetErrorString(e));
+  return RV_OK;
+}
+
+int rv_last_kernel_ms(rv_ctx* ctx, float* pileup_ms, float* score_ms) {
+  if (!ctx) return RV_ERR_ARG;
+  if (pileup_ms) *pileup_ms = ctx->pileup_ms;
+  if (score_ms) *score_ms = ctx->score_ms;
+  return RV_OK;
+}
+
+int64_t rv_launch_count(const rv_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,360 @@
+// rv_dump — TEST TOOL.  Runs the pileup(+score) path over a BAM/FASTA for a list of regions and writes the
+// same text dump oracle/ref_dump.cpp writes for the reference, so the two can be diffed line by line.
+//
+//   rv_dump --backend gpu|sim --fasta ref.fa --bam S.bam --chr chrS1 (--region S-E | --bed tiles.bed)
+//           [--k 0|1] [--f 0.01] [--u 1] [--three 1] [--fisher 1] [--bam2 1] --out dump.txt [--stages CV]
+//
+// backend gpu : calls the product through its C ABI (librvgpu.so) — this is what `-m gpu` tests use.
+// backend sim : single-steps the SAME __host__ __device__ per-read / per-position functions on the CPU
+//               with a plain-add sink.  It exists only so kernel logic can be debugged in a container
+//               without a GPU; it is not part of the library and nothing in the product links it.
+#include "../../include/rabbitvar_b200.h"
+#include "../../rabbitvar_b200/csrc/kernels/rv_core.cuh"
+#include "../../rabbitvar_b200/csrc/kernels/rv_score.cuh"
+#include "../../rabbitvar_b200/csrc/host/batch_loader.hpp"
+#include "../../rabbitvar_b200/csrc/host/pileup_model.hpp"
+#include "../../rabbitvar_b200/csrc/host/realign.hpp"
+#include "../../rabbitvar_b200/csrc/host/assemble.hpp"
+#include <map>
+#include <set>
+#include <string>
+#include <algorithm>
+
+using namespace rvhost;
+
+struct SimSink {
+  RegionPileup* R;
+  std::vector<rv_event>* events;
+  double goodq;
+  int64_t kept_reads, kept_bases, unsup, over;
+  bool idx(int pos) {
+    if (!R->in_table(pos)) { over++; return false; }
+    return true;
+  }
+  void single(int pos, int allele, bool dir, int tp, int q, int mapq, int nm) {
+    if (!idx(pos)) return;
+    uint32_t* row = R->row(pos, allele);
+    row[dir ? RV_F_REV : RV_F_FWD] += 1;
+    row[RV_F_SUM_TP] += (uint32_t)tp;
+    row[RV_F_SUM_Q] += (uint32_t)q;
+    row[RV_F_SUM_MAPQ] += (uint32_t)mapq;
+    row[RV_F_SUM_NM] += (uint32_t)nm;
+    if ((double)q >= goodq) row[RV_F_HI] += 1;
+    uint32_t mine = ((uint32_t)tp & 0xffffu) | (((uint32_t)q & 0xffu) << 16) | (1u << 31);
+    uint32_t old = row[RV_F_STD];
+    if (old == 0) row[RV_F_STD] = mine;
+    else {
+      if ((old & 0xffffu) != ((uint32_t)tp & 0xffffu)) row[RV_F_STD] |= 1u << 24;
+      if (((old >> 16) & 0xffu) != ((uint32_t)q & 0xffu)) row[RV_F_STD] |= 1u << 25;
+    }
+  }
+  void adj(int pos, int allele, int sign, bool dir, int tp, int q, int mapq, int nm) {
+    if (!idx(pos)) return;
+    uint32_t* row = R->row(pos, allele);
+    row[dir ? RV_F_REV : RV_F_FWD] += (uint32_t)sign;
+    row[RV_F_SUM_TP] += (uint32_t)(sign * tp);
+    row[RV_F_SUM_Q] += (uint32_t)(sign * q);
+    row[RV_F_SUM_MAPQ] += (uint32_t)(sign * mapq);
+    row[RV_F_SUM_NM] += (uint32_t)(sign * nm);
+    if ((double)q >= goodq) row[RV_F_HI] += (uint32_t)sign;
+    row[RV_F_STD] |= 1u << 30;
+  }
+  void cov(int pos) {
+    if (!idx(pos)) return;
+    R->cov[pos - R->first_pos]++;
+  }
+  void event(const rv_event& e) { events->push_back(e); }
+  void max_read_len(int t) { if (t > R->max_read_len) R->max_read_len = t; }
+  void kept(int aligned) { kept_reads++; kept_bases += aligned; }
+  void unsupported() { unsup++; }
+};
+
+struct SimEmit {
+  std::vector<rv_variant>* out;
+  void emit(const rv_variant& v) { out->push_back(v); }
+};
+
+static FILE* OUT = NULL;
+
+static void print_var_fields(const Variation& v) {
+  fprintf(OUT, "%d\t%d\t%d\t%.17g\t%.17g\t%.17g\t%.17g\t%d\t%d\t%d\t%d\t%d", v.cnt, v.fwd, v.rev, v.sum_tp, v.sum_q,
+          v.sum_mapq, v.sum_nm, v.lo, v.hi, v.pstd ? 1 : 0, v.qstd ? 1 : 0, v.extracnt);
+}
+
+static void dump_tables(const char* stage, const RegionPileup& R) {
+  // NI: merge dense + sparse, ordered by (pos, key)
+  std::map<std::pair<int, std::string>, Variation> all;
+  static const char B[5] = "ACGT";
+  for (int i = 0; i < R.n_pos; ++i)
+    for (int a = 0; a < 4; ++a) {
+      const uint32_t* r = R.counts.data() + ((size_t)i * 4 + a) * RV_ROW_U32;
+      if (RegionPileup::row_exists(r)) all[std::make_pair(R.first_pos + i, std::string(1, B[a]))] = RegionPileup::row_to_variation(r);
+    }
+  for (auto& p : R.ni)
+    for (auto& k : p.second) all[std::make_pair(p.first, k.first)] = k.second;  // sparse overrides dense
+  for (auto& e : all) {
+    fprintf(OUT, "%s.NI\t%d\t%s\t", stage, e.first.first, e.first.second.c_str());
+    print_var_fields(e.second);
+    fputc('\n', OUT);
+  }
+  for (auto& p : R.ins)
+    for (auto& k : p.second) {
+      fprintf(OUT, "%s.IN\t%d\t%s\t", stage, p.first, k.first.c_str());
+      print_var_fields(k.second);
+      fputc('\n', OUT);
+    }
+  for (int i = 0; i < R.n_pos; ++i)
+    if (R.cov[i]) fprintf(OUT, "%s.COV\t%d\t%d\n", stage, R.first_pos + i, (int)R.cov[i]);
+  for (int end = 5; end >= 3; end -= 2) {
+    const std::map<int, Sclip>& sc = end == 5 ? R.sc5 : R.sc3;
+    for (auto& p : sc) {
+      fprintf(OUT, "%s.SC%d\t%d\t", stage, end, p.first);
+      print_var_fields(p.second);
+      fprintf(OUT, "\t%d\n", p.second.used ? 1 : 0);
+      for (auto& ie : p.second.nt)
+        for (auto& bc : ie.second) fprintf(OUT, "%s.SCNT\t%d\t%d\t%d\t%c\t%d\n", stage, end, p.first, ie.first, bc.first, bc.second);
+      for (auto& ie : p.second.seq)
+        for (auto& bc : ie.second) {
+          fprintf(OUT, "%s.SCSEQ\t%d\t%d\t%d\t%c\t", stage, end, p.first, ie.first, bc.first);
+          print_var_fields(bc.second);
+          fputc('\n', OUT);
+        }
+    }
+  }
+}
+
+static void dump_counts(const char* tag, const std::map<int, std::map<std::string, int> >& m) {
+  for (auto& p : m)
+    for (auto& k : p.second) fprintf(OUT, "%s\t%d\t%s\t%d\n", tag, p.first, k.first.c_str(), k.second);
+}
+
+int main(int argc, char** argv) {
+  std::map<std::string, std::string> kv;
+  for (int i = 1; i + 1 < argc; i += 2) kv[argv[i]] = argv[i + 1];
+  std::string backend = kv.count("--backend") ? kv["--backend"] : "gpu";
+  std::string stages = kv.count("--stages") ? kv["--stages"] : "C";
+  std::string sample = kv.count("--sample") ? kv["--sample"] : "S";
+  rv_params P;
+  rv_default_params(&P);
+  if (kv.count("--k")) P.local_realign = (uint8_t)atoi(kv["--k"].c_str());
+  if (kv.count("--f")) P.freq = atof(kv["--f"].c_str());
+  if (kv.count("--u")) P.uniq_u = (uint8_t)atoi(kv["--u"].c_str());
+  if (kv.count("--three")) P.move3 = (uint8_t)atoi(kv["--three"].c_str());
+  if (kv.count("--fisher")) P.fisher = (uint8_t)atoi(kv["--fisher"].c_str());
+  if (kv.count("--bam2")) P.has_bam2 = (uint8_t)atoi(kv["--bam2"].c_str());
+  if (kv.count("--p")) { P.pileup = 1; P.freq = -1; P.minr = 0; }
+  OUT = fopen(kv["--out"].c_str(), "wb");
+  if (!OUT) { fprintf(stderr, "rv_dump: cannot open --out\n"); return 2; }
+
+  rvio::BamReader bam;
+  rvio::BaiIndex bai;
+  rvio::Fasta fa;
+  if (!bam.open(kv["--bam"]) || !bai.load(kv["--bam"] + ".bai") || !fa.open(kv["--fasta"])) {
+    fprintf(stderr, "rv_dump: cannot open inputs\n");
+    return 2;
+  }
+  std::string chr = kv["--chr"];
+  int tid = bam.header().tid_of(chr);
+  int32_t chr_len = bam.header().lens[tid];
+  std::vector<RegionSpec> specs;
+  if (kv.count("--region")) {
+    RegionSpec s;
+    s.chr = chr;
+    sscanf(kv["--region"].c_str(), "%d-%d", &s.start, &s.end);
+    specs.push_back(s);
+  } else {
+    FILE* bf = fopen(kv["--bed"].c_str(), "r");
+    char c[256], g[256];
+    int s, e;
+    while (bf && fscanf(bf, "%255s %d %d %255s", c, &s, &e, g) == 4) {
+      RegionSpec r;
+      r.chr = c; r.start = s; r.end = e; r.gene = g;
+      if (r.chr == chr) specs.push_back(r);
+    }
+    if (bf) fclose(bf);
+  }
+  int32_t smin = specs[0].start, smax = specs[0].end;
+  for (auto& s : specs) { smin = std::min(smin, s.start); smax = std::max(smax, s.end); }
+  ReadBatch batch;
+  load_span(bam, bai, tid, smin, smax, &batch);
+  std::vector<rv_region> regs;
+  make_regions(batch, specs, chr_len, 1200, 0, &regs);
+  // reference slice covering every window
+  int32_t ref_lo = std::max(1, smin - 1300), ref_hi = std::min(chr_len, smax + 1300);
+  std::string refseq;
+  fa.fetch(chr, ref_lo, ref_hi, &refseq);
+  for (auto& ch : refseq) ch = (char)toupper(ch);
+
+  const int halo = 512;
+  std::vector<RegionPileup> rp(regs.size());
+  std::vector<rv_event> events;
+  std::vector<rv_variant> variants;
+  rv_pileup_stats st;
+  memset(&st, 0, sizeof st);
+  rv_ctx* ctx = NULL;
+
+  if (backend == "sim") {
+    rvk::RefView ref;
+    ref.bases = refseq.data();
+    ref.base_pos = ref_lo;
+    ref.n = (int64_t)refseq.size();
+    for (size_t r = 0; r < regs.size(); ++r) {
+      RegionPileup& R = rp[r];
+      R.region_idx = (int)r;
+      R.start = regs[r].start; R.end = regs[r].end;
+      R.first_pos = regs[r].start - halo;
+      R.n_pos = regs[r].end - regs[r].start + 1 + 2 * halo;
+      R.counts.assign((size_t)R.n_pos * RV_POS_U32, 0);
+      R.cov.assign((size_t)R.n_pos, 0);
+      R.max_read_len = regs[r].max_read_len_in;
+      ref.lo = regs[r].ref_lo;
+      ref.hi = regs[r].ref_hi;
+      SimSink s;
+      s.R = &R; s.events = &events; s.goodq = P.goodq;
+      s.kept_reads = s.kept_bases = s.unsup = s.over = 0;
+      for (int64_t i = regs[r].read_lo; i < regs[r].read_hi; ++i) {
+        const rv_read& rd = batch.reads[(size_t)i];
+        if (!(rd.pos - 1 < regs[r].end && rd.end_pos > regs[r].start - 1)) continue;
+        st.n_items++;
+        rvk::process_read(P, regs[r], (int)r, rd, batch.pool.data(), ref, (uint32_t)i, s);
+      }
+      st.n_reads_kept += s.kept_reads; st.n_aligned_bases += s.kept_bases;
+      st.n_unsupported += s.unsup; st.n_overflow += s.over;
+    }
+    st.n_events = (int64_t)events.size();
+  } else {
+    rv_limits L;
+    rv_default_limits(&L);
+    L.halo = halo;
+    L.max_reads = (int64_t)batch.reads.size() + 16;
+    L.max_read_bytes = (int64_t)batch.pool.size() + 64;
+    int64_t npos = 0;
+    for (auto& r : regs) npos += r.end - r.start + 1 + 2 * halo;
+    L.max_positions = npos + 16;
+    L.max_regions = (int32_t)regs.size() + 1;
+    L.max_events = std::max<int64_t>(1 << 16, (int64_t)batch.reads.size() * 4);
+    L.max_variants = npos + 1024;
+    L.max_patch = 1 << 20;
+    L.max_ref_bases = (int64_t)refseq.size() + 16;
+    int rc = rv_create(&ctx, 0, &P, &L);
+    if (rc != RV_OK) { fprintf(stderr, "rv_create failed (%d): %s\n", rc, ctx ? rv_last_error(ctx) : "no device"); return 3; }
+    rv_read_batch bv = batch.view();
+#define RVCK(x) do { int rc_ = (x); if (rc_ != RV_OK) { fprintf(stderr, "%s failed (%d): %s\n", #x, rc_, rv_last_error(ctx)); return 3; } } while (0)
+    RVCK(rv_set_reference(ctx, ref_lo, (int64_t)refseq.size(), refseq.data()));
+    RVCK(rv_push_reads(ctx, &bv));
+    RVCK(rv_set_regions(ctx, regs.data(), (int32_t)regs.size()));
+    RVCK(rv_pileup(ctx));
+    RVCK(rv_get_pileup_stats(ctx, &st));
+    const rv_event* ev;
+    int64_t nev;
+    RVCK(rv_fetch_events(ctx, &ev, &nev));
+    events.assign(ev, ev + nev);
+    const int32_t* mrl;
+    int32_t nmrl;
+    RVCK(rv_fetch_max_read_len(ctx, &mrl, &nmrl));
+    for (size_t r = 0; r < regs.size(); ++r) {
+      RegionPileup& R = rp[r];
+      const uint32_t *c, *cv;
+      RVCK(rv_fetch_tables(ctx, (int32_t)r, &c, &cv, &R.first_pos, &R.n_pos));
+      R.region_idx = (int)r;
+      R.start = regs[r].start; R.end = regs[r].end;
+      R.counts.assign(c, c + (size_t)R.n_pos * RV_POS_U32);
+      R.cov.assign(cv, cv + R.n_pos);
+      R.max_read_len = mrl[r];
+    }
+  }
+  if (backend == "sim") {
+    std::stable_sort(events.begin(), events.end(), [](const rv_event& a, const rv_event& b) {
+      if (a.region != b.region) return a.region < b.region;
+      if (a.read_idx != b.read_idx) return a.read_idx < b.read_idx;
+      return a.seq_no < b.seq_no;
+    });
+  }
+  reduce_events(events.data(), (int64_t)events.size(), batch, P.goodq, rp);
+
+  // stage R: host realigner on the pileup model, then patch upload + scoring
+  rvk::RefView refv;
+  refv.bases = refseq.data();
+  refv.base_pos = ref_lo;
+  refv.n = (int64_t)refseq.size();
+  std::vector<std::vector<rv_patch_entry> > patches(regs.size());
+  for (size_t r = 0; r < regs.size(); ++r) {
+    fprintf(OUT, "REGION\t%s\t%s\t%d\t%d\n", sample.c_str(), chr.c_str(), regs[r].start, regs[r].end);
+    if (stages.find('C') != std::string::npos) {
+      fprintf(OUT, "C.MAXRL\t%d\n", rp[r].max_read_len);
+      dump_tables("C", rp[r]);
+      dump_counts("C.PINS", rp[r].pins);
+      dump_counts("C.PDEL", rp[r].pdel);
+      dump_counts("C.MNP", rp[r].mnp);
+    }
+    refv.lo = regs[r].ref_lo;
+    refv.hi = regs[r].ref_hi;
+    realign_region(P, rp[r], refv, regs[r].chr_len);
+    if (stages.find('R') != std::string::npos) {
+      fprintf(OUT, "R.MAXRL\t%d\n", rp[r].max_read_len);
+      dump_tables("R", rp[r]);
+    }
+    build_patch(rp[r], &patches[r]);
+    if (stages.find('V') != std::string::npos && backend == "sim") {
+      // CPU single-step of score_position over the region
+      rvk::LgTable lgt;
+      lgt.t = NULL; lgt.n = 0;
+      RegionPileup& R = rp[r];
+      std::vector<rv_patch_entry>& pe = patches[r];
+      std::map<int, std::pair<int, int> > grp;
+      for (size_t i = 0; i < pe.size();) {
+        size_t j = i;
+        while (j < pe.size() && pe[j].pos == pe[i].pos) ++j;
+        grp[pe[i].pos] = std::make_pair((int)i, (int)(j - i));
+        i = j;
+      }
+      SimEmit em;
+      em.out = &variants;
+      int unsup = 0;
+      for (int pos = regs[r].start; pos <= regs[r].end; ++pos) {
+        int i = pos - R.first_pos;
+        bool has_next = i + 1 < R.n_pos;
+        int pf = 0, pn = 0;
+        if (grp.count(pos)) { pf = grp[pos].first; pn = grp[pos].second; }
+        rvk::score_position(P, regs[r], (int)r, pos, refv, R.counts.data() + (size_t)i * RV_POS_U32, R.cov[i], has_next,
+                            R.counts.data() + (size_t)(i + 1) * RV_POS_U32, has_next ? R.cov[i + 1] : 0u, pe.data(), pf, pn,
+                            lgt, em, &unsup);
+      }
+    }
+  }
+  if (stages.find('V') != std::string::npos && backend != "sim") {
+    // upload patches of all regions, score on the device
+    std::vector<rv_patch_entry> all;
+    std::vector<int32_t> creg, cpos, cval;
+    for (size_t r = 0; r < regs.size(); ++r) {
+      for (auto& e : patches[r]) all.push_back(e);
+      collect_cov_patch(rp[r], &creg, &cpos, &cval);
+    }
+    RVCK(rv_apply_patch(ctx, all.data(), (int64_t)all.size(), creg.data(), cpos.data(), cval.data(), (int64_t)creg.size()));
+    RVCK(rv_score(ctx));
+    const rv_variant* vv;
+    int64_t nv;
+    RVCK(rv_fetch_variants(ctx, &vv, &nv));
+    variants.assign(vv, vv + nv);
+    // key_id of patch entries is an index into the concatenated list: rebase per region below
+    size_t base = 0;
+    std::vector<size_t> bases;
+    for (size_t r = 0; r < regs.size(); ++r) { bases.push_back(base); base += patches[r].size(); }
+    for (auto& v : variants)
+      if (v.key_kind == 1) v.key_id -= (int32_t)bases[v.region];
+  }
+  if (stages.find('V') != std::string::npos) {
+    std::stable_sort(variants.begin(), variants.end(), [](const rv_variant& a, const rv_variant& b) {
+      if (a.region != b.region) return a.region < b.region;
+      if (a.pos != b.pos) return a.pos < b.pos;
+      return a.rank < b.rank;
+    });
+    dump_variants(OUT, P, variants, patches, regs, refv, chr);
+  }
+  fprintf(stderr, "rv_dump[%s]: items %lld kept %lld bases %lld events %lld overflow %lld unsupported %lld variants %zu\n",
+          backend.c_str(), (long long)st.n_items, (long long)st.n_reads_kept, (long long)st.n_aligned_bases,
+          (long long)st.n_events, (long long)st.n_overflow, (long long)st.n_unsupported, variants.size());
+  if (ctx) rv_destroy(ctx);
+  fclose(OUT);
+  return 0;
+}
