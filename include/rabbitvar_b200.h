@@ -148,7 +148,7 @@ typedef struct rv_event {
   int32_t aux0;        /* soft clips: remaining clip length m ; TTREF: pstd|qstd<<1 of the insertion */
   int32_t aux1;        /* soft clips: number of high-quality bases kept (n_hi) */
   int32_t aux2;        /* soft clips: read offset of the base nearest the junction */
-  char key[52];
+  char key[48];
 } rv_event;
 
 /* One accumulator in the reference's own field set (include/Variation.h:12-82) for the host-side
@@ -165,10 +165,11 @@ typedef struct rv_variation {
 typedef struct rv_patch_entry {
   int32_t region;
   int32_t pos;
-  uint8_t table;   /* 0 = nonInsertionVariants, 1 = insertionVariants */
+  uint8_t table;   /* 0 = nonInsertionVariants, 1 = insertionVariants, 2 = tombstone: the dense
+                      single-base key `key` no longer exists at this position */
   uint8_t keylen;
   uint8_t pad[2];
-  char key[52];
+  char key[48];
   rv_variation v;
 } rv_patch_entry;
 

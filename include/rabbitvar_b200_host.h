@@ -1,0 +1,52 @@
+/* rabbitvar_b200_host.h — C ABI of the host side of the path: BAM/FASTA decode into the staging
+ * buffers rv_push_reads consumes, and the batch-level replacement of one_region_run (reference
+ * src/modes/simpleMode.cpp:18-64) that returns TSV text in the reference's output format
+ * (print_output_variant_simple, simpleMode.cpp:66-142).  Lives in the same shared library as
+ * rabbitvar_b200.h. */
+#ifndef RABBITVAR_B200_HOST_H
+#define RABBITVAR_B200_HOST_H
+#include "rabbitvar_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rvh_batch rvh_batch;
+
+/* Decode every read overlapping chr:start-end (1-based inclusive) of an indexed BAM, in file order
+ * (replaces sam_itr_querys/sam_itr_next, recordPreprocessor.cpp:10-32,101-103). NULL on failure. */
+rvh_batch* rvh_load_bam(const char* bam_path, const char* chr, int32_t start, int32_t end, int32_t* chr_len_out);
+/* Concatenate b onto a (reads of a second sample); returns the read-index offset of b's reads inside a. */
+int64_t rvh_batch_append(rvh_batch* a, const rvh_batch* b);
+int64_t rvh_batch_n_reads(const rvh_batch* b);
+const rv_read* rvh_batch_reads(const rvh_batch* b);
+const uint8_t* rvh_batch_pool(const rvh_batch* b);
+int64_t rvh_batch_pool_bytes(const rvh_batch* b);
+int32_t rvh_batch_max_ref_span(const rvh_batch* b);
+void rvh_batch_free(rvh_batch* b);
+
+/* Region descriptors (read ranges + reference window of RecordPreprocessor::makeReference,
+ * recordPreprocessor.cpp:41-78) for n regions of one contig. read_offset/n_reads_sample restrict the
+ * search to one sample's slice of a concatenated batch (0, -1 = whole batch). */
+int rvh_make_regions(const rvh_batch* b, const int32_t* starts, const int32_t* ends, int32_t n, int32_t chr_len,
+                     int32_t ref_extension, int64_t read_offset, int64_t n_reads_sample, rv_region* out);
+
+/* Upper-cased reference bases chr:lo-hi (1-based inclusive) from an indexed FASTA into out (hi-lo+1 bytes).
+ * Returns the number of bases written, <0 on failure. */
+int64_t rvh_fetch_ref(const char* fasta_path, const char* chr, int32_t lo, int32_t hi, char* out);
+
+/* The whole per-batch path on host buffers: H2D, pileup, realign hand-off, scoring, D2H, TSV formatting
+ * (simple mode).  tsv_out is library-owned (valid until the next call on this ctx or rv_destroy). */
+typedef struct rvh_timing {
+  double push_ms, pileup_ms, fetch_ms, host_ms, patch_ms, score_ms, assemble_ms;
+  float pileup_kernel_ms, score_kernel_ms;
+  int64_t n_items, n_reads_kept, n_aligned_bases, n_events, n_unsupported, n_variants, n_lines, h2d_bytes, d2h_bytes;
+} rvh_timing;
+int rvh_call_regions(rv_ctx* ctx, const rv_params* params, const rvh_batch* batch, const rv_region* regions,
+                     int32_t n_regions, const char* ref_bases, int32_t ref_lo, int64_t ref_n, int push_reference,
+                     const char* sample, const char* chr, const char** tsv_out, int64_t* tsv_len, rvh_timing* timing);
+const char* rvh_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

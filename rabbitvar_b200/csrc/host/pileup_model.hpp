@@ -10,10 +10,16 @@
 #include "../../../include/rabbitvar_b200.h"
 #include "batch_loader.hpp"
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
 namespace rvhost {
+
+inline void replace_first_char(std::string& s, char c) {  // replaceFirst(s, c, "")
+  size_t p = s.find(c);
+  if (p != std::string::npos) s.erase(p, 1);
+}
 
 struct Variation {
   int cnt, fwd, rev;
@@ -82,6 +88,9 @@ struct RegionPileup {
   std::map<int, KeyMap> ins;  // insertionVariants
   std::map<int, Sclip> sc5, sc3;
   std::map<int, std::map<std::string, int> > pins, pdel, mnp;
+  // realigner bookkeeping for the write-back
+  std::set<int> cov_touched;
+  std::set<std::pair<int, char> > erased_dense;
 
   bool in_table(int pos) const { return pos >= first_pos && pos < first_pos + n_pos; }
   uint32_t* row(int pos, int allele) { return counts.data() + ((size_t)(pos - first_pos) * 4 + allele) * RV_ROW_U32; }
@@ -128,10 +137,6 @@ inline void reduce_events(const rv_event* ev, int64_t n, const ReadBatch& batch,
       case RV_EV_NI: {
         Variation& v = R.ni[e.pos][key];
         if (e.flags & RV_EVF_MNP) R.mnp[e.pos][key]++;
-        if ((e.flags & RV_EVF_PDEL) && key[0] == '-' && key.find('&') == std::string::npos &&
-            key.find('#') == std::string::npos && key.find('^') == std::string::npos) {
-          // plain deletions count into positionToDeletionCount before the observation (:1041)
-        }
         add_obs(v, dir, e.tp, q, e.mapq, e.nm, goodq);
         if (e.flags & RV_EVF_PDEL) R.pdel[e.pos][key]++;
         break;

@@ -1,0 +1,132 @@
+// pipeline.hpp — the product's replacement for one_region_run (reference src/modes/simpleMode.cpp:18-64)
+// over a BATCH of regions: host buffers in, TSV text out.
+//
+//   rv_push_reads -> rv_pileup (GPU)            == CigarParser::process
+//   events/tables D2H -> reduce -> realign      == VariationRealigner::process (host, north_star)
+//   rv_apply_patch -> rv_score (GPU)            == ToVarsBuilder::process
+//   variants D2H -> assemble/filter/format      == SimpleMode::output + print_output_variant_simple
+#pragma once
+#include "batch_loader.hpp"
+#include "pileup_model.hpp"
+#include "realign.hpp"
+#include "assemble.hpp"
+#include <chrono>
+
+namespace rvhost {
+
+struct BatchTiming {
+  double push_ms, pileup_ms, fetch_ms, host_ms, patch_ms, score_ms, assemble_ms;
+  float pileup_kernel_ms, score_kernel_ms;
+  rv_pileup_stats stats;
+  int64_t n_variants, n_lines, h2d_bytes, d2h_bytes;
+};
+
+inline double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// Runs every region of `regs` (all on one contig) through the path; appends the TSV lines of simple mode.
+// `genes[i]` is the BED name column of region i.  Returns an rv_* error code.
+inline int run_batch_simple(rv_ctx* ctx, const rv_params& P, const ReadBatch& batch, const std::vector<rv_region>& regs,
+                            const std::vector<std::string>& genes, const std::string& refseq, int32_t ref_lo,
+                            const std::string& sample, const std::string& chr, bool push_reference, std::string* tsv,
+                            BatchTiming* tm, std::string* err) {
+  BatchTiming t;
+  memset(&t, 0, sizeof t);
+  int rc;
+#define RV_STEP(x)                                                  \
+  do {                                                              \
+    rc = (x);                                                       \
+    if (rc != RV_OK) {                                              \
+      if (err) *err = std::string(#x) + ": " + rv_last_error(ctx);  \
+      return rc;                                                    \
+    }                                                               \
+  } while (0)
+  double t0 = now_ms();
+  if (push_reference) RV_STEP(rv_set_reference(ctx, ref_lo, (int64_t)refseq.size(), refseq.data()));
+  rv_read_batch bv = batch.view();
+  RV_STEP(rv_push_reads(ctx, &bv));
+  RV_STEP(rv_set_regions(ctx, regs.data(), (int32_t)regs.size()));
+  t.h2d_bytes += (int64_t)batch.reads.size() * (int64_t)sizeof(rv_read) + (int64_t)batch.pool.size() +
+                 (push_reference ? (int64_t)refseq.size() : 0);
+  double t1 = now_ms();
+  RV_STEP(rv_pileup(ctx));
+  RV_STEP(rv_get_pileup_stats(ctx, &t.stats));
+  double t2 = now_ms();
+  const rv_event* ev;
+  int64_t nev;
+  RV_STEP(rv_fetch_events(ctx, &ev, &nev));
+  const int32_t* mrl;
+  int32_t nmrl;
+  RV_STEP(rv_fetch_max_read_len(ctx, &mrl, &nmrl));
+  std::vector<RegionPileup> rp(regs.size());
+  for (size_t r = 0; r < regs.size(); ++r) {
+    RegionPileup& R = rp[r];
+    const uint32_t *c, *cv;
+    RV_STEP(rv_fetch_tables(ctx, (int32_t)r, &c, &cv, &R.first_pos, &R.n_pos));
+    R.region_idx = (int)r;
+    R.start = regs[r].start;
+    R.end = regs[r].end;
+    R.counts.assign(c, c + (size_t)R.n_pos * RV_POS_U32);
+    R.cov.assign(cv, cv + R.n_pos);
+    R.max_read_len = mrl[r];
+    t.d2h_bytes += (int64_t)R.n_pos * (RV_POS_U32 + 1) * 4;
+  }
+  t.d2h_bytes += nev * (int64_t)sizeof(rv_event);
+  double t3 = now_ms();
+  reduce_events(ev, nev, batch, P.goodq, rp);
+  rvk::RefView refv;
+  refv.bases = refseq.data();
+  refv.base_pos = ref_lo;
+  refv.n = (int64_t)refseq.size();
+  std::vector<std::vector<rv_patch_entry> > patches(regs.size());
+  std::vector<rv_patch_entry> all;
+  std::vector<size_t> bases;
+  std::vector<int32_t> creg, cpos, cval;
+  for (size_t r = 0; r < regs.size(); ++r) {
+    refv.lo = regs[r].ref_lo;
+    refv.hi = regs[r].ref_hi;
+    realign_region(P, rp[r], refv, regs[r].chr_len);
+    build_patch(rp[r], &patches[r]);
+    bases.push_back(all.size());
+    all.insert(all.end(), patches[r].begin(), patches[r].end());
+    collect_cov_patch(rp[r], &creg, &cpos, &cval);
+  }
+  double t4 = now_ms();
+  RV_STEP(rv_apply_patch(ctx, all.data(), (int64_t)all.size(), creg.data(), cpos.data(), cval.data(), (int64_t)creg.size()));
+  t.h2d_bytes += (int64_t)all.size() * (int64_t)sizeof(rv_patch_entry) + (int64_t)creg.size() * 12;
+  double t5 = now_ms();
+  RV_STEP(rv_score(ctx));
+  const rv_variant* vv;
+  int64_t nv;
+  RV_STEP(rv_fetch_variants(ctx, &vv, &nv));
+  t.d2h_bytes += nv * (int64_t)sizeof(rv_variant);
+  double t6 = now_ms();
+  std::vector<rv_variant> group;
+  for (int64_t i = 0; i < nv;) {
+    int64_t j = i;
+    while (j < nv && vv[j].region == vv[i].region && vv[j].pos == vv[i].pos) ++j;
+    const size_t r = (size_t)vv[i].region;
+    group.assign(vv + i, vv + j);
+    for (size_t k = 0; k < group.size(); ++k)
+      if (group[k].key_kind == 1) group[k].key_id -= (int32_t)bases[r];
+    refv.lo = regs[r].ref_lo;
+    refv.hi = regs[r].ref_hi;
+    PositionVars pv;
+    assemble_position(P, group.data(), (int)group.size(), patches[r], refv, regs[r].chr_len, &pv);
+    size_t before = tsv->size();
+    output_position_simple(P, pv, sample, genes[r], chr, regs[r].start, regs[r].end, tsv);
+    for (size_t k = before; k < tsv->size(); ++k) t.n_lines += (*tsv)[k] == '\n';
+    i = j;
+  }
+  double t7 = now_ms();
+  t.push_ms = t1 - t0; t.pileup_ms = t2 - t1; t.fetch_ms = t3 - t2; t.host_ms = t4 - t3; t.patch_ms = t5 - t4;
+  t.score_ms = t6 - t5; t.assemble_ms = t7 - t6;
+  t.n_variants = nv;
+  rv_last_kernel_ms(ctx, &t.pileup_kernel_ms, &t.score_kernel_ms);
+  if (tm) *tm = t;
+#undef RV_STEP
+  return RV_OK;
+}
+
+}  // namespace rvhost

@@ -80,11 +80,11 @@ struct Cigar {
 
 // Small fixed-capacity key builder (allele description strings, include/Variant.h:24-33).
 struct Key {
-  char c[52];
+  char c[48];
   int n;
   bool trunc;
   RV_HD void clear() { n = 0; trunc = false; }
-  RV_HD void push(char ch) { if (n < 52) c[n++] = ch; else trunc = true; }
+  RV_HD void push(char ch) { if (n < 48) c[n++] = ch; else trunc = true; }
   RV_HD void push_int(int v) {
     char tmp[12];
     int k = 0;
@@ -97,7 +97,7 @@ struct Key {
   }
   RV_HD void insert_at(int idx, char ch) {  // std::string::insert(idx, 1, ch); idx <= n assumed
     if (idx > n) idx = n;
-    if (n >= 52) { trunc = true; return; }
+    if (n >= 48) { trunc = true; return; }
     for (int k = n; k > idx; --k) c[k] = c[k - 1];
     c[idx] = ch;
     n++;
@@ -107,7 +107,7 @@ struct Key {
       if (c[k] == ch) { for (int j = k; j + 1 < n; ++j) c[j] = c[j + 1]; n--; return; }
   }
   RV_HD void prepend(const char* s, int len) {
-    if (n + len > 52) { trunc = true; return; }
+    if (n + len > 48) { trunc = true; return; }
     for (int k = n - 1; k >= 0; --k) c[k + len] = c[k];
     for (int k = 0; k < len; ++k) c[k] = s[k];
     n += len;
@@ -615,7 +615,7 @@ RV_HD void emit_event(Sink& s, WalkState& w, int region_idx, uint32_t read_idx, 
   e.aux0 = aux0;
   e.aux1 = aux1;
   e.aux2 = aux2;
-  for (int k = 0; k < 52; ++k) e.key[k] = (key && k < key->n) ? key->c[k] : (char)0;
+  for (int k = 0; k < 48; ++k) e.key[k] = (key && k < key->n) ? key->c[k] : (char)0;
   s.event(e);
 }
 

@@ -249,7 +249,7 @@ RV_HDN void score_position(const rv_params& P, const rv_region& R, int region_id
     bool shadow = false;
     for (int j = 0; j < patch_n; ++j) {
       const rv_patch_entry& e = patch[patch_first + j];
-      if (e.table == 0 && e.keylen == 1 && e.key[0] == BASES[a]) shadow = true;
+      if (e.table != 1 && e.keylen == 1 && e.key[0] == BASES[a]) shadow = true;  // 2 = tombstone
     }
     if (shadow) continue;
     if (dense_exists(rows + a * RV_ROW_U32)) {
@@ -260,6 +260,7 @@ RV_HDN void score_position(const rv_params& P, const rv_region& R, int region_id
   }
   for (int j = 0; j < patch_n; ++j) {
     const rv_patch_entry& e = patch[patch_first + j];
+    if (e.table == 2) continue;  // key erased by the realigner
     if (nk >= RV_MAX_KEYS) { (*unsupported)++; break; }
     acc_from_patch(keys[nk], e, patch_first + j);
     if (e.table == 0) n_ni++;

@@ -97,7 +97,7 @@ struct DeviceSink {
     atomicAdd(row + RV_F_SUM_MAPQ, (uint32_t)(sign * mapq));
     if (nm) atomicAdd(row + RV_F_SUM_NM, (uint32_t)(sign * nm));
     if ((double)q >= goodq) atomicAdd(row + RV_F_HI, (uint32_t)sign);
-    atomicOr(row + RV_F_STD, 1u << 30);  // key exists even if it nets to zero
+    // (a key only ever nets to zero after an M-path observation, whose STD word keeps it "existing")
   }
   __device__ __forceinline__ void cov(int pos) {
     int i;

@@ -1,0 +1,80 @@
+"""Seeded synthetic parity cases shared by the tests and tests/golden/make_golden.py.
+
+Shapes follow BASELINE.json's five configs at sizes the reference finishes in seconds."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "build")
+WORK = os.path.join(ROOT, "_work", "cases")
+
+
+def _simple(chrom, region, extra=()):
+    def f(d):
+        return ["-G", os.path.join(d, "ref.fa"), "-b", os.path.join(d, "S.bam"), "-N", "S", "-f", "0.01",
+                "-R", f"{chrom}:{region}"] + list(extra)
+    return f
+
+
+def _bed(chrom, bed, extra=()):
+    def f(d):
+        return ["-G", os.path.join(d, "ref.fa"), "-b", os.path.join(d, "S.bam"), "-N", "S", "-i",
+                os.path.join(d, bed), "-c", "1", "-S", "2", "-E", "3", "-g", "4"] + list(extra)
+    return f
+
+
+# name -> synthgen args, reference CLI args, rv_dump args (our side), which stages are expected to match
+CASES = {
+    # cfg 1: single sample, simple mode, SNVs + a few indels; default -k 1: CigarParser stage must be bit-exact
+    "c1_k1": dict(gen=["--cfg", "1", "--len", "22600", "--depth", "100"], chrom="chrS1", region="1301-21300",
+                  ref_args=_simple("chrS1", "1301-21300"), dump_args=[], stages="CRV", exact_stages=["C."]),
+    # same data, -k 0: every stage (pileup, adjustMNP, scoring) must match
+    "c1_k0": dict(gen=["--cfg", "1", "--len", "22600", "--depth", "100"], chrom="chrS1", region="1301-21300",
+                  ref_args=_simple("chrS1", "1301-21300", ["-k", "0"]), dump_args=["--k", "0"], stages="CRV",
+                  exact_stages=["C.", "R.", "V."]),
+    # cfg 5: indel / soft-clip / MNV heavy with -3 -u
+    "c5_k1": dict(gen=["--cfg", "5", "--len", "12600", "--depth", "100"], chrom="chrS5", region="1301-11300",
+                  ref_args=_simple("chrS5", "1301-11300", ["-3", "-u"]), dump_args=["--three", "1", "--u", "1"],
+                  stages="CRV", exact_stages=["C."]),
+    "c5_k0": dict(gen=["--cfg", "5", "--len", "12600", "--depth", "100"], chrom="chrS5", region="1301-11300",
+                  ref_args=_simple("chrS5", "1301-11300", ["-3", "-u", "-k", "0"]),
+                  dump_args=["--three", "1", "--u", "1", "--k", "0"], stages="CRV", exact_stages=["C.", "R.", "V."]),
+    # cfg 3: deep amplicon panel, low VAF, BED input (4-column BED => simple mode)
+    "c3_k0": dict(gen=["--cfg", "3", "--len", "14600", "--depth", "2000", "--amplicons", "3"], chrom="chrS3",
+                  bed="panel.bed", ref_args=_bed("chrS3", "panel.bed", ["-f", "0.005", "-k", "0"]),
+                  dump_args=["--f", "0.005", "--k", "0"], stages="CV", exact_stages=["C.", "V."]),
+    # cfg 2 shape: the tumor sample scored the way the somatic driver scores it (every covered position kept)
+    "c2_pileup_k0": dict(gen=["--cfg", "1", "--len", "8600", "--depth", "150", "--seed", "99"], chrom="chrS1",
+                         region="1301-7300", ref_args=_simple("chrS1", "1301-7300", ["-k", "0", "-p", "--fisher"]),
+                         dump_args=["--k", "0", "--p", "1", "--fisher", "1"], stages="CV", exact_stages=["C.", "V."]),
+    # empty / ragged: a region with no reads at all and a region at the contig edge of the read cloud
+    "edge_empty": dict(gen=["--cfg", "1", "--len", "8600", "--depth", "20", "--seed", "5"], chrom="chrS1",
+                       region="10-1250", ref_args=_simple("chrS1", "10-1250"), dump_args=[], stages="CRV",
+                       exact_stages=["C.", "R.", "V."]),
+}
+
+
+def dataset_dir(name):
+    return os.path.join(WORK, name)
+
+
+def generate(name):
+    d = dataset_dir(name)
+    marker = os.path.join(d, "meta.txt")
+    if not os.path.exists(marker):
+        os.makedirs(d, exist_ok=True)
+        subprocess.run([os.path.join(BUILD, "synthgen")] + CASES[name]["gen"] + ["--out", d], check=True,
+                       stderr=subprocess.DEVNULL)
+    return d
+
+
+def dump_cmd(name, backend, out, stages):
+    c = CASES[name]
+    d = dataset_dir(name)
+    cmd = [os.path.join(BUILD, "rv_dump"), "--backend", backend, "--fasta", os.path.join(d, "ref.fa"), "--bam",
+           os.path.join(d, "S.bam"), "--chr", c["chrom"], "--out", out, "--stages", stages]
+    if "region" in c:
+        cmd += ["--region", c["region"]]
+    else:
+        cmd += ["--bed", os.path.join(d, c["bed"])]
+    return cmd + c["dump_args"]

@@ -1,0 +1,137 @@
+"""GPU parity tests proper: the CUDA path, driven through the C ABI (tests/tools/rv_dump.cpp --backend gpu
+and the product CLI), against the oracle.  The oracle is the reference binary when oracle/_ref travelled to
+the box, and in any case the committed golden vectors generated from it (tests/golden/make_golden.py).
+
+Bar: integer / byte / index fields bit-exact; floating-point fields within 1e-9 relative.
+"""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import dumpcmp
+from conftest import ROOT, golden_path, run, unpack_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_cuda_path_matches_golden(built, name, tmp_path):
+    c = cases.CASES[name]
+    cases.generate(name)
+    got = str(tmp_path / "gpu.txt")
+    run(cases.dump_cmd(name, "gpu", got, c["stages"]))
+    want = unpack_golden(name, "dump.txt", str(tmp_path / "golden.txt"))
+    n, problems = dumpcmp.compare(want, got, c["exact_stages"])
+    assert n > 0 or name == "edge_empty"
+    assert not problems, problems[:5]
+
+
+@pytest.mark.parametrize("name", ["c1_k1", "c5_k1"])
+def test_cuda_path_matches_reference_binary_run_here(built, ref_tools, name, tmp_path):
+    if ref_tools is None:
+        pytest.skip("oracle/_ref did not travel to this box")
+    c = cases.CASES[name]
+    d = cases.generate(name)
+    want = str(tmp_path / "ref.txt")
+    env = dict(os.environ, RV_DUMP=want, RV_DUMP_STAGES="C")
+    run([ref_tools["ref_dump"]] + c["ref_args"](d), env=env)
+    got = str(tmp_path / "gpu.txt")
+    run(cases.dump_cmd(name, "gpu", got, "C"))
+    n, problems = dumpcmp.compare(want, got, ["C."], rel_tol=0.0)
+    assert n > 1000 and not problems, problems[:5]
+
+
+def _tsv_lines(text):
+    return sorted(l for l in text.splitlines() if l)
+
+
+def _tsv_equal(a, b):
+    ta, tb = a.split("\t"), b.split("\t")
+    return len(ta) == len(tb) and all(dumpcmp.fields_equal(x, y, 2e-6) for x, y in zip(ta, tb))
+
+
+@pytest.mark.parametrize("name", ["c1_k0", "c5_k0", "c3_k0", "c2_pileup_k0"])
+def test_cli_tsv_matches_reference_output(built, name, tmp_path):
+    """End to end through the drop-in CLI: same flags as the reference, same TSV (sorted multiset of lines;
+    %f-printed doubles may differ in the last printed digit when the oracle's -ffast-math quotient is off by an ulp)."""
+    c = cases.CASES[name]
+    d = cases.generate(name)
+    out = str(tmp_path / "out.tsv")
+    run([os.path.join(ROOT, "build", "rabbitvar_b200")] + c["ref_args"](d) + ["--out", out])
+    got = _tsv_lines(open(out).read())
+    with gzip.open(golden_path(name, "tsv"), "rt") as f:
+        want = _tsv_lines(f.read())
+    assert len(got) == len(want)
+    bad = [(w, g) for w, g in zip(want, got) if w != g and not _tsv_equal(w, g)]
+    assert not bad, bad[:3]
+
+
+def test_tiled_bed_equals_per_tile_runs(built, tmp_path):
+    """A tile is the parity unit: running N tiles in one batch must equal running them one at a time."""
+    import rabbitvar_b200 as rv
+    d = cases.generate("c1_k1")
+    bam, fa = os.path.join(d, "S.bam"), os.path.join(d, "ref.fa")
+    starts = [1301, 6301, 11301, 16301]
+    ends = [6300, 11300, 16300, 21300]
+    b = rv.HostBatch(bam, "chrS1", starts[0], ends[-1])
+    ref = rv.fetch_ref(fa, "chrS1", 1, b.chr_len)
+    lim = rv.default_limits(max_reads=b.n_reads + 16, max_read_bytes=b.pool_bytes + 64, max_ref_bases=len(ref) + 16)
+    ctx = rv.Context(0, rv.default_params(), lim)
+    ctx.set_reference(1, ref)
+    ctx.push_reads(b)
+    regs = b.make_regions(starts, ends)
+    ctx.set_regions(regs)
+    st_all = ctx.pileup()
+    tabs_all = [ctx.fetch_tables(i) for i in range(4)]
+    total = 0
+    for i in range(4):
+        one = b.make_regions(starts[i:i + 1], ends[i:i + 1])
+        ctx.set_regions(one)
+        st = ctx.pileup()
+        total += st.n_aligned_bases
+        counts, cov, first = ctx.fetch_tables(0)
+        assert first == tabs_all[i][2]
+        assert np.array_equal(counts, tabs_all[i][0]) and np.array_equal(cov, tabs_all[i][1])
+    assert total == st_all.n_aligned_bases
+    ctx.close()
+
+
+def test_pileup_is_deterministic_and_additive(built):
+    """Size-independent properties of the atomics-based accumulation: repeating the launch gives identical
+    tables (order independence), and the tables of two disjoint read halves add up to the table of the whole."""
+    import ctypes as C
+    import rabbitvar_b200 as rv
+    d = cases.generate("c5_k1")
+    bam, fa = os.path.join(d, "S.bam"), os.path.join(d, "ref.fa")
+    b = rv.HostBatch(bam, "chrS5", 1301, 11300)
+    ref = rv.fetch_ref(fa, "chrS5", 1, b.chr_len)
+    lim = rv.default_limits(max_reads=b.n_reads + 16, max_read_bytes=b.pool_bytes + 64, max_ref_bases=len(ref) + 16)
+    ctx = rv.Context(0, rv.default_params(move3=1, uniq_u=1), lim)
+    ctx.set_reference(1, ref)
+    ctx.push_reads(b)
+    regs = b.make_regions([1301], [11300])
+    ctx.set_regions(regs)
+    ctx.pileup()
+    c1, v1, _ = ctx.fetch_tables(0)
+    ctx.pileup()
+    c2, v2, _ = ctx.fetch_tables(0)
+    assert np.array_equal(c1[..., :7], c2[..., :7]) and np.array_equal(v1, v2)
+    assert np.array_equal(c1[..., 7] >> 24, c2[..., 7] >> 24)  # pstd/qstd flags (the recorded first value may differ)
+    # halves
+    n = b.n_reads
+    lo, hi = regs[0].read_lo, regs[0].read_hi
+    mid = (lo + hi) // 2
+    parts = []
+    for a, z in ((lo, mid), (mid, hi)):
+        r = (rv.Region * 1)()
+        C.memmove(r, regs, C.sizeof(rv.Region))
+        r[0].read_lo, r[0].read_hi = a, z
+        ctx.set_regions(r)
+        ctx.pileup()
+        parts.append(ctx.fetch_tables(0))
+    assert np.array_equal(parts[0][0][..., :7] + parts[1][0][..., :7], c1[..., :7])
+    assert np.array_equal(parts[0][1] + parts[1][1], v1)
+    ctx.close()

@@ -1,0 +1,43 @@
+"""Host decode path: BGZF/BAM/BAI/FAI reader against the generator's own bookkeeping."""
+import os
+
+import numpy as np
+
+import cases
+import rabbitvar_b200 as rv
+
+
+def test_bam_roundtrip_counts(built):
+    d = cases.generate("c1_k1")
+    meta = dict(l.split("\t") for l in open(os.path.join(d, "meta.txt")).read().splitlines())
+    b = rv.HostBatch(os.path.join(d, "S.bam"), "chrS1", 1, int(meta["len"]))
+    assert b.n_reads == int(meta["reads"])
+    assert b.chr_len == int(meta["len"])
+    reads = b.reads_numpy().view(np.dtype([("pos", "<i4"), ("mpos", "<i4"), ("off", "<u4"), ("l_seq", "<i4"),
+                                          ("flag", "<u2"), ("n_cigar", "<u2"), ("nm", "<i2"), ("mapq", "u1"),
+                                          ("same", "u1"), ("end", "<i4"), ("rsv", "<i4")]))
+    assert (np.diff(reads["pos"]) >= 0).all()          # coordinate sorted
+    assert (reads["l_seq"] == 150).all()
+    assert (reads["nm"] >= 0).all()                     # NM always present
+    assert (reads["end"] >= reads["pos"]).all()
+
+
+def test_region_query_matches_linear_scan(built):
+    d = cases.generate("c1_k1")
+    whole = rv.HostBatch(os.path.join(d, "S.bam"), "chrS1", 1, 30000)
+    part = rv.HostBatch(os.path.join(d, "S.bam"), "chrS1", 5001, 6000)
+    dt = np.dtype([("pos", "<i4"), ("mpos", "<i4"), ("off", "<u4"), ("l_seq", "<i4"), ("flag", "<u2"),
+                   ("n_cigar", "<u2"), ("nm", "<i2"), ("mapq", "u1"), ("same", "u1"), ("end", "<i4"), ("rsv", "<i4")])
+    w = whole.reads_numpy().view(dt)
+    p = part.reads_numpy().view(dt)
+    # htslib iterator semantics: pos0 < end && endpos > beg0
+    sel = w[(w["pos"] - 1 < 6000) & (w["end"] > 5000)]
+    assert len(sel) == len(p)
+    assert (sel["pos"] == p["pos"]).all() and (sel["flag"] == p["flag"]).all()
+
+
+def test_fetch_ref_matches_fasta(built):
+    d = cases.generate("c1_k1")
+    fa = "".join(open(os.path.join(d, "ref.fa")).read().splitlines()[1:])
+    got = rv.fetch_ref(os.path.join(d, "ref.fa"), "chrS1", 1234, 2345).decode()
+    assert got == fa[1233:2345]

@@ -32,6 +32,7 @@ struct SimSink {
     return true;
   }
   void single(int pos, int allele, bool dir, int tp, int q, int mapq, int nm) {
+    if (getenv("RV_DEBUG_POS") && atoi(getenv("RV_DEBUG_POS")) == pos) fprintf(stderr, "single pos %d al %d dir %d tp %d q %d mapq %d nm %d\n", pos, allele, dir, tp, q, mapq, nm);
     if (!idx(pos)) return;
     uint32_t* row = R->row(pos, allele);
     row[dir ? RV_F_REV : RV_F_FWD] += 1;
@@ -49,6 +50,7 @@ struct SimSink {
     }
   }
   void adj(int pos, int allele, int sign, bool dir, int tp, int q, int mapq, int nm) {
+    if (getenv("RV_DEBUG_POS") && atoi(getenv("RV_DEBUG_POS")) == pos) fprintf(stderr, "adj pos %d al %d sign %d dir %d tp %d q %d\n", pos, allele, sign, dir, tp, q);
     if (!idx(pos)) return;
     uint32_t* row = R->row(pos, allele);
     row[dir ? RV_F_REV : RV_F_FWD] += (uint32_t)sign;
@@ -57,7 +59,6 @@ struct SimSink {
     row[RV_F_SUM_MAPQ] += (uint32_t)(sign * mapq);
     row[RV_F_SUM_NM] += (uint32_t)(sign * nm);
     if ((double)q >= goodq) row[RV_F_HI] += (uint32_t)sign;
-    row[RV_F_STD] |= 1u << 30;
   }
   void cov(int pos) {
     if (!idx(pos)) return;
@@ -278,7 +279,13 @@ int main(int argc, char** argv) {
   refv.base_pos = ref_lo;
   refv.n = (int64_t)refseq.size();
   std::vector<std::vector<rv_patch_entry> > patches(regs.size());
+  FILE* const final_out = OUT;
+  std::vector<char*> rbuf(regs.size(), (char*)NULL);
+  std::vector<size_t> rlen(regs.size(), 0);
+  std::vector<FILE*> rfile(regs.size(), (FILE*)NULL);
   for (size_t r = 0; r < regs.size(); ++r) {
+    rfile[r] = open_memstream(&rbuf[r], &rlen[r]);
+    OUT = rfile[r];
     fprintf(OUT, "REGION\t%s\t%s\t%d\t%d\n", sample.c_str(), chr.c_str(), regs[r].start, regs[r].end);
     if (stages.find('C') != std::string::npos) {
       fprintf(OUT, "C.MAXRL\t%d\n", rp[r].max_read_len);
@@ -349,8 +356,21 @@ int main(int argc, char** argv) {
       if (a.pos != b.pos) return a.pos < b.pos;
       return a.rank < b.rank;
     });
-    dump_variants(OUT, P, variants, patches, regs, refv, chr);
+    // V lines go to their own region's buffer
+    for (size_t i = 0; i < variants.size();) {
+      size_t j = i;
+      while (j < variants.size() && variants[j].region == variants[i].region) ++j;
+      std::vector<rv_variant> one(variants.begin() + i, variants.begin() + j);
+      dump_variants(rfile[(size_t)variants[i].region], P, one, patches, regs, refv, chr);
+      i = j;
+    }
   }
+  for (size_t r = 0; r < regs.size(); ++r) {
+    fclose(rfile[r]);
+    fwrite(rbuf[r], 1, rlen[r], final_out);
+    free(rbuf[r]);
+  }
+  OUT = final_out;
   fprintf(stderr, "rv_dump[%s]: items %lld kept %lld bases %lld events %lld overflow %lld unsupported %lld variants %zu\n",
           backend.c_str(), (long long)st.n_items, (long long)st.n_reads_kept, (long long)st.n_aligned_bases,
           (long long)st.n_events, (long long)st.n_overflow, (long long)st.n_unsupported, variants.size());

@@ -17,6 +17,7 @@
 #include <random>
 #include <functional>
 #include <sys/stat.h>
+#include <thread>
 
 using namespace rvio;
 
@@ -179,14 +180,20 @@ struct ReadOut {
   BamRecord rec;
 };
 
-static int draw_qual(Rng& rng) {
-  double r = rng.uni();
-  if (r < 0.70) return 37;
-  if (r < 0.85) return 30;
-  if (r < 0.92) return 25;
-  if (r < 0.97) return 20;
-  if (r < 0.99) return 12;
+// quality per base from {37:0.70, 30:0.15, 25:0.07, 20:0.05, 12:0.02, 5:0.01}; 16 random bits per base
+static inline int qual_of(uint32_t r16) {
+  if (r16 < 45875) return 37;
+  if (r16 < 55706) return 30;
+  if (r16 < 60293) return 25;
+  if (r16 < 63570) return 20;
+  if (r16 < 64881) return 12;
   return 5;
+}
+static void draw_quals(Rng& rng, uint8_t* q, int n) {
+  for (int k = 0; k < n; k += 4) {
+    uint64_t r = rng.next();
+    for (int j = 0; j < 4 && k + j < n; ++j) q[k + j] = (uint8_t)qual_of((uint32_t)(r >> (16 * j)) & 0xffffu);
+  }
 }
 
 static inline uint8_t nt16(char c) {
@@ -249,22 +256,33 @@ static bool build_read(const Params& P, const std::string& ref, const std::vecto
       continue;
     }
     if (!applied) {
-      seq->push_back(ref[(size_t)(rpos - 1)]);
-      push('M', 1);
-      rpos++;
+      // copy the matched run up to the next candidate variant in one go
+      int run = rl - (int)seq->size();
+      if (vi < vs.size() && vs[vi].pos > rpos) run = std::min(run, vs[vi].pos - rpos);
+      else if (vi < vs.size()) run = 1;
+      if (rpos - 1 + run > (int)ref.size()) return false;
+      seq->append(ref, (size_t)(rpos - 1), (size_t)run);
+      push('M', run);
+      rpos += run;
     }
   }
   // sequencing errors (substitutions) on matched bases only
   {
-    int q = 0;
+    // error positions by geometric skipping (p = 0.002 per matched base); may accidentally revert a
+    // planted SNV, NM is recomputed below
+    int next_err = (int)(log(1.0 - rng.uni() * 0.999999) / log(1.0 - 0.002));
+    int q = 0, mcount = 0;
     for (size_t o = 0; o < ops.size(); ++o) {
-      if (ops[o].first == 'M' || ops[o].first == 'I') {
-        for (int k = 0; k < ops[o].second; ++k, ++q) {
-          if (ops[o].first == 'M' && rng.uni() < 0.002) {
-            (*seq)[q] = other_base((*seq)[q], rng);
-            // may accidentally revert a planted SNV; NM is recomputed below
-          }
+      if (ops[o].first == 'M') {
+        while (next_err < mcount + ops[o].second) {
+          int at = q + (next_err - mcount);
+          (*seq)[at] = other_base((*seq)[at], rng);
+          next_err += 1 + (int)(log(1.0 - rng.uni() * 0.999999) / log(1.0 - 0.002));
         }
+        mcount += ops[o].second;
+        q += ops[o].second;
+      } else if (ops[o].first == 'I') {
+        q += ops[o].second;
       }
     }
   }
@@ -376,7 +394,7 @@ static void make_bam(const Params& P, const std::string& path, const std::string
   size_t vlo = 0;
   auto flush_to = [&](int pos0) {
     while (!heap.empty() && heap.top().rec.pos <= pos0) {
-      Pending p = heap.top();
+      Pending p = std::move(const_cast<Pending&>(heap.top()));
       heap.pop();
       w.append(p.rec);
     }
@@ -409,7 +427,8 @@ static void make_bam(const Params& P, const std::string& path, const std::string
       if (!build_read(P, ref, vs, vlo, carried, fstart, RL, rng, P.softclip_frac, &seq1, &cg1, &nm1, &s1)) continue;
       if (!build_read(P, ref, vs, vlo, carried, r2start, RL, rng, P.softclip_frac, &seq2, &cg2, &nm2, &s2)) continue;
       q1.resize(RL); q2.resize(RL);
-      for (int k = 0; k < RL; ++k) { q1[k] = (uint8_t)draw_qual(rng); q2[k] = (uint8_t)draw_qual(rng); }
+      draw_quals(rng, q1.data(), RL);
+      draw_quals(rng, q2.data(), RL);
       int mapq = rng.uni() < 0.9 ? 60 : rng.range(20, 59);
       bool first_fwd = rng.uni() < 0.5;  // which of read1/read2 is the forward (leftmost) mate
       int extra = 0;
@@ -427,8 +446,8 @@ static void make_bam(const Params& P, const std::string& path, const std::string
       a.ord = ord * 2; b.ord = ord * 2 + 1;
       ++ord;
       flush_to(fstart - 2);  // every later read has 1-based pos >= fstart
-      heap.push(a);
-      heap.push(b);
+      heap.push(std::move(a));
+      heap.push(std::move(b));
       n_reads += 2;
       n_bases += 2 * RL;
     }
@@ -503,8 +522,9 @@ int main(int argc, char** argv) {
 
   uint64_t nr = 0, nb = 0, nr2 = 0, nb2 = 0;
   if (P.somatic) {
+    std::thread tn([&]() { make_bam(P, P.out + "/N.bam", P.chr, ref, vs, 1, P.depth_n, P.seed * 31 + 2, windows, &nr2, &nb2); });
     make_bam(P, P.out + "/T.bam", P.chr, ref, vs, 0, P.depth, P.seed * 31 + 1, windows, &nr, &nb);
-    make_bam(P, P.out + "/N.bam", P.chr, ref, vs, 1, P.depth_n, P.seed * 31 + 2, windows, &nr2, &nb2);
+    tn.join();
   } else {
     make_bam(P, P.out + "/S.bam", P.chr, ref, vs, 0, P.depth, P.seed * 31 + 1, windows, &nr, &nb);
   }
