@@ -94,7 +94,9 @@ def test_tiled_bed_equals_per_tile_runs(built, tmp_path):
         total += st.n_aligned_bases
         counts, cov, first = ctx.fetch_tables(0)
         assert first == tabs_all[i][2]
-        assert np.array_equal(counts, tabs_all[i][0]) and np.array_equal(cov, tabs_all[i][1])
+        # field 7 keeps "the first (tp, q) recorded", which depends on atomic arrival order: compare its flags only
+        assert np.array_equal(counts[..., :7], tabs_all[i][0][..., :7]) and np.array_equal(cov, tabs_all[i][1])
+        assert np.array_equal(counts[..., 7] >> 24, tabs_all[i][0][..., 7] >> 24)
     assert total == st_all.n_aligned_bases
     ctx.close()
 
