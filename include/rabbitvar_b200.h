@@ -241,6 +241,8 @@ int rv_fetch_events(rv_ctx* ctx, const rv_event** events, int64_t* n_events);
 int rv_apply_patch(rv_ctx* ctx, const rv_patch_entry* entries, int64_t n_entries, const int32_t* cov_region,
                    const int32_t* cov_pos, const int32_t* cov_val, int64_t n_cov);
 int rv_fetch_variants(rv_ctx* ctx, const rv_variant** variants, int64_t* n_variants);
+/* Number of records the last rv_score produced (no copy). */
+int64_t rv_variant_count(const rv_ctx* ctx);
 
 /* Fisher exact test for a batch of 2x2 tables on the device (call sites simpleMode.cpp:98,
  * somaticMode.cpp:132; algorithm of htslib kfunc.c kt_fisher_exact).  tables: n x 4 ints
@@ -249,6 +251,10 @@ int rv_fisher_exact(rv_ctx* ctx, const int32_t* tables, int64_t n, double* out);
 
 /* Device timing of the last rv_pileup / rv_score in milliseconds (CUDA events on the context stream). */
 int rv_last_kernel_ms(rv_ctx* ctx, float* pileup_ms, float* score_ms);
+/* Brackets any sequence of calls with CUDA events recorded on the context's (launching) stream;
+ * rv_timer_stop synchronises and returns the elapsed device time in milliseconds. */
+int rv_timer_start(rv_ctx* ctx);
+int rv_timer_stop(rv_ctx* ctx, float* ms);
 /* Number of kernels launched by this context so far. */
 int64_t rv_launch_count(const rv_ctx* ctx);
 

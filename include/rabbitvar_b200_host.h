@@ -22,6 +22,8 @@ const rv_read* rvh_batch_reads(const rvh_batch* b);
 const uint8_t* rvh_batch_pool(const rvh_batch* b);
 int64_t rvh_batch_pool_bytes(const rvh_batch* b);
 int32_t rvh_batch_max_ref_span(const rvh_batch* b);
+/* Page-lock the batch's host buffers (cudaHostRegister) so rv_push_reads copies from pinned memory. */
+int rvh_batch_pin(rvh_batch* b);
 void rvh_batch_free(rvh_batch* b);
 
 /* Region descriptors (read ranges + reference window of RecordPreprocessor::makeReference,
@@ -44,6 +46,10 @@ typedef struct rvh_timing {
 int rvh_call_regions(rv_ctx* ctx, const rv_params* params, const rvh_batch* batch, const rv_region* regions,
                      int32_t n_regions, const char* ref_bases, int32_t ref_lo, int64_t ref_n, int push_reference,
                      const char* sample, const char* chr, const char** tsv_out, int64_t* tsv_len, rvh_timing* timing);
+/* The host hand-off alone, for a batch that is already resident and piled up on ctx (after rv_pileup):
+ * events/tables D2H, BAM-order reduce, host realigner, patch write-back (rv_apply_patch). */
+int rvh_install_patch(rv_ctx* ctx, const rv_params* params, const rvh_batch* batch, const rv_region* regions,
+                      int32_t n_regions, const char* ref_bases, int32_t ref_lo, int64_t ref_n);
 const char* rvh_last_error(void);
 
 #ifdef __cplusplus

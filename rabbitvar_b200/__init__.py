@@ -111,10 +111,11 @@ ABI_SYMBOLS = [
     "rv_abi_version", "rv_device_count", "rv_default_params", "rv_default_limits", "rv_create", "rv_destroy",
     "rv_last_error", "rv_sync", "rv_set_reference", "rv_push_reads", "rv_push_reads_device", "rv_set_regions",
     "rv_pileup", "rv_score", "rv_get_pileup_stats", "rv_fetch_max_read_len", "rv_fetch_tables", "rv_fetch_events",
-    "rv_apply_patch", "rv_fetch_variants", "rv_fisher_exact", "rv_last_kernel_ms", "rv_launch_count",
+    "rv_apply_patch", "rv_fetch_variants", "rv_variant_count", "rv_fisher_exact", "rv_last_kernel_ms", "rv_timer_start",
+    "rv_timer_stop", "rv_launch_count",
     "rvh_load_bam", "rvh_batch_append", "rvh_batch_n_reads", "rvh_batch_reads", "rvh_batch_pool",
-    "rvh_batch_pool_bytes", "rvh_batch_max_ref_span", "rvh_batch_free", "rvh_make_regions", "rvh_fetch_ref",
-    "rvh_call_regions", "rvh_last_error",
+    "rvh_batch_pool_bytes", "rvh_batch_max_ref_span", "rvh_batch_pin", "rvh_batch_free", "rvh_make_regions", "rvh_fetch_ref",
+    "rvh_call_regions", "rvh_install_patch", "rvh_last_error",
 ]
 
 
@@ -144,6 +145,8 @@ def _declare(L):
     L.rv_fetch_variants.argtypes = [vp, C.POINTER(C.POINTER(Variant)), C.POINTER(i64)]
     L.rv_fisher_exact.argtypes = [vp, vp, i64, vp]
     L.rv_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.rv_timer_start.argtypes = [vp]
+    L.rv_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.rv_launch_count.argtypes = [vp]
     L.rv_launch_count.restype = i64
     L.rvh_load_bam.argtypes = [C.c_char_p, C.c_char_p, i32, i32, C.POINTER(i32)]
@@ -160,12 +163,16 @@ def _declare(L):
     L.rvh_batch_pool_bytes.restype = i64
     L.rvh_batch_max_ref_span.argtypes = [vp]
     L.rvh_batch_max_ref_span.restype = i32
+    L.rvh_batch_pin.argtypes = [vp]
     L.rvh_batch_free.argtypes = [vp]
     L.rvh_make_regions.argtypes = [vp, vp, vp, i32, i32, i32, i64, i64, C.POINTER(Region)]
     L.rvh_fetch_ref.argtypes = [C.c_char_p, C.c_char_p, i32, i32, vp]
     L.rvh_fetch_ref.restype = i64
     L.rvh_call_regions.argtypes = [vp, C.POINTER(Params), vp, C.POINTER(Region), i32, vp, i32, i64, C.c_int,
                                    C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(i64), C.POINTER(Timing)]
+    L.rvh_install_patch.argtypes = [vp, C.POINTER(Params), vp, C.POINTER(Region), i32, vp, i32, i64]
+    L.rv_variant_count.argtypes = [vp]
+    L.rv_variant_count.restype = i64
     L.rvh_last_error.restype = C.c_char_p
 
 
@@ -224,6 +231,11 @@ class HostBatch:
         import numpy as np
         n = self.pool_bytes
         return np.ctypeslib.as_array(C.cast(self.pool_ptr, C.POINTER(C.c_uint8)), shape=(n,)) if n else np.zeros(0, np.uint8)
+
+    def pin(self):
+        rc = lib().rvh_batch_pin(self._h)
+        if rc != 0:
+            raise RabbitVarError("rvh_batch_pin: " + lib().rvh_last_error().decode())
 
     def make_regions(self, starts, ends, ref_extension=1200, read_offset=0, n_reads_sample=-1):
         n = len(starts)
@@ -342,8 +354,33 @@ class Context:
         lib().rv_last_kernel_ms(self._h, C.byref(a), C.byref(b))
         return a.value, b.value
 
+    def timer_start(self):
+        self._ck(lib().rv_timer_start(self._h), "rv_timer_start")
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(lib().rv_timer_stop(self._h, C.byref(ms)), "rv_timer_stop")
+        return ms.value
+
+    def apply_patch_raw(self, entries_ptr, n_entries):
+        self._ck(lib().rv_apply_patch(self._h, entries_ptr, n_entries, None, None, None, 0), "rv_apply_patch")
+
     def launch_count(self):
         return lib().rv_launch_count(self._h)
+
+    def n_variants(self):
+        return lib().rv_variant_count(self._h)
+
+    def install_patch_from_events(self, batch, regions, ref_bases, ref_lo):
+        rc = lib().rvh_install_patch(self._h, C.byref(self.params), batch._h, regions, len(regions),
+                                     C.cast(C.c_char_p(ref_bases), C.c_void_p), ref_lo, len(ref_bases))
+        if rc != 0:
+            raise RabbitVarError(f"rvh_install_patch failed ({rc}): {lib().rvh_last_error().decode()}")
+
+    def call_regions_range(self, batch, regions, lo, hi, ref_bases, ref_lo, sample, chrom, push_reference=False):
+        """call_regions over regions[lo:hi] of a ctypes Region array."""
+        sub = (Region * (hi - lo)).from_address(C.addressof(regions) + lo * C.sizeof(Region))
+        return self.call_regions(batch, sub, ref_bases, ref_lo, sample, chrom, push_reference)
 
     def call_regions(self, batch, regions, ref_bases, ref_lo, sample, chrom, push_reference=True, params=None):
         """Host buffers in, TSV text out: the batch-level replacement of one_region_run."""

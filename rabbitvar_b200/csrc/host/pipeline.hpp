@@ -25,6 +25,75 @@ inline double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+struct Handoff {
+  std::vector<std::vector<rv_patch_entry> > patches;  // per region
+  std::vector<size_t> bases;                          // offset of each region's entries in the uploaded list
+};
+
+// After rv_pileup: events + dense tables D2H, BAM-order reduce of the sparse keys, host realigner,
+// write-back of the result as the patch list (rv_apply_patch).
+inline int host_handoff(rv_ctx* ctx, const rv_params& P, const ReadBatch& batch, const std::vector<rv_region>& regs,
+                        const std::string& refseq, int32_t ref_lo, Handoff* out, BatchTiming* t, std::string* err) {
+  int rc;
+#define RV_STEP(x)                                                  \
+  do {                                                              \
+    rc = (x);                                                       \
+    if (rc != RV_OK) {                                              \
+      if (err) *err = std::string(#x) + ": " + rv_last_error(ctx);  \
+      return rc;                                                    \
+    }                                                               \
+  } while (0)
+  double t2 = now_ms();
+  const rv_event* ev;
+  int64_t nev;
+  RV_STEP(rv_fetch_events(ctx, &ev, &nev));
+  const int32_t* mrl;
+  int32_t nmrl;
+  RV_STEP(rv_fetch_max_read_len(ctx, &mrl, &nmrl));
+  std::vector<RegionPileup> rp(regs.size());
+  for (size_t r = 0; r < regs.size(); ++r) {
+    RegionPileup& R = rp[r];
+    const uint32_t *c, *cv;
+    RV_STEP(rv_fetch_tables(ctx, (int32_t)r, &c, &cv, &R.first_pos, &R.n_pos));
+    R.region_idx = (int)r;
+    R.start = regs[r].start;
+    R.end = regs[r].end;
+    R.counts.assign(c, c + (size_t)R.n_pos * RV_POS_U32);
+    R.cov.assign(cv, cv + R.n_pos);
+    R.max_read_len = mrl[r];
+    t->d2h_bytes += (int64_t)R.n_pos * (RV_POS_U32 + 1) * 4;
+  }
+  t->d2h_bytes += nev * (int64_t)sizeof(rv_event);
+  double t3 = now_ms();
+  reduce_events(ev, nev, batch, P.goodq, rp);
+  rvk::RefView refv;
+  refv.bases = refseq.data();
+  refv.base_pos = ref_lo;
+  refv.n = (int64_t)refseq.size();
+  out->patches.assign(regs.size(), std::vector<rv_patch_entry>());
+  out->bases.clear();
+  std::vector<rv_patch_entry> all;
+  std::vector<int32_t> creg, cpos, cval;
+  for (size_t r = 0; r < regs.size(); ++r) {
+    refv.lo = regs[r].ref_lo;
+    refv.hi = regs[r].ref_hi;
+    realign_region(P, rp[r], refv, regs[r].chr_len);
+    build_patch(rp[r], &out->patches[r]);
+    out->bases.push_back(all.size());
+    all.insert(all.end(), out->patches[r].begin(), out->patches[r].end());
+    collect_cov_patch(rp[r], &creg, &cpos, &cval);
+  }
+  double t4 = now_ms();
+  RV_STEP(rv_apply_patch(ctx, all.data(), (int64_t)all.size(), creg.data(), cpos.data(), cval.data(), (int64_t)creg.size()));
+  t->h2d_bytes += (int64_t)all.size() * (int64_t)sizeof(rv_patch_entry) + (int64_t)creg.size() * 12;
+  double t5 = now_ms();
+  t->fetch_ms = t3 - t2;
+  t->host_ms = t4 - t3;
+  t->patch_ms = t5 - t4;
+#undef RV_STEP
+  return RV_OK;
+}
+
 // Runs every region of `regs` (all on one contig) through the path; appends the TSV lines of simple mode.
 // `genes[i]` is the BED name column of region i.  Returns an rv_* error code.
 inline int run_batch_simple(rv_ctx* ctx, const rv_params& P, const ReadBatch& batch, const std::vector<rv_region>& regs,
@@ -53,48 +122,15 @@ inline int run_batch_simple(rv_ctx* ctx, const rv_params& P, const ReadBatch& ba
   RV_STEP(rv_pileup(ctx));
   RV_STEP(rv_get_pileup_stats(ctx, &t.stats));
   double t2 = now_ms();
-  const rv_event* ev;
-  int64_t nev;
-  RV_STEP(rv_fetch_events(ctx, &ev, &nev));
-  const int32_t* mrl;
-  int32_t nmrl;
-  RV_STEP(rv_fetch_max_read_len(ctx, &mrl, &nmrl));
-  std::vector<RegionPileup> rp(regs.size());
-  for (size_t r = 0; r < regs.size(); ++r) {
-    RegionPileup& R = rp[r];
-    const uint32_t *c, *cv;
-    RV_STEP(rv_fetch_tables(ctx, (int32_t)r, &c, &cv, &R.first_pos, &R.n_pos));
-    R.region_idx = (int)r;
-    R.start = regs[r].start;
-    R.end = regs[r].end;
-    R.counts.assign(c, c + (size_t)R.n_pos * RV_POS_U32);
-    R.cov.assign(cv, cv + R.n_pos);
-    R.max_read_len = mrl[r];
-    t.d2h_bytes += (int64_t)R.n_pos * (RV_POS_U32 + 1) * 4;
-  }
-  t.d2h_bytes += nev * (int64_t)sizeof(rv_event);
-  double t3 = now_ms();
-  reduce_events(ev, nev, batch, P.goodq, rp);
+  Handoff ho;
+  rc = host_handoff(ctx, P, batch, regs, refseq, ref_lo, &ho, &t, err);
+  if (rc != RV_OK) return rc;
+  std::vector<std::vector<rv_patch_entry> >& patches = ho.patches;
+  std::vector<size_t>& bases = ho.bases;
   rvk::RefView refv;
   refv.bases = refseq.data();
   refv.base_pos = ref_lo;
   refv.n = (int64_t)refseq.size();
-  std::vector<std::vector<rv_patch_entry> > patches(regs.size());
-  std::vector<rv_patch_entry> all;
-  std::vector<size_t> bases;
-  std::vector<int32_t> creg, cpos, cval;
-  for (size_t r = 0; r < regs.size(); ++r) {
-    refv.lo = regs[r].ref_lo;
-    refv.hi = regs[r].ref_hi;
-    realign_region(P, rp[r], refv, regs[r].chr_len);
-    build_patch(rp[r], &patches[r]);
-    bases.push_back(all.size());
-    all.insert(all.end(), patches[r].begin(), patches[r].end());
-    collect_cov_patch(rp[r], &creg, &cpos, &cval);
-  }
-  double t4 = now_ms();
-  RV_STEP(rv_apply_patch(ctx, all.data(), (int64_t)all.size(), creg.data(), cpos.data(), cval.data(), (int64_t)creg.size()));
-  t.h2d_bytes += (int64_t)all.size() * (int64_t)sizeof(rv_patch_entry) + (int64_t)creg.size() * 12;
   double t5 = now_ms();
   RV_STEP(rv_score(ctx));
   const rv_variant* vv;
@@ -107,6 +143,7 @@ inline int run_batch_simple(rv_ctx* ctx, const rv_params& P, const ReadBatch& ba
     int64_t j = i;
     while (j < nv && vv[j].region == vv[i].region && vv[j].pos == vv[i].pos) ++j;
     const size_t r = (size_t)vv[i].region;
+    if (j - i == 1 && vv[i].is_ref && !P.pileup) { i = j; continue; }  // SimpleMode::output skips variant-less positions
     group.assign(vv + i, vv + j);
     for (size_t k = 0; k < group.size(); ++k)
       if (group[k].key_kind == 1) group[k].key_id -= (int32_t)bases[r];
@@ -120,7 +157,7 @@ inline int run_batch_simple(rv_ctx* ctx, const rv_params& P, const ReadBatch& ba
     i = j;
   }
   double t7 = now_ms();
-  t.push_ms = t1 - t0; t.pileup_ms = t2 - t1; t.fetch_ms = t3 - t2; t.host_ms = t4 - t3; t.patch_ms = t5 - t4;
+  t.push_ms = t1 - t0; t.pileup_ms = t2 - t1;
   t.score_ms = t6 - t5; t.assemble_ms = t7 - t6;
   t.n_variants = nv;
   rv_last_kernel_ms(ctx, &t.pileup_kernel_ms, &t.score_kernel_ms);

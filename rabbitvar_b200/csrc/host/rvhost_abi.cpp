@@ -6,8 +6,18 @@
 
 using namespace rvhost;
 
+#include <cuda_runtime_api.h>
+
 struct rvh_batch {
   ReadBatch b;
+  bool pinned;
+  rvh_batch() : pinned(false) {}
+  ~rvh_batch() {
+    if (pinned) {
+      cudaHostUnregister((void*)b.reads.data());
+      cudaHostUnregister((void*)b.pool.data());
+    }
+  }
 };
 
 static thread_local std::string g_err;
@@ -54,6 +64,18 @@ const rv_read* rvh_batch_reads(const rvh_batch* b) { return b->b.reads.data(); }
 const uint8_t* rvh_batch_pool(const rvh_batch* b) { return b->b.pool.data(); }
 int64_t rvh_batch_pool_bytes(const rvh_batch* b) { return (int64_t)b->b.pool.size(); }
 int32_t rvh_batch_max_ref_span(const rvh_batch* b) { return b->b.max_ref_span; }
+int rvh_batch_pin(rvh_batch* b) {
+  if (!b) return RV_ERR_ARG;
+  if (b->pinned || b->b.reads.empty()) return RV_OK;
+  if (cudaHostRegister((void*)b->b.reads.data(), b->b.reads.size() * sizeof(rv_read), cudaHostRegisterDefault) != cudaSuccess ||
+      cudaHostRegister((void*)b->b.pool.data(), b->b.pool.size(), cudaHostRegisterDefault) != cudaSuccess) {
+    g_err = "cudaHostRegister failed";
+    cudaGetLastError();
+    return RV_ERR_CUDA;
+  }
+  b->pinned = true;
+  return RV_OK;
+}
 void rvh_batch_free(rvh_batch* b) { delete b; }
 
 int rvh_make_regions(const rvh_batch* b, const int32_t* starts, const int32_t* ends, int32_t n, int32_t chr_len,
@@ -96,6 +118,25 @@ int64_t rvh_fetch_ref(const char* fasta_path, const char* chr, int32_t lo, int32
   } catch (const std::exception& e) {
     g_err = e.what();
     return -1;
+  }
+}
+
+int rvh_install_patch(rv_ctx* ctx, const rv_params* params, const rvh_batch* batch, const rv_region* regions,
+                      int32_t n_regions, const char* ref_bases, int32_t ref_lo, int64_t ref_n) {
+  if (!ctx || !params || !batch || !regions || !ref_bases) return RV_ERR_ARG;
+  try {
+    std::vector<rv_region> regs(regions, regions + n_regions);
+    std::string refseq(ref_bases, (size_t)ref_n);
+    Handoff ho;
+    BatchTiming t;
+    memset(&t, 0, sizeof t);
+    std::string err;
+    int rc = host_handoff(ctx, *params, batch->b, regs, refseq, ref_lo, &ho, &t, &err);
+    if (rc != RV_OK) g_err = err;
+    return rc;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return RV_ERR_STATE;
   }
 }
 

@@ -301,7 +301,7 @@ struct rv_ctx {
   rv_params P;
   rv_limits L;
   cudaStream_t stream;
-  cudaEvent_t ev0, ev1;
+  cudaEvent_t ev0, ev1, tev0, tev1;
   std::string err;
   int64_t launches;
   // device buffers
@@ -424,6 +424,8 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&ctx->ev0));
   CK(cudaEventCreate(&ctx->ev1));
+  CK(cudaEventCreate(&ctx->tev0));
+  CK(cudaEventCreate(&ctx->tev1));
   const rv_limits& L = ctx->L;
   CK(cudaMalloc(&ctx->d_reads, sizeof(rv_read) * (size_t)L.max_reads));
   CK(cudaMalloc(&ctx->d_pool, (size_t)L.max_read_bytes));
@@ -464,6 +466,8 @@ void rv_destroy(rv_ctx* ctx) {
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->tev0) cudaEventDestroy(ctx->tev0);
+  if (ctx->tev1) cudaEventDestroy(ctx->tev1);
   delete ctx;
 }
 
@@ -575,7 +579,8 @@ int rv_pileup(rv_ctx* ctx) {
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaEventElapsedTime(&ctx->pileup_ms, ctx->ev0, ctx->ev1));
   ctx->h_stats.n_items = (unsigned long long)ctx->n_items;
-  ctx->have_patch = false;
+  // the patch list stays attached until rv_set_regions / the next rv_apply_patch: a caller that
+  // re-runs the same resident batch may score against it again
   ctx->tables_fetched = false;
   if (ctx->h_stats.n_overflow) return fail(ctx, RV_ERR_OVERFLOW, "pileup dropped observations (halo/event buffer too small)");
   return RV_OK;
@@ -785,6 +790,8 @@ int rv_fetch_variants(rv_ctx* ctx, const rv_variant** variants, int64_t* n_varia
   return RV_OK;
 }
 
+int64_t rv_variant_count(const rv_ctx* ctx) { return ctx ? (int64_t)ctx->h_stats.n_variants : 0; }
+
 int rv_fisher_exact(rv_ctx* ctx, const int32_t* tables, int64_t n, double* out) {
   if (!ctx || (!tables && n) || (!out && n) || n < 0) return RV_ERR_ARG;
   if (n == 0) return RV_OK;
@@ -809,6 +816,22 @@ int rv_last_kernel_ms(rv_ctx* ctx, float* pileup_ms, float* score_ms) {
   if (!ctx) return RV_ERR_ARG;
   if (pileup_ms) *pileup_ms = ctx->pileup_ms;
   if (score_ms) *score_ms = ctx->score_ms;
+  return RV_OK;
+}
+
+int rv_timer_start(rv_ctx* ctx) {
+  if (!ctx) return RV_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->tev0, ctx->stream));
+  return RV_OK;
+}
+
+int rv_timer_stop(rv_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return RV_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->tev1, ctx->stream));
+  CK(cudaEventSynchronize(ctx->tev1));
+  CK(cudaEventElapsedTime(ms, ctx->tev0, ctx->tev1));
   return RV_OK;
 }
 
