@@ -247,7 +247,7 @@ def main():
     n_pos = sum(e - s + 1 + 2 * halo for s, e in tiles) * 2
     lim = rv.default_limits(max_reads=bt.n_reads + 64, max_read_bytes=bt.pool_bytes + 256, max_positions=n_pos + 64,
                             max_regions=nreg + 8, halo=halo, max_events=max(1 << 20, bt.n_reads),
-                            max_variants=n_pos + 1024, max_patch=max(1 << 20, bt.n_reads // 2),
+                            max_variants=3 * n_pos + 1024, max_patch=max(1 << 20, bt.n_reads // 2),
                             max_ref_bases=len(ref) + 64)
     params = rv.default_params(fisher=1, has_bam2=1)
     ctx = rv.Context(local, params, lim)
