@@ -59,6 +59,10 @@ typedef struct rv_params {
   uint8_t pileup;          /* -p */
   uint8_t fisher;          /* --fisher */
   uint8_t has_bam2;        /* somatic: second BAM present (ToVarsBuilder.cpp:170-175,213-233) */
+  uint8_t candidates_only; /* scoring emits a position only if one of its variants passes the numeric part of
+                              Variant::isGoodVar (freq, hicnt, pmean, qual, qratio: include/Variant.h:205-231) —
+                              exact for simple-mode output, which prints nothing else (simpleMode.cpp:176-190) */
+  uint8_t pad_[7];
 } rv_params;
 
 void rv_default_params(rv_params* p);
@@ -201,6 +205,9 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
 void rv_destroy(rv_ctx* ctx);
 const char* rv_last_error(const rv_ctx* ctx);
 int rv_sync(rv_ctx* ctx);
+/* Table halo (limits.halo) of the context, and replacement of its parameter block between batches. */
+int32_t rv_ctx_halo(const rv_ctx* ctx);
+int rv_set_params(rv_ctx* ctx, const rv_params* params);
 
 /* ---- inputs ---------------------------------------------------------------------------------- */
 /* Reference bases [ref_start, ref_start+n) of the contig being processed, upper-case ASCII. */
@@ -235,6 +242,9 @@ int rv_fetch_max_read_len(rv_ctx* ctx, const int32_t** out, int32_t* n);
  * counts: RV_POS_U32 u32 per position; cov: 1 u32 per position. Host copies (pinned, library-owned). */
 int rv_fetch_tables(rv_ctx* ctx, int32_t region, const uint32_t** counts, const uint32_t** cov,
                     int32_t* first_pos, int32_t* n_pos);
+/* Gather of selected dense rows: for each (region[i], pos[i]) 33 u32 = RV_POS_U32 counts + coverage.
+ * Positions outside the region's table come back as zeros. Host pointers in, library-owned pinned buffer out. */
+int rv_fetch_rows(rv_ctx* ctx, const int32_t* region, const int32_t* pos, int64_t n, const uint32_t** rows);
 int rv_fetch_events(rv_ctx* ctx, const rv_event** events, int64_t* n_events);
 /* Replace/insert accumulators before scoring (realigner write-back): dense single-base keys update the
  * dense row, everything else goes to the per-position patch list; cov_pos/cov_val overwrite coverage. */

@@ -44,7 +44,8 @@ typedef struct rvh_timing {
   int64_t n_items, n_reads_kept, n_aligned_bases, n_events, n_unsupported, n_variants, n_lines, h2d_bytes, d2h_bytes;
 } rvh_timing;
 int rvh_call_regions(rv_ctx* ctx, const rv_params* params, const rvh_batch* batch, const rv_region* regions,
-                     int32_t n_regions, const char* ref_bases, int32_t ref_lo, int64_t ref_n, int push_reference,
+                     int32_t n_regions, const char* ref_bases, int32_t ref_lo, int64_t ref_n,
+                     int push_flags /* bit0: upload the reference, bit1: upload the reads (else reuse resident) */,
                      const char* sample, const char* chr, const char** tsv_out, int64_t* tsv_len, rvh_timing* timing);
 /* The host hand-off alone, for a batch that is already resident and piled up on ctx (after rv_pileup):
  * events/tables D2H, BAM-order reduce, host realigner, patch write-back (rv_apply_patch). */

@@ -48,7 +48,8 @@ class Params(C.Structure):
                 ("minmatch", C.c_int32), ("trim_bases_after", C.c_int32), ("indelsize", C.c_int32),
                 ("mapping_quality", C.c_int32), ("samfilter", C.c_int32), ("local_realign", C.c_uint8),
                 ("move3", C.c_uint8), ("uniq_u", C.c_uint8), ("uniq_un", C.c_uint8), ("dedup", C.c_uint8),
-                ("pileup", C.c_uint8), ("fisher", C.c_uint8), ("has_bam2", C.c_uint8)]
+                ("pileup", C.c_uint8), ("fisher", C.c_uint8), ("has_bam2", C.c_uint8), ("candidates_only", C.c_uint8),
+                ("pad_", C.c_uint8 * 7)]
 
 
 class Limits(C.Structure):
@@ -109,8 +110,9 @@ class Timing(C.Structure):
 # every symbol include/*.h declares (checked by tests without a GPU)
 ABI_SYMBOLS = [
     "rv_abi_version", "rv_device_count", "rv_default_params", "rv_default_limits", "rv_create", "rv_destroy",
-    "rv_last_error", "rv_sync", "rv_set_reference", "rv_push_reads", "rv_push_reads_device", "rv_set_regions",
-    "rv_pileup", "rv_score", "rv_get_pileup_stats", "rv_fetch_max_read_len", "rv_fetch_tables", "rv_fetch_events",
+    "rv_last_error", "rv_sync", "rv_ctx_halo", "rv_set_params", "rv_set_reference", "rv_push_reads", "rv_push_reads_device", "rv_set_regions",
+    "rv_pileup", "rv_score", "rv_get_pileup_stats", "rv_fetch_max_read_len", "rv_fetch_tables", "rv_fetch_rows",
+    "rv_fetch_events",
     "rv_apply_patch", "rv_fetch_variants", "rv_variant_count", "rv_fisher_exact", "rv_last_kernel_ms", "rv_timer_start",
     "rv_timer_stop", "rv_launch_count",
     "rvh_load_bam", "rvh_batch_append", "rvh_batch_n_reads", "rvh_batch_reads", "rvh_batch_pool",
@@ -130,6 +132,9 @@ def _declare(L):
     L.rv_last_error.argtypes = [vp]
     L.rv_last_error.restype = C.c_char_p
     L.rv_sync.argtypes = [vp]
+    L.rv_ctx_halo.argtypes = [vp]
+    L.rv_ctx_halo.restype = i32
+    L.rv_set_params.argtypes = [vp, C.POINTER(Params)]
     L.rv_set_reference.argtypes = [vp, i32, i64, vp]
     L.rv_push_reads.argtypes = [vp, C.POINTER(ReadBatch)]
     L.rv_push_reads_device.argtypes = [vp, C.POINTER(ReadBatch)]
@@ -140,6 +145,7 @@ def _declare(L):
     L.rv_fetch_max_read_len.argtypes = [vp, C.POINTER(C.POINTER(i32)), C.POINTER(i32)]
     L.rv_fetch_tables.argtypes = [vp, i32, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_uint32)),
                                   C.POINTER(i32), C.POINTER(i32)]
+    L.rv_fetch_rows.argtypes = [vp, vp, vp, i64, C.POINTER(C.POINTER(C.c_uint32))]
     L.rv_fetch_events.argtypes = [vp, C.POINTER(C.POINTER(Event)), C.POINTER(i64)]
     L.rv_apply_patch.argtypes = [vp, vp, i64, vp, vp, vp, i64]
     L.rv_fetch_variants.argtypes = [vp, C.POINTER(C.POINTER(Variant)), C.POINTER(i64)]
@@ -290,6 +296,10 @@ class Context:
         if rc != 0:
             raise RabbitVarError(f"{what} failed ({rc}): {lib().rv_last_error(self._h).decode()}")
 
+    def set_params(self, params):
+        self.params = params
+        self._ck(lib().rv_set_params(self._h, C.byref(params)), "rv_set_params")
+
     def set_reference(self, ref_start, bases):
         self._ref_keep = bases
         self._ck(lib().rv_set_reference(self._h, ref_start, len(bases), C.cast(C.c_char_p(bases), C.c_void_p)),
@@ -377,12 +387,14 @@ class Context:
         if rc != 0:
             raise RabbitVarError(f"rvh_install_patch failed ({rc}): {lib().rvh_last_error().decode()}")
 
-    def call_regions_range(self, batch, regions, lo, hi, ref_bases, ref_lo, sample, chrom, push_reference=False):
+    def call_regions_range(self, batch, regions, lo, hi, ref_bases, ref_lo, sample, chrom, push_reference=False,
+                           push_reads=True):
         """call_regions over regions[lo:hi] of a ctypes Region array."""
         sub = (Region * (hi - lo)).from_address(C.addressof(regions) + lo * C.sizeof(Region))
-        return self.call_regions(batch, sub, ref_bases, ref_lo, sample, chrom, push_reference)
+        return self.call_regions(batch, sub, ref_bases, ref_lo, sample, chrom, push_reference, push_reads=push_reads)
 
-    def call_regions(self, batch, regions, ref_bases, ref_lo, sample, chrom, push_reference=True, params=None):
+    def call_regions(self, batch, regions, ref_bases, ref_lo, sample, chrom, push_reference=True, params=None,
+                     push_reads=True):
         """Host buffers in, TSV text out: the batch-level replacement of one_region_run."""
         out = C.c_char_p()
         n = C.c_int64()
@@ -390,7 +402,8 @@ class Context:
         p = params or self.params
         rc = lib().rvh_call_regions(self._h, C.byref(p), batch._h, regions, len(regions),
                                     C.cast(C.c_char_p(ref_bases), C.c_void_p), ref_lo, len(ref_bases),
-                                    1 if push_reference else 0, sample.encode(), chrom.encode(), C.byref(out),
+                                    (1 if push_reference else 0) | (2 if push_reads else 0), sample.encode(),
+                                    chrom.encode(), C.byref(out),
                                     C.byref(n), C.byref(tm))
         if rc != 0:
             raise RabbitVarError(f"rvh_call_regions failed ({rc}): {lib().rvh_last_error().decode()}")

@@ -94,6 +94,7 @@ static bool parse(int argc, char** argv, Cli& c) {
     else { fprintf(stderr, "unrecognized option: %s\n", a.c_str()); usage(); exit(1); }
   }
   if (c.P.pileup) { c.P.freq = -1; c.P.minr = 0; }  // Launcher.cpp:455-459
+  c.P.candidates_only = c.P.pileup ? 0 : 1;         // simple-mode output prints only passing variants
   if (c.fasta.empty() || c.bam.empty()) { usage(); return false; }
   if (c.bam.find('|') != std::string::npos) {
     fprintf(stderr, "rabbitvar_b200: somatic pairing (-b 'T|N') is not wired into this front end yet\n");
@@ -229,7 +230,7 @@ static void worker(const Cli& c, int device, std::vector<Block*> blocks) {
       std::vector<std::string> genes;
       for (auto& s : blk->specs) genes.push_back(s.gene);
       BatchTiming tm;
-      int rc = run_batch_simple(ctx, c.P, batch, regs, genes, refseq, ref_lo, c.sample, chr, true, &blk->tsv, &tm, &blk->err);
+      int rc = run_batch_simple(ctx, c.P, batch, regs, genes, refseq, ref_lo, c.sample, chr, 3, L.halo, &blk->tsv, &tm, &blk->err);
       if (rc != RV_OK) continue;
       blk->bases = tm.stats.n_aligned_bases;
       blk->reads = tm.stats.n_reads_kept;

@@ -9,6 +9,7 @@
 #pragma once
 #include "../../../include/rabbitvar_b200.h"
 #include "batch_loader.hpp"
+#include <array>
 #include <map>
 #include <set>
 #include <string>
@@ -78,11 +79,16 @@ inline void add_obs(Variation& v, bool dir, int tp, double q, int mapq, int nm, 
 struct RegionPileup {
   int region_idx;
   int32_t start, end;
-  // dense device tables (copied so the realigner can edit them)
+  // dense device tables: either a full copy (tests / dumps: `dense`) or only the rows the host stage
+  // asked for (rv_fetch_rows), keyed by position: 32 count words + coverage
   int32_t first_pos, n_pos;
-  std::vector<uint32_t> counts;  // n_pos * RV_POS_U32
-  std::vector<uint32_t> cov;     // n_pos
+  bool dense;
+  std::vector<uint32_t> counts;  // n_pos * RV_POS_U32 when dense
+  std::vector<uint32_t> cov;     // n_pos when dense
+  std::map<int, std::array<uint32_t, 33> > srows;
+  int64_t row_misses;            // accesses to rows that were not fetched (must stay 0)
   int max_read_len;
+  RegionPileup() : region_idx(0), start(0), end(0), first_pos(0), n_pos(0), dense(true), row_misses(0), max_read_len(0) {}
   // sparse accumulators
   std::map<int, KeyMap> ni;   // nonInsertionVariants, multi-character keys (and overridden dense keys)
   std::map<int, KeyMap> ins;  // insertionVariants
@@ -93,9 +99,20 @@ struct RegionPileup {
   std::set<std::pair<int, char> > erased_dense;
 
   bool in_table(int pos) const { return pos >= first_pos && pos < first_pos + n_pos; }
-  uint32_t* row(int pos, int allele) { return counts.data() + ((size_t)(pos - first_pos) * 4 + allele) * RV_ROW_U32; }
-  const uint32_t* row(int pos, int allele) const {
-    return counts.data() + ((size_t)(pos - first_pos) * 4 + allele) * RV_ROW_U32;
+  uint32_t* row(int pos, int allele) {
+    if (dense) return counts.data() + ((size_t)(pos - first_pos) * 4 + allele) * RV_ROW_U32;
+    std::map<int, std::array<uint32_t, 33> >::iterator it = srows.find(pos);
+    if (it == srows.end()) {
+      row_misses++;
+      std::array<uint32_t, 33> z;
+      z.fill(0);
+      it = srows.insert(std::make_pair(pos, z)).first;
+    }
+    return it->second.data() + allele * RV_ROW_U32;
+  }
+  uint32_t& cov_at(int pos) {
+    if (dense) return cov[(size_t)(pos - first_pos)];
+    return row(pos, 0)[32];
   }
   static bool row_exists(const uint32_t* r) {
     uint32_t o = 0;

@@ -33,7 +33,8 @@ struct Handoff {
 // After rv_pileup: events + dense tables D2H, BAM-order reduce of the sparse keys, host realigner,
 // write-back of the result as the patch list (rv_apply_patch).
 inline int host_handoff(rv_ctx* ctx, const rv_params& P, const ReadBatch& batch, const std::vector<rv_region>& regs,
-                        const std::string& refseq, int32_t ref_lo, Handoff* out, BatchTiming* t, std::string* err) {
+                        const std::string& refseq, int32_t ref_lo, int halo, Handoff* out, BatchTiming* t,
+                        std::string* err) {
   int rc;
 #define RV_STEP(x)                                                  \
   do {                                                              \
@@ -53,15 +54,35 @@ inline int host_handoff(rv_ctx* ctx, const rv_params& P, const ReadBatch& batch,
   std::vector<RegionPileup> rp(regs.size());
   for (size_t r = 0; r < regs.size(); ++r) {
     RegionPileup& R = rp[r];
-    const uint32_t *c, *cv;
-    RV_STEP(rv_fetch_tables(ctx, (int32_t)r, &c, &cv, &R.first_pos, &R.n_pos));
     R.region_idx = (int)r;
     R.start = regs[r].start;
     R.end = regs[r].end;
-    R.counts.assign(c, c + (size_t)R.n_pos * RV_POS_U32);
-    R.cov.assign(cv, cv + R.n_pos);
+    R.first_pos = regs[r].start - halo;
+    R.n_pos = regs[r].end - regs[r].start + 1 + 2 * halo;
+    R.dense = false;
     R.max_read_len = mrl[r];
-    t->d2h_bytes += (int64_t)R.n_pos * (RV_POS_U32 + 1) * 4;
+  }
+  // dense rows the host stage will look at: around multi-nucleotide keys (adjustMNP reads the single-base
+  // keys left/right of an MNV, VariationRealigner.cpp:357-399) and under TTREF observations
+  {
+    std::vector<int32_t> qreg, qpos;
+    std::set<std::pair<int, int> > seen;
+    for (int64_t i = 0; i < nev; ++i) {
+      const rv_event& e = ev[i];
+      int lo = 0, hi = -1;
+      if (e.kind == RV_EV_NI && (e.flags & RV_EVF_MNP)) { lo = e.pos - 1; hi = e.pos + e.keylen + 1; }
+      else if (e.kind == RV_EV_TTREF) { lo = hi = e.pos; }
+      for (int p = lo; p <= hi; ++p)
+        if (seen.insert(std::make_pair(e.region, p)).second) { qreg.push_back(e.region); qpos.push_back(p); }
+    }
+    const uint32_t* rows = NULL;
+    RV_STEP(rv_fetch_rows(ctx, qreg.data(), qpos.data(), (int64_t)qreg.size(), &rows));
+    for (size_t i = 0; i < qreg.size(); ++i) {
+      std::array<uint32_t, 33> a;
+      memcpy(a.data(), rows + i * 33, sizeof(uint32_t) * 33);
+      rp[(size_t)qreg[i]].srows[qpos[i]] = a;
+    }
+    t->d2h_bytes += (int64_t)qreg.size() * 33 * 4;
   }
   t->d2h_bytes += nev * (int64_t)sizeof(rv_event);
   double t3 = now_ms();
@@ -78,6 +99,10 @@ inline int host_handoff(rv_ctx* ctx, const rv_params& P, const ReadBatch& batch,
     refv.lo = regs[r].ref_lo;
     refv.hi = regs[r].ref_hi;
     realign_region(P, rp[r], refv, regs[r].chr_len);
+    if (rp[r].row_misses) {
+      if (err) *err = "host stage touched dense rows that were not fetched";
+      return RV_ERR_STATE;
+    }
     build_patch(rp[r], &out->patches[r]);
     out->bases.push_back(all.size());
     all.insert(all.end(), out->patches[r].begin(), out->patches[r].end());
@@ -98,8 +123,8 @@ inline int host_handoff(rv_ctx* ctx, const rv_params& P, const ReadBatch& batch,
 // `genes[i]` is the BED name column of region i.  Returns an rv_* error code.
 inline int run_batch_simple(rv_ctx* ctx, const rv_params& P, const ReadBatch& batch, const std::vector<rv_region>& regs,
                             const std::vector<std::string>& genes, const std::string& refseq, int32_t ref_lo,
-                            const std::string& sample, const std::string& chr, bool push_reference, std::string* tsv,
-                            BatchTiming* tm, std::string* err) {
+                            const std::string& sample, const std::string& chr, int push_flags, int halo,
+                            std::string* tsv, BatchTiming* tm, std::string* err) {
   BatchTiming t;
   memset(&t, 0, sizeof t);
   int rc;
@@ -112,18 +137,21 @@ inline int run_batch_simple(rv_ctx* ctx, const rv_params& P, const ReadBatch& ba
     }                                                               \
   } while (0)
   double t0 = now_ms();
+  const bool push_reference = (push_flags & 1) != 0, push_reads = (push_flags & 2) != 0;
   if (push_reference) RV_STEP(rv_set_reference(ctx, ref_lo, (int64_t)refseq.size(), refseq.data()));
-  rv_read_batch bv = batch.view();
-  RV_STEP(rv_push_reads(ctx, &bv));
+  if (push_reads) {
+    rv_read_batch bv = batch.view();
+    RV_STEP(rv_push_reads(ctx, &bv));
+    t.h2d_bytes += (int64_t)batch.reads.size() * (int64_t)sizeof(rv_read) + (int64_t)batch.pool.size();
+  }
   RV_STEP(rv_set_regions(ctx, regs.data(), (int32_t)regs.size()));
-  t.h2d_bytes += (int64_t)batch.reads.size() * (int64_t)sizeof(rv_read) + (int64_t)batch.pool.size() +
-                 (push_reference ? (int64_t)refseq.size() : 0);
+  t.h2d_bytes += (push_reference ? (int64_t)refseq.size() : 0);
   double t1 = now_ms();
   RV_STEP(rv_pileup(ctx));
   RV_STEP(rv_get_pileup_stats(ctx, &t.stats));
   double t2 = now_ms();
   Handoff ho;
-  rc = host_handoff(ctx, P, batch, regs, refseq, ref_lo, &ho, &t, err);
+  rc = host_handoff(ctx, P, batch, regs, refseq, ref_lo, halo, &ho, &t, err);
   if (rc != RV_OK) return rc;
   std::vector<std::vector<rv_patch_entry> >& patches = ho.patches;
   std::vector<size_t>& bases = ho.bases;

@@ -60,7 +60,7 @@ struct NiView {
   }
   void add_cov(int pos, int n) {
     if (!R.in_table(pos)) return;
-    R.cov[pos - R.first_pos] += (uint32_t)n;
+    R.cov_at(pos) += (uint32_t)n;
     cov_touched.insert(pos);
   }
   std::set<std::pair<int, char> > promoted;
@@ -314,13 +314,13 @@ inline void build_patch(const RegionPileup& R, std::vector<rv_patch_entry>* out)
   }
 }
 
-inline void collect_cov_patch(const RegionPileup& R, std::vector<int32_t>* reg, std::vector<int32_t>* pos,
+inline void collect_cov_patch(RegionPileup& R, std::vector<int32_t>* reg, std::vector<int32_t>* pos,
                               std::vector<int32_t>* val) {
   for (std::set<int>::const_iterator p = R.cov_touched.begin(); p != R.cov_touched.end(); ++p) {
     if (!R.in_table(*p)) continue;
     reg->push_back(R.region_idx);
     pos->push_back(*p);
-    val->push_back((int32_t)R.cov[*p - R.first_pos]);
+    val->push_back((int32_t)R.cov_at(*p));
   }
 }
 

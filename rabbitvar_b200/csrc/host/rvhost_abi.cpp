@@ -131,7 +131,7 @@ int rvh_install_patch(rv_ctx* ctx, const rv_params* params, const rvh_batch* bat
     BatchTiming t;
     memset(&t, 0, sizeof t);
     std::string err;
-    int rc = host_handoff(ctx, *params, batch->b, regs, refseq, ref_lo, &ho, &t, &err);
+    int rc = host_handoff(ctx, *params, batch->b, regs, refseq, ref_lo, rv_ctx_halo(ctx), &ho, &t, &err);
     if (rc != RV_OK) g_err = err;
     return rc;
   } catch (const std::exception& e) {
@@ -141,7 +141,7 @@ int rvh_install_patch(rv_ctx* ctx, const rv_params* params, const rvh_batch* bat
 }
 
 int rvh_call_regions(rv_ctx* ctx, const rv_params* params, const rvh_batch* batch, const rv_region* regions,
-                     int32_t n_regions, const char* ref_bases, int32_t ref_lo, int64_t ref_n, int push_reference,
+                     int32_t n_regions, const char* ref_bases, int32_t ref_lo, int64_t ref_n, int push_flags,
                      const char* sample, const char* chr, const char** tsv_out, int64_t* tsv_len, rvh_timing* timing) {
   if (!ctx || !params || !batch || !regions || !ref_bases || !tsv_out || !tsv_len) return RV_ERR_ARG;
   try {
@@ -150,8 +150,13 @@ int rvh_call_regions(rv_ctx* ctx, const rv_params* params, const rvh_batch* batc
     std::string refseq(ref_bases, (size_t)ref_n);
     std::string tsv, err;
     BatchTiming t;
-    int rc = run_batch_simple(ctx, *params, batch->b, regs, genes, refseq, ref_lo, sample, chr, push_reference != 0, &tsv,
-                              &t, &err);
+    // simple-mode text output only ever prints positions with a passing variant: let the device drop the rest
+    rv_params P = *params;
+    P.candidates_only = P.pileup ? 0 : 1;
+    rv_set_params(ctx, &P);
+    int halo = rv_ctx_halo(ctx);
+    int rc = run_batch_simple(ctx, P, batch->b, regs, genes, refseq, ref_lo, sample, chr, push_flags, halo, &tsv, &t, &err);
+    rv_set_params(ctx, params);
     if (rc != RV_OK) { g_err = err; return rc; }
     std::lock_guard<std::mutex> lk(g_tsv_mu);
     std::string& slot = g_tsv[ctx];

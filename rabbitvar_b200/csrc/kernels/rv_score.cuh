@@ -364,6 +364,19 @@ RV_HDN void score_position(const rv_params& P, const rv_region& R, int region_id
   // note: an insertion whose key is "+X" never equals the 1-char ref base, so `!ins` above is implied
   if (!P.pileup && maxfreq <= P.freq && !P.has_bam2) return;  // :170-175
   if (nv == 0) return;
+  if (P.candidates_only && !P.pileup) {
+    // necessary conditions of Variant::isGoodVar (include/Variant.h:205-231); a position none of whose variants
+    // can pass them prints nothing in simple mode (simpleMode.cpp:176-190)
+    bool any = false;
+    for (int oi = 0; oi < nv; ++oi) {
+      if (vord[oi] == ref_i) continue;
+      const ScoredVar& v = var[vord[oi]];
+      if (v.freq >= P.freq && v.hicnt >= P.minr && v.pmean >= P.read_pos_filter && v.qual >= P.goodq &&
+          v.qratio >= P.qratio)
+        any = true;
+    }
+    if (!any) return;
+  }
   // collectReferenceVariants :730-1098 — numeric part; allele strings / genotype / flanks are host work
   int rfc = 0, rrc = 0;
   if (ref_i >= 0) { rfc = var[ref_i].k->fwd; rrc = var[ref_i].k->rev; }

@@ -280,6 +280,18 @@ __global__ void rv_fisher_kernel(const int32_t* tables, int64_t n, double* out, 
   out[3 * i + 2] = two;
 }
 
+// gather of selected dense rows (33 u32 per position) into a compact buffer
+__global__ void rv_gather_rows_kernel(const int64_t* tab, int64_t n, const uint32_t* counts, const uint32_t* cov,
+                                      uint32_t* out) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 33;
+  int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) % 33);
+  if (i >= n) return;
+  int64_t t = tab[i];
+  uint32_t v = 0;
+  if (t >= 0) v = w < RV_POS_U32 ? counts[(size_t)t * RV_POS_U32 + w] : cov[t];
+  out[(size_t)i * 33 + w] = v;
+}
+
 // scatter of patch groups / coverage overrides / dense-row overrides
 __global__ void rv_patch_scatter_kernel(const int64_t* grp_tab, const uint32_t* grp_first, const uint8_t* grp_n, int64_t n,
                                         uint32_t* patch_first, uint8_t* patch_count) {
@@ -336,6 +348,8 @@ struct rv_ctx {
   bool tables_fetched;
   rv_event* h_events;
   size_t h_events_cap;
+  uint32_t* h_rows;
+  size_t h_rows_cap;
   rv_variant* h_variants;
   size_t h_variants_cap;
   int32_t* h_max_rl;
@@ -415,7 +429,7 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   ctx->d_events = NULL; ctx->d_variants = NULL; ctx->d_patch = NULL; ctx->d_patch_first = NULL;
   ctx->d_patch_count = NULL; ctx->d_regions = NULL; ctx->d_max_rl = NULL; ctx->d_stats = NULL; ctx->d_lgt = NULL;
   ctx->h_counts = NULL; ctx->h_cov = NULL; ctx->h_tab_cap = 0; ctx->h_events = NULL; ctx->h_events_cap = 0;
-  ctx->h_variants = NULL; ctx->h_variants_cap = 0; ctx->h_max_rl = NULL;
+  ctx->h_variants = NULL; ctx->h_variants_cap = 0; ctx->h_max_rl = NULL; ctx->h_rows = NULL; ctx->h_rows_cap = 0;
   ctx->n_reads = 0; ctx->n_positions = 0; ctx->n_items = 0; ctx->have_patch = false; ctx->tables_fetched = false;
   ctx->ref_start = 1; ctx->ref_n = 0; ctx->pileup_ms = ctx->score_ms = 0;
   ctx->reads_dev_view = NULL; ctx->pool_dev_view = NULL;
@@ -461,6 +475,7 @@ void rv_destroy(rv_ctx* ctx) {
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
   if (ctx->h_cov) cudaFreeHost(ctx->h_cov);
   if (ctx->h_events) cudaFreeHost(ctx->h_events);
+  if (ctx->h_rows) cudaFreeHost(ctx->h_rows);
   if (ctx->h_variants) cudaFreeHost(ctx->h_variants);
   if (ctx->h_max_rl) cudaFreeHost(ctx->h_max_rl);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -469,6 +484,14 @@ void rv_destroy(rv_ctx* ctx) {
   if (ctx->tev0) cudaEventDestroy(ctx->tev0);
   if (ctx->tev1) cudaEventDestroy(ctx->tev1);
   delete ctx;
+}
+
+int32_t rv_ctx_halo(const rv_ctx* ctx) { return ctx ? ctx->L.halo : 0; }
+
+int rv_set_params(rv_ctx* ctx, const rv_params* params) {
+  if (!ctx || !params) return RV_ERR_ARG;
+  ctx->P = *params;
+  return RV_OK;
 }
 
 int rv_sync(rv_ctx* ctx) {
@@ -631,12 +654,50 @@ int rv_fetch_tables(rv_ctx* ctx, int32_t region, const uint32_t** counts, const 
   return RV_OK;
 }
 
+int rv_fetch_rows(rv_ctx* ctx, const int32_t* region, const int32_t* pos, int64_t n, const uint32_t** rows) {
+  if (!ctx || !rows || n < 0 || (n && (!region || !pos))) return RV_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  *rows = NULL;
+  if (n == 0) return RV_OK;
+  std::vector<int64_t> tab((size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    int r = region[i];
+    if (r < 0 || r >= (int)ctx->regions.size()) return fail(ctx, RV_ERR_ARG, "rv_fetch_rows: bad region");
+    const DevRegion& d = ctx->regions[r];
+    int idx = pos[i] - d.first_pos;
+    tab[(size_t)i] = (idx >= 0 && idx < d.n_pos) ? d.tab_off + idx : -1;
+  }
+  if ((size_t)n > ctx->h_rows_cap) {
+    if (ctx->h_rows) cudaFreeHost(ctx->h_rows);
+    ctx->h_rows = NULL;
+    CK(cudaMallocHost(&ctx->h_rows, sizeof(uint32_t) * 33 * (size_t)n));
+    ctx->h_rows_cap = (size_t)n;
+  }
+  int64_t* d_tab = NULL;
+  uint32_t* d_out = NULL;
+  CK(cudaMalloc(&d_tab, 8 * (size_t)n));
+  cudaError_t e = cudaMalloc(&d_out, sizeof(uint32_t) * 33 * (size_t)n);
+  if (e != cudaSuccess) { cudaFree(d_tab); return fail(ctx, RV_ERR_NOMEM, "rv_fetch_rows: out of device memory"); }
+  cudaMemcpyAsync(d_tab, tab.data(), 8 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+  int64_t threads = n * 33;
+  rv_gather_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(d_tab, n, ctx->d_counts, ctx->d_cov, d_out);
+  ctx->launches++;
+  cudaMemcpyAsync(ctx->h_rows, d_out, sizeof(uint32_t) * 33 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+  e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_tab);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail(ctx, RV_ERR_CUDA, std::string("rv_fetch_rows: ") + cudaGetErrorString(e));
+  *rows = ctx->h_rows;
+  return RV_OK;
+}
+
 int rv_fetch_events(rv_ctx* ctx, const rv_event** events, int64_t* n_events) {
   if (!ctx || !events || !n_events) return RV_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   size_t n = (size_t)std::min<unsigned long long>(ctx->h_stats.n_events, (unsigned long long)ctx->L.max_events);
   if (n > ctx->h_events_cap) {
     if (ctx->h_events) cudaFreeHost(ctx->h_events);
+  if (ctx->h_rows) cudaFreeHost(ctx->h_rows);
     ctx->h_events = NULL;
     CK(cudaMallocHost(&ctx->h_events, sizeof(rv_event) * n));
     ctx->h_events_cap = n;
