@@ -318,6 +318,10 @@ def main():
             e2e_t.append(dt)
             e2e_tm = tms
     e2e_sec = sum(e2e_t) / len(e2e_t)
+    for nm, t in zip("TN", e2e_tm):
+        log(f"[bench r{rank}] e2e {nm}: push {t.push_ms:.1f} pileup {t.pileup_ms:.1f} fetch {t.fetch_ms:.1f} host {t.host_ms:.1f} "
+            f"patch {t.patch_ms:.1f} score {t.score_ms:.1f} assemble {t.assemble_ms:.1f} ms; events {t.n_events} "
+            f"variants {t.n_variants} lines {t.n_lines}")
     h2d = sum(t.h2d_bytes for t in e2e_tm)
     d2h = sum(t.d2h_bytes for t in e2e_tm)
 

@@ -13,6 +13,7 @@
 #include <map>
 #include <set>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace rvhost {
@@ -138,15 +139,12 @@ struct RegionPileup {
 
 inline int allele_index(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
 
-// Rebuilds the sparse accumulators of every region from the BAM-ordered event list.
-inline void reduce_events(const rv_event* ev, int64_t n, const ReadBatch& batch, double goodq,
-                          std::vector<RegionPileup>& regions) {
+// Rebuilds the sparse accumulators of ONE region from its slice of the BAM-ordered event list.
+inline void reduce_events_region(const rv_event* ev, int64_t n, const ReadBatch& batch, double goodq, RegionPileup& R) {
   Variation* last_ins = NULL;
   uint32_t last_ins_read = 0xffffffffu;
   for (int64_t i = 0; i < n; ++i) {
     const rv_event& e = ev[i];
-    if (e.region < 0 || e.region >= (int)regions.size()) continue;
-    RegionPileup& R = regions[e.region];
     const bool dir = e.dir != 0;
     const double q = e.qsum / (double)e.qcnt;
     std::string key(e.key, e.keylen);
@@ -211,6 +209,47 @@ inline void reduce_events(const rv_event* ev, int64_t n, const ReadBatch& batch,
       default: break;
     }
   }
+}
+
+// Simple static-partition parallel loop over [0, n) on up to `threads` host threads.
+template <class F>
+inline void parallel_for(size_t n, int threads, F f) {
+  if (threads <= 1 || n <= 1) {
+    for (size_t i = 0; i < n; ++i) f(i);
+    return;
+  }
+  std::vector<std::thread> th;
+  size_t nt = std::min<size_t>((size_t)threads, n);
+  for (size_t t = 0; t < nt; ++t)
+    th.emplace_back([=]() {
+      for (size_t i = t; i < n; i += nt) f(i);
+    });
+  for (size_t t = 0; t < th.size(); ++t) th[t].join();
+}
+inline int host_threads() {
+  const char* e = getenv("RV_HOST_THREADS");
+  if (e && atoi(e) > 0) return atoi(e);
+  unsigned hc = std::thread::hardware_concurrency();
+  return hc == 0 ? 4 : (int)std::min(hc, 32u);
+}
+
+// Rebuilds the sparse accumulators of every region (events are sorted by region, then BAM order).
+inline void reduce_events(const rv_event* ev, int64_t n, const ReadBatch& batch, double goodq,
+                          std::vector<RegionPileup>& regions) {
+  std::vector<int64_t> first(regions.size() + 1, n);
+  int64_t i = 0;
+  for (size_t r = 0; r < regions.size(); ++r) {
+    while (i < n && ev[i].region < (int)r) ++i;
+    first[r] = i;
+  }
+  first[regions.size()] = n;
+  for (size_t r = regions.size(); r-- > 0;)
+    if (first[r] > first[r + 1]) first[r] = first[r + 1];
+  parallel_for(regions.size(), host_threads(), [&](size_t r) {
+    int64_t a = first[r], z = first[r + 1];
+    while (z > a && ev[z - 1].region != (int)r) --z;
+    reduce_events_region(ev + a, z - a, batch, goodq, regions[r]);
+  });
 }
 
 }  // namespace rvhost

@@ -48,6 +48,7 @@ inline int host_handoff(rv_ctx* ctx, const rv_params& P, const ReadBatch& batch,
   const rv_event* ev;
   int64_t nev;
   RV_STEP(rv_fetch_events(ctx, &ev, &nev));
+  double t2a = now_ms();
   const int32_t* mrl;
   int32_t nmrl;
   RV_STEP(rv_fetch_max_read_len(ctx, &mrl, &nmrl));
@@ -76,7 +77,11 @@ inline int host_handoff(rv_ctx* ctx, const rv_params& P, const ReadBatch& batch,
         if (seen.insert(std::make_pair(e.region, p)).second) { qreg.push_back(e.region); qpos.push_back(p); }
     }
     const uint32_t* rows = NULL;
+    double t2b = now_ms();
     RV_STEP(rv_fetch_rows(ctx, qreg.data(), qpos.data(), (int64_t)qreg.size(), &rows));
+    if (getenv("RV_TRACE"))
+      fprintf(stderr, "[trace] fetch_events %.1f ms (%lld), interest set %.1f ms (%zu rows), fetch_rows %.1f ms\n", t2a - t2,
+              (long long)nev, t2b - t2a, qreg.size(), now_ms() - t2b);
     for (size_t i = 0; i < qreg.size(); ++i) {
       std::array<uint32_t, 33> a;
       memcpy(a.data(), rows + i * 33, sizeof(uint32_t) * 33);
@@ -95,15 +100,20 @@ inline int host_handoff(rv_ctx* ctx, const rv_params& P, const ReadBatch& batch,
   out->bases.clear();
   std::vector<rv_patch_entry> all;
   std::vector<int32_t> creg, cpos, cval;
+  std::vector<int> bad(regs.size(), 0);
+  parallel_for(regs.size(), host_threads(), [&](size_t r) {
+    rvk::RefView rv = refv;
+    rv.lo = regs[r].ref_lo;
+    rv.hi = regs[r].ref_hi;
+    realign_region(P, rp[r], rv, regs[r].chr_len);
+    if (rp[r].row_misses) bad[r] = 1;
+    build_patch(rp[r], &out->patches[r]);
+  });
   for (size_t r = 0; r < regs.size(); ++r) {
-    refv.lo = regs[r].ref_lo;
-    refv.hi = regs[r].ref_hi;
-    realign_region(P, rp[r], refv, regs[r].chr_len);
-    if (rp[r].row_misses) {
+    if (bad[r]) {
       if (err) *err = "host stage touched dense rows that were not fetched";
       return RV_ERR_STATE;
     }
-    build_patch(rp[r], &out->patches[r]);
     out->bases.push_back(all.size());
     all.insert(all.end(), out->patches[r].begin(), out->patches[r].end());
     collect_cov_patch(rp[r], &creg, &cpos, &cval);
@@ -166,23 +176,42 @@ inline int run_batch_simple(rv_ctx* ctx, const rv_params& P, const ReadBatch& ba
   RV_STEP(rv_fetch_variants(ctx, &vv, &nv));
   t.d2h_bytes += nv * (int64_t)sizeof(rv_variant);
   double t6 = now_ms();
-  std::vector<rv_variant> group;
-  for (int64_t i = 0; i < nv;) {
-    int64_t j = i;
-    while (j < nv && vv[j].region == vv[i].region && vv[j].pos == vv[i].pos) ++j;
-    const size_t r = (size_t)vv[i].region;
-    if (j - i == 1 && vv[i].is_ref && !P.pileup) { i = j; continue; }  // SimpleMode::output skips variant-less positions
-    group.assign(vv + i, vv + j);
-    for (size_t k = 0; k < group.size(); ++k)
-      if (group[k].key_kind == 1) group[k].key_id -= (int32_t)bases[r];
-    refv.lo = regs[r].ref_lo;
-    refv.hi = regs[r].ref_hi;
-    PositionVars pv;
-    assemble_position(P, group.data(), (int)group.size(), patches[r], refv, regs[r].chr_len, &pv);
-    size_t before = tsv->size();
-    output_position_simple(P, pv, sample, genes[r], chr, regs[r].start, regs[r].end, tsv);
-    for (size_t k = before; k < tsv->size(); ++k) t.n_lines += (*tsv)[k] == '\n';
-    i = j;
+  // records are sorted by (region, pos, rank): format every region's lines independently, concatenate in order
+  std::vector<int64_t> rfirst(regs.size() + 1, nv);
+  {
+    int64_t i = 0;
+    for (size_t r = 0; r < regs.size(); ++r) {
+      while (i < nv && vv[i].region < (int)r) ++i;
+      rfirst[r] = i;
+    }
+    rfirst[regs.size()] = nv;
+  }
+  std::vector<std::string> rtsv(regs.size());
+  std::vector<int64_t> rlines(regs.size(), 0);
+  parallel_for(regs.size(), host_threads(), [&](size_t r) {
+    rvk::RefView rv = refv;
+    rv.lo = regs[r].ref_lo;
+    rv.hi = regs[r].ref_hi;
+    std::vector<rv_variant> group;
+    std::string& out_s = rtsv[r];
+    for (int64_t i = rfirst[r]; i < rfirst[r + 1];) {
+      int64_t j = i;
+      while (j < rfirst[r + 1] && vv[j].pos == vv[i].pos) ++j;
+      if (j - i == 1 && vv[i].is_ref && !P.pileup) { i = j; continue; }  // SimpleMode::output skips variant-less positions
+      group.assign(vv + i, vv + j);
+      for (size_t k = 0; k < group.size(); ++k)
+        if (group[k].key_kind == 1) group[k].key_id -= (int32_t)bases[r];
+      PositionVars pv;
+      assemble_position(P, group.data(), (int)group.size(), patches[r], rv, regs[r].chr_len, &pv);
+      size_t before = out_s.size();
+      output_position_simple(P, pv, sample, genes[r], chr, regs[r].start, regs[r].end, &out_s);
+      for (size_t k = before; k < out_s.size(); ++k) rlines[r] += out_s[k] == '\n';
+      i = j;
+    }
+  });
+  for (size_t r = 0; r < regs.size(); ++r) {
+    tsv->append(rtsv[r]);
+    t.n_lines += rlines[r];
   }
   double t7 = now_ms();
   t.push_ms = t1 - t0; t.pileup_ms = t2 - t1;

@@ -350,6 +350,8 @@ struct rv_ctx {
   size_t h_events_cap;
   uint32_t* h_rows;
   size_t h_rows_cap;
+  uint8_t* d_scratch;   // persistent device scratch (no cudaMalloc/cudaFree on the per-batch path: both
+  size_t scratch_cap;   // stall for ~100 ms once GBs of host memory are page-locked)
   rv_variant* h_variants;
   size_t h_variants_cap;
   int32_t* h_max_rl;
@@ -357,6 +359,17 @@ struct rv_ctx {
   float pileup_ms, score_ms;
 };
 
+static int fail(rv_ctx* c, int code, const std::string& msg);
+static int ensure_scratch(rv_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->scratch_cap) return RV_OK;
+  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  ctx->d_scratch = NULL;
+  ctx->scratch_cap = 0;
+  size_t cap = bytes + bytes / 4 + (1 << 20);
+  if (cudaMalloc(&ctx->d_scratch, cap) != cudaSuccess) return fail(ctx, RV_ERR_NOMEM, "out of device memory (scratch)");
+  ctx->scratch_cap = cap;
+  return RV_OK;
+}
 static int fail(rv_ctx* c, int code, const std::string& msg) {
   if (c) c->err = msg;
   return code;
@@ -429,7 +442,7 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   ctx->d_events = NULL; ctx->d_variants = NULL; ctx->d_patch = NULL; ctx->d_patch_first = NULL;
   ctx->d_patch_count = NULL; ctx->d_regions = NULL; ctx->d_max_rl = NULL; ctx->d_stats = NULL; ctx->d_lgt = NULL;
   ctx->h_counts = NULL; ctx->h_cov = NULL; ctx->h_tab_cap = 0; ctx->h_events = NULL; ctx->h_events_cap = 0;
-  ctx->h_variants = NULL; ctx->h_variants_cap = 0; ctx->h_max_rl = NULL; ctx->h_rows = NULL; ctx->h_rows_cap = 0;
+  ctx->h_variants = NULL; ctx->h_variants_cap = 0; ctx->h_max_rl = NULL; ctx->h_rows = NULL; ctx->h_rows_cap = 0; ctx->d_scratch = NULL; ctx->scratch_cap = 0;
   ctx->n_reads = 0; ctx->n_positions = 0; ctx->n_items = 0; ctx->have_patch = false; ctx->tables_fetched = false;
   ctx->ref_start = 1; ctx->ref_n = 0; ctx->pileup_ms = ctx->score_ms = 0;
   ctx->reads_dev_view = NULL; ctx->pool_dev_view = NULL;
@@ -472,6 +485,7 @@ void rv_destroy(rv_ctx* ctx) {
   cudaFree(ctx->d_events); cudaFree(ctx->d_variants); cudaFree(ctx->d_patch); cudaFree(ctx->d_patch_first);
   cudaFree(ctx->d_patch_count); cudaFree(ctx->d_regions); cudaFree(ctx->d_max_rl); cudaFree(ctx->d_stats);
   cudaFree(ctx->d_lgt);
+  cudaFree(ctx->d_scratch);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
   if (ctx->h_cov) cudaFreeHost(ctx->h_cov);
   if (ctx->h_events) cudaFreeHost(ctx->h_events);
@@ -673,19 +687,17 @@ int rv_fetch_rows(rv_ctx* ctx, const int32_t* region, const int32_t* pos, int64_
     CK(cudaMallocHost(&ctx->h_rows, sizeof(uint32_t) * 33 * (size_t)n));
     ctx->h_rows_cap = (size_t)n;
   }
-  int64_t* d_tab = NULL;
-  uint32_t* d_out = NULL;
-  CK(cudaMalloc(&d_tab, 8 * (size_t)n));
-  cudaError_t e = cudaMalloc(&d_out, sizeof(uint32_t) * 33 * (size_t)n);
-  if (e != cudaSuccess) { cudaFree(d_tab); return fail(ctx, RV_ERR_NOMEM, "rv_fetch_rows: out of device memory"); }
+  int rcs = ensure_scratch(ctx, (size_t)n * (8 + 33 * 4) + 64);
+  if (rcs != RV_OK) return rcs;
+  int64_t* d_tab = (int64_t*)ctx->d_scratch;
+  uint32_t* d_out = (uint32_t*)(ctx->d_scratch + 8 * (size_t)n);
+  cudaError_t e;
   cudaMemcpyAsync(d_tab, tab.data(), 8 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
   int64_t threads = n * 33;
   rv_gather_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(d_tab, n, ctx->d_counts, ctx->d_cov, d_out);
   ctx->launches++;
   cudaMemcpyAsync(ctx->h_rows, d_out, sizeof(uint32_t) * 33 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
   e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_tab);
-  cudaFree(d_out);
   if (e != cudaSuccess) return fail(ctx, RV_ERR_CUDA, std::string("rv_fetch_rows: ") + cudaGetErrorString(e));
   *rows = ctx->h_rows;
   return RV_OK;
@@ -745,10 +757,10 @@ int rv_apply_patch(rv_ctx* ctx, const rv_patch_entry* entries, int64_t n_entries
   CK(cudaMemsetAsync(ctx->d_patch_count, 0, (size_t)(ctx->n_positions + 1), ctx->stream));
   if (n_entries) CK(cudaMemcpyAsync(ctx->d_patch, entries, sizeof(rv_patch_entry) * (size_t)n_entries, cudaMemcpyHostToDevice, ctx->stream));
   int64_t ng = (int64_t)grp_tab.size();
-  void* scratch = NULL;
   size_t sbytes = (size_t)ng * (8 + 4 + 1) + (size_t)n_cov * (8 + 4) + 64;
-  CK(cudaMalloc(&scratch, sbytes));
-  uint8_t* sp = (uint8_t*)scratch;
+  int rcs = ensure_scratch(ctx, sbytes);
+  if (rcs != RV_OK) return rcs;
+  uint8_t* sp = ctx->d_scratch;
   int64_t* d_tab = (int64_t*)sp; sp += 8 * (size_t)ng;
   int64_t* d_ctab = (int64_t*)sp; sp += 8 * (size_t)n_cov;
   uint32_t* d_first = (uint32_t*)sp; sp += 4 * (size_t)ng;
@@ -759,7 +771,7 @@ int rv_apply_patch(rv_ctx* ctx, const rv_patch_entry* entries, int64_t n_entries
   int64_t nc = 0;
   for (int64_t i = 0; i < n_cov; ++i) {
     int r = cov_region[i];
-    if (r < 0 || r >= (int)ctx->regions.size()) { cudaFree(scratch); return fail(ctx, RV_ERR_ARG, "coverage patch with bad region"); }
+    if (r < 0 || r >= (int)ctx->regions.size()) return fail(ctx, RV_ERR_ARG, "coverage patch with bad region");
     const DevRegion& d = ctx->regions[r];
     int idx = cov_pos[i] - d.first_pos;
     if (idx < 0 || idx >= d.n_pos) continue;
@@ -781,7 +793,6 @@ int rv_apply_patch(rv_ctx* ctx, const rv_patch_entry* entries, int64_t n_entries
     ctx->launches++;
   }
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(scratch);
   if (e != cudaSuccess) return fail(ctx, RV_ERR_CUDA, std::string("rv_apply_patch: ") + cudaGetErrorString(e));
   ctx->have_patch = true;
   ctx->tables_fetched = false;
