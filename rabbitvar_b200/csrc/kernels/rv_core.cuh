@@ -580,6 +580,44 @@ RV_HD void cleanup_cigar(Cigar& c) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fast-path descriptor.  A read whose rewritten CIGAR is [H][S] M [S][H] and whose matched run cannot
+// start a multi-nucleotide key (no two mismatches within vext+1 bases, parseCigar.cpp:711-768) contributes
+// nothing but independent single-base observations from its M op (:884-937).  Those are not pushed
+// through atomics: the walk emits this descriptor and the gather kernel (one lane per reference
+// position) accumulates them in registers.
+// ------------------------------------------------------------------------------------------------
+struct FastDesc {       // 32 bytes
+  int32_t m_start;      // reference position of the first matched base
+  uint16_t m_len;       // matched bases (== rlen of the read); 0 = no fast-path contribution
+  uint16_t rp0;         // read offset of the first matched base
+  uint32_t data_off16;  // the read's variable part in the pool
+  uint16_t n_cigar;
+  int16_t nm;
+  uint16_t l_seq;
+  uint8_t mapq;
+  uint8_t dir;
+  uint32_t read_idx;
+  uint32_t pad[2];
+};
+
+// One observation of the fast path: base/quality of descriptor d at reference position p.
+// Returns false when p is outside the matched run or the read base is N (skipped, :686-692).
+RV_HD bool fast_obs(const FastDesc& d, int p, const uint8_t* pool, int* allele, int* tp, int* q) {
+  int k = p - d.m_start;
+  if (k < 0 || k >= (int)d.m_len) return false;
+  const uint8_t* var = pool + (size_t)d.data_off16 * 16 + 4 * (size_t)d.n_cigar;
+  int r = (int)d.rp0 + k;
+  int b = var[r >> 1];
+  int nib = (r & 1) ? (b & 15) : (b >> 4);
+  int a = nib == 1 ? 0 : nib == 2 ? 1 : nib == 4 ? 2 : nib == 8 ? 3 : -1;
+  if (a < 0) return false;
+  *allele = a;
+  *q = var[((d.l_seq + 1) >> 1) + r];
+  *tp = k < (int)d.m_len - k ? k + 1 : (int)d.m_len - k;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
 // CigarParser::parseCigar, parseCigar.cpp:497-974, with its helpers.
 // Sink concept:
 //   void single(int pos, int allele, bool dir, int tp, int q, int mapq, int nm)   M-path obs, single base key
@@ -651,7 +689,8 @@ RV_HD int lookahead_offset(const rv_params& P, const ReadView& rd, const RefView
 
 template <class Sink>
 RV_HDN void process_read(const rv_params& P, const rv_region& R, int region_idx, const rv_read& rdh,
-                         const uint8_t* pool, const RefView& ref, uint32_t read_idx, Sink& sink) {
+                         const uint8_t* pool, const RefView& ref, uint32_t read_idx, Sink& sink,
+                         FastDesc* fast = (FastDesc*)0) {
   const uint8_t* var = pool + (size_t)rdh.data_off16 * 16;
   const uint32_t* cig_in = (const uint32_t*)var;
   ReadView rd;
@@ -720,6 +759,17 @@ RV_HDN void process_read(const rv_params& P, const rv_region& R, int region_idx,
   sink.kept(aligned);
   const int mate_start = rdh.mpos;
   const bool paired_same = (rdh.flag & 1) && rdh.mate_same_tid;
+  // fast-path shape: [H][S] M [S][H], no trimming option
+  bool fast_shape = fast != (FastDesc*)0 && P.trim_bases_after == 0 && tlen < 65536;
+  if (fast_shape) {
+    int n_m = 0;
+    for (int k = 0; k < n_cigar; ++k) {
+      int o = c_op(cg.op[k]);
+      if (o == OP_M) n_m++;
+      else if (o != OP_S && o != OP_H) fast_shape = false;
+    }
+    if (n_m != 1) fast_shape = false;
+  }
 
   bool need_break = true;
   for (int ci = 0; ci < n_cigar; ++ci) {
@@ -1039,6 +1089,39 @@ RV_HDN void process_read(const rv_params& P, const rv_region& R, int region_idx,
     }
 
     // ---- match part :675-959 ------------------------------------------------------------------------
+    if (fast_shape && w.offset == 0 && c_operator == OP_M) {
+      // can any base of this run start a multi-nucleotide key?  (two mismatches within vext+1 bases; a
+      // missing reference base or a non-ACGTN read base also sends the read down the exact path)
+      bool plain = true;
+      int last_mm = -1000;
+      for (int i = 0; i < w.clen && plain; ++i) {
+        char b = rd.base(w.rp + i);
+        if (b == 'N') continue;
+        if (!is_atgc(b)) { plain = false; break; }
+        char rc = ref.at(w.start + i);
+        if (rc != b) {
+          if (i - last_mm <= P.vext + 1) plain = false;
+          last_mm = i;
+        }
+      }
+      if (plain) {
+        fast->m_start = w.start;
+        fast->m_len = (uint16_t)w.clen;
+        fast->rp0 = (uint16_t)w.rp;
+        fast->data_off16 = rdh.data_off16;
+        fast->n_cigar = rdh.n_cigar;
+        fast->nm = (int16_t)nm;
+        fast->l_seq = (uint16_t)rdh.l_seq;
+        fast->mapq = (uint8_t)mapq;
+        fast->dir = dir ? 1 : 0;
+        fast->read_idx = read_idx;
+        w.start += w.clen;
+        w.rp += w.clen;
+        w.re += w.clen;
+        if (w.start > R.end) break;
+        continue;
+      }
+    }
     int nmoff = 0, moffset = 0;
     for (int i = w.offset; i < w.clen; i++) {
       bool trim = false;

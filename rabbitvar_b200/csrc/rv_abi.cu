@@ -30,7 +30,10 @@ struct DevRegion {
   int32_t first_pos;  // reference position of table index tab_off
   int32_t n_pos;
   int64_t item_base;  // first (region, read) work item of this region
+  int64_t tile_base;  // first gather tile (GATHER_TILE positions each) of this region
 };
+
+static const int GATHER_TILE = 256;
 
 struct DevStats {
   unsigned long long n_items, n_kept, n_bases, n_events, n_overflow, n_unsupported, n_variants, n_score_unsupported;
@@ -52,6 +55,8 @@ struct PileupArgs {
   unsigned long long max_events;
   int32_t* max_rl;
   DevStats* stats;
+  FastDesc* descs;     // one per work item; m_len == 0 when the item has no fast-path contribution
+  int32_t* max_lseq;   // longest read seen (bounds the gather kernel's candidate window)
 };
 
 struct DeviceSink {
@@ -149,7 +154,8 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
       s.covtab = a.cov + dr->tab_off;
       s.goodq = a.P.goodq;
       s.kept_bases = s.n_kept = s.n_unsup = s.n_over = s.n_ev = 0;
-      process_read(a.P, dr->r, ri, rd, a.pool, ref, (uint32_t)read_idx, s);
+      process_read(a.P, dr->r, ri, rd, a.pool, ref, (uint32_t)read_idx, s, a.descs ? a.descs + item : (FastDesc*)0);
+      if (a.descs && rd.l_seq > *a.max_lseq) atomicMax(a.max_lseq, rd.l_seq);
       kept = s.n_kept;
       bases = s.kept_bases;
       unsup = s.n_unsup;
@@ -178,6 +184,166 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
     if (sh[1]) atomicAdd(&a.stats->n_bases, sh[1]);
     if (sh[2]) atomicAdd(&a.stats->n_unsupported, sh[2]);
     if (sh[3]) atomicAdd(&a.stats->n_overflow, sh[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gather pileup: one lane per reference position, no atomics.  A CTA owns GATHER_TILE consecutive
+// positions of one region; it stages the fast-path descriptors whose matched run overlaps the tile in
+// shared memory (chunks of GATHER_TILE), then every lane walks the staged list and accumulates the
+// observations that fall on its position: the dominant allele in registers, the rare other alleles in
+// a conflict-free private shared-memory row ([allele][field][lane]).  Results are added to the dense
+// table with plain read-modify-write (the position is owned by exactly one lane).
+// ------------------------------------------------------------------------------------------------
+struct GatherArgs {
+  double goodq;
+  const DevRegion* regions;
+  int n_regions;
+  const rv_read* reads;
+  const FastDesc* descs;
+  const uint8_t* pool;
+  uint32_t* counts;
+  uint32_t* cov;
+  const int32_t* max_lseq;
+};
+
+__device__ __forceinline__ int find_region_by_tile(const DevRegion* regs, int n, int64_t tile) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (regs[mid].tile_base <= tile) lo = mid;
+    else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(GATHER_TILE) rv_gather_kernel(GatherArgs a) {
+  __shared__ FastDesc s_list[GATHER_TILE];
+  __shared__ uint32_t s_other[4 * 8 * GATHER_TILE];  // [allele][field][lane]: rare non-dominant alleles
+  __shared__ int s_warp_cnt[GATHER_TILE / 32];
+  __shared__ int s_count;
+  const int tid = threadIdx.x;
+  const int ri = find_region_by_tile(a.regions, a.n_regions, (int64_t)blockIdx.x);
+  const DevRegion* dr = a.regions + ri;
+  const int p_lo = dr->r.start + (int)((int64_t)blockIdx.x - dr->tile_base) * GATHER_TILE;
+  int p_hi = p_lo + GATHER_TILE - 1;
+  if (p_hi > dr->r.end) p_hi = dr->r.end;
+  const int p = p_lo + tid;
+  const bool live = p <= p_hi;
+  // candidate items: reads whose start lies in [p_lo - 2 Lmax, p_hi + Lmax] (|m_start - pos| <= l_seq, m_len <= l_seq)
+  const int lmax = *a.max_lseq;
+  int64_t lo = dr->r.read_lo, hi = dr->r.read_hi;
+  {
+    int64_t x = lo, y = hi;
+    const int want = p_lo - 2 * lmax;
+    while (x < y) { int64_t m = (x + y) >> 1; if (a.reads[m].pos < want) x = m + 1; else y = m; }
+    lo = x;
+    y = hi;
+    const int wanthi = p_hi + lmax;
+    while (x < y) { int64_t m = (x + y) >> 1; if (a.reads[m].pos <= wanthi) x = m + 1; else y = m; }
+    hi = x;
+  }
+  for (int k = tid; k < 4 * 8 * GATHER_TILE; k += GATHER_TILE) s_other[k] = 0;
+  int a0 = -1;
+  uint32_t r_fwd = 0, r_rev = 0, r_tp = 0, r_q = 0, r_mq = 0, r_nm = 0, r_hi = 0, r_first = 0, r_flags = 0;
+  uint32_t n_obs = 0, other_mask = 0;
+  const FastDesc* item_desc = a.descs + dr->item_base - dr->r.read_lo;  // desc of read index i = item_desc[i]
+  for (int64_t base = lo; base < hi; base += GATHER_TILE) {
+    // ---- stage: compact the overlapping descriptors of this chunk into shared memory ----
+    int64_t i = base + tid;
+    FastDesc d;
+    bool take = false;
+    if (i < hi) {
+      d = item_desc[i];
+      take = d.m_len != 0 && d.m_start <= p_hi && d.m_start + (int)d.m_len > p_lo;
+    }
+    unsigned bal = __ballot_sync(0xffffffffu, take);
+    if ((tid & 31) == 0) s_warp_cnt[tid >> 5] = __popc(bal);
+    __syncthreads();
+    int off = 0;
+    for (int wq = 0; wq < (tid >> 5); ++wq) off += s_warp_cnt[wq];
+    if (take) s_list[off + __popc(bal & ((1u << (tid & 31)) - 1u))] = d;
+    if (tid == GATHER_TILE - 1) s_count = off + __popc(bal);
+    __syncthreads();
+    const int cnt = s_count;
+    // ---- walk the staged list ----
+    if (live) {
+      for (int j = 0; j < cnt; ++j) {
+        const int m_start = s_list[j].m_start;
+        const int m_len = s_list[j].m_len;
+        const int k = p - m_start;
+        if (k < 0 || k >= m_len) continue;
+        const FastDesc& e = s_list[j];
+        const uint8_t* var = a.pool + (size_t)e.data_off16 * 16 + 4 * (size_t)e.n_cigar;
+        const int r = (int)e.rp0 + k;
+        const int b = var[r >> 1];
+        const int nib = (r & 1) ? (b & 15) : (b >> 4);
+        const int al = nib == 1 ? 0 : nib == 2 ? 1 : nib == 4 ? 2 : nib == 8 ? 3 : -1;
+        if (al < 0) continue;  // N
+        const uint32_t q = var[((e.l_seq + 1) >> 1) + r];
+        const uint32_t tp = (uint32_t)(k < m_len - k ? k + 1 : m_len - k);
+        const uint32_t hiq = (double)q >= a.goodq ? 1u : 0u;
+        const uint32_t packed = (tp & 0xffffu) | (q << 16);
+        n_obs++;
+        if (a0 < 0) a0 = al;
+        if (al == a0) {
+          if (e.dir) r_rev++; else r_fwd++;
+          r_tp += tp; r_q += q; r_mq += e.mapq; r_nm += (uint32_t)(int)e.nm; r_hi += hiq;
+          if (r_first == 0) r_first = packed | (1u << 31);
+          else {
+            if ((r_first & 0xffffu) != tp) r_flags |= 1u << 24;
+            if (((r_first >> 16) & 0xffu) != q) r_flags |= 1u << 25;
+          }
+        } else {
+          uint32_t* o = s_other + (size_t)al * 8 * GATHER_TILE + tid;
+          o[(e.dir ? RV_F_REV : RV_F_FWD) * GATHER_TILE] += 1;
+          o[RV_F_SUM_TP * GATHER_TILE] += tp;
+          o[RV_F_SUM_Q * GATHER_TILE] += q;
+          o[RV_F_SUM_MAPQ * GATHER_TILE] += e.mapq;
+          o[RV_F_SUM_NM * GATHER_TILE] += (uint32_t)(int)e.nm;
+          o[RV_F_HI * GATHER_TILE] += hiq;
+          uint32_t w = o[RV_F_STD * GATHER_TILE];
+          if (w == 0) w = packed | (1u << 31);
+          else {
+            if ((w & 0xffffu) != tp) w |= 1u << 24;
+            if (((w >> 16) & 0xffu) != q) w |= 1u << 25;
+          }
+          o[RV_F_STD * GATHER_TILE] = w;
+          other_mask |= 1u << al;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (!live || n_obs == 0) return;
+  // ---- add into the dense table (K1's atomics for the exact path have completed) ----
+  const int64_t t = dr->tab_off + (p - dr->first_pos);
+  uint32_t* row0 = a.counts + (size_t)t * RV_POS_U32;
+  a.cov[t] += n_obs;
+  for (int al = 0; al < 4; ++al) {
+    uint32_t v[8];
+    if (al == a0) {
+      v[RV_F_FWD] = r_fwd; v[RV_F_REV] = r_rev; v[RV_F_SUM_TP] = r_tp; v[RV_F_SUM_Q] = r_q; v[RV_F_SUM_MAPQ] = r_mq;
+      v[RV_F_SUM_NM] = r_nm; v[RV_F_HI] = r_hi; v[RV_F_STD] = r_first | r_flags;
+    } else if (other_mask & (1u << al)) {
+      const uint32_t* o = s_other + (size_t)al * 8 * GATHER_TILE + tid;
+      for (int f = 0; f < 8; ++f) v[f] = o[f * GATHER_TILE];
+    } else continue;
+    uint4* row4 = (uint4*)(row0 + al * RV_ROW_U32);
+    uint4 x = row4[0], y = row4[1];
+    x.x += v[0]; x.y += v[1]; x.z += v[2]; x.w += v[3];
+    y.x += v[4]; y.y += v[5]; y.z += v[6];
+    const uint32_t mine = v[RV_F_STD];
+    uint32_t w = y.w;
+    if ((w & (1u << 31)) == 0) w |= mine;  // no first value recorded yet (w can only hold nothing here)
+    else {
+      w |= mine & (3u << 24);
+      if ((w & 0xffffu) != (mine & 0xffffu)) w |= 1u << 24;
+      if (((w >> 16) & 0xffu) != ((mine >> 16) & 0xffu)) w |= 1u << 25;
+    }
+    y.w = w;
+    row4[0] = x;
+    row4[1] = y;
   }
 }
 
@@ -334,6 +500,10 @@ struct rv_ctx {
   DevStats* d_stats;
   double* d_lgt;
   int lgt_n;
+  FastDesc* d_descs;
+  int32_t* d_max_lseq;
+  int64_t n_tiles;
+  bool use_gather;
   // batch state
   const rv_read* reads_dev_view;  // d_reads or a caller-provided device pointer
   const uint8_t* pool_dev_view;
@@ -440,7 +610,8 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   ctx->launches = 0;
   ctx->d_reads = NULL; ctx->d_pool = NULL; ctx->d_ref = NULL; ctx->d_counts = NULL; ctx->d_cov = NULL;
   ctx->d_events = NULL; ctx->d_variants = NULL; ctx->d_patch = NULL; ctx->d_patch_first = NULL;
-  ctx->d_patch_count = NULL; ctx->d_regions = NULL; ctx->d_max_rl = NULL; ctx->d_stats = NULL; ctx->d_lgt = NULL;
+  ctx->d_patch_count = NULL; ctx->d_regions = NULL; ctx->d_max_rl = NULL; ctx->d_stats = NULL; ctx->d_lgt = NULL; ctx->d_descs = NULL; ctx->d_max_lseq = NULL; ctx->n_tiles = 0;
+  ctx->use_gather = getenv("RV_NO_GATHER") == NULL;
   ctx->h_counts = NULL; ctx->h_cov = NULL; ctx->h_tab_cap = 0; ctx->h_events = NULL; ctx->h_events_cap = 0;
   ctx->h_variants = NULL; ctx->h_variants_cap = 0; ctx->h_max_rl = NULL; ctx->h_rows = NULL; ctx->h_rows_cap = 0; ctx->d_scratch = NULL; ctx->scratch_cap = 0;
   ctx->n_reads = 0; ctx->n_positions = 0; ctx->n_items = 0; ctx->have_patch = false; ctx->tables_fetched = false;
@@ -467,6 +638,9 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   CK(cudaMalloc(&ctx->d_regions, sizeof(DevRegion) * (size_t)L.max_regions));
   CK(cudaMalloc(&ctx->d_max_rl, sizeof(int32_t) * (size_t)L.max_regions));
   CK(cudaMalloc(&ctx->d_stats, sizeof(DevStats)));
+  // work items are (region, read) pairs: a read overlapping two tiles is walked once per tile
+  CK(cudaMalloc(&ctx->d_descs, sizeof(FastDesc) * (size_t)(2 * L.max_reads + 1024)));
+  CK(cudaMalloc(&ctx->d_max_lseq, sizeof(int32_t)));
   CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->stream));
   ctx->lgt_n = 1 << 20;
   CK(cudaMalloc(&ctx->d_lgt, sizeof(double) * (size_t)ctx->lgt_n));
@@ -486,6 +660,8 @@ void rv_destroy(rv_ctx* ctx) {
   cudaFree(ctx->d_patch_count); cudaFree(ctx->d_regions); cudaFree(ctx->d_max_rl); cudaFree(ctx->d_stats);
   cudaFree(ctx->d_lgt);
   cudaFree(ctx->d_scratch);
+  cudaFree(ctx->d_descs);
+  cudaFree(ctx->d_max_lseq);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
   if (ctx->h_cov) cudaFreeHost(ctx->h_cov);
   if (ctx->h_events) cudaFreeHost(ctx->h_events);
@@ -551,7 +727,7 @@ int rv_set_regions(rv_ctx* ctx, const rv_region* regs, int32_t n) {
   if (n > ctx->L.max_regions) return fail(ctx, RV_ERR_OVERFLOW, "more regions than limits.max_regions");
   CK(cudaSetDevice(ctx->device));
   ctx->regions.resize(n);
-  int64_t tab = 0, items = 0;
+  int64_t tab = 0, items = 0, tiles = 0;
   for (int i = 0; i < n; ++i) {
     DevRegion& d = ctx->regions[i];
     d.r = regs[i];
@@ -561,13 +737,18 @@ int rv_set_regions(rv_ctx* ctx, const rv_region* regs, int32_t n) {
     d.n_pos = d.r.end - d.r.start + 1 + 2 * ctx->L.halo;
     d.tab_off = tab;
     d.item_base = items;
+    d.tile_base = tiles;
+    tiles += (d.r.end - d.r.start + 1 + GATHER_TILE - 1) / GATHER_TILE;
     tab += d.n_pos;
     items += d.r.read_hi - d.r.read_lo;
     ctx->h_max_rl[i] = d.r.max_read_len_in;
   }
   if (tab > ctx->L.max_positions) return fail(ctx, RV_ERR_OVERFLOW, "regions need more table positions than limits.max_positions");
+  if (items > 2 * ctx->L.max_reads + 1024)
+    return fail(ctx, RV_ERR_OVERFLOW, "more (region, read) work items than 2 x limits.max_reads");
   ctx->n_positions = tab;
   ctx->n_items = items;
+  ctx->n_tiles = tiles;
   ctx->have_patch = false;
   ctx->tables_fetched = false;
   if (n) {
@@ -604,11 +785,32 @@ int rv_pileup(rv_ctx* ctx) {
   a.max_events = (unsigned long long)ctx->L.max_events;
   a.max_rl = ctx->d_max_rl;
   a.stats = ctx->d_stats;
+  a.descs = ctx->use_gather ? ctx->d_descs : NULL;
+  a.max_lseq = ctx->d_max_lseq;
   if (ctx->n_items > 0) {
+    if (ctx->use_gather) {
+      CK(cudaMemsetAsync(ctx->d_descs, 0, sizeof(FastDesc) * (size_t)ctx->n_items, ctx->stream));
+      CK(cudaMemsetAsync(ctx->d_max_lseq, 0, sizeof(int32_t), ctx->stream));
+    }
     unsigned grid = (unsigned)((ctx->n_items + 127) / 128);
     rv_pileup_kernel<<<grid, 128, 0, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
+    if (ctx->use_gather && ctx->n_tiles > 0) {
+      GatherArgs g;
+      g.goodq = ctx->P.goodq;
+      g.regions = ctx->d_regions;
+      g.n_regions = (int)ctx->regions.size();
+      g.reads = ctx->reads_dev_view;
+      g.descs = ctx->d_descs;
+      g.pool = ctx->pool_dev_view;
+      g.counts = ctx->d_counts;
+      g.cov = ctx->d_cov;
+      g.max_lseq = ctx->d_max_lseq;
+      rv_gather_kernel<<<(unsigned)ctx->n_tiles, GATHER_TILE, 0, ctx->stream>>>(g);
+      ctx->launches++;
+      CK(cudaGetLastError());
+    }
   }
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   CK(cudaMemcpyAsync(&ctx->h_stats, ctx->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, ctx->stream));

@@ -213,11 +213,27 @@ int main(int argc, char** argv) {
       SimSink s;
       s.R = &R; s.events = &events; s.goodq = P.goodq;
       s.kept_reads = s.kept_bases = s.unsup = s.over = 0;
+      const bool use_fast = getenv("RV_NO_GATHER") == NULL;
+      std::vector<rvk::FastDesc> descs;
       for (int64_t i = regs[r].read_lo; i < regs[r].read_hi; ++i) {
         const rv_read& rd = batch.reads[(size_t)i];
         if (!(rd.pos - 1 < regs[r].end && rd.end_pos > regs[r].start - 1)) continue;
         st.n_items++;
-        rvk::process_read(P, regs[r], (int)r, rd, batch.pool.data(), ref, (uint32_t)i, s);
+        rvk::FastDesc d;
+        memset(&d, 0, sizeof d);
+        rvk::process_read(P, regs[r], (int)r, rd, batch.pool.data(), ref, (uint32_t)i, s, use_fast ? &d : (rvk::FastDesc*)0);
+        if (d.m_len) descs.push_back(d);
+      }
+      // the gather kernel's work, position by position
+      for (size_t k = 0; k < descs.size(); ++k) {
+        const rvk::FastDesc& d = descs[k];
+        int lo = std::max(d.m_start, (int)regs[r].start), hi = std::min(d.m_start + (int)d.m_len - 1, (int)regs[r].end);
+        for (int p = lo; p <= hi; ++p) {
+          int al, tp, q;
+          if (!rvk::fast_obs(d, p, batch.pool.data(), &al, &tp, &q)) continue;
+          s.single(p, al, d.dir != 0, tp, q, d.mapq, d.nm);
+          s.cov(p);
+        }
       }
       st.n_reads_kept += s.kept_reads; st.n_aligned_bases += s.kept_bases;
       st.n_unsupported += s.unsup; st.n_overflow += s.over;
