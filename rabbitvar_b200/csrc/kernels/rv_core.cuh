@@ -687,10 +687,20 @@ RV_HD int lookahead_offset(const rv_params& P, const ReadView& rd, const RefView
   return offset;
 }
 
+// Everything parseCigar does before its op loop (:497-625): filters, CIGAR rewrite, clean-up, lengths.
+struct Prep {
+  Cigar cg;
+  int n_cigar, nm, position, rlen, tlen, mapq;
+  bool dir, ok, fast_shape;
+  int m_start, m_len, rp0;  // the single matched run of a fast-shaped read
+};
+
 template <class Sink>
-RV_HDN void process_read(const rv_params& P, const rv_region& R, int region_idx, const rv_read& rdh,
-                         const uint8_t* pool, const RefView& ref, uint32_t read_idx, Sink& sink,
-                         FastDesc* fast = (FastDesc*)0) {
+RV_HDN void prepare_read(const rv_params& P, const rv_region& R, const rv_read& rdh, const uint8_t* pool,
+                         const RefView& ref, Sink& sink, bool want_fast, Prep& pr) {
+  pr.ok = false;
+  pr.fast_shape = false;
+  Cigar& cg = pr.cg;
   const uint8_t* var = pool + (size_t)rdh.data_off16 * 16;
   const uint32_t* cig_in = (const uint32_t*)var;
   ReadView rd;
@@ -706,7 +716,6 @@ RV_HDN void process_read(const rv_params& P, const rv_region& R, int region_idx,
   int n_cigar = rdh.n_cigar;
   if (n_cigar <= 0) return;
   if (n_cigar > RV_MAX_OPS - 8) { sink.unsupported(); return; }
-  Cigar cg;
   cg.n = n_cigar;
   cg.overflow = false;
   int indel = 0;
@@ -735,12 +744,6 @@ RV_HDN void process_read(const rv_params& P, const rv_region& R, int region_idx,
   }
   cleanup_cigar(cg);
   n_cigar = cg.n;
-  WalkState w;
-  w.start = position;
-  w.offset = 0;
-  w.rp = 0;
-  w.re = 0;
-  w.seq_no = 0;
   // :584-588
   if (c_op(cg.op[0]) == OP_S && c_len(cg.op[0]) >= 10 && c_op(cg.op[n_cigar - 1]) == OP_S &&
       c_len(cg.op[n_cigar - 1]) >= 10)
@@ -757,19 +760,56 @@ RV_HDN void process_read(const rv_params& P, const rv_region& R, int region_idx,
   sink.max_read_len(tlen);
   if (rdh.flag & 2048) return;  // :603
   sink.kept(aligned);
-  const int mate_start = rdh.mpos;
-  const bool paired_same = (rdh.flag & 1) && rdh.mate_same_tid;
-  // fast-path shape: [H][S] M [S][H], no trimming option
-  bool fast_shape = fast != (FastDesc*)0 && P.trim_bases_after == 0 && tlen < 65536;
+  // fast-path shape: [H][S] M [S][H], no trimming option.  The matched run starts at `position`
+  // (process_softclip resets start to it, :1300) and at the read offset after the leading clips.
+  bool fast_shape = want_fast && P.trim_bases_after == 0 && tlen < 65536;
+  int m_len = 0, rp0 = 0;
   if (fast_shape) {
     int n_m = 0;
     for (int k = 0; k < n_cigar; ++k) {
       int o = c_op(cg.op[k]);
-      if (o == OP_M) n_m++;
-      else if (o != OP_S && o != OP_H) fast_shape = false;
+      if (o == OP_M) { n_m++; m_len = c_len(cg.op[k]); }
+      else if (o == OP_S) { if (n_m == 0) rp0 += c_len(cg.op[k]); }
+      else if (o != OP_H) fast_shape = false;
     }
     if (n_m != 1) fast_shape = false;
   }
+  pr.n_cigar = n_cigar;
+  pr.nm = nm;
+  pr.position = position;
+  pr.rlen = rlen;
+  pr.tlen = tlen;
+  pr.mapq = mapq;
+  pr.dir = dir;
+  pr.fast_shape = fast_shape;
+  pr.m_start = position;
+  pr.m_len = m_len;
+  pr.rp0 = rp0;
+  pr.ok = true;
+}
+
+// plain_hint: 1 = the matched run was already proven plain (warp-cooperative scan in the kernel),
+// 0 = proven not plain, -1 = decide here with the scalar scan.
+template <class Sink>
+RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, const rv_read& rdh, const uint8_t* pool,
+                      const RefView& ref, uint32_t read_idx, Sink& sink, Prep& pr, FastDesc* fast, int plain_hint) {
+  Cigar& cg = pr.cg;
+  const uint8_t* var = pool + (size_t)rdh.data_off16 * 16;
+  ReadView rd;
+  rd.seq4 = var + 4 * (size_t)rdh.n_cigar;
+  rd.lseq = rdh.l_seq;
+  rd.qual = rd.seq4 + ((rdh.l_seq + 1) >> 1);
+  const int n_cigar = pr.n_cigar, nm = pr.nm, position = pr.position, rlen = pr.rlen, tlen = pr.tlen, mapq = pr.mapq;
+  const bool dir = pr.dir;
+  const bool fast_shape = pr.fast_shape && fast != (FastDesc*)0 && plain_hint != 0;
+  WalkState w;
+  w.start = position;
+  w.offset = 0;
+  w.rp = 0;
+  w.re = 0;
+  w.seq_no = 0;
+  const int mate_start = rdh.mpos;
+  const bool paired_same = (rdh.flag & 1) && rdh.mate_same_tid;
 
   bool need_break = true;
   for (int ci = 0; ci < n_cigar; ++ci) {
@@ -1094,7 +1134,7 @@ RV_HDN void process_read(const rv_params& P, const rv_region& R, int region_idx,
       // missing reference base or a non-ACGTN read base also sends the read down the exact path)
       bool plain = true;
       int last_mm = -1000;
-      for (int i = 0; i < w.clen && plain; ++i) {
+      for (int i = 0; plain_hint < 0 && i < w.clen && plain; ++i) {
         char b = rd.base(w.rp + i);
         if (b == 'N') continue;
         if (!is_atgc(b)) { plain = false; break; }
@@ -1289,6 +1329,16 @@ RV_HDN void process_read(const rv_params& P, const rv_region& R, int region_idx,
     }
     if (w.start > R.end) break;
   }
+}
+
+template <class Sink>
+RV_HDN void process_read(const rv_params& P, const rv_region& R, int region_idx, const rv_read& rdh,
+                         const uint8_t* pool, const RefView& ref, uint32_t read_idx, Sink& sink,
+                         FastDesc* fast = (FastDesc*)0) {
+  Prep pr;
+  prepare_read(P, R, rdh, pool, ref, sink, fast != (FastDesc*)0, pr);
+  if (!pr.ok) return;
+  walk_read(P, R, region_idx, rdh, pool, ref, read_idx, sink, pr, fast, -1);
 }
 
 }  // namespace rvk

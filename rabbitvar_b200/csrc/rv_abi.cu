@@ -130,38 +130,133 @@ __device__ __forceinline__ int find_region(const DevRegion* regs, int n, int64_t
   return lo;
 }
 
-// One (region, read) pair per thread: read filters, CIGAR rewrite, CIGAR walk, accumulation.
+// One (region, read) pair per thread, three stages:
+//   1. per thread : read filters, CIGAR rewrite rules, clean-up (prepare_read)
+//   2. per warp   : the matched run of every fast-shaped read of the warp is scanned by all 32 lanes
+//                   (coalesced 4-bit bases + reference bytes, mismatch masks by ballot) to prove that it
+//                   cannot start a multi-nucleotide key; such reads only leave a FastDesc for the gather kernel
+//   3. per thread : the exact CIGAR walk for soft clips and for every read that is not plain (atomics + events)
 __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
   int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
   unsigned long long kept = 0, bases = 0, unsup = 0, over = 0;
+  Prep pr;
+  pr.ok = false;
+  pr.fast_shape = false;
+  pr.m_start = pr.m_len = pr.rp0 = 0;
+  DeviceSink s;
+  s.a = &a;
+  s.kept_bases = s.n_kept = s.n_unsup = s.n_over = s.n_ev = 0;
+  s.goodq = a.P.goodq;
+  const DevRegion* dr = a.regions;
+  rv_read rd;
+  rd.data_off16 = 0; rd.n_cigar = 0; rd.l_seq = 0;
+  RefView ref;
+  ref.bases = a.ref;
+  ref.base_pos = a.ref_start;
+  ref.n = a.ref_n;
+  ref.lo = 1;
+  ref.hi = 0;
+  int ri = 0;
+  int64_t read_idx = 0;
   if (item < a.n_items) {
-    int ri = find_region(a.regions, a.n_regions, item);
-    const DevRegion* dr = a.regions + ri;
-    int64_t read_idx = dr->r.read_lo + (item - dr->item_base);
-    const rv_read rd = a.reads[read_idx];
+    ri = find_region(a.regions, a.n_regions, item);
+    dr = a.regions + ri;
+    read_idx = dr->r.read_lo + (item - dr->item_base);
+    rd = a.reads[read_idx];
+    ref.lo = dr->r.ref_lo;
+    ref.hi = dr->r.ref_hi;
+    s.dr = dr;
+    s.counts = a.counts + (size_t)dr->tab_off * RV_POS_U32;
+    s.covtab = a.cov + dr->tab_off;
     // htslib iterator overlap test (sam_itr_next): pos0 < end && endpos > beg0
-    if (rd.pos - 1 < dr->r.end && rd.end_pos > dr->r.start - 1) {
-      RefView ref;
-      ref.bases = a.ref;
-      ref.base_pos = a.ref_start;
-      ref.n = a.ref_n;
-      ref.lo = dr->r.ref_lo;
-      ref.hi = dr->r.ref_hi;
-      DeviceSink s;
-      s.a = &a;
-      s.dr = dr;
-      s.counts = a.counts + (size_t)dr->tab_off * RV_POS_U32;
-      s.covtab = a.cov + dr->tab_off;
-      s.goodq = a.P.goodq;
-      s.kept_bases = s.n_kept = s.n_unsup = s.n_over = s.n_ev = 0;
-      process_read(a.P, dr->r, ri, rd, a.pool, ref, (uint32_t)read_idx, s, a.descs ? a.descs + item : (FastDesc*)0);
-      if (a.descs && rd.l_seq > *a.max_lseq) atomicMax(a.max_lseq, rd.l_seq);
-      kept = s.n_kept;
-      bases = s.kept_bases;
-      unsup = s.n_unsup;
-      over = s.n_over;
+    if (rd.pos - 1 < dr->r.end && rd.end_pos > dr->r.start - 1)
+      prepare_read(a.P, dr->r, rd, a.pool, ref, s, a.descs != NULL, pr);
+  }
+  // ---- stage 2: warp-cooperative scan of the matched runs -------------------------------------------
+  int plain = -1;
+  if (a.descs != NULL) {
+    const bool cand = pr.ok && pr.fast_shape;
+    unsigned cand_mask = __ballot_sync(0xffffffffu, cand);
+    const int D = a.P.vext + 1;
+    plain = cand ? 1 : 0;
+    while (cand_mask) {
+      const int j = __ffs(cand_mask) - 1;
+      cand_mask &= cand_mask - 1;
+      const int ms = __shfl_sync(0xffffffffu, pr.m_start, j);
+      const int ml = __shfl_sync(0xffffffffu, pr.m_len, j);
+      const int r0 = __shfl_sync(0xffffffffu, pr.rp0, j);
+      const unsigned off16 = __shfl_sync(0xffffffffu, rd.data_off16, j);
+      const int ncg = __shfl_sync(0xffffffffu, (int)rd.n_cigar, j);
+      const int rlo = __shfl_sync(0xffffffffu, ref.lo, j);
+      const int rhi = __shfl_sync(0xffffffffu, ref.hi, j);
+      const uint8_t* seq4 = a.pool + (size_t)off16 * 16 + 4 * (size_t)ncg;
+      bool pl = D < 32;
+      unsigned prev = 0;
+      for (int base = 0; base < ml && pl; base += 32) {
+        const int i = base + lane;
+        bool mm = false, odd = false;
+        if (i < ml) {
+          const int r = r0 + i;
+          const int b = seq4[r >> 1];
+          const int nib = (r & 1) ? (b & 15) : (b >> 4);
+          if (nib != 15) {  // a read 'N' is skipped by the walk and never starts a key
+            const char c = nib == 1 ? 'A' : nib == 2 ? 'C' : nib == 4 ? 'G' : nib == 8 ? 'T' : (char)0;
+            if (c == 0) odd = true;
+            else {
+              const int p = ms + i;
+              const int64_t o = (int64_t)p - a.ref_start;
+              const char rc = (p >= rlo && p <= rhi && o >= 0 && o < a.ref_n) ? a.ref[o] : (char)0;
+              mm = rc != c;
+            }
+          }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, mm);
+        const unsigned x = __ballot_sync(0xffffffffu, odd);
+        unsigned near = 0;
+        for (int d = 1; d <= D; ++d) near |= m & ((m << d) | (prev >> (32 - d)));
+        if (near || x) pl = false;
+        prev = m;
+      }
+      if (lane == j) plain = pl ? 1 : 0;
     }
   }
+  // ---- stage 3: exact walk (soft clips, indels, multi-nucleotide keys, non-plain reads) -------------
+  if (pr.ok) {
+    FastDesc* fd = a.descs ? a.descs + item : (FastDesc*)0;
+    const bool only_m = plain == 1 && pr.n_cigar == 1;  // nothing but the matched run: skip the walk entirely
+    if (only_m) {
+      fd->m_start = pr.m_start;
+      fd->m_len = (uint16_t)pr.m_len;
+      fd->rp0 = (uint16_t)pr.rp0;
+      fd->data_off16 = rd.data_off16;
+      fd->n_cigar = rd.n_cigar;
+      fd->nm = (int16_t)pr.nm;
+      fd->l_seq = (uint16_t)rd.l_seq;
+      fd->mapq = (uint8_t)pr.mapq;
+      fd->dir = pr.dir ? 1 : 0;
+      fd->read_idx = (uint32_t)read_idx;
+      // parseCigar.cpp:630 — the -u / --UN overlap test happens before the first op
+      bool skip = false;
+      const bool paired_same = (rd.flag & 1) && rd.mate_same_tid;
+      if (a.P.uniq_u && paired_same && !pr.dir && pr.position >= rd.mpos) skip = true;
+      if (!skip && a.P.uniq_un && (rd.flag & 1) && paired_same) {
+        const int ref_len = rd.end_pos - (rd.pos - 1);
+        bool ov;
+        if (pr.position >= rd.mpos) ov = pr.position <= rd.mpos + ref_len - 1;
+        else ov = false;  // start >= mate_start cannot hold when position < mate_start
+        if (ov) skip = true;
+      }
+      if (skip) fd->m_len = 0;
+    } else {
+      walk_read(a.P, dr->r, ri, rd, a.pool, ref, (uint32_t)read_idx, s, pr, fd, plain);
+    }
+    if (a.descs && rd.l_seq > *a.max_lseq) atomicMax(a.max_lseq, rd.l_seq);
+  }
+  kept = s.n_kept;
+  bases = s.kept_bases;
+  unsup = s.n_unsup;
+  over = s.n_over;
   // block-level reduction of the statistics, one atomic per block and counter
   __shared__ unsigned long long sh[4];
   if (threadIdx.x < 4) sh[threadIdx.x] = 0;
