@@ -326,13 +326,11 @@ def main():
     d2h = sum(t.d2h_bytes for t in e2e_tm)
 
     # ---- reductions over ranks (max time, sum of work) ---------------------------------------------------
-    t_all = torch.tensor([dev_ms, wall_ms, e2e_sec], dtype=torch.float64, device=dev)
-    w_all = torch.tensor([float(bases_per_step)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-        dist.all_reduce(w_all, op=dist.ReduceOp.SUM)
-    dev_ms_max, wall_ms_max, e2e_sec_max = [float(x) for x in t_all.tolist()]
-    total_bases = float(w_all.item())
+    from rabbitvar_b200.shard import reduce_step_metrics
+    d = dist if world > 1 else None
+    dev_ms_max, total_bases = reduce_step_metrics(dev_ms, bases_per_step, d)
+    wall_ms_max, _ = reduce_step_metrics(wall_ms, 0, d)
+    e2e_sec_max, _ = reduce_step_metrics(e2e_sec, 0, d)
     value = total_bases * args.steps / (dev_ms_max / 1000.0)
     e2e_value = total_bases / e2e_sec_max
 
