@@ -13,6 +13,7 @@
 #include "kernels/rv_core.cuh"
 #include "kernels/rv_score.cuh"
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdio.h>
 #include <string.h>
 #include <string>
@@ -20,6 +21,7 @@
 #include <algorithm>
 
 using namespace rvk;
+namespace cg = cooperative_groups;
 
 // ------------------------------------------------------------------------------------------------
 // device-side views
@@ -30,13 +32,25 @@ struct DevRegion {
   int32_t first_pos;  // reference position of table index tab_off
   int32_t n_pos;
   int64_t item_base;  // first (region, read) work item of this region
-  int64_t tile_base;  // first gather tile (GATHER_TILE positions each) of this region
+  int64_t tile_base;  // first gather tile (GATHER_TILE table positions each, halo included) of this region
 };
 
 static const int GATHER_TILE = 256;
 
 struct DevStats {
   unsigned long long n_items, n_kept, n_bases, n_events, n_overflow, n_unsupported, n_variants, n_score_unsupported;
+};
+
+// Gather descriptor of one (region, read) work item whose rewritten CIGAR is [H][S] M [S][H] and whose matched
+// run is "plain" (see rv_pileup_kernel): all the gather kernel needs to find the run's bases and qualities.
+struct GDesc {          // 16 bytes, one LDG.128
+  int32_t m_start;      // reference position of the first matched base
+  uint16_t m_len;       // matched bases; 0 = the item contributes nothing through the gather path
+  uint16_t rp0;         // read offset of the first matched base
+  uint32_t seq_off4;    // byte offset of the packed bases in the pool / 4 (qualities follow the bases)
+  uint16_t l_seq;
+  uint8_t mapq;
+  uint8_t dir_nm;       // bit 7: reverse strand; bits 0-6: nm (0..127)
 };
 
 struct PileupArgs {
@@ -47,6 +61,7 @@ struct PileupArgs {
   const rv_read* reads;
   const uint8_t* pool;
   const char* ref;
+  const uint32_t* ref4;  // the same slice, 4 bits / base (A=1 C=2 G=4 T=8 other=15), base e in bits 28-4*(e&7) of word e>>3
   int32_t ref_start;
   int64_t ref_n;
   uint32_t* counts;
@@ -55,9 +70,15 @@ struct PileupArgs {
   unsigned long long max_events;
   int32_t* max_rl;
   DevStats* stats;
-  FastDesc* descs;     // one per work item; m_len == 0 when the item has no fast-path contribution
-  int32_t* max_lseq;   // longest read seen (bounds the gather kernel's candidate window)
+  GDesc* descs;          // one per work item
+  int32_t* reach;        // [0] = max(pos - m_start), [1] = max(m_start + m_len - pos) over the descriptors
+  int force_exact;       // debugging: every read takes the exact walk
+  // reads that need the exact CIGAR walk are not walked by the classifying kernel (one slow lane would stall
+  // its 31 neighbours): their work item goes to this queue and rv_walk_kernel runs them densely packed
+  unsigned long long* walk_queue;   // item | WALK_PLAIN_DONE
+  unsigned long long* walk_count;
 };
+static const unsigned long long WALK_PLAIN_DONE = 1ull << 62;  // the matched run already left a descriptor
 
 struct DeviceSink {
   const PileupArgs* a;
@@ -66,6 +87,7 @@ struct DeviceSink {
   uint32_t* covtab;
   double goodq;
   int kept_bases, n_kept, n_unsup, n_over, n_ev;
+  bool mute;  // rv_walk_kernel re-runs prepare_read: its statistics were already counted by rv_pileup_kernel
   __device__ __forceinline__ bool idx_of(int pos, int* idx) {
     int i = pos - dr->first_pos;
     if (i < 0 || i >= dr->n_pos) { n_over++; return false; }
@@ -110,14 +132,20 @@ struct DeviceSink {
     atomicAdd(covtab + i, 1u);
   }
   __device__ __forceinline__ void event(const rv_event& e) {
-    unsigned long long slot = atomicAdd(&a->stats->n_events, 1ull);
+    // one atomic per group of converged lanes
+    cg::coalesced_group g = cg::coalesced_threads();
+    unsigned long long slot = 0;
+    if (g.thread_rank() == 0) slot = atomicAdd(&a->stats->n_events, (unsigned long long)g.size());
+    slot = g.shfl(slot, 0) + g.thread_rank();
     if (slot >= a->max_events) { n_over++; return; }
     a->events[slot] = e;
     n_ev++;
   }
-  __device__ __forceinline__ void max_read_len(int tlen) { atomicMax(a->max_rl + (dr - a->regions), tlen); }
-  __device__ __forceinline__ void kept(int aligned) { kept_bases += aligned; n_kept++; }
-  __device__ __forceinline__ void unsupported() { n_unsup++; }
+  __device__ __forceinline__ void max_read_len(int tlen) {
+    if (!mute && tlen > a->max_rl[dr - a->regions]) atomicMax(a->max_rl + (dr - a->regions), tlen);
+  }
+  __device__ __forceinline__ void kept(int aligned) { if (!mute) { kept_bases += aligned; n_kept++; } }
+  __device__ __forceinline__ void unsupported() { if (!mute) n_unsup++; }
 };
 
 __device__ __forceinline__ int find_region(const DevRegion* regs, int n, int64_t item) {
@@ -130,16 +158,39 @@ __device__ __forceinline__ int find_region(const DevRegion* regs, int n, int64_t
   return lo;
 }
 
+// bit 0 of every nibble = OR of the nibble's four bits
+__device__ __forceinline__ uint32_t nib_any(uint32_t x) { return (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u; }
+
+// 4-bit packing of the reference slice (one thread per 8 bases)
+__global__ void rv_pack_ref_kernel(const char* ref, int64_t n, uint32_t* out, int64_t n_words) {
+  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  uint32_t v = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t e = w * 8 + i;
+    uint32_t code = 0;  // beyond the slice: equal to no read base
+    if (e < n) {
+      const char c = ref[e];
+      code = c == 'A' ? 1u : c == 'C' ? 2u : c == 'G' ? 4u : c == 'T' ? 8u : 15u;
+    }
+    v |= code << (28 - 4 * i);
+  }
+  out[w] = v;
+}
+
 // One (region, read) pair per thread, three stages:
 //   1. per thread : read filters, CIGAR rewrite rules, clean-up (prepare_read)
-//   2. per warp   : the matched run of every fast-shaped read of the warp is scanned by all 32 lanes
-//                   (coalesced 4-bit bases + reference bytes, mismatch masks by ballot) to prove that it
-//                   cannot start a multi-nucleotide key; such reads only leave a FastDesc for the gather kernel
-//   3. per thread : the exact CIGAR walk for soft clips and for every read that is not plain (atomics + events)
+//   2. per warp   : the matched run of every fast-shaped read of the warp is compared with the reference by all
+//                   32 lanes, 8 bases per lane and step: the BAM 4-bit bases XOR the 4-bit reference give one
+//                   mismatch flag per nibble; shifted copies of the flag word prove that no two mismatches lie
+//                   within vext+1 bases, i.e. that no base of the run can start a multi-nucleotide key
+//                   (parseCigar.cpp:711-768).  Such a "plain" run only leaves a GDesc for the gather kernel.
+//   3. per thread : everything that needs the exact CIGAR walk (soft clips, indels, non-plain runs, reads with N
+//                   or IUPAC bases) is appended to the walk queue
 __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
   int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  unsigned long long kept = 0, bases = 0, unsup = 0, over = 0;
   Prep pr;
   pr.ok = false;
   pr.fast_shape = false;
@@ -147,20 +198,20 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
   DeviceSink s;
   s.a = &a;
   s.kept_bases = s.n_kept = s.n_unsup = s.n_over = s.n_ev = 0;
+  s.mute = false;
   s.goodq = a.P.goodq;
   const DevRegion* dr = a.regions;
   rv_read rd;
-  rd.data_off16 = 0; rd.n_cigar = 0; rd.l_seq = 0;
+  rd.data_off16 = 0; rd.n_cigar = 0; rd.l_seq = 0; rd.pos = 0;
   RefView ref;
   ref.bases = a.ref;
   ref.base_pos = a.ref_start;
   ref.n = a.ref_n;
   ref.lo = 1;
   ref.hi = 0;
-  int ri = 0;
   int64_t read_idx = 0;
   if (item < a.n_items) {
-    ri = find_region(a.regions, a.n_regions, item);
+    const int ri = find_region(a.regions, a.n_regions, item);
     dr = a.regions + ri;
     read_idx = dr->r.read_lo + (item - dr->item_base);
     rd = a.reads[read_idx];
@@ -171,107 +222,133 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
     s.covtab = a.cov + dr->tab_off;
     // htslib iterator overlap test (sam_itr_next): pos0 < end && endpos > beg0
     if (rd.pos - 1 < dr->r.end && rd.end_pos > dr->r.start - 1)
-      prepare_read(a.P, dr->r, rd, a.pool, ref, s, a.descs != NULL, pr);
+      prepare_read(a.P, dr->r, rd, a.pool, ref, s, true, pr);
   }
-  // ---- stage 2: warp-cooperative scan of the matched runs -------------------------------------------
-  int plain = -1;
-  if (a.descs != NULL) {
-    const bool cand = pr.ok && pr.fast_shape;
+  // ---- stage 2: warp-cooperative plain-run proof ------------------------------------------------------
+  const size_t seq_word = (size_t)rd.data_off16 * 4 + rd.n_cigar;  // u32 index of the packed bases in the pool
+  int E0 = 0;  // reference-slice index of read base 0
+  bool cand = pr.ok && pr.fast_shape && !a.force_exact;
+  if (cand) {
+    E0 = pr.m_start - pr.rp0 - a.ref_start;
+    const int64_t w_lo = ref.lo > a.ref_start ? ref.lo : a.ref_start;
+    const int64_t w_hi = (int64_t)ref.hi < a.ref_start + a.ref_n - 1 ? (int64_t)ref.hi : a.ref_start + a.ref_n - 1;
+    cand = pr.m_len > 0 && E0 >= 0 && pr.m_start >= w_lo && (int64_t)pr.m_start + pr.m_len - 1 <= w_hi && pr.nm >= 0 &&
+           pr.nm <= 127 && pr.mapq <= 255;
+  }
+  bool plain = cand;
+  {
     unsigned cand_mask = __ballot_sync(0xffffffffu, cand);
     const int D = a.P.vext + 1;
-    plain = cand ? 1 : 0;
+    const uint32_t* pool32 = (const uint32_t*)a.pool;
     while (cand_mask) {
       const int j = __ffs(cand_mask) - 1;
       cand_mask &= cand_mask - 1;
-      const int ms = __shfl_sync(0xffffffffu, pr.m_start, j);
+      const int rp0 = __shfl_sync(0xffffffffu, pr.rp0, j);
       const int ml = __shfl_sync(0xffffffffu, pr.m_len, j);
-      const int r0 = __shfl_sync(0xffffffffu, pr.rp0, j);
-      const unsigned off16 = __shfl_sync(0xffffffffu, rd.data_off16, j);
-      const int ncg = __shfl_sync(0xffffffffu, (int)rd.n_cigar, j);
-      const int rlo = __shfl_sync(0xffffffffu, ref.lo, j);
-      const int rhi = __shfl_sync(0xffffffffu, ref.hi, j);
-      const uint8_t* seq4 = a.pool + (size_t)off16 * 16 + 4 * (size_t)ncg;
-      bool pl = D < 32;
-      unsigned prev = 0;
-      for (int base = 0; base < ml && pl; base += 32) {
-        const int i = base + lane;
-        bool mm = false, odd = false;
-        if (i < ml) {
-          const int r = r0 + i;
-          const int b = seq4[r >> 1];
-          const int nib = (r & 1) ? (b & 15) : (b >> 4);
-          if (nib != 15) {  // a read 'N' is skipped by the walk and never starts a key
-            const char c = nib == 1 ? 'A' : nib == 2 ? 'C' : nib == 4 ? 'G' : nib == 8 ? 'T' : (char)0;
-            if (c == 0) odd = true;
-            else {
-              const int p = ms + i;
-              const int64_t o = (int64_t)p - a.ref_start;
-              const char rc = (p >= rlo && p <= rhi && o >= 0 && o < a.ref_n) ? a.ref[o] : (char)0;
-              mm = rc != c;
-            }
-          }
+      const int e0 = __shfl_sync(0xffffffffu, E0, j);
+      const size_t sw = __shfl_sync(0xffffffffu, (unsigned long long)seq_word, j);
+      const int w_last = (rp0 + ml - 1) >> 3;
+      bool bad = false;
+      uint32_t carry = 0;
+      for (int w0 = rp0 >> 3; w0 <= w_last && !bad; w0 += 32) {
+        const int wi = w0 + lane;
+        uint32_t nz = 0, special = 0;
+        if (wi <= w_last) {
+          const uint32_t sq = __byte_perm(pool32[sw + wi], 0, 0x0123);  // base 8*wi in the top nibble
+          const int e = e0 + 8 * wi;
+          const uint32_t rf = __funnelshift_l(a.ref4[(e >> 3) + 1], a.ref4[e >> 3], (e & 7) * 4);
+          const int lo = rp0 - 8 * wi > 0 ? rp0 - 8 * wi : 0;
+          const int hi = rp0 + ml - 8 * wi < 8 ? rp0 + ml - 8 * wi : 8;
+          uint32_t vm = 0xffffffffu >> (4 * lo);
+          if (hi < 8) vm &= ~(0xffffffffu >> (4 * hi));
+          nz = nib_any(sq ^ rf) & vm;
+          // read bases other than A, C, G, T (N included): zero nibble, or more than one bit in the nibble
+          special = (~nib_any(sq) | nib_any(sq & (sq - 0x11111111u))) & 0x11111111u & vm;
         }
-        const unsigned m = __ballot_sync(0xffffffffu, mm);
-        const unsigned x = __ballot_sync(0xffffffffu, odd);
-        unsigned near = 0;
-        for (int d = 1; d <= D; ++d) near |= m & ((m << d) | (prev >> (32 - d)));
-        if (near || x) pl = false;
-        prev = m;
+        uint32_t prev = __shfl_up_sync(0xffffffffu, nz, 1);
+        if (lane == 0) prev = carry;
+        uint32_t near = 0;
+        if (D <= 7) {
+          for (int d = 1; d <= D; ++d) near |= nz & __funnelshift_r(nz, prev, 4 * d);
+        } else {
+          near = (nz & (nz - 1)) | (nz && prev ? 1u : 0u);  // conservative: any two mismatches in 16 bases
+          if (__popc(__ballot_sync(0xffffffffu, nz != 0)) > 1) near = 1;
+        }
+        bad = __any_sync(0xffffffffu, (near | special) != 0);
+        carry = __shfl_sync(0xffffffffu, nz, 31);
       }
-      if (lane == j) plain = pl ? 1 : 0;
+      if (lane == j) plain = !bad;
     }
   }
-  // ---- stage 3: exact walk (soft clips, indels, multi-nucleotide keys, non-plain reads) -------------
-  if (pr.ok) {
-    FastDesc* fd = a.descs ? a.descs + item : (FastDesc*)0;
-    const bool only_m = plain == 1 && pr.n_cigar == 1;  // nothing but the matched run: skip the walk entirely
-    if (only_m) {
-      fd->m_start = pr.m_start;
-      fd->m_len = (uint16_t)pr.m_len;
-      fd->rp0 = (uint16_t)pr.rp0;
-      fd->data_off16 = rd.data_off16;
-      fd->n_cigar = rd.n_cigar;
-      fd->nm = (int16_t)pr.nm;
-      fd->l_seq = (uint16_t)rd.l_seq;
-      fd->mapq = (uint8_t)pr.mapq;
-      fd->dir = pr.dir ? 1 : 0;
-      fd->read_idx = (uint32_t)read_idx;
-      // parseCigar.cpp:630 — the -u / --UN overlap test happens before the first op
+  // ---- stage 3: descriptor for plain matched runs; everything else is queued for rv_walk_kernel -----
+  int back = 0, reach = 0;
+  if (item < a.n_items) {
+    GDesc gd;
+    gd.m_start = 0; gd.m_len = 0; gd.rp0 = 0; gd.seq_off4 = 0; gd.l_seq = 0; gd.mapq = 0; gd.dir_nm = 0;
+    if (pr.ok) {
+      // parseCigar.cpp:630 / skipOverlappingReads :182-206 — the -u / --UN test happens once, before the first op
       bool skip = false;
       const bool paired_same = (rd.flag & 1) && rd.mate_same_tid;
       if (a.P.uniq_u && paired_same && !pr.dir && pr.position >= rd.mpos) skip = true;
       if (!skip && a.P.uniq_un && (rd.flag & 1) && paired_same) {
         const int ref_len = rd.end_pos - (rd.pos - 1);
-        bool ov;
-        if (pr.position >= rd.mpos) ov = pr.position <= rd.mpos + ref_len - 1;
-        else ov = false;  // start >= mate_start cannot hold when position < mate_start
-        if (ov) skip = true;
+        // start == position before the first op, so the "position < mate_start" arm can never hold
+        if (pr.position >= rd.mpos && pr.position <= rd.mpos + ref_len - 1) skip = true;
       }
-      if (skip) fd->m_len = 0;
-    } else {
-      walk_read(a.P, dr->r, ri, rd, a.pool, ref, (uint32_t)read_idx, s, pr, fd, plain);
+      bool queue = false;
+      unsigned long long entry = (unsigned long long)item;
+      if (!skip) {
+        if (plain) {
+          gd.m_start = pr.m_start;
+          gd.m_len = (uint16_t)pr.m_len;
+          gd.rp0 = (uint16_t)pr.rp0;
+          gd.seq_off4 = (uint32_t)seq_word;
+          gd.l_seq = (uint16_t)rd.l_seq;
+          gd.mapq = (uint8_t)pr.mapq;
+          gd.dir_nm = (uint8_t)((pr.dir ? 0x80 : 0) | pr.nm);
+          back = rd.pos - pr.m_start;
+          reach = pr.m_start + pr.m_len - rd.pos;
+          // ops other than M/H (soft clips) still need the walk
+          bool only_mh = true;
+          for (int k = 0; k < pr.n_cigar; ++k) {
+            const int o = c_op(pr.cg.op[k]);
+            if (o != OP_M && o != OP_H) only_mh = false;
+          }
+          if (!only_mh) { queue = true; entry |= WALK_PLAIN_DONE; }
+        } else {
+          queue = true;
+        }
+      }
+      if (queue) {
+        cg::coalesced_group g = cg::coalesced_threads();
+        unsigned long long slot = 0;
+        if (g.thread_rank() == 0) slot = atomicAdd(a.walk_count, (unsigned long long)g.size());
+        slot = g.shfl(slot, 0) + g.thread_rank();
+        a.walk_queue[slot] = entry;
+      }
     }
-    if (a.descs && rd.l_seq > *a.max_lseq) atomicMax(a.max_lseq, rd.l_seq);
+    *(uint4*)(a.descs + item) = *(const uint4*)&gd;
   }
-  kept = s.n_kept;
-  bases = s.kept_bases;
-  unsup = s.n_unsup;
-  over = s.n_over;
-  // block-level reduction of the statistics, one atomic per block and counter
-  __shared__ unsigned long long sh[4];
-  if (threadIdx.x < 4) sh[threadIdx.x] = 0;
-  __syncthreads();
+  // ---- statistics and the candidate-window bounds of the gather kernel: one atomic per warp / block ----
+  unsigned long long kept = s.n_kept, bases = s.kept_bases, unsup = s.n_unsup, over = s.n_over;
   for (int off = 16; off > 0; off >>= 1) {
     kept += __shfl_down_sync(0xffffffffu, kept, off);
     bases += __shfl_down_sync(0xffffffffu, bases, off);
     unsup += __shfl_down_sync(0xffffffffu, unsup, off);
     over += __shfl_down_sync(0xffffffffu, over, off);
+    back = max(back, __shfl_down_sync(0xffffffffu, back, off));
+    reach = max(reach, __shfl_down_sync(0xffffffffu, reach, off));
   }
-  if ((threadIdx.x & 31) == 0) {
+  __shared__ unsigned long long sh[4];
+  if (threadIdx.x < 4) sh[threadIdx.x] = 0;
+  __syncthreads();
+  if (lane == 0) {
     if (kept) atomicAdd(&sh[0], kept);
     if (bases) atomicAdd(&sh[1], bases);
     if (unsup) atomicAdd(&sh[2], unsup);
     if (over) atomicAdd(&sh[3], over);
+    if (back > a.reach[0]) atomicMax(a.reach + 0, back);
+    if (reach > a.reach[1]) atomicMax(a.reach + 1, reach);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -282,24 +359,77 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
   }
 }
 
+// The exact CIGAR walk for the queued work items, one per thread (all lanes busy with walks).
+__global__ void __launch_bounds__(128) rv_walk_kernel(PileupArgs a) {
+  const unsigned long long n = *a.walk_count;
+  unsigned long long over = 0, unsup = 0;
+  for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < n;
+       q += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long entry = a.walk_queue[q];
+    const int64_t item = (int64_t)(entry & ~WALK_PLAIN_DONE);
+    const bool plain_done = (entry & WALK_PLAIN_DONE) != 0;
+    const int ri = find_region(a.regions, a.n_regions, item);
+    const DevRegion* dr = a.regions + ri;
+    const int64_t read_idx = dr->r.read_lo + (item - dr->item_base);
+    const rv_read rd = a.reads[read_idx];
+    RefView ref;
+    ref.bases = a.ref;
+    ref.base_pos = a.ref_start;
+    ref.n = a.ref_n;
+    ref.lo = dr->r.ref_lo;
+    ref.hi = dr->r.ref_hi;
+    DeviceSink s;
+    s.a = &a;
+    s.dr = dr;
+    s.counts = a.counts + (size_t)dr->tab_off * RV_POS_U32;
+    s.covtab = a.cov + dr->tab_off;
+    s.kept_bases = s.n_kept = s.n_unsup = s.n_over = s.n_ev = 0;
+    s.goodq = a.P.goodq;
+    s.mute = true;
+    Prep pr;
+    prepare_read(a.P, dr->r, rd, a.pool, ref, s, true, pr);
+    s.mute = false;
+    if (!pr.ok) continue;  // cannot happen: the item was queued because it passed
+    FastDesc scratch;
+    walk_read(a.P, dr->r, ri, rd, a.pool, ref, (uint32_t)read_idx, s, pr, plain_done ? &scratch : (FastDesc*)0,
+              plain_done ? 1 : 0);
+    over += s.n_over;
+    unsup += s.n_unsup;
+  }
+  if (over) atomicAdd(&a.stats->n_overflow, over);
+  if (unsup) atomicAdd(&a.stats->n_unsupported, unsup);
+}
+
 // ------------------------------------------------------------------------------------------------
-// Gather pileup: one lane per reference position, no atomics.  A CTA owns GATHER_TILE consecutive
-// positions of one region; it stages the fast-path descriptors whose matched run overlaps the tile in
-// shared memory (chunks of GATHER_TILE), then every lane walks the staged list and accumulates the
-// observations that fall on its position: the dominant allele in registers, the rare other alleles in
-// a conflict-free private shared-memory row ([allele][field][lane]).  Results are added to the dense
-// table with plain read-modify-write (the position is owned by exactly one lane).
+// Gather pileup: one lane per table position, no atomics.
+// A CTA owns GATHER_TILE consecutive table positions of one region (halo included: the kernel writes
+// every row of the table, so no memset is needed).  Per round it
+//   1. reads up to 256 descriptors of the candidate window, clips their matched run to the tile and sizes the
+//      16-byte chunks of packed bases / qualities each needs (block prefix sum = arena offsets),
+//   2. copies those chunks global -> shared, one warp per read (coalesced LDG.128 / STS.128),
+//   3. appends each staged read to the list of every warp whose 32 positions it overlaps,
+//   4. lets every lane walk its warp's list: one broadcast record + two shared-memory byte loads per
+//      observation; the reference allele accumulates in registers, anything else goes straight to the
+//      lane's own table row (plain read-modify-write: the position is owned by exactly this lane).
+// pstd/qstd ("two observations differ", parseCigar.cpp:902-914) = AND-reduction != OR-reduction of (tp, q).
 // ------------------------------------------------------------------------------------------------
+static const int ARENA_CHUNKS = 2048;  // 32 KB of staged read bytes per round
+
 struct GatherArgs {
   double goodq;
   const DevRegion* regions;
   int n_regions;
   const rv_read* reads;
-  const FastDesc* descs;
+  const GDesc* descs;
   const uint8_t* pool;
+  const char* ref;
+  int32_t ref_start;
+  int64_t ref_n;
   uint32_t* counts;
   uint32_t* cov;
-  const int32_t* max_lseq;
+  const int32_t* reach;
+  int64_t* tile_range;  // [2 * tile]: candidate read range of every tile
+  int64_t n_tiles;
 };
 
 __device__ __forceinline__ int find_region_by_tile(const DevRegion* regs, int n, int64_t tile) {
@@ -312,133 +442,209 @@ __device__ __forceinline__ int find_region_by_tile(const DevRegion* regs, int n,
   return lo;
 }
 
-__global__ void __launch_bounds__(GATHER_TILE) rv_gather_kernel(GatherArgs a) {
-  __shared__ FastDesc s_list[GATHER_TILE];
-  __shared__ uint32_t s_other[4 * 8 * GATHER_TILE];  // [allele][field][lane]: rare non-dominant alleles
-  __shared__ int s_warp_cnt[GATHER_TILE / 32];
-  __shared__ int s_count;
-  const int tid = threadIdx.x;
-  const int ri = find_region_by_tile(a.regions, a.n_regions, (int64_t)blockIdx.x);
-  const DevRegion* dr = a.regions + ri;
-  const int p_lo = dr->r.start + (int)((int64_t)blockIdx.x - dr->tile_base) * GATHER_TILE;
-  int p_hi = p_lo + GATHER_TILE - 1;
-  if (p_hi > dr->r.end) p_hi = dr->r.end;
-  const int p = p_lo + tid;
-  const bool live = p <= p_hi;
-  // candidate items: reads whose start lies in [p_lo - 2 Lmax, p_hi + Lmax] (|m_start - pos| <= l_seq, m_len <= l_seq)
-  const int lmax = *a.max_lseq;
-  int64_t lo = dr->r.read_lo, hi = dr->r.read_hi;
-  {
-    int64_t x = lo, y = hi;
-    const int want = p_lo - 2 * lmax;
-    while (x < y) { int64_t m = (x + y) >> 1; if (a.reads[m].pos < want) x = m + 1; else y = m; }
+// candidate reads of every tile: read start in (c_lo - max_reach, c_hi + max_back]  (one thread per tile)
+__global__ void rv_tile_index_kernel(GatherArgs a) {
+  const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile >= a.n_tiles) return;
+  const DevRegion* dr = a.regions + find_region_by_tile(a.regions, a.n_regions, tile);
+  const int p_lo = dr->first_pos + (int)(tile - dr->tile_base) * GATHER_TILE;
+  const int c_lo = p_lo > dr->r.start ? p_lo : dr->r.start;
+  const int c_hi = p_lo + GATHER_TILE - 1 < dr->r.end ? p_lo + GATHER_TILE - 1 : dr->r.end;
+  int64_t lo = dr->r.read_lo, hi = dr->r.read_lo;
+  if (c_lo <= c_hi) {
+    const int want_lo = c_lo - a.reach[1];  // pos > want_lo
+    const int want_hi = c_hi + a.reach[0];  // pos <= want_hi
+    int64_t x = dr->r.read_lo, y = dr->r.read_hi;
+    while (x < y) { const int64_t m = (x + y) >> 1; if (a.reads[m].pos <= want_lo) x = m + 1; else y = m; }
     lo = x;
-    y = hi;
-    const int wanthi = p_hi + lmax;
-    while (x < y) { int64_t m = (x + y) >> 1; if (a.reads[m].pos <= wanthi) x = m + 1; else y = m; }
+    y = dr->r.read_hi;
+    while (x < y) { const int64_t m = (x + y) >> 1; if (a.reads[m].pos <= want_hi) x = m + 1; else y = m; }
     hi = x;
   }
-  for (int k = tid; k < 4 * 8 * GATHER_TILE; k += GATHER_TILE) s_other[k] = 0;
-  int a0 = -1;
-  uint32_t r_fwd = 0, r_rev = 0, r_tp = 0, r_q = 0, r_mq = 0, r_nm = 0, r_hi = 0, r_first = 0, r_flags = 0;
-  uint32_t n_obs = 0, other_mask = 0;
-  const FastDesc* item_desc = a.descs + dr->item_base - dr->r.read_lo;  // desc of read index i = item_desc[i]
-  for (int64_t base = lo; base < hi; base += GATHER_TILE) {
-    // ---- stage: compact the overlapping descriptors of this chunk into shared memory ----
-    int64_t i = base + tid;
-    FastDesc d;
+  a.tile_range[2 * tile] = lo;
+  a.tile_range[2 * tile + 1] = hi;
+}
+
+__device__ __forceinline__ int nib_allele(int nib) { return (nib >> 1) - (nib >> 3); }  // 1,2,4,8 -> 0,1,2,3
+
+__global__ void __launch_bounds__(GATHER_TILE) rv_gather_kernel(GatherArgs a) {
+  __shared__ uint4 s_arena[ARENA_CHUNKS];
+  __shared__ int4 s_rec[GATHER_TILE];        // {rel_start, seq byte offset, qual byte offset, m_len | par<<16 | dir<<17}
+  __shared__ uint32_t s_add[GATHER_TILE];    // mapq | nm << 16
+  __shared__ uint4 s_copy[GATHER_TILE];      // {first seq chunk, first qual chunk, n seq chunks | n qual chunks << 8, arena chunk}
+  __shared__ uint8_t s_wlist[GATHER_TILE / 32][GATHER_TILE];
+  __shared__ int s_wcnt[GATHER_TILE / 32];
+  __shared__ int s_wsum[GATHER_TILE / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t tile = blockIdx.x;
+  const DevRegion* dr = a.regions + find_region_by_tile(a.regions, a.n_regions, tile);
+  const int p_lo = dr->first_pos + (int)(tile - dr->tile_base) * GATHER_TILE;
+  const int c_lo = p_lo > dr->r.start ? p_lo : dr->r.start;  // positions that can receive observations
+  const int c_hi = p_lo + GATHER_TILE - 1 < dr->r.end ? p_lo + GATHER_TILE - 1 : dr->r.end;
+  const int x = tid;
+  const int p = p_lo + x;
+  const bool in_table = p - dr->first_pos < dr->n_pos;
+  const bool live = p >= c_lo && p <= c_hi;
+  // the lane's reference allele, as a BAM nibble (0 = none: every observation takes the row path)
+  int refnib = 0;
+  if (live && p >= dr->r.ref_lo && p <= dr->r.ref_hi && p >= a.ref_start && (int64_t)(p - a.ref_start) < a.ref_n) {
+    const char c = a.ref[p - a.ref_start];
+    refnib = c == 'A' ? 1 : c == 'C' ? 2 : c == 'G' ? 4 : c == 'T' ? 8 : 0;
+  }
+  const int thr = (int)ceil(a.goodq);  // integer q >= goodq
+  const int64_t t_row = dr->tab_off + (p - dr->first_pos);
+  uint32_t* const row0 = a.counts + (size_t)t_row * RV_POS_U32;
+  uint32_t n_ref = 0, n_rev = 0, sum_tp = 0, sum_q = 0, sum_mapq = 0, sum_nm = 0, n_hi = 0;
+  uint32_t v_and = 0xffffffffu, v_or = 0, v_last = 0, n_other = 0, other_mask = 0;
+  const int64_t lo = a.tile_range[2 * tile], hi = a.tile_range[2 * tile + 1];
+  const GDesc* item_desc = a.descs + (dr->item_base - dr->r.read_lo);  // descriptor of read index i
+  const uint4* pool16 = (const uint4*)a.pool;
+  const uint8_t* arena = (const uint8_t*)s_arena;
+
+  for (int64_t base = lo; base < hi;) {
+    // ---- 1. descriptors of this round, clipped to the tile ------------------------------------------
+    if (tid < GATHER_TILE / 32) s_wcnt[tid] = 0;
+    const int64_t i = base + tid;
+    GDesc d;
+    d.m_len = 0;
+    if (i < hi) *(uint4*)&d = *(const uint4*)(item_desc + i);
     bool take = false;
-    if (i < hi) {
-      d = item_desc[i];
-      take = d.m_len != 0 && d.m_start <= p_hi && d.m_start + (int)d.m_len > p_lo;
+    int ns = 0, nq = 0, n_lo = 0;
+    size_t s_first = 0, q_first = 0;
+    if (d.m_len != 0) {
+      const int k_lo = c_lo - d.m_start > 0 ? c_lo - d.m_start : 0;
+      const int k_hi = c_hi + 1 - d.m_start < (int)d.m_len ? c_hi + 1 - d.m_start : (int)d.m_len;
+      if (k_lo < k_hi) {
+        take = true;
+        n_lo = d.rp0 + k_lo;
+        const int n_hi_ = d.rp0 + k_hi;
+        const size_t sb = (size_t)d.seq_off4 * 4;
+        const size_t qb = sb + ((d.l_seq + 1) >> 1);
+        s_first = sb + (n_lo >> 1);
+        q_first = qb + n_lo;
+        ns = (int)(((sb + ((n_hi_ - 1) >> 1)) >> 4) - (s_first >> 4)) + 1;
+        nq = (int)(((qb + n_hi_ - 1) >> 4) - (q_first >> 4)) + 1;
+      }
     }
-    unsigned bal = __ballot_sync(0xffffffffu, take);
-    if ((tid & 31) == 0) s_warp_cnt[tid >> 5] = __popc(bal);
+    // block inclusive scan of (chunks needed | take << 16)
+    const int mine = (ns + nq) | (take ? 1 << 16 : 0);
+    int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += y;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
     __syncthreads();
-    int off = 0;
-    for (int wq = 0; wq < (tid >> 5); ++wq) off += s_warp_cnt[wq];
-    if (take) s_list[off + __popc(bal & ((1u << (tid & 31)) - 1u))] = d;
-    if (tid == GATHER_TILE - 1) s_count = off + __popc(bal);
+    for (int w = 0; w < warp; ++w) incl += s_wsum[w];
+    const int chunks_incl = incl & 0xffff;
+    const bool fits = chunks_incl <= ARENA_CHUNKS;  // a prefix of the round (the scan is monotone)
+    const bool staged = take && fits;
+    const int n_take = __syncthreads_count(fits);
+    const int n_slots = __syncthreads_count(staged);
+    if (staged) {
+      const int slot = (incl >> 16) - 1;
+      const int chunk0 = chunks_incl - (ns + nq);
+      const int rel_start = d.m_start - p_lo;
+      const int n0 = (int)d.rp0 - rel_start;  // read offset of the base under tile coordinate 0
+      const int par = n0 & 1;
+      int4 r;
+      r.x = rel_start;
+      r.y = chunk0 * 16 + (int)(s_first & 15) - (n_lo >> 1) + ((n0 - par) >> 1);  // + ((x + par) >> 1)
+      r.z = (chunk0 + ns) * 16 + (int)(q_first & 15) - n_lo + n0;                  // + x
+      r.w = (int)d.m_len | (par << 16) | ((d.dir_nm >> 7) << 17);
+      s_rec[slot] = r;
+      s_add[slot] = (uint32_t)d.mapq | ((uint32_t)(d.dir_nm & 0x7f) << 16);
+      s_copy[slot] = make_uint4((uint32_t)(s_first >> 4), (uint32_t)(q_first >> 4), (uint32_t)(ns | (nq << 8)), (uint32_t)chunk0);
+      const int x_lo = rel_start > c_lo - p_lo ? rel_start : c_lo - p_lo;
+      const int x_hi = rel_start + (int)d.m_len - 1 < c_hi - p_lo ? rel_start + (int)d.m_len - 1 : c_hi - p_lo;
+      for (int w = x_lo >> 5; w <= (x_hi >> 5); ++w) s_wlist[w][atomicAdd(&s_wcnt[w], 1)] = (uint8_t)slot;
+    }
     __syncthreads();
-    const int cnt = s_count;
-    // ---- walk the staged list ----
-    if (live) {
-      for (int j = 0; j < cnt; ++j) {
-        const int m_start = s_list[j].m_start;
-        const int m_len = s_list[j].m_len;
-        const int k = p - m_start;
-        if (k < 0 || k >= m_len) continue;
-        const FastDesc& e = s_list[j];
-        const uint8_t* var = a.pool + (size_t)e.data_off16 * 16 + 4 * (size_t)e.n_cigar;
-        const int r = (int)e.rp0 + k;
-        const int b = var[r >> 1];
-        const int nib = (r & 1) ? (b & 15) : (b >> 4);
-        const int al = nib == 1 ? 0 : nib == 2 ? 1 : nib == 4 ? 2 : nib == 8 ? 3 : -1;
-        if (al < 0) continue;  // N
-        const uint32_t q = var[((e.l_seq + 1) >> 1) + r];
-        const uint32_t tp = (uint32_t)(k < m_len - k ? k + 1 : m_len - k);
-        const uint32_t hiq = (double)q >= a.goodq ? 1u : 0u;
-        const uint32_t packed = (tp & 0xffffu) | (q << 16);
-        n_obs++;
-        if (a0 < 0) a0 = al;
-        if (al == a0) {
-          if (e.dir) r_rev++; else r_fwd++;
-          r_tp += tp; r_q += q; r_mq += e.mapq; r_nm += (uint32_t)(int)e.nm; r_hi += hiq;
-          if (r_first == 0) r_first = packed | (1u << 31);
-          else {
-            if ((r_first & 0xffffu) != tp) r_flags |= 1u << 24;
-            if (((r_first >> 16) & 0xffu) != q) r_flags |= 1u << 25;
-          }
-        } else {
-          uint32_t* o = s_other + (size_t)al * 8 * GATHER_TILE + tid;
-          o[(e.dir ? RV_F_REV : RV_F_FWD) * GATHER_TILE] += 1;
-          o[RV_F_SUM_TP * GATHER_TILE] += tp;
-          o[RV_F_SUM_Q * GATHER_TILE] += q;
-          o[RV_F_SUM_MAPQ * GATHER_TILE] += e.mapq;
-          o[RV_F_SUM_NM * GATHER_TILE] += (uint32_t)(int)e.nm;
-          o[RV_F_HI * GATHER_TILE] += hiq;
-          uint32_t w = o[RV_F_STD * GATHER_TILE];
-          if (w == 0) w = packed | (1u << 31);
-          else {
-            if ((w & 0xffffu) != tp) w |= 1u << 24;
-            if (((w >> 16) & 0xffu) != q) w |= 1u << 25;
-          }
-          o[RV_F_STD * GATHER_TILE] = w;
-          other_mask |= 1u << al;
-        }
+    // ---- 2. stage the bytes: one warp per read, one 16-byte chunk per lane ---------------------------
+    for (int sidx = warp; sidx < n_slots; sidx += GATHER_TILE / 32) {
+      const uint4 c = s_copy[sidx];
+      const int cns = (int)(c.z & 0xff), cnq = (int)(c.z >> 8);
+      if (lane < cns + cnq) {
+        const size_t src = lane < cns ? (size_t)c.x + lane : (size_t)c.y + (lane - cns);
+        s_arena[c.w + lane] = pool16[src];
       }
     }
     __syncthreads();
-  }
-  if (!live || n_obs == 0) return;
-  // ---- add into the dense table (K1's atomics for the exact path have completed) ----
-  const int64_t t = dr->tab_off + (p - dr->first_pos);
-  uint32_t* row0 = a.counts + (size_t)t * RV_POS_U32;
-  a.cov[t] += n_obs;
-  for (int al = 0; al < 4; ++al) {
-    uint32_t v[8];
-    if (al == a0) {
-      v[RV_F_FWD] = r_fwd; v[RV_F_REV] = r_rev; v[RV_F_SUM_TP] = r_tp; v[RV_F_SUM_Q] = r_q; v[RV_F_SUM_MAPQ] = r_mq;
-      v[RV_F_SUM_NM] = r_nm; v[RV_F_HI] = r_hi; v[RV_F_STD] = r_first | r_flags;
-    } else if (other_mask & (1u << al)) {
-      const uint32_t* o = s_other + (size_t)al * 8 * GATHER_TILE + tid;
-      for (int f = 0; f < 8; ++f) v[f] = o[f * GATHER_TILE];
-    } else continue;
-    uint4* row4 = (uint4*)(row0 + al * RV_ROW_U32);
-    uint4 x = row4[0], y = row4[1];
-    x.x += v[0]; x.y += v[1]; x.z += v[2]; x.w += v[3];
-    y.x += v[4]; y.y += v[5]; y.z += v[6];
-    const uint32_t mine = v[RV_F_STD];
-    uint32_t w = y.w;
-    if ((w & (1u << 31)) == 0) w |= mine;  // no first value recorded yet (w can only hold nothing here)
-    else {
-      w |= mine & (3u << 24);
-      if ((w & 0xffffu) != (mine & 0xffffu)) w |= 1u << 24;
-      if (((w >> 16) & 0xffu) != ((mine >> 16) & 0xffu)) w |= 1u << 25;
+    // ---- 3. every lane walks its warp's list ----------------------------------------------------------
+    if (live) {
+      const int cnt = s_wcnt[warp];
+      uint32_t add_acc = 0;
+      for (int j = 0; j < cnt; ++j) {
+        const int slot = s_wlist[warp][j];
+        const int4 r = s_rec[slot];
+        const int m_len = r.w & 0xffff;
+        const int k = x - r.x;
+        if ((unsigned)k >= (unsigned)m_len) continue;
+        const uint32_t q = arena[r.z + x];
+        const int t = x + ((r.w >> 16) & 1);
+        const int sbyte = arena[r.y + (t >> 1)];
+        const int nib = (t & 1) ? (sbyte & 15) : (sbyte >> 4);
+        const uint32_t tp = (uint32_t)(k + 1 < m_len - k ? k + 1 : m_len - k);
+        const uint32_t v = tp | (q << 16);
+        const uint32_t hiq = (int)q >= thr ? 1u : 0u;
+        const uint32_t dir = (uint32_t)(r.w >> 17) & 1u;
+        if (nib == refnib) {
+          n_ref++;
+          n_rev += dir;
+          sum_tp += tp;
+          sum_q += q;
+          add_acc += s_add[slot];
+          n_hi += hiq;
+          v_and &= v;
+          v_or |= v;
+          v_last = v;
+        } else {
+          // a base that differs from the reference: the lane's own row of that allele, read-modify-write
+          const int al = nib_allele(nib);
+          const uint32_t ad = s_add[slot];
+          uint4* row4 = (uint4*)(row0 + al * RV_ROW_U32);
+          uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
+          if (other_mask & (1u << al)) { ra = row4[0]; rb = row4[1]; }
+          ra.x += 1u - dir; ra.y += dir; ra.z += tp; ra.w += q;
+          rb.x += ad & 0xffffu; rb.y += ad >> 16; rb.z += hiq;
+          uint32_t w = rb.w;
+          if ((w >> 31) == 0) w = v | (1u << 31);
+          else {
+            if ((w ^ v) & 0xffffu) w |= 1u << 24;
+            if ((w ^ v) & 0xff0000u) w |= 1u << 25;
+          }
+          rb.w = w;
+          row4[0] = ra;
+          row4[1] = rb;
+          other_mask |= 1u << al;
+          n_other++;
+        }
+      }
+      sum_mapq += add_acc & 0xffffu;  // at most 256 reads per round: neither half can overflow
+      sum_nm += add_acc >> 16;
     }
-    y.w = w;
-    row4[0] = x;
-    row4[1] = y;
+    __syncthreads();
+    base += n_take;
+  }
+  if (!in_table) return;
+  // ---- write the position: the reference allele from registers, untouched alleles as zeros ------------
+  a.cov[t_row] = n_ref + n_other;
+  const int a0 = refnib ? nib_allele(refnib) : -1;
+#pragma unroll
+  for (int al = 0; al < 4; ++al) {
+    if (other_mask & (1u << al)) continue;
+    uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
+    if (al == a0 && n_ref) {
+      ra = make_uint4(n_ref - n_rev, n_rev, sum_tp, sum_q);
+      uint32_t w = v_last | (1u << 31);
+      if ((v_and ^ v_or) & 0xffffu) w |= 1u << 24;
+      if ((v_and ^ v_or) & 0xff0000u) w |= 1u << 25;
+      rb = make_uint4(sum_mapq, sum_nm, n_hi, w);
+    }
+    uint4* row4 = (uint4*)(row0 + al * RV_ROW_U32);
+    row4[0] = ra;
+    row4[1] = rb;
   }
 }
 
@@ -465,7 +671,10 @@ struct ScoreArgs {
 struct DeviceEmit {
   const ScoreArgs* a;
   __device__ __forceinline__ void emit(const rv_variant& v) {
-    unsigned long long slot = atomicAdd(&a->stats->n_variants, 1ull);
+    cg::coalesced_group g = cg::coalesced_threads();
+    unsigned long long slot = 0;
+    if (g.thread_rank() == 0) slot = atomicAdd(&a->stats->n_variants, (unsigned long long)g.size());
+    slot = g.shfl(slot, 0) + g.thread_rank();
     if (slot < a->max_variants) a->variants[slot] = v;
   }
 };
@@ -595,8 +804,13 @@ struct rv_ctx {
   DevStats* d_stats;
   double* d_lgt;
   int lgt_n;
-  FastDesc* d_descs;
-  int32_t* d_max_lseq;
+  GDesc* d_descs;
+  int32_t* d_reach;
+  uint32_t* d_ref4;
+  int64_t* d_tile_range;
+  int64_t tile_cap;
+  unsigned long long* d_walk_queue;
+  unsigned long long* d_walk_count;
   int64_t n_tiles;
   bool use_gather;
   // batch state
@@ -705,7 +919,7 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   ctx->launches = 0;
   ctx->d_reads = NULL; ctx->d_pool = NULL; ctx->d_ref = NULL; ctx->d_counts = NULL; ctx->d_cov = NULL;
   ctx->d_events = NULL; ctx->d_variants = NULL; ctx->d_patch = NULL; ctx->d_patch_first = NULL;
-  ctx->d_patch_count = NULL; ctx->d_regions = NULL; ctx->d_max_rl = NULL; ctx->d_stats = NULL; ctx->d_lgt = NULL; ctx->d_descs = NULL; ctx->d_max_lseq = NULL; ctx->n_tiles = 0;
+  ctx->d_patch_count = NULL; ctx->d_regions = NULL; ctx->d_max_rl = NULL; ctx->d_stats = NULL; ctx->d_lgt = NULL; ctx->d_descs = NULL; ctx->d_reach = NULL; ctx->d_ref4 = NULL; ctx->d_tile_range = NULL; ctx->tile_cap = 0; ctx->d_walk_queue = NULL; ctx->d_walk_count = NULL; ctx->n_tiles = 0;
   ctx->use_gather = getenv("RV_NO_GATHER") == NULL;
   ctx->h_counts = NULL; ctx->h_cov = NULL; ctx->h_tab_cap = 0; ctx->h_events = NULL; ctx->h_events_cap = 0;
   ctx->h_variants = NULL; ctx->h_variants_cap = 0; ctx->h_max_rl = NULL; ctx->h_rows = NULL; ctx->h_rows_cap = 0; ctx->d_scratch = NULL; ctx->scratch_cap = 0;
@@ -721,7 +935,7 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   CK(cudaEventCreate(&ctx->tev1));
   const rv_limits& L = ctx->L;
   CK(cudaMalloc(&ctx->d_reads, sizeof(rv_read) * (size_t)L.max_reads));
-  CK(cudaMalloc(&ctx->d_pool, (size_t)L.max_read_bytes));
+  CK(cudaMalloc(&ctx->d_pool, (size_t)L.max_read_bytes + 64));  // the gather kernel copies whole 16-byte chunks
   CK(cudaMalloc(&ctx->d_ref, (size_t)L.max_ref_bases));
   CK(cudaMalloc(&ctx->d_counts, sizeof(uint32_t) * RV_POS_U32 * (size_t)(L.max_positions + 1)));
   CK(cudaMalloc(&ctx->d_cov, sizeof(uint32_t) * (size_t)(L.max_positions + 1)));
@@ -734,8 +948,14 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   CK(cudaMalloc(&ctx->d_max_rl, sizeof(int32_t) * (size_t)L.max_regions));
   CK(cudaMalloc(&ctx->d_stats, sizeof(DevStats)));
   // work items are (region, read) pairs: a read overlapping two tiles is walked once per tile
-  CK(cudaMalloc(&ctx->d_descs, sizeof(FastDesc) * (size_t)(2 * L.max_reads + 1024)));
-  CK(cudaMalloc(&ctx->d_max_lseq, sizeof(int32_t)));
+  CK(cudaMalloc(&ctx->d_descs, sizeof(GDesc) * (size_t)(2 * L.max_reads + 1024)));
+  CK(cudaMalloc(&ctx->d_reach, 2 * sizeof(int32_t)));
+  CK(cudaMalloc(&ctx->d_ref4, sizeof(uint32_t) * (size_t)(L.max_ref_bases / 8 + 16)));
+  // gather tiles: every region rounds its table (length + 2*halo) up to whole tiles
+  ctx->tile_cap = L.max_positions / GATHER_TILE + L.max_regions + 1;
+  CK(cudaMalloc(&ctx->d_tile_range, 2 * sizeof(int64_t) * (size_t)ctx->tile_cap));
+  CK(cudaMalloc(&ctx->d_walk_queue, sizeof(unsigned long long) * (size_t)(2 * L.max_reads + 1024)));
+  CK(cudaMalloc(&ctx->d_walk_count, sizeof(unsigned long long)));
   CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->stream));
   ctx->lgt_n = 1 << 20;
   CK(cudaMalloc(&ctx->d_lgt, sizeof(double) * (size_t)ctx->lgt_n));
@@ -756,7 +976,11 @@ void rv_destroy(rv_ctx* ctx) {
   cudaFree(ctx->d_lgt);
   cudaFree(ctx->d_scratch);
   cudaFree(ctx->d_descs);
-  cudaFree(ctx->d_max_lseq);
+  cudaFree(ctx->d_reach);
+  cudaFree(ctx->d_ref4);
+  cudaFree(ctx->d_tile_range);
+  cudaFree(ctx->d_walk_queue);
+  cudaFree(ctx->d_walk_count);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
   if (ctx->h_cov) cudaFreeHost(ctx->h_cov);
   if (ctx->h_events) cudaFreeHost(ctx->h_events);
@@ -793,6 +1017,10 @@ int rv_set_reference(rv_ctx* ctx, int32_t ref_start, int64_t n, const char* base
   CK(cudaMemcpyAsync(ctx->d_ref, bases, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
   ctx->ref_start = ref_start;
   ctx->ref_n = n;
+  const int64_t n_words = n / 8 + 16;
+  rv_pack_ref_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_ref, n, ctx->d_ref4, n_words);
+  ctx->launches++;
+  CK(cudaGetLastError());
   return RV_OK;
 }
 
@@ -833,12 +1061,13 @@ int rv_set_regions(rv_ctx* ctx, const rv_region* regs, int32_t n) {
     d.tab_off = tab;
     d.item_base = items;
     d.tile_base = tiles;
-    tiles += (d.r.end - d.r.start + 1 + GATHER_TILE - 1) / GATHER_TILE;
+    tiles += (d.n_pos + GATHER_TILE - 1) / GATHER_TILE;
     tab += d.n_pos;
     items += d.r.read_hi - d.r.read_lo;
     ctx->h_max_rl[i] = d.r.max_read_len_in;
   }
   if (tab > ctx->L.max_positions) return fail(ctx, RV_ERR_OVERFLOW, "regions need more table positions than limits.max_positions");
+  if (tiles > ctx->tile_cap) return fail(ctx, RV_ERR_OVERFLOW, "regions need more gather tiles than the context was sized for");
   if (items > 2 * ctx->L.max_reads + 1024)
     return fail(ctx, RV_ERR_OVERFLOW, "more (region, read) work items than 2 x limits.max_reads");
   ctx->n_positions = tab;
@@ -861,9 +1090,10 @@ int rv_pileup(rv_ctx* ctx) {
   if (!ctx->reads_dev_view) return fail(ctx, RV_ERR_STATE, "rv_push_reads has not been called");
   CK(cudaSetDevice(ctx->device));
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  CK(cudaMemsetAsync(ctx->d_counts, 0, sizeof(uint32_t) * RV_POS_U32 * (size_t)(ctx->n_positions + 1), ctx->stream));
-  CK(cudaMemsetAsync(ctx->d_cov, 0, sizeof(uint32_t) * (size_t)(ctx->n_positions + 1), ctx->stream));
+  // no table memset: rv_gather_kernel stores every row (halo included) before rv_walk_kernel adds to them
   CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_walk_count, 0, sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_reach, 0, 2 * sizeof(int32_t), ctx->stream));
   PileupArgs a;
   a.P = ctx->P;
   a.regions = ctx->d_regions;
@@ -872,6 +1102,7 @@ int rv_pileup(rv_ctx* ctx) {
   a.reads = ctx->reads_dev_view;
   a.pool = ctx->pool_dev_view;
   a.ref = ctx->d_ref;
+  a.ref4 = ctx->d_ref4;
   a.ref_start = ctx->ref_start;
   a.ref_n = ctx->ref_n;
   a.counts = ctx->d_counts;
@@ -880,32 +1111,43 @@ int rv_pileup(rv_ctx* ctx) {
   a.max_events = (unsigned long long)ctx->L.max_events;
   a.max_rl = ctx->d_max_rl;
   a.stats = ctx->d_stats;
-  a.descs = ctx->use_gather ? ctx->d_descs : NULL;
-  a.max_lseq = ctx->d_max_lseq;
+  a.descs = ctx->d_descs;
+  a.reach = ctx->d_reach;
+  a.force_exact = ctx->use_gather ? 0 : 1;
+  a.walk_queue = ctx->d_walk_queue;
+  a.walk_count = ctx->d_walk_count;
   if (ctx->n_items > 0) {
-    if (ctx->use_gather) {
-      CK(cudaMemsetAsync(ctx->d_descs, 0, sizeof(FastDesc) * (size_t)ctx->n_items, ctx->stream));
-      CK(cudaMemsetAsync(ctx->d_max_lseq, 0, sizeof(int32_t), ctx->stream));
-    }
     unsigned grid = (unsigned)((ctx->n_items + 127) / 128);
     rv_pileup_kernel<<<grid, 128, 0, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
-    if (ctx->use_gather && ctx->n_tiles > 0) {
-      GatherArgs g;
-      g.goodq = ctx->P.goodq;
-      g.regions = ctx->d_regions;
-      g.n_regions = (int)ctx->regions.size();
-      g.reads = ctx->reads_dev_view;
-      g.descs = ctx->d_descs;
-      g.pool = ctx->pool_dev_view;
-      g.counts = ctx->d_counts;
-      g.cov = ctx->d_cov;
-      g.max_lseq = ctx->d_max_lseq;
-      rv_gather_kernel<<<(unsigned)ctx->n_tiles, GATHER_TILE, 0, ctx->stream>>>(g);
-      ctx->launches++;
-      CK(cudaGetLastError());
-    }
+  }
+  if (ctx->n_tiles > 0) {
+    GatherArgs g;
+    g.goodq = ctx->P.goodq;
+    g.regions = ctx->d_regions;
+    g.n_regions = (int)ctx->regions.size();
+    g.reads = ctx->reads_dev_view;
+    g.descs = ctx->d_descs;
+    g.pool = ctx->pool_dev_view;
+    g.ref = ctx->d_ref;
+    g.ref_start = ctx->ref_start;
+    g.ref_n = ctx->ref_n;
+    g.counts = ctx->d_counts;
+    g.cov = ctx->d_cov;
+    g.reach = ctx->d_reach;
+    g.tile_range = ctx->d_tile_range;
+    g.n_tiles = ctx->n_tiles;
+    rv_tile_index_kernel<<<(unsigned)((ctx->n_tiles + 127) / 128), 128, 0, ctx->stream>>>(g);
+    rv_gather_kernel<<<(unsigned)ctx->n_tiles, GATHER_TILE, 0, ctx->stream>>>(g);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+  }
+  if (ctx->n_items > 0) {
+    // the queue length is only known on the device: a fixed grid of grid-stride threads
+    rv_walk_kernel<<<148 * 8, 128, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
   }
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   CK(cudaMemcpyAsync(&ctx->h_stats, ctx->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, ctx->stream));
