@@ -40,13 +40,10 @@ struct RefView {
 };
 
 RV_HD char nt16_char(int nib) {
-  // seq_nt16_str "=ACMGRSVTWYHKDBN" packed 4 chars per word would also do; a switch keeps it in registers
-  switch (nib) {
-    case 1: return 'A'; case 2: return 'C'; case 4: return 'G'; case 8: return 'T'; case 15: return 'N';
-    case 0: return '='; case 3: return 'M'; case 5: return 'R'; case 6: return 'S'; case 7: return 'V';
-    case 9: return 'W'; case 10: return 'Y'; case 11: return 'H'; case 12: return 'K'; case 13: return 'D';
-    default: return 'B';
-  }
+  // seq_nt16_str "=ACMGRSVTWYHKDBN" as two 64-bit literals (a switch diverges and costs a jump table)
+  const unsigned long long lo = 0x565352474d43413dull;  // "=ACMGRSV"
+  const unsigned long long hi = 0x4e42444b48595754ull;  // "TWYHKDBN"
+  return (char)(((nib & 8) ? hi : lo) >> (8 * (nib & 7)));
 }
 RV_HD int allele_of(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
 RV_HD bool is_atgc(char c) { return c == 'A' || c == 'T' || c == 'G' || c == 'C'; }

@@ -87,6 +87,9 @@ struct DeviceSink {
   uint32_t* covtab;
   double goodq;
   int kept_bases, n_kept, n_unsup, n_over, n_ev;
+  uint32_t* pend_row;
+  uint32_t pend_old, pend_mine;
+  bool pend;
   bool mute;  // rv_walk_kernel re-runs prepare_read: its statistics were already counted by rv_pileup_kernel
   __device__ __forceinline__ bool idx_of(int pos, int* idx) {
     int i = pos - dr->first_pos;
@@ -104,14 +107,24 @@ struct DeviceSink {
     atomicAdd(row + RV_F_SUM_MAPQ, (uint32_t)mapq);
     if (nm) atomicAdd(row + RV_F_SUM_NM, (uint32_t)nm);
     if ((double)q >= goodq) atomicAdd(row + RV_F_HI, 1u);
-    // pstd/qstd: "two observations differ" == "some observation differs from the first one recorded"
-    uint32_t mine = ((uint32_t)tp & 0xffffu) | (((uint32_t)q & 0xffu) << 16) | (1u << 31);
-    uint32_t old = atomicCAS(row + RV_F_STD, 0u, mine);
+    // pstd/qstd: "two observations differ" == "some observation differs from the first one recorded".
+    // The compare-and-swap result is consumed one observation later (resolve), so its round trip to L2
+    // overlaps the walk of the next base instead of stalling this one.
+    resolve();
+    pend_row = row + RV_F_STD;
+    pend_mine = ((uint32_t)tp & 0xffffu) | (((uint32_t)q & 0xffu) << 16) | (1u << 31);
+    pend_old = atomicCAS(pend_row, 0u, pend_mine);
+    pend = true;
+  }
+  __device__ __forceinline__ void resolve() {
+    if (!pend) return;
+    pend = false;
+    const uint32_t old = pend_old;
     if (old != 0u) {
       uint32_t bits = 0;
-      if ((old & 0xffffu) != ((uint32_t)tp & 0xffffu)) bits |= 1u << 24;
-      if (((old >> 16) & 0xffu) != ((uint32_t)q & 0xffu)) bits |= 1u << 25;
-      if (bits & ~old) atomicOr(row + RV_F_STD, bits);
+      if ((old ^ pend_mine) & 0xffffu) bits |= 1u << 24;
+      if ((old ^ pend_mine) & 0xff0000u) bits |= 1u << 25;
+      if (bits & ~old) atomicOr(pend_row, bits);
     }
   }
   __device__ __forceinline__ void adj(int pos, int allele, int sign, bool dir, int tp, int q, int mapq, int nm) {
@@ -199,6 +212,7 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
   s.a = &a;
   s.kept_bases = s.n_kept = s.n_unsup = s.n_over = s.n_ev = 0;
   s.mute = false;
+  s.pend = false;
   s.goodq = a.P.goodq;
   const DevRegion* dr = a.regions;
   rv_read rd;
@@ -385,6 +399,7 @@ __global__ void __launch_bounds__(128) rv_walk_kernel(PileupArgs a) {
     s.covtab = a.cov + dr->tab_off;
     s.kept_bases = s.n_kept = s.n_unsup = s.n_over = s.n_ev = 0;
     s.goodq = a.P.goodq;
+    s.pend = false;
     s.mute = true;
     Prep pr;
     prepare_read(a.P, dr->r, rd, a.pool, ref, s, true, pr);
@@ -393,6 +408,7 @@ __global__ void __launch_bounds__(128) rv_walk_kernel(PileupArgs a) {
     FastDesc scratch;
     walk_read(a.P, dr->r, ri, rd, a.pool, ref, (uint32_t)read_idx, s, pr, plain_done ? &scratch : (FastDesc*)0,
               plain_done ? 1 : 0);
+    s.resolve();
     over += s.n_over;
     unsup += s.n_unsup;
   }
@@ -428,7 +444,7 @@ struct GatherArgs {
   uint32_t* counts;
   uint32_t* cov;
   const int32_t* reach;
-  int64_t* tile_range;  // [2 * tile]: candidate read range of every tile
+  int64_t* tile_range;  // [2 * tile]: first candidate read of the tile; number of candidates | region << 32
   int64_t n_tiles;
 };
 
@@ -446,7 +462,8 @@ __device__ __forceinline__ int find_region_by_tile(const DevRegion* regs, int n,
 __global__ void rv_tile_index_kernel(GatherArgs a) {
   const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tile >= a.n_tiles) return;
-  const DevRegion* dr = a.regions + find_region_by_tile(a.regions, a.n_regions, tile);
+  const int ri = find_region_by_tile(a.regions, a.n_regions, tile);
+  const DevRegion* dr = a.regions + ri;
   const int p_lo = dr->first_pos + (int)(tile - dr->tile_base) * GATHER_TILE;
   const int c_lo = p_lo > dr->r.start ? p_lo : dr->r.start;
   const int c_hi = p_lo + GATHER_TILE - 1 < dr->r.end ? p_lo + GATHER_TILE - 1 : dr->r.end;
@@ -462,22 +479,28 @@ __global__ void rv_tile_index_kernel(GatherArgs a) {
     hi = x;
   }
   a.tile_range[2 * tile] = lo;
-  a.tile_range[2 * tile + 1] = hi;
+  a.tile_range[2 * tile + 1] = (int64_t)(((unsigned long long)(unsigned)ri << 32) | (unsigned)(hi - lo));
 }
 
 __device__ __forceinline__ int nib_allele(int nib) { return (nib >> 1) - (nib >> 3); }  // 1,2,4,8 -> 0,1,2,3
 
+static const int REC_BIAS = 256;  // keeps the arena byte offsets of a staged read non-negative 16-bit numbers
+
 __global__ void __launch_bounds__(GATHER_TILE) rv_gather_kernel(GatherArgs a) {
-  __shared__ uint4 s_arena[ARENA_CHUNKS];
-  __shared__ int4 s_rec[GATHER_TILE];        // {rel_start, seq byte offset, qual byte offset, m_len | par<<16 | dir<<17}
-  __shared__ uint32_t s_add[GATHER_TILE];    // mapq | nm << 16
-  __shared__ uint4 s_copy[GATHER_TILE];      // {first seq chunk, first qual chunk, n seq chunks | n qual chunks << 8, arena chunk}
-  __shared__ uint8_t s_wlist[GATHER_TILE / 32][GATHER_TILE];
-  __shared__ int s_wcnt[GATHER_TILE / 32];
+  __shared__ __align__(16) uint8_t s_arena[ARENA_CHUNKS * 16];
+  // staged read: {rel_start, seq byte offset | qual byte offset << 16 (both + REC_BIAS), m_len | par << 16 | dir << 17,
+  //               mapq | nm << 16}
+  __shared__ uint4 s_rec[GATHER_TILE];
+  __shared__ uint4 s_copy[GATHER_TILE];  // {first seq chunk, first qual chunk, n seq chunks | n qual chunks << 8, arena chunk}
+  __shared__ int s_wlo[GATHER_TILE / 32], s_whi[GATHER_TILE / 32];  // staged reads [lo, hi) that may overlap the warp
   __shared__ int s_wsum[GATHER_TILE / 32];
+  __shared__ int s_ntake, s_nslots;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t tile = blockIdx.x;
-  const DevRegion* dr = a.regions + find_region_by_tile(a.regions, a.n_regions, tile);
+  const int4 tinfo = ((const int4*)a.tile_range)[tile];  // {read lo (64 bit), n reads, region}
+  const DevRegion* dr = a.regions + tinfo.w;
+  const int64_t lo = (int64_t)(((unsigned long long)(unsigned)tinfo.y << 32) | (unsigned)tinfo.x);
+  const int64_t hi = lo + tinfo.z;
   const int p_lo = dr->first_pos + (int)(tile - dr->tile_base) * GATHER_TILE;
   const int c_lo = p_lo > dr->r.start ? p_lo : dr->r.start;  // positions that can receive observations
   const int c_hi = p_lo + GATHER_TILE - 1 < dr->r.end ? p_lo + GATHER_TILE - 1 : dr->r.end;
@@ -496,14 +519,15 @@ __global__ void __launch_bounds__(GATHER_TILE) rv_gather_kernel(GatherArgs a) {
   uint32_t* const row0 = a.counts + (size_t)t_row * RV_POS_U32;
   uint32_t n_ref = 0, n_rev = 0, sum_tp = 0, sum_q = 0, sum_mapq = 0, sum_nm = 0, n_hi = 0;
   uint32_t v_and = 0xffffffffu, v_or = 0, v_last = 0, n_other = 0, other_mask = 0;
-  const int64_t lo = a.tile_range[2 * tile], hi = a.tile_range[2 * tile + 1];
   const GDesc* item_desc = a.descs + (dr->item_base - dr->r.read_lo);  // descriptor of read index i
   const uint4* pool16 = (const uint4*)a.pool;
-  const uint8_t* arena = (const uint8_t*)s_arena;
+  // lane constants of the byte lookups: seq byte = offset + ((x + par) >> 1), qual byte = offset + x
+  const int xs0 = (x >> 1) - REC_BIAS, xs1 = ((x + 1) >> 1) - REC_BIAS, xq = x - REC_BIAS;
 
   for (int64_t base = lo; base < hi;) {
     // ---- 1. descriptors of this round, clipped to the tile ------------------------------------------
-    if (tid < GATHER_TILE / 32) s_wcnt[tid] = 0;
+    if (tid < GATHER_TILE / 32) { s_wlo[tid] = GATHER_TILE; s_whi[tid] = 0; }
+    if (tid == 0) { s_ntake = 0; s_nslots = 0; }
     const int64_t i = base + tid;
     GDesc d;
     d.m_len = 0;
@@ -540,61 +564,71 @@ __global__ void __launch_bounds__(GATHER_TILE) rv_gather_kernel(GatherArgs a) {
     const int chunks_incl = incl & 0xffff;
     const bool fits = chunks_incl <= ARENA_CHUNKS;  // a prefix of the round (the scan is monotone)
     const bool staged = take && fits;
-    const int n_take = __syncthreads_count(fits);
-    const int n_slots = __syncthreads_count(staged);
+    {
+      const unsigned bf = __ballot_sync(0xffffffffu, fits), bs = __ballot_sync(0xffffffffu, staged);
+      if (lane == 0) {
+        if (bf) atomicAdd(&s_ntake, __popc(bf));
+        if (bs) atomicAdd(&s_nslots, __popc(bs));
+      }
+    }
     if (staged) {
       const int slot = (incl >> 16) - 1;
       const int chunk0 = chunks_incl - (ns + nq);
       const int rel_start = d.m_start - p_lo;
       const int n0 = (int)d.rp0 - rel_start;  // read offset of the base under tile coordinate 0
       const int par = n0 & 1;
-      int4 r;
-      r.x = rel_start;
-      r.y = chunk0 * 16 + (int)(s_first & 15) - (n_lo >> 1) + ((n0 - par) >> 1);  // + ((x + par) >> 1)
-      r.z = (chunk0 + ns) * 16 + (int)(q_first & 15) - n_lo + n0;                  // + x
-      r.w = (int)d.m_len | (par << 16) | ((d.dir_nm >> 7) << 17);
-      s_rec[slot] = r;
-      s_add[slot] = (uint32_t)d.mapq | ((uint32_t)(d.dir_nm & 0x7f) << 16);
+      const int so = chunk0 * 16 + (int)(s_first & 15) - (n_lo >> 1) + ((n0 - par) >> 1) + REC_BIAS;
+      const int qo = (chunk0 + ns) * 16 + (int)(q_first & 15) - n_lo + n0 + REC_BIAS;
+      s_rec[slot] = make_uint4((uint32_t)rel_start, (uint32_t)so | ((uint32_t)qo << 16),
+                               (uint32_t)d.m_len | ((uint32_t)par << 16) | ((uint32_t)(d.dir_nm >> 7) << 17),
+                               (uint32_t)d.mapq | ((uint32_t)(d.dir_nm & 0x7f) << 16));
       s_copy[slot] = make_uint4((uint32_t)(s_first >> 4), (uint32_t)(q_first >> 4), (uint32_t)(ns | (nq << 8)), (uint32_t)chunk0);
       const int x_lo = rel_start > c_lo - p_lo ? rel_start : c_lo - p_lo;
       const int x_hi = rel_start + (int)d.m_len - 1 < c_hi - p_lo ? rel_start + (int)d.m_len - 1 : c_hi - p_lo;
-      for (int w = x_lo >> 5; w <= (x_hi >> 5); ++w) s_wlist[w][atomicAdd(&s_wcnt[w], 1)] = (uint8_t)slot;
+      for (int w = x_lo >> 5; w <= (x_hi >> 5); ++w) {
+        if (slot < s_wlo[w]) atomicMin(&s_wlo[w], slot);
+        if (slot + 1 > s_whi[w]) atomicMax(&s_whi[w], slot + 1);
+      }
     }
     __syncthreads();
-    // ---- 2. stage the bytes: one warp per read, one 16-byte chunk per lane ---------------------------
+    // ---- 2. stage the bytes: one warp per read, one 16-byte chunk per lane, asynchronous copies ---------
+    const int n_slots = s_nslots, n_take = s_ntake;
     for (int sidx = warp; sidx < n_slots; sidx += GATHER_TILE / 32) {
       const uint4 c = s_copy[sidx];
       const int cns = (int)(c.z & 0xff), cnq = (int)(c.z >> 8);
       if (lane < cns + cnq) {
         const size_t src = lane < cns ? (size_t)c.x + lane : (size_t)c.y + (lane - cns);
-        s_arena[c.w + lane] = pool16[src];
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(s_arena + (size_t)(c.w + lane) * 16);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(pool16 + src) : "memory");
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    // ---- 3. every lane walks its warp's list ----------------------------------------------------------
+    // ---- 3. every lane walks the staged reads that may overlap its warp ---------------------------------
     if (live) {
-      const int cnt = s_wcnt[warp];
+      const int w_lo = s_wlo[warp], w_hi = s_whi[warp];
       uint32_t add_acc = 0;
-      for (int j = 0; j < cnt; ++j) {
-        const int slot = s_wlist[warp][j];
-        const int4 r = s_rec[slot];
-        const int m_len = r.w & 0xffff;
-        const int k = x - r.x;
+#pragma unroll 4
+      for (int slot = w_lo; slot < w_hi; ++slot) {
+        const uint4 r = s_rec[slot];
+        const int m_len = (int)(r.z & 0xffffu);
+        const int k = x - (int)r.x;
         if ((unsigned)k >= (unsigned)m_len) continue;
-        const uint32_t q = arena[r.z + x];
-        const int t = x + ((r.w >> 16) & 1);
-        const int sbyte = arena[r.y + (t >> 1)];
-        const int nib = (t & 1) ? (sbyte & 15) : (sbyte >> 4);
-        const uint32_t tp = (uint32_t)(k + 1 < m_len - k ? k + 1 : m_len - k);
+        const uint32_t q = s_arena[(int)(r.y >> 16) + xq];
+        const bool odd = (r.z >> 16) & 1;  // parity of the read offset under tile coordinate 0
+        const int sbyte = s_arena[(int)(r.y & 0xffffu) + (odd ? xs1 : xs0)];
+        const int nib = ((x ^ (int)odd) & 1) ? (sbyte & 15) : (sbyte >> 4);
+        const uint32_t tp = (uint32_t)min(k + 1, m_len - k);
         const uint32_t v = tp | (q << 16);
         const uint32_t hiq = (int)q >= thr ? 1u : 0u;
-        const uint32_t dir = (uint32_t)(r.w >> 17) & 1u;
+        const uint32_t dir = (r.z >> 17) & 1u;
         if (nib == refnib) {
           n_ref++;
           n_rev += dir;
           sum_tp += tp;
           sum_q += q;
-          add_acc += s_add[slot];
+          add_acc += r.w;
           n_hi += hiq;
           v_and &= v;
           v_or |= v;
@@ -602,12 +636,11 @@ __global__ void __launch_bounds__(GATHER_TILE) rv_gather_kernel(GatherArgs a) {
         } else {
           // a base that differs from the reference: the lane's own row of that allele, read-modify-write
           const int al = nib_allele(nib);
-          const uint32_t ad = s_add[slot];
           uint4* row4 = (uint4*)(row0 + al * RV_ROW_U32);
           uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
           if (other_mask & (1u << al)) { ra = row4[0]; rb = row4[1]; }
           ra.x += 1u - dir; ra.y += dir; ra.z += tp; ra.w += q;
-          rb.x += ad & 0xffffu; rb.y += ad >> 16; rb.z += hiq;
+          rb.x += r.w & 0xffffu; rb.y += r.w >> 16; rb.z += hiq;
           uint32_t w = rb.w;
           if ((w >> 31) == 0) w = v | (1u << 31);
           else {
