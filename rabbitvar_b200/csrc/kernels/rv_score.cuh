@@ -24,7 +24,8 @@ struct Span {
   bool lit_first;
   RV_HD int len() const { return lit_n + ref_n; }
 };
-RV_HD char span_at(const Span& s, const RefView& ref, int i) {
+template <class RefT>
+RV_HD char span_at(const Span& s, const RefT& ref, int i) {
   if (s.lit_first) {
     if (i < s.lit_n) return s.lit[i];
     return ref.at(s.ref_a + (i - s.lit_n));
@@ -51,6 +52,12 @@ RV_HD Span lit_span(const char* p, int n) {
   return s;
 }
 
+// Reference view without bounds tests, for callers that proved the whole span lies inside the loaded window.
+struct RefRaw {
+  const char* b;  // b[p] = base at reference position p
+  RV_HD char at(int p) const { return b[p]; }
+};
+
 struct Msi {
   double msi;
   int shift3;
@@ -58,7 +65,8 @@ struct Msi {
 };
 
 // findMSI(tseq1, tseq2, left), ToVarsBuilder.cpp:656-722 — the off-by-one guards are reproduced as written.
-RV_HDN Msi find_msi(const Span& tseq1, const Span& tseq2, const Span& left, const RefView& ref) {
+template <class RefT>
+RV_HDN Msi find_msi(const Span& tseq1, const Span& tseq2, const Span& left, const RefT& ref) {
   int nmsi = 1, shift3 = 0, best_len = 0;
   double msicnt = 0;
   const int l1 = tseq1.len(), l2 = tseq2.len(), ll = left.len();
@@ -475,6 +483,160 @@ RV_HDN void score_position(const rv_params& P, const rv_region& R, int region_id
     if (o.fwd < 0) o.fwd = 0;
     if (o.rev < 0) o.rev = 0;
     out.emit(o);
+  }
+}
+
+// ---- dense positions ---------------------------------------------------------------------------------
+// score_position restricted to positions whose only keys are the four single-base alleles of the dense table
+// (no patch entry, no insertion key): same arithmetic, fixed-size state.  The MSI context and the Fisher test
+// of the non-reference alleles are left to the caller (emit_variant), which runs them densely packed.
+// Emit concept:  void emit(const rv_variant&)                                   complete record
+//                void emit_variant(const rv_variant&, int a11, int a12, int a21, int a22)  msi/pvalue still to fill
+template <class Emit>
+RV_HDN void score_dense_position(const rv_params& P, int region_idx, int pos, char refb, const uint32_t* rows,
+                                 uint32_t cov_p, Emit& out) {
+  static const char BASES[5] = "ACGT";
+  int n_exist = 0, only_al = -1, hicov = 0;
+  for (int a = 0; a < 4; ++a)
+    if (dense_exists(rows + a * RV_ROW_U32)) {
+      n_exist++;
+      only_al = a;
+      hicov += (int)rows[a * RV_ROW_U32 + RV_F_HI];  // calcHicov :570-587 (zero-count keys included)
+    }
+  if (n_exist == 0 || cov_p == 0) return;  // ToVarsBuilder.cpp:103-128
+  if (n_exist == 1 && refb && BASES[only_al] == refb && !P.pileup && !P.has_bam2) return;  // :133, :213-233
+  const int tcov = (int)cov_p;
+  int al[4], cnt[4], bias[4];
+  double qual[4], freq[4], pmean[4];
+  int nv = 0;
+  for (int a = 0; a < 4; ++a) {  // keys in ascending order (:159-166); createVariant :466-536
+    const uint32_t* row = rows + a * RV_ROW_U32;
+    if (!dense_exists(row)) continue;
+    const int c = (int)(row[RV_F_FWD] + row[RV_F_REV]);
+    if (c == 0) continue;
+    al[nv] = a;
+    cnt[nv] = c;
+    bias[nv] = strand_bias((int)row[RV_F_FWD], (int)row[RV_F_REV], P);
+    qual[nv] = (double)(int)row[RV_F_SUM_Q] / c;
+    freq[nv] = c / (double)tcov;
+    pmean[nv] = (double)(int)row[RV_F_SUM_TP] / (double)c;
+    nv++;
+  }
+  if (nv == 0) return;
+  // sort(var, CMP_VARI) :167 — qual*cnt descending, ties (|d| < 1e-5) by key ascending
+  int vord[4];
+  for (int i = 0; i < nv; ++i) {
+    int j = i;
+    vord[j] = i;
+    while (j > 0) {
+      const int x = vord[j], y = vord[j - 1];
+      const double res = qual[x] * cnt[x] - qual[y] * cnt[y];
+      bool before;
+      if (res < 0.00001 && res > -0.00001) before = al[x] < al[y];
+      else before = res > 0;
+      if (!before) break;
+      vord[j] = y;
+      vord[j - 1] = x;
+      --j;
+    }
+  }
+  int ref_i = -1, n_variants = 0;
+  double maxfreq = 0;
+  for (int oi = 0; oi < nv; ++oi) {  // collectVarsAtPosition :327-346
+    const int v = vord[oi];
+    if (refb && BASES[al[v]] == refb) ref_i = v;
+    else {
+      n_variants++;
+      if (freq[v] > maxfreq) maxfreq = freq[v];
+    }
+  }
+  if (!P.pileup && maxfreq <= P.freq && !P.has_bam2) return;  // :170-175
+  if (P.candidates_only && !P.pileup) {
+    bool any = false;
+    for (int v = 0; v < nv; ++v) {
+      if (v == ref_i) continue;
+      const uint32_t* row = rows + al[v] * RV_ROW_U32;
+      const int hi = (int)row[RV_F_HI], lo = cnt[v] - hi;
+      const double qratio = hi / (lo != 0 ? (double)lo : 0.5);
+      if (freq[v] >= P.freq && hi >= P.minr && pmean[v] >= P.read_pos_filter && qual[v] >= P.goodq && qratio >= P.qratio)
+        any = true;
+    }
+    if (!any) return;
+  }
+  int rfc = 0, rrc = 0;
+  if (ref_i >= 0) {
+    rfc = (int)rows[al[ref_i] * RV_ROW_U32 + RV_F_FWD];
+    rrc = (int)rows[al[ref_i] * RV_ROW_U32 + RV_F_REV];
+  }
+  int rank = 0;
+  for (int oi = 0; oi < nv; ++oi) {
+    const int v = vord[oi];
+    const uint32_t* row = rows + al[v] * RV_ROW_U32;
+    const bool is_ref = v == ref_i;
+    const int c = cnt[v], hi = (int)row[RV_F_HI], lo = c - hi;
+    rv_variant o;
+    o.region = region_idx;
+    o.pos = pos;
+    o.cnt = c; o.fwd = (int)row[RV_F_FWD]; o.rev = (int)row[RV_F_REV];
+    o.tcov = tcov;
+    o.hicnt = hi; o.hicov = hicov;
+    o.ref_fwd = rfc; o.ref_rev = rrc;
+    o.shift3 = 0; o.msint = 0; o.msi = 0;
+    o.freq = freq[v]; o.pmean = pmean[v]; o.qual = qual[v];
+    o.mapq = (double)(int)row[RV_F_SUM_MAPQ] / (double)c;
+    o.qratio = hi / (lo != 0 ? (double)lo : 0.5);
+    o.hifreq = hicov > 0 ? hi / (double)hicov : 0;
+    o.extrafreq = 0;
+    o.nm = (double)(int)row[RV_F_SUM_NM] / (double)c;
+    o.bias_ref = (uint8_t)(ref_i >= 0 ? bias[ref_i] : 0);
+    o.bias_var = (uint8_t)bias[v];
+    o.pstd = (row[RV_F_STD] >> 24) & 1; o.qstd = (row[RV_F_STD] >> 25) & 1;
+    o.is_ref = is_ref ? 1 : 0;
+    o.key_kind = 0;
+    o.key_id = al[v];
+    o.pad = 0;
+    o.pvalue = 1.0; o.oddratio = 0.0;
+    if (o.ref_fwd < 0) o.ref_fwd = 0;
+    if (o.ref_rev < 0) o.ref_rev = 0;
+    if (is_ref) {
+      o.rank = 255;
+      if (n_variants == 0) {  // :1066-1090 — no variant reads detected
+        o.cnt = 0; o.freq = 0; o.fwd = 0; o.rev = 0; o.bias_var = 0;
+      }
+      if (o.fwd < 0) o.fwd = 0;
+      if (o.rev < 0) o.rev = 0;
+      out.emit(o);
+    } else {
+      o.rank = (uint8_t)rank++;
+      const int a11 = rfc < 0 ? 0 : rfc, a12 = rrc < 0 ? 0 : rrc, a21 = o.fwd < 0 ? 0 : o.fwd, a22 = o.rev < 0 ? 0 : o.rev;
+      if (o.fwd < 0) o.fwd = 0;
+      if (o.rev < 0) o.rev = 0;
+      out.emit_variant(o, a11, a12, a21, a22);
+    }
+  }
+}
+
+// MSI context of an SNV/MNV key (ToVarsBuilder.cpp:864-878) and the Fisher test of print_output_variant_simple
+// (simpleMode.cpp:96-108): the part of a dense record that emit_variant left open.
+template <class RefT>
+RV_HDN void finish_dense_variant(const rv_params& P, int pos, int chr_len, const RefT& ref, const LgTable& lgt, int a11,
+                                 int a12, int a21, int a22, double* msi, int* shift3, int* msint, double* pvalue,
+                                 double* oddratio) {
+  Span t1 = ref_span(pos - 30 > 1 ? pos - 30 : 1, pos + 1);
+  Span t2 = ref_span(pos + 2, pos + 70 > chr_len ? chr_len : pos + 70);
+  Span none = ref_span(1, 0);
+  Msi m = find_msi(t1, t2, none, ref);
+  *msi = m.msi;
+  *shift3 = m.shift3;
+  *msint = m.msint_len;
+  *pvalue = 1.0;
+  *oddratio = 0.0;
+  if (P.fisher) {
+    double l, r, two;
+    fisher_exact(lgt, a11, a12, a21, a22, &l, &r, &two);
+    *pvalue = two;
+    const double ad = (double)a11 * a22, bc = (double)a12 * a21;
+    *oddratio = (bc != 0 && ad != 0) ? (ad > bc ? ad / bc : bc / ad) : 0.0;
   }
 }
 

@@ -699,15 +699,20 @@ struct ScoreArgs {
   const double* lgt;
   int lgt_n;
   DevStats* stats;
+  int64_t* patched_queue;             // table positions that carry patch entries
+  unsigned long long* patched_count;
 };
 
 struct DeviceEmit {
   const ScoreArgs* a;
-  __device__ __forceinline__ void emit(const rv_variant& v) {
+  __device__ __forceinline__ unsigned long long reserve() {  // one atomic per group of converged lanes
     cg::coalesced_group g = cg::coalesced_threads();
     unsigned long long slot = 0;
     if (g.thread_rank() == 0) slot = atomicAdd(&a->stats->n_variants, (unsigned long long)g.size());
-    slot = g.shfl(slot, 0) + g.thread_rank();
+    return g.shfl(slot, 0) + g.thread_rank();
+  }
+  __device__ __forceinline__ void emit(const rv_variant& v) {
+    const unsigned long long slot = reserve();
     if (slot < a->max_variants) a->variants[slot] = v;
   }
 };
@@ -722,47 +727,144 @@ __device__ __forceinline__ int find_region_by_tab(const DevRegion* regs, int n, 
   return lo;
 }
 
-// One table position per thread (ToVarsBuilder::process): gathers the position's keys, scores them,
-// applies the frequency cut and appends the survivors.  Only positions inside the region are scored
-// (simpleMode.cpp:155-159 drops the rest at output time).
-__global__ void __launch_bounds__(128) rv_score_kernel(ScoreArgs a) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= a.n_positions) return;
-  int ri = find_region_by_tab(a.regions, a.n_regions, t);
-  const DevRegion* dr = a.regions + ri;
-  int i = (int)(t - dr->tab_off);
-  int pos = dr->first_pos + i;
-  if (pos < dr->r.start || pos > dr->r.end) return;
-  const uint32_t* rows = a.counts + (size_t)t * RV_POS_U32;
-  uint32_t pf = a.patch_first ? a.patch_first[t] : 0u;
-  int pn = pf ? (int)a.patch_count[t] : 0;
-  // cheap early-out: nothing recorded here at all
-  bool any = pf != 0;
-  if (!any) {
-    const uint4* r4 = (const uint4*)rows;
+// Scoring, ToVarsBuilder::process, in two kernels:
+//   rv_score_kernel         one table position per thread; positions whose keys are all dense single-base
+//                           alleles are scored here (score_dense_position), the MSI context + Fisher test of
+//                           their non-reference alleles go through a per-block work list so that all lanes
+//                           run them together; positions with patch entries are queued
+//   rv_score_patched_kernel the general score_position for the queued positions
+// Only positions inside the region are scored (simpleMode.cpp:155-159 drops the rest at output time).
+static const int SCORE_BLOCK = 128;
+struct ScoreWork {  // 32 bytes
+  uint32_t slot;
+  int32_t pos, region, a11, a12, a21, a22, pad;
+};
+
+struct DenseEmit {
+  const ScoreArgs* a;
+  DeviceEmit base;
+  ScoreWork* work;
+  int* n_work;
+  int pos, region;
+  __device__ __forceinline__ void emit(const rv_variant& v) { base.emit(v); }
+  __device__ __forceinline__ void emit_variant(const rv_variant& v, int a11, int a12, int a21, int a22) {
+    const unsigned long long slot = base.reserve();
+    if (slot >= a->max_variants) return;
+    a->variants[slot] = v;
+    ScoreWork w;
+    w.slot = (uint32_t)slot; w.pos = pos; w.region = region; w.a11 = a11; w.a12 = a12; w.a21 = a21; w.a22 = a22; w.pad = 0;
+    work[atomicAdd(n_work, 1)] = w;
+  }
+};
+
+__global__ void __launch_bounds__(SCORE_BLOCK, 4) rv_score_kernel(ScoreArgs a) {
+  __shared__ ScoreWork s_work[SCORE_BLOCK * 3];  // at most three non-reference alleles per position
+  __shared__ int s_nwork;
+  if (threadIdx.x == 0) s_nwork = 0;
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < a.n_positions) {
+    const int ri = find_region_by_tab(a.regions, a.n_regions, t);
+    const DevRegion* dr = a.regions + ri;
+    const int pos = dr->first_pos + (int)(t - dr->tab_off);
+    if (pos >= dr->r.start && pos <= dr->r.end) {
+      const uint32_t pf = a.patch_first ? a.patch_first[t] : 0u;
+      if (pf != 0) {
+        cg::coalesced_group g = cg::coalesced_threads();
+        unsigned long long slot = 0;
+        if (g.thread_rank() == 0) slot = atomicAdd(a.patched_count, (unsigned long long)g.size());
+        a.patched_queue[g.shfl(slot, 0) + g.thread_rank()] = t;
+      } else {
+        uint32_t rows[RV_POS_U32];
+        const uint4* r4 = (const uint4*)(a.counts + (size_t)t * RV_POS_U32);
+        uint32_t any = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      uint4 v = r4[k];
-      any = any || (v.x | v.y | v.z | v.w);
+        for (int k = 0; k < 8; ++k) {
+          const uint4 v = r4[k];
+          rows[4 * k] = v.x; rows[4 * k + 1] = v.y; rows[4 * k + 2] = v.z; rows[4 * k + 3] = v.w;
+          any |= v.x | v.y | v.z | v.w;
+        }
+        if (any) {
+          char refb = 0;
+          if (pos >= dr->r.ref_lo && pos <= dr->r.ref_hi && pos >= a.ref_start && (int64_t)(pos - a.ref_start) < a.ref_n)
+            refb = a.ref[pos - a.ref_start];
+          DenseEmit em;
+          em.a = &a;
+          em.base.a = &a;
+          em.work = s_work;
+          em.n_work = &s_nwork;
+          em.pos = pos;
+          em.region = ri;
+          score_dense_position(a.P, ri, pos, refb, rows, a.cov[t], em);
+        }
+      }
     }
   }
-  if (!any) return;
-  RefView ref;
-  ref.bases = a.ref;
-  ref.base_pos = a.ref_start;
-  ref.n = a.ref_n;
-  ref.lo = dr->r.ref_lo;
-  ref.hi = dr->r.ref_hi;
-  bool has_next = i + 1 < dr->n_pos;
+  __syncthreads();
+  // ---- the open part of the non-reference records, one work item per lane ----------------------------
+  const int n_work = s_nwork;
   LgTable L;
   L.t = a.lgt;
   L.n = a.lgt_n;
-  DeviceEmit em;
-  em.a = &a;
-  int unsup = 0;
-  score_position(a.P, dr->r, ri, pos, ref, rows, a.cov[t], has_next, rows + RV_POS_U32, has_next ? a.cov[t + 1] : 0u,
-                 a.patch, pf ? (int)(pf - 1) : 0, pn, L, em, &unsup);
-  if (unsup) atomicAdd(&a.stats->n_score_unsupported, (unsigned long long)unsup);
+  for (int w = threadIdx.x; w < n_work; w += SCORE_BLOCK) {
+    const ScoreWork k = s_work[w];
+    const rv_region& R = a.regions[k.region].r;
+    double msi, pvalue, oddratio;
+    int shift3, msint;
+    // the spans [pos-30, pos+70] of findMSI: unchecked loads when they lie inside the loaded window
+    const int64_t w_lo = R.ref_lo > a.ref_start ? R.ref_lo : a.ref_start;
+    const int64_t w_hi = (int64_t)R.ref_hi < a.ref_start + a.ref_n - 1 ? (int64_t)R.ref_hi : a.ref_start + a.ref_n - 1;
+    if (k.pos - 30 >= w_lo && k.pos + 70 <= w_hi) {
+      RefRaw raw;
+      raw.b = a.ref - a.ref_start;
+      finish_dense_variant(a.P, k.pos, R.chr_len, raw, L, k.a11, k.a12, k.a21, k.a22, &msi, &shift3, &msint, &pvalue, &oddratio);
+    } else {
+      RefView ref;
+      ref.bases = a.ref;
+      ref.base_pos = a.ref_start;
+      ref.n = a.ref_n;
+      ref.lo = R.ref_lo;
+      ref.hi = R.ref_hi;
+      finish_dense_variant(a.P, k.pos, R.chr_len, ref, L, k.a11, k.a12, k.a21, k.a22, &msi, &shift3, &msint, &pvalue, &oddratio);
+    }
+    rv_variant* o = a.variants + k.slot;
+    o->msi = msi;
+    o->shift3 = shift3;
+    o->msint = msint;
+    o->pvalue = pvalue;
+    o->oddratio = oddratio;
+  }
+}
+
+__global__ void __launch_bounds__(128) rv_score_patched_kernel(ScoreArgs a) {
+  const unsigned long long n = *a.patched_count;
+  for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < n;
+       q += (unsigned long long)gridDim.x * blockDim.x) {
+    const int64_t t = a.patched_queue[q];
+    const int ri = find_region_by_tab(a.regions, a.n_regions, t);
+    const DevRegion* dr = a.regions + ri;
+    const int i = (int)(t - dr->tab_off);
+    const int pos = dr->first_pos + i;
+    const uint32_t* rows = a.counts + (size_t)t * RV_POS_U32;
+    const uint32_t pf = a.patch_first[t];
+    const int pn = (int)a.patch_count[t];
+    RefView ref;
+    ref.bases = a.ref;
+    ref.base_pos = a.ref_start;
+    ref.n = a.ref_n;
+    ref.lo = dr->r.ref_lo;
+    ref.hi = dr->r.ref_hi;
+    const bool has_next = i + 1 < dr->n_pos;
+    LgTable L;
+    L.t = a.lgt;
+    L.n = a.lgt_n;
+    DeviceEmit em;
+    em.a = &a;
+    int unsup = 0;
+    score_position(a.P, dr->r, ri, pos, ref, rows, a.cov[t], has_next, rows + RV_POS_U32, has_next ? a.cov[t + 1] : 0u,
+                   a.patch, (int)(pf - 1), pn, L, em, &unsup);
+    if (unsup) atomicAdd(&a.stats->n_score_unsupported, (unsigned long long)unsup);
+  }
 }
 
 __global__ void rv_lgamma_table_kernel(double* t, int n) {
@@ -842,6 +944,8 @@ struct rv_ctx {
   uint32_t* d_ref4;
   int64_t* d_tile_range;
   int64_t tile_cap;
+  int64_t* d_patched_queue;
+  unsigned long long* d_patched_count;
   unsigned long long* d_walk_queue;
   unsigned long long* d_walk_count;
   int64_t n_tiles;
@@ -952,7 +1056,7 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   ctx->launches = 0;
   ctx->d_reads = NULL; ctx->d_pool = NULL; ctx->d_ref = NULL; ctx->d_counts = NULL; ctx->d_cov = NULL;
   ctx->d_events = NULL; ctx->d_variants = NULL; ctx->d_patch = NULL; ctx->d_patch_first = NULL;
-  ctx->d_patch_count = NULL; ctx->d_regions = NULL; ctx->d_max_rl = NULL; ctx->d_stats = NULL; ctx->d_lgt = NULL; ctx->d_descs = NULL; ctx->d_reach = NULL; ctx->d_ref4 = NULL; ctx->d_tile_range = NULL; ctx->tile_cap = 0; ctx->d_walk_queue = NULL; ctx->d_walk_count = NULL; ctx->n_tiles = 0;
+  ctx->d_patch_count = NULL; ctx->d_regions = NULL; ctx->d_max_rl = NULL; ctx->d_stats = NULL; ctx->d_lgt = NULL; ctx->d_descs = NULL; ctx->d_reach = NULL; ctx->d_ref4 = NULL; ctx->d_tile_range = NULL; ctx->tile_cap = 0; ctx->d_patched_queue = NULL; ctx->d_patched_count = NULL; ctx->d_walk_queue = NULL; ctx->d_walk_count = NULL; ctx->n_tiles = 0;
   ctx->use_gather = getenv("RV_NO_GATHER") == NULL;
   ctx->h_counts = NULL; ctx->h_cov = NULL; ctx->h_tab_cap = 0; ctx->h_events = NULL; ctx->h_events_cap = 0;
   ctx->h_variants = NULL; ctx->h_variants_cap = 0; ctx->h_max_rl = NULL; ctx->h_rows = NULL; ctx->h_rows_cap = 0; ctx->d_scratch = NULL; ctx->scratch_cap = 0;
@@ -987,6 +1091,9 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   // gather tiles: every region rounds its table (length + 2*halo) up to whole tiles
   ctx->tile_cap = L.max_positions / GATHER_TILE + L.max_regions + 1;
   CK(cudaMalloc(&ctx->d_tile_range, 2 * sizeof(int64_t) * (size_t)ctx->tile_cap));
+  // a patch group is one position: at most max_patch positions carry patch entries
+  CK(cudaMalloc(&ctx->d_patched_queue, sizeof(int64_t) * (size_t)(L.max_patch + 1)));
+  CK(cudaMalloc(&ctx->d_patched_count, sizeof(unsigned long long)));
   CK(cudaMalloc(&ctx->d_walk_queue, sizeof(unsigned long long) * (size_t)(2 * L.max_reads + 1024)));
   CK(cudaMalloc(&ctx->d_walk_count, sizeof(unsigned long long)));
   CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->stream));
@@ -1012,6 +1119,8 @@ void rv_destroy(rv_ctx* ctx) {
   cudaFree(ctx->d_reach);
   cudaFree(ctx->d_ref4);
   cudaFree(ctx->d_tile_range);
+  cudaFree(ctx->d_patched_queue);
+  cudaFree(ctx->d_patched_count);
   cudaFree(ctx->d_walk_queue);
   cudaFree(ctx->d_walk_count);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
@@ -1395,11 +1504,19 @@ int rv_score(rv_ctx* ctx) {
   a.lgt = ctx->d_lgt;
   a.lgt_n = ctx->lgt_n;
   a.stats = ctx->d_stats;
+  a.patched_queue = ctx->d_patched_queue;
+  a.patched_count = ctx->d_patched_count;
   if (ctx->n_positions > 0) {
-    unsigned grid = (unsigned)((ctx->n_positions + 127) / 128);
-    rv_score_kernel<<<grid, 128, 0, ctx->stream>>>(a);
+    CK(cudaMemsetAsync(ctx->d_patched_count, 0, sizeof(unsigned long long), ctx->stream));
+    unsigned grid = (unsigned)((ctx->n_positions + SCORE_BLOCK - 1) / SCORE_BLOCK);
+    rv_score_kernel<<<grid, SCORE_BLOCK, 0, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
+    if (ctx->have_patch) {
+      rv_score_patched_kernel<<<148 * 4, 128, 0, ctx->stream>>>(a);
+      ctx->launches++;
+      CK(cudaGetLastError());
+    }
   }
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   CK(cudaMemcpyAsync(&ctx->h_stats.n_variants, &ctx->d_stats->n_variants, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
