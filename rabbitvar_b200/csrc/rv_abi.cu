@@ -194,10 +194,10 @@ __global__ void rv_pack_ref_kernel(const char* ref, int64_t n, uint32_t* out, in
 
 // One (region, read) pair per thread, three stages:
 //   1. per thread : read filters, CIGAR rewrite rules, clean-up (prepare_read)
-//   2. per warp   : the matched run of every fast-shaped read of the warp is compared with the reference by all
-//                   32 lanes, 8 bases per lane and step: the BAM 4-bit bases XOR the 4-bit reference give one
-//                   mismatch flag per nibble; shifted copies of the flag word prove that no two mismatches lie
-//                   within vext+1 bases, i.e. that no base of the run can start a multi-nucleotide key
+//   2. per thread : the matched run of a fast-shaped read is compared with the reference 8 bases per step: the
+//                   BAM 4-bit bases XOR the 4-bit reference give one mismatch flag per nibble; shifted copies
+//                   of the flag word (carried across words) prove that no two mismatches lie within vext+1
+//                   bases, i.e. that no base of the run can start a multi-nucleotide key
 //                   (parseCigar.cpp:711-768).  Such a "plain" run only leaves a GDesc for the gather kernel.
 //   3. per thread : everything that needs the exact CIGAR walk (soft clips, indels, non-plain runs, reads with N
 //                   or IUPAC bases) is appended to the walk queue
@@ -250,49 +250,44 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
            pr.nm <= 127 && pr.mapq <= 255;
   }
   bool plain = cand;
-  {
-    unsigned cand_mask = __ballot_sync(0xffffffffu, cand);
+  if (cand) {
     const int D = a.P.vext + 1;
-    const uint32_t* pool32 = (const uint32_t*)a.pool;
-    while (cand_mask) {
-      const int j = __ffs(cand_mask) - 1;
-      cand_mask &= cand_mask - 1;
-      const int rp0 = __shfl_sync(0xffffffffu, pr.rp0, j);
-      const int ml = __shfl_sync(0xffffffffu, pr.m_len, j);
-      const int e0 = __shfl_sync(0xffffffffu, E0, j);
-      const size_t sw = __shfl_sync(0xffffffffu, (unsigned long long)seq_word, j);
-      const int w_last = (rp0 + ml - 1) >> 3;
-      bool bad = false;
-      uint32_t carry = 0;
-      for (int w0 = rp0 >> 3; w0 <= w_last && !bad; w0 += 32) {
-        const int wi = w0 + lane;
-        uint32_t nz = 0, special = 0;
-        if (wi <= w_last) {
-          const uint32_t sq = __byte_perm(pool32[sw + wi], 0, 0x0123);  // base 8*wi in the top nibble
-          const int e = e0 + 8 * wi;
-          const uint32_t rf = __funnelshift_l(a.ref4[(e >> 3) + 1], a.ref4[e >> 3], (e & 7) * 4);
-          const int lo = rp0 - 8 * wi > 0 ? rp0 - 8 * wi : 0;
-          const int hi = rp0 + ml - 8 * wi < 8 ? rp0 + ml - 8 * wi : 8;
-          uint32_t vm = 0xffffffffu >> (4 * lo);
-          if (hi < 8) vm &= ~(0xffffffffu >> (4 * hi));
-          nz = nib_any(sq ^ rf) & vm;
-          // read bases other than A, C, G, T (N included): zero nibble, or more than one bit in the nibble
-          special = (~nib_any(sq) | nib_any(sq & (sq - 0x11111111u))) & 0x11111111u & vm;
-        }
-        uint32_t prev = __shfl_up_sync(0xffffffffu, nz, 1);
-        if (lane == 0) prev = carry;
-        uint32_t near = 0;
-        if (D <= 7) {
-          for (int d = 1; d <= D; ++d) near |= nz & __funnelshift_r(nz, prev, 4 * d);
-        } else {
-          near = (nz & (nz - 1)) | (nz && prev ? 1u : 0u);  // conservative: any two mismatches in 16 bases
-          if (__popc(__ballot_sync(0xffffffffu, nz != 0)) > 1) near = 1;
-        }
-        bad = __any_sync(0xffffffffu, (near | special) != 0);
-        carry = __shfl_sync(0xffffffffu, nz, 31);
+    const uint32_t* sq = (const uint32_t*)a.pool + seq_word;
+    const int rp0 = pr.rp0, ml = pr.m_len;
+    const int w_first = rp0 >> 3, w_last = (rp0 + ml - 1) >> 3;
+    const int e = E0 + 8 * w_first;
+    const int sh = (e & 7) * 4;
+    const uint32_t* rw = a.ref4 + (e >> 3);
+    uint32_t r_lo = rw[0];
+    uint32_t prev = 0, bad = 0, seen = 0;
+    for (int wi = w_first; wi <= w_last; ++wi) {
+      const uint32_t r_hi = *++rw;
+      const uint32_t rf = __funnelshift_l(r_hi, r_lo, sh);
+      r_lo = r_hi;
+      const uint32_t b8 = __byte_perm(sq[wi], 0, 0x0123);  // base 8*wi in the top nibble
+      uint32_t vm = 0xffffffffu;
+      if (wi == w_first) vm >>= 4 * (rp0 & 7);
+      if (wi == w_last) {
+        const int hi = ((rp0 + ml - 1) & 7) + 1;
+        if (hi < 8) vm &= ~(0xffffffffu >> (4 * hi));
       }
-      if (lane == j) plain = !bad;
+      const uint32_t nz = nib_any(b8 ^ rf) & vm;
+      // read bases other than A, C, G, T (N included): zero nibble, or more than one bit in the nibble
+      const uint32_t special = (~nib_any(b8) | nib_any(b8 & (b8 - 0x11111111u))) & 0x11111111u & vm;
+      uint32_t near;
+      if (D == 3) {
+        near = nz & (__funnelshift_r(nz, prev, 4) | __funnelshift_r(nz, prev, 8) | __funnelshift_r(nz, prev, 12));
+      } else if (D <= 7) {
+        near = 0;
+        for (int d = 1; d <= D; ++d) near |= nz & __funnelshift_r(nz, prev, 4 * d);
+      } else {
+        near = (nz & (nz - 1)) | ((nz && seen) ? 1u : 0u);  // conservative: any two mismatches in the run
+        seen |= nz;
+      }
+      bad |= near | special;
+      prev = nz;
     }
+    plain = bad == 0;
   }
   // ---- stage 3: descriptor for plain matched runs; everything else is queued for rv_walk_kernel -----
   int back = 0, reach = 0;
