@@ -214,7 +214,11 @@ int rv_set_params(rv_ctx* ctx, const rv_params* params);
 int rv_set_reference(rv_ctx* ctx, int32_t ref_start, int64_t n, const char* bases);
 /* Stage a read batch (host pointers; copied H2D asynchronously on the context stream). */
 int rv_push_reads(rv_ctx* ctx, const rv_read_batch* batch);
-/* Same, from buffers already resident on the device (all pointers are device pointers). */
+/* Stage only reads [read_lo, read_hi) of the batch (and their slice of the pool).  Regions set afterwards keep
+ * batch-global read indices and must lie inside the staged range; events report batch-global read indices.
+ * Lets several contexts work through one large host batch chunk by chunk. */
+int rv_push_reads_range(rv_ctx* ctx, const rv_read_batch* batch, int64_t read_lo, int64_t read_hi);
+/* Same, from buffers already resident on the device (all pointers are device pointers; 16-byte aligned pool). */
 int rv_push_reads_device(rv_ctx* ctx, const rv_read_batch* batch);
 /* Regions of this batch. */
 int rv_set_regions(rv_ctx* ctx, const rv_region* regions, int32_t n_regions);

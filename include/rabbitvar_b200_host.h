@@ -51,6 +51,21 @@ int rvh_call_regions(rv_ctx* ctx, const rv_params* params, const rvh_batch* batc
  * events/tables D2H, BAM-order reduce, host realigner, patch write-back (rv_apply_patch). */
 int rvh_install_patch(rv_ctx* ctx, const rv_params* params, const rvh_batch* batch, const rv_region* regions,
                       int32_t n_regions, const char* ref_bases, int32_t ref_lo, int64_t ref_n);
+
+/* Pipelined form of rvh_call_regions for large batches: the region list is cut into chunks of chunk_regions
+ * regions; n_workers host threads, each with its own context (stream + device buffers sized for one chunk) on
+ * `device`, pull chunks from a queue, so the H2D copy of one chunk overlaps the kernels of another and the host
+ * stages (event reduce, realign hand-off, TSV assembly) of a third.  This is the region loop of the reference
+ * (simpleMode.cpp:320-347: one region per OpenMP thread) with chunks in place of regions.  Output = the
+ * concatenation of the chunks' TSV in region order, identical to a single rvh_call_regions over all regions. */
+typedef struct rvh_pipeline rvh_pipeline;
+rvh_pipeline* rvh_pipeline_create(int device, int n_workers);
+void rvh_pipeline_destroy(rvh_pipeline* p);
+int rvh_pipeline_run(rvh_pipeline* p, const rv_params* params, const rvh_batch* batch, const rv_region* regions,
+                     int32_t n_regions, int32_t chunk_regions, const char* ref_bases, int32_t ref_lo, int64_t ref_n,
+                     const char* sample, const char* chr, const char** tsv_out, int64_t* tsv_len, rvh_timing* timing);
+/* Kernels launched by the pipeline's contexts so far. */
+int64_t rvh_pipeline_launch_count(const rvh_pipeline* p);
 const char* rvh_last_error(void);
 
 #ifdef __cplusplus

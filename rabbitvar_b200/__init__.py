@@ -12,7 +12,7 @@ import ctypes as C
 import os
 
 __all__ = ["RabbitVarError", "lib", "lib_path", "Params", "Limits", "Read", "Region", "Event", "Variant",
-           "PileupStats", "Timing", "Context", "HostBatch", "default_params", "default_limits", "fetch_ref"]
+           "PileupStats", "Timing", "Context", "Pipeline", "HostBatch", "default_params", "default_limits", "fetch_ref"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -110,7 +110,7 @@ class Timing(C.Structure):
 # every symbol include/*.h declares (checked by tests without a GPU)
 ABI_SYMBOLS = [
     "rv_abi_version", "rv_device_count", "rv_default_params", "rv_default_limits", "rv_create", "rv_destroy",
-    "rv_last_error", "rv_sync", "rv_ctx_halo", "rv_set_params", "rv_set_reference", "rv_push_reads", "rv_push_reads_device", "rv_set_regions",
+    "rv_last_error", "rv_sync", "rv_ctx_halo", "rv_set_params", "rv_set_reference", "rv_push_reads", "rv_push_reads_range", "rv_push_reads_device", "rv_set_regions",
     "rv_pileup", "rv_score", "rv_get_pileup_stats", "rv_fetch_max_read_len", "rv_fetch_tables", "rv_fetch_rows",
     "rv_fetch_events",
     "rv_apply_patch", "rv_fetch_variants", "rv_variant_count", "rv_fisher_exact", "rv_last_kernel_ms", "rv_timer_start",
@@ -118,6 +118,7 @@ ABI_SYMBOLS = [
     "rvh_load_bam", "rvh_batch_append", "rvh_batch_n_reads", "rvh_batch_reads", "rvh_batch_pool",
     "rvh_batch_pool_bytes", "rvh_batch_max_ref_span", "rvh_batch_pin", "rvh_batch_free", "rvh_make_regions", "rvh_fetch_ref",
     "rvh_call_regions", "rvh_install_patch", "rvh_last_error",
+    "rvh_pipeline_create", "rvh_pipeline_destroy", "rvh_pipeline_run", "rvh_pipeline_launch_count",
 ]
 
 
@@ -138,6 +139,14 @@ def _declare(L):
     L.rv_set_reference.argtypes = [vp, i32, i64, vp]
     L.rv_push_reads.argtypes = [vp, C.POINTER(ReadBatch)]
     L.rv_push_reads_device.argtypes = [vp, C.POINTER(ReadBatch)]
+    L.rv_push_reads_range.argtypes = [vp, C.POINTER(ReadBatch), i64, i64]
+    L.rvh_pipeline_create.argtypes = [C.c_int, C.c_int]
+    L.rvh_pipeline_create.restype = vp
+    L.rvh_pipeline_destroy.argtypes = [vp]
+    L.rvh_pipeline_run.argtypes = [vp, C.POINTER(Params), vp, C.POINTER(Region), i32, i32, vp, i32, i64, C.c_char_p,
+                                   C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(i64), C.POINTER(Timing)]
+    L.rvh_pipeline_launch_count.argtypes = [vp]
+    L.rvh_pipeline_launch_count.restype = i64
     L.rv_set_regions.argtypes = [vp, C.POINTER(Region), i32]
     L.rv_pileup.argtypes = [vp]
     L.rv_score.argtypes = [vp]
@@ -180,6 +189,43 @@ def _declare(L):
     L.rv_variant_count.argtypes = [vp]
     L.rv_variant_count.restype = i64
     L.rvh_last_error.restype = C.c_char_p
+
+
+class Pipeline:
+    """Chunked, multi-worker form of :meth:`Context.call_regions` (``rvh_pipeline_*``): several contexts on one
+    GPU work through the region list chunk by chunk so copies, kernels and the host stages overlap."""
+
+    def __init__(self, device=0, n_workers=4):
+        if lib().rv_device_count() <= 0:
+            raise RabbitVarError("no CUDA device: the pipeline has no CPU path")
+        self._h = lib().rvh_pipeline_create(device, n_workers)
+        if not self._h:
+            raise RabbitVarError("rvh_pipeline_create failed")
+
+    def run(self, params, batch, regions, chunk_regions, ref_bases, ref_lo, sample, chrom):
+        out = C.c_char_p()
+        n = C.c_int64()
+        tm = Timing()
+        rc = lib().rvh_pipeline_run(self._h, C.byref(params), batch._h, regions, len(regions), chunk_regions,
+                                    C.cast(C.c_char_p(ref_bases), C.c_void_p), ref_lo, len(ref_bases), sample.encode(),
+                                    chrom.encode(), C.byref(out), C.byref(n), C.byref(tm))
+        if rc != 0:
+            raise RabbitVarError(f"rvh_pipeline_run failed ({rc}): {lib().rvh_last_error().decode()}")
+        return C.string_at(out, n.value).decode(), tm
+
+    def launch_count(self):
+        return lib().rvh_pipeline_launch_count(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rvh_pipeline_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def default_params(**kw):

@@ -226,7 +226,12 @@ inline void parallel_for(size_t n, int threads, F f) {
     });
   for (size_t t = 0; t < th.size(); ++t) th[t].join();
 }
+inline int& host_threads_override() {  // per calling thread: workers of a pipeline share the cores
+  static thread_local int v = 0;
+  return v;
+}
 inline int host_threads() {
+  if (host_threads_override() > 0) return host_threads_override();
   const char* e = getenv("RV_HOST_THREADS");
   if (e && atoi(e) > 0) return atoi(e);
   unsigned hc = std::thread::hardware_concurrency();

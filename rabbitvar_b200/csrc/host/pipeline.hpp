@@ -134,7 +134,7 @@ inline int host_handoff(rv_ctx* ctx, const rv_params& P, const ReadBatch& batch,
 inline int run_batch_simple(rv_ctx* ctx, const rv_params& P, const ReadBatch& batch, const std::vector<rv_region>& regs,
                             const std::vector<std::string>& genes, const std::string& refseq, int32_t ref_lo,
                             const std::string& sample, const std::string& chr, int push_flags, int halo,
-                            std::string* tsv, BatchTiming* tm, std::string* err) {
+                            std::string* tsv, BatchTiming* tm, std::string* err, const int64_t* read_range = NULL) {
   BatchTiming t;
   memset(&t, 0, sizeof t);
   int rc;
@@ -151,8 +151,18 @@ inline int run_batch_simple(rv_ctx* ctx, const rv_params& P, const ReadBatch& ba
   if (push_reference) RV_STEP(rv_set_reference(ctx, ref_lo, (int64_t)refseq.size(), refseq.data()));
   if (push_reads) {
     rv_read_batch bv = batch.view();
-    RV_STEP(rv_push_reads(ctx, &bv));
-    t.h2d_bytes += (int64_t)batch.reads.size() * (int64_t)sizeof(rv_read) + (int64_t)batch.pool.size();
+    if (read_range) {
+      RV_STEP(rv_push_reads_range(ctx, &bv, read_range[0], read_range[1]));
+      if (read_range[1] > read_range[0]) {
+        const int64_t p_lo = (int64_t)batch.reads[(size_t)read_range[0]].data_off16 * 16;
+        const int64_t p_hi = read_range[1] < (int64_t)batch.reads.size()
+                                 ? (int64_t)batch.reads[(size_t)read_range[1]].data_off16 * 16 : (int64_t)batch.pool.size();
+        t.h2d_bytes += (read_range[1] - read_range[0]) * (int64_t)sizeof(rv_read) + (p_hi - p_lo);
+      }
+    } else {
+      RV_STEP(rv_push_reads(ctx, &bv));
+      t.h2d_bytes += (int64_t)batch.reads.size() * (int64_t)sizeof(rv_read) + (int64_t)batch.pool.size();
+    }
   }
   RV_STEP(rv_set_regions(ctx, regs.data(), (int32_t)regs.size()));
   t.h2d_bytes += (push_reference ? (int64_t)refseq.size() : 0);

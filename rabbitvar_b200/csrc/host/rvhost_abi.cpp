@@ -1,8 +1,10 @@
 // rvhost_abi.cpp — C ABI over the host side of the path (include/rabbitvar_b200_host.h).
 #include "../../../include/rabbitvar_b200_host.h"
 #include "pipeline.hpp"
+#include <atomic>
 #include <map>
 #include <mutex>
+#include <thread>
 
 using namespace rvhost;
 
@@ -24,7 +26,176 @@ static thread_local std::string g_err;
 static std::mutex g_tsv_mu;
 static std::map<rv_ctx*, std::string> g_tsv;  // per-context output buffers
 
+// ---- pipelined region loop --------------------------------------------------------------------------
+struct rvh_pipeline {
+  int device;
+  int n_workers;
+  std::vector<rv_ctx*> ctx;
+  std::vector<rv_limits> lim;        // capacity the worker contexts were created with
+  std::vector<const char*> ref_seen; // reference slice resident on each worker context
+  std::vector<int32_t> ref_lo_seen;
+  std::vector<int64_t> ref_n_seen;
+  std::string tsv;
+  std::string refseq;
+  int64_t launches_retired;
+};
+
+static bool limits_cover(const rv_limits& have, const rv_limits& need) {
+  return have.max_reads >= need.max_reads && have.max_read_bytes >= need.max_read_bytes &&
+         have.max_positions >= need.max_positions && have.max_regions >= need.max_regions &&
+         have.max_events >= need.max_events && have.max_variants >= need.max_variants &&
+         have.max_patch >= need.max_patch && have.max_ref_bases >= need.max_ref_bases && have.halo == need.halo;
+}
+
 extern "C" {
+
+rvh_pipeline* rvh_pipeline_create(int device, int n_workers) {
+  if (n_workers < 1) n_workers = 1;
+  if (n_workers > 16) n_workers = 16;
+  rvh_pipeline* p = new rvh_pipeline();
+  p->device = device;
+  p->n_workers = n_workers;
+  p->ctx.assign((size_t)n_workers, (rv_ctx*)NULL);
+  p->lim.resize((size_t)n_workers);
+  p->ref_seen.assign((size_t)n_workers, (const char*)NULL);
+  p->ref_lo_seen.assign((size_t)n_workers, 0);
+  p->ref_n_seen.assign((size_t)n_workers, 0);
+  p->launches_retired = 0;
+  return p;
+}
+
+void rvh_pipeline_destroy(rvh_pipeline* p) {
+  if (!p) return;
+  for (size_t i = 0; i < p->ctx.size(); ++i) rv_destroy(p->ctx[i]);
+  delete p;
+}
+
+int64_t rvh_pipeline_launch_count(const rvh_pipeline* p) {
+  if (!p) return 0;
+  int64_t n = p->launches_retired;
+  for (size_t i = 0; i < p->ctx.size(); ++i) n += rv_launch_count(p->ctx[i]);
+  return n;
+}
+
+int rvh_pipeline_run(rvh_pipeline* p, const rv_params* params, const rvh_batch* batch, const rv_region* regions,
+                     int32_t n_regions, int32_t chunk_regions, const char* ref_bases, int32_t ref_lo, int64_t ref_n,
+                     const char* sample, const char* chr, const char** tsv_out, int64_t* tsv_len, rvh_timing* timing) {
+  if (!p || !params || !batch || (!regions && n_regions) || !ref_bases || !tsv_out || !tsv_len || n_regions < 0)
+    return RV_ERR_ARG;
+  try {
+    if (chunk_regions < 1) chunk_regions = 1;
+    const int n_chunks = (n_regions + chunk_regions - 1) / chunk_regions;
+    const ReadBatch& B = batch->b;
+    const int halo = 512;
+    // capacity one chunk needs
+    rv_limits need;
+    rv_default_limits(&need);
+    need.halo = halo;
+    need.max_reads = 1024; need.max_read_bytes = 4096; need.max_positions = 1024; need.max_regions = chunk_regions + 8;
+    std::vector<int64_t> c_lo((size_t)n_chunks), c_hi((size_t)n_chunks);
+    for (int c = 0; c < n_chunks; ++c) {
+      const int r0 = c * chunk_regions, r1 = std::min(n_regions, r0 + chunk_regions);
+      int64_t lo = -1, hi = -1, npos = 0;
+      for (int r = r0; r < r1; ++r) {
+        npos += regions[r].end - regions[r].start + 1 + 2 * halo;
+        if (regions[r].read_hi <= regions[r].read_lo) continue;
+        if (lo < 0 || regions[r].read_lo < lo) lo = regions[r].read_lo;
+        if (regions[r].read_hi > hi) hi = regions[r].read_hi;
+      }
+      if (lo < 0) lo = hi = 0;
+      c_lo[(size_t)c] = lo;
+      c_hi[(size_t)c] = hi;
+      int64_t bytes = 0;
+      if (hi > lo) {
+        const int64_t p_lo = (int64_t)B.reads[(size_t)lo].data_off16 * 16;
+        const int64_t p_hi = hi < (int64_t)B.reads.size() ? (int64_t)B.reads[(size_t)hi].data_off16 * 16 : (int64_t)B.pool.size();
+        bytes = p_hi - p_lo;
+      }
+      need.max_reads = std::max<int64_t>(need.max_reads, hi - lo + 64);
+      need.max_read_bytes = std::max<int64_t>(need.max_read_bytes, bytes + 256);
+      need.max_positions = std::max<int64_t>(need.max_positions, npos + 64);
+    }
+    need.max_events = std::max<int64_t>(1 << 18, need.max_reads);
+    need.max_variants = 3 * need.max_positions + 1024;
+    need.max_patch = std::max<int64_t>(1 << 18, need.max_reads / 2);
+    need.max_ref_bases = ref_n + 64;
+    for (int w = 0; w < p->n_workers; ++w) {
+      if (p->ctx[(size_t)w] && limits_cover(p->lim[(size_t)w], need)) continue;
+      if (p->ctx[(size_t)w]) {
+        p->launches_retired += rv_launch_count(p->ctx[(size_t)w]);
+        rv_destroy(p->ctx[(size_t)w]);
+        p->ctx[(size_t)w] = NULL;
+      }
+      rv_limits L = need;  // head-room so that similar batches do not re-allocate
+      L.max_reads += L.max_reads / 8; L.max_read_bytes += L.max_read_bytes / 8; L.max_positions += L.max_positions / 8;
+      L.max_variants = 3 * L.max_positions + 1024;
+      int rc = rv_create(&p->ctx[(size_t)w], p->device, params, &L);
+      if (rc != RV_OK) {
+        g_err = std::string("rv_create (pipeline worker): ") + rv_last_error(p->ctx[(size_t)w]);
+        rv_destroy(p->ctx[(size_t)w]);
+        p->ctx[(size_t)w] = NULL;
+        return rc;
+      }
+      p->lim[(size_t)w] = L;
+      p->ref_seen[(size_t)w] = NULL;
+    }
+    p->refseq.assign(ref_bases, (size_t)ref_n);
+    rv_params P = *params;
+    P.candidates_only = P.pileup ? 0 : 1;  // simple-mode text output only prints positions with a passing variant
+    std::vector<std::string> ctsv((size_t)n_chunks), cerr((size_t)n_chunks);
+    std::vector<BatchTiming> ctm((size_t)n_chunks);
+    std::vector<int> crc((size_t)n_chunks, RV_OK);
+    std::atomic<int> next(0);
+    const int host_thr = std::max(1, host_threads() / p->n_workers);
+    const double t_begin = now_ms();
+    std::vector<std::thread> th;
+    for (int w = 0; w < p->n_workers; ++w)
+      th.emplace_back([&, w]() {
+        host_threads_override() = host_thr;
+        rv_ctx* ctx = p->ctx[(size_t)w];
+        rv_set_params(ctx, &P);
+        bool first = true;  // the reference slice is uploaded once per worker and run
+        for (;;) {
+          const int c = next.fetch_add(1);
+          if (c >= n_chunks) break;
+          const int r0 = c * chunk_regions, r1 = std::min(n_regions, r0 + chunk_regions);
+          std::vector<rv_region> regs(regions + r0, regions + r1);
+          std::vector<std::string> genes(regs.size(), std::string(chr));
+          const int flags = 2 | (first ? 1 : 0);
+          first = false;
+          const int64_t range[2] = {c_lo[(size_t)c], c_hi[(size_t)c]};
+          crc[(size_t)c] = run_batch_simple(ctx, P, B, regs, genes, p->refseq, ref_lo, sample, chr, flags, halo,
+                                            &ctsv[(size_t)c], &ctm[(size_t)c], &cerr[(size_t)c], range);
+          if (crc[(size_t)c] != RV_OK) break;
+        }
+        rv_set_params(ctx, params);
+      });
+    for (size_t i = 0; i < th.size(); ++i) th[i].join();
+    const double t_end = now_ms();
+    p->tsv.clear();
+    rvh_timing tt;
+    memset(&tt, 0, sizeof tt);
+    for (int c = 0; c < n_chunks; ++c) {
+      if (crc[(size_t)c] != RV_OK) { g_err = cerr[(size_t)c]; return crc[(size_t)c]; }
+      p->tsv.append(ctsv[(size_t)c]);
+      const BatchTiming& t = ctm[(size_t)c];
+      tt.push_ms += t.push_ms; tt.pileup_ms += t.pileup_ms; tt.fetch_ms += t.fetch_ms; tt.host_ms += t.host_ms;
+      tt.patch_ms += t.patch_ms; tt.score_ms += t.score_ms; tt.assemble_ms += t.assemble_ms;
+      tt.pileup_kernel_ms += t.pileup_kernel_ms; tt.score_kernel_ms += t.score_kernel_ms;
+      tt.n_items += t.stats.n_items; tt.n_reads_kept += t.stats.n_reads_kept; tt.n_aligned_bases += t.stats.n_aligned_bases;
+      tt.n_events += t.stats.n_events; tt.n_unsupported += t.stats.n_unsupported; tt.n_variants += t.n_variants;
+      tt.n_lines += t.n_lines; tt.h2d_bytes += t.h2d_bytes; tt.d2h_bytes += t.d2h_bytes;
+    }
+    (void)t_begin; (void)t_end;
+    *tsv_out = p->tsv.data();
+    *tsv_len = (int64_t)p->tsv.size();
+    if (timing) *timing = tt;
+    return RV_OK;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return RV_ERR_STATE;
+  }
+}
 
 const char* rvh_last_error(void) { return g_err.c_str(); }
 

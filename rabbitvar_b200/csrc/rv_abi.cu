@@ -949,6 +949,7 @@ struct rv_ctx {
   const rv_read* reads_dev_view;  // d_reads or a caller-provided device pointer
   const uint8_t* pool_dev_view;
   int64_t n_reads;
+  int64_t read_origin;  // first batch read index that is resident (rv_push_reads_range)
   std::vector<DevRegion> regions;
   int64_t n_positions, n_items;
   bool have_patch;
@@ -1055,7 +1056,7 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   ctx->use_gather = getenv("RV_NO_GATHER") == NULL;
   ctx->h_counts = NULL; ctx->h_cov = NULL; ctx->h_tab_cap = 0; ctx->h_events = NULL; ctx->h_events_cap = 0;
   ctx->h_variants = NULL; ctx->h_variants_cap = 0; ctx->h_max_rl = NULL; ctx->h_rows = NULL; ctx->h_rows_cap = 0; ctx->d_scratch = NULL; ctx->scratch_cap = 0;
-  ctx->n_reads = 0; ctx->n_positions = 0; ctx->n_items = 0; ctx->have_patch = false; ctx->tables_fetched = false;
+  ctx->n_reads = 0; ctx->read_origin = 0; ctx->n_positions = 0; ctx->n_items = 0; ctx->have_patch = false; ctx->tables_fetched = false;
   ctx->ref_start = 1; ctx->ref_n = 0; ctx->pileup_ms = ctx->score_ms = 0;
   ctx->reads_dev_view = NULL; ctx->pool_dev_view = NULL;
   *out = ctx;  // returned even on failure so the caller can read rv_last_error, then rv_destroy
@@ -1171,6 +1172,29 @@ int rv_push_reads(rv_ctx* ctx, const rv_read_batch* b) {
   ctx->reads_dev_view = ctx->d_reads;
   ctx->pool_dev_view = ctx->d_pool;
   ctx->n_reads = b->n_reads;
+  ctx->read_origin = 0;
+  return RV_OK;
+}
+
+int rv_push_reads_range(rv_ctx* ctx, const rv_read_batch* b, int64_t read_lo, int64_t read_hi) {
+  if (!ctx || !b || read_lo < 0 || read_hi < read_lo || read_hi > b->n_reads) return RV_ERR_ARG;
+  const int64_t n = read_hi - read_lo;
+  if (n > ctx->L.max_reads) return fail(ctx, RV_ERR_OVERFLOW, "read range larger than limits.max_reads");
+  CK(cudaSetDevice(ctx->device));
+  int64_t pool_lo = 0, pool_hi = 0;
+  if (n) {
+    pool_lo = (int64_t)b->reads[read_lo].data_off16 * 16;
+    pool_hi = read_hi < b->n_reads ? (int64_t)b->reads[read_hi].data_off16 * 16 : b->pool_bytes;
+    if (pool_hi < pool_lo || pool_hi > b->pool_bytes) return fail(ctx, RV_ERR_ARG, "read headers do not index the pool in order");
+    if (pool_hi - pool_lo > ctx->L.max_read_bytes) return fail(ctx, RV_ERR_OVERFLOW, "read range pool larger than limits.max_read_bytes");
+    CK(cudaMemcpyAsync(ctx->d_reads, b->reads + read_lo, sizeof(rv_read) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_pool, b->pool + pool_lo, (size_t)(pool_hi - pool_lo), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  // device views biased so that batch-global read indices and pool offsets address the uploaded slice
+  ctx->reads_dev_view = ctx->d_reads - read_lo;
+  ctx->pool_dev_view = ctx->d_pool - pool_lo;
+  ctx->n_reads = read_hi;
+  ctx->read_origin = read_lo;
   return RV_OK;
 }
 
@@ -1179,6 +1203,7 @@ int rv_push_reads_device(rv_ctx* ctx, const rv_read_batch* b) {
   ctx->reads_dev_view = b->reads;
   ctx->pool_dev_view = b->pool;
   ctx->n_reads = b->n_reads;
+  ctx->read_origin = 0;
   return RV_OK;
 }
 
@@ -1191,7 +1216,8 @@ int rv_set_regions(rv_ctx* ctx, const rv_region* regs, int32_t n) {
   for (int i = 0; i < n; ++i) {
     DevRegion& d = ctx->regions[i];
     d.r = regs[i];
-    if (d.r.end < d.r.start || d.r.read_hi < d.r.read_lo || d.r.read_hi > ctx->n_reads)
+    if (d.r.end < d.r.start || d.r.read_hi < d.r.read_lo || d.r.read_hi > ctx->n_reads ||
+        (d.r.read_hi > d.r.read_lo && d.r.read_lo < ctx->read_origin))
       return fail(ctx, RV_ERR_ARG, "bad region " + std::to_string(i));
     d.first_pos = d.r.start - ctx->L.halo;
     d.n_pos = d.r.end - d.r.start + 1 + 2 * ctx->L.halo;
@@ -1360,8 +1386,10 @@ int rv_fetch_rows(rv_ctx* ctx, const int32_t* region, const int32_t* pos, int64_
   if ((size_t)n > ctx->h_rows_cap) {
     if (ctx->h_rows) cudaFreeHost(ctx->h_rows);
     ctx->h_rows = NULL;
-    CK(cudaMallocHost(&ctx->h_rows, sizeof(uint32_t) * 33 * (size_t)n));
-    ctx->h_rows_cap = (size_t)n;
+    ctx->h_rows_cap = 0;
+    const size_t cap = (size_t)n + (size_t)n / 2 + 1024;  // geometric growth: page-locking is slow
+    CK(cudaMallocHost(&ctx->h_rows, sizeof(uint32_t) * 33 * cap));
+    ctx->h_rows_cap = cap;
   }
   int rcs = ensure_scratch(ctx, (size_t)n * (8 + 33 * 4) + 64);
   if (rcs != RV_OK) return rcs;
@@ -1385,10 +1413,11 @@ int rv_fetch_events(rv_ctx* ctx, const rv_event** events, int64_t* n_events) {
   size_t n = (size_t)std::min<unsigned long long>(ctx->h_stats.n_events, (unsigned long long)ctx->L.max_events);
   if (n > ctx->h_events_cap) {
     if (ctx->h_events) cudaFreeHost(ctx->h_events);
-  if (ctx->h_rows) cudaFreeHost(ctx->h_rows);
     ctx->h_events = NULL;
-    CK(cudaMallocHost(&ctx->h_events, sizeof(rv_event) * n));
-    ctx->h_events_cap = n;
+    ctx->h_events_cap = 0;
+    const size_t cap = n + n / 2 + 1024;
+    CK(cudaMallocHost(&ctx->h_events, sizeof(rv_event) * cap));
+    ctx->h_events_cap = cap;
   }
   if (n) {
     CK(cudaMemcpyAsync(ctx->h_events, ctx->d_events, sizeof(rv_event) * n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1529,8 +1558,10 @@ int rv_fetch_variants(rv_ctx* ctx, const rv_variant** variants, int64_t* n_varia
   if (n > ctx->h_variants_cap) {
     if (ctx->h_variants) cudaFreeHost(ctx->h_variants);
     ctx->h_variants = NULL;
-    CK(cudaMallocHost(&ctx->h_variants, sizeof(rv_variant) * n));
-    ctx->h_variants_cap = n;
+    ctx->h_variants_cap = 0;
+    const size_t cap = n + n / 2 + 1024;
+    CK(cudaMallocHost(&ctx->h_variants, sizeof(rv_variant) * cap));
+    ctx->h_variants_cap = cap;
   }
   if (n) {
     CK(cudaMemcpyAsync(ctx->h_variants, ctx->d_variants, sizeof(rv_variant) * n, cudaMemcpyDeviceToHost, ctx->stream));

@@ -137,3 +137,30 @@ def test_pileup_is_deterministic_and_additive(built):
     assert np.array_equal(parts[0][0][..., :7] + parts[1][0][..., :7], c1[..., :7])
     assert np.array_equal(parts[0][1] + parts[1][1], v1)
     ctx.close()
+
+
+def test_pipeline_equals_single_call(built):
+    """rvh_pipeline_run (chunks of tiles on several worker contexts, ranged read uploads) must print exactly what one
+    rvh_call_regions over all tiles prints."""
+    import rabbitvar_b200 as rv
+    d = cases.generate("c1_k1")
+    bam, fa = os.path.join(d, "S.bam"), os.path.join(d, "ref.fa")
+    starts = list(range(1301, 21301, 2500))
+    ends = [s + 2499 for s in starts]
+    b = rv.HostBatch(bam, "chrS1", starts[0], ends[-1])
+    ref = rv.fetch_ref(fa, "chrS1", 1, b.chr_len)
+    lim = rv.default_limits(max_reads=b.n_reads + 16, max_read_bytes=b.pool_bytes + 64, max_ref_bases=len(ref) + 16)
+    params = rv.default_params()
+    ctx = rv.Context(0, params, lim)
+    regs = b.make_regions(starts, ends)
+    want, tm = ctx.call_regions(b, regs, ref, 1, "S", "chrS1")
+    ctx.close()
+    assert tm.n_lines > 10
+    for workers, chunk in ((1, 8), (3, 3), (4, 1)):
+        pipe = rv.Pipeline(0, workers)
+        got, tm2 = pipe.run(params, b, regs, chunk, ref, 1, "S", "chrS1")
+        assert pipe.launch_count() > 0
+        pipe.close()
+        assert got == want
+        assert tm2.n_aligned_bases == tm.n_aligned_bases and tm2.n_lines == tm.n_lines
+    b.close()
