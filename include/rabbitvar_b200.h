@@ -265,6 +265,9 @@ int rv_fisher_exact(rv_ctx* ctx, const int32_t* tables, int64_t n, double* out);
 
 /* Device timing of the last rv_pileup / rv_score in milliseconds (CUDA events on the context stream). */
 int rv_last_kernel_ms(rv_ctx* ctx, float* pileup_ms, float* score_ms);
+/* The same for the kernels of the last rv_pileup: rv_pileup_kernel (filters, CIGAR rewrite, plain-run proof),
+ * rv_tile_index_kernel + rv_gather_kernel (position-major accumulation), rv_walk_kernel (exact CIGAR walks). */
+int rv_last_pileup_split_ms(rv_ctx* ctx, float* classify_ms, float* gather_ms, float* walk_ms);
 /* Brackets any sequence of calls with CUDA events recorded on the context's (launching) stream;
  * rv_timer_stop synchronises and returns the elapsed device time in milliseconds. */
 int rv_timer_start(rv_ctx* ctx);

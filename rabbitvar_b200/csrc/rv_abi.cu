@@ -676,6 +676,249 @@ __global__ void __launch_bounds__(GATHER_TILE) rv_gather_kernel(GatherArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Warp-specialised form of the gather kernel: warp 8 is a producer that prepares the next round (descriptor
+// loads, clipping, arena layout, asynchronous global->shared copies) into one of two shared-memory stages
+// while warps 0-7 (one lane per table position) consume the other; named barriers hand the stages over.
+// ------------------------------------------------------------------------------------------------
+static const int WS_CAND = 128;          // candidate descriptors per round (4 per producer lane)
+static const int WS_STAGE_CHUNKS = 1024; // 16 KB of staged read bytes per stage
+static const int WS_THREADS = GATHER_TILE + 32;
+
+struct WsStage {
+  uint4 arena[WS_STAGE_CHUNKS];
+  uint4 rec[WS_CAND];
+  int wlo[GATHER_TILE / 32], whi[GATHER_TILE / 32];
+  int n_slots, done;
+  int pad[2];
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 4) rv_gather_ws_kernel(GatherArgs a) {
+  __shared__ __align__(16) WsStage s_stage[2];
+  __shared__ uint4 s_copy[WS_CAND];  // producer scratch: {first seq chunk, first qual chunk, ns | nq << 8, arena chunk}
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t tile = blockIdx.x;
+  const int4 tinfo = ((const int4*)a.tile_range)[tile];  // {read lo (64 bit), n reads, region}
+  const DevRegion* dr = a.regions + tinfo.w;
+  const int64_t lo = (int64_t)(((unsigned long long)(unsigned)tinfo.y << 32) | (unsigned)tinfo.x);
+  const int64_t hi = lo + tinfo.z;
+  const int p_lo = dr->first_pos + (int)(tile - dr->tile_base) * GATHER_TILE;
+  const int c_lo = p_lo > dr->r.start ? p_lo : dr->r.start;  // positions that can receive observations
+  const int c_hi = p_lo + GATHER_TILE - 1 < dr->r.end ? p_lo + GATHER_TILE - 1 : dr->r.end;
+  enum { BAR_FULL = 1, BAR_EMPTY = 3 };
+
+  if (warp == GATHER_TILE / 32) {
+    // =========================== producer warp ===========================
+    const GDesc* item_desc = a.descs + (dr->item_base - dr->r.read_lo);  // descriptor of read index i
+    const uint4* pool16 = (const uint4*)a.pool;
+    int round = 0;
+    for (int64_t base = lo;; ++round) {
+      WsStage& st = s_stage[round & 1];
+      if (round >= 2) named_bar_sync(BAR_EMPTY + (round & 1), WS_THREADS);
+      if (base >= hi) {  // nothing left: tell the consumers
+        if (lane == 0) { st.n_slots = 0; st.done = 1; }
+        __syncwarp();
+        named_bar_arrive(BAR_FULL + (round & 1), WS_THREADS);
+        break;
+      }
+      if (lane < GATHER_TILE / 32) { st.wlo[lane] = WS_CAND; st.whi[lane] = 0; }
+      __syncwarp();
+      // ---- four consecutive candidates per lane: clip to the tile, size the chunks ----
+      GDesc d[4];
+      int ns[4], nq[4], n_lo[4];
+      unsigned sfirst_lo[4], qfirst_lo[4];  // low 4 bits of the first seq / qual byte address
+      unsigned sc0[4], qc0[4];
+      int mine = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t i = base + lane * 4 + j;
+        d[j].m_len = 0;
+        if (i < hi) *(uint4*)&d[j] = *(const uint4*)(item_desc + i);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ns[j] = nq[j] = 0;
+        n_lo[j] = 0; sfirst_lo[j] = qfirst_lo[j] = 0; sc0[j] = qc0[j] = 0;
+        if (d[j].m_len != 0) {
+          const int k_lo = c_lo - d[j].m_start > 0 ? c_lo - d[j].m_start : 0;
+          const int k_hi = c_hi + 1 - d[j].m_start < (int)d[j].m_len ? c_hi + 1 - d[j].m_start : (int)d[j].m_len;
+          if (k_lo < k_hi) {
+            n_lo[j] = d[j].rp0 + k_lo;
+            const int n_hi_ = d[j].rp0 + k_hi;
+            const size_t sb = (size_t)d[j].seq_off4 * 4;
+            const size_t qb = sb + ((d[j].l_seq + 1) >> 1);
+            const size_t s_first = sb + (n_lo[j] >> 1), q_first = qb + n_lo[j];
+            ns[j] = (int)(((sb + ((n_hi_ - 1) >> 1)) >> 4) - (s_first >> 4)) + 1;
+            nq[j] = (int)(((qb + n_hi_ - 1) >> 4) - (q_first >> 4)) + 1;
+            sfirst_lo[j] = (unsigned)(s_first & 15);
+            qfirst_lo[j] = (unsigned)(q_first & 15);
+            sc0[j] = (unsigned)(s_first >> 4);
+            qc0[j] = (unsigned)(q_first >> 4);
+            mine += (ns[j] + nq[j]) | (1 << 16);
+          }
+        }
+      }
+      // warp scan of (chunks | staged reads << 16) over the lanes, then over the lane's four candidates
+      int incl = mine;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += y;
+      }
+      int run = incl - mine;  // exclusive prefix of this lane
+      int n_fit = 0, n_staged = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int need = ns[j] + nq[j];
+        const int chunk0 = run & 0xffff, slot = run >> 16;
+        const bool fits = chunk0 + need <= WS_STAGE_CHUNKS;  // a prefix of the round (the scan is monotone)
+        if (need) run += need | (1 << 16);
+        if (fits) n_fit++;
+        if (fits && need) {
+          n_staged++;
+          const int rel_start = d[j].m_start - p_lo;
+          const int n0 = (int)d[j].rp0 - rel_start;  // read offset of the base under tile coordinate 0
+          const int par = n0 & 1;
+          const int so = chunk0 * 16 + (int)sfirst_lo[j] - (n_lo[j] >> 1) + ((n0 - par) >> 1) + REC_BIAS;
+          const int qo = (chunk0 + ns[j]) * 16 + (int)qfirst_lo[j] - n_lo[j] + n0 + REC_BIAS;
+          st.rec[slot] = make_uint4((uint32_t)rel_start, (uint32_t)so | ((uint32_t)qo << 16),
+                                    (uint32_t)d[j].m_len | ((uint32_t)par << 16) | ((uint32_t)(d[j].dir_nm >> 7) << 17),
+                                    (uint32_t)d[j].mapq | ((uint32_t)(d[j].dir_nm & 0x7f) << 16));
+          s_copy[slot] = make_uint4(sc0[j], qc0[j], (uint32_t)(ns[j] | (nq[j] << 8)), (uint32_t)chunk0);
+          const int x_lo = rel_start > c_lo - p_lo ? rel_start : c_lo - p_lo;
+          const int x_hi = rel_start + (int)d[j].m_len - 1 < c_hi - p_lo ? rel_start + (int)d[j].m_len - 1 : c_hi - p_lo;
+          for (int w = x_lo >> 5; w <= (x_hi >> 5); ++w) {
+            atomicMin(&st.wlo[w], slot);
+            atomicMax(&st.whi[w], slot + 1);
+          }
+        }
+      }
+      n_fit = __reduce_add_sync(0xffffffffu, n_fit);
+      n_staged = __reduce_add_sync(0xffffffffu, n_staged);
+      __syncwarp();
+      // ---- asynchronous copies: one read per step, one 16-byte chunk per lane ----
+      for (int sidx = 0; sidx < n_staged; ++sidx) {
+        const uint4 c = s_copy[sidx];
+        const int cns = (int)(c.z & 0xff), cnq = (int)(c.z >> 8);
+        if (lane < cns + cnq) {
+          const size_t src = lane < cns ? (size_t)c.x + lane : (size_t)c.y + (lane - cns);
+          const unsigned dst = (unsigned)__cvta_generic_to_shared(&st.arena[c.w + lane]);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(pool16 + src) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (lane == 0) { st.n_slots = n_staged; st.done = 0; }
+      __syncwarp();
+      named_bar_arrive(BAR_FULL + (round & 1), WS_THREADS);
+      base += n_fit;
+    }
+    return;
+  }
+
+  // =========================== consumer warps: one lane per table position ===========================
+  const int x = tid;
+  const int p = p_lo + x;
+  const bool in_table = p - dr->first_pos < dr->n_pos;
+  const bool live = p >= c_lo && p <= c_hi;
+  int refnib = 0;  // the lane's reference allele, as a BAM nibble (0 = none: every observation takes the row path)
+  if (live && p >= dr->r.ref_lo && p <= dr->r.ref_hi && p >= a.ref_start && (int64_t)(p - a.ref_start) < a.ref_n) {
+    const char c = a.ref[p - a.ref_start];
+    refnib = c == 'A' ? 1 : c == 'C' ? 2 : c == 'G' ? 4 : c == 'T' ? 8 : 0;
+  }
+  const int thr = (int)ceil(a.goodq);  // integer q >= goodq
+  const int64_t t_row = dr->tab_off + (p - dr->first_pos);
+  uint32_t* const row0 = a.counts + (size_t)t_row * RV_POS_U32;
+  uint32_t n_ref = 0, n_rev = 0, sum_tp = 0, sum_q = 0, sum_mapq = 0, sum_nm = 0, n_hi = 0;
+  uint32_t v_and = 0xffffffffu, v_or = 0, v_last = 0, n_other = 0, other_mask = 0;
+  const int xs0 = (x >> 1) - REC_BIAS, xs1 = ((x + 1) >> 1) - REC_BIAS, xq = x - REC_BIAS;
+
+  for (int round = 0;; ++round) {
+    WsStage& st = s_stage[round & 1];
+    named_bar_sync(BAR_FULL + (round & 1), WS_THREADS);
+    if (st.done) break;
+    if (live) {
+      const uint8_t* arena = (const uint8_t*)st.arena;
+      const int w_lo = st.wlo[warp], w_hi = st.whi[warp];
+      uint32_t add_acc = 0;
+#pragma unroll 4
+      for (int slot = w_lo; slot < w_hi; ++slot) {
+        const uint4 r = st.rec[slot];
+        const int m_len = (int)(r.z & 0xffffu);
+        const int k = x - (int)r.x;
+        if ((unsigned)k >= (unsigned)m_len) continue;
+        const uint32_t q = arena[(int)(r.y >> 16) + xq];
+        const bool odd = (r.z >> 16) & 1;  // parity of the read offset under tile coordinate 0
+        const int sbyte = arena[(int)(r.y & 0xffffu) + (odd ? xs1 : xs0)];
+        const int nib = ((x ^ (int)odd) & 1) ? (sbyte & 15) : (sbyte >> 4);
+        const uint32_t tp = (uint32_t)min(k + 1, m_len - k);
+        const uint32_t v = tp | (q << 16);
+        const uint32_t hiq = (int)q >= thr ? 1u : 0u;
+        const uint32_t dir = (r.z >> 17) & 1u;
+        if (nib == refnib) {
+          n_ref++;
+          n_rev += dir;
+          sum_tp += tp;
+          sum_q += q;
+          add_acc += r.w;
+          n_hi += hiq;
+          v_and &= v;
+          v_or |= v;
+          v_last = v;
+        } else {
+          // a base that differs from the reference: the lane's own row of that allele, read-modify-write
+          const int al = nib_allele(nib);
+          uint4* row4 = (uint4*)(row0 + al * RV_ROW_U32);
+          uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
+          if (other_mask & (1u << al)) { ra = row4[0]; rb = row4[1]; }
+          ra.x += 1u - dir; ra.y += dir; ra.z += tp; ra.w += q;
+          rb.x += r.w & 0xffffu; rb.y += r.w >> 16; rb.z += hiq;
+          uint32_t w = rb.w;
+          if ((w >> 31) == 0) w = v | (1u << 31);
+          else {
+            if ((w ^ v) & 0xffffu) w |= 1u << 24;
+            if ((w ^ v) & 0xff0000u) w |= 1u << 25;
+          }
+          rb.w = w;
+          row4[0] = ra;
+          row4[1] = rb;
+          other_mask |= 1u << al;
+          n_other++;
+        }
+      }
+      sum_mapq += add_acc & 0xffffu;  // at most 128 reads per round: neither half can overflow
+      sum_nm += add_acc >> 16;
+    }
+    named_bar_arrive(BAR_EMPTY + (round & 1), WS_THREADS);
+  }
+  if (!in_table) return;
+  // ---- write the position: the reference allele from registers, untouched alleles as zeros ------------
+  a.cov[t_row] = n_ref + n_other;
+  const int a0 = refnib ? nib_allele(refnib) : -1;
+#pragma unroll
+  for (int al = 0; al < 4; ++al) {
+    if (other_mask & (1u << al)) continue;
+    uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
+    if (al == a0 && n_ref) {
+      ra = make_uint4(n_ref - n_rev, n_rev, sum_tp, sum_q);
+      uint32_t w = v_last | (1u << 31);
+      if ((v_and ^ v_or) & 0xffffu) w |= 1u << 24;
+      if ((v_and ^ v_or) & 0xff0000u) w |= 1u << 25;
+      rb = make_uint4(sum_mapq, sum_nm, n_hi, w);
+    }
+    uint4* row4 = (uint4*)(row0 + al * RV_ROW_U32);
+    row4[0] = ra;
+    row4[1] = rb;
+  }
+}
+
 struct ScoreArgs {
   rv_params P;
   const DevRegion* regions;
@@ -914,6 +1157,8 @@ struct rv_ctx {
   rv_limits L;
   cudaStream_t stream;
   cudaEvent_t ev0, ev1, tev0, tev1;
+  cudaEvent_t evs[3];      // boundaries between the kernels of the pileup stage
+  float split_ms[4];       // classify, tile index + gather, walk, (unused)
   std::string err;
   int64_t launches;
   // device buffers
@@ -945,6 +1190,7 @@ struct rv_ctx {
   unsigned long long* d_walk_count;
   int64_t n_tiles;
   bool use_gather;
+  bool gather_ws;   // warp-specialised gather kernel (RV_GATHER_WS=0 selects the single-role form)
   // batch state
   const rv_read* reads_dev_view;  // d_reads or a caller-provided device pointer
   const uint8_t* pool_dev_view;
@@ -1054,10 +1300,12 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   ctx->d_events = NULL; ctx->d_variants = NULL; ctx->d_patch = NULL; ctx->d_patch_first = NULL;
   ctx->d_patch_count = NULL; ctx->d_regions = NULL; ctx->d_max_rl = NULL; ctx->d_stats = NULL; ctx->d_lgt = NULL; ctx->d_descs = NULL; ctx->d_reach = NULL; ctx->d_ref4 = NULL; ctx->d_tile_range = NULL; ctx->tile_cap = 0; ctx->d_patched_queue = NULL; ctx->d_patched_count = NULL; ctx->d_walk_queue = NULL; ctx->d_walk_count = NULL; ctx->n_tiles = 0;
   ctx->use_gather = getenv("RV_NO_GATHER") == NULL;
+  ctx->gather_ws = !(getenv("RV_GATHER_WS") && atoi(getenv("RV_GATHER_WS")) == 0);
   ctx->h_counts = NULL; ctx->h_cov = NULL; ctx->h_tab_cap = 0; ctx->h_events = NULL; ctx->h_events_cap = 0;
   ctx->h_variants = NULL; ctx->h_variants_cap = 0; ctx->h_max_rl = NULL; ctx->h_rows = NULL; ctx->h_rows_cap = 0; ctx->d_scratch = NULL; ctx->scratch_cap = 0;
   ctx->n_reads = 0; ctx->read_origin = 0; ctx->n_positions = 0; ctx->n_items = 0; ctx->have_patch = false; ctx->tables_fetched = false;
   ctx->ref_start = 1; ctx->ref_n = 0; ctx->pileup_ms = ctx->score_ms = 0;
+  ctx->evs[0] = ctx->evs[1] = ctx->evs[2] = NULL; ctx->split_ms[0] = ctx->split_ms[1] = ctx->split_ms[2] = ctx->split_ms[3] = 0;
   ctx->reads_dev_view = NULL; ctx->pool_dev_view = NULL;
   *out = ctx;  // returned even on failure so the caller can read rv_last_error, then rv_destroy
   CK(cudaSetDevice(device));
@@ -1066,6 +1314,7 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   CK(cudaEventCreate(&ctx->ev1));
   CK(cudaEventCreate(&ctx->tev0));
   CK(cudaEventCreate(&ctx->tev1));
+  for (int k = 0; k < 3; ++k) CK(cudaEventCreate(&ctx->evs[k]));
   const rv_limits& L = ctx->L;
   CK(cudaMalloc(&ctx->d_reads, sizeof(rv_read) * (size_t)L.max_reads));
   CK(cudaMalloc(&ctx->d_pool, (size_t)L.max_read_bytes + 64));  // the gather kernel copies whole 16-byte chunks
@@ -1130,6 +1379,7 @@ void rv_destroy(rv_ctx* ctx) {
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->tev0) cudaEventDestroy(ctx->tev0);
   if (ctx->tev1) cudaEventDestroy(ctx->tev1);
+  for (int k = 0; k < 3; ++k) if (ctx->evs[k]) cudaEventDestroy(ctx->evs[k]);
   delete ctx;
 }
 
@@ -1285,6 +1535,7 @@ int rv_pileup(rv_ctx* ctx) {
     ctx->launches++;
     CK(cudaGetLastError());
   }
+  CK(cudaEventRecord(ctx->evs[0], ctx->stream));
   if (ctx->n_tiles > 0) {
     GatherArgs g;
     g.goodq = ctx->P.goodq;
@@ -1302,10 +1553,12 @@ int rv_pileup(rv_ctx* ctx) {
     g.tile_range = ctx->d_tile_range;
     g.n_tiles = ctx->n_tiles;
     rv_tile_index_kernel<<<(unsigned)((ctx->n_tiles + 127) / 128), 128, 0, ctx->stream>>>(g);
-    rv_gather_kernel<<<(unsigned)ctx->n_tiles, GATHER_TILE, 0, ctx->stream>>>(g);
+    if (ctx->gather_ws) rv_gather_ws_kernel<<<(unsigned)ctx->n_tiles, WS_THREADS, 0, ctx->stream>>>(g);
+    else rv_gather_kernel<<<(unsigned)ctx->n_tiles, GATHER_TILE, 0, ctx->stream>>>(g);
     ctx->launches += 2;
     CK(cudaGetLastError());
   }
+  CK(cudaEventRecord(ctx->evs[1], ctx->stream));
   if (ctx->n_items > 0) {
     // the queue length is only known on the device: a fixed grid of grid-stride threads
     rv_walk_kernel<<<148 * 8, 128, 0, ctx->stream>>>(a);
@@ -1317,6 +1570,9 @@ int rv_pileup(rv_ctx* ctx) {
   CK(cudaMemcpyAsync(ctx->h_max_rl, ctx->d_max_rl, sizeof(int32_t) * ctx->regions.size(), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaEventElapsedTime(&ctx->pileup_ms, ctx->ev0, ctx->ev1));
+  CK(cudaEventElapsedTime(&ctx->split_ms[0], ctx->ev0, ctx->evs[0]));
+  CK(cudaEventElapsedTime(&ctx->split_ms[1], ctx->evs[0], ctx->evs[1]));
+  CK(cudaEventElapsedTime(&ctx->split_ms[2], ctx->evs[1], ctx->ev1));
   ctx->h_stats.n_items = (unsigned long long)ctx->n_items;
   // the patch list stays attached until rv_set_regions / the next rv_apply_patch: a caller that
   // re-runs the same resident batch may score against it again
@@ -1603,6 +1859,14 @@ int rv_last_kernel_ms(rv_ctx* ctx, float* pileup_ms, float* score_ms) {
   if (!ctx) return RV_ERR_ARG;
   if (pileup_ms) *pileup_ms = ctx->pileup_ms;
   if (score_ms) *score_ms = ctx->score_ms;
+  return RV_OK;
+}
+
+int rv_last_pileup_split_ms(rv_ctx* ctx, float* classify_ms, float* gather_ms, float* walk_ms) {
+  if (!ctx) return RV_ERR_ARG;
+  if (classify_ms) *classify_ms = ctx->split_ms[0];
+  if (gather_ms) *gather_ms = ctx->split_ms[1];
+  if (walk_ms) *walk_ms = ctx->split_ms[2];
   return RV_OK;
 }
 
