@@ -11,6 +11,7 @@
 #include "batch_loader.hpp"
 #include <array>
 #include <map>
+#include <memory>
 #include <set>
 #include <string>
 #include <thread>
@@ -39,12 +40,29 @@ struct Variation {
   void sub_dir(bool d, int n) { if (d) rev -= n; else fwd -= n; }
 };
 
-struct Sclip : Variation {
+// Per-offset base histograms of a soft-clip cluster.  Built once by reduce_events_region and read-only afterwards,
+// so copies of a Sclip (the realigner works on copies of the region state) share them.
+struct SclipBases {
   std::map<int, std::map<char, int> > nt;
   std::map<int, std::map<char, Variation> > seq;
+};
+struct Sclip : Variation {
+  std::shared_ptr<SclipBases> bases;
   std::string sequence;
   bool used;
   Sclip() : used(false) {}
+  SclipBases& b() {
+    if (!bases) bases.reset(new SclipBases());
+    return *bases;
+  }
+  std::map<int, std::map<char, int> >& nt() { return b().nt; }
+  std::map<int, std::map<char, Variation> >& seq() { return b().seq; }
+  const SclipBases& cb() const {
+    static const SclipBases none;
+    return bases ? *bases : none;
+  }
+  const std::map<int, std::map<char, int> >& nt() const { return cb().nt; }
+  const std::map<int, std::map<char, Variation> >& seq() const { return cb().seq; }
 };
 
 typedef std::map<std::string, Variation> KeyMap;
@@ -170,8 +188,8 @@ inline void reduce_events_region(const rv_event* ev, int64_t n, const ReadBatch&
         for (int si = m - 1; m - si <= nhi; si--) {
           char ch = batch.base(e.read_idx, si);
           int idx = m - 1 - si;
-          s.nt[idx][ch]++;
-          add_cnt(s.seq[idx][ch], dir, si - (m - nhi), batch.qual(e.read_idx)[si], e.mapq, e.nm, goodq);
+          s.nt()[idx][ch]++;
+          add_cnt(s.seq()[idx][ch], dir, si - (m - nhi), batch.qual(e.read_idx)[si], e.mapq, e.nm, goodq);
         }
         add_cnt(s, dir, m, q, e.mapq, e.nm, goodq);
         break;
@@ -181,8 +199,8 @@ inline void reduce_events_region(const rv_event* ev, int64_t n, const ReadBatch&
         const int m = e.aux0, nhi = e.aux1, rp = e.aux2;
         for (int si = 0; si < nhi; si++) {
           char ch = batch.base(e.read_idx, rp + si);
-          s.nt[si][ch]++;
-          add_cnt(s.seq[si][ch], dir, nhi - si, batch.qual(e.read_idx)[rp + si], e.mapq, e.nm, goodq);
+          s.nt()[si][ch]++;
+          add_cnt(s.seq()[si][ch], dir, nhi - si, batch.qual(e.read_idx)[rp + si], e.mapq, e.nm, goodq);
         }
         add_cnt(s, dir, m, q, e.mapq, e.nm, goodq);
         break;

@@ -101,14 +101,52 @@ inline int host_handoff(rv_ctx* ctx, const rv_params& P, const ReadBatch& batch,
   std::vector<rv_patch_entry> all;
   std::vector<int32_t> creg, cpos, cval;
   std::vector<int> bad(regs.size(), 0);
-  parallel_for(regs.size(), host_threads(), [&](size_t r) {
-    rvk::RefView rv = refv;
-    rv.lo = regs[r].ref_lo;
-    rv.hi = regs[r].ref_hi;
-    realign_region(P, rp[r], rv, regs[r].chr_len);
-    if (rp[r].row_misses) bad[r] = 1;
-    build_patch(rp[r], &out->patches[r]);
-  });
+  // The realigner reads dense rows next to indels and soft clips that cannot be known in advance.  It runs on a
+  // copy of the region state; rows it touched without having them are fetched and the region is re-run from the
+  // pristine state (the stage is a pure function of its inputs) until a run completes without a miss.
+  {
+    std::vector<RegionPileup> work(regs.size());
+    std::vector<size_t> todo(regs.size());
+    for (size_t r = 0; r < regs.size(); ++r) todo[r] = r;
+    for (int iter = 0; !todo.empty(); ++iter) {
+      parallel_for(todo.size(), host_threads(), [&](size_t k) {
+        const size_t r = todo[k];
+        work[r] = rp[r];
+        rvk::RefView rv = refv;
+        rv.lo = regs[r].ref_lo;
+        rv.hi = regs[r].ref_hi;
+        realign_region(P, work[r], rv, regs[r].chr_len, NULL, &batch, regs[r].read_lo, regs[r].read_hi);
+      });
+      std::vector<int32_t> qreg, qpos;
+      std::vector<size_t> again;
+      for (size_t k = 0; k < todo.size(); ++k) {
+        const size_t r = todo[k];
+        if (!work[r].row_misses) continue;
+        again.push_back(r);
+        for (std::map<int, std::array<uint32_t, 33> >::const_iterator it = work[r].srows.begin(); it != work[r].srows.end(); ++it)
+          if (!rp[r].srows.count(it->first)) { qreg.push_back((int32_t)r); qpos.push_back(it->first); }
+      }
+      if (again.empty()) break;
+      if (iter >= 8) {
+        if (err) *err = "host stage did not converge on the set of dense rows it needs";
+        return RV_ERR_STATE;
+      }
+      const uint32_t* rows = NULL;
+      RV_STEP(rv_fetch_rows(ctx, qreg.data(), qpos.data(), (int64_t)qreg.size(), &rows));
+      for (size_t i = 0; i < qreg.size(); ++i) {
+        std::array<uint32_t, 33> a;
+        memcpy(a.data(), rows + i * 33, sizeof(uint32_t) * 33);
+        rp[(size_t)qreg[i]].srows[qpos[i]] = a;
+      }
+      t->d2h_bytes += (int64_t)qreg.size() * 33 * 4;
+      todo.swap(again);
+    }
+    parallel_for(regs.size(), host_threads(), [&](size_t r) {
+      rp[r] = work[r];
+      if (rp[r].row_misses) bad[r] = 1;
+      build_patch(rp[r], &out->patches[r]);
+    });
+  }
   for (size_t r = 0; r < regs.size(); ++r) {
     if (bad[r]) {
       if (err) *err = "host stage touched dense rows that were not fetched";

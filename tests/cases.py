@@ -25,9 +25,9 @@ def _bed(chrom, bed, extra=()):
 
 # name -> synthgen args, reference CLI args, rv_dump args (our side), which stages are expected to match
 CASES = {
-    # cfg 1: single sample, simple mode, SNVs + a few indels; default -k 1: CigarParser stage must be bit-exact
+    # cfg 1: single sample, simple mode, SNVs + a few indels; default -k 1 (CigarModifier + realignIndels): every stage exact
     "c1_k1": dict(gen=["--cfg", "1", "--len", "22600", "--depth", "100"], chrom="chrS1", region="1301-21300",
-                  ref_args=_simple("chrS1", "1301-21300"), dump_args=[], stages="CRV", exact_stages=["C."]),
+                  ref_args=_simple("chrS1", "1301-21300"), dump_args=[], stages="CRV", exact_stages=["C.", "R.", "V."]),
     # same data, -k 0: every stage (pileup, adjustMNP, scoring) must match
     "c1_k0": dict(gen=["--cfg", "1", "--len", "22600", "--depth", "100"], chrom="chrS1", region="1301-21300",
                   ref_args=_simple("chrS1", "1301-21300", ["-k", "0"]), dump_args=["--k", "0"], stages="CRV",
@@ -35,7 +35,7 @@ CASES = {
     # cfg 5: indel / soft-clip / MNV heavy with -3 -u
     "c5_k1": dict(gen=["--cfg", "5", "--len", "12600", "--depth", "100"], chrom="chrS5", region="1301-11300",
                   ref_args=_simple("chrS5", "1301-11300", ["-3", "-u"]), dump_args=["--three", "1", "--u", "1"],
-                  stages="CRV", exact_stages=["C."]),
+                  stages="CRV", exact_stages=["C.", "R.", "V."]),
     "c5_k0": dict(gen=["--cfg", "5", "--len", "12600", "--depth", "100"], chrom="chrS5", region="1301-11300",
                   ref_args=_simple("chrS5", "1301-11300", ["-3", "-u", "-k", "0"]),
                   dump_args=["--three", "1", "--u", "1", "--k", "0"], stages="CRV", exact_stages=["C.", "R.", "V."]),

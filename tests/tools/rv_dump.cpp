@@ -112,9 +112,9 @@ static void dump_tables(const char* stage, const RegionPileup& R) {
       fprintf(OUT, "%s.SC%d\t%d\t", stage, end, p.first);
       print_var_fields(p.second);
       fprintf(OUT, "\t%d\n", p.second.used ? 1 : 0);
-      for (auto& ie : p.second.nt)
+      for (auto& ie : p.second.nt())
         for (auto& bc : ie.second) fprintf(OUT, "%s.SCNT\t%d\t%d\t%d\t%c\t%d\n", stage, end, p.first, ie.first, bc.first, bc.second);
-      for (auto& ie : p.second.seq)
+      for (auto& ie : p.second.seq())
         for (auto& bc : ie.second) {
           fprintf(OUT, "%s.SCSEQ\t%d\t%d\t%d\t%c\t", stage, end, p.first, ie.first, bc.first);
           print_var_fields(bc.second);
@@ -312,7 +312,7 @@ int main(int argc, char** argv) {
     }
     refv.lo = regs[r].ref_lo;
     refv.hi = regs[r].ref_hi;
-    realign_region(P, rp[r], refv, regs[r].chr_len);
+    realign_region(P, rp[r], refv, regs[r].chr_len, NULL, &batch, regs[r].read_lo, regs[r].read_hi);
     if (stages.find('R') != std::string::npos) {
       fprintf(OUT, "R.MAXRL\t%d\n", rp[r].max_read_len);
       dump_tables("R", rp[r]);
