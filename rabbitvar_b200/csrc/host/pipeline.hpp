@@ -73,6 +73,14 @@ inline int host_handoff(rv_ctx* ctx, const rv_params& P, const ReadBatch& batch,
       int lo = 0, hi = -1;
       if (e.kind == RV_EV_NI && (e.flags & RV_EVF_MNP)) { lo = e.pos - 1; hi = e.pos + e.keylen + 1; }
       else if (e.kind == RV_EV_TTREF) { lo = hi = e.pos; }
+      else if (P.local_realign && e.kind == RV_EV_NI && (e.flags & RV_EVF_PDEL)) {
+        // realigndel looks at the reference allele under the deletion and at mismatches right next to it
+        // (a first guess: whatever else it touches is fetched by the re-run loop below)
+        int dellen = 0;
+        for (int k = 1; k < e.keylen && e.key[k] >= '0' && e.key[k] <= '9'; ++k) dellen = dellen * 10 + (e.key[k] - '0');
+        lo = e.pos - 3;
+        hi = e.pos + dellen + 4;
+      } else if (P.local_realign && e.kind == RV_EV_IN) { lo = e.pos - 3; hi = e.pos + 5; }
       for (int p = lo; p <= hi; ++p)
         if (seen.insert(std::make_pair(e.region, p)).second) { qreg.push_back(e.region); qpos.push_back(p); }
     }
