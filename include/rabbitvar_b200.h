@@ -230,6 +230,11 @@ int rv_pileup(rv_ctx* ctx);
 /* Per-position scoring + compaction of candidate variants (ToVarsBuilder::process). */
 int rv_score(rv_ctx* ctx);
 
+/* The same scoring for an explicit list of (region, position) pairs only, without the frequency / candidate cuts
+ * of the per-sample passes deciding which positions to visit (somatic mode joins the tumor and normal records of
+ * the positions where either sample has a candidate: somaticMode.cpp:311-352). */
+int rv_score_positions(rv_ctx* ctx, const int32_t* region, const int32_t* pos, int64_t n);
+
 /* ---- outputs --------------------------------------------------------------------------------- */
 typedef struct rv_pileup_stats {
   int64_t n_items;          /* (region, read) pairs examined */

@@ -111,7 +111,7 @@ class Timing(C.Structure):
 ABI_SYMBOLS = [
     "rv_abi_version", "rv_device_count", "rv_default_params", "rv_default_limits", "rv_create", "rv_destroy",
     "rv_last_error", "rv_sync", "rv_ctx_halo", "rv_set_params", "rv_set_reference", "rv_push_reads", "rv_push_reads_range", "rv_push_reads_device", "rv_set_regions",
-    "rv_pileup", "rv_score", "rv_get_pileup_stats", "rv_fetch_max_read_len", "rv_fetch_tables", "rv_fetch_rows",
+    "rv_pileup", "rv_score", "rv_score_positions", "rv_get_pileup_stats", "rv_fetch_max_read_len", "rv_fetch_tables", "rv_fetch_rows",
     "rv_fetch_events",
     "rv_apply_patch", "rv_fetch_variants", "rv_variant_count", "rv_fisher_exact", "rv_last_kernel_ms", "rv_last_pileup_split_ms", "rv_timer_start",
     "rv_timer_stop", "rv_launch_count",
@@ -150,6 +150,7 @@ def _declare(L):
     L.rv_set_regions.argtypes = [vp, C.POINTER(Region), i32]
     L.rv_pileup.argtypes = [vp]
     L.rv_score.argtypes = [vp]
+    L.rv_score_positions.argtypes = [vp, vp, vp, i64]
     L.rv_get_pileup_stats.argtypes = [vp, C.POINTER(PileupStats)]
     L.rv_fetch_max_read_len.argtypes = [vp, C.POINTER(C.POINTER(i32)), C.POINTER(i32)]
     L.rv_fetch_tables.argtypes = [vp, i32, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_uint32)),

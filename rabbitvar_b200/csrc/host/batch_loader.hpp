@@ -77,6 +77,21 @@ inline bool load_span(rvio::BamReader& rd, const rvio::BaiIndex& bai, int tid, i
   return true;
 }
 
+// Concatenates b onto a (the reads of a second sample); returns the read-index offset of b's reads inside a.
+inline int64_t append_batch(ReadBatch& a, const ReadBatch& b) {
+  const int64_t off = (int64_t)a.reads.size();
+  const size_t pool_off = (a.pool.size() + 15) & ~(size_t)15;
+  a.pool.resize(pool_off);
+  a.pool.insert(a.pool.end(), b.pool.begin(), b.pool.end());
+  for (size_t i = 0; i < b.reads.size(); ++i) {
+    rv_read r = b.reads[i];
+    r.data_off16 += (uint32_t)(pool_off / 16);
+    a.reads.push_back(r);
+  }
+  if (b.max_ref_span > a.max_ref_span) a.max_ref_span = b.max_ref_span;
+  return off;
+}
+
 // Fills rv_region entries for regions (all on one contig, any order) against a loaded batch.
 // ref window = [max(1, start - x - Y), min(len, end + x + Y) - 17]  (recordPreprocessor.cpp:42-55,
 // CONF_SEED_1 = 17); here x (numberNucleotideToExtend) is already applied to the region by the caller.

@@ -7,8 +7,8 @@
 // host concatenates the TSV blocks in region order (replaces the `omp critical` write, simpleMode.cpp:339).
 // No collective sits on the path.
 //
-// Supported: simple mode (-b one BAM), -R or -i BED with -c/-S/-E/-g, the scoring/filter flags below.
-// Somatic pairing (-b 'T|N') output formatting is the next row of SURVEY.md §8(f) and is refused here.
+// Supported: simple mode (-b one BAM) and paired somatic mode (-b 'tumor.bam|normal.bam', somaticMode.cpp), -R or
+// -i BED with -c/-S/-E/-g, the scoring/filter flags below.
 #include "../../../include/rabbitvar_b200.h"
 #include "pipeline.hpp"
 #include <thread>
@@ -20,7 +20,7 @@
 using namespace rvhost;
 
 struct Cli {
-  std::string fasta, bam, region, bed, out = "./out.txt", sample, delim = "\t";
+  std::string fasta, bam, bam2, region, bed, out = "./out.txt", sample, delim = "\t";
   int c_col = 2, S_col = 6, E_col = 7, g_col = 12;  // DEFAULT_BED_ROW_FORMAT (Launcher.cpp:21), 0-based after -1
   bool c_set = false, S_set = false, E_set = false, g_set = false, zero_based = false;
   int nucl_ext = 0, ref_ext = 1200, gpus = 1, threads = 1, batch_regions = 256;
@@ -96,9 +96,15 @@ static bool parse(int argc, char** argv, Cli& c) {
   if (c.P.pileup) { c.P.freq = -1; c.P.minr = 0; }  // Launcher.cpp:455-459
   c.P.candidates_only = c.P.pileup ? 0 : 1;         // simple-mode output prints only passing variants
   if (c.fasta.empty() || c.bam.empty()) { usage(); return false; }
-  if (c.bam.find('|') != std::string::npos) {
-    fprintf(stderr, "rabbitvar_b200: somatic pairing (-b 'T|N') is not wired into this front end yet\n");
-    return false;
+  size_t bar = c.bam.find('|');
+  if (bar != std::string::npos) {  // BamNames, Configuration.h: "bam1|bam2" selects the somatic mode
+    c.bam2 = c.bam.substr(bar + 1);
+    c.bam = c.bam.substr(0, bar);
+    if (c.bam.empty() || c.bam2.empty()) { usage(); return false; }
+    // getSampleNamesSomatic (Launcher.cpp:250-279) is only used together with -R (Launcher.cpp:46-50): it prints
+    // the first of the "T|N" names; with a BED file the -N string is printed as given
+    size_t sb = c.sample.find('|');
+    if (sb != std::string::npos && !c.region.empty()) c.sample = c.sample.substr(0, sb);
   }
   return true;
 }
@@ -181,6 +187,13 @@ static void worker(const Cli& c, int device, std::vector<Block*> blocks) {
     for (Block* b : blocks) b->err = "cannot open BAM/BAI/FASTA";
     return;
   }
+  const bool somatic = !c.bam2.empty();
+  rvio::BamReader bamN;
+  rvio::BaiIndex baiN;
+  if (somatic && (!bamN.open(c.bam2) || !baiN.load(c.bam2 + ".bai"))) {
+    for (Block* b : blocks) b->err = "cannot open the second BAM/BAI";
+    return;
+  }
   rv_ctx* ctx = NULL;
   rv_limits L;
   rv_default_limits(&L);
@@ -197,6 +210,16 @@ static void worker(const Cli& c, int device, std::vector<Block*> blocks) {
       load_span(bam, bai, tid, smin, smax, &batch);
       std::vector<rv_region> regs;
       make_regions(batch, blk->specs, chr_len, c.ref_ext, c.nucl_ext, &regs);
+      if (somatic) {  // the same tiles of the normal sample follow the tumor's (one_region_run_somt)
+        int tidN = bamN.header().tid_of(chr);
+        if (tidN < 0) { blk->err = "contig not in the second BAM: " + chr; continue; }
+        ReadBatch batchN;
+        load_span(bamN, baiN, tidN, smin, smax, &batchN);
+        std::vector<rv_region> regsN;
+        make_regions(batchN, blk->specs, chr_len, c.ref_ext, c.nucl_ext, &regsN);
+        const int64_t off = append_batch(batch, batchN);
+        for (auto& r : regsN) { r.read_lo += off; r.read_hi += off; regs.push_back(r); }
+      }
       int32_t ref_lo = std::max(1, smin - c.ref_ext - c.nucl_ext - 100);
       int32_t ref_hi = std::min(chr_len, smax + c.ref_ext + c.nucl_ext + 100);
       std::string refseq;
@@ -214,9 +237,9 @@ static void worker(const Cli& c, int device, std::vector<Block*> blocks) {
         L.max_reads = cap_reads;
         L.max_read_bytes = cap_bytes;
         L.max_positions = cap_pos;
-        L.max_regions = (int32_t)std::max<size_t>(regs.size(), (size_t)c.batch_regions) + 1;
+        L.max_regions = (int32_t)std::max<size_t>(regs.size(), (size_t)c.batch_regions * (somatic ? 2 : 1)) + 1;
         L.max_events = std::max<int64_t>(1 << 16, cap_reads * 4);
-        L.max_variants = cap_pos + 1024;
+        L.max_variants = (somatic ? 3 : 1) * cap_pos + 1024;
         L.max_patch = std::max<int64_t>(1 << 16, cap_reads);
         L.max_ref_bases = cap_ref;
         int rc = rv_create(&ctx, device, &c.P, &L);
@@ -230,7 +253,8 @@ static void worker(const Cli& c, int device, std::vector<Block*> blocks) {
       std::vector<std::string> genes;
       for (auto& s : blk->specs) genes.push_back(s.gene);
       BatchTiming tm;
-      int rc = run_batch_simple(ctx, c.P, batch, regs, genes, refseq, ref_lo, c.sample, chr, 3, L.halo, &blk->tsv, &tm, &blk->err);
+      int rc = somatic ? run_batch_somatic(ctx, c.P, batch, regs, genes, refseq, ref_lo, c.sample, chr, 3, L.halo, &blk->tsv, &tm, &blk->err)
+                       : run_batch_simple(ctx, c.P, batch, regs, genes, refseq, ref_lo, c.sample, chr, 3, L.halo, &blk->tsv, &tm, &blk->err);
       if (rc != RV_OK) continue;
       blk->bases = tm.stats.n_aligned_bases;
       blk->reads = tm.stats.n_reads_kept;

@@ -10,6 +10,7 @@
 #include "pileup_model.hpp"
 #include "realign.hpp"
 #include "assemble.hpp"
+#include "somatic.hpp"
 #include <chrono>
 
 namespace rvhost {
@@ -34,7 +35,7 @@ struct Handoff {
 // write-back of the result as the patch list (rv_apply_patch).
 inline int host_handoff(rv_ctx* ctx, const rv_params& P, const ReadBatch& batch, const std::vector<rv_region>& regs,
                         const std::string& refseq, int32_t ref_lo, int halo, Handoff* out, BatchTiming* t,
-                        std::string* err) {
+                        std::string* err, const std::vector<int>* pair_of = NULL) {
   int rc;
 #define RV_STEP(x)                                                  \
   do {                                                              \
@@ -62,6 +63,8 @@ inline int host_handoff(rv_ctx* ctx, const rv_params& P, const ReadBatch& batch,
     R.n_pos = regs[r].end - regs[r].start + 1 + 2 * halo;
     R.dense = false;
     R.max_read_len = mrl[r];
+    // somatic mode: the normal pass starts from the tumor's maxReadLength (somaticMode.cpp:109)
+    if (pair_of && (*pair_of)[r] >= 0 && mrl[(*pair_of)[r]] > R.max_read_len) R.max_read_len = mrl[(*pair_of)[r]];
   }
   // dense rows the host stage will look at: around multi-nucleotide keys (adjustMNP reads the single-base
   // keys left/right of an MNV, VariationRealigner.cpp:357-399) and under TTREF observations
@@ -266,6 +269,137 @@ inline int run_batch_simple(rv_ctx* ctx, const rv_params& P, const ReadBatch& ba
     }
   });
   for (size_t r = 0; r < regs.size(); ++r) {
+    tsv->append(rtsv[r]);
+    t.n_lines += rlines[r];
+  }
+  double t7 = now_ms();
+  t.push_ms = t1 - t0; t.pileup_ms = t2 - t1;
+  t.score_ms = t6 - t5; t.assemble_ms = t7 - t6;
+  t.n_variants = nv;
+  rv_last_kernel_ms(ctx, &t.pileup_kernel_ms, &t.score_kernel_ms);
+  if (tm) *tm = t;
+#undef RV_STEP
+  return RV_OK;
+}
+
+// Paired (tumor | normal) form of run_batch_simple: regs = the n tumor tiles followed by the same n tiles of the
+// normal sample (one_region_run_somt + SomaticMode::output, somaticMode.cpp:83-127, :311-352).  Both samples
+// are piled in one launch; scoring runs twice: once per sample with the device-side candidate cut to find the
+// positions where either sample has something to print, then in full at exactly those positions of both samples.
+inline int run_batch_somatic(rv_ctx* ctx, const rv_params& P_in, const ReadBatch& batch, const std::vector<rv_region>& regs,
+                             const std::vector<std::string>& genes, const std::string& refseq, int32_t ref_lo,
+                             const std::string& sample, const std::string& chr, int push_flags, int halo,
+                             std::string* tsv, BatchTiming* tm, std::string* err) {
+  BatchTiming t;
+  memset(&t, 0, sizeof t);
+  int rc;
+#define RV_STEP(x)                                                  \
+  do {                                                              \
+    rc = (x);                                                       \
+    if (rc != RV_OK) {                                              \
+      if (err) *err = std::string(#x) + ": " + rv_last_error(ctx);  \
+      return rc;                                                    \
+    }                                                               \
+  } while (0)
+  if (regs.size() % 2) { if (err) *err = "somatic batch needs tumor and normal regions in pairs"; return RV_ERR_ARG; }
+  const size_t n = regs.size() / 2;
+  rv_params P = P_in;
+  P.has_bam2 = 1;
+  double t0 = now_ms();
+  if (push_flags & 1) RV_STEP(rv_set_reference(ctx, ref_lo, (int64_t)refseq.size(), refseq.data()));
+  if (push_flags & 2) {
+    rv_read_batch bv = batch.view();
+    RV_STEP(rv_push_reads(ctx, &bv));
+    t.h2d_bytes += (int64_t)batch.reads.size() * (int64_t)sizeof(rv_read) + (int64_t)batch.pool.size();
+  }
+  RV_STEP(rv_set_params(ctx, &P));
+  RV_STEP(rv_set_regions(ctx, regs.data(), (int32_t)regs.size()));
+  double t1 = now_ms();
+  RV_STEP(rv_pileup(ctx));
+  RV_STEP(rv_get_pileup_stats(ctx, &t.stats));
+  double t2 = now_ms();
+  std::vector<int> pair_of(regs.size(), -1);
+  for (size_t r = n; r < regs.size(); ++r) pair_of[r] = (int)(r - n);
+  Handoff ho;
+  rc = host_handoff(ctx, P, batch, regs, refseq, ref_lo, halo, &ho, &t, err, &pair_of);
+  if (rc != RV_OK) return rc;
+  double t5 = now_ms();
+  // ---- pass A: candidate positions of either sample ----
+  rv_params PA = P;
+  PA.candidates_only = 1;
+  RV_STEP(rv_set_params(ctx, &PA));
+  RV_STEP(rv_score(ctx));
+  const rv_variant* vv;
+  int64_t nv;
+  RV_STEP(rv_fetch_variants(ctx, &vv, &nv));
+  t.d2h_bytes += nv * (int64_t)sizeof(rv_variant);
+  std::vector<std::set<int> > cand(n);
+  for (int64_t i = 0; i < nv; ++i) cand[(size_t)vv[i].region % n].insert(vv[i].pos);
+  std::vector<int32_t> qreg, qpos;
+  for (size_t i = 0; i < n; ++i)
+    for (std::set<int>::const_iterator p = cand[i].begin(); p != cand[i].end(); ++p) {
+      qreg.push_back((int32_t)i); qpos.push_back(*p);
+      qreg.push_back((int32_t)(i + n)); qpos.push_back(*p);
+    }
+  // ---- pass B: full records of both samples at those positions ----
+  rv_params PB = P;
+  PB.candidates_only = 0;
+  RV_STEP(rv_set_params(ctx, &PB));
+  RV_STEP(rv_score_positions(ctx, qreg.data(), qpos.data(), (int64_t)qreg.size()));
+  RV_STEP(rv_fetch_variants(ctx, &vv, &nv));
+  t.d2h_bytes += nv * (int64_t)sizeof(rv_variant);
+  t.h2d_bytes += (int64_t)qreg.size() * 8;
+  RV_STEP(rv_set_params(ctx, &P_in));
+  double t6 = now_ms();
+  std::vector<int64_t> rfirst(regs.size() + 1, nv);
+  {
+    int64_t i = 0;
+    for (size_t r = 0; r < regs.size(); ++r) {
+      while (i < nv && vv[i].region < (int)r) ++i;
+      rfirst[r] = i;
+    }
+  }
+  rvk::RefView refv;
+  refv.bases = refseq.data();
+  refv.base_pos = ref_lo;
+  refv.n = (int64_t)refseq.size();
+  std::vector<std::string> rtsv(n);
+  std::vector<int64_t> rlines(n, 0);
+  parallel_for(n, host_threads(), [&](size_t r) {
+    rvk::RefView rv = refv;
+    rv.lo = regs[r].ref_lo;
+    rv.hi = regs[r].ref_hi;
+    // the normal sample's positions of this tile
+    std::map<int, PositionVars> normal;
+    std::vector<rv_variant> group;
+    const size_t rn = r + n;
+    for (int64_t i = rfirst[rn]; i < rfirst[rn + 1];) {
+      int64_t j = i;
+      while (j < rfirst[rn + 1] && vv[j].pos == vv[i].pos) ++j;
+      group.assign(vv + i, vv + j);
+      for (size_t k = 0; k < group.size(); ++k)
+        if (group[k].key_kind == 1) group[k].key_id -= (int32_t)ho.bases[rn];
+      assemble_position(P, group.data(), (int)group.size(), ho.patches[rn], rv, regs[rn].chr_len, &normal[vv[i].pos]);
+      i = j;
+    }
+    std::string& out_s = rtsv[r];
+    for (int64_t i = rfirst[r]; i < rfirst[r + 1];) {
+      int64_t j = i;
+      while (j < rfirst[r + 1] && vv[j].pos == vv[i].pos) ++j;
+      group.assign(vv + i, vv + j);
+      for (size_t k = 0; k < group.size(); ++k)
+        if (group[k].key_kind == 1) group[k].key_id -= (int32_t)ho.bases[r];
+      PositionVars pv;
+      assemble_position(P, group.data(), (int)group.size(), ho.patches[r], rv, regs[r].chr_len, &pv);
+      std::map<int, PositionVars>::iterator nit = normal.find(pv.pos);
+      size_t before = out_s.size();
+      output_position_somatic(P, pv, nit == normal.end() ? (PositionVars*)NULL : &nit->second, sample, genes[r], chr,
+                              regs[r].start, regs[r].end, &out_s);
+      for (size_t k = before; k < out_s.size(); ++k) rlines[r] += out_s[k] == '\n';
+      i = j;
+    }
+  });
+  for (size_t r = 0; r < n; ++r) {
     tsv->append(rtsv[r]);
     t.n_lines += rlines[r];
   }

@@ -1105,6 +1105,38 @@ __global__ void __launch_bounds__(128) rv_score_patched_kernel(ScoreArgs a) {
   }
 }
 
+// The general score_position for an explicit list of table positions (somatic mode: full records of both
+// samples at the positions where either sample has a candidate).
+__global__ void __launch_bounds__(128) rv_score_list_kernel(ScoreArgs a, const int64_t* list, int64_t n) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = list[q];
+    if (t < 0) continue;
+    const int ri = find_region_by_tab(a.regions, a.n_regions, t);
+    const DevRegion* dr = a.regions + ri;
+    const int i = (int)(t - dr->tab_off);
+    const int pos = dr->first_pos + i;
+    const uint32_t* rows = a.counts + (size_t)t * RV_POS_U32;
+    const uint32_t pf = a.patch_first ? a.patch_first[t] : 0u;
+    const int pn = pf ? (int)a.patch_count[t] : 0;
+    RefView ref;
+    ref.bases = a.ref;
+    ref.base_pos = a.ref_start;
+    ref.n = a.ref_n;
+    ref.lo = dr->r.ref_lo;
+    ref.hi = dr->r.ref_hi;
+    const bool has_next = i + 1 < dr->n_pos;
+    LgTable L;
+    L.t = a.lgt;
+    L.n = a.lgt_n;
+    DeviceEmit em;
+    em.a = &a;
+    int unsup = 0;
+    score_position(a.P, dr->r, ri, pos, ref, rows, a.cov[t], has_next, rows + RV_POS_U32, has_next ? a.cov[t + 1] : 0u,
+                   a.patch, pf ? (int)(pf - 1) : 0, pn, L, em, &unsup);
+    if (unsup) atomicAdd(&a.stats->n_score_unsupported, (unsigned long long)unsup);
+  }
+}
+
 __global__ void rv_lgamma_table_kernel(double* t, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) t[i] = lgamma((double)i + 1.0);
@@ -1760,13 +1792,7 @@ int rv_apply_patch(rv_ctx* ctx, const rv_patch_entry* entries, int64_t n_entries
   return RV_OK;
 }
 
-int rv_score(rv_ctx* ctx) {
-  if (!ctx) return RV_ERR_ARG;
-  if (ctx->regions.empty()) return fail(ctx, RV_ERR_STATE, "rv_set_regions has not been called");
-  CK(cudaSetDevice(ctx->device));
-  CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  CK(cudaMemsetAsync(&ctx->d_stats->n_variants, 0, 2 * sizeof(unsigned long long), ctx->stream));
-  ScoreArgs a;
+static void fill_score_args(rv_ctx* ctx, ScoreArgs& a) {
   a.P = ctx->P;
   a.regions = ctx->d_regions;
   a.n_regions = (int)ctx->regions.size();
@@ -1786,6 +1812,16 @@ int rv_score(rv_ctx* ctx) {
   a.stats = ctx->d_stats;
   a.patched_queue = ctx->d_patched_queue;
   a.patched_count = ctx->d_patched_count;
+}
+
+int rv_score(rv_ctx* ctx) {
+  if (!ctx) return RV_ERR_ARG;
+  if (ctx->regions.empty()) return fail(ctx, RV_ERR_STATE, "rv_set_regions has not been called");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  CK(cudaMemsetAsync(&ctx->d_stats->n_variants, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  ScoreArgs a;
+  fill_score_args(ctx, a);
   if (ctx->n_positions > 0) {
     CK(cudaMemsetAsync(ctx->d_patched_count, 0, sizeof(unsigned long long), ctx->stream));
     unsigned grid = (unsigned)((ctx->n_positions + SCORE_BLOCK - 1) / SCORE_BLOCK);
@@ -1801,6 +1837,41 @@ int rv_score(rv_ctx* ctx) {
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   CK(cudaMemcpyAsync(&ctx->h_stats.n_variants, &ctx->d_stats->n_variants, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaEventElapsedTime(&ctx->score_ms, ctx->ev0, ctx->ev1));
+  if (ctx->h_stats.n_variants > (unsigned long long)ctx->L.max_variants)
+    return fail(ctx, RV_ERR_OVERFLOW, "more variants than limits.max_variants");
+  return RV_OK;
+}
+
+int rv_score_positions(rv_ctx* ctx, const int32_t* region, const int32_t* pos, int64_t n) {
+  if (!ctx || n < 0 || (n && (!region || !pos))) return RV_ERR_ARG;
+  if (ctx->regions.empty()) return fail(ctx, RV_ERR_STATE, "rv_set_regions has not been called");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<int64_t> tab((size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    const int r = region[i];
+    if (r < 0 || r >= (int)ctx->regions.size()) return fail(ctx, RV_ERR_ARG, "rv_score_positions: bad region");
+    const DevRegion& d = ctx->regions[(size_t)r];
+    const int idx = pos[i] - d.first_pos;
+    tab[(size_t)i] = (pos[i] >= d.r.start && pos[i] <= d.r.end && idx >= 0 && idx < d.n_pos) ? d.tab_off + idx : -1;
+  }
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  CK(cudaMemsetAsync(&ctx->d_stats->n_variants, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  if (n) {
+    int rcs = ensure_scratch(ctx, 8 * (size_t)n + 64);
+    if (rcs != RV_OK) return rcs;
+    int64_t* d_list = (int64_t*)ctx->d_scratch;
+    CK(cudaMemcpyAsync(d_list, tab.data(), 8 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    ScoreArgs a;
+    fill_score_args(ctx, a);
+    unsigned grid = (unsigned)std::min<int64_t>((n + 127) / 128, 148 * 8);
+    rv_score_list_kernel<<<grid, 128, 0, ctx->stream>>>(a, d_list, n);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaMemcpyAsync(&ctx->h_stats.n_variants, &ctx->d_stats->n_variants, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));  // also keeps `tab` alive until the copy has been consumed
   CK(cudaEventElapsedTime(&ctx->score_ms, ctx->ev0, ctx->ev1));
   if (ctx->h_stats.n_variants > (unsigned long long)ctx->L.max_variants)
     return fail(ctx, RV_ERR_OVERFLOW, "more variants than limits.max_variants");

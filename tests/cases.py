@@ -54,6 +54,28 @@ CASES = {
 }
 
 
+def _somatic(chrom, region=None, bed=None, extra=()):
+    def f(d):
+        a = ["-G", os.path.join(d, "ref.fa"), "-b", os.path.join(d, "T.bam") + "|" + os.path.join(d, "N.bam"), "-N", "T|N",
+             "-f", "0.01", "--fisher"]
+        if region:
+            a += ["-R", f"{chrom}:{region}"]
+        else:
+            a += ["-i", os.path.join(d, bed), "-c", "1", "-S", "2", "-E", "3", "-g", "4"]
+        return a + list(extra)
+    return f
+
+
+# paired tumor | normal cases (BASELINE.json configs[1]): only the CLI's TSV is compared (the stage dumps of
+# oracle/ref_dump cover one sample at a time and are exercised by the cases above)
+SOMATIC_CASES = {
+    "c2_somatic_k1": dict(gen=["--cfg", "2", "--len", "22600", "--depth", "120", "--depth-n", "60"], chrom="chrS2",
+                          ref_args=_somatic("chrS2", region="1301-21300")),
+    "c2_somatic_bed_k0": dict(gen=["--cfg", "2", "--len", "32600", "--depth", "80", "--depth-n", "50", "--seed", "31"],
+                              chrom="chrS2", ref_args=_somatic("chrS2", bed="tiles.bed", extra=["-k", "0"])),
+}
+
+
 def dataset_dir(name):
     return os.path.join(WORK, name)
 
@@ -63,8 +85,8 @@ def generate(name):
     marker = os.path.join(d, "meta.txt")
     if not os.path.exists(marker):
         os.makedirs(d, exist_ok=True)
-        subprocess.run([os.path.join(BUILD, "synthgen")] + CASES[name]["gen"] + ["--out", d], check=True,
-                       stderr=subprocess.DEVNULL)
+        gen = (CASES.get(name) or SOMATIC_CASES[name])["gen"]
+        subprocess.run([os.path.join(BUILD, "synthgen")] + gen + ["--out", d], check=True, stderr=subprocess.DEVNULL)
     return d
 
 

@@ -15,7 +15,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from cases import CASES, dataset_dir, generate  # noqa: E402
+from cases import CASES, SOMATIC_CASES, dataset_dir, generate  # noqa: E402
 
 
 def main():
@@ -37,6 +37,15 @@ def main():
             g.write("\n".join(lines) + "\n")
         print(name, os.path.getsize(os.path.join(ROOT, "tests", "golden", name + ".dump.txt.gz")), "bytes dump,",
               len(lines), "tsv lines")
+    for name, case in SOMATIC_CASES.items():  # paired mode: the reference binary's TSV only
+        d = generate(name)
+        tsv = os.path.join(d, "ref.tsv")
+        subprocess.run([ref_bin] + case["ref_args"](d) + ["--out", tsv], check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL)
+        lines = sorted(open(tsv).read().splitlines())
+        with gzip.open(os.path.join(ROOT, "tests", "golden", name + ".tsv.gz"), "wt") as g:
+            g.write("\n".join(lines) + "\n")
+        print(name, len(lines), "tsv lines")
 
 
 if __name__ == "__main__":

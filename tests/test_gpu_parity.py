@@ -69,6 +69,22 @@ def test_cli_tsv_matches_reference_output(built, name, tmp_path):
     assert not bad, bad[:3]
 
 
+@pytest.mark.parametrize("name", sorted(cases.SOMATIC_CASES))
+def test_cli_somatic_tsv_matches_reference_output(built, name, tmp_path):
+    """Paired tumor | normal mode (BASELINE.json configs[1]) end to end through the drop-in CLI: the per-position
+    join of the two samples, the classification labels and the 63-column lines of the reference binary."""
+    c = cases.SOMATIC_CASES[name]
+    d = cases.generate(name)
+    out = str(tmp_path / "out.tsv")
+    run([os.path.join(ROOT, "build", "rabbitvar_b200")] + c["ref_args"](d) + ["--out", out])
+    got = _tsv_lines(open(out).read())
+    with gzip.open(golden_path(name, "tsv"), "rt") as f:
+        want = _tsv_lines(f.read())
+    assert len(got) == len(want), (len(got), len(want))
+    bad = [(w, g) for w, g in zip(want, got) if w != g and not _tsv_equal(w, g)]
+    assert not bad, bad[:3]
+
+
 def test_tiled_bed_equals_per_tile_runs(built, tmp_path):
     """A tile is the parity unit: running N tiles in one batch must equal running them one at a time."""
     import rabbitvar_b200 as rv
