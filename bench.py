@@ -160,8 +160,8 @@ def run_reference_arm(args):
     if not os.path.exists(binp):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/RabbitVar was not built/shipped"}))
         return
-    work = os.path.join(ROOT, "_work", "bench_ref")
     n_tiles = args.ref_tiles
+    work = os.path.join(ROOT, "_work", f"bench_ref_{n_tiles}")
     length = 1300 + n_tiles * TILE + 1300
     make_dataset(work, length, level=1)
     bed = sample_bed(work, n_tiles)

@@ -218,6 +218,10 @@ int rv_push_reads(rv_ctx* ctx, const rv_read_batch* batch);
  * batch-global read indices and must lie inside the staged range; events report batch-global read indices.
  * Lets several contexts work through one large host batch chunk by chunk. */
 int rv_push_reads_range(rv_ctx* ctx, const rv_read_batch* batch, int64_t read_lo, int64_t read_hi);
+/* Several disjoint ranges at once (paired mode: the tumor tiles' reads and the normal tiles' reads of one chunk);
+ * every region must lie inside one of them. */
+int rv_push_reads_ranges(rv_ctx* ctx, const rv_read_batch* batch, int32_t n_ranges, const int64_t* read_lo,
+                         const int64_t* read_hi);
 /* Same, from buffers already resident on the device (all pointers are device pointers; 16-byte aligned pool). */
 int rv_push_reads_device(rv_ctx* ctx, const rv_read_batch* batch);
 /* Regions of this batch. */

@@ -64,6 +64,13 @@ void rvh_pipeline_destroy(rvh_pipeline* p);
 int rvh_pipeline_run(rvh_pipeline* p, const rv_params* params, const rvh_batch* batch, const rv_region* regions,
                      int32_t n_regions, int32_t chunk_regions, const char* ref_bases, int32_t ref_lo, int64_t ref_n,
                      const char* sample, const char* chr, const char** tsv_out, int64_t* tsv_len, rvh_timing* timing);
+/* Paired tumor | normal form (one_region_run_somt + SomaticMode::output, somaticMode.cpp:83-127, :311-352):
+ * `regions` = the n tumor tiles followed by the same n tiles of the normal sample (n_regions = 2n), both referring to
+ * reads of one concatenated batch (rvh_batch_append); a chunk takes chunk_tiles tiles of both samples.  Output = the
+ * 55/63-column lines of the reference's somatic mode. */
+int rvh_pipeline_run_paired(rvh_pipeline* p, const rv_params* params, const rvh_batch* batch, const rv_region* regions,
+                            int32_t n_regions, int32_t chunk_tiles, const char* ref_bases, int32_t ref_lo, int64_t ref_n,
+                            const char* sample, const char* chr, const char** tsv_out, int64_t* tsv_len, rvh_timing* timing);
 /* Kernels launched by the pipeline's contexts so far. */
 int64_t rvh_pipeline_launch_count(const rvh_pipeline* p);
 const char* rvh_last_error(void);

@@ -110,7 +110,7 @@ class Timing(C.Structure):
 # every symbol include/*.h declares (checked by tests without a GPU)
 ABI_SYMBOLS = [
     "rv_abi_version", "rv_device_count", "rv_default_params", "rv_default_limits", "rv_create", "rv_destroy",
-    "rv_last_error", "rv_sync", "rv_ctx_halo", "rv_set_params", "rv_set_reference", "rv_push_reads", "rv_push_reads_range", "rv_push_reads_device", "rv_set_regions",
+    "rv_last_error", "rv_sync", "rv_ctx_halo", "rv_set_params", "rv_set_reference", "rv_push_reads", "rv_push_reads_range", "rv_push_reads_ranges", "rv_push_reads_device", "rv_set_regions",
     "rv_pileup", "rv_score", "rv_score_positions", "rv_get_pileup_stats", "rv_fetch_max_read_len", "rv_fetch_tables", "rv_fetch_rows",
     "rv_fetch_events",
     "rv_apply_patch", "rv_fetch_variants", "rv_variant_count", "rv_fisher_exact", "rv_last_kernel_ms", "rv_last_pileup_split_ms", "rv_timer_start",
@@ -118,7 +118,7 @@ ABI_SYMBOLS = [
     "rvh_load_bam", "rvh_batch_append", "rvh_batch_n_reads", "rvh_batch_reads", "rvh_batch_pool",
     "rvh_batch_pool_bytes", "rvh_batch_max_ref_span", "rvh_batch_pin", "rvh_batch_free", "rvh_make_regions", "rvh_fetch_ref",
     "rvh_call_regions", "rvh_install_patch", "rvh_last_error",
-    "rvh_pipeline_create", "rvh_pipeline_destroy", "rvh_pipeline_run", "rvh_pipeline_launch_count",
+    "rvh_pipeline_create", "rvh_pipeline_destroy", "rvh_pipeline_run", "rvh_pipeline_run_paired", "rvh_pipeline_launch_count",
 ]
 
 
@@ -140,11 +140,13 @@ def _declare(L):
     L.rv_push_reads.argtypes = [vp, C.POINTER(ReadBatch)]
     L.rv_push_reads_device.argtypes = [vp, C.POINTER(ReadBatch)]
     L.rv_push_reads_range.argtypes = [vp, C.POINTER(ReadBatch), i64, i64]
+    L.rv_push_reads_ranges.argtypes = [vp, C.POINTER(ReadBatch), i32, vp, vp]
     L.rvh_pipeline_create.argtypes = [C.c_int, C.c_int]
     L.rvh_pipeline_create.restype = vp
     L.rvh_pipeline_destroy.argtypes = [vp]
     L.rvh_pipeline_run.argtypes = [vp, C.POINTER(Params), vp, C.POINTER(Region), i32, i32, vp, i32, i64, C.c_char_p,
                                    C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(i64), C.POINTER(Timing)]
+    L.rvh_pipeline_run_paired.argtypes = L.rvh_pipeline_run.argtypes
     L.rvh_pipeline_launch_count.argtypes = [vp]
     L.rvh_pipeline_launch_count.restype = i64
     L.rv_set_regions.argtypes = [vp, C.POINTER(Region), i32]
@@ -204,11 +206,13 @@ class Pipeline:
         if not self._h:
             raise RabbitVarError("rvh_pipeline_create failed")
 
-    def run(self, params, batch, regions, chunk_regions, ref_bases, ref_lo, sample, chrom):
+    def run(self, params, batch, regions, chunk_regions, ref_bases, ref_lo, sample, chrom, paired=False):
+        """paired=True: regions = n tumor tiles followed by the same n normal tiles; returns the somatic-mode TSV."""
         out = C.c_char_p()
         n = C.c_int64()
         tm = Timing()
-        rc = lib().rvh_pipeline_run(self._h, C.byref(params), batch._h, regions, len(regions), chunk_regions,
+        fn = lib().rvh_pipeline_run_paired if paired else lib().rvh_pipeline_run
+        rc = fn(self._h, C.byref(params), batch._h, regions, len(regions), chunk_regions,
                                     C.cast(C.c_char_p(ref_bases), C.c_void_p), ref_lo, len(ref_bases), sample.encode(),
                                     chrom.encode(), C.byref(out), C.byref(n), C.byref(tm))
         if rc != 0:

@@ -289,7 +289,7 @@ inline int run_batch_simple(rv_ctx* ctx, const rv_params& P, const ReadBatch& ba
 inline int run_batch_somatic(rv_ctx* ctx, const rv_params& P_in, const ReadBatch& batch, const std::vector<rv_region>& regs,
                              const std::vector<std::string>& genes, const std::string& refseq, int32_t ref_lo,
                              const std::string& sample, const std::string& chr, int push_flags, int halo,
-                             std::string* tsv, BatchTiming* tm, std::string* err) {
+                             std::string* tsv, BatchTiming* tm, std::string* err, const int64_t* read_ranges = NULL) {
   BatchTiming t;
   memset(&t, 0, sizeof t);
   int rc;
@@ -309,8 +309,20 @@ inline int run_batch_somatic(rv_ctx* ctx, const rv_params& P_in, const ReadBatch
   if (push_flags & 1) RV_STEP(rv_set_reference(ctx, ref_lo, (int64_t)refseq.size(), refseq.data()));
   if (push_flags & 2) {
     rv_read_batch bv = batch.view();
-    RV_STEP(rv_push_reads(ctx, &bv));
-    t.h2d_bytes += (int64_t)batch.reads.size() * (int64_t)sizeof(rv_read) + (int64_t)batch.pool.size();
+    if (read_ranges) {  // {tumor lo, tumor hi, normal lo, normal hi}: only the reads of this chunk's tiles
+      const int64_t lo[2] = {read_ranges[0], read_ranges[2]}, hi[2] = {read_ranges[1], read_ranges[3]};
+      RV_STEP(rv_push_reads_ranges(ctx, &bv, 2, lo, hi));
+      for (int k = 0; k < 2; ++k)
+        if (hi[k] > lo[k]) {
+          const int64_t p_lo = (int64_t)batch.reads[(size_t)lo[k]].data_off16 * 16;
+          const int64_t p_hi = hi[k] < (int64_t)batch.reads.size() ? (int64_t)batch.reads[(size_t)hi[k]].data_off16 * 16
+                                                                    : (int64_t)batch.pool.size();
+          t.h2d_bytes += (hi[k] - lo[k]) * (int64_t)sizeof(rv_read) + (p_hi - p_lo);
+        }
+    } else {
+      RV_STEP(rv_push_reads(ctx, &bv));
+      t.h2d_bytes += (int64_t)batch.reads.size() * (int64_t)sizeof(rv_read) + (int64_t)batch.pool.size();
+    }
   }
   RV_STEP(rv_set_params(ctx, &P));
   RV_STEP(rv_set_regions(ctx, regs.data(), (int32_t)regs.size()));

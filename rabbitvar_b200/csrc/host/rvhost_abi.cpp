@@ -1,6 +1,7 @@
 // rvhost_abi.cpp — C ABI over the host side of the path (include/rabbitvar_b200_host.h).
 #include "../../../include/rabbitvar_b200_host.h"
 #include "pipeline.hpp"
+#include <array>
 #include <atomic>
 #include <map>
 #include <mutex>
@@ -77,12 +78,19 @@ int64_t rvh_pipeline_launch_count(const rvh_pipeline* p) {
   return n;
 }
 
-int rvh_pipeline_run(rvh_pipeline* p, const rv_params* params, const rvh_batch* batch, const rv_region* regions,
-                     int32_t n_regions, int32_t chunk_regions, const char* ref_bases, int32_t ref_lo, int64_t ref_n,
-                     const char* sample, const char* chr, const char** tsv_out, int64_t* tsv_len, rvh_timing* timing) {
-  if (!p || !params || !batch || (!regions && n_regions) || !ref_bases || !tsv_out || !tsv_len || n_regions < 0)
+static int pipeline_run(rvh_pipeline* p, const rv_params* params, const rvh_batch* batch, const rv_region* regions_in,
+                        int32_t n_regions_in, int32_t chunk_regions, const char* ref_bases, int32_t ref_lo, int64_t ref_n,
+                        const char* sample, const char* chr, const char** tsv_out, int64_t* tsv_len, rvh_timing* timing,
+                        bool paired) {
+  if (!p || !params || !batch || (!regions_in && n_regions_in) || !ref_bases || !tsv_out || !tsv_len || n_regions_in < 0)
     return RV_ERR_ARG;
+  if (paired && (n_regions_in % 2)) return RV_ERR_ARG;
   try {
+    // paired: regions_in = n tumor tiles followed by the same n tiles of the normal sample; a chunk takes tiles
+    // [r0, r1) of both.  The loops below run over tiles.
+    const rv_region* regions = regions_in;
+    const int32_t n_regions = paired ? n_regions_in / 2 : n_regions_in;
+    const int per_tile = paired ? 2 : 1;
     if (chunk_regions < 1) chunk_regions = 1;
     const int n_chunks = (n_regions + chunk_regions - 1) / chunk_regions;
     const ReadBatch& B = batch->b;
@@ -91,27 +99,34 @@ int rvh_pipeline_run(rvh_pipeline* p, const rv_params* params, const rvh_batch* 
     rv_limits need;
     rv_default_limits(&need);
     need.halo = halo;
-    need.max_reads = 1024; need.max_read_bytes = 4096; need.max_positions = 1024; need.max_regions = chunk_regions + 8;
-    std::vector<int64_t> c_lo((size_t)n_chunks), c_hi((size_t)n_chunks);
+    need.max_reads = 1024; need.max_read_bytes = 4096; need.max_positions = 1024;
+    need.max_regions = per_tile * chunk_regions + 8;
+    // read range of every chunk, per sample: [c][2*k] = lo, [c][2*k+1] = hi
+    std::vector<std::array<int64_t, 4> > c_rng((size_t)n_chunks);
     for (int c = 0; c < n_chunks; ++c) {
       const int r0 = c * chunk_regions, r1 = std::min(n_regions, r0 + chunk_regions);
-      int64_t lo = -1, hi = -1, npos = 0;
-      for (int r = r0; r < r1; ++r) {
-        npos += regions[r].end - regions[r].start + 1 + 2 * halo;
-        if (regions[r].read_hi <= regions[r].read_lo) continue;
-        if (lo < 0 || regions[r].read_lo < lo) lo = regions[r].read_lo;
-        if (regions[r].read_hi > hi) hi = regions[r].read_hi;
+      int64_t npos = 0, reads = 0, bytes = 0;
+      for (int k = 0; k < per_tile; ++k) {
+        int64_t lo = -1, hi = -1;
+        for (int r = r0; r < r1; ++r) {
+          const rv_region& g = regions[r + k * n_regions];
+          npos += g.end - g.start + 1 + 2 * halo;
+          if (g.read_hi <= g.read_lo) continue;
+          if (lo < 0 || g.read_lo < lo) lo = g.read_lo;
+          if (g.read_hi > hi) hi = g.read_hi;
+        }
+        if (lo < 0) lo = hi = 0;
+        c_rng[(size_t)c][2 * k] = lo;
+        c_rng[(size_t)c][2 * k + 1] = hi;
+        if (hi > lo) {
+          const int64_t p_lo = (int64_t)B.reads[(size_t)lo].data_off16 * 16;
+          const int64_t p_hi = hi < (int64_t)B.reads.size() ? (int64_t)B.reads[(size_t)hi].data_off16 * 16 : (int64_t)B.pool.size();
+          bytes += p_hi - p_lo + 16;
+          reads += hi - lo;
+        }
       }
-      if (lo < 0) lo = hi = 0;
-      c_lo[(size_t)c] = lo;
-      c_hi[(size_t)c] = hi;
-      int64_t bytes = 0;
-      if (hi > lo) {
-        const int64_t p_lo = (int64_t)B.reads[(size_t)lo].data_off16 * 16;
-        const int64_t p_hi = hi < (int64_t)B.reads.size() ? (int64_t)B.reads[(size_t)hi].data_off16 * 16 : (int64_t)B.pool.size();
-        bytes = p_hi - p_lo;
-      }
-      need.max_reads = std::max<int64_t>(need.max_reads, hi - lo + 64);
+      if (!paired) { c_rng[(size_t)c][2] = c_rng[(size_t)c][3] = 0; }
+      need.max_reads = std::max<int64_t>(need.max_reads, reads + 64);
       need.max_read_bytes = std::max<int64_t>(need.max_read_bytes, bytes + 256);
       need.max_positions = std::max<int64_t>(need.max_positions, npos + 64);
     }
@@ -160,12 +175,15 @@ int rvh_pipeline_run(rvh_pipeline* p, const rv_params* params, const rvh_batch* 
           if (c >= n_chunks) break;
           const int r0 = c * chunk_regions, r1 = std::min(n_regions, r0 + chunk_regions);
           std::vector<rv_region> regs(regions + r0, regions + r1);
-          std::vector<std::string> genes(regs.size(), std::string(chr));
+          if (paired) regs.insert(regs.end(), regions + n_regions + r0, regions + n_regions + r1);
+          std::vector<std::string> genes((size_t)(r1 - r0), std::string(chr));
           const int flags = 2 | (first ? 1 : 0);
           first = false;
-          const int64_t range[2] = {c_lo[(size_t)c], c_hi[(size_t)c]};
-          crc[(size_t)c] = run_batch_simple(ctx, P, B, regs, genes, p->refseq, ref_lo, sample, chr, flags, halo,
-                                            &ctsv[(size_t)c], &ctm[(size_t)c], &cerr[(size_t)c], range);
+          const int64_t* range = c_rng[(size_t)c].data();
+          crc[(size_t)c] = paired ? run_batch_somatic(ctx, *params, B, regs, genes, p->refseq, ref_lo, sample, chr, flags, halo,
+                                                      &ctsv[(size_t)c], &ctm[(size_t)c], &cerr[(size_t)c], range)
+                                  : run_batch_simple(ctx, P, B, regs, genes, p->refseq, ref_lo, sample, chr, flags, halo,
+                                                     &ctsv[(size_t)c], &ctm[(size_t)c], &cerr[(size_t)c], range);
           if (crc[(size_t)c] != RV_OK) break;
         }
         rv_set_params(ctx, params);
@@ -195,6 +213,20 @@ int rvh_pipeline_run(rvh_pipeline* p, const rv_params* params, const rvh_batch* 
     g_err = e.what();
     return RV_ERR_STATE;
   }
+}
+
+int rvh_pipeline_run(rvh_pipeline* p, const rv_params* params, const rvh_batch* batch, const rv_region* regions,
+                     int32_t n_regions, int32_t chunk_regions, const char* ref_bases, int32_t ref_lo, int64_t ref_n,
+                     const char* sample, const char* chr, const char** tsv_out, int64_t* tsv_len, rvh_timing* timing) {
+  return pipeline_run(p, params, batch, regions, n_regions, chunk_regions, ref_bases, ref_lo, ref_n, sample, chr, tsv_out,
+                      tsv_len, timing, false);
+}
+
+int rvh_pipeline_run_paired(rvh_pipeline* p, const rv_params* params, const rvh_batch* batch, const rv_region* regions,
+                            int32_t n_regions, int32_t chunk_tiles, const char* ref_bases, int32_t ref_lo, int64_t ref_n,
+                            const char* sample, const char* chr, const char** tsv_out, int64_t* tsv_len, rvh_timing* timing) {
+  return pipeline_run(p, params, batch, regions, n_regions, chunk_tiles, ref_bases, ref_lo, ref_n, sample, chr, tsv_out,
+                      tsv_len, timing, true);
 }
 
 const char* rvh_last_error(void) { return g_err.c_str(); }

@@ -33,6 +33,9 @@ struct DevRegion {
   int32_t n_pos;
   int64_t item_base;  // first (region, read) work item of this region
   int64_t tile_base;  // first gather tile (GATHER_TILE table positions each, halo included) of this region
+  // the region's reads live in one uploaded slice of the host batch: device read index = batch index - read_bias,
+  // device pool byte = batch pool byte - pool_bias (rv_push_reads_ranges)
+  int64_t read_bias, pool_bias;
 };
 
 static const int GATHER_TILE = 256;
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
     const int ri = find_region(a.regions, a.n_regions, item);
     dr = a.regions + ri;
     read_idx = dr->r.read_lo + (item - dr->item_base);
-    rd = a.reads[read_idx];
+    rd = a.reads[read_idx - dr->read_bias];
     ref.lo = dr->r.ref_lo;
     ref.hi = dr->r.ref_hi;
     s.dr = dr;
@@ -236,10 +239,11 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
     s.covtab = a.cov + dr->tab_off;
     // htslib iterator overlap test (sam_itr_next): pos0 < end && endpos > beg0
     if (rd.pos - 1 < dr->r.end && rd.end_pos > dr->r.start - 1)
-      prepare_read(a.P, dr->r, rd, a.pool, ref, s, true, pr);
+      prepare_read(a.P, dr->r, rd, a.pool - dr->pool_bias, ref, s, true, pr);
   }
   // ---- stage 2: warp-cooperative plain-run proof ------------------------------------------------------
-  const size_t seq_word = (size_t)rd.data_off16 * 4 + rd.n_cigar;  // u32 index of the packed bases in the pool
+  // u32 index of the packed bases in the DEVICE pool
+  const size_t seq_word = (size_t)(((int64_t)rd.data_off16 * 16 - dr->pool_bias) >> 2) + rd.n_cigar;
   int E0 = 0;  // reference-slice index of read base 0
   bool cand = pr.ok && pr.fast_shape && !a.force_exact;
   if (cand) {
@@ -380,7 +384,8 @@ __global__ void __launch_bounds__(128) rv_walk_kernel(PileupArgs a) {
     const int ri = find_region(a.regions, a.n_regions, item);
     const DevRegion* dr = a.regions + ri;
     const int64_t read_idx = dr->r.read_lo + (item - dr->item_base);
-    const rv_read rd = a.reads[read_idx];
+    const rv_read rd = a.reads[read_idx - dr->read_bias];
+    const uint8_t* pool = a.pool - dr->pool_bias;
     RefView ref;
     ref.bases = a.ref;
     ref.base_pos = a.ref_start;
@@ -397,11 +402,11 @@ __global__ void __launch_bounds__(128) rv_walk_kernel(PileupArgs a) {
     s.pend = false;
     s.mute = true;
     Prep pr;
-    prepare_read(a.P, dr->r, rd, a.pool, ref, s, true, pr);
+    prepare_read(a.P, dr->r, rd, pool, ref, s, true, pr);
     s.mute = false;
     if (!pr.ok) continue;  // cannot happen: the item was queued because it passed
     FastDesc scratch;
-    walk_read(a.P, dr->r, ri, rd, a.pool, ref, (uint32_t)read_idx, s, pr, plain_done ? &scratch : (FastDesc*)0,
+    walk_read(a.P, dr->r, ri, rd, pool, ref, (uint32_t)read_idx, s, pr, plain_done ? &scratch : (FastDesc*)0,
               plain_done ? 1 : 0);
     s.resolve();
     over += s.n_over;
@@ -467,10 +472,11 @@ __global__ void rv_tile_index_kernel(GatherArgs a) {
     const int want_lo = c_lo - a.reach[1];  // pos > want_lo
     const int want_hi = c_hi + a.reach[0];  // pos <= want_hi
     int64_t x = dr->r.read_lo, y = dr->r.read_hi;
-    while (x < y) { const int64_t m = (x + y) >> 1; if (a.reads[m].pos <= want_lo) x = m + 1; else y = m; }
+    const rv_read* rr = a.reads - dr->read_bias;
+    while (x < y) { const int64_t m = (x + y) >> 1; if (rr[m].pos <= want_lo) x = m + 1; else y = m; }
     lo = x;
     y = dr->r.read_hi;
-    while (x < y) { const int64_t m = (x + y) >> 1; if (a.reads[m].pos <= want_hi) x = m + 1; else y = m; }
+    while (x < y) { const int64_t m = (x + y) >> 1; if (rr[m].pos <= want_hi) x = m + 1; else y = m; }
     hi = x;
   }
   a.tile_range[2 * tile] = lo;
@@ -1222,12 +1228,14 @@ struct rv_ctx {
   unsigned long long* d_walk_count;
   int64_t n_tiles;
   bool use_gather;
-  bool gather_ws;   // warp-specialised gather kernel (RV_GATHER_WS=0 selects the single-role form)
+  bool gather_ws;   // RV_GATHER_WS=1 selects the warp-specialised gather kernel (experimental)
   // batch state
   const rv_read* reads_dev_view;  // d_reads or a caller-provided device pointer
   const uint8_t* pool_dev_view;
   int64_t n_reads;
   int64_t read_origin;  // first batch read index that is resident (rv_push_reads_range)
+  struct Slice { int64_t read_lo, read_hi, read_bias, pool_bias; };
+  std::vector<Slice> slices;  // uploaded slices of the host batch (one for rv_push_reads / rv_push_reads_device)
   std::vector<DevRegion> regions;
   int64_t n_positions, n_items;
   bool have_patch;
@@ -1332,7 +1340,7 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   ctx->d_events = NULL; ctx->d_variants = NULL; ctx->d_patch = NULL; ctx->d_patch_first = NULL;
   ctx->d_patch_count = NULL; ctx->d_regions = NULL; ctx->d_max_rl = NULL; ctx->d_stats = NULL; ctx->d_lgt = NULL; ctx->d_descs = NULL; ctx->d_reach = NULL; ctx->d_ref4 = NULL; ctx->d_tile_range = NULL; ctx->tile_cap = 0; ctx->d_patched_queue = NULL; ctx->d_patched_count = NULL; ctx->d_walk_queue = NULL; ctx->d_walk_count = NULL; ctx->n_tiles = 0;
   ctx->use_gather = getenv("RV_NO_GATHER") == NULL;
-  ctx->gather_ws = !(getenv("RV_GATHER_WS") && atoi(getenv("RV_GATHER_WS")) == 0);
+  ctx->gather_ws = getenv("RV_GATHER_WS") && atoi(getenv("RV_GATHER_WS")) == 1;
   ctx->h_counts = NULL; ctx->h_cov = NULL; ctx->h_tab_cap = 0; ctx->h_events = NULL; ctx->h_events_cap = 0;
   ctx->h_variants = NULL; ctx->h_variants_cap = 0; ctx->h_max_rl = NULL; ctx->h_rows = NULL; ctx->h_rows_cap = 0; ctx->d_scratch = NULL; ctx->scratch_cap = 0;
   ctx->n_reads = 0; ctx->read_origin = 0; ctx->n_positions = 0; ctx->n_items = 0; ctx->have_patch = false; ctx->tables_fetched = false;
@@ -1455,29 +1463,43 @@ int rv_push_reads(rv_ctx* ctx, const rv_read_batch* b) {
   ctx->pool_dev_view = ctx->d_pool;
   ctx->n_reads = b->n_reads;
   ctx->read_origin = 0;
+  ctx->slices.assign(1, rv_ctx::Slice{0, b->n_reads, 0, 0});
+  return RV_OK;
+}
+
+int rv_push_reads_ranges(rv_ctx* ctx, const rv_read_batch* b, int32_t n_ranges, const int64_t* read_lo, const int64_t* read_hi) {
+  if (!ctx || !b || n_ranges < 0 || (n_ranges && (!read_lo || !read_hi))) return RV_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  ctx->slices.clear();
+  int64_t dev_reads = 0, dev_pool = 0, hi_max = 0;
+  for (int k = 0; k < n_ranges; ++k) {
+    const int64_t lo = read_lo[k], hi = read_hi[k];
+    if (lo < 0 || hi < lo || hi > b->n_reads) return fail(ctx, RV_ERR_ARG, "bad read range");
+    const int64_t n = hi - lo;
+    if (n == 0) continue;
+    const int64_t pool_lo = (int64_t)b->reads[lo].data_off16 * 16;
+    const int64_t pool_hi = hi < b->n_reads ? (int64_t)b->reads[hi].data_off16 * 16 : ((b->pool_bytes + 15) & ~(int64_t)15);
+    if (pool_hi < pool_lo) return fail(ctx, RV_ERR_ARG, "read headers do not index the pool in order");
+    if (dev_reads + n > ctx->L.max_reads) return fail(ctx, RV_ERR_OVERFLOW, "read ranges larger than limits.max_reads");
+    if (dev_pool + (pool_hi - pool_lo) > ctx->L.max_read_bytes + 16)
+      return fail(ctx, RV_ERR_OVERFLOW, "read ranges' pool larger than limits.max_read_bytes");
+    const int64_t copy_hi = pool_hi < b->pool_bytes ? pool_hi : b->pool_bytes;
+    CK(cudaMemcpyAsync(ctx->d_reads + dev_reads, b->reads + lo, sizeof(rv_read) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_pool + dev_pool, b->pool + pool_lo, (size_t)(copy_hi - pool_lo), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->slices.push_back(rv_ctx::Slice{lo, hi, lo - dev_reads, pool_lo - dev_pool});
+    dev_reads += n;
+    dev_pool += pool_hi - pool_lo;  // a multiple of 16: every read starts on a 16-byte boundary
+    if (hi > hi_max) hi_max = hi;
+  }
+  ctx->reads_dev_view = ctx->d_reads;
+  ctx->pool_dev_view = ctx->d_pool;
+  ctx->n_reads = hi_max;
+  ctx->read_origin = 0;
   return RV_OK;
 }
 
 int rv_push_reads_range(rv_ctx* ctx, const rv_read_batch* b, int64_t read_lo, int64_t read_hi) {
-  if (!ctx || !b || read_lo < 0 || read_hi < read_lo || read_hi > b->n_reads) return RV_ERR_ARG;
-  const int64_t n = read_hi - read_lo;
-  if (n > ctx->L.max_reads) return fail(ctx, RV_ERR_OVERFLOW, "read range larger than limits.max_reads");
-  CK(cudaSetDevice(ctx->device));
-  int64_t pool_lo = 0, pool_hi = 0;
-  if (n) {
-    pool_lo = (int64_t)b->reads[read_lo].data_off16 * 16;
-    pool_hi = read_hi < b->n_reads ? (int64_t)b->reads[read_hi].data_off16 * 16 : b->pool_bytes;
-    if (pool_hi < pool_lo || pool_hi > b->pool_bytes) return fail(ctx, RV_ERR_ARG, "read headers do not index the pool in order");
-    if (pool_hi - pool_lo > ctx->L.max_read_bytes) return fail(ctx, RV_ERR_OVERFLOW, "read range pool larger than limits.max_read_bytes");
-    CK(cudaMemcpyAsync(ctx->d_reads, b->reads + read_lo, sizeof(rv_read) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_pool, b->pool + pool_lo, (size_t)(pool_hi - pool_lo), cudaMemcpyHostToDevice, ctx->stream));
-  }
-  // device views biased so that batch-global read indices and pool offsets address the uploaded slice
-  ctx->reads_dev_view = ctx->d_reads - read_lo;
-  ctx->pool_dev_view = ctx->d_pool - pool_lo;
-  ctx->n_reads = read_hi;
-  ctx->read_origin = read_lo;
-  return RV_OK;
+  return rv_push_reads_ranges(ctx, b, 1, &read_lo, &read_hi);
 }
 
 int rv_push_reads_device(rv_ctx* ctx, const rv_read_batch* b) {
@@ -1486,6 +1508,7 @@ int rv_push_reads_device(rv_ctx* ctx, const rv_read_batch* b) {
   ctx->pool_dev_view = b->pool;
   ctx->n_reads = b->n_reads;
   ctx->read_origin = 0;
+  ctx->slices.assign(1, rv_ctx::Slice{0, b->n_reads, 0, 0});
   return RV_OK;
 }
 
@@ -1498,9 +1521,19 @@ int rv_set_regions(rv_ctx* ctx, const rv_region* regs, int32_t n) {
   for (int i = 0; i < n; ++i) {
     DevRegion& d = ctx->regions[i];
     d.r = regs[i];
-    if (d.r.end < d.r.start || d.r.read_hi < d.r.read_lo || d.r.read_hi > ctx->n_reads ||
-        (d.r.read_hi > d.r.read_lo && d.r.read_lo < ctx->read_origin))
-      return fail(ctx, RV_ERR_ARG, "bad region " + std::to_string(i));
+    if (d.r.end < d.r.start || d.r.read_hi < d.r.read_lo) return fail(ctx, RV_ERR_ARG, "bad region " + std::to_string(i));
+    d.read_bias = 0;
+    d.pool_bias = 0;
+    if (d.r.read_hi > d.r.read_lo) {
+      bool found = false;
+      for (size_t k = 0; k < ctx->slices.size() && !found; ++k)
+        if (d.r.read_lo >= ctx->slices[k].read_lo && d.r.read_hi <= ctx->slices[k].read_hi) {
+          d.read_bias = ctx->slices[k].read_bias;
+          d.pool_bias = ctx->slices[k].pool_bias;
+          found = true;
+        }
+      if (!found) return fail(ctx, RV_ERR_ARG, "region " + std::to_string(i) + " refers to reads that are not resident");
+    }
     d.first_pos = d.r.start - ctx->L.halo;
     d.n_pos = d.r.end - d.r.start + 1 + 2 * ctx->L.halo;
     d.tab_off = tab;

@@ -180,3 +180,49 @@ def test_pipeline_equals_single_call(built):
         assert got == want
         assert tm2.n_aligned_bases == tm.n_aligned_bases and tm2.n_lines == tm.n_lines
     b.close()
+
+
+def test_paired_pipeline_matches_reference_output(built):
+    """rvh_pipeline_run_paired (chunks of tumor + normal tiles, two-range read uploads, several worker contexts) prints
+    the reference binary's somatic-mode lines (the BED name column aside: the pipeline call carries no BED names)."""
+    import ctypes as C
+    import rabbitvar_b200 as rv
+    name = "c2_somatic_bed_k0"
+    d = cases.generate(name)
+    tiles = [l.split() for l in open(os.path.join(d, "tiles.bed"))]
+    starts, ends = [int(t[1]) for t in tiles], [int(t[2]) for t in tiles]
+    bt = rv.HostBatch(os.path.join(d, "T.bam"), "chrS2", starts[0], ends[-1])
+    bn = rv.HostBatch(os.path.join(d, "N.bam"), "chrS2", starts[0], ends[-1])
+    n_t = bt.n_reads
+    off = bt.append(bn)
+    n_n = bn.n_reads
+    bn.close()
+    rt = bt.make_regions(starts, ends, 1200, 0, n_t)
+    rn = bt.make_regions(starts, ends, 1200, off, n_n)
+    n = len(tiles)
+    regs = (rv.Region * (2 * n))()
+    C.memmove(regs, rt, C.sizeof(rv.Region) * n)
+    C.memmove(C.byref(regs, C.sizeof(rv.Region) * n), rn, C.sizeof(rv.Region) * n)
+    ref = rv.fetch_ref(os.path.join(d, "ref.fa"), "chrS2", 1, bt.chr_len)
+    params = rv.default_params(fisher=1, local_realign=0)
+    with gzip.open(golden_path(name, "tsv"), "rt") as f:
+        want = _tsv_lines(f.read())
+
+    def strip_gene(lines):
+        out = []
+        for l in lines:
+            t = l.split("\t")
+            t[1] = ""
+            out.append("\t".join(t))
+        return sorted(out)
+
+    want = strip_gene(want)
+    for workers, chunk in ((1, 3), (3, 1)):
+        pipe = rv.Pipeline(0, workers)
+        tsv, tm = pipe.run(params, bt, regs, chunk, ref, 1, "T|N", "chrS2", paired=True)
+        pipe.close()
+        got = strip_gene(_tsv_lines(tsv))
+        assert len(got) == len(want), (len(got), len(want))
+        bad = [(w, g) for w, g in zip(want, got) if w != g and not _tsv_equal(w, g)]
+        assert not bad, bad[:3]
+    bt.close()
