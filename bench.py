@@ -200,8 +200,8 @@ def main():
     ap.add_argument("--ref-tiles", type=int, default=150, help="tiles in the CPU-baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--workers", type=int, default=6, help="pipeline workers (contexts) per GPU in the e2e path")
-    ap.add_argument("--chunk", type=int, default=25, help="tiles per pipeline chunk in the e2e path")
+    ap.add_argument("--workers", type=int, default=16, help="pipeline workers (contexts) per GPU in the e2e path")
+    ap.add_argument("--chunk", type=int, default=5, help="tiles per pipeline chunk in the e2e path")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -251,7 +251,7 @@ def main():
                             max_regions=nreg + 8, halo=halo, max_events=max(1 << 20, bt.n_reads),
                             max_variants=3 * n_pos + 1024, max_patch=max(1 << 20, bt.n_reads // 2),
                             max_ref_bases=len(ref) + 64)
-    params = rv.default_params(fisher=1, has_bam2=1)
+    params = rv.default_params(fisher=1, has_bam2=1, candidates_only=1)
     ctx = rv.Context(local, params, lim)
     ctx.set_reference(1, ref)
 
@@ -269,6 +269,7 @@ def main():
     bt.pin()
 
     pipe = rv.Pipeline(local, args.workers)
+    e2e_params = rv.default_params(fisher=1)  # the reference CLI's flags for this config: -f 0.01 --fisher, -b 'T|N'
     regs_t_arr = (rv.Region * half).from_address(C.addressof(regs))
     regs_n_arr = (rv.Region * half).from_address(C.addressof(regs) + half * C.sizeof(rv.Region))
 
@@ -276,11 +277,13 @@ def main():
         t_a = time.perf_counter()
         # host buffers in, TSV out: every chunk of tiles is copied H2D, piled, handed to the host stage, scored,
         # copied back and formatted; the pipeline's workers overlap those stages across chunks
-        tsv_t, tm_t = pipe.run(params, bt, regs_t_arr, args.chunk, ref, 1, "T", "chrS2")
-        tsv_n, tm_n = pipe.run(params, bt, regs_n_arr, args.chunk, ref, 1, "N", "chrS2")
-        return time.perf_counter() - t_a, (tm_t, tm_n), len(tsv_t) + len(tsv_n)
+        tsv, tm_p = pipe.run(e2e_params, bt, regs, args.chunk, ref, 1, "T|N", "chrS2", paired=True)
+        return time.perf_counter() - t_a, (tm_p,), len(tsv)
 
     # ---- device-resident steps ---------------------------------------------------------------------------
+    # One step = what run_batch_somatic launches for this workload: rv_pileup over every (tile, sample), rv_score with the
+    # device-side candidate cut over every position of both samples, rv_score_positions for the full records of both
+    # samples at the positions where either has a candidate (the tumor | normal join list, built once here).
     ctx.push_reads_ptr(bt.n_reads, d_reads.data_ptr(), d_pool.data_ptr(), int(pool_np.size), device=True)
     ctx.set_regions(regs)
     st = ctx.pileup()
@@ -289,9 +292,31 @@ def main():
     # sparse keys of this batch (identical every step): reduce once on the host, keep the patch resident
     ctx.install_patch_from_events(bt, regs, ref, 1)
     ctx.score()
-    for _ in range(max(0, args.warmup - 1)):
+    vp, n_candidate_records = ctx.fetch_variants()
+    if n_candidate_records > 5000000:
+        raise rv.RabbitVarError("candidate pass returned an implausible number of records")
+    rec = np.frombuffer((C.c_char * (n_candidate_records * C.sizeof(rv.Variant))).from_address(C.addressof(vp.contents)),
+                        dtype=np.int32).reshape(n_candidate_records, C.sizeof(rv.Variant) // 4) \
+        if n_candidate_records else np.zeros((0, C.sizeof(rv.Variant) // 4), np.int32)
+    cr = rec[:, 0].astype(np.int64) % half
+    cp = rec[:, 1].astype(np.int64)
+    uniq = np.unique(cr * (1 << 32) + cp)
+    jr = (uniq >> 32).astype(np.int32)
+    jp = (uniq & 0xffffffff).astype(np.int32)
+    join_regions = np.concatenate([jr, jr + half]).astype(np.int32)
+    join_positions = np.concatenate([jp, jp]).astype(np.int32)
+
+    def step():
         ctx.pileup()
         ctx.score()
+        a, b = ctx.kernel_ms()
+        sp = ctx.pileup_split_ms()
+        ctx.score_positions(join_regions, join_positions)
+        _, b2 = ctx.kernel_ms()
+        return a, b + b2, sp
+
+    for _ in range(max(0, args.warmup - 1)):
+        step()
     ctx.sync()
     if world > 1:
         dist.barrier()
@@ -303,12 +328,10 @@ def main():
     ctx.timer_start()
     w0 = time.perf_counter()
     for _ in range(args.steps):
-        ctx.pileup()
-        ctx.score()
-        a, b = ctx.kernel_ms()
+        a, b, sp = step()
         pile_ms.append(a)
         score_ms.append(b)
-        split_ms.append(ctx.pileup_split_ms())
+        split_ms.append(sp)
     dev_ms = ctx.timer_stop()
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - w0) * 1000.0
@@ -316,7 +339,7 @@ def main():
         dist.barrier()
     launches = ctx.launch_count() - l0
     clocks = sampler.finish()
-    n_var_step = ctx.n_variants()
+    n_var_step = ctx.n_variants() + n_candidate_records
 
     # ---- e2e steps (host buffers, copies inside the timed region) ---------------------------------------
     e2e_t, e2e_tm, tsv_len = [], None, 0
@@ -326,7 +349,7 @@ def main():
             e2e_t.append(dt)
             e2e_tm = tms
     e2e_sec = sum(e2e_t) / len(e2e_t)
-    for nm, t in zip("TN", e2e_tm):
+    for nm, t in zip(("T|N",), e2e_tm):
         log(f"[bench r{rank}] e2e {nm}: push {t.push_ms:.1f} pileup {t.pileup_ms:.1f} fetch {t.fetch_ms:.1f} host {t.host_ms:.1f} "
             f"patch {t.patch_ms:.1f} score {t.score_ms:.1f} assemble {t.assemble_ms:.1f} ms; events {t.n_events} "
             f"variants {t.n_variants} lines {t.n_lines}")
@@ -388,10 +411,10 @@ def main():
                        "regions_per_gpu": nreg, "reads_per_gpu": int(bt.n_reads), "aligned_bases_per_step_per_gpu": int(bases_per_step),
                        "l2_policy": f"inputs ({read_bytes_total / 1e9:.2f} GB reads + {n_pos * 132 / 1e9:.2f} GB tables) exceed the 126 MB L2",
                        "wall_ms_per_step": wall_ms_max / args.steps,
-                       "note": "somatic T/N join + classification (somaticMode.cpp:311-620) is host-side and not part of the timed path"},
+                       "step": "rv_pileup + rv_score (candidate cut, every position of both samples) + rv_score_positions (full records of both samples at the joined candidate positions): the launches of run_batch_somatic; the join list and the host realigner patch are built once outside the timed loop"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": f"rvh_pipeline_run (host buffers -> TSV), {args.workers} worker contexts x {args.chunk}-tile chunks, pinned H2D", "sec_per_step": e2e_sec_max,
+                    "api": f"rvh_pipeline_run_paired (host buffers -> somatic-mode TSV), {args.workers} worker contexts x {args.chunk}-tile chunks of both samples, pinned H2D", "sec_per_step": e2e_sec_max,
                     "tsv_bytes": tsv_len},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm",

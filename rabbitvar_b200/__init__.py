@@ -378,6 +378,13 @@ class Context:
     def score(self):
         self._ck(lib().rv_score(self._h), "rv_score")
 
+    def score_positions(self, regions, positions):
+        """Full records at an explicit list of (region, position) pairs (numpy int32 arrays)."""
+        import numpy as np
+        r = np.ascontiguousarray(regions, dtype=np.int32)
+        p = np.ascontiguousarray(positions, dtype=np.int32)
+        self._ck(lib().rv_score_positions(self._h, r.ctypes.data, p.ctypes.data, len(r)), "rv_score_positions")
+
     def sync(self):
         self._ck(lib().rv_sync(self._h), "rv_sync")
 

@@ -52,7 +52,7 @@ extern "C" {
 
 rvh_pipeline* rvh_pipeline_create(int device, int n_workers) {
   if (n_workers < 1) n_workers = 1;
-  if (n_workers > 16) n_workers = 16;
+  if (n_workers > 64) n_workers = 64;
   rvh_pipeline* p = new rvh_pipeline();
   p->device = device;
   p->n_workers = n_workers;

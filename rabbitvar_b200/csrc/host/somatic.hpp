@@ -29,9 +29,15 @@ inline bool is_noise(VariantOut& v, const rv_params& P) {
 
 // put_fisher_ext_and_odds, somaticMode.cpp:130-149 (single-precision odds, as written)
 inline void put_fisher_and_odds(std::string& s, int ref_fwd, int ref_rev, int alt_fwd, int alt_rev) {
+  // lgamma(n + 1) table for the host-side Fisher tests (three per printed line)
+  static const std::vector<double> table = [] {
+    std::vector<double> t(1 << 16);
+    for (size_t i = 0; i < t.size(); ++i) t[i] = lgamma((double)i + 1.0);
+    return t;
+  }();
   rvk::LgTable lg;
-  lg.t = NULL;
-  lg.n = 0;
+  lg.t = table.data();
+  lg.n = (int)table.size();
   double l, r, two;
   rvk::fisher_exact(lg, ref_fwd, ref_rev, alt_fwd, alt_rev, &l, &r, &two);
   s += std::to_string(two);

@@ -505,6 +505,17 @@ RV_HDN void score_dense_position(const rv_params& P, int region_idx, int pos, ch
     }
   if (n_exist == 0 || cov_p == 0) return;  // ToVarsBuilder.cpp:103-128
   if (n_exist == 1 && refb && BASES[only_al] == refb && !P.pileup && !P.has_bam2) return;  // :133, :213-233
+  if (P.candidates_only && !P.pileup) {
+    // integer pre-screen of the candidate cut below: a position none of whose non-reference alleles has
+    // hicnt >= minr cannot print anything (most sequencing-error alleles stop here, before any double arithmetic)
+    bool possible = false;
+    for (int a = 0; a < 4; ++a) {
+      const uint32_t* row = rows + a * RV_ROW_U32;
+      if (BASES[a] != refb && dense_exists(row) && row[RV_F_FWD] + row[RV_F_REV] != 0 && (int)row[RV_F_HI] >= P.minr)
+        possible = true;
+    }
+    if (!possible) return;
+  }
   const int tcov = (int)cov_p;
   int al[4], cnt[4], bias[4];
   double qual[4], freq[4], pmean[4];
