@@ -1080,6 +1080,42 @@ __global__ void __launch_bounds__(SCORE_BLOCK, 4) rv_score_kernel(ScoreArgs a) {
   }
 }
 
+// Candidate mode (rv_params.candidates_only, simple-mode and paired-mode output): one position per thread, integer
+// work only.  A position can print something only if one of its non-reference alleles has hicnt >= minr (a
+// necessary condition of Variant::isGoodVar, include/Variant.h:205-231); those positions, and the positions with
+// patch entries, are queued for the general scoring kernel.  Everything else ends here after one pass over its row.
+__global__ void __launch_bounds__(256) rv_score_screen_kernel(ScoreArgs a) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.n_positions) return;
+  const int ri = find_region_by_tab(a.regions, a.n_regions, t);
+  const DevRegion* dr = a.regions + ri;
+  const int pos = dr->first_pos + (int)(t - dr->tab_off);
+  if (pos < dr->r.start || pos > dr->r.end) return;
+  bool queue = (a.patch_first ? a.patch_first[t] : 0u) != 0;
+  if (!queue) {
+    const uint4* r4 = (const uint4*)(a.counts + (size_t)t * RV_POS_U32);
+    int refal = -1;
+    if (pos >= dr->r.ref_lo && pos <= dr->r.ref_hi && pos >= a.ref_start && (int64_t)(pos - a.ref_start) < a.ref_n)
+      refal = allele_of(a.ref[pos - a.ref_start]);
+    uint32_t any = 0;
+    bool possible = false;
+#pragma unroll
+    for (int al = 0; al < 4; ++al) {
+      const uint4 x = r4[2 * al], y = r4[2 * al + 1];
+      const uint32_t ex = x.x | x.y | x.z | x.w | y.x | y.y | y.z | y.w;
+      any |= ex;
+      if (al != refal && ex && x.x + x.y != 0 && (int)y.z >= a.P.minr) possible = true;  // fwd + rev, hicnt
+    }
+    queue = any && a.cov[t] != 0 && possible;
+  }
+  if (queue) {
+    cg::coalesced_group g = cg::coalesced_threads();
+    unsigned long long slot = 0;
+    if (g.thread_rank() == 0) slot = atomicAdd(a.patched_count, (unsigned long long)g.size());
+    a.patched_queue[g.shfl(slot, 0) + g.thread_rank()] = t;
+  }
+}
+
 __global__ void __launch_bounds__(128) rv_score_patched_kernel(ScoreArgs a) {
   const unsigned long long n = *a.patched_count;
   for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < n;
@@ -1090,8 +1126,8 @@ __global__ void __launch_bounds__(128) rv_score_patched_kernel(ScoreArgs a) {
     const int i = (int)(t - dr->tab_off);
     const int pos = dr->first_pos + i;
     const uint32_t* rows = a.counts + (size_t)t * RV_POS_U32;
-    const uint32_t pf = a.patch_first[t];
-    const int pn = (int)a.patch_count[t];
+    const uint32_t pf = a.patch_first ? a.patch_first[t] : 0u;
+    const int pn = pf ? (int)a.patch_count[t] : 0;
     RefView ref;
     ref.bases = a.ref;
     ref.base_pos = a.ref_start;
@@ -1106,7 +1142,7 @@ __global__ void __launch_bounds__(128) rv_score_patched_kernel(ScoreArgs a) {
     em.a = &a;
     int unsup = 0;
     score_position(a.P, dr->r, ri, pos, ref, rows, a.cov[t], has_next, rows + RV_POS_U32, has_next ? a.cov[t + 1] : 0u,
-                   a.patch, (int)(pf - 1), pn, L, em, &unsup);
+                   a.patch, pf ? (int)(pf - 1) : 0, pn, L, em, &unsup);
     if (unsup) atomicAdd(&a.stats->n_score_unsupported, (unsigned long long)unsup);
   }
 }
@@ -1376,8 +1412,8 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   // gather tiles: every region rounds its table (length + 2*halo) up to whole tiles
   ctx->tile_cap = L.max_positions / GATHER_TILE + L.max_regions + 1;
   CK(cudaMalloc(&ctx->d_tile_range, 2 * sizeof(int64_t) * (size_t)ctx->tile_cap));
-  // a patch group is one position: at most max_patch positions carry patch entries
-  CK(cudaMalloc(&ctx->d_patched_queue, sizeof(int64_t) * (size_t)(L.max_patch + 1)));
+  // positions queued for the general scoring kernel (patched positions, screened candidates): at most every position
+  CK(cudaMalloc(&ctx->d_patched_queue, sizeof(int64_t) * (size_t)(L.max_positions + 1)));
   CK(cudaMalloc(&ctx->d_patched_count, sizeof(unsigned long long)));
   CK(cudaMalloc(&ctx->d_walk_queue, sizeof(unsigned long long) * (size_t)(2 * L.max_reads + 1024)));
   CK(cudaMalloc(&ctx->d_walk_count, sizeof(unsigned long long)));
@@ -1857,14 +1893,21 @@ int rv_score(rv_ctx* ctx) {
   fill_score_args(ctx, a);
   if (ctx->n_positions > 0) {
     CK(cudaMemsetAsync(ctx->d_patched_count, 0, sizeof(unsigned long long), ctx->stream));
-    unsigned grid = (unsigned)((ctx->n_positions + SCORE_BLOCK - 1) / SCORE_BLOCK);
-    rv_score_kernel<<<grid, SCORE_BLOCK, 0, ctx->stream>>>(a);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    if (ctx->have_patch) {
-      rv_score_patched_kernel<<<148 * 4, 128, 0, ctx->stream>>>(a);
+    if (ctx->P.candidates_only && !ctx->P.pileup) {
+      rv_score_screen_kernel<<<(unsigned)((ctx->n_positions + 255) / 256), 256, 0, ctx->stream>>>(a);
+      rv_score_patched_kernel<<<148 * 8, 128, 0, ctx->stream>>>(a);
+      ctx->launches += 2;
+      CK(cudaGetLastError());
+    } else {
+      unsigned grid = (unsigned)((ctx->n_positions + SCORE_BLOCK - 1) / SCORE_BLOCK);
+      rv_score_kernel<<<grid, SCORE_BLOCK, 0, ctx->stream>>>(a);
       ctx->launches++;
       CK(cudaGetLastError());
+      if (ctx->have_patch) {
+        rv_score_patched_kernel<<<148 * 4, 128, 0, ctx->stream>>>(a);
+        ctx->launches++;
+        CK(cudaGetLastError());
+      }
     }
   }
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
