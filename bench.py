@@ -289,6 +289,8 @@ def main():
     st = ctx.pileup()
     bases_per_step = st.n_aligned_bases
     kept_per_step = st.n_reads_kept
+    log(f"[bench r{rank}] pileup: {st.n_items} work items, {st.n_reads_kept} kept, {st.n_walk_items} walked "
+        f"({st.n_walk_full} whole reads), {st.n_events} events")
     # sparse keys of this batch (identical every step): reduce once on the host, keep the patch resident
     ctx.install_patch_from_events(bt, regs, ref, 1)
     ctx.score()

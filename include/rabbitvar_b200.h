@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RV_ABI_VERSION 1
+#define RV_ABI_VERSION 2
 #define RV_OK 0
 #define RV_ERR_ARG (-1)
 #define RV_ERR_CUDA (-2)
@@ -247,6 +247,8 @@ typedef struct rv_pileup_stats {
   int64_t n_events;
   int64_t n_overflow;       /* dropped observations (halo / op-table / event-buffer overflow) */
   int64_t n_unsupported;    /* reads that hit a corner the device path refuses (counted, not guessed) */
+  int64_t n_walk_items;     /* work items that took the exact CIGAR walk (rv_walk_kernel) ... */
+  int64_t n_walk_full;      /* ... of which the whole read was walked (the rest: soft clips of a plain read only) */
 } rv_pileup_stats;
 int rv_get_pileup_stats(rv_ctx* ctx, rv_pileup_stats* out);
 /* maxReadLength per region after the pileup (parseCigar.cpp:598-601). */

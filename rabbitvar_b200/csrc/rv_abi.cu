@@ -42,6 +42,7 @@ static const int GATHER_TILE = 256;
 
 struct DevStats {
   unsigned long long n_items, n_kept, n_bases, n_events, n_overflow, n_unsupported, n_variants, n_score_unsupported;
+  unsigned long long n_walk_items, n_walk_full;
 };
 
 // Gather descriptor of one (region, read) work item whose rewritten CIGAR is [H][S] M [S][H] and whose matched
@@ -375,12 +376,14 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
 // The exact CIGAR walk for the queued work items, one per thread (all lanes busy with walks).
 __global__ void __launch_bounds__(128) rv_walk_kernel(PileupArgs a) {
   const unsigned long long n = *a.walk_count;
-  unsigned long long over = 0, unsup = 0;
+  unsigned long long over = 0, unsup = 0, full = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.stats->n_walk_items = n;
   for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < n;
        q += (unsigned long long)gridDim.x * blockDim.x) {
     const unsigned long long entry = a.walk_queue[q];
     const int64_t item = (int64_t)(entry & ~WALK_PLAIN_DONE);
     const bool plain_done = (entry & WALK_PLAIN_DONE) != 0;
+    if (!plain_done) full++;
     const int ri = find_region(a.regions, a.n_regions, item);
     const DevRegion* dr = a.regions + ri;
     const int64_t read_idx = dr->r.read_lo + (item - dr->item_base);
@@ -414,6 +417,7 @@ __global__ void __launch_bounds__(128) rv_walk_kernel(PileupArgs a) {
   }
   if (over) atomicAdd(&a.stats->n_overflow, over);
   if (unsup) atomicAdd(&a.stats->n_unsupported, unsup);
+  if (full) atomicAdd(&a.stats->n_walk_full, full);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -487,7 +491,7 @@ __device__ __forceinline__ int nib_allele(int nib) { return (nib >> 1) - (nib >>
 
 static const int REC_BIAS = 256;  // keeps the arena byte offsets of a staged read non-negative 16-bit numbers
 
-__global__ void __launch_bounds__(GATHER_TILE) rv_gather_kernel(GatherArgs a) {
+__global__ void __launch_bounds__(GATHER_TILE, 5) rv_gather_kernel(GatherArgs a) {
   __shared__ __align__(16) uint8_t s_arena[ARENA_CHUNKS * 16];
   // staged read: {rel_start, seq byte offset | qual byte offset << 16 (both + REC_BIAS), m_len | par << 16 | dir << 17,
   //               mapq | nm << 16}
@@ -1690,6 +1694,8 @@ int rv_get_pileup_stats(rv_ctx* ctx, rv_pileup_stats* o) {
   o->n_events = (int64_t)ctx->h_stats.n_events;
   o->n_overflow = (int64_t)ctx->h_stats.n_overflow;
   o->n_unsupported = (int64_t)ctx->h_stats.n_unsupported;
+  o->n_walk_items = (int64_t)ctx->h_stats.n_walk_items;
+  o->n_walk_full = (int64_t)ctx->h_stats.n_walk_full;
   return RV_OK;
 }
 
