@@ -6,6 +6,7 @@
 // Only string work happens here; every number comes from the scoring kernel.
 #pragma once
 #include "pileup_model.hpp"
+#include "fmt.hpp"
 #include "../kernels/rv_core.cuh"
 #include <stdio.h>
 #include <string>
@@ -318,15 +319,15 @@ inline std::string format_simple(const VariantOut& v, const std::string& sample,
   add(std::to_string(v.start)); add(std::to_string(v.end)); add(v.refallele); add(v.varallele);
   add(std::to_string(v.tcov)); add(std::to_string(v.cnt)); add(std::to_string(v.ref_fwd)); add(std::to_string(v.ref_rev));
   add(std::to_string(v.fwd)); add(std::to_string(v.rev)); add(v.genotype.empty() ? "0" : v.genotype);
-  add(std::to_string(v.freq)); add(v.bias); add(std::to_string(v.pmean)); add(v.pstd ? "1" : "0");
-  add(std::to_string(v.qual)); add(v.qstd ? "1" : "0");
-  if (fisher) { add(std::to_string(v.pvalue)); add(std::to_string(v.oddratio)); }
-  add(std::to_string(v.mapq)); add(std::to_string(v.qratio)); add(std::to_string(v.hifreq));
-  add(std::to_string(v.extrafreq)); add(std::to_string(v.shift3)); add(std::to_string(v.msi));
-  add(std::to_string(v.msint)); add(v.nm > 0 ? std::to_string(v.nm) : std::to_string(0)); add(std::to_string(v.hicnt));
+  add(f6(v.freq)); add(v.bias); add(f6(v.pmean)); add(v.pstd ? "1" : "0");
+  add(f6(v.qual)); add(v.qstd ? "1" : "0");
+  if (fisher) { add(f6(v.pvalue)); add(f6(v.oddratio)); }
+  add(f6(v.mapq)); add(f6(v.qratio)); add(f6(v.hifreq));
+  add(f6(v.extrafreq)); add(std::to_string(v.shift3)); add(f6(v.msi));
+  add(std::to_string(v.msint)); add(v.nm > 0 ? f6(v.nm) : std::to_string(0)); add(std::to_string(v.hicnt));
   add(std::to_string(v.hicov)); add(v.leftseq.empty() ? "0" : v.leftseq); add(v.rightseq.empty() ? "0" : v.rightseq);
   add(chr + ":" + std::to_string(rstart) + "-" + std::to_string(rend)); add(v.vartype);
-  add(std::to_string(0.0));  // duprate: CigarParser::process forces 0 (parseCigar.cpp:432)
+  add(f6(0.0));  // duprate: CigarParser::process forces 0 (parseCigar.cpp:432)
   s += "0\n";                // sv placeholder
   return s;
 }

@@ -40,13 +40,13 @@ inline void put_fisher_and_odds(std::string& s, int ref_fwd, int ref_rev, int al
   lg.n = (int)table.size();
   double l, r, two;
   rvk::fisher_exact(lg, ref_fwd, ref_rev, alt_fwd, alt_rev, &l, &r, &two);
-  s += std::to_string(two);
+  append_f6(s, two);
   s += '\t';
   const float t_ref_fwd = ref_fwd + 0.5, t_ref_rev = ref_rev + 0.5, t_alt_fwd = alt_fwd + 0.5, t_alt_rev = alt_rev + 0.5;
   const float ad = t_ref_fwd * t_alt_rev;
   const float bc = t_ref_rev * t_alt_fwd;
   const float ratio = std::log(ad / bc + bc / ad);
-  s += std::to_string(ratio);
+  append_f6(s, (double)ratio);
   s += '\t';
 }
 
@@ -60,9 +60,9 @@ inline void sample_block(std::string& s, const VariantOut* v, const VariantOut* 
   add(std::to_string(v->fwd)); add(std::to_string(v->rev));
   // the normal block prints the TUMOR genotype when its own is set (somaticMode.cpp:205, as written)
   add(v->genotype.empty() ? "0" : (tumor_for_genotype ? tumor_for_genotype->genotype : v->genotype));
-  add(std::to_string(v->freq)); add(v->bias); add(std::to_string(v->pmean)); add(v->pstd ? "1" : "0");
-  add(std::to_string(v->qual)); add(v->qstd ? "1" : "0"); add(std::to_string(v->mapq)); add(std::to_string(v->qratio));
-  add(std::to_string(v->hifreq)); add(std::to_string(v->extrafreq)); add(std::to_string(v->nm));
+  add(f6(v->freq)); add(v->bias); add(f6(v->pmean)); add(v->pstd ? "1" : "0");
+  add(f6(v->qual)); add(v->qstd ? "1" : "0"); add(f6(v->mapq)); add(f6(v->qratio));
+  add(f6(v->hifreq)); add(f6(v->extrafreq)); add(f6(v->nm));
 }
 
 // print_output_variant_simple, somaticMode.cpp:151-309
@@ -90,7 +90,7 @@ inline std::string format_somatic(const VariantOut* begin, const VariantOut* end
     else s += "0\t0\t";
   }
   if (end) {
-    add(std::to_string(end->shift3)); add(std::to_string(end->msi)); add(std::to_string(end->msint));
+    add(std::to_string(end->shift3)); add(f6(end->msi)); add(std::to_string(end->msint));
     add(end->leftseq.empty() ? "0" : end->leftseq); add(end->rightseq.empty() ? "0" : end->rightseq);
   } else {
     s += "\t\t\t\t\t";
@@ -99,9 +99,9 @@ inline std::string format_somatic(const VariantOut* begin, const VariantOut* end
   add(label);
   if (begin) add(begin->vartype);
   else s += "\t";
-  add(tumor ? std::to_string(0.0) : "0");  // duprate is forced to 0 by CigarParser::process (parseCigar.cpp:432)
+  add(tumor ? f6(0.0) : "0");  // duprate is forced to 0 by CigarParser::process (parseCigar.cpp:432)
   add("0");
-  add(normal ? std::to_string(0.0) : "0");
+  add(normal ? f6(0.0) : "0");
   add("0");
   if (fisher) {
     const int v1t = tumor ? tumor->tcov : 0, v1v = tumor ? tumor->cnt : 0, v2t = normal ? normal->tcov : 0, v2v = normal ? normal->cnt : 0;
@@ -111,8 +111,8 @@ inline std::string format_somatic(const VariantOut* begin, const VariantOut* end
     put_fisher_and_odds(s, v1v, tref, v2v, rref);
     const double tumor_vaf = tumor ? tumor->freq : 0, normal_vaf = normal ? normal->freq : 0;
     const double lo = std::log(std::max(tumor_vaf, 0.0001) / std::max(normal_vaf, 0.0001));
-    add(std::to_string(lo));
-    add(std::to_string(std::log((static_cast<float>(v1v) + 0.5) / (static_cast<float>(v2v) + 0.5))));
+    add(f6(lo));
+    add(f6(std::log((static_cast<float>(v1v) + 0.5) / (static_cast<float>(v2v) + 0.5))));
   }
   s += "\n";
   return s;

@@ -41,3 +41,12 @@ def test_fetch_ref_matches_fasta(built):
     fa = "".join(open(os.path.join(d, "ref.fa")).read().splitlines()[1:])
     got = rv.fetch_ref(os.path.join(d, "ref.fa"), "chrS1", 1234, 2345).decode()
     assert got == fa[1233:2345]
+
+
+def test_fixed_point_formatter_matches_libc(tmp_path):
+    """csrc/host/fmt.hpp (the %f replacement of the TSV writers) against std::to_string on 3 M values incl. ties."""
+    import subprocess
+    exe = str(tmp_path / "fmt_test")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(cases.ROOT, "tests", "tools", "fmt_test.cpp")], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-500:]
