@@ -251,7 +251,7 @@ def main():
                             max_regions=nreg + 8, halo=halo, max_events=max(1 << 20, bt.n_reads),
                             max_variants=3 * n_pos + 1024, max_patch=max(1 << 20, bt.n_reads // 2),
                             max_ref_bases=len(ref) + 64)
-    params = rv.default_params(fisher=1, has_bam2=1, candidates_only=1)
+    params = rv.default_params(fisher=1, has_bam2=1, candidates_only=2)
     ctx = rv.Context(local, params, lim)
     ctx.set_reference(1, ref)
 

@@ -61,7 +61,9 @@ typedef struct rv_params {
   uint8_t has_bam2;        /* somatic: second BAM present (ToVarsBuilder.cpp:170-175,213-233) */
   uint8_t candidates_only; /* scoring emits a position only if one of its variants passes the numeric part of
                               Variant::isGoodVar (freq, hicnt, pmean, qual, qratio: include/Variant.h:205-231) —
-                              exact for simple-mode output, which prints nothing else (simpleMode.cpp:176-190) */
+                              exact for simple-mode output, which prints nothing else (simpleMode.cpp:176-190).
+                              2 = the same cut, but only one bare (region, pos) record per passing position: the
+                              candidate list of the paired mode (see rv_score_positions) */
   uint8_t pad_[7];
 } rv_params;
 

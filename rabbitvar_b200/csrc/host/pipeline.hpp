@@ -338,7 +338,7 @@ inline int run_batch_somatic(rv_ctx* ctx, const rv_params& P_in, const ReadBatch
   double t5 = now_ms();
   // ---- pass A: candidate positions of either sample ----
   rv_params PA = P;
-  PA.candidates_only = 1;
+  PA.candidates_only = 2;  // positions only
   RV_STEP(rv_set_params(ctx, &PA));
   RV_STEP(rv_score(ctx));
   const rv_variant* vv;

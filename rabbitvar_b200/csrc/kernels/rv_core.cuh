@@ -23,6 +23,10 @@ enum { OP_M = 0, OP_I = 1, OP_D = 2, OP_N = 3, OP_S = 4, OP_H = 5, OP_P = 6, OP_
 static const int RV_MAX_OPS = 48;
 static const int CONF_LOWQUAL = 10;  // include/Configuration.h:14-27
 
+RV_HD int iceil(double x) {  // ceil() for thresholds in the int range
+  int i = (int)x;
+  return (double)i < x ? i + 1 : i;
+}
 RV_HD int c_op(uint32_t c) { return (int)(c & 0xf); }
 RV_HD int c_len(uint32_t c) { return (int)(c >> 4); }
 RV_HD uint32_t c_make(int len, int op) { return ((uint32_t)len << 4) | (uint32_t)op; }
@@ -672,7 +676,7 @@ RV_HD int lookahead_offset(const rv_params& P, const ReadView& rd, const RefView
   for (int vi = 0; vsn <= P.vext && vi < mlen; vi++) {
     char ch = rd.base(read_pos + vi);
     if (ch == 'N') break;
-    if ((double)rd.q(read_pos + vi) < P.goodq) break;
+    if (rd.q(read_pos + vi) < iceil(P.goodq)) break;  // integer q: q < g <=> q < ceil(g)
     if (n_break_mode == 1 && has_eq(ref, ref_pos + vi, 'N')) break;  // :1582 (before the has() test)
     if (ref.has(ref_pos + vi)) {
       char rc = ref.at(ref_pos + vi);
@@ -799,6 +803,8 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
   const int n_cigar = pr.n_cigar, nm = pr.nm, position = pr.position, rlen = pr.rlen, tlen = pr.tlen, mapq = pr.mapq;
   const bool dir = pr.dir;
   const bool fast_shape = pr.fast_shape && fast != (FastDesc*)0 && plain_hint != 0;
+  // qualities are integers: comparisons with the double thresholds are done on their ceilings
+  const int goodq_i = iceil(P.goodq), goodq5_i = iceil(P.goodq + 5);
   WalkState w;
   w.start = position;
   w.offset = 0;
@@ -1178,9 +1184,9 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
       Key ss;
       ss.clear();
       bool start_with_deletion = false;
-      while ((w.start + 1) >= R.start && (w.start + 1) <= R.end && (i + 1) < w.clen && (double)q >= P.goodq &&
+      while ((w.start + 1) >= R.start && (w.start + 1) <= R.end && (i + 1) < w.clen && q >= goodq_i &&
              has_ne(ref, w.start, rd.base(w.rp)) && ref.at(w.start) != 'N') {
-        if ((double)rd.q(w.rp + 1) < P.goodq + 5) break;
+        if (rd.q(w.rp + 1) < goodq5_i) break;
         char nuc = rd.base(w.rp + 1);
         if (nuc == 'N') break;
         if (has_eq(ref, w.start + 1, 'N')) break;
@@ -1203,7 +1209,7 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
             }
           }
           if (ssn == 0) break;
-          if ((double)rd.q(w.rp + ssn) < P.goodq + 5) break;
+          if (rd.q(w.rp + ssn) < goodq5_i) break;
           for (int ssi = 1; ssi <= ssn; ssi++) {
             ss.push(rd.base(w.rp + ssi));
             q += rd.q(w.rp + ssi);
@@ -1221,7 +1227,7 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
       }
       int ddlen = 0;
       bool near_end = P.local_realign && w.clen - i <= P.vext && ci + 1 < n_cigar && ref.has(w.start) &&
-                      (ss.n > 0 || rd.base(w.rp) != ref.at(w.start)) && (double)rd.q(w.rp) >= P.goodq;
+                      (ss.n > 0 || rd.base(w.rp) != ref.at(w.start)) && rd.q(w.rp) >= goodq_i;
       if (near_end && c_op(cg.op[ci + 1]) == OP_D) {
         // :779-846
         while (i + 1 < w.clen) {

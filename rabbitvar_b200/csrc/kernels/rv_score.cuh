@@ -384,6 +384,20 @@ RV_HDN void score_position(const rv_params& P, const rv_region& R, int region_id
         any = true;
     }
     if (!any) return;
+    if (P.candidates_only == 2) {
+      // the caller only wants to know WHERE something can be printed (paired mode: the join list of
+      // rv_score_positions): one record carrying region and position, no MSI / Fisher work
+      rv_variant o;
+      o.region = region_idx; o.pos = pos; o.cnt = o.fwd = o.rev = o.tcov = o.hicnt = o.hicov = o.ref_fwd = o.ref_rev = 0;
+      o.shift3 = o.msint = 0;
+      o.freq = o.pmean = o.qual = o.mapq = o.qratio = o.hifreq = o.extrafreq = o.nm = o.msi = 0;
+      o.pvalue = 1.0; o.oddratio = 0.0;
+      o.bias_ref = o.bias_var = o.pstd = o.qstd = o.is_ref = o.key_kind = o.pad = 0;
+      o.rank = 0;
+      o.key_id = 0;
+      out.emit(o);
+      return;
+    }
   }
   // collectReferenceVariants :730-1098 — numeric part; allele strings / genotype / flanks are host work
   int rfc = 0, rrc = 0;

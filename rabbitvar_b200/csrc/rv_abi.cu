@@ -90,6 +90,7 @@ struct DeviceSink {
   uint32_t* counts;  // region slice
   uint32_t* covtab;
   double goodq;
+  int goodq_i;  // ceil(goodq): integer qualities compare against it
   int kept_bases, n_kept, n_unsup, n_over, n_ev;
   uint32_t* pend_row;
   uint32_t pend_old, pend_mine;
@@ -110,7 +111,7 @@ struct DeviceSink {
     atomicAdd(row + RV_F_SUM_Q, (uint32_t)q);
     atomicAdd(row + RV_F_SUM_MAPQ, (uint32_t)mapq);
     if (nm) atomicAdd(row + RV_F_SUM_NM, (uint32_t)nm);
-    if ((double)q >= goodq) atomicAdd(row + RV_F_HI, 1u);
+    if (q >= goodq_i) atomicAdd(row + RV_F_HI, 1u);
     // pstd/qstd: "two observations differ" == "some observation differs from the first one recorded".
     // The compare-and-swap result is consumed one observation later (resolve), so its round trip to L2
     // overlaps the walk of the next base instead of stalling this one.
@@ -140,7 +141,7 @@ struct DeviceSink {
     atomicAdd(row + RV_F_SUM_Q, (uint32_t)(sign * q));
     atomicAdd(row + RV_F_SUM_MAPQ, (uint32_t)(sign * mapq));
     if (nm) atomicAdd(row + RV_F_SUM_NM, (uint32_t)(sign * nm));
-    if ((double)q >= goodq) atomicAdd(row + RV_F_HI, (uint32_t)sign);
+    if (q >= goodq_i) atomicAdd(row + RV_F_HI, (uint32_t)sign);
     // (a key only ever nets to zero after an M-path observation, whose STD word keeps it "existing")
   }
   __device__ __forceinline__ void cov(int pos) {
@@ -218,6 +219,7 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
   s.mute = false;
   s.pend = false;
   s.goodq = a.P.goodq;
+  s.goodq_i = iceil(a.P.goodq);
   const DevRegion* dr = a.regions;
   rv_read rd;
   rd.data_off16 = 0; rd.n_cigar = 0; rd.l_seq = 0; rd.pos = 0;
@@ -402,6 +404,7 @@ __global__ void __launch_bounds__(128) rv_walk_kernel(PileupArgs a) {
     s.covtab = a.cov + dr->tab_off;
     s.kept_bases = s.n_kept = s.n_unsup = s.n_over = s.n_ev = 0;
     s.goodq = a.P.goodq;
+    s.goodq_i = iceil(a.P.goodq);
     s.pend = false;
     s.mute = true;
     Prep pr;
