@@ -187,7 +187,7 @@ def run_reference_arm(args):
                          "sample": f"oracle/_ref/RabbitVar --th {cores}, first {n_tiles} tiles of config 2 (T+N), {bases} aligned bases"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -218,6 +218,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the one JSON line (NCCL's banner goes there otherwise)
         dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world)
     if not torch.cuda.is_available():
         raise rv.RabbitVarError("bench.py needs a GPU (there is no CPU path); use --impl reference for the CPU arm")
@@ -431,9 +432,14 @@ def main():
                                           "algorithmic_bytes_per_launch": alg_score}},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    # explicit teardown in a fixed order (nothing is left to interpreter shutdown, where CUDA may already be gone)
+    pipe.close()
     ctx.close()
+    del d_reads, d_pool
+    bt.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

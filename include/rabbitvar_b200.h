@@ -268,6 +268,9 @@ int rv_fetch_events(rv_ctx* ctx, const rv_event** events, int64_t* n_events);
 int rv_apply_patch(rv_ctx* ctx, const rv_patch_entry* entries, int64_t n_entries, const int32_t* cov_region,
                    const int32_t* cov_pos, const int32_t* cov_val, int64_t n_cov);
 int rv_fetch_variants(rv_ctx* ctx, const rv_variant** variants, int64_t* n_variants);
+/* Per region: sum of the coverage and number of covered positions over [start, end) (add_depth_by_region,
+ * somaticMode.cpp:69-81: the numbers behind the paired mode's <out>.info file).  Host arrays of n_regions. */
+int rv_cov_summary(rv_ctx* ctx, int64_t* sum, int64_t* covered);
 /* Number of records the last rv_score produced (no copy). */
 int64_t rv_variant_count(const rv_ctx* ctx);
 

@@ -114,7 +114,7 @@ ABI_SYMBOLS = [
     "rv_last_error", "rv_sync", "rv_ctx_halo", "rv_set_params", "rv_set_reference", "rv_push_reads", "rv_push_reads_range", "rv_push_reads_ranges", "rv_push_reads_device", "rv_set_regions",
     "rv_pileup", "rv_score", "rv_score_positions", "rv_get_pileup_stats", "rv_fetch_max_read_len", "rv_fetch_tables", "rv_fetch_rows",
     "rv_fetch_events",
-    "rv_apply_patch", "rv_fetch_variants", "rv_variant_count", "rv_fisher_exact", "rv_last_kernel_ms", "rv_last_pileup_split_ms", "rv_timer_start",
+    "rv_apply_patch", "rv_fetch_variants", "rv_cov_summary", "rv_variant_count", "rv_fisher_exact", "rv_last_kernel_ms", "rv_last_pileup_split_ms", "rv_timer_start",
     "rv_timer_stop", "rv_launch_count",
     "rvh_load_bam", "rvh_batch_append", "rvh_batch_n_reads", "rvh_batch_reads", "rvh_batch_pool",
     "rvh_batch_pool_bytes", "rvh_batch_max_ref_span", "rvh_batch_pin", "rvh_batch_free", "rvh_make_regions", "rvh_fetch_ref",
@@ -163,6 +163,7 @@ def _declare(L):
     L.rv_apply_patch.argtypes = [vp, vp, i64, vp, vp, vp, i64]
     L.rv_fetch_variants.argtypes = [vp, C.POINTER(C.POINTER(Variant)), C.POINTER(i64)]
     L.rv_fisher_exact.argtypes = [vp, vp, i64, vp]
+    L.rv_cov_summary.argtypes = [vp, vp, vp]
     L.rv_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.rv_last_pileup_split_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.rv_timer_start.argtypes = [vp]

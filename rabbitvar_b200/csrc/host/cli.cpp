@@ -175,6 +175,7 @@ struct Block {
   std::vector<RegionSpec> specs;  // same contig, ascending
   std::string tsv;
   int64_t bases = 0, reads = 0, lines = 0;
+  int64_t cov_sum[2] = {0, 0}, cov_pos[2] = {0, 0};
   double pileup_ms = 0, score_ms = 0;
   std::string err;
 };
@@ -259,6 +260,7 @@ static void worker(const Cli& c, int device, std::vector<Block*> blocks) {
       blk->bases = tm.stats.n_aligned_bases;
       blk->reads = tm.stats.n_reads_kept;
       blk->lines = tm.n_lines;
+      for (int k = 0; k < 2; ++k) { blk->cov_sum[k] = tm.cov_sum[k]; blk->cov_pos[k] = tm.cov_pos[k]; }
       blk->pileup_ms = tm.pileup_kernel_ms;
       blk->score_ms = tm.score_kernel_ms;
       if (tm.stats.n_unsupported)
@@ -320,6 +322,16 @@ int main(int argc, char** argv) {
     kms += b.pileup_ms + b.score_ms;
   }
   fclose(out);
+  if (!c.bam2.empty()) {  // SomaticMode::process, somaticMode.cpp:916-929: average coverages (both over the tumor's sites)
+    int64_t ts = 0, tp = 0, ns = 0;
+    for (auto& b : blocks) { ts += b.cov_sum[0]; tp += b.cov_pos[0]; ns += b.cov_sum[1]; }
+    FILE* info = fopen((c.out + ".info").c_str(), "wb");
+    if (info) {
+      const std::string s = std::to_string(ts / (double)tp) + "\n" + std::to_string(ns / (double)tp) + "\n";
+      fwrite(s.data(), 1, s.size(), info);
+      fclose(info);
+    }
+  }
   printf("[info] output file name: %s\n[info] regions: %zu blocks: %zu gpus: %d aligned bases: %lld variant lines: %lld kernel ms: %.3f\n",
          c.out.c_str(), specs.size(), blocks.size(), c.gpus, (long long)bases, (long long)lines, kms);
   printf("total time: %f s \n", (now_ms() - t0) / 1000.0);

@@ -20,6 +20,7 @@ struct BatchTiming {
   float pileup_kernel_ms, score_kernel_ms;
   rv_pileup_stats stats;
   int64_t n_variants, n_lines, h2d_bytes, d2h_bytes;
+  int64_t cov_sum[2], cov_pos[2];  // paired mode: coverage summary of the tumor / normal tiles (<out>.info)
 };
 
 inline double now_ms() {
@@ -362,6 +363,14 @@ inline int run_batch_somatic(rv_ctx* ctx, const rv_params& P_in, const ReadBatch
   t.d2h_bytes += nv * (int64_t)sizeof(rv_variant);
   t.h2d_bytes += (int64_t)qreg.size() * 8;
   RV_STEP(rv_set_params(ctx, &P_in));
+  {  // add_depth_by_region for both samples (somaticMode.cpp:101, :116)
+    std::vector<int64_t> cs(regs.size()), cp(regs.size());
+    RV_STEP(rv_cov_summary(ctx, cs.data(), cp.data()));
+    for (size_t r = 0; r < regs.size(); ++r) {
+      t.cov_sum[r < n ? 0 : 1] += cs[r];
+      t.cov_pos[r < n ? 0 : 1] += cp[r];
+    }
+  }
   double t6 = now_ms();
   std::vector<int64_t> rfirst(regs.size() + 1, nv);
   {

@@ -1186,6 +1186,29 @@ __global__ void __launch_bounds__(128) rv_score_list_kernel(ScoreArgs a, const i
   }
 }
 
+// Per-region coverage summary (add_depth_by_region, somaticMode.cpp:69-81): sum and number of covered positions
+// over [start, end) — the end is exclusive there.  One CTA per region.
+__global__ void rv_cov_summary_kernel(const DevRegion* regions, int n_regions, const uint32_t* cov, unsigned long long* out) {
+  const int r = blockIdx.x;
+  if (r >= n_regions) return;
+  const DevRegion* dr = regions + r;
+  unsigned long long sum = 0, cnt = 0;
+  for (int p = dr->r.start + (int)threadIdx.x; p < dr->r.end; p += (int)blockDim.x) {
+    const uint32_t c = cov[dr->tab_off + (p - dr->first_pos)];
+    if (c) { sum += c; cnt++; }
+  }
+  __shared__ unsigned long long sh[2];
+  if (threadIdx.x < 2) sh[threadIdx.x] = 0;
+  __syncthreads();
+  for (int off = 16; off > 0; off >>= 1) {
+    sum += __shfl_down_sync(0xffffffffu, sum, off);
+    cnt += __shfl_down_sync(0xffffffffu, cnt, off);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&sh[0], sum); atomicAdd(&sh[1], cnt); }
+  __syncthreads();
+  if (threadIdx.x == 0) { out[2 * r] = sh[0]; out[2 * r + 1] = sh[1]; }
+}
+
 __global__ void rv_lgamma_table_kernel(double* t, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) t[i] = lgamma((double)i + 1.0);
@@ -1986,6 +2009,24 @@ int rv_fetch_variants(rv_ctx* ctx, const rv_variant** variants, int64_t* n_varia
   }
   *variants = ctx->h_variants;
   *n_variants = (int64_t)n;
+  return RV_OK;
+}
+
+int rv_cov_summary(rv_ctx* ctx, int64_t* sum, int64_t* covered) {
+  if (!ctx || !sum || !covered) return RV_ERR_ARG;
+  const size_t n = ctx->regions.size();
+  if (n == 0) return RV_OK;
+  CK(cudaSetDevice(ctx->device));
+  int rcs = ensure_scratch(ctx, 16 * n + 64);
+  if (rcs != RV_OK) return rcs;
+  unsigned long long* d_out = (unsigned long long*)ctx->d_scratch;
+  rv_cov_summary_kernel<<<(unsigned)n, 256, 0, ctx->stream>>>(ctx->d_regions, (int)n, ctx->d_cov, d_out);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  std::vector<unsigned long long> h(2 * n);
+  CK(cudaMemcpyAsync(h.data(), d_out, 16 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (size_t r = 0; r < n; ++r) { sum[r] = (int64_t)h[2 * r]; covered[r] = (int64_t)h[2 * r + 1]; }
   return RV_OK;
 }
 

@@ -76,6 +76,10 @@ SOMATIC_CASES = {
 }
 
 
+# contents of the reference's <out>.info side file for the cases above (tests/golden/make_golden.py prints them)
+SOMATIC_INFO = {"c2_somatic_k1": (114.754443, 56.724382), "c2_somatic_bed_k0": (78.601912, 49.945043)}
+
+
 def dataset_dir(name):
     return os.path.join(WORK, name)
 

@@ -45,7 +45,7 @@ def main():
         lines = sorted(open(tsv).read().splitlines())
         with gzip.open(os.path.join(ROOT, "tests", "golden", name + ".tsv.gz"), "wt") as g:
             g.write("\n".join(lines) + "\n")
-        print(name, len(lines), "tsv lines")
+        print(name, len(lines), "tsv lines; .info =", open(tsv + ".info").read().split())
 
 
 if __name__ == "__main__":

@@ -83,6 +83,10 @@ def test_cli_somatic_tsv_matches_reference_output(built, name, tmp_path):
     assert len(got) == len(want), (len(got), len(want))
     bad = [(w, g) for w, g in zip(want, got) if w != g and not _tsv_equal(w, g)]
     assert not bad, bad[:3]
+    # the <out>.info side file: average coverage of the tumor and the normal sample
+    info = [float(x) for x in open(out + ".info").read().split()]
+    want_info = cases.SOMATIC_INFO[name]
+    assert len(info) == 2 and all(abs(a - b) <= 2e-6 * max(1.0, abs(b)) for a, b in zip(info, want_info)), (info, want_info)
 
 
 def test_tiled_bed_equals_per_tile_runs(built, tmp_path):
