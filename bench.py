@@ -71,6 +71,25 @@ class ClockSampler:
         self.t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
+        # NVML in-process (a sample every ~20 ms); nvidia-smi as the fallback
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = ((getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), 3), (getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40), 4),
+                    (getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), 5), (getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4), 6))
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop:
+                r = get_reasons(h)
+                row = [str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(sm_max), "0", "", "", "", ""]
+                for bit, i in bits:
+                    row[i] = "Active" if (r & bit) else "Not Active"
+                self.rows.append(row)
+                time.sleep(0.02)
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")

@@ -75,6 +75,7 @@ struct PileupArgs {
   int32_t* max_rl;
   DevStats* stats;
   GDesc* descs;          // one per work item
+  uint16_t* desc_mm;     // per work item: bit b set = the plain run has a mismatch in its bases [16b, 16b+16) (bit 15: and beyond)
   int32_t* reach;        // [0] = max(pos - m_start), [1] = max(m_start + m_len - pos) over the descriptors
   int force_exact;       // debugging: every read takes the exact walk
   // reads that need the exact CIGAR walk are not walked by the classifying kernel (one slow lane would stall
@@ -257,6 +258,7 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
            pr.nm <= 127 && pr.mapq <= 255;
   }
   bool plain = cand;
+  uint32_t mm_blocks = 0;
   if (cand) {
     const int D = a.P.vext + 1;
     const uint32_t* sq = (const uint32_t*)a.pool + seq_word;
@@ -293,6 +295,11 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
       }
       bad |= near | special;
       prev = nz;
+      if (nz) {  // 16-base blocks of the run this word's mismatches may lie in (a word touches at most two)
+        const int k_lo = 8 * wi - rp0 > 0 ? 8 * wi - rp0 : 0;
+        const int k_hi = 8 * wi + 7 - rp0 < ml - 1 ? 8 * wi + 7 - rp0 : ml - 1;
+        mm_blocks |= (1u << min(k_lo >> 4, 15)) | (1u << min(k_hi >> 4, 15));
+      }
     }
     plain = bad == 0;
   }
@@ -344,6 +351,7 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
       }
     }
     *(uint4*)(a.descs + item) = *(const uint4*)&gd;
+    a.desc_mm[item] = (uint16_t)mm_blocks;
   }
   // ---- statistics and the candidate-window bounds of the gather kernel: one atomic per warp / block ----
   unsigned long long kept = s.n_kept, bases = s.kept_bases, unsup = s.n_unsup, over = s.n_over;
@@ -444,6 +452,7 @@ struct GatherArgs {
   int n_regions;
   const rv_read* reads;
   const GDesc* descs;
+  const uint16_t* desc_mm;
   const uint8_t* pool;
   const char* ref;
   int32_t ref_start;
@@ -528,7 +537,9 @@ __global__ void __launch_bounds__(GATHER_TILE, 5) rv_gather_kernel(GatherArgs a)
   uint32_t n_ref = 0, n_rev = 0, sum_tp = 0, sum_q = 0, sum_mapq = 0, sum_nm = 0, n_hi = 0;
   uint32_t v_and = 0xffffffffu, v_or = 0, v_last = 0, n_other = 0, other_mask = 0;
   const GDesc* item_desc = a.descs + (dr->item_base - dr->r.read_lo);  // descriptor of read index i
+  const uint16_t* item_mm = a.desc_mm + (dr->item_base - dr->r.read_lo);
   const uint4* pool16 = (const uint4*)a.pool;
+  const uint32_t wbit = 1u << (18 + warp);  // this warp's "decode the bases" flag in a staged record
   // lane constants of the byte lookups: seq byte = offset + ((x + par) >> 1), qual byte = offset + x
   const int xs0 = (x >> 1) - REC_BIAS, xs1 = ((x + 1) >> 1) - REC_BIAS, xq = x - REC_BIAS;
 
@@ -539,7 +550,11 @@ __global__ void __launch_bounds__(GATHER_TILE, 5) rv_gather_kernel(GatherArgs a)
     const int64_t i = base + tid;
     GDesc d;
     d.m_len = 0;
-    if (i < hi) *(uint4*)&d = *(const uint4*)(item_desc + i);
+    uint32_t mm = 0;
+    if (i < hi) {
+      *(uint4*)&d = *(const uint4*)(item_desc + i);
+      mm = item_mm[i];
+    }
     bool take = false;
     int ns = 0, nq = 0, n_lo = 0;
     size_t s_first = 0, q_first = 0;
@@ -587,16 +602,21 @@ __global__ void __launch_bounds__(GATHER_TILE, 5) rv_gather_kernel(GatherArgs a)
       const int par = n0 & 1;
       const int so = chunk0 * 16 + (int)(s_first & 15) - (n_lo >> 1) + ((n0 - par) >> 1) + REC_BIAS;
       const int qo = (chunk0 + ns) * 16 + (int)(q_first & 15) - n_lo + n0 + REC_BIAS;
-      s_rec[slot] = make_uint4((uint32_t)rel_start, (uint32_t)so | ((uint32_t)qo << 16),
-                               (uint32_t)d.m_len | ((uint32_t)par << 16) | ((uint32_t)(d.dir_nm >> 7) << 17),
-                               (uint32_t)d.mapq | ((uint32_t)(d.dir_nm & 0x7f) << 16));
       s_copy[slot] = make_uint4((uint32_t)(s_first >> 4), (uint32_t)(q_first >> 4), (uint32_t)(ns | (nq << 8)), (uint32_t)chunk0);
       const int x_lo = rel_start > c_lo - p_lo ? rel_start : c_lo - p_lo;
       const int x_hi = rel_start + (int)d.m_len - 1 < c_hi - p_lo ? rel_start + (int)d.m_len - 1 : c_hi - p_lo;
+      uint32_t wbits = 0;  // warps whose 32 positions see a 16-base block of the run with a mismatch in it
       for (int w = x_lo >> 5; w <= (x_hi >> 5); ++w) {
         if (slot < s_wlo[w]) atomicMin(&s_wlo[w], slot);
         if (slot + 1 > s_whi[w]) atomicMax(&s_whi[w], slot + 1);
+        const int kw_lo = 32 * w - rel_start > 0 ? 32 * w - rel_start : 0;
+        const int kw_hi = 32 * w + 31 - rel_start < (int)d.m_len - 1 ? 32 * w + 31 - rel_start : (int)d.m_len - 1;
+        const int bl = min(kw_lo >> 4, 15), bh = min(kw_hi >> 4, 15);
+        if (mm & (((2u << (bh - bl)) - 1u) << bl)) wbits |= 1u << w;
       }
+      s_rec[slot] = make_uint4((uint32_t)rel_start, (uint32_t)so | ((uint32_t)qo << 16),
+                               (uint32_t)d.m_len | ((uint32_t)par << 16) | ((uint32_t)(d.dir_nm >> 7) << 17) | (wbits << 18),
+                               (uint32_t)d.mapq | ((uint32_t)(d.dir_nm & 0x7f) << 16));
     }
     __syncthreads();
     // ---- 2. stage the bytes: one warp per read, one 16-byte chunk per lane, asynchronous copies ---------
@@ -624,9 +644,14 @@ __global__ void __launch_bounds__(GATHER_TILE, 5) rv_gather_kernel(GatherArgs a)
         const int k = x - (int)r.x;
         if ((unsigned)k >= (unsigned)m_len) continue;
         const uint32_t q = s_arena[(int)(r.y >> 16) + xq];
-        const bool odd = (r.z >> 16) & 1;  // parity of the read offset under tile coordinate 0
-        const int sbyte = s_arena[(int)(r.y & 0xffffu) + (odd ? xs1 : xs0)];
-        const int nib = ((x ^ (int)odd) & 1) ? (sbyte & 15) : (sbyte >> 4);
+        int nib = refnib;
+        if (r.z & wbit) {
+          // (warp-uniform: the record is broadcast) some base of the run under this warp differs from the reference:
+          // decode the lane's base.  Otherwise the classify kernel has proven it equal to the reference base.
+          const bool odd = (r.z >> 16) & 1;  // parity of the read offset under tile coordinate 0
+          const int sbyte = s_arena[(int)(r.y & 0xffffu) + (odd ? xs1 : xs0)];
+          nib = ((x ^ (int)odd) & 1) ? (sbyte & 15) : (sbyte >> 4);
+        }
         const uint32_t tp = (uint32_t)min(k + 1, m_len - k);
         const uint32_t v = tp | (q << 16);
         const uint32_t hiq = (int)q >= thr ? 1u : 0u;
@@ -1284,6 +1309,7 @@ struct rv_ctx {
   double* d_lgt;
   int lgt_n;
   GDesc* d_descs;
+  uint16_t* d_desc_mm;
   int32_t* d_reach;
   uint32_t* d_ref4;
   int64_t* d_tile_range;
@@ -1404,7 +1430,7 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   ctx->launches = 0;
   ctx->d_reads = NULL; ctx->d_pool = NULL; ctx->d_ref = NULL; ctx->d_counts = NULL; ctx->d_cov = NULL;
   ctx->d_events = NULL; ctx->d_variants = NULL; ctx->d_patch = NULL; ctx->d_patch_first = NULL;
-  ctx->d_patch_count = NULL; ctx->d_regions = NULL; ctx->d_max_rl = NULL; ctx->d_stats = NULL; ctx->d_lgt = NULL; ctx->d_descs = NULL; ctx->d_reach = NULL; ctx->d_ref4 = NULL; ctx->d_tile_range = NULL; ctx->tile_cap = 0; ctx->d_patched_queue = NULL; ctx->d_patched_count = NULL; ctx->d_walk_queue = NULL; ctx->d_walk_count = NULL; ctx->n_tiles = 0;
+  ctx->d_patch_count = NULL; ctx->d_regions = NULL; ctx->d_max_rl = NULL; ctx->d_stats = NULL; ctx->d_lgt = NULL; ctx->d_descs = NULL; ctx->d_desc_mm = NULL; ctx->d_reach = NULL; ctx->d_ref4 = NULL; ctx->d_tile_range = NULL; ctx->tile_cap = 0; ctx->d_patched_queue = NULL; ctx->d_patched_count = NULL; ctx->d_walk_queue = NULL; ctx->d_walk_count = NULL; ctx->n_tiles = 0;
   ctx->use_gather = getenv("RV_NO_GATHER") == NULL;
   ctx->gather_ws = getenv("RV_GATHER_WS") && atoi(getenv("RV_GATHER_WS")) == 1;
   ctx->h_counts = NULL; ctx->h_cov = NULL; ctx->h_tab_cap = 0; ctx->h_events = NULL; ctx->h_events_cap = 0;
@@ -1437,6 +1463,7 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   CK(cudaMalloc(&ctx->d_stats, sizeof(DevStats)));
   // work items are (region, read) pairs: a read overlapping two tiles is walked once per tile
   CK(cudaMalloc(&ctx->d_descs, sizeof(GDesc) * (size_t)(2 * L.max_reads + 1024)));
+  CK(cudaMalloc(&ctx->d_desc_mm, sizeof(uint16_t) * (size_t)(2 * L.max_reads + 1024)));
   CK(cudaMalloc(&ctx->d_reach, 2 * sizeof(int32_t)));
   CK(cudaMalloc(&ctx->d_ref4, sizeof(uint32_t) * (size_t)(L.max_ref_bases / 8 + 16)));
   // gather tiles: every region rounds its table (length + 2*halo) up to whole tiles
@@ -1467,6 +1494,7 @@ void rv_destroy(rv_ctx* ctx) {
   cudaFree(ctx->d_lgt);
   cudaFree(ctx->d_scratch);
   cudaFree(ctx->d_descs);
+  cudaFree(ctx->d_desc_mm);
   cudaFree(ctx->d_reach);
   cudaFree(ctx->d_ref4);
   cudaFree(ctx->d_tile_range);
@@ -1656,6 +1684,7 @@ int rv_pileup(rv_ctx* ctx) {
   a.max_rl = ctx->d_max_rl;
   a.stats = ctx->d_stats;
   a.descs = ctx->d_descs;
+  a.desc_mm = ctx->d_desc_mm;
   a.reach = ctx->d_reach;
   a.force_exact = ctx->use_gather ? 0 : 1;
   a.walk_queue = ctx->d_walk_queue;
@@ -1674,6 +1703,7 @@ int rv_pileup(rv_ctx* ctx) {
     g.n_regions = (int)ctx->regions.size();
     g.reads = ctx->reads_dev_view;
     g.descs = ctx->d_descs;
+    g.desc_mm = ctx->d_desc_mm;
     g.pool = ctx->pool_dev_view;
     g.ref = ctx->d_ref;
     g.ref_start = ctx->ref_start;
