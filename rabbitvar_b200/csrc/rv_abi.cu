@@ -534,14 +534,15 @@ __global__ void __launch_bounds__(GATHER_TILE, 5) rv_gather_kernel(GatherArgs a)
   const int thr = (int)ceil(a.goodq);  // integer q >= goodq
   const int64_t t_row = dr->tab_off + (p - dr->first_pos);
   uint32_t* const row0 = a.counts + (size_t)t_row * RV_POS_U32;
-  uint32_t n_ref = 0, n_rev = 0, sum_tp = 0, sum_q = 0, sum_mapq = 0, sum_nm = 0, n_hi = 0;
-  uint32_t v_and = 0xffffffffu, v_or = 0, v_last = 0, n_other = 0, other_mask = 0;
+  uint32_t n_ref = 0, n_rev = 0, sum_tp = 0, sum_q = 0, sum_mapq = 0, sum_nm = 0;
+  uint32_t v_and = 0xffffffffu, v_or = 0, n_other = 0, other_mask = 0;
+  int n_lowq = 0;  // minus the number of reference-allele observations below the quality threshold
   const GDesc* item_desc = a.descs + (dr->item_base - dr->r.read_lo);  // descriptor of read index i
   const uint16_t* item_mm = a.desc_mm + (dr->item_base - dr->r.read_lo);
   const uint4* pool16 = (const uint4*)a.pool;
   const uint32_t wbit = 1u << (18 + warp);  // this warp's "decode the bases" flag in a staged record
   // lane constants of the byte lookups: seq byte = offset + ((x + par) >> 1), qual byte = offset + x
-  const int xs0 = (x >> 1) - REC_BIAS, xs1 = ((x + 1) >> 1) - REC_BIAS, xq = x - REC_BIAS;
+  const int xq = x - REC_BIAS;
 
   for (int64_t base = lo; base < hi;) {
     // ---- 1. descriptors of this round, clipped to the tile ------------------------------------------
@@ -649,12 +650,11 @@ __global__ void __launch_bounds__(GATHER_TILE, 5) rv_gather_kernel(GatherArgs a)
           // (warp-uniform: the record is broadcast) some base of the run under this warp differs from the reference:
           // decode the lane's base.  Otherwise the classify kernel has proven it equal to the reference base.
           const bool odd = (r.z >> 16) & 1;  // parity of the read offset under tile coordinate 0
-          const int sbyte = s_arena[(int)(r.y & 0xffffu) + (odd ? xs1 : xs0)];
+          const int sbyte = s_arena[(int)(r.y & 0xffffu) - REC_BIAS + ((x + (int)odd) >> 1)];
           nib = ((x ^ (int)odd) & 1) ? (sbyte & 15) : (sbyte >> 4);
         }
         const uint32_t tp = (uint32_t)min(k + 1, m_len - k);
         const uint32_t v = tp | (q << 16);
-        const uint32_t hiq = (int)q >= thr ? 1u : 0u;
         const uint32_t dir = (r.z >> 17) & 1u;
         if (nib == refnib) {
           n_ref++;
@@ -662,12 +662,12 @@ __global__ void __launch_bounds__(GATHER_TILE, 5) rv_gather_kernel(GatherArgs a)
           sum_tp += tp;
           sum_q += q;
           add_acc += r.w;
-          n_hi += hiq;
+          n_lowq += ((int)q - thr) >> 31;  // -1 below the threshold
           v_and &= v;
           v_or |= v;
-          v_last = v;
         } else {
           // a base that differs from the reference: the lane's own row of that allele, read-modify-write
+          const uint32_t hiq = (int)q >= thr ? 1u : 0u;
           const int al = nib_allele(nib);
           uint4* row4 = (uint4*)(row0 + al * RV_ROW_U32);
           uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
@@ -703,10 +703,12 @@ __global__ void __launch_bounds__(GATHER_TILE, 5) rv_gather_kernel(GatherArgs a)
     uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
     if (al == a0 && n_ref) {
       ra = make_uint4(n_ref - n_rev, n_rev, sum_tp, sum_q);
-      uint32_t w = v_last | (1u << 31);
+      // the recorded (tp, q): a field of the AND-reduction is the common value whenever that field's flag stays
+      // clear, and is never looked at again once the flag is set
+      uint32_t w = (v_and & 0xffffffu) | (1u << 31);
       if ((v_and ^ v_or) & 0xffffu) w |= 1u << 24;
       if ((v_and ^ v_or) & 0xff0000u) w |= 1u << 25;
-      rb = make_uint4(sum_mapq, sum_nm, n_hi, w);
+      rb = make_uint4(sum_mapq, sum_nm, n_ref + (uint32_t)n_lowq, w);
     }
     uint4* row4 = (uint4*)(row0 + al * RV_ROW_U32);
     row4[0] = ra;
