@@ -80,8 +80,11 @@ struct PileupArgs {
   int force_exact;       // debugging: every read takes the exact walk
   // reads that need the exact CIGAR walk are not walked by the classifying kernel (one slow lane would stall
   // its 31 neighbours): their work item goes to this queue and rv_walk_kernel runs them densely packed
+  // Whole-read walks fill the queue from the front, soft-clip-only walks (WALK_PLAIN_DONE) from the back, so that the
+  // lanes of a warp of rv_walk_kernel run the same kind of walk side by side.
   unsigned long long* walk_queue;   // item | WALK_PLAIN_DONE
-  unsigned long long* walk_count;
+  unsigned long long* walk_count;   // [0] whole-read entries, [1] soft-clip-only entries
+  unsigned long long walk_cap;
 };
 static const unsigned long long WALK_PLAIN_DONE = 1ull << 62;  // the matched run already left a descriptor
 
@@ -343,11 +346,12 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
         }
       }
       if (queue) {
-        cg::coalesced_group g = cg::coalesced_threads();
+        const int kind = (entry & WALK_PLAIN_DONE) ? 1 : 0;
+        cg::coalesced_group g = cg::labeled_partition(cg::coalesced_threads(), kind);
         unsigned long long slot = 0;
-        if (g.thread_rank() == 0) slot = atomicAdd(a.walk_count, (unsigned long long)g.size());
+        if (g.thread_rank() == 0) slot = atomicAdd(a.walk_count + kind, (unsigned long long)g.size());
         slot = g.shfl(slot, 0) + g.thread_rank();
-        a.walk_queue[slot] = entry;
+        a.walk_queue[kind ? a.walk_cap - 1 - slot : slot] = entry;
       }
     }
     *(uint4*)(a.descs + item) = *(const uint4*)&gd;
@@ -385,12 +389,12 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
 
 // The exact CIGAR walk for the queued work items, one per thread (all lanes busy with walks).
 __global__ void __launch_bounds__(128) rv_walk_kernel(PileupArgs a) {
-  const unsigned long long n = *a.walk_count;
+  const unsigned long long n_full = a.walk_count[0], n = n_full + a.walk_count[1];
   unsigned long long over = 0, unsup = 0, full = 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) a.stats->n_walk_items = n;
   for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < n;
        q += (unsigned long long)gridDim.x * blockDim.x) {
-    const unsigned long long entry = a.walk_queue[q];
+    const unsigned long long entry = a.walk_queue[q < n_full ? q : a.walk_cap - 1 - (q - n_full)];
     const int64_t item = (int64_t)(entry & ~WALK_PLAIN_DONE);
     const bool plain_done = (entry & WALK_PLAIN_DONE) != 0;
     if (!plain_done) full++;
@@ -1475,7 +1479,7 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   CK(cudaMalloc(&ctx->d_patched_queue, sizeof(int64_t) * (size_t)(L.max_positions + 1)));
   CK(cudaMalloc(&ctx->d_patched_count, sizeof(unsigned long long)));
   CK(cudaMalloc(&ctx->d_walk_queue, sizeof(unsigned long long) * (size_t)(2 * L.max_reads + 1024)));
-  CK(cudaMalloc(&ctx->d_walk_count, sizeof(unsigned long long)));
+  CK(cudaMalloc(&ctx->d_walk_count, 2 * sizeof(unsigned long long)));
   CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->stream));
   ctx->lgt_n = 1 << 20;
   CK(cudaMalloc(&ctx->d_lgt, sizeof(double) * (size_t)ctx->lgt_n));
@@ -1666,7 +1670,7 @@ int rv_pileup(rv_ctx* ctx) {
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   // no table memset: rv_gather_kernel stores every row (halo included) before rv_walk_kernel adds to them
   CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->stream));
-  CK(cudaMemsetAsync(ctx->d_walk_count, 0, sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_walk_count, 0, 2 * sizeof(unsigned long long), ctx->stream));
   CK(cudaMemsetAsync(ctx->d_reach, 0, 2 * sizeof(int32_t), ctx->stream));
   PileupArgs a;
   a.P = ctx->P;
@@ -1691,6 +1695,7 @@ int rv_pileup(rv_ctx* ctx) {
   a.force_exact = ctx->use_gather ? 0 : 1;
   a.walk_queue = ctx->d_walk_queue;
   a.walk_count = ctx->d_walk_count;
+  a.walk_cap = (unsigned long long)(2 * ctx->L.max_reads + 1024);
   if (ctx->n_items > 0) {
     unsigned grid = (unsigned)((ctx->n_items + 127) / 128);
     rv_pileup_kernel<<<grid, 128, 0, ctx->stream>>>(a);
