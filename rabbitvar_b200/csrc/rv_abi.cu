@@ -308,6 +308,8 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
   }
   // ---- stage 3: descriptor for plain matched runs; everything else is queued for rv_walk_kernel -----
   int back = 0, reach = 0;
+  int queue_kind = -1;  // 0: whole-read walk, 1: soft clips of a plain read
+  unsigned long long queue_entry = 0;
   if (item < a.n_items) {
     GDesc gd;
     gd.m_start = 0; gd.m_len = 0; gd.rp0 = 0; gd.seq_off4 = 0; gd.l_seq = 0; gd.mapq = 0; gd.dir_nm = 0;
@@ -346,12 +348,8 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
         }
       }
       if (queue) {
-        const int kind = (entry & WALK_PLAIN_DONE) ? 1 : 0;
-        cg::coalesced_group g = cg::labeled_partition(cg::coalesced_threads(), kind);
-        unsigned long long slot = 0;
-        if (g.thread_rank() == 0) slot = atomicAdd(a.walk_count + kind, (unsigned long long)g.size());
-        slot = g.shfl(slot, 0) + g.thread_rank();
-        a.walk_queue[kind ? a.walk_cap - 1 - slot : slot] = entry;
+        queue_kind = (entry & WALK_PLAIN_DONE) ? 1 : 0;
+        queue_entry = entry;
       }
     }
     *(uint4*)(a.descs + item) = *(const uint4*)&gd;
@@ -367,9 +365,26 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
     back = max(back, __shfl_down_sync(0xffffffffu, back, off));
     reach = max(reach, __shfl_down_sync(0xffffffffu, reach, off));
   }
+  // queue slots: one atomic per CTA and kind, entries of a CTA stay together in item order, so that neighbouring
+  // lanes of rv_walk_kernel walk neighbouring reads (same indel site, same CIGAR shape: the lanes stay in step)
   __shared__ unsigned long long sh[4];
+  __shared__ unsigned s_qcnt[2][4];
+  __shared__ unsigned long long s_qbase[2];
+  const unsigned b0 = __ballot_sync(0xffffffffu, queue_kind == 0), b1 = __ballot_sync(0xffffffffu, queue_kind == 1);
+  if (lane == 0) { s_qcnt[0][threadIdx.x >> 5] = __popc(b0); s_qcnt[1][threadIdx.x >> 5] = __popc(b1); }
   if (threadIdx.x < 4) sh[threadIdx.x] = 0;
   __syncthreads();
+  if (threadIdx.x < 2) {
+    const unsigned tot = s_qcnt[threadIdx.x][0] + s_qcnt[threadIdx.x][1] + s_qcnt[threadIdx.x][2] + s_qcnt[threadIdx.x][3];
+    s_qbase[threadIdx.x] = tot ? atomicAdd(a.walk_count + threadIdx.x, (unsigned long long)tot) : 0ull;
+  }
+  __syncthreads();
+  if (queue_kind >= 0) {
+    unsigned long long slot = s_qbase[queue_kind];
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) slot += s_qcnt[queue_kind][w];
+    slot += __popc((queue_kind ? b1 : b0) & ((1u << lane) - 1u));
+    a.walk_queue[queue_kind ? a.walk_cap - 1 - slot : slot] = queue_entry;
+  }
   if (lane == 0) {
     if (kept) atomicAdd(&sh[0], kept);
     if (bases) atomicAdd(&sh[1], bases);
