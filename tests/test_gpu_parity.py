@@ -29,6 +29,20 @@ def test_cuda_path_matches_golden(built, name, tmp_path):
     assert not problems, problems[:5]
 
 
+@pytest.mark.parametrize("env", [{"RV_GATHER_WS": "1"}, {"RV_NO_GATHER": "1"}])
+def test_alternative_kernel_paths_match_golden(built, env, tmp_path):
+    """The opt-in kernel variants must stay exact too: the warp-specialised gather kernel (RV_GATHER_WS=1) and the
+    all-reads-through-the-exact-walk path (RV_NO_GATHER=1, the debugging reference for the gather path)."""
+    name = "c5_k1"
+    c = cases.CASES[name]
+    cases.generate(name)
+    got = str(tmp_path / "gpu.txt")
+    run(cases.dump_cmd(name, "gpu", got, "C"), env=dict(os.environ, **env))
+    want = unpack_golden(name, "dump.txt", str(tmp_path / "golden.txt"))
+    n, problems = dumpcmp.compare(want, got, ["C."])
+    assert n > 1000 and not problems, problems[:5]
+
+
 @pytest.mark.parametrize("name", ["c1_k1", "c5_k1"])
 def test_cuda_path_matches_reference_binary_run_here(built, ref_tools, name, tmp_path):
     if ref_tools is None:
