@@ -279,7 +279,9 @@ def main():
     reads_np = bt.reads_numpy()
     pool_np = bt.pool_numpy()
     d_reads = torch.from_numpy(reads_np).to(dev)
-    d_pool = torch.from_numpy(pool_np).to(dev)
+    # rv_push_reads_device: the pool buffer extends 32 readable bytes beyond pool_bytes (look-ahead loads of the gather kernel)
+    d_pool = torch.zeros(int(pool_np.size) + 32, dtype=torch.uint8, device=dev)
+    d_pool[: int(pool_np.size)].copy_(torch.from_numpy(pool_np))
     torch.cuda.synchronize()
     read_bytes_total = int(reads_np.size + pool_np.size)
     avg_read_bytes = 32 + float((pool_np.size) / max(1, bt.n_reads))  # 32 B header + cigar + packed seq + qual (16 B aligned)

@@ -224,7 +224,8 @@ int rv_push_reads_range(rv_ctx* ctx, const rv_read_batch* batch, int64_t read_lo
  * every region must lie inside one of them. */
 int rv_push_reads_ranges(rv_ctx* ctx, const rv_read_batch* batch, int32_t n_ranges, const int64_t* read_lo,
                          const int64_t* read_hi);
-/* Same, from buffers already resident on the device (all pointers are device pointers; 16-byte aligned pool). */
+/* Same, from buffers already resident on the device (all pointers are device pointers; 16-byte aligned pool whose
+ * allocation extends at least 32 readable bytes beyond pool_bytes: the gather kernel's look-ahead loads stop there). */
 int rv_push_reads_device(rv_ctx* ctx, const rv_read_batch* batch);
 /* Regions of this batch. */
 int rv_set_regions(rv_ctx* ctx, const rv_region* regions, int32_t n_regions);

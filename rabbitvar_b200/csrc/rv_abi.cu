@@ -76,6 +76,8 @@ struct PileupArgs {
   DevStats* stats;
   GDesc* descs;          // one per work item
   uint16_t* desc_mm;     // per work item: bit b set = the plain run has a mismatch in its bases [16b, 16b+16) (bit 15: and beyond)
+  uint4* desc_mml;       // per work item with desc_mm != 0: the run's mismatches, up to 8 entries of 16 bits,
+                         // 0x8000 | run offset << 2 | allele of the read base (rv_gather4_kernel)
   int32_t* reach;        // [0] = max(pos - m_start), [1] = max(m_start + m_len - pos) over the descriptors
   int force_exact;       // debugging: every read takes the exact walk
   // reads that need the exact CIGAR walk are not walked by the classifying kernel (one slow lane would stall
@@ -180,6 +182,8 @@ __device__ __forceinline__ int find_region(const DevRegion* regs, int n, int64_t
   return lo;
 }
 
+__device__ __forceinline__ int nib_allele(int nib) { return (nib >> 1) - (nib >> 3); }  // 1,2,4,8 -> 0,1,2,3
+
 // bit 0 of every nibble = OR of the nibble's four bits
 __device__ __forceinline__ uint32_t nib_any(uint32_t x) { return (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u; }
 
@@ -258,10 +262,12 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
     const int64_t w_lo = ref.lo > a.ref_start ? ref.lo : a.ref_start;
     const int64_t w_hi = (int64_t)ref.hi < a.ref_start + a.ref_n - 1 ? (int64_t)ref.hi : a.ref_start + a.ref_n - 1;
     cand = pr.m_len > 0 && E0 >= 0 && pr.m_start >= w_lo && (int64_t)pr.m_start + pr.m_len - 1 <= w_hi && pr.nm >= 0 &&
-           pr.nm <= 127 && pr.mapq <= 255;
+           pr.nm <= 127 && pr.mapq <= 255 && pr.m_len <= 8192;
   }
   bool plain = cand;
   uint32_t mm_blocks = 0;
+  unsigned long long ml_lo = 0, ml_hi = 0;  // the run's mismatches, 16 bits each (newest in the low bits)
+  int ml_n = 0;
   if (cand) {
     const int D = a.P.vext + 1;
     const uint32_t* sq = (const uint32_t*)a.pool + seq_word;
@@ -302,9 +308,17 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
         const int k_lo = 8 * wi - rp0 > 0 ? 8 * wi - rp0 : 0;
         const int k_hi = 8 * wi + 7 - rp0 < ml - 1 ? 8 * wi + 7 - rp0 : ml - 1;
         mm_blocks |= (1u << min(k_lo >> 4, 15)) | (1u << min(k_hi >> 4, 15));
+        for (uint32_t z = nz; z;) {  // the mismatches themselves: base 8*wi + i has its flag at bit 28 - 4i
+          const int i = __clz(z) >> 2;
+          z &= ~(0x10000000u >> (4 * i));
+          const uint32_t e = 0x8000u | ((uint32_t)(8 * wi + i - rp0) << 2) | ((uint32_t)nib_allele((b8 >> (28 - 4 * i)) & 15u) & 3u);
+          ml_hi = (ml_hi << 16) | (ml_lo >> 48);
+          ml_lo = (ml_lo << 16) | e;
+          ml_n++;
+        }
       }
     }
-    plain = bad == 0;
+    plain = bad == 0 && ml_n <= 8;
   }
   // ---- stage 3: descriptor for plain matched runs; everything else is queued for rv_walk_kernel -----
   int back = 0, reach = 0;
@@ -354,6 +368,8 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
     }
     *(uint4*)(a.descs + item) = *(const uint4*)&gd;
     a.desc_mm[item] = (uint16_t)mm_blocks;
+    if (mm_blocks && plain)
+      a.desc_mml[item] = make_uint4((uint32_t)ml_lo, (uint32_t)(ml_lo >> 32), (uint32_t)ml_hi, (uint32_t)(ml_hi >> 32));
   }
   // ---- statistics and the candidate-window bounds of the gather kernel: one atomic per warp / block ----
   unsigned long long kept = s.n_kept, bases = s.kept_bases, unsup = s.n_unsup, over = s.n_over;
@@ -481,6 +497,10 @@ struct GatherArgs {
   const int32_t* reach;
   int64_t* tile_range;  // [2 * tile]: first candidate read of the tile; number of candidates | region << 32
   int64_t n_tiles;
+  int tile;             // table positions per tile (GATHER_TILE, or G4_W for rv_gather4_kernel)
+  const uint4* desc_mml;
+  int64_t pool_bytes;   // bytes of the device pool (rv_gather4_kernel clamps its look-ahead loads to it)
+  int thr;              // ceil(goodq)
 };
 
 __device__ __forceinline__ int find_region_by_tile(const DevRegion* regs, int n, int64_t tile) {
@@ -499,9 +519,9 @@ __global__ void rv_tile_index_kernel(GatherArgs a) {
   if (tile >= a.n_tiles) return;
   const int ri = find_region_by_tile(a.regions, a.n_regions, tile);
   const DevRegion* dr = a.regions + ri;
-  const int p_lo = dr->first_pos + (int)(tile - dr->tile_base) * GATHER_TILE;
+  const int p_lo = dr->first_pos + (int)(tile - dr->tile_base) * a.tile;
   const int c_lo = p_lo > dr->r.start ? p_lo : dr->r.start;
-  const int c_hi = p_lo + GATHER_TILE - 1 < dr->r.end ? p_lo + GATHER_TILE - 1 : dr->r.end;
+  const int c_hi = p_lo + a.tile - 1 < dr->r.end ? p_lo + a.tile - 1 : dr->r.end;
   int64_t lo = dr->r.read_lo, hi = dr->r.read_lo;
   if (c_lo <= c_hi) {
     const int want_lo = c_lo - a.reach[1];  // pos > want_lo
@@ -517,8 +537,6 @@ __global__ void rv_tile_index_kernel(GatherArgs a) {
   a.tile_range[2 * tile] = lo;
   a.tile_range[2 * tile + 1] = (int64_t)(((unsigned long long)(unsigned)ri << 32) | (unsigned)(hi - lo));
 }
-
-__device__ __forceinline__ int nib_allele(int nib) { return (nib >> 1) - (nib >> 3); }  // 1,2,4,8 -> 0,1,2,3
 
 static const int REC_BIAS = 256;  // keeps the arena byte offsets of a staged read non-negative 16-bit numbers
 
@@ -730,6 +748,281 @@ __global__ void __launch_bounds__(GATHER_TILE, 5) rv_gather_kernel(GatherArgs a)
       rb = make_uint4(sum_mapq, sum_nm, n_ref + (uint32_t)n_lowq, w);
     }
     uint4* row4 = (uint4*)(row0 + al * RV_ROW_U32);
+    row4[0] = ra;
+    row4[1] = rb;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rv_gather4_kernel — the plain matched runs, four table positions per lane.
+// A WARP owns G4_W = 128 consecutive table positions (lane l: positions 4l..4l+3); warps share nothing, so the
+// kernel has no CTA barrier.  What a plain run adds to the reference allele of a position splits in two:
+//   * per-read constants (count, reverse count, mapq, nm) and tp = min(k+1, L-k), a tent over the run: range adds /
+//     second-order differences into per-warp shared-memory arrays, 2-5 shared atomics per (read, warp), prefix-summed
+//     once per tile;
+//   * what depends on the base quality (sum, high-quality count) and the "all observations equal" tests of pstd/qstd
+//     (AND- and OR-reductions of tp and q): one pass over the warp's reads with byte / halfword SIMD in registers:
+//     tp of two positions per VIADDMNMX.S16x2.RELU (0 = the read does not cover the position), the four qualities
+//     as one unaligned 32-bit word (two LDG.32 + PRMT, prefetched G4_PF records ahead).
+// Mismatching bases (listed by the classify kernel, rv_pileup_kernel: desc_mml) are handled by the lane that owns
+// the READ while it builds the record: it masks them out of the SIMD pass (a 128-bit exclusion map per record),
+// takes their share back out of the difference arrays and adds them to the row of their allele with the same
+// atomics rv_walk_kernel uses.  The rows those atomics land in are zeroed by the warp before its first read.
+// ------------------------------------------------------------------------------------------------
+static const int G4_W = 128;
+static const int G4_WARPS = 4;
+static const int G4_PF = 4;       // quality words are fetched this many records ahead
+static const int G4_B = 16384;    // bias that keeps tile coordinates non-negative halfwords
+
+struct G4Warp {
+  uint4 rec[32 + 2 * G4_PF];      // {-(s+B) x2, (s+L+1+B) x2, word index of the quality under coordinate 0, PRMT selector | flag << 16}
+  uint4 excl[32];                 // positions of the record masked out of the SIMD pass
+  uint32_t d_n[G4_W + 4], c_n[G4_W + 4], d_rev[G4_W + 4], d_mapq[G4_W + 4], d_nm[G4_W + 4], d_tp1[G4_W + 4], d_tp2[G4_W + 4];
+};
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// the observation of one base on its allele's row, as DeviceSink::single does it
+__device__ __forceinline__ void row_observe(uint32_t* row, uint32_t dir, uint32_t tp, uint32_t q, uint32_t mapq, uint32_t nm, int thr) {
+  atomicAdd(row + (dir ? RV_F_REV : RV_F_FWD), 1u);
+  atomicAdd(row + RV_F_SUM_TP, tp);
+  atomicAdd(row + RV_F_SUM_Q, q);
+  atomicAdd(row + RV_F_SUM_MAPQ, mapq);
+  if (nm) atomicAdd(row + RV_F_SUM_NM, nm);
+  if ((int)q >= thr) atomicAdd(row + RV_F_HI, 1u);
+  const uint32_t mine = (tp & 0xffffu) | ((q & 0xffu) << 16) | (1u << 31);
+  const uint32_t old = atomicCAS(row + RV_F_STD, 0u, mine);
+  if (old != 0u) {
+    uint32_t bits = 0;
+    if ((old ^ mine) & 0xffffu) bits |= 1u << 24;
+    if ((old ^ mine) & 0xff0000u) bits |= 1u << 25;
+    if (bits & ~old) atomicOr(row + RV_F_STD, bits);
+  }
+}
+
+// inclusive prefix sum over the warp's 128 values, four consecutive ones per lane
+__device__ __forceinline__ void warp_scan4(uint32_t v[4], int lane) {
+  v[1] += v[0]; v[2] += v[1]; v[3] += v[2];
+  uint32_t t = v[3];
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, t, off);
+    if (lane >= off) t += y;
+  }
+  const uint32_t ex = t - v[3];
+  v[0] += ex; v[1] += ex; v[2] += ex; v[3] += ex;
+}
+
+__global__ void __launch_bounds__(G4_WARPS * 32, 4) rv_gather4_kernel(GatherArgs a) {
+  __shared__ __align__(16) G4Warp s_w[G4_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t tile = (int64_t)blockIdx.x * G4_WARPS + warp;
+  if (tile >= a.n_tiles) return;  // (no CTA barrier anywhere below)
+  G4Warp& W = s_w[warp];
+  const int4 tinfo = ((const int4*)a.tile_range)[tile];  // {read lo (64 bit), n reads, region}
+  const DevRegion* dr = a.regions + tinfo.w;
+  const int64_t lo = (int64_t)(((unsigned long long)(unsigned)tinfo.y << 32) | (unsigned)tinfo.x);
+  const int64_t hi = lo + tinfo.z;
+  const int p_lo = dr->first_pos + (int)(tile - dr->tile_base) * G4_W;
+  const int c_lo = p_lo > dr->r.start ? p_lo : dr->r.start;  // positions that can receive observations
+  const int c_hi = p_lo + G4_W - 1 < dr->r.end ? p_lo + G4_W - 1 : dr->r.end;
+  const int x4 = lane * 4;
+  const int thr = a.thr;
+  const int64_t t_row0 = dr->tab_off + (p_lo - dr->first_pos);
+  uint32_t* const tile_rows = a.counts + (size_t)t_row0 * RV_POS_U32;
+  // ---- the lane's four positions: table / live flags, reference alleles; rows the atomics may land in start at zero
+  int refal[4];
+  bool in_tab[4], live[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int p = p_lo + x4 + j;
+    in_tab[j] = p - dr->first_pos < dr->n_pos;
+    live[j] = p >= c_lo && p <= c_hi;
+    refal[j] = -1;
+    if (live[j] && p >= dr->r.ref_lo && p <= dr->r.ref_hi && p >= a.ref_start && (int64_t)(p - a.ref_start) < a.ref_n) {
+      const char c = a.ref[p - a.ref_start];
+      refal[j] = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
+    }
+    if (in_tab[j]) {
+      uint4* row4 = (uint4*)(tile_rows + (size_t)(x4 + j) * RV_POS_U32);
+#pragma unroll
+      for (int al = 0; al < 4; ++al)
+        if (al != refal[j]) { row4[2 * al] = make_uint4(0, 0, 0, 0); row4[2 * al + 1] = make_uint4(0, 0, 0, 0); }
+    }
+  }
+  for (int i = lane; i < G4_W + 4; i += 32) {
+    W.d_n[i] = 0; W.c_n[i] = 0; W.d_rev[i] = 0; W.d_mapq[i] = 0; W.d_nm[i] = 0; W.d_tp1[i] = 0; W.d_tp2[i] = 0;
+  }
+  __threadfence();  // the zero rows are in place before any lane's atomics on them
+  __syncwarp();
+  // ---- lane constants of the SIMD pass
+  const uint32_t X01 = (uint32_t)(x4 + 1 + G4_B) | ((uint32_t)(x4 + 2 + G4_B) << 16);
+  const uint32_t X23 = X01 + 0x00020002u;
+  const uint32_t bias4 = (uint32_t)(128 - thr) * 0x01010101u;  // 1 <= thr <= 128 (checked by the host)
+  const uint32_t* const pool32 = (const uint32_t*)a.pool;
+  const int w_max = (int)(((a.pool_bytes + 15) >> 4) << 2) - 1;
+  const GDesc* item_desc = a.descs + (dr->item_base - dr->r.read_lo);  // descriptor of read index i
+  const uint16_t* item_mm = a.desc_mm + (dr->item_base - dr->r.read_lo);
+  const uint4* item_mml = a.desc_mml + (dr->item_base - dr->r.read_lo);
+  uint32_t tp_and01 = 0xffffffffu, tp_and23 = 0xffffffffu, tp_or01 = 0, tp_or23 = 0, q_and = 0xffffffffu, q_or = 0;
+  uint32_t sum_q[4] = {0, 0, 0, 0}, n_hi[4] = {0, 0, 0, 0};
+
+  for (int64_t base = lo; base < hi; base += 32) {
+    // ---- 1. one candidate descriptor per lane -> record of the SIMD pass, range adds, mismatching bases -----------
+    const int64_t i = base + lane;
+    GDesc d;
+    d.m_len = 0;
+    uint32_t mm = 0;
+    if (i < hi) {
+      *(uint4*)&d = *(const uint4*)(item_desc + i);
+      mm = item_mm[i];
+    }
+    bool take = false;
+    int k_lo = 0, k_hi = 0;
+    if (d.m_len != 0) {
+      k_lo = c_lo - d.m_start > 0 ? c_lo - d.m_start : 0;
+      k_hi = c_hi + 1 - d.m_start < (int)d.m_len ? c_hi + 1 - d.m_start : (int)d.m_len;
+      take = k_lo < k_hi;
+    }
+    const unsigned bt = __ballot_sync(0xffffffffu, take);
+    const int n_rec = __popc(bt);
+    if (take) {
+      const int slot = __popc(bt & ((1u << lane) - 1u));
+      const int s = d.m_start - p_lo, L = (int)d.m_len;
+      const uint32_t dir = d.dir_nm >> 7, nm = d.dir_nm & 0x7fu, mapq = d.mapq;
+      const int64_t qb = (int64_t)d.seq_off4 * 4 + ((d.l_seq + 1) >> 1) + d.rp0;  // pool byte of the run's first quality
+      const int64_t q0 = qb - s;                                                   // ... of the quality under coordinate 0
+      uint4 ex = make_uint4(0, 0, 0, 0);
+      if (mm) {
+        // mismatching bases of the run that fall on this warp's live positions
+        const uint4 ml = item_mml[i];
+        unsigned long long l_lo = (unsigned long long)ml.x | ((unsigned long long)ml.y << 32);
+        unsigned long long l_hi = (unsigned long long)ml.z | ((unsigned long long)ml.w << 32);
+#pragma unroll 1
+        while (l_lo | l_hi) {
+          const uint32_t e = (uint32_t)l_lo & 0xffffu;
+          l_lo = (l_lo >> 16) | (l_hi << 48);
+          l_hi >>= 16;
+          const int k = (int)((e >> 2) & 0x1fffu);
+          if ((e & 0x8000u) && k >= k_lo && k < k_hi) {
+            const int x = s + k;
+            const uint32_t bit = 1u << (x & 31);
+            if ((x >> 5) == 0) ex.x |= bit; else if ((x >> 5) == 1) ex.y |= bit; else if ((x >> 5) == 2) ex.z |= bit; else ex.w |= bit;
+            const uint32_t tp = (uint32_t)min(k + 1, L - k);
+            const uint32_t q = a.pool[qb + k];
+            row_observe(tile_rows + (size_t)x * RV_POS_U32 + (e & 3u) * RV_ROW_U32, dir, tp, q, mapq, nm, thr);
+            atomicAdd(&W.c_n[x], 1u);
+            if (dir) { atomicAdd(&W.d_rev[x], 0u - 1u); atomicAdd(&W.d_rev[x + 1], 1u); }
+            atomicAdd(&W.d_mapq[x], 0u - mapq); atomicAdd(&W.d_mapq[x + 1], mapq);
+            if (nm) { atomicAdd(&W.d_nm[x], 0u - nm); atomicAdd(&W.d_nm[x + 1], nm); }
+            atomicAdd(&W.d_tp1[x], 0u - tp); atomicAdd(&W.d_tp1[x + 1], tp);
+          }
+        }
+      }
+      const uint32_t flag = (ex.x | ex.y | ex.z | ex.w) ? 0x10000u : 0u;
+      W.rec[slot] = make_uint4(((uint32_t)(-(s + G4_B)) & 0xffffu) * 0x10001u, ((uint32_t)(s + L + 1 + G4_B) & 0xffffu) * 0x10001u,
+                               (uint32_t)(int)(q0 >> 2), (0x3210u + 0x1111u * (uint32_t)(q0 & 3)) | flag);
+      W.excl[slot] = ex;
+      // range adds of the per-read constants over [s, s+L) clipped to the tile
+      const int ra = s > 0 ? s : 0, rb = s + L < G4_W ? s + L : G4_W;
+      atomicAdd(&W.d_n[ra], 1u); atomicAdd(&W.d_n[rb], 0u - 1u);
+      if (dir) { atomicAdd(&W.d_rev[ra], 1u); atomicAdd(&W.d_rev[rb], 0u - 1u); }
+      atomicAdd(&W.d_mapq[ra], mapq); atomicAdd(&W.d_mapq[rb], 0u - mapq);
+      if (nm) { atomicAdd(&W.d_nm[ra], nm); atomicAdd(&W.d_nm[rb], 0u - nm); }
+      // tp = min(k+1, L-k): slope +1 on [s, s+h), -1 on [s+L-h+1, s+L], h = ceil(L/2); second differences, the part
+      // left of the tile folded into coordinate 0
+      const int h = (L + 1) >> 1;
+      const int i0 = s, i1 = s + h, i2 = s + L - h + 1, i3 = s + L + 1;
+      if (i0 < G4_W) atomicAdd(&W.d_tp2[i0 > 0 ? i0 : 0], 1u);
+      if (i1 < G4_W) atomicAdd(&W.d_tp2[i1 > 0 ? i1 : 0], 0u - 1u);
+      if (i2 < G4_W) atomicAdd(&W.d_tp2[i2 > 0 ? i2 : 0], 0u - 1u);
+      if (i3 < G4_W) atomicAdd(&W.d_tp2[i3 > 0 ? i3 : 0], 1u);
+      if (s < 0) atomicAdd(&W.d_tp1[0], (uint32_t)min(-s, s + L + 1));  // tp under coordinate -1
+    }
+    if (lane < 2 * G4_PF)  // records that cover nothing: the pass runs in steps of G4_PF and prefetches G4_PF ahead
+      W.rec[n_rec + lane] = make_uint4(((uint32_t)(-G4_B) & 0xffffu) * 0x10001u, ((uint32_t)(1 + G4_B) & 0xffffu) * 0x10001u, 0u, 0x3210u);
+    __syncwarp();
+    // ---- 2. the SIMD pass over the records ----------------------------------------------------------------------
+    if (n_rec) {
+      uint32_t w0[G4_PF], w1[G4_PF];
+#pragma unroll
+      for (int u = 0; u < G4_PF; ++u) {
+        int widx = (int)W.rec[u].z + lane;
+        widx = max(min(widx, w_max), 0);
+        w0[u] = __ldg(pool32 + widx);
+        w1[u] = __ldg(pool32 + widx + 1);
+      }
+      uint32_t sq_lo = 0, sq_hi = 0, hi_acc = 0;  // at most 32 + G4_PF records: no byte / halfword can overflow
+      for (int r = 0; r < n_rec; r += G4_PF) {
+#pragma unroll
+        for (int u = 0; u < G4_PF; ++u) {
+          const uint4 rc = W.rec[r + u];
+          const uint32_t dn01 = rc.y - X01, dn23 = rc.y - X23;
+          uint32_t t01 = __viaddmin_s16x2_relu(X01, rc.x, dn01);  // tp of positions 0, 1 (0 = not covered)
+          uint32_t t23 = __viaddmin_s16x2_relu(X23, rc.x, dn23);
+          uint32_t m = prmt(t01 + 0x7fff7fffu, t23 + 0x7fff7fffu, 0xfdb9u);  // 0xff per covered position
+          if (rc.w & 0x10000u) {  // (warp-uniform) the record has bases that differ from the reference under this warp
+            const uint32_t ew = ((const uint32_t*)&W.excl[r + u])[lane >> 3];
+            const uint32_t e4 = (ew >> ((lane & 7) * 4)) & 15u;
+            m &= ~(((e4 * 0x00204081u) & 0x01010101u) * 0xffu);
+            t01 &= prmt(m, 0u, 0x1100u);
+            t23 &= prmt(m, 0u, 0x3322u);
+          }
+          const uint32_t m01 = prmt(m, 0u, 0x1100u), m23 = prmt(m, 0u, 0x3322u);
+          tp_and01 &= t01 | ~m01; tp_or01 |= t01;
+          tp_and23 &= t23 | ~m23; tp_or23 |= t23;
+          const uint32_t q4 = prmt(w0[u], w1[u], rc.w);
+          const uint32_t qm = q4 & m;
+          q_and &= q4 | ~m; q_or |= qm;
+          sq_lo += qm & 0x00ff00ffu;
+          sq_hi += (qm >> 8) & 0x00ff00ffu;
+          hi_acc += ((((qm & 0x7f7f7f7fu) + bias4) | qm) & 0x80808080u) >> 7;
+          // fetch for record r + u + G4_PF
+          int widx = (int)W.rec[r + u + G4_PF].z + lane;
+          widx = max(min(widx, w_max), 0);
+          w0[u] = __ldg(pool32 + widx);
+          w1[u] = __ldg(pool32 + widx + 1);
+        }
+      }
+      sum_q[0] += sq_lo & 0xffffu; sum_q[2] += sq_lo >> 16; sum_q[1] += sq_hi & 0xffffu; sum_q[3] += sq_hi >> 16;
+      n_hi[0] += hi_acc & 0xffu; n_hi[1] += (hi_acc >> 8) & 0xffu; n_hi[2] += (hi_acc >> 16) & 0xffu; n_hi[3] += hi_acc >> 24;
+    }
+    __syncwarp();
+  }
+  // ---- 3. prefix sums of the difference arrays, rows of the reference alleles -------------------------------------
+  __syncwarp();
+  uint32_t cnt[4], rev[4], smq[4], snm[4], stp[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    cnt[j] = W.d_n[x4 + j]; rev[j] = W.d_rev[x4 + j]; smq[j] = W.d_mapq[x4 + j]; snm[j] = W.d_nm[x4 + j]; stp[j] = W.d_tp2[x4 + j];
+  }
+  warp_scan4(cnt, lane); warp_scan4(rev, lane); warp_scan4(smq, lane); warp_scan4(snm, lane); warp_scan4(stp, lane);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) stp[j] += W.d_tp1[x4 + j];
+  warp_scan4(stp, lane);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (!in_tab[j]) continue;
+    const int x = x4 + j;
+    a.cov[t_row0 + x] = live[j] ? cnt[j] : 0u;
+    if (refal[j] < 0) continue;
+    const uint32_t n_ref = cnt[j] - W.c_n[x];
+    uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
+    if (n_ref) {
+      const uint32_t t_and = ((j & 2) ? tp_and23 : tp_and01) >> (16 * (j & 1)) & 0xffffu;
+      const uint32_t t_or = ((j & 2) ? tp_or23 : tp_or01) >> (16 * (j & 1)) & 0xffffu;
+      const uint32_t qa = (q_and >> (8 * j)) & 0xffu, qo = (q_or >> (8 * j)) & 0xffu;
+      uint32_t w = t_and | (qa << 16) | (1u << 31);
+      if (t_and != t_or) w |= 1u << 24;
+      if (qa != qo) w |= 1u << 25;
+      ra = make_uint4(n_ref - rev[j], rev[j], stp[j], sum_q[j]);
+      rb = make_uint4(smq[j], snm[j], n_hi[j], w);
+    }
+    uint4* row4 = (uint4*)(tile_rows + (size_t)x * RV_POS_U32 + refal[j] * RV_ROW_U32);
     row4[0] = ra;
     row4[1] = rb;
   }
@@ -1342,6 +1635,10 @@ struct rv_ctx {
   int64_t n_tiles;
   bool use_gather;
   bool gather_ws;   // RV_GATHER_WS=1 selects the warp-specialised gather kernel (experimental)
+  bool gather4;     // rv_gather4_kernel (default; RV_GATHER_LEGACY=1 or goodq outside [0, 128] selects rv_gather_kernel)
+  int tile;         // table positions per gather tile
+  uint4* d_desc_mml;
+  int64_t pool_dev_bytes;
   // batch state
   const rv_read* reads_dev_view;  // d_reads or a caller-provided device pointer
   const uint8_t* pool_dev_view;
@@ -1454,6 +1751,14 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   ctx->d_patch_count = NULL; ctx->d_regions = NULL; ctx->d_max_rl = NULL; ctx->d_stats = NULL; ctx->d_lgt = NULL; ctx->d_descs = NULL; ctx->d_desc_mm = NULL; ctx->d_reach = NULL; ctx->d_ref4 = NULL; ctx->d_tile_range = NULL; ctx->tile_cap = 0; ctx->d_patched_queue = NULL; ctx->d_patched_count = NULL; ctx->d_walk_queue = NULL; ctx->d_walk_count = NULL; ctx->n_tiles = 0;
   ctx->use_gather = getenv("RV_NO_GATHER") == NULL;
   ctx->gather_ws = getenv("RV_GATHER_WS") && atoi(getenv("RV_GATHER_WS")) == 1;
+  {
+    const int thr = (int)ceil(params->goodq);
+    ctx->gather4 = !ctx->gather_ws && !(getenv("RV_GATHER_LEGACY") && atoi(getenv("RV_GATHER_LEGACY")) == 1) && thr >= 1 &&
+                   thr <= 128 && limits->max_read_bytes < ((int64_t)1 << 32);
+    ctx->tile = ctx->gather4 ? G4_W : GATHER_TILE;
+  }
+  ctx->d_desc_mml = NULL;
+  ctx->pool_dev_bytes = 0;
   ctx->h_counts = NULL; ctx->h_cov = NULL; ctx->h_tab_cap = 0; ctx->h_events = NULL; ctx->h_events_cap = 0;
   ctx->h_variants = NULL; ctx->h_variants_cap = 0; ctx->h_max_rl = NULL; ctx->h_rows = NULL; ctx->h_rows_cap = 0; ctx->d_scratch = NULL; ctx->scratch_cap = 0;
   ctx->n_reads = 0; ctx->read_origin = 0; ctx->n_positions = 0; ctx->n_items = 0; ctx->have_patch = false; ctx->tables_fetched = false;
@@ -1485,10 +1790,11 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   // work items are (region, read) pairs: a read overlapping two tiles is walked once per tile
   CK(cudaMalloc(&ctx->d_descs, sizeof(GDesc) * (size_t)(2 * L.max_reads + 1024)));
   CK(cudaMalloc(&ctx->d_desc_mm, sizeof(uint16_t) * (size_t)(2 * L.max_reads + 1024)));
+  CK(cudaMalloc(&ctx->d_desc_mml, sizeof(uint4) * (size_t)(2 * L.max_reads + 1024)));
   CK(cudaMalloc(&ctx->d_reach, 2 * sizeof(int32_t)));
   CK(cudaMalloc(&ctx->d_ref4, sizeof(uint32_t) * (size_t)(L.max_ref_bases / 8 + 16)));
   // gather tiles: every region rounds its table (length + 2*halo) up to whole tiles
-  ctx->tile_cap = L.max_positions / GATHER_TILE + L.max_regions + 1;
+  ctx->tile_cap = L.max_positions / ctx->tile + L.max_regions + 1;
   CK(cudaMalloc(&ctx->d_tile_range, 2 * sizeof(int64_t) * (size_t)ctx->tile_cap));
   // positions queued for the general scoring kernel (patched positions, screened candidates): at most every position
   CK(cudaMalloc(&ctx->d_patched_queue, sizeof(int64_t) * (size_t)(L.max_positions + 1)));
@@ -1516,6 +1822,7 @@ void rv_destroy(rv_ctx* ctx) {
   cudaFree(ctx->d_scratch);
   cudaFree(ctx->d_descs);
   cudaFree(ctx->d_desc_mm);
+  cudaFree(ctx->d_desc_mml);
   cudaFree(ctx->d_reach);
   cudaFree(ctx->d_ref4);
   cudaFree(ctx->d_tile_range);
@@ -1542,6 +1849,8 @@ int32_t rv_ctx_halo(const rv_ctx* ctx) { return ctx ? ctx->L.halo : 0; }
 
 int rv_set_params(rv_ctx* ctx, const rv_params* params) {
   if (!ctx || !params) return RV_ERR_ARG;
+  if (ctx->gather4 && !(ceil(params->goodq) >= 1 && ceil(params->goodq) <= 128))
+    return fail(ctx, RV_ERR_ARG, "goodq outside (0, 128]: create the context with these parameters instead");
   ctx->P = *params;
   return RV_OK;
 }
@@ -1576,6 +1885,7 @@ int rv_push_reads(rv_ctx* ctx, const rv_read_batch* b) {
   if (b->pool_bytes) CK(cudaMemcpyAsync(ctx->d_pool, b->pool, (size_t)b->pool_bytes, cudaMemcpyHostToDevice, ctx->stream));
   ctx->reads_dev_view = ctx->d_reads;
   ctx->pool_dev_view = ctx->d_pool;
+  ctx->pool_dev_bytes = b->pool_bytes;
   ctx->n_reads = b->n_reads;
   ctx->read_origin = 0;
   ctx->slices.assign(1, rv_ctx::Slice{0, b->n_reads, 0, 0});
@@ -1608,6 +1918,7 @@ int rv_push_reads_ranges(rv_ctx* ctx, const rv_read_batch* b, int32_t n_ranges, 
   }
   ctx->reads_dev_view = ctx->d_reads;
   ctx->pool_dev_view = ctx->d_pool;
+  ctx->pool_dev_bytes = dev_pool;
   ctx->n_reads = hi_max;
   ctx->read_origin = 0;
   return RV_OK;
@@ -1621,6 +1932,7 @@ int rv_push_reads_device(rv_ctx* ctx, const rv_read_batch* b) {
   if (!ctx || !b || b->n_reads < 0) return RV_ERR_ARG;
   ctx->reads_dev_view = b->reads;
   ctx->pool_dev_view = b->pool;
+  ctx->pool_dev_bytes = b->pool_bytes;
   ctx->n_reads = b->n_reads;
   ctx->read_origin = 0;
   ctx->slices.assign(1, rv_ctx::Slice{0, b->n_reads, 0, 0});
@@ -1654,7 +1966,7 @@ int rv_set_regions(rv_ctx* ctx, const rv_region* regs, int32_t n) {
     d.tab_off = tab;
     d.item_base = items;
     d.tile_base = tiles;
-    tiles += (d.n_pos + GATHER_TILE - 1) / GATHER_TILE;
+    tiles += (d.n_pos + ctx->tile - 1) / ctx->tile;
     tab += d.n_pos;
     items += d.r.read_hi - d.r.read_lo;
     ctx->h_max_rl[i] = d.r.max_read_len_in;
@@ -1706,6 +2018,7 @@ int rv_pileup(rv_ctx* ctx) {
   a.stats = ctx->d_stats;
   a.descs = ctx->d_descs;
   a.desc_mm = ctx->d_desc_mm;
+  a.desc_mml = ctx->d_desc_mml;
   a.reach = ctx->d_reach;
   a.force_exact = ctx->use_gather ? 0 : 1;
   a.walk_queue = ctx->d_walk_queue;
@@ -1735,8 +2048,13 @@ int rv_pileup(rv_ctx* ctx) {
     g.reach = ctx->d_reach;
     g.tile_range = ctx->d_tile_range;
     g.n_tiles = ctx->n_tiles;
+    g.tile = ctx->tile;
+    g.desc_mml = ctx->d_desc_mml;
+    g.pool_bytes = ctx->pool_dev_bytes;
+    g.thr = (int)ceil(ctx->P.goodq);
     rv_tile_index_kernel<<<(unsigned)((ctx->n_tiles + 127) / 128), 128, 0, ctx->stream>>>(g);
-    if (ctx->gather_ws) rv_gather_ws_kernel<<<(unsigned)ctx->n_tiles, WS_THREADS, 0, ctx->stream>>>(g);
+    if (ctx->gather4) rv_gather4_kernel<<<(unsigned)((ctx->n_tiles + G4_WARPS - 1) / G4_WARPS), G4_WARPS * 32, 0, ctx->stream>>>(g);
+    else if (ctx->gather_ws) rv_gather_ws_kernel<<<(unsigned)ctx->n_tiles, WS_THREADS, 0, ctx->stream>>>(g);
     else rv_gather_kernel<<<(unsigned)ctx->n_tiles, GATHER_TILE, 0, ctx->stream>>>(g);
     ctx->launches += 2;
     CK(cudaGetLastError());
