@@ -775,8 +775,9 @@ static const int G4_PF = 4;       // quality words are fetched this many records
 static const int G4_B = 16384;    // bias that keeps tile coordinates non-negative halfwords
 
 struct G4Warp {
-  uint4 rec[32 + 2 * G4_PF];      // {-(s+B) x2, (s+L+1+B) x2, word index of the quality under coordinate 0, PRMT selector | flag << 16}
-  uint4 excl[32];                 // positions of the record masked out of the SIMD pass
+  uint4 rec[32 + 2 * G4_PF];      // {-(s+B) x2, (s+L+1+B) x2, PRMT selector | flag << 16, -}
+  uint4 ldr[32 + 2 * G4_PF];      // {word index of the quality under coordinate 0, first lane, last lane the run covers, -}
+  uint8_t excl[32][32];           // [record][lane]: bit j = position j of the lane is masked out of the SIMD pass
   uint32_t d_n[G4_W + 4], c_n[G4_W + 4], d_rev[G4_W + 4], d_mapq[G4_W + 4], d_nm[G4_W + 4], d_tp1[G4_W + 4], d_tp2[G4_W + 4];
 };
 
@@ -817,7 +818,7 @@ __device__ __forceinline__ void warp_scan4(uint32_t v[4], int lane) {
   v[0] += ex; v[1] += ex; v[2] += ex; v[3] += ex;
 }
 
-__global__ void __launch_bounds__(G4_WARPS * 32, 4) rv_gather4_kernel(GatherArgs a) {
+__global__ void __launch_bounds__(G4_WARPS * 32, 8) rv_gather4_kernel(GatherArgs a) {
   __shared__ __align__(16) G4Warp s_w[G4_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t tile = (int64_t)blockIdx.x * G4_WARPS + warp;
@@ -864,22 +865,29 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 4) rv_gather4_kernel(GatherArgs
   const uint32_t X23 = X01 + 0x00020002u;
   const uint32_t bias4 = (uint32_t)(128 - thr) * 0x01010101u;  // 1 <= thr <= 128 (checked by the host)
   const uint32_t* const pool32 = (const uint32_t*)a.pool;
-  const int w_max = (int)(((a.pool_bytes + 15) >> 4) << 2) - 1;
   const GDesc* item_desc = a.descs + (dr->item_base - dr->r.read_lo);  // descriptor of read index i
   const uint16_t* item_mm = a.desc_mm + (dr->item_base - dr->r.read_lo);
   const uint4* item_mml = a.desc_mml + (dr->item_base - dr->r.read_lo);
   uint32_t tp_and01 = 0xffffffffu, tp_and23 = 0xffffffffu, tp_or01 = 0, tp_or23 = 0, q_and = 0xffffffffu, q_or = 0;
   uint32_t sum_q[4] = {0, 0, 0, 0}, n_hi[4] = {0, 0, 0, 0};
 
+  uint4 d_nxt = make_uint4(0, 0, 0, 0);
+  uint32_t mm_nxt = 0;
+  if (lo + lane < hi) {
+    d_nxt = *(const uint4*)(item_desc + lo + lane);
+    mm_nxt = item_mm[lo + lane];
+  }
   for (int64_t base = lo; base < hi; base += 32) {
     // ---- 1. one candidate descriptor per lane -> record of the SIMD pass, range adds, mismatching bases -----------
     const int64_t i = base + lane;
     GDesc d;
-    d.m_len = 0;
-    uint32_t mm = 0;
-    if (i < hi) {
-      *(uint4*)&d = *(const uint4*)(item_desc + i);
-      mm = item_mm[i];
+    *(uint4*)&d = d_nxt;
+    const uint32_t mm = mm_nxt;
+    d_nxt = make_uint4(0, 0, 0, 0);  // (m_len = 0) the next round's descriptor travels while this round computes
+    mm_nxt = 0;
+    if (i + 32 < hi) {
+      d_nxt = *(const uint4*)(item_desc + i + 32);
+      mm_nxt = item_mm[i + 32];
     }
     bool take = false;
     int k_lo = 0, k_hi = 0;
@@ -896,7 +904,7 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 4) rv_gather4_kernel(GatherArgs
       const uint32_t dir = d.dir_nm >> 7, nm = d.dir_nm & 0x7fu, mapq = d.mapq;
       const int64_t qb = (int64_t)d.seq_off4 * 4 + ((d.l_seq + 1) >> 1) + d.rp0;  // pool byte of the run's first quality
       const int64_t q0 = qb - s;                                                   // ... of the quality under coordinate 0
-      uint4 ex = make_uint4(0, 0, 0, 0);
+      bool any_ex = false;
       if (mm) {
         // mismatching bases of the run that fall on this warp's live positions
         const uint4 ml = item_mml[i];
@@ -910,8 +918,12 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 4) rv_gather4_kernel(GatherArgs
           const int k = (int)((e >> 2) & 0x1fffu);
           if ((e & 0x8000u) && k >= k_lo && k < k_hi) {
             const int x = s + k;
-            const uint32_t bit = 1u << (x & 31);
-            if ((x >> 5) == 0) ex.x |= bit; else if ((x >> 5) == 1) ex.y |= bit; else if ((x >> 5) == 2) ex.z |= bit; else ex.w |= bit;
+            if (!any_ex) {
+              any_ex = true;
+              ((uint4*)W.excl[slot])[0] = make_uint4(0, 0, 0, 0);
+              ((uint4*)W.excl[slot])[1] = make_uint4(0, 0, 0, 0);
+            }
+            W.excl[slot][x >> 2] |= (uint8_t)(1u << (x & 3));
             const uint32_t tp = (uint32_t)min(k + 1, L - k);
             const uint32_t q = a.pool[qb + k];
             row_observe(tile_rows + (size_t)x * RV_POS_U32 + (e & 3u) * RV_ROW_U32, dir, tp, q, mapq, nm, thr);
@@ -923,10 +935,11 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 4) rv_gather4_kernel(GatherArgs
           }
         }
       }
-      const uint32_t flag = (ex.x | ex.y | ex.z | ex.w) ? 0x10000u : 0u;
+      const uint32_t flag = any_ex ? 0x10000u : 0u;
       W.rec[slot] = make_uint4(((uint32_t)(-(s + G4_B)) & 0xffffu) * 0x10001u, ((uint32_t)(s + L + 1 + G4_B) & 0xffffu) * 0x10001u,
-                               (uint32_t)(int)(q0 >> 2), (0x3210u + 0x1111u * (uint32_t)(q0 & 3)) | flag);
-      W.excl[slot] = ex;
+                               (0x3210u + 0x1111u * (uint32_t)(q0 & 3)) | flag, 0u);
+      // lanes outside the run load what its nearest covered lane loads (no sector that no lane needs is fetched)
+      W.ldr[slot] = make_uint4((uint32_t)(int)(q0 >> 2), (uint32_t)((s > 0 ? s : 0) >> 2), (uint32_t)((s + L - 1 < G4_W - 1 ? s + L - 1 : G4_W - 1) >> 2), 0u);
       // range adds of the per-read constants over [s, s+L) clipped to the tile
       const int ra = s > 0 ? s : 0, rb = s + L < G4_W ? s + L : G4_W;
       atomicAdd(&W.d_n[ra], 1u); atomicAdd(&W.d_n[rb], 0u - 1u);
@@ -943,16 +956,18 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 4) rv_gather4_kernel(GatherArgs
       if (i3 < G4_W) atomicAdd(&W.d_tp2[i3 > 0 ? i3 : 0], 1u);
       if (s < 0) atomicAdd(&W.d_tp1[0], (uint32_t)min(-s, s + L + 1));  // tp under coordinate -1
     }
-    if (lane < 2 * G4_PF)  // records that cover nothing: the pass runs in steps of G4_PF and prefetches G4_PF ahead
-      W.rec[n_rec + lane] = make_uint4(((uint32_t)(-G4_B) & 0xffffu) * 0x10001u, ((uint32_t)(1 + G4_B) & 0xffffu) * 0x10001u, 0u, 0x3210u);
+    if (lane < 2 * G4_PF) {  // records that cover nothing: the pass runs in steps of G4_PF and prefetches G4_PF ahead
+      W.rec[n_rec + lane] = make_uint4(((uint32_t)(-G4_B) & 0xffffu) * 0x10001u, ((uint32_t)(1 + G4_B) & 0xffffu) * 0x10001u, 0x3210u, 0u);
+      W.ldr[n_rec + lane] = make_uint4(0u, 0u, 0u, 0u);
+    }
     __syncwarp();
     // ---- 2. the SIMD pass over the records ----------------------------------------------------------------------
     if (n_rec) {
       uint32_t w0[G4_PF], w1[G4_PF];
 #pragma unroll
       for (int u = 0; u < G4_PF; ++u) {
-        int widx = (int)W.rec[u].z + lane;
-        widx = max(min(widx, w_max), 0);
+        const uint4 lr = W.ldr[u];
+        const int widx = (int)lr.x + max(min(lane, (int)lr.z), (int)lr.y);
         w0[u] = __ldg(pool32 + widx);
         w1[u] = __ldg(pool32 + widx + 1);
       }
@@ -962,28 +977,23 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 4) rv_gather4_kernel(GatherArgs
         for (int u = 0; u < G4_PF; ++u) {
           const uint4 rc = W.rec[r + u];
           const uint32_t dn01 = rc.y - X01, dn23 = rc.y - X23;
-          uint32_t t01 = __viaddmin_s16x2_relu(X01, rc.x, dn01);  // tp of positions 0, 1 (0 = not covered)
-          uint32_t t23 = __viaddmin_s16x2_relu(X23, rc.x, dn23);
+          const uint32_t t01 = __viaddmin_s16x2_relu(X01, rc.x, dn01);  // tp of positions 0, 1 (0 = not covered)
+          const uint32_t t23 = __viaddmin_s16x2_relu(X23, rc.x, dn23);
           uint32_t m = prmt(t01 + 0x7fff7fffu, t23 + 0x7fff7fffu, 0xfdb9u);  // 0xff per covered position
-          if (rc.w & 0x10000u) {  // (warp-uniform) the record has bases that differ from the reference under this warp
-            const uint32_t ew = ((const uint32_t*)&W.excl[r + u])[lane >> 3];
-            const uint32_t e4 = (ew >> ((lane & 7) * 4)) & 15u;
-            m &= ~(((e4 * 0x00204081u) & 0x01010101u) * 0xffu);
-            t01 &= prmt(m, 0u, 0x1100u);
-            t23 &= prmt(m, 0u, 0x3322u);
-          }
+          if (rc.z & 0x10000u)  // (warp-uniform) the record has bases that differ from the reference under this warp
+            m &= ~((((uint32_t)W.excl[r + u][lane] * 0x00204081u) & 0x01010101u) * 0xffu);
           const uint32_t m01 = prmt(m, 0u, 0x1100u), m23 = prmt(m, 0u, 0x3322u);
-          tp_and01 &= t01 | ~m01; tp_or01 |= t01;
-          tp_and23 &= t23 | ~m23; tp_or23 |= t23;
-          const uint32_t q4 = prmt(w0[u], w1[u], rc.w);
+          tp_and01 &= t01 | ~m01; tp_or01 |= t01 & m01;
+          tp_and23 &= t23 | ~m23; tp_or23 |= t23 & m23;
+          const uint32_t q4 = prmt(w0[u], w1[u], rc.z);
           const uint32_t qm = q4 & m;
           q_and &= q4 | ~m; q_or |= qm;
           sq_lo += qm & 0x00ff00ffu;
-          sq_hi += (qm >> 8) & 0x00ff00ffu;
-          hi_acc += ((((qm & 0x7f7f7f7fu) + bias4) | qm) & 0x80808080u) >> 7;
+          sq_hi += prmt(qm, 0u, 0x4341u);
+          hi_acc += __umulhi((((qm & 0x7f7f7f7fu) + bias4) | qm) & 0x80808080u, 1u << 25);
           // fetch for record r + u + G4_PF
-          int widx = (int)W.rec[r + u + G4_PF].z + lane;
-          widx = max(min(widx, w_max), 0);
+          const uint4 lr = W.ldr[r + u + G4_PF];
+          const int widx = (int)lr.x + max(min(lane, (int)lr.z), (int)lr.y);
           w0[u] = __ldg(pool32 + widx);
           w1[u] = __ldg(pool32 + widx + 1);
         }
