@@ -501,6 +501,8 @@ struct GatherArgs {
   const uint4* desc_mml;
   int64_t pool_bytes;   // bytes of the device pool (rv_gather4_kernel clamps its look-ahead loads to it)
   int thr;              // ceil(goodq)
+  int run;              // consecutive tiles per warp (rv_gather4_kernel)
+  int alternate;        // odd tiles walk their candidates downward
 };
 
 __device__ __forceinline__ int find_region_by_tile(const DevRegion* regs, int n, int64_t tile) {
@@ -771,9 +773,9 @@ __global__ void __launch_bounds__(GATHER_TILE, 5) rv_gather_kernel(GatherArgs a)
 // ------------------------------------------------------------------------------------------------
 static const int G4_W = 128;
 static const int G4_WARPS = 4;
-static const int G4_PF = 4;       // quality words are fetched this many records ahead
 static const int G4_B = 16384;    // bias that keeps tile coordinates non-negative halfwords
 
+template <int G4_PF>  // quality words are fetched this many records ahead
 struct G4Warp {
   uint4 rec[32 + 2 * G4_PF];      // {-(s+B) x2, (s+L+1+B) x2, PRMT selector | flag << 16, -}
   uint4 ldr[32 + 2 * G4_PF];      // {word index of the quality under coordinate 0, first lane, last lane the run covers, -}
@@ -818,12 +820,16 @@ __device__ __forceinline__ void warp_scan4(uint32_t v[4], int lane) {
   v[0] += ex; v[1] += ex; v[2] += ex; v[3] += ex;
 }
 
-__global__ void __launch_bounds__(G4_WARPS * 32, 8) rv_gather4_kernel(GatherArgs a) {
-  __shared__ __align__(16) G4Warp s_w[G4_WARPS];
+template <int G4_PF, int MIN_CTAS>
+__global__ void __launch_bounds__(G4_WARPS * 32, MIN_CTAS) rv_gather4_kernel(GatherArgs a) {
+  __shared__ __align__(16) G4Warp<G4_PF> s_w[G4_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t tile = (int64_t)blockIdx.x * G4_WARPS + warp;
-  if (tile >= a.n_tiles) return;  // (no CTA barrier anywhere below)
-  G4Warp& W = s_w[warp];
+  G4Warp<G4_PF>& W = s_w[warp];
+  // A warp works through a.run consecutive tiles: the reads a tile shares with the next one are needed again right
+  // after they were used (L2 / L1 hits), not a whole tile's duration later by some other warp.
+  const int64_t tile0 = ((int64_t)blockIdx.x * G4_WARPS + warp) * a.run;
+#pragma unroll 1
+  for (int64_t tile = tile0; tile < tile0 + a.run && tile < a.n_tiles; ++tile) {  // (no CTA barrier anywhere below)
   const int4 tinfo = ((const int4*)a.tile_range)[tile];  // {read lo (64 bit), n reads, region}
   const DevRegion* dr = a.regions + tinfo.w;
   const int64_t lo = (int64_t)(((unsigned long long)(unsigned)tinfo.y << 32) | (unsigned)tinfo.x);
@@ -848,12 +854,13 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 8) rv_gather4_kernel(GatherArgs
       const char c = a.ref[p - a.ref_start];
       refal[j] = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
     }
-    if (in_tab[j]) {
-      uint4* row4 = (uint4*)(tile_rows + (size_t)(x4 + j) * RV_POS_U32);
-#pragma unroll
-      for (int al = 0; al < 4; ++al)
-        if (al != refal[j]) { row4[2 * al] = make_uint4(0, 0, 0, 0); row4[2 * al + 1] = make_uint4(0, 0, 0, 0); }
-    }
+  }
+  {
+    // every row of the tile starts at zero (512 contiguous bytes per store instruction); the rows of the reference
+    // alleles are written again at the end, the others only ever receive the atomics of mismatching bases
+    const int n_in = dr->n_pos - (p_lo - dr->first_pos) < G4_W ? dr->n_pos - (p_lo - dr->first_pos) : G4_W;
+    uint4* blk = (uint4*)tile_rows;
+    for (int c = lane; c < n_in * (RV_POS_U32 / 4); c += 32) blk[c] = make_uint4(0, 0, 0, 0);
   }
   for (int i = lane; i < G4_W + 4; i += 32) {
     W.d_n[i] = 0; W.c_n[i] = 0; W.d_rev[i] = 0; W.d_mapq[i] = 0; W.d_nm[i] = 0; W.d_tp1[i] = 0; W.d_tp2[i] = 0;
@@ -871,23 +878,33 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 8) rv_gather4_kernel(GatherArgs
   uint32_t tp_and01 = 0xffffffffu, tp_and23 = 0xffffffffu, tp_or01 = 0, tp_or23 = 0, q_and = 0xffffffffu, q_or = 0;
   uint32_t sum_q[4] = {0, 0, 0, 0}, n_hi[4] = {0, 0, 0, 0};
 
+  // Neighbouring tiles walk their candidates in opposite directions: the reads two tiles share are then needed by
+  // both at the same end of their loops, i.e. close in time (L1 / L2 hits instead of a second trip to DRAM).
+  const bool downward = a.alternate && ((tile - dr->tile_base) & 1) != 0;
+  const int n_batches = (int)((hi - lo + 31) >> 5);
   uint4 d_nxt = make_uint4(0, 0, 0, 0);
   uint32_t mm_nxt = 0;
-  if (lo + lane < hi) {
-    d_nxt = *(const uint4*)(item_desc + lo + lane);
-    mm_nxt = item_mm[lo + lane];
+  {
+    const int64_t i0 = (downward ? lo + 32 * (int64_t)(n_batches - 1) : lo) + lane;
+    if (n_batches > 0 && i0 < hi) {
+      d_nxt = *(const uint4*)(item_desc + i0);
+      mm_nxt = item_mm[i0];
+    }
   }
-  for (int64_t base = lo; base < hi; base += 32) {
+  for (int bi = 0; bi < n_batches; ++bi) {
     // ---- 1. one candidate descriptor per lane -> record of the SIMD pass, range adds, mismatching bases -----------
-    const int64_t i = base + lane;
+    const int64_t i = lo + 32 * (int64_t)(downward ? n_batches - 1 - bi : bi) + lane;
     GDesc d;
     *(uint4*)&d = d_nxt;
     const uint32_t mm = mm_nxt;
     d_nxt = make_uint4(0, 0, 0, 0);  // (m_len = 0) the next round's descriptor travels while this round computes
     mm_nxt = 0;
-    if (i + 32 < hi) {
-      d_nxt = *(const uint4*)(item_desc + i + 32);
-      mm_nxt = item_mm[i + 32];
+    {
+      const int64_t i_n = downward ? i - 32 : i + 32;
+      if (bi + 1 < n_batches && i_n < hi) {
+        d_nxt = *(const uint4*)(item_desc + i_n);
+        mm_nxt = item_mm[i_n];
+      }
     }
     bool take = false;
     int k_lo = 0, k_hi = 0;
@@ -898,6 +915,7 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 8) rv_gather4_kernel(GatherArgs
     }
     const unsigned bt = __ballot_sync(0xffffffffu, take);
     const int n_rec = __popc(bt);
+    int g_n = 0, g_rev = 0, g_mapq = 0, g_nm = 0, g_tp2 = 0, g_tp1 = 0;  // what this lane adds at coordinate 0
     if (take) {
       const int slot = __popc(bt & ((1u << lane) - 1u));
       const int s = d.m_start - p_lo, L = (int)d.m_len;
@@ -940,21 +958,40 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 8) rv_gather4_kernel(GatherArgs
                                (0x3210u + 0x1111u * (uint32_t)(q0 & 3)) | flag, 0u);
       // lanes outside the run load what its nearest covered lane loads (no sector that no lane needs is fetched)
       W.ldr[slot] = make_uint4((uint32_t)(int)(q0 >> 2), (uint32_t)((s > 0 ? s : 0) >> 2), (uint32_t)((s + L - 1 < G4_W - 1 ? s + L - 1 : G4_W - 1) >> 2), 0u);
-      // range adds of the per-read constants over [s, s+L) clipped to the tile
-      const int ra = s > 0 ? s : 0, rb = s + L < G4_W ? s + L : G4_W;
-      atomicAdd(&W.d_n[ra], 1u); atomicAdd(&W.d_n[rb], 0u - 1u);
-      if (dir) { atomicAdd(&W.d_rev[ra], 1u); atomicAdd(&W.d_rev[rb], 0u - 1u); }
-      atomicAdd(&W.d_mapq[ra], mapq); atomicAdd(&W.d_mapq[rb], 0u - mapq);
-      if (nm) { atomicAdd(&W.d_nm[ra], nm); atomicAdd(&W.d_nm[rb], 0u - nm); }
+      // range adds of the per-read constants over [s, s+L) clipped to the tile (index G4_W is never read)
+      const int rb = s + L;
+      if (s > 0) {
+        atomicAdd(&W.d_n[s], 1u);
+        if (dir) atomicAdd(&W.d_rev[s], 1u);
+        atomicAdd(&W.d_mapq[s], mapq);
+        if (nm) atomicAdd(&W.d_nm[s], nm);
+      } else {  // runs that begin at or before coordinate 0 all add there: summed over the warp below
+        g_n = 1; g_rev = (int)dir; g_mapq = (int)mapq; g_nm = (int)nm;
+      }
+      if (rb < G4_W) {
+        atomicAdd(&W.d_n[rb], 0u - 1u);
+        if (dir) atomicAdd(&W.d_rev[rb], 0u - 1u);
+        atomicAdd(&W.d_mapq[rb], 0u - mapq);
+        if (nm) atomicAdd(&W.d_nm[rb], 0u - nm);
+      }
       // tp = min(k+1, L-k): slope +1 on [s, s+h), -1 on [s+L-h+1, s+L], h = ceil(L/2); second differences, the part
       // left of the tile folded into coordinate 0
       const int h = (L + 1) >> 1;
       const int i0 = s, i1 = s + h, i2 = s + L - h + 1, i3 = s + L + 1;
-      if (i0 < G4_W) atomicAdd(&W.d_tp2[i0 > 0 ? i0 : 0], 1u);
-      if (i1 < G4_W) atomicAdd(&W.d_tp2[i1 > 0 ? i1 : 0], 0u - 1u);
-      if (i2 < G4_W) atomicAdd(&W.d_tp2[i2 > 0 ? i2 : 0], 0u - 1u);
-      if (i3 < G4_W) atomicAdd(&W.d_tp2[i3 > 0 ? i3 : 0], 1u);
-      if (s < 0) atomicAdd(&W.d_tp1[0], (uint32_t)min(-s, s + L + 1));  // tp under coordinate -1
+      if (i0 <= 0) g_tp2 += 1; else if (i0 < G4_W) atomicAdd(&W.d_tp2[i0], 1u);
+      if (i1 <= 0) g_tp2 -= 1; else if (i1 < G4_W) atomicAdd(&W.d_tp2[i1], 0u - 1u);
+      if (i2 <= 0) g_tp2 -= 1; else if (i2 < G4_W) atomicAdd(&W.d_tp2[i2], 0u - 1u);
+      if (i3 <= 0) g_tp2 += 1; else if (i3 < G4_W) atomicAdd(&W.d_tp2[i3], 1u);
+      if (s < 0) g_tp1 = min(-s, s + L + 1);  // tp under coordinate -1
+    }
+    if (__any_sync(0xffffffffu, g_n != 0)) {
+      const int t_n = __reduce_add_sync(0xffffffffu, g_n), t_rev = __reduce_add_sync(0xffffffffu, g_rev);
+      const int t_mapq = __reduce_add_sync(0xffffffffu, g_mapq), t_nm = __reduce_add_sync(0xffffffffu, g_nm);
+      const int t_tp2 = __reduce_add_sync(0xffffffffu, g_tp2), t_tp1 = __reduce_add_sync(0xffffffffu, g_tp1);
+      if (lane == 0) {
+        atomicAdd(&W.d_n[0], (uint32_t)t_n); atomicAdd(&W.d_rev[0], (uint32_t)t_rev); atomicAdd(&W.d_mapq[0], (uint32_t)t_mapq);
+        atomicAdd(&W.d_nm[0], (uint32_t)t_nm); atomicAdd(&W.d_tp2[0], (uint32_t)t_tp2); atomicAdd(&W.d_tp1[0], (uint32_t)t_tp1);
+      }
     }
     if (lane < 2 * G4_PF) {  // records that cover nothing: the pass runs in steps of G4_PF and prefetches G4_PF ahead
       W.rec[n_rec + lane] = make_uint4(((uint32_t)(-G4_B) & 0xffffu) * 0x10001u, ((uint32_t)(1 + G4_B) & 0xffffu) * 0x10001u, 0x3210u, 0u);
@@ -1032,10 +1069,14 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 8) rv_gather4_kernel(GatherArgs
       ra = make_uint4(n_ref - rev[j], rev[j], stp[j], sum_q[j]);
       rb = make_uint4(smq[j], snm[j], n_hi[j], w);
     }
-    uint4* row4 = (uint4*)(tile_rows + (size_t)x * RV_POS_U32 + refal[j] * RV_ROW_U32);
-    row4[0] = ra;
-    row4[1] = rb;
+    if (n_ref) {  // (the row is zero already)
+      uint4* row4 = (uint4*)(tile_rows + (size_t)x * RV_POS_U32 + refal[j] * RV_ROW_U32);
+      row4[0] = ra;
+      row4[1] = rb;
+    }
   }
+  __syncwarp();
+  }  // tiles of the warp
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2063,7 +2104,18 @@ int rv_pileup(rv_ctx* ctx) {
     g.pool_bytes = ctx->pool_dev_bytes;
     g.thr = (int)ceil(ctx->P.goodq);
     rv_tile_index_kernel<<<(unsigned)((ctx->n_tiles + 127) / 128), 128, 0, ctx->stream>>>(g);
-    if (ctx->gather4) rv_gather4_kernel<<<(unsigned)((ctx->n_tiles + G4_WARPS - 1) / G4_WARPS), G4_WARPS * 32, 0, ctx->stream>>>(g);
+    if (ctx->gather4) {
+      g.run = getenv("RV_G4_RUN") ? atoi(getenv("RV_G4_RUN")) : 1;
+      if (g.run < 1) g.run = 1;
+      g.alternate = getenv("RV_G4_ALT") ? atoi(getenv("RV_G4_ALT")) : 1;
+      const int64_t g4_warps = (ctx->n_tiles + g.run - 1) / g.run;
+      const unsigned g4_grid = (unsigned)((g4_warps + G4_WARPS - 1) / G4_WARPS);
+      const int variant = getenv("RV_G4_VARIANT") ? atoi(getenv("RV_G4_VARIANT")) : 0;
+      if (variant == 1) rv_gather4_kernel<8, 6><<<g4_grid, G4_WARPS * 32, 0, ctx->stream>>>(g);
+      else if (variant == 2) rv_gather4_kernel<8, 5><<<g4_grid, G4_WARPS * 32, 0, ctx->stream>>>(g);
+      else if (variant == 3) rv_gather4_kernel<4, 6><<<g4_grid, G4_WARPS * 32, 0, ctx->stream>>>(g);
+      else rv_gather4_kernel<4, 8><<<g4_grid, G4_WARPS * 32, 0, ctx->stream>>>(g);
+    }
     else if (ctx->gather_ws) rv_gather_ws_kernel<<<(unsigned)ctx->n_tiles, WS_THREADS, 0, ctx->stream>>>(g);
     else rv_gather_kernel<<<(unsigned)ctx->n_tiles, GATHER_TILE, 0, ctx->stream>>>(g);
     ctx->launches += 2;
