@@ -367,18 +367,19 @@ def main():
 
     # ---- e2e steps (host buffers, copies inside the timed region) ---------------------------------------
     e2e_t, e2e_tm, tsv_len = [], None, 0
-    for i in range(1 + args.e2e_steps):
+    for i in range(1 + args.e2e_steps if args.e2e_steps > 0 else 0):
         dt, tms, tsv_len = e2e_pass()
         if i > 0:
             e2e_t.append(dt)
             e2e_tm = tms
-    e2e_sec = sum(e2e_t) / len(e2e_t)
-    for nm, t in zip(("T|N",), e2e_tm):
+    # --e2e-steps 0 (kernel experiments, ncu captures): no end-to-end number, the line says so
+    e2e_sec = sum(e2e_t) / len(e2e_t) if e2e_t else float("nan")
+    for nm, t in zip(("T|N",), e2e_tm or ()):
         log(f"[bench r{rank}] e2e {nm}: push {t.push_ms:.1f} pileup {t.pileup_ms:.1f} fetch {t.fetch_ms:.1f} host {t.host_ms:.1f} "
             f"patch {t.patch_ms:.1f} score {t.score_ms:.1f} assemble {t.assemble_ms:.1f} ms; events {t.n_events} "
             f"variants {t.n_variants} lines {t.n_lines}")
-    h2d = sum(t.h2d_bytes for t in e2e_tm)
-    d2h = sum(t.d2h_bytes for t in e2e_tm)
+    h2d = sum(t.h2d_bytes for t in e2e_tm or ())
+    d2h = sum(t.d2h_bytes for t in e2e_tm or ())
 
     # ---- reductions over ranks (max time, sum of work) ---------------------------------------------------
     from rabbitvar_b200.shard import reduce_step_metrics
@@ -437,8 +438,8 @@ def main():
                        "wall_ms_per_step": wall_ms_max / args.steps,
                        "step": "rv_pileup + rv_score (candidate cut, every position of both samples) + rv_score_positions (full records of both samples at the joined candidate positions): the launches of run_batch_somatic; the join list and the host realigner patch are built once outside the timed loop"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": f"rvh_pipeline_run_paired (host buffers -> somatic-mode TSV), {args.workers} worker contexts x {args.chunk}-tile chunks of both samples, pinned H2D", "sec_per_step": e2e_sec_max,
+            "e2e": {"value": e2e_value if e2e_t else None, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "api": f"rvh_pipeline_run_paired (host buffers -> somatic-mode TSV), {args.workers} worker contexts x {args.chunk}-tile chunks of both samples, pinned H2D", "sec_per_step": e2e_sec_max if e2e_t else None,
                     "tsv_bytes": tsv_len},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm",

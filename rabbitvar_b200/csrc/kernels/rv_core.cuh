@@ -16,6 +16,13 @@
 #define RV_HD inline
 #define RV_HDN inline
 #endif
+// Pins a loop-invariant in a register: kernel parameters live in the constant bank and the compiler otherwise re-loads
+// them (LDC) inside the per-base loops, where the load sits on the critical path of every iteration.
+#if defined(__CUDA_ARCH__)
+#define RV_KEEP_REG(x) asm volatile("" : "+r"(x))
+#else
+#define RV_KEEP_REG(x) ((void)0)
+#endif
 
 namespace rvk {
 
@@ -804,7 +811,9 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
   const bool dir = pr.dir;
   const bool fast_shape = pr.fast_shape && fast != (FastDesc*)0 && plain_hint != 0;
   // qualities are integers: comparisons with the double thresholds are done on their ceilings
-  const int goodq_i = iceil(P.goodq), goodq5_i = iceil(P.goodq + 5);
+  int goodq_i = iceil(P.goodq), goodq5_i = iceil(P.goodq + 5);
+  int trim_after = P.trim_bases_after, vext = P.vext, r_start = R.start, r_end = R.end;
+  RV_KEEP_REG(goodq_i); RV_KEEP_REG(goodq5_i); RV_KEEP_REG(trim_after); RV_KEEP_REG(vext); RV_KEEP_REG(r_start); RV_KEEP_REG(r_end);
   WalkState w;
   w.start = position;
   w.offset = 0;
@@ -1168,7 +1177,7 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
     int nmoff = 0, moffset = 0;
     for (int i = w.offset; i < w.clen; i++) {
       bool trim = false;
-      if (P.trim_bases_after != 0) trim = !dir ? (w.rp > P.trim_bases_after) : (tlen - w.rp > P.trim_bases_after);
+      if (trim_after != 0) trim = !dir ? (w.rp > trim_after) : (tlen - w.rp > trim_after);
       const char ch1 = rd.base(w.rp);
       if (ch1 == 'N') {
         w.start++;
@@ -1184,8 +1193,9 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
       Key ss;
       ss.clear();
       bool start_with_deletion = false;
-      while ((w.start + 1) >= R.start && (w.start + 1) <= R.end && (i + 1) < w.clen && q >= goodq_i &&
-             has_ne(ref, w.start, rd.base(w.rp)) && ref.at(w.start) != 'N') {
+      char cur = ch1;  // rd.base(w.rp), carried along instead of re-loaded
+      while ((w.start + 1) >= r_start && (w.start + 1) <= r_end && (i + 1) < w.clen && q >= goodq_i &&
+             has_ne(ref, w.start, cur) && ref.at(w.start) != 'N') {
         if (rd.q(w.rp + 1) < goodq5_i) break;
         char nuc = rd.base(w.rp + 1);
         if (nuc == 'N') break;
@@ -1199,9 +1209,10 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
           i++;
           w.start++;
           nmoff++;
+          cur = nuc;
         } else {
           int ssn = 0;
-          for (int ssi = 1; ssi <= P.vext; ssi++) {
+          for (int ssi = 1; ssi <= vext; ssi++) {
             if (i + 1 + ssi >= w.clen) break;
             if (w.rp + 1 + ssi < rd.lseq && has_ne(ref, w.start + 1 + ssi, rd.base(w.rp + 1 + ssi))) {
               ssn = ssi + 1;
@@ -1219,6 +1230,7 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
           w.re += ssn;
           i += ssn;
           w.start += ssn;
+          cur = rd.base(w.rp);
         }
       }
       if (ss.n > 0) {
@@ -1226,8 +1238,8 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
         for (int k = 0; k < ss.n; ++k) s.push(ss.c[k]);
       }
       int ddlen = 0;
-      bool near_end = P.local_realign && w.clen - i <= P.vext && ci + 1 < n_cigar && ref.has(w.start) &&
-                      (ss.n > 0 || rd.base(w.rp) != ref.at(w.start)) && rd.q(w.rp) >= goodq_i;
+      bool near_end = w.clen - i <= vext && P.local_realign && ci + 1 < n_cigar && ref.has(w.start) &&
+                      (ss.n > 0 || cur != ref.at(w.start)) && rd.q(w.rp) >= goodq_i;
       if (near_end && c_op(cg.op[ci + 1]) == OP_D) {
         // :779-846
         while (i + 1 < w.clen) {
@@ -1303,7 +1315,7 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
       }
       if (!trim) {
         const int pos = w.start - qbases + 1;
-        if (pos >= R.start && pos <= R.end) {
+        if (pos >= r_start && pos <= r_end) {
           int tp = w.re < rlen - w.re ? w.re + 1 : rlen - w.re;
           if (s.n == 1) {
             int al = allele_of(ch1);

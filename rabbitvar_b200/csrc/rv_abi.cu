@@ -102,9 +102,17 @@ struct DeviceSink {
   uint32_t pend_old, pend_mine;
   bool pend;
   bool mute;  // rv_walk_kernel re-runs prepare_read: its statistics were already counted by rv_pileup_kernel
+  int first_pos, n_pos;  // copies of dr->first_pos / dr->n_pos (registers instead of a global load per observation)
+  __device__ __forceinline__ void bind(const DevRegion* r, uint32_t* counts_all, uint32_t* cov_all) {
+    dr = r;
+    counts = counts_all + (size_t)r->tab_off * RV_POS_U32;
+    covtab = cov_all + r->tab_off;
+    first_pos = r->first_pos;
+    n_pos = r->n_pos;
+  }
   __device__ __forceinline__ bool idx_of(int pos, int* idx) {
-    int i = pos - dr->first_pos;
-    if (i < 0 || i >= dr->n_pos) { n_over++; return false; }
+    int i = pos - first_pos;
+    if (i < 0 || i >= n_pos) { n_over++; return false; }
     *idx = i;
     return true;
   }
@@ -245,9 +253,7 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
     rd = a.reads[read_idx - dr->read_bias];
     ref.lo = dr->r.ref_lo;
     ref.hi = dr->r.ref_hi;
-    s.dr = dr;
-    s.counts = a.counts + (size_t)dr->tab_off * RV_POS_U32;
-    s.covtab = a.cov + dr->tab_off;
+    s.bind(dr, a.counts, a.cov);
     // htslib iterator overlap test (sam_itr_next): pos0 < end && endpos > beg0
     if (rd.pos - 1 < dr->r.end && rd.end_pos > dr->r.start - 1)
       prepare_read(a.P, dr->r, rd, a.pool - dr->pool_bias, ref, s, true, pr);
@@ -419,12 +425,21 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
 }
 
 // The exact CIGAR walk for the queued work items, one per thread (all lanes busy with walks).
-__global__ void __launch_bounds__(128) rv_walk_kernel(PileupArgs a) {
+// The grid is sized to what is resident (MIN_CTAS per SM); a warp takes its next 32 queue entries from a cursor, whole-read
+// walks first, so the long walks start early and the short soft-clip walks fill the tail.
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(128, MIN_CTAS) rv_walk_kernel(PileupArgs a) {
   const unsigned long long n_full = a.walk_count[0], n = n_full + a.walk_count[1];
   unsigned long long over = 0, unsup = 0, full = 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) a.stats->n_walk_items = n;
-  for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < n;
-       q += (unsigned long long)gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned long long q0 = 0;
+    if (lane == 0) q0 = atomicAdd(a.walk_count + 2, 32ull);
+    q0 = __shfl_sync(0xffffffffu, q0, 0);
+    if (q0 >= n) break;
+    const unsigned long long q = q0 + lane;
+    if (q >= n) continue;
     const unsigned long long entry = a.walk_queue[q < n_full ? q : a.walk_cap - 1 - (q - n_full)];
     const int64_t item = (int64_t)(entry & ~WALK_PLAIN_DONE);
     const bool plain_done = (entry & WALK_PLAIN_DONE) != 0;
@@ -442,20 +457,19 @@ __global__ void __launch_bounds__(128) rv_walk_kernel(PileupArgs a) {
     ref.hi = dr->r.ref_hi;
     DeviceSink s;
     s.a = &a;
-    s.dr = dr;
-    s.counts = a.counts + (size_t)dr->tab_off * RV_POS_U32;
-    s.covtab = a.cov + dr->tab_off;
+    s.bind(dr, a.counts, a.cov);
     s.kept_bases = s.n_kept = s.n_unsup = s.n_over = s.n_ev = 0;
     s.goodq = a.P.goodq;
     s.goodq_i = iceil(a.P.goodq);
     s.pend = false;
     s.mute = true;
     Prep pr;
-    prepare_read(a.P, dr->r, rd, pool, ref, s, true, pr);
+    const rv_region R = dr->r;  // by value: the walk compares against start / end at every base
+    prepare_read(a.P, R, rd, pool, ref, s, true, pr);
     s.mute = false;
     if (!pr.ok) continue;  // cannot happen: the item was queued because it passed
     FastDesc scratch;
-    walk_read(a.P, dr->r, ri, rd, pool, ref, (uint32_t)read_idx, s, pr, plain_done ? &scratch : (FastDesc*)0,
+    walk_read(a.P, R, ri, rd, pool, ref, (uint32_t)read_idx, s, pr, plain_done ? &scratch : (FastDesc*)0,
               plain_done ? 1 : 0);
     s.resolve();
     over += s.n_over;
@@ -1688,6 +1702,7 @@ struct rv_ctx {
   bool gather_ws;   // RV_GATHER_WS=1 selects the warp-specialised gather kernel (experimental)
   bool gather4;     // rv_gather4_kernel (default; RV_GATHER_LEGACY=1 or goodq outside [0, 128] selects rv_gather_kernel)
   int tile;         // table positions per gather tile
+  int n_sms;        // SMs of the device (persistent grids)
   uint4* d_desc_mml;
   int64_t pool_dev_bytes;
   // batch state
@@ -1819,6 +1834,8 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   *out = ctx;  // returned even on failure so the caller can read rv_last_error, then rv_destroy
   CK(cudaSetDevice(device));
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ctx->n_sms = 148;
+  CK(cudaDeviceGetAttribute(&ctx->n_sms, cudaDevAttrMultiProcessorCount, ctx->device));
   CK(cudaEventCreate(&ctx->ev0));
   CK(cudaEventCreate(&ctx->ev1));
   CK(cudaEventCreate(&ctx->tev0));
@@ -1851,7 +1868,7 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   CK(cudaMalloc(&ctx->d_patched_queue, sizeof(int64_t) * (size_t)(L.max_positions + 1)));
   CK(cudaMalloc(&ctx->d_patched_count, sizeof(unsigned long long)));
   CK(cudaMalloc(&ctx->d_walk_queue, sizeof(unsigned long long) * (size_t)(2 * L.max_reads + 1024)));
-  CK(cudaMalloc(&ctx->d_walk_count, 2 * sizeof(unsigned long long)));
+  CK(cudaMalloc(&ctx->d_walk_count, 3 * sizeof(unsigned long long)));  // whole-read walks, soft-clip walks, walk cursor
   CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->stream));
   ctx->lgt_n = 1 << 20;
   CK(cudaMalloc(&ctx->d_lgt, sizeof(double) * (size_t)ctx->lgt_n));
@@ -2048,7 +2065,7 @@ int rv_pileup(rv_ctx* ctx) {
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   // no table memset: rv_gather_kernel stores every row (halo included) before rv_walk_kernel adds to them
   CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->stream));
-  CK(cudaMemsetAsync(ctx->d_walk_count, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_walk_count, 0, 3 * sizeof(unsigned long long), ctx->stream));
   CK(cudaMemsetAsync(ctx->d_reach, 0, 2 * sizeof(int32_t), ctx->stream));
   PileupArgs a;
   a.P = ctx->P;
@@ -2124,7 +2141,11 @@ int rv_pileup(rv_ctx* ctx) {
   CK(cudaEventRecord(ctx->evs[1], ctx->stream));
   if (ctx->n_items > 0) {
     // the queue length is only known on the device: a fixed grid of grid-stride threads
-    rv_walk_kernel<<<148 * 8, 128, 0, ctx->stream>>>(a);
+    const int occ = getenv("RV_WALK_OCC") ? atoi(getenv("RV_WALK_OCC")) : 4;
+    if (occ == 8) rv_walk_kernel<8><<<ctx->n_sms * 8, 128, 0, ctx->stream>>>(a);
+    else if (occ == 6) rv_walk_kernel<6><<<ctx->n_sms * 6, 128, 0, ctx->stream>>>(a);
+    else if (occ == 5) rv_walk_kernel<5><<<ctx->n_sms * 5, 128, 0, ctx->stream>>>(a);
+    else rv_walk_kernel<4><<<ctx->n_sms * 4, 128, 0, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
   }
