@@ -59,6 +59,27 @@ RV_HD char nt16_char(int nib) {
 RV_HD int allele_of(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
 RV_HD bool is_atgc(char c) { return c == 'A' || c == 'T' || c == 'G' || c == 'C'; }
 
+// One aligned 32-bit word of a byte array kept in registers: the per-base loop of walk_read reads its bytes (8 packed
+// bases, 4 qualities, 4 reference bases per word) from it and touches memory once per word.  Device only — the host
+// build (tests/tools/rv_dump --backend sim) reads the bytes themselves.
+struct WordCache {
+  uintptr_t tag;
+  uint32_t w;
+};
+RV_HD int cached_byte(const uint8_t* p, WordCache& c) {
+#if defined(__CUDA_ARCH__)
+  const uintptr_t a = (uintptr_t)p, al = a & ~(uintptr_t)3;
+  if (al != c.tag) {
+    c.w = *(const uint32_t*)al;
+    c.tag = al;
+  }
+  return (int)((c.w >> (8 * (unsigned)(a & 3))) & 0xffu);
+#else
+  (void)c;
+  return (int)*p;
+#endif
+}
+
 struct ReadView {
   const uint8_t* seq4;
   const uint8_t* qual;
@@ -1175,17 +1196,54 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
       }
     }
     int nmoff = 0, moffset = 0;
+    // The base, its quality and the reference base of the NEXT iteration are loaded one iteration ahead (read and
+    // reference bytes never change during a pileup), so the common step "base equals the reference" waits on no load.
+    int pf_rp = -1, pf_start = 0, pf_q = 0;
+    char pf_base = 0, pf_ref = 0;
+    WordCache c_seq, c_qual, c_ref;
+    c_seq.tag = c_qual.tag = c_ref.tag = 0;
+    c_seq.w = c_qual.w = c_ref.w = 0;
     for (int i = w.offset; i < w.clen; i++) {
       bool trim = false;
       if (trim_after != 0) trim = !dir ? (w.rp > trim_after) : (tlen - w.rp > trim_after);
-      const char ch1 = rd.base(w.rp);
+      char ch1_, rc_;  // rc_: reference base at w.start, 0 outside the loaded window
+      int q0_;
+      if (pf_rp == w.rp && pf_start == w.start) {
+        ch1_ = pf_base; q0_ = pf_q; rc_ = pf_ref;
+      } else {
+        ch1_ = rd.base(w.rp); q0_ = rd.q(w.rp); rc_ = ref.at(w.start);
+      }
+      pf_rp = w.rp + 1; pf_start = w.start + 1;
+      pf_base = 0; pf_q = 0; pf_ref = 0;
+      if (pf_rp < rd.lseq) {  // (pf_rp >= 1)
+        const int b = cached_byte(rd.seq4 + (pf_rp >> 1), c_seq);
+        pf_base = nt16_char((pf_rp & 1) ? (b & 15) : (b >> 4));
+        pf_q = cached_byte(rd.qual + pf_rp, c_qual);
+      }
+      if (ref.has(pf_start)) pf_ref = (char)cached_byte((const uint8_t*)ref.bases + (pf_start - ref.base_pos), c_ref);
+      const char ch1 = ch1_;
       if (ch1 == 'N') {
         w.start++;
         w.rp++;
         w.re++;
         continue;
       }
-      int q = rd.q(w.rp);  // running SUM of qualities (a double in the reference; integer-valued)
+      if (rc_ == (char)0 || rc_ == ch1) {
+        // !isHasAndNotEquals(ref, start, base): no multi-base key can start here (:711) and the indel-adjacent
+        // forms need a mismatch (:779, :847) — the plain single-base observation of :884-937
+        if (!trim && w.start >= r_start && w.start <= r_end) {
+          const int tp = w.re < rlen - w.re ? w.re + 1 : rlen - w.re;
+          const int al = allele_of(ch1);
+          if (al >= 0) sink.single(w.start, al, dir, tp, q0_, mapq, nm - nmoff);
+          else sink.unsupported();
+          sink.cov(w.start);
+        }
+        w.start++;
+        w.rp++;
+        w.re++;
+        continue;
+      }
+      int q = q0_;  // running SUM of qualities (a double in the reference; integer-valued)
       int qbases = 1, qibases = 0;
       Key s;
       s.clear();

@@ -120,6 +120,8 @@ struct DeviceSink {
     int i;
     if (!idx_of(pos, &i)) return;
     uint32_t* row = counts + ((size_t)i * 4 + allele) * RV_ROW_U32;
+    // (32-bit adds: the sums may legitimately end negative — subCnt of an insertion's anchor base — so two fields cannot
+    // share one 64-bit add)
     atomicAdd(row + (dir ? RV_F_REV : RV_F_FWD), 1u);
     atomicAdd(row + RV_F_SUM_TP, (uint32_t)tp);
     atomicAdd(row + RV_F_SUM_Q, (uint32_t)q);
