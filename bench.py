@@ -299,7 +299,7 @@ def main():
         t_a = time.perf_counter()
         # host buffers in, TSV out: every chunk of tiles is copied H2D, piled, handed to the host stage, scored,
         # copied back and formatted; the pipeline's workers overlap those stages across chunks
-        tsv, tm_p = pipe.run(e2e_params, bt, regs, args.chunk, ref, 1, "T|N", "chrS2", paired=True)
+        tsv, tm_p = pipe.run(e2e_params, bt, regs, args.chunk, ref, 1, "T|N", "chrS2", paired=True, raw=True)
         return time.perf_counter() - t_a, (tm_p,), len(tsv)
 
     # ---- device-resident steps ---------------------------------------------------------------------------

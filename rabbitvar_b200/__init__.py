@@ -208,8 +208,9 @@ class Pipeline:
         if not self._h:
             raise RabbitVarError("rvh_pipeline_create failed")
 
-    def run(self, params, batch, regions, chunk_regions, ref_bases, ref_lo, sample, chrom, paired=False):
-        """paired=True: regions = n tumor tiles followed by the same n normal tiles; returns the somatic-mode TSV."""
+    def run(self, params, batch, regions, chunk_regions, ref_bases, ref_lo, sample, chrom, paired=False, raw=False):
+        """paired=True: regions = n tumor tiles followed by the same n normal tiles; returns the somatic-mode TSV.
+        raw=True returns a memoryview of the library-owned text (valid until the next run) instead of a str copy."""
         out = C.c_char_p()
         n = C.c_int64()
         tm = Timing()
@@ -219,6 +220,9 @@ class Pipeline:
                                     chrom.encode(), C.byref(out), C.byref(n), C.byref(tm))
         if rc != 0:
             raise RabbitVarError(f"rvh_pipeline_run failed ({rc}): {lib().rvh_last_error().decode()}")
+        if raw:
+            addr = C.cast(out, C.c_void_p).value
+            return memoryview((C.c_char * n.value).from_address(addr) if n.value else b""), tm
         return C.string_at(out, n.value).decode(), tm
 
     def launch_count(self):

@@ -21,6 +21,7 @@ struct BatchTiming {
   rv_pileup_stats stats;
   int64_t n_variants, n_lines, h2d_bytes, d2h_bytes;
   int64_t cov_sum[2], cov_pos[2];  // paired mode: coverage summary of the tumor / normal tiles (<out>.info)
+  double t_abs[6];                 // paired mode: stage boundaries on the host clock (RV_PIPE_TRACE)
 };
 
 inline double now_ms() {
@@ -427,6 +428,7 @@ inline int run_batch_somatic(rv_ctx* ctx, const rv_params& P_in, const ReadBatch
   double t7 = now_ms();
   t.push_ms = t1 - t0; t.pileup_ms = t2 - t1;
   t.score_ms = t6 - t5; t.assemble_ms = t7 - t6;
+  t.t_abs[0] = t0; t.t_abs[1] = t1; t.t_abs[2] = t2; t.t_abs[3] = t5; t.t_abs[4] = t6; t.t_abs[5] = t7;
   t.n_variants = nv;
   rv_last_kernel_ms(ctx, &t.pileup_kernel_ms, &t.score_kernel_ms);
   if (tm) *tm = t;

@@ -85,6 +85,7 @@ static int pipeline_run(rvh_pipeline* p, const rv_params* params, const rvh_batc
   if (!p || !params || !batch || (!regions_in && n_regions_in) || !ref_bases || !tsv_out || !tsv_len || n_regions_in < 0)
     return RV_ERR_ARG;
   if (paired && (n_regions_in % 2)) return RV_ERR_ARG;
+  const double t_enter = now_ms();
   try {
     // paired: regions_in = n tumor tiles followed by the same n tiles of the normal sample; a chunk takes tiles
     // [r0, r1) of both.  The loops below run over tiles.
@@ -92,7 +93,23 @@ static int pipeline_run(rvh_pipeline* p, const rv_params* params, const rvh_batc
     const int32_t n_regions = paired ? n_regions_in / 2 : n_regions_in;
     const int per_tile = paired ? 2 : 1;
     if (chunk_regions < 1) chunk_regions = 1;
-    const int n_chunks = (n_regions + chunk_regions - 1) / chunk_regions;
+    // chunk boundaries (in tiles): full-size chunks first, shrinking ones over the last stretch so that the workers
+    // finish together (a worker runs its chunk's stages back to back; the tail would otherwise idle the other workers
+    // for up to one chunk's duration)
+    std::vector<int> cb(1, 0);
+    while (cb.back() < n_regions) {
+      const int left = n_regions - cb.back();
+      int size = chunk_regions;
+      // ... and growing ones at the start: every worker begins with an upload, small first chunks put the first
+      // kernels and host stages behind a short copy instead of all workers' full-size ones
+      const int wave = p->n_workers > 1 ? (int)(cb.size() - 1) / p->n_workers : 2;
+      if (wave == 0) size = std::max(1, chunk_regions / 4);
+      else if (wave == 1) size = std::max(1, chunk_regions / 2);
+      if (p->n_workers > 1 && left < 2 * p->n_workers * chunk_regions)
+        size = std::max(1, std::min(size, (left + 2 * p->n_workers - 1) / (2 * p->n_workers)));
+      cb.push_back(cb.back() + std::min(size, left));
+    }
+    const int n_chunks = (int)cb.size() - 1;
     const ReadBatch& B = batch->b;
     const int halo = 512;
     // capacity one chunk needs
@@ -104,7 +121,7 @@ static int pipeline_run(rvh_pipeline* p, const rv_params* params, const rvh_batc
     // read range of every chunk, per sample: [c][2*k] = lo, [c][2*k+1] = hi
     std::vector<std::array<int64_t, 4> > c_rng((size_t)n_chunks);
     for (int c = 0; c < n_chunks; ++c) {
-      const int r0 = c * chunk_regions, r1 = std::min(n_regions, r0 + chunk_regions);
+      const int r0 = cb[(size_t)c], r1 = cb[(size_t)c + 1];
       int64_t npos = 0, reads = 0, bytes = 0;
       for (int k = 0; k < per_tile; ++k) {
         int64_t lo = -1, hi = -1;
@@ -173,7 +190,7 @@ static int pipeline_run(rvh_pipeline* p, const rv_params* params, const rvh_batc
         for (;;) {
           const int c = next.fetch_add(1);
           if (c >= n_chunks) break;
-          const int r0 = c * chunk_regions, r1 = std::min(n_regions, r0 + chunk_regions);
+          const int r0 = cb[(size_t)c], r1 = cb[(size_t)c + 1];
           std::vector<rv_region> regs(regions + r0, regions + r1);
           if (paired) regs.insert(regs.end(), regions + n_regions + r0, regions + n_regions + r1);
           std::vector<std::string> genes((size_t)(r1 - r0), std::string(chr));
@@ -190,12 +207,34 @@ static int pipeline_run(rvh_pipeline* p, const rv_params* params, const rvh_batc
       });
     for (size_t i = 0; i < th.size(); ++i) th[i].join();
     const double t_end = now_ms();
-    p->tsv.clear();
+    // the chunks' text, in chunk order, into one buffer that keeps its size across runs (no re-zeroing); the copies
+    // run on a few threads
+    std::vector<size_t> toff((size_t)n_chunks + 1, 0);
+    for (int c = 0; c < n_chunks; ++c) {
+      if (crc[(size_t)c] != RV_OK) { g_err = cerr[(size_t)c]; return crc[(size_t)c]; }
+      toff[(size_t)c + 1] = toff[(size_t)c] + ctsv[(size_t)c].size();
+    }
+    const size_t total = toff[(size_t)n_chunks];
+    if (p->tsv.size() < total + 1) p->tsv.resize(total + 1);
+    {
+      const int nt = std::max(1, std::min(8, host_threads()));
+      std::atomic<int> nc(0);
+      std::vector<std::thread> ct;
+      char* dst = &p->tsv[0];
+      for (int t = 0; t < nt; ++t)
+        ct.emplace_back([&]() {
+          for (;;) {
+            const int c = nc.fetch_add(1);
+            if (c >= n_chunks) break;
+            memcpy(dst + toff[(size_t)c], ctsv[(size_t)c].data(), ctsv[(size_t)c].size());
+          }
+        });
+      for (size_t i = 0; i < ct.size(); ++i) ct[i].join();
+      dst[total] = 0;
+    }
     rvh_timing tt;
     memset(&tt, 0, sizeof tt);
     for (int c = 0; c < n_chunks; ++c) {
-      if (crc[(size_t)c] != RV_OK) { g_err = cerr[(size_t)c]; return crc[(size_t)c]; }
-      p->tsv.append(ctsv[(size_t)c]);
       const BatchTiming& t = ctm[(size_t)c];
       tt.push_ms += t.push_ms; tt.pileup_ms += t.pileup_ms; tt.fetch_ms += t.fetch_ms; tt.host_ms += t.host_ms;
       tt.patch_ms += t.patch_ms; tt.score_ms += t.score_ms; tt.assemble_ms += t.assemble_ms;
@@ -204,9 +243,24 @@ static int pipeline_run(rvh_pipeline* p, const rv_params* params, const rvh_batc
       tt.n_events += t.stats.n_events; tt.n_unsupported += t.stats.n_unsupported; tt.n_variants += t.n_variants;
       tt.n_lines += t.n_lines; tt.h2d_bytes += t.h2d_bytes; tt.d2h_bytes += t.d2h_bytes;
     }
-    (void)t_begin; (void)t_end;
+    if (getenv("RV_PIPE_TRACE") && paired) {
+      FILE* tf = fopen(getenv("RV_PIPE_TRACE"), "w");
+      if (tf) {
+        fprintf(tf, "chunk,tiles,t0,t1,t2,t5,t6,t7,fetch_ms,host_ms,patch_ms,h2d_bytes\n");
+        for (int c = 0; c < n_chunks; ++c) {
+          const BatchTiming& t = ctm[(size_t)c];
+          fprintf(tf, "%d,%d,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%lld\n", c, cb[(size_t)c + 1] - cb[(size_t)c],
+                  t.t_abs[0] - t_begin, t.t_abs[1] - t_begin, t.t_abs[2] - t_begin, t.t_abs[3] - t_begin, t.t_abs[4] - t_begin,
+                  t.t_abs[5] - t_begin, t.fetch_ms, t.host_ms, t.patch_ms, (long long)t.h2d_bytes);
+        }
+        fclose(tf);
+      }
+    }
+    if (getenv("RV_PIPE_TRACE"))
+      fprintf(stderr, "[rvh_pipeline] %d chunks on %d workers: setup %.1f ms, workers %.1f ms, concat %.1f ms\n", n_chunks,
+              p->n_workers, t_begin - t_enter, t_end - t_begin, now_ms() - t_end);
     *tsv_out = p->tsv.data();
-    *tsv_len = (int64_t)p->tsv.size();
+    *tsv_len = (int64_t)total;
     if (timing) *timing = tt;
     return RV_OK;
   } catch (const std::exception& e) {

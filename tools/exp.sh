@@ -1,5 +1,9 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-ncu --set full --clock-control none --import-source on -k regex:rv_walk_kernel -c 1 -o gpurun_out/r01_v8walk -f python bench.py --steps 1 --warmup 1 --e2e-steps 0 --skip-cpu > gpurun_out/ncu8w.log 2>&1
-RV_WALK_OCC=4 python bench.py --steps 6 --warmup 3 --e2e-steps 0 --skip-cpu 2>gpurun_out/w4.err | python -c "
+export RV_PIPE_TRACE=gpurun_out/pipe_trace.csv
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+for cfg in "16 5" "16 6" "16 8" "15 5"; do
+  set -- $cfg
+  python bench.py --steps 2 --warmup 3 --e2e-steps 3 --skip-cpu --workers $1 --chunk $2 2>gpurun_out/e.err | python -c "
 import json,sys
-l=json.loads(sys.stdin.read()); r=l['roofline']; print('occ 4', l['ms_per_step'], r['split_ms'])"
+l=json.loads(sys.stdin.read()); print('workers $1 chunk $2 e2e', l['e2e']['sec_per_step'], l['e2e']['value'])"
+  grep "rvh_pipeline\|e2e T" gpurun_out/e.err | tail -2 | cut -c1-220
+done
