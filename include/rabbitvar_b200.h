@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RV_ABI_VERSION 2
+#define RV_ABI_VERSION 3
 #define RV_OK 0
 #define RV_ERR_ARG (-1)
 #define RV_ERR_CUDA (-2)
@@ -100,7 +100,7 @@ typedef struct rv_read {
   uint8_t mapq;
   uint8_t mate_same_tid; /* tid == mtid */
   int32_t end_pos;    /* htslib bam_endpos(): 0-based exclusive end == 1-based inclusive end */
-  int32_t reserved;
+  int32_t mtid;       /* mate's contig id (bam mtid, -1 = none): part of the -t duplicate key */
 } rv_read;
 
 typedef struct rv_read_batch {

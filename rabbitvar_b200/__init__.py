@@ -61,7 +61,7 @@ class Limits(C.Structure):
 class Read(C.Structure):
     _fields_ = [("pos", C.c_int32), ("mpos", C.c_int32), ("data_off16", C.c_uint32), ("l_seq", C.c_int32),
                 ("flag", C.c_uint16), ("n_cigar", C.c_uint16), ("nm", C.c_int16), ("mapq", C.c_uint8),
-                ("mate_same_tid", C.c_uint8), ("end_pos", C.c_int32), ("reserved", C.c_int32)]
+                ("mate_same_tid", C.c_uint8), ("end_pos", C.c_int32), ("mtid", C.c_int32)]
 
 
 class ReadBatch(C.Structure):

@@ -54,7 +54,7 @@ inline void append_record(ReadBatch& out, const rvio::BamRecord& r) {
   h.mapq = r.mapq;
   h.mate_same_tid = r.tid == r.mtid ? 1 : 0;
   h.end_pos = r.end_pos();
-  h.reserved = 0;
+  h.mtid = r.mtid;
   size_t bytes = 4 * (size_t)r.n_cigar + (size_t)((r.l_seq + 1) >> 1) + (size_t)r.l_seq;
   size_t off = (out.pool.size() + 15) & ~(size_t)15;
   h.data_off16 = (uint32_t)(off / 16);

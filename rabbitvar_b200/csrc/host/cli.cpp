@@ -89,6 +89,11 @@ static bool parse(int argc, char** argv, Cli& c) {
     else if (a == "--gpus") c.gpus = std::max(1, atoi(val().c_str()));
     else if (a == "--batch-regions") c.batch_regions = std::max(1, atoi(val().c_str()));
     else if (a == "--auto_resize" || a == "-y" || a == "--verbose" || a == "--chimeric" || a == "--deldupvar") {}
+    else if (a == "-Z" || a == "--downsample") {
+      // recordPreprocessor.cpp:133 drops records by rand(): "random and non-reproducible" (Launcher.cpp:355)
+      fprintf(stderr, "-Z (random downsampling) is not supported: its output is not reproducible by definition\n");
+      exit(1);
+    }
     else if (a == "-H" || a == "--help") { usage(); exit(0); }
     else if (a == "--version") { printf("rabbitvar_b200 0.1 (ABI %d)\n", rv_abi_version()); exit(0); }
     else { fprintf(stderr, "unrecognized option: %s\n", a.c_str()); usage(); exit(1); }

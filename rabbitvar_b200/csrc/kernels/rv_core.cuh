@@ -716,6 +716,57 @@ RV_HD int lookahead_offset(const rv_params& P, const ReadView& rd, const RefView
   return offset;
 }
 
+// The -t filter of RecordPreprocessor::next_record (recordPreprocessor.cpp:153-176) without its running set.
+// The reference keeps a set of keys that it clears whenever a record's start differs from the start of the last
+// record it inserted; every key begins with the record's start and a BAM is coordinate-sorted, so the set only ever
+// holds keys of the current start.  "Seen before" is therefore: an EARLIER record of the same fetch (same region,
+// passing the htslib overlap test and the filters that run before the -t block, :121-146) with the same start and
+// the same key.  Two key kinds, in this order (:157, :166):
+//   mate start < 10                  -> POS - mate name - PNEXT   (mate name: "*" unpaired, "=" same contig, else name)
+//   else paired and flagged unmapped -> POS - CIGAR string
+// A key of one kind never equals a key of the other (a CIGAR string holds no '-').  One thread decides for its own
+// read by scanning back over the reads that share its start; eligible reads are rare (mate start < 10, or 0x4 reads
+// that survive -F), so the scan is off the common path.  `reads` is indexable by batch read index.
+RV_HDN bool record_prefilters_pass(const rv_params& P, const rv_region& R, const rv_read& r) {
+  if (!(r.pos - 1 < R.end && r.end_pos > R.start - 1)) return false;  // never returned by the iterator
+  if ((r.flag & P.samfilter) != 0) return false;
+  if ((int)r.mapq < P.mapping_quality) return false;
+  if (r.l_seq == 1) return false;
+  return true;
+}
+
+RV_HDN int dedup_key_kind(const rv_read& r) {
+  if (r.mpos < 10) return 1;
+  if ((r.flag & 1) && (r.flag & 4)) return 2;
+  return 0;
+}
+
+RV_HDN bool is_duplicate_read(const rv_params& P, const rv_region& R, const rv_read* reads, const uint8_t* pool,
+                              int64_t read_idx) {
+  const rv_read me = reads[read_idx];
+  const int kind = dedup_key_kind(me);
+  if (kind == 0 || !record_prefilters_pass(P, R, me)) return false;
+  const uint32_t* my_cigar = (const uint32_t*)(pool + (size_t)me.data_off16 * 16);
+  for (int64_t j = read_idx - 1; j >= R.read_lo; --j) {
+    const rv_read o = reads[j];
+    if (o.pos != me.pos) break;
+    if (dedup_key_kind(o) != kind || !record_prefilters_pass(P, R, o)) continue;
+    if (kind == 1) {
+      if (o.mpos != me.mpos) continue;
+      const bool mp = (me.flag & 1) != 0, op = (o.flag & 1) != 0;
+      if (mp != op) continue;
+      if (mp && (me.mate_same_tid != o.mate_same_tid || (!me.mate_same_tid && me.mtid != o.mtid))) continue;
+      return true;
+    }
+    if (o.n_cigar != me.n_cigar) continue;
+    const uint32_t* oc = (const uint32_t*)(pool + (size_t)o.data_off16 * 16);
+    bool same = true;
+    for (int k = 0; k < (int)me.n_cigar; ++k) same = same && oc[k] == my_cigar[k];
+    if (same) return true;
+  }
+  return false;
+}
+
 // Everything parseCigar does before its op loop (:497-625): filters, CIGAR rewrite, clean-up, lengths.
 struct Prep {
   Cigar cg;

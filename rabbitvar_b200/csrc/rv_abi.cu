@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
     ref.hi = dr->r.ref_hi;
     s.bind(dr, a.counts, a.cov);
     // htslib iterator overlap test (sam_itr_next): pos0 < end && endpos > beg0
-    if (rd.pos - 1 < dr->r.end && rd.end_pos > dr->r.start - 1)
+    if (rd.pos - 1 < dr->r.end && rd.end_pos > dr->r.start - 1 &&
+        !(a.P.dedup && is_duplicate_read(a.P, dr->r, a.reads - dr->read_bias, a.pool - dr->pool_bias, read_idx)))
       prepare_read(a.P, dr->r, rd, a.pool - dr->pool_bias, ref, s, true, pr);
   }
   // ---- stage 2: warp-cooperative plain-run proof ------------------------------------------------------

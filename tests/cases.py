@@ -47,6 +47,18 @@ CASES = {
     "c2_pileup_k0": dict(gen=["--cfg", "1", "--len", "8600", "--depth", "150", "--seed", "99"], chrom="chrS1",
                          region="1301-7300", ref_args=_simple("chrS1", "1301-7300", ["-k", "0", "-p", "--fisher"]),
                          dump_args=["--k", "0", "--p", "1", "--fisher", "1"], stages="CV", exact_stages=["C.", "V."]),
+    # -t (recordPreprocessor.cpp:153-176): half of the fragments are single-end records, whose POS-RNEXT-PNEXT key
+    # ("POS-*-0") makes every later single-end record of the same start a duplicate
+    "dedup_t": dict(gen=["--cfg", "1", "--len", "12600", "--depth", "150", "--single-frac", "0.5", "--seed", "11"],
+                    chrom="chrS1", region="1301-11300", ref_args=_simple("chrS1", "1301-11300", ["-t"]),
+                    dump_args=["--t", "1"], stages="CRV", exact_stages=["C.", "R.", "V."]),
+    # -t with -F 0x500: paired records flagged 0x4 survive the flag filter and take the POS-CIGAR key
+    "dedup_t_F500": dict(gen=["--cfg", "5", "--len", "8600", "--depth", "400", "--single-frac", "0.2",
+                              "--unmapped-frac", "0.6", "--seed", "12"],
+                         chrom="chrS5", region="1301-7300",
+                         ref_args=_simple("chrS5", "1301-7300", ["-t", "-F", "0x500", "-k", "0"]),
+                         dump_args=["--t", "1", "--F", "500", "--k", "0"], stages="CRV",
+                         exact_stages=["C.", "R.", "V."]),
     # empty / ragged: a region with no reads at all and a region at the contig edge of the read cloud
     "edge_empty": dict(gen=["--cfg", "1", "--len", "8600", "--depth", "20", "--seed", "5"], chrom="chrS1",
                        region="10-1250", ref_args=_simple("chrS1", "10-1250"), dump_args=[], stages="CRV",

@@ -28,7 +28,7 @@ def test_every_declared_symbol_is_exported(built):
 
 def test_abi_version_and_struct_sizes(built):
     L = rv.lib()
-    assert L.rv_abi_version() == 2
+    assert L.rv_abi_version() == 3
     assert C.sizeof(rv.Read) == 32          # fixed per-read header (SURVEY §8d accounting)
     assert C.sizeof(rv.Event) == 96
     assert C.sizeof(rv.Region) == 40

@@ -142,6 +142,8 @@ int main(int argc, char** argv) {
   if (kv.count("--u")) P.uniq_u = (uint8_t)atoi(kv["--u"].c_str());
   if (kv.count("--three")) P.move3 = (uint8_t)atoi(kv["--three"].c_str());
   if (kv.count("--fisher")) P.fisher = (uint8_t)atoi(kv["--fisher"].c_str());
+  if (kv.count("--t")) P.dedup = (uint8_t)atoi(kv["--t"].c_str());
+  if (kv.count("--F")) P.samfilter = (int)strtol(kv["--F"].c_str(), NULL, 16);
   if (kv.count("--bam2")) P.has_bam2 = (uint8_t)atoi(kv["--bam2"].c_str());
   if (kv.count("--p")) { P.pileup = 1; P.freq = -1; P.minr = 0; }
   OUT = fopen(kv["--out"].c_str(), "wb");
@@ -219,6 +221,7 @@ int main(int argc, char** argv) {
         const rv_read& rd = batch.reads[(size_t)i];
         if (!(rd.pos - 1 < regs[r].end && rd.end_pos > regs[r].start - 1)) continue;
         st.n_items++;
+        if (P.dedup && rvk::is_duplicate_read(P, regs[r], batch.reads.data(), batch.pool.data(), i)) continue;
         rvk::FastDesc d;
         memset(&d, 0, sizeof d);
         rvk::process_read(P, regs[r], (int)r, rd, batch.pool.data(), ref, (uint32_t)i, s, use_fast ? &d : (rvk::FastDesc*)0);

@@ -70,6 +70,8 @@ struct Params {
   int max_indel = 30;
   double softclip_frac = 0.0;
   double mnv_frac = 0.0;
+  double single_frac = 0.0;    // fraction of fragments written as two single-end records (-t cases)
+  double unmapped_frac = 0.0;  // fraction of pairs flagged 0x4 (placed but "unmapped": the POS-CIGAR key of -t)
   bool somatic = false, panel = false;
   int read_len = 150;
   int n_amplicons = 500, amp_len = 200, amp_space = 4000;
@@ -440,9 +442,21 @@ static void make_bam(const Params& P, const std::string& path, const std::string
       snprintf(nm, sizeof nm, "f%llu", (unsigned long long)ord);
       int flagL = 0x1 | 0x2 | 0x20 | (first_fwd ? 0x40 : 0x80) | extra;
       int flagR = 0x1 | 0x2 | 0x10 | (first_fwd ? 0x80 : 0x40) | extra;
+      // -t cases: single-end records (no mate: RNEXT "*", PNEXT 0 => the POS-RNEXT-PNEXT duplicate key applies) and
+      // paired records flagged unmapped (0x4; reach the POS-CIGAR key when -F lets them through).  The extra draws
+      // happen only when the options are set, so that every other data set keeps its bytes.
+      bool single = false;
+      if (P.single_frac > 0 && rng.uni() < P.single_frac) single = true;
+      if (!single && P.unmapped_frac > 0 && rng.uni() < P.unmapped_frac) { flagL |= 0x4; flagR |= 0x4; }
+      if (single) { flagL = extra; flagR = 0x10 | extra; }
       Pending a, b;
       fill_record(a.rec, nm, 0, s1, mapq, flagL, cg1, seq1, q1, s2, isz, nm1);
       fill_record(b.rec, nm, 0, s2, mapq, flagR, cg2, seq2, q2, s1, -isz, nm2);
+      if (single) {
+        a.rec.mtid = b.rec.mtid = -1;
+        a.rec.mpos = b.rec.mpos = -1;
+        a.rec.isize = b.rec.isize = 0;
+      }
       a.ord = ord * 2; b.ord = ord * 2 + 1;
       ++ord;
       flush_to(fstart - 2);  // every later read has 1-based pos >= fstart
@@ -485,6 +499,8 @@ int main(int argc, char** argv) {
   if (kv.count("--indel-every")) P.indel_every = atoi(kv["--indel-every"].c_str());
   if (kv.count("--softclip-frac")) P.softclip_frac = atof(kv["--softclip-frac"].c_str());
   if (kv.count("--mnv-frac")) P.mnv_frac = atof(kv["--mnv-frac"].c_str());
+  if (kv.count("--single-frac")) P.single_frac = atof(kv["--single-frac"].c_str());
+  if (kv.count("--unmapped-frac")) P.unmapped_frac = atof(kv["--unmapped-frac"].c_str());
   if (kv.count("--amplicons")) P.n_amplicons = atoi(kv["--amplicons"].c_str());
   if (kv.count("--chr")) P.chr = kv["--chr"];
   mkdirs(P.out);
