@@ -773,6 +773,7 @@ struct Prep {
   int n_cigar, nm, position, rlen, tlen, mapq;
   bool dir, ok, fast_shape;
   int m_start, m_len, rp0;  // the single matched run of a fast-shaped read
+  int rec_ref_len;          // getReferenceLength(record) as skipOverlappingReads sees it (--UN only)
 };
 
 template <class Sink>
@@ -824,6 +825,20 @@ RV_HDN void prepare_read(const rv_params& P, const rv_region& R, const rv_read& 
   }
   cleanup_cigar(cg);
   n_cigar = cg.n;
+  // --UN (isReadsOverlap :196-206) asks the RECORD for its reference length and end.  CigarModifier writes the
+  // rewritten ops over the record's own CIGAR (cigarstr_2cigar, cigarModifier.cpp:386) while core.n_cigar and
+  // core.pos keep their values: the record then answers with the first core.n_cigar entries of that array — the
+  // rewritten ops followed by whatever original ops they did not reach.
+  pr.rec_ref_len = 0;
+  if (P.uniq_un) {
+    int rl = 0;
+    for (int k = 0; k < (int)rdh.n_cigar; ++k) {
+      const uint32_t e = k < n_cigar ? cg.op[k] : cig_in[k];
+      const int o = c_op(e);
+      if (o == OP_M || o == OP_D || o == OP_N || o == OP_EQ || o == OP_X) rl += c_len(e);
+    }
+    pr.rec_ref_len = rl;
+  }
   // :584-588
   if (c_op(cg.op[0]) == OP_S && c_len(cg.op[0]) >= 10 && c_op(cg.op[n_cigar - 1]) == OP_S &&
       c_len(cg.op[n_cigar - 1]) >= 10)
@@ -902,11 +917,12 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
       bool skip = false;
       if (P.uniq_u && paired_same && !dir && w.start >= mate_start) skip = true;
       if (!skip && P.uniq_un && (rdh.flag & 1) && paired_same) {
-        // isReadsOverlap :196-206 ; getReferenceLength/getAlignmentEnd of the record (original span)
-        int ref_len = rdh.end_pos - (rdh.pos - 1);
+        // isReadsOverlap :196-206 ; getReferenceLength / getAlignmentEnd of the record (see prepare_read)
+        const int ref_len = pr.rec_ref_len;
+        const int rec_end = rdh.pos - 1 + (ref_len ? ref_len : 1);  // bam_endpos
         bool ov;
         if (position >= mate_start) ov = w.start >= mate_start && w.start <= mate_start + ref_len - 1;
-        else ov = w.start >= mate_start && mate_start <= rdh.end_pos;
+        else ov = w.start >= mate_start && mate_start <= rec_end;
         if (ov) skip = true;
       }
       if (skip) break;

@@ -494,8 +494,10 @@ RV_HDN void score_position(const rv_params& P, const rv_region& R, int region_id
     }
     if (o.ref_fwd < 0) o.ref_fwd = 0;
     if (o.ref_rev < 0) o.ref_rev = 0;
-    if (o.fwd < 0) o.fwd = 0;
-    if (o.rev < 0) o.rev = 0;
+    if (!is_ref) {  // adjustVariantCounts (:1061) never sees the reference variant of a position that has variants
+      if (o.fwd < 0) o.fwd = 0;
+      if (o.rev < 0) o.rev = 0;
+    }
     out.emit(o);
   }
 }
@@ -628,8 +630,8 @@ RV_HDN void score_dense_position(const rv_params& P, int region_idx, int pos, ch
       if (n_variants == 0) {  // :1066-1090 — no variant reads detected
         o.cnt = 0; o.freq = 0; o.fwd = 0; o.rev = 0; o.bias_var = 0;
       }
-      if (o.fwd < 0) o.fwd = 0;
-      if (o.rev < 0) o.rev = 0;
+      // adjustVariantCounts (:1061) runs over the non-reference variants only: the reference variant of a
+      // position that has variants keeps negative forward / reverse counts
       out.emit(o);
     } else {
       o.rank = (uint8_t)rank++;

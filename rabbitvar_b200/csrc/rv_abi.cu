@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
       const bool paired_same = (rd.flag & 1) && rd.mate_same_tid;
       if (a.P.uniq_u && paired_same && !pr.dir && pr.position >= rd.mpos) skip = true;
       if (!skip && a.P.uniq_un && (rd.flag & 1) && paired_same) {
-        const int ref_len = rd.end_pos - (rd.pos - 1);
+        const int ref_len = pr.rec_ref_len;
         // start == position before the first op, so the "position < mate_start" arm can never hold
         if (pr.position >= rd.mpos && pr.position <= rd.mpos + ref_len - 1) skip = true;
       }

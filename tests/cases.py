@@ -39,6 +39,11 @@ CASES = {
     "c5_k0": dict(gen=["--cfg", "5", "--len", "12600", "--depth", "100"], chrom="chrS5", region="1301-11300",
                   ref_args=_simple("chrS5", "1301-11300", ["-3", "-u", "-k", "0"]),
                   dump_args=["--three", "1", "--u", "1", "--k", "0"], stages="CRV", exact_stages=["C.", "R.", "V."]),
+    # --UN with the CIGAR rewrite on: isReadsOverlap asks the record for its reference length AFTER CigarModifier
+    # wrote the rewritten ops over the record's CIGAR (parseCigar.cpp:196-206, cigarModifier.cpp:386)
+    "c5_un_k1": dict(gen=["--cfg", "5", "--len", "8600", "--depth", "100", "--seed", "21"], chrom="chrS5",
+                     region="1301-7300", ref_args=_simple("chrS5", "1301-7300", ["-3", "--UN"]),
+                     dump_args=["--three", "1", "--UN", "1"], stages="CRV", exact_stages=["C.", "R.", "V."]),
     # cfg 3: deep amplicon panel, low VAF, BED input (4-column BED => simple mode)
     "c3_k0": dict(gen=["--cfg", "3", "--len", "14600", "--depth", "2000", "--amplicons", "3"], chrom="chrS3",
                   bed="panel.bed", ref_args=_bed("chrS3", "panel.bed", ["-f", "0.005", "-k", "0"]),

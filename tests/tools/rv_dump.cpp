@@ -142,6 +142,17 @@ int main(int argc, char** argv) {
   if (kv.count("--u")) P.uniq_u = (uint8_t)atoi(kv["--u"].c_str());
   if (kv.count("--three")) P.move3 = (uint8_t)atoi(kv["--three"].c_str());
   if (kv.count("--fisher")) P.fisher = (uint8_t)atoi(kv["--fisher"].c_str());
+  if (kv.count("--UN")) P.uniq_un = (uint8_t)atoi(kv["--UN"].c_str());
+  if (kv.count("--Q")) P.mapping_quality = atoi(kv["--Q"].c_str());
+  if (kv.count("--m")) P.mismatch = atoi(kv["--m"].c_str());
+  if (kv.count("--M")) P.minmatch = atoi(kv["--M"].c_str());
+  if (kv.count("--T")) P.trim_bases_after = atoi(kv["--T"].c_str());
+  if (kv.count("--q")) P.goodq = atof(kv["--q"].c_str());
+  if (kv.count("--X")) P.vext = atoi(kv["--X"].c_str());
+  if (kv.count("--B")) P.min_bias_reads = atoi(kv["--B"].c_str());
+  if (kv.count("--I")) P.indelsize = atoi(kv["--I"].c_str());
+  if (kv.count("--V")) P.lofreq = atof(kv["--V"].c_str());
+  if (kv.count("--r")) P.minr = atoi(kv["--r"].c_str());
   if (kv.count("--t")) P.dedup = (uint8_t)atoi(kv["--t"].c_str());
   if (kv.count("--F")) P.samfilter = (int)strtol(kv["--F"].c_str(), NULL, 16);
   if (kv.count("--bam2")) P.has_bam2 = (uint8_t)atoi(kv["--bam2"].c_str());
