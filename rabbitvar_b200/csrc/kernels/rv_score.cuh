@@ -248,7 +248,8 @@ template <class Emit>
 RV_HDN void score_position(const rv_params& P, const rv_region& R, int region_idx, int pos, const RefView& ref,
                            const uint32_t* rows /*4 alleles x 8*/, uint32_t cov_p, bool has_next,
                            const uint32_t* rows_next, uint32_t cov_next, const rv_patch_entry* patch, int patch_first,
-                           int patch_n, const LgTable& lgt, Emit& out, int* unsupported) {
+                           int patch_n, int patch_first_next, int patch_n_next, const LgTable& lgt, Emit& out,
+                           int* unsupported) {
   static const char BASES[5] = "ACGT";
   KeyAcc keys[RV_MAX_KEYS];
   int nk = 0, n_ni = 0, n_ins = 0;
@@ -403,11 +404,20 @@ RV_HDN void score_position(const rv_params& P, const rv_region& R, int region_id
   int rfc = 0, rrc = 0;
   if (ref_i >= 0) { rfc = var[ref_i].k->fwd; rrc = var[ref_i].k->rev; }
   if (tcov > (int)cov_p && has_next && ref.has(pos + 1)) {  // :754-760
-    int a = allele_of(ref.at(pos + 1));
-    if (a >= 0 && dense_exists(rows_next + a * RV_ROW_U32)) {
+    // the next position's reference allele as the realigner left it: a patch entry with that key shadows the
+    // dense row (table 2 = erased: the key is gone and nothing is taken over)
+    const char nb = ref.at(pos + 1);
+    int a = allele_of(nb);
+    bool shadowed = false;
+    for (int j = 0; j < patch_n_next; ++j) {
+      const rv_patch_entry& e = patch[patch_first_next + j];
+      if (e.table == 1 || e.keylen != 1 || e.key[0] != nb) continue;
+      shadowed = true;
+      if (e.table == 0) { rfc = e.v.fwd; rrc = e.v.rev; }
+    }
+    if (!shadowed && a >= 0 && dense_exists(rows_next + a * RV_ROW_U32)) {
       rfc = (int)rows_next[a * RV_ROW_U32 + RV_F_FWD];
       rrc = (int)rows_next[a * RV_ROW_U32 + RV_F_REV];
-      (*unsupported)++;  // pos+1 may itself be patched; exact only for untouched rows
     }
   }
   int rank = 0;

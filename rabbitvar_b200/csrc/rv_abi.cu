@@ -1549,6 +1549,8 @@ __global__ void __launch_bounds__(128) rv_score_patched_kernel(ScoreArgs a) {
     ref.lo = dr->r.ref_lo;
     ref.hi = dr->r.ref_hi;
     const bool has_next = i + 1 < dr->n_pos;
+    const uint32_t pfn = (has_next && a.patch_first) ? a.patch_first[t + 1] : 0u;  // ToVarsBuilder.cpp:754-760
+    const int pnn = pfn ? (int)a.patch_count[t + 1] : 0;
     LgTable L;
     L.t = a.lgt;
     L.n = a.lgt_n;
@@ -1556,7 +1558,7 @@ __global__ void __launch_bounds__(128) rv_score_patched_kernel(ScoreArgs a) {
     em.a = &a;
     int unsup = 0;
     score_position(a.P, dr->r, ri, pos, ref, rows, a.cov[t], has_next, rows + RV_POS_U32, has_next ? a.cov[t + 1] : 0u,
-                   a.patch, pf ? (int)(pf - 1) : 0, pn, L, em, &unsup);
+                   a.patch, pf ? (int)(pf - 1) : 0, pn, pfn ? (int)(pfn - 1) : 0, pnn, L, em, &unsup);
     if (unsup) atomicAdd(&a.stats->n_score_unsupported, (unsigned long long)unsup);
   }
 }
@@ -1581,6 +1583,8 @@ __global__ void __launch_bounds__(128) rv_score_list_kernel(ScoreArgs a, const i
     ref.lo = dr->r.ref_lo;
     ref.hi = dr->r.ref_hi;
     const bool has_next = i + 1 < dr->n_pos;
+    const uint32_t pfn = (has_next && a.patch_first) ? a.patch_first[t + 1] : 0u;  // ToVarsBuilder.cpp:754-760
+    const int pnn = pfn ? (int)a.patch_count[t + 1] : 0;
     LgTable L;
     L.t = a.lgt;
     L.n = a.lgt_n;
@@ -1588,7 +1592,7 @@ __global__ void __launch_bounds__(128) rv_score_list_kernel(ScoreArgs a, const i
     em.a = &a;
     int unsup = 0;
     score_position(a.P, dr->r, ri, pos, ref, rows, a.cov[t], has_next, rows + RV_POS_U32, has_next ? a.cov[t + 1] : 0u,
-                   a.patch, pf ? (int)(pf - 1) : 0, pn, L, em, &unsup);
+                   a.patch, pf ? (int)(pf - 1) : 0, pn, pfn ? (int)(pfn - 1) : 0, pnn, L, em, &unsup);
     if (unsup) atomicAdd(&a.stats->n_score_unsupported, (unsigned long long)unsup);
   }
 }

@@ -353,9 +353,11 @@ int main(int argc, char** argv) {
         bool has_next = i + 1 < R.n_pos;
         int pf = 0, pn = 0;
         if (grp.count(pos)) { pf = grp[pos].first; pn = grp[pos].second; }
+        int pfn = 0, pnn = 0;
+        if (has_next && grp.count(pos + 1)) { pfn = grp[pos + 1].first; pnn = grp[pos + 1].second; }
         rvk::score_position(P, regs[r], (int)r, pos, refv, R.counts.data() + (size_t)i * RV_POS_U32, R.cov[i], has_next,
                             R.counts.data() + (size_t)(i + 1) * RV_POS_U32, has_next ? R.cov[i + 1] : 0u, pe.data(), pf, pn,
-                            lgt, em, &unsup);
+                            pfn, pnn, lgt, em, &unsup);
       }
     }
   }
