@@ -37,3 +37,20 @@ def test_device_logic_single_stepped_matches_golden(built, name, tmp_path):
     n, problems = dumpcmp.compare(want, got, c["exact_stages"])
     assert n > 0 or name == "edge_empty"
     assert not problems, problems[:5]
+
+
+def test_smoke_golden_matches_single_stepped_device_logic(built, tmp_path):
+    """tests/golden/smoke_C.txt.gz is what __graft_entry__.smoke() falls back to on a box without oracle/_ref."""
+    import gzip
+    import __graft_entry__ as g
+    work = str(tmp_path / "smoke")
+    os.makedirs(work)
+    g._smoke_dataset(work)
+    got = str(tmp_path / "sim.txt")
+    run([os.path.join(cases.BUILD, "rv_dump"), "--backend", "sim", "--fasta", os.path.join(work, "ref.fa"), "--bam",
+         os.path.join(work, "S.bam"), "--chr", "chrS1", "--region", "1301-13300", "--out", got, "--stages", "C"])
+    want = str(tmp_path / "golden.txt")
+    with gzip.open(os.path.join(cases.ROOT, "tests", "golden", "smoke_C.txt.gz"), "rt") as f, open(want, "w") as o:
+        o.write(f.read())
+    n, problems = dumpcmp.compare(want, got, ["C."])
+    assert n > 0 and not problems, problems[:5]
