@@ -44,6 +44,12 @@ CASES = {
     "c5_un_k1": dict(gen=["--cfg", "5", "--len", "8600", "--depth", "100", "--seed", "21"], chrom="chrS5",
                      region="1301-7300", ref_args=_simple("chrS5", "1301-7300", ["-3", "--UN"]),
                      dump_args=["--three", "1", "--UN", "1"], stages="CRV", exact_stages=["C.", "R.", "V."]),
+    # read bases 'N' (quality 2) in 30 % of the reads, a hard clip at one end of 20 %: the N skip of the M loop
+    # (parseCigar.cpp:686-692), N inside soft clips (:1186), H ops (:655)
+    "edge_nh_k1": dict(gen=["--cfg", "5", "--len", "10600", "--depth", "80", "--nbase-frac", "0.3", "--hardclip-frac", "0.2",
+                            "--seed", "41"], chrom="chrS5", region="1301-9300",
+                       ref_args=_simple("chrS5", "1301-9300", ["-3", "-u"]), dump_args=["--three", "1", "--u", "1"],
+                       stages="CRV", exact_stages=["C.", "R.", "V."]),
     # cfg 3: deep amplicon panel, low VAF, BED input (4-column BED => simple mode)
     "c3_k0": dict(gen=["--cfg", "3", "--len", "14600", "--depth", "2000", "--amplicons", "3"], chrom="chrS3",
                   bed="panel.bed", ref_args=_bed("chrS3", "panel.bed", ["-f", "0.005", "-k", "0"]),

@@ -71,7 +71,9 @@ struct Params {
   double softclip_frac = 0.0;
   double mnv_frac = 0.0;
   double single_frac = 0.0;    // fraction of fragments written as two single-end records (-t cases)
-  double unmapped_frac = 0.0;  // fraction of pairs flagged 0x4 (placed but "unmapped": the POS-CIGAR key of -t)
+  double unmapped_frac = 0.0;
+  double nbase_frac = 0.0;     // fraction of reads that get 1-3 'N' bases (quality 2), NM counted like an aligner does
+  double hardclip_frac = 0.0;  // fraction of reads that get an H op at one end  // fraction of pairs flagged 0x4 (placed but "unmapped": the POS-CIGAR key of -t)
   bool somatic = false, panel = false;
   int read_len = 150;
   int n_amplicons = 500, amp_len = 200, amp_space = 4000;
@@ -337,6 +339,34 @@ static bool build_read(const Params& P, const std::string& ref, const std::vecto
   return true;
 }
 
+// Optional extras of the edge-case data sets (drawn only when the options are set): N read bases and hard clips.
+static void add_edge_cases(const Params& P, Rng& rng, const std::string& ref, int start1, std::string& seq,
+                           std::vector<uint8_t>& qual, std::vector<uint32_t>& cigar, int* nm) {
+  if (P.nbase_frac > 0 && rng.uni() < P.nbase_frac) {
+    int k = rng.range(1, 3);
+    for (int t = 0; t < k; ++t) {
+      int at = (int)rng.below((uint64_t)seq.size());
+      if (seq[(size_t)at] == 'N') continue;
+      int q = 0, r = start1;  // which op holds read offset `at`?
+      for (size_t o = 0; o < cigar.size(); ++o) {
+        int op = (int)(cigar[o] & 15), n = (int)(cigar[o] >> 4);
+        if (op == 0) {
+          if (at < q + n) { if (seq[(size_t)at] == ref[(size_t)(r - 1 + (at - q))]) ++*nm; break; }
+          q += n; r += n;
+        } else if (op == 1 || op == 4) { if (at < q + n) break; q += n; }
+        else if (op == 2) r += n;
+      }
+      seq[(size_t)at] = 'N';
+      qual[(size_t)at] = 2;
+    }
+  }
+  if (P.hardclip_frac > 0 && rng.uni() < P.hardclip_frac) {
+    uint32_t h = ((uint32_t)rng.range(5, 60) << 4) | 5u;
+    if (rng.uni() < 0.5) cigar.insert(cigar.begin(), h);
+    else cigar.push_back(h);
+  }
+}
+
 static void fill_record(BamRecord& r, const std::string& name, int tid, int pos1, int mapq, int flag,
                         const std::vector<uint32_t>& cigar, const std::string& seq, const std::vector<uint8_t>& qual,
                         int mpos1, int isize, int nm) {
@@ -445,6 +475,10 @@ static void make_bam(const Params& P, const std::string& path, const std::string
       // -t cases: single-end records (no mate: RNEXT "*", PNEXT 0 => the POS-RNEXT-PNEXT duplicate key applies) and
       // paired records flagged unmapped (0x4; reach the POS-CIGAR key when -F lets them through).  The extra draws
       // happen only when the options are set, so that every other data set keeps its bytes.
+      if (P.nbase_frac > 0 || P.hardclip_frac > 0) {
+        add_edge_cases(P, rng, ref, s1, seq1, q1, cg1, &nm1);
+        add_edge_cases(P, rng, ref, s2, seq2, q2, cg2, &nm2);
+      }
       bool single = false;
       if (P.single_frac > 0 && rng.uni() < P.single_frac) single = true;
       if (!single && P.unmapped_frac > 0 && rng.uni() < P.unmapped_frac) { flagL |= 0x4; flagR |= 0x4; }
@@ -501,6 +535,8 @@ int main(int argc, char** argv) {
   if (kv.count("--mnv-frac")) P.mnv_frac = atof(kv["--mnv-frac"].c_str());
   if (kv.count("--single-frac")) P.single_frac = atof(kv["--single-frac"].c_str());
   if (kv.count("--unmapped-frac")) P.unmapped_frac = atof(kv["--unmapped-frac"].c_str());
+  if (kv.count("--nbase-frac")) P.nbase_frac = atof(kv["--nbase-frac"].c_str());
+  if (kv.count("--hardclip-frac")) P.hardclip_frac = atof(kv["--hardclip-frac"].c_str());
   if (kv.count("--amplicons")) P.n_amplicons = atoi(kv["--amplicons"].c_str());
   if (kv.count("--chr")) P.chr = kv["--chr"];
   mkdirs(P.out);
