@@ -57,12 +57,47 @@ inline void append_record(ReadBatch& out, const rvio::BamRecord& r) {
   h.mtid = r.mtid;
   size_t bytes = 4 * (size_t)r.n_cigar + (size_t)((r.l_seq + 1) >> 1) + (size_t)r.l_seq;
   size_t off = (out.pool.size() + 15) & ~(size_t)15;
+  if ((off >> 4) > (size_t)0xffffffffu) throw std::runtime_error("read batch pool exceeds 64 GiB: use smaller region blocks");
   h.data_off16 = (uint32_t)(off / 16);
   out.pool.resize(off + bytes);
   if (bytes) memcpy(out.pool.data() + off, r.data.data() + r.l_qname, bytes);
   int span = h.end_pos - r.pos;
   if (span > out.max_ref_span) out.max_ref_span = span;
   out.reads.push_back(h);
+}
+
+// The same from a record that still lies in the inflated BGZF stream (rvio::SpanScanner): one memcpy of the
+// record's cigar | seq | qual bytes into the pool, no intermediate copy.
+inline void append_raw_record(ReadBatch& out, const rvio::RawRecord& r) {
+  rv_read h;
+  h.pos = r.pos() + 1;
+  h.mpos = r.mpos() + 1;
+  h.l_seq = r.l_seq();
+  h.flag = r.flag();
+  h.n_cigar = r.n_cigar();
+  int64_t nm;
+  h.nm = rvio::aux_get_int(r.aux(), r.aux_len(), "NM", &nm) ? (int16_t)nm : (int16_t)-1;
+  h.mapq = r.mapq();
+  h.mate_same_tid = r.tid() == r.mtid() ? 1 : 0;
+  h.end_pos = r.end_pos();
+  h.mtid = r.mtid();
+  const size_t bytes = r.tail_bytes();
+  const size_t off = (out.pool.size() + 15) & ~(size_t)15;
+  if ((off >> 4) > (size_t)0xffffffffu) throw std::runtime_error("read batch pool exceeds 64 GiB: use smaller region blocks");
+  h.data_off16 = (uint32_t)(off / 16);
+  out.pool.resize(off + bytes);
+  if (bytes) memcpy(out.pool.data() + off, r.cigar_bytes(), bytes);
+  const int span = h.end_pos - r.pos();
+  if (span > out.max_ref_span) out.max_ref_span = span;
+  out.reads.push_back(h);
+}
+
+// Appends every read overlapping [span_start, span_end] of `tid`, in file order, to `out` (which keeps what it
+// holds: the spans of one job are loaded one after the other, ascending).
+inline void load_span_fast(rvio::SpanScanner& sc, const rvio::BaiIndex& bai, int tid, int32_t span_start, int32_t span_end,
+                           ReadBatch* out) {
+  sc.scan(bai, tid, (int64_t)span_start - 1, (int64_t)span_end, [&](const rvio::RawRecord& r) { append_raw_record(*out, r); });
+  out->pool.resize((out->pool.size() + 15) & ~(size_t)15);
 }
 
 // Loads every read overlapping [span_start, span_end] of `tid` in file order.

@@ -10,6 +10,9 @@
 // Header-only, C++11, depends on zlib only.
 #pragma once
 #include <zlib.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/stat.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -132,6 +135,8 @@ class BgzfReader {
       int rc = inflate(&zs, Z_FINISH);
       inflateEnd(&zs);
       if (rc != Z_STREAM_END || zs.total_out != isize) throw std::runtime_error("bgzf: inflate failed");
+      uint32_t crc_want = cbuf_[remain - 8] | (cbuf_[remain - 7] << 8) | (cbuf_[remain - 6] << 16) | ((uint32_t)cbuf_[remain - 5] << 24);
+      if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), buf_, isize) != crc_want) throw std::runtime_error("bgzf: CRC mismatch");
     }
     block_len_ = isize;
     block_off_ = 0;
@@ -293,8 +298,14 @@ inline bool aux_get_int(const uint8_t* aux, size_t len, const char tag[2], int64
       case 's': case 'S': sz = 2; break;
       case 'i': case 'I': case 'f': sz = 4; break;
       case 'd': sz = 8; break;
-      case 'Z': case 'H': sz = strlen((const char*)v) + 1; break;
+      case 'Z': case 'H': {
+        const void* z = memchr(v, 0, len - (p + 3));
+        if (!z) return false;  // unterminated string: malformed aux area
+        sz = (size_t)((const uint8_t*)z - v) + 1;
+        break;
+      }
       case 'B': {
+        if (p + 3 + 5 > len) return false;
         char sub = (char)v[0];
         uint32_t n;
         memcpy(&n, v + 1, 4);
@@ -304,6 +315,7 @@ inline bool aux_get_int(const uint8_t* aux, size_t len, const char tag[2], int64
       }
       default: return false;
     }
+    if (p + 3 + sz > len) return false;  // value runs past the record
     if (t[0] == (uint8_t)tag[0] && t[1] == (uint8_t)tag[1]) {
       if (where) *where = t + 2;
       switch (ty) {
@@ -335,11 +347,11 @@ class BamReader {
     if (bgzf_.read(&n_ref, 4) != 4) return false;
     for (int i = 0; i < n_ref; ++i) {
       int32_t l_name, l_ref;
-      bgzf_.read(&l_name, 4);
+      if (bgzf_.read(&l_name, 4) != 4 || l_name < 1 || l_name > (1 << 20)) return false;
       std::string nm(l_name, '\0');
-      bgzf_.read(&nm[0], l_name);
+      if (bgzf_.read(&nm[0], l_name) != (size_t)l_name) return false;
       nm.resize(strlen(nm.c_str()));
-      bgzf_.read(&l_ref, 4);
+      if (bgzf_.read(&l_ref, 4) != 4) return false;
       hdr_.names.push_back(nm);
       hdr_.lens.push_back(l_ref);
     }
@@ -355,7 +367,8 @@ class BamReader {
     int32_t bs;
     if (bgzf_.read(&bs, 4) != 4) return false;
     uint8_t core[32];
-    if (bs < 32 || bgzf_.read(core, 32) != 32) return false;
+    if (bs < 32) throw std::runtime_error("bam: record shorter than its fixed part");
+    if (bgzf_.read(core, 32) != 32) throw std::runtime_error("bam: truncated record");
     uint32_t u[8];
     memcpy(u, core, 32);
     r.tid = (int32_t)u[0];
@@ -369,8 +382,12 @@ class BamReader {
     r.mtid = (int32_t)u[5];
     r.mpos = (int32_t)u[6];
     r.isize = (int32_t)u[7];
+    if (bs > (64 << 20)) throw std::runtime_error("bam: implausible record size");
     r.data.resize(bs - 32);
-    if (bs > 32 && bgzf_.read(r.data.data(), bs - 32) != (size_t)(bs - 32)) return false;
+    if (bs > 32 && bgzf_.read(r.data.data(), bs - 32) != (size_t)(bs - 32))
+      throw std::runtime_error("bam: truncated record");
+    if (r.l_seq < 0 || (size_t)r.l_qname + 4 * (size_t)r.n_cigar + (size_t)((r.l_seq + 1) >> 1) + (size_t)r.l_seq > r.data.size())
+      throw std::runtime_error("bam: record fields exceed its size");
     return true;
   }
 
@@ -581,6 +598,187 @@ class BamRegionIter {
   int tid_;
   int64_t beg_, end_;
   bool done_;
+};
+
+// ------------------------------------------------------------------------------------------------
+// SpanScanner — the decode path of the product's loader threads: the same records, in the same order, as
+// BamRegionIter, but without per-record copies.  Compressed bytes come from pread() in large chunks, every BGZF
+// block is inflated (one z_stream per scanner, reset between blocks: BGZF blocks are independent deflate
+// streams) onto the tail of a sliding buffer, and the records are handed to the callback IN PLACE.  The CRC32 of
+// every block is checked.  A scanner belongs to one thread; threads share nothing but the page cache (the
+// reference gives every OpenMP thread its own BAM handle: simpleMode.cpp:296-320).
+// ------------------------------------------------------------------------------------------------
+struct RawRecord {       // a BAM alignment record as it lies in the inflated stream
+  const uint8_t* core;   // 32 fixed bytes (refID .. tlen), then the variable part
+  int32_t block_size;    // bytes after the block_size word
+  int32_t tid() const { int32_t v; memcpy(&v, core, 4); return v; }
+  int32_t pos() const { int32_t v; memcpy(&v, core + 4, 4); return v; }
+  uint8_t l_qname() const { return core[8]; }
+  uint8_t mapq() const { return core[9]; }
+  uint16_t n_cigar() const { uint16_t v; memcpy(&v, core + 12, 2); return v; }
+  uint16_t flag() const { uint16_t v; memcpy(&v, core + 14, 2); return v; }
+  int32_t l_seq() const { int32_t v; memcpy(&v, core + 16, 4); return v; }
+  int32_t mtid() const { int32_t v; memcpy(&v, core + 20, 4); return v; }
+  int32_t mpos() const { int32_t v; memcpy(&v, core + 24, 4); return v; }
+  const uint8_t* var() const { return core + 32; }
+  const uint8_t* cigar_bytes() const { return var() + l_qname(); }
+  size_t tail_bytes() const { return 4 * (size_t)n_cigar() + (size_t)((l_seq() + 1) >> 1) + (size_t)l_seq(); }
+  const uint8_t* aux() const { return cigar_bytes() + tail_bytes(); }
+  size_t aux_len() const { return (size_t)block_size - 32 - l_qname() - tail_bytes(); }
+  int32_t ref_len() const {
+    int32_t l = 0;
+    const uint8_t* c = cigar_bytes();
+    for (int i = 0, n = n_cigar(); i < n; ++i) {
+      uint32_t w;
+      memcpy(&w, c + 4 * i, 4);
+      const int op = (int)(w & 0xf);
+      if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) l += (int32_t)(w >> 4);
+    }
+    return l;
+  }
+  int32_t end_pos() const {  // htslib bam_endpos
+    const int32_t l = (flag() & 4) || n_cigar() == 0 ? 0 : ref_len();
+    return pos() + (l ? l : 1);
+  }
+};
+
+class SpanScanner {
+ public:
+  SpanScanner() : fd_(-1), zinit_(false), check_crc_(true) {}
+  ~SpanScanner() { close(); }
+  bool open(const std::string& path) {
+    close();
+    BamReader hdr_reader;  // the header (text + reference dictionary) through the plain reader
+    if (!hdr_reader.open(path)) return false;
+    hdr_ = hdr_reader.header();
+    fd_ = ::open(path.c_str(), O_RDONLY);
+    if (fd_ < 0) return false;
+    struct stat st;
+    if (fstat(fd_, &st) != 0) return false;
+    file_size_ = (uint64_t)st.st_size;
+    memset(&zs_, 0, sizeof(zs_));
+    if (inflateInit2(&zs_, -15) != Z_OK) return false;
+    zinit_ = true;
+    return true;
+  }
+  void close() {
+    if (fd_ >= 0) ::close(fd_);
+    fd_ = -1;
+    if (zinit_) inflateEnd(&zs_);
+    zinit_ = false;
+  }
+  const BamHeader& header() const { return hdr_; }
+  void set_check_crc(bool on) { check_crc_ = on; }
+  // Calls f(const RawRecord&) for every record of `tid` overlapping [beg0, end0) (0-based half-open), in file order.
+  template <class F>
+  void scan(const BaiIndex& bai, int tid, int64_t beg0, int64_t end0, F f) {
+    uint64_t voff;
+    if (!bai.start_offset(tid, beg0, &voff)) return;
+    caddr_ = voff >> 16;
+    cbuf_lo_ = cbuf_hi_ = caddr_;
+    ubuf_.clear();
+    size_t cur = (size_t)(voff & 0xffff);
+    bool first = true, eof = false;
+    for (;;) {
+      // complete records available at ubuf_[cur..]?
+      while (ubuf_.size() >= cur + 4) {
+        int32_t bs;
+        memcpy(&bs, ubuf_.data() + cur, 4);
+        if (bs < 32) throw std::runtime_error("bam: record shorter than its fixed part");
+        if (bs > (64 << 20)) throw std::runtime_error("bam: implausible record size");
+        if (ubuf_.size() < cur + 4 + (size_t)bs) break;
+        RawRecord r;
+        r.core = ubuf_.data() + cur + 4;
+        r.block_size = bs;
+        if (r.l_seq() < 0 || (size_t)r.l_qname() + r.tail_bytes() > (size_t)bs - 32)
+          throw std::runtime_error("bam: record fields exceed its size");
+        if (r.tid() != tid || r.pos() >= end0) return;
+        if (r.end_pos() > beg0) f(r);
+        cur += 4 + (size_t)bs;
+      }
+      if (eof) {
+        if (ubuf_.size() > cur) throw std::runtime_error("bam: truncated record at end of file");
+        return;
+      }
+      // drop what has been consumed, then append the next block
+      if (cur > (size_t)(1 << 20) || cur == ubuf_.size()) {
+        ubuf_.erase(ubuf_.begin(), ubuf_.begin() + (std::ptrdiff_t)cur);
+        cur = 0;
+      }
+      if (!append_block(&eof)) eof = true;
+      if (first) {
+        first = false;
+        if (cur > ubuf_.size()) throw std::runtime_error("bam: index offset beyond its block");
+      }
+    }
+  }
+
+ private:
+  // make [caddr_, caddr_ + n) available in cbuf_; returns a pointer or NULL at end of file
+  const uint8_t* need(size_t n) {
+    if (caddr_ < cbuf_lo_ || caddr_ + n > cbuf_hi_) {
+      if (caddr_ + n > file_size_) return NULL;
+      const size_t want = std::min<uint64_t>((uint64_t)(4 << 20), file_size_ - caddr_);
+      cbuf_.resize(want);
+      size_t got = 0;
+      while (got < want) {
+        const ssize_t r = pread(fd_, cbuf_.data() + got, want - got, (off_t)(caddr_ + got));
+        if (r <= 0) break;
+        got += (size_t)r;
+      }
+      if (got < n) return NULL;
+      cbuf_lo_ = caddr_;
+      cbuf_hi_ = caddr_ + got;
+    }
+    return cbuf_.data() + (caddr_ - cbuf_lo_);
+  }
+  bool append_block(bool* eof) {
+    *eof = false;
+    const uint8_t* h = need(18);
+    if (!h) { *eof = true; return false; }
+    if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) throw std::runtime_error("bgzf: bad block header");
+    const int xlen = h[10] | (h[11] << 8);
+    h = need(12 + (size_t)xlen);
+    if (!h) throw std::runtime_error("bgzf: truncated extra field");
+    int bsize = -1;
+    for (int p = 0; p + 4 <= xlen;) {
+      const uint8_t* x = h + 12 + p;
+      const int slen = x[2] | (x[3] << 8);
+      if (x[0] == 'B' && x[1] == 'C' && slen == 2) bsize = (x[4] | (x[5] << 8)) + 1;
+      p += 4 + slen;
+    }
+    if (bsize < 0) throw std::runtime_error("bgzf: no BC subfield");
+    const int remain = bsize - 12 - xlen;
+    if (remain < 8) throw std::runtime_error("bgzf: bad block size");
+    h = need((size_t)bsize);
+    if (!h) throw std::runtime_error("bgzf: truncated block");
+    const uint8_t* def = h + 12 + xlen;
+    uint32_t crc_want, isize;
+    memcpy(&crc_want, def + remain - 8, 4);
+    memcpy(&isize, def + remain - 4, 4);
+    if (isize > (uint32_t)BGZF_MAX_BLOCK) throw std::runtime_error("bgzf: bad isize");
+    if (isize) {
+      const size_t at = ubuf_.size();
+      ubuf_.resize(at + isize);
+      inflateReset(&zs_);
+      zs_.next_in = (Bytef*)def;
+      zs_.avail_in = (uInt)(remain - 8);
+      zs_.next_out = ubuf_.data() + at;
+      zs_.avail_out = isize;
+      const int rc = inflate(&zs_, Z_FINISH);
+      if (rc != Z_STREAM_END || zs_.total_out != isize) throw std::runtime_error("bgzf: inflate failed");
+      if (check_crc_ && (uint32_t)crc32(crc32(0L, Z_NULL, 0), ubuf_.data() + at, isize) != crc_want)
+        throw std::runtime_error("bgzf: CRC mismatch");
+    }
+    caddr_ += (uint64_t)bsize;
+    return true;
+  }
+  int fd_;
+  uint64_t file_size_, caddr_, cbuf_lo_, cbuf_hi_;
+  BamHeader hdr_;
+  z_stream zs_;
+  bool zinit_, check_crc_;
+  std::vector<uint8_t> cbuf_, ubuf_;
 };
 
 // ------------------------------------------------------------------------------------------------
