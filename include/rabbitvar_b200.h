@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RV_ABI_VERSION 3
+#define RV_ABI_VERSION 4
 #define RV_OK 0
 #define RV_ERR_ARG (-1)
 #define RV_ERR_CUDA (-2)
@@ -128,8 +128,14 @@ enum { RV_F_FWD = 0, RV_F_REV = 1, RV_F_SUM_TP = 2, RV_F_SUM_Q = 3, RV_F_SUM_MAP
 #define RV_ROW_U32 8
 #define RV_POS_U32 (4 * RV_ROW_U32)
 
+/* Capacity of an allele-key string (include/Variant.h:24-33) in an event / in a patch entry.  A key that does not
+ * fit is never scored silently: the event carries RV_EVF_KEY_TRUNC, the read counts in rv_pileup_stats.n_unsupported
+ * and the host stage refuses the batch (rvh_*: RV_ERR_OVERFLOW). */
+#define RV_EVENT_KEY_MAX 112
+#define RV_PATCH_KEY_MAX 240
+
 /* Sparse event: one observation that does not fit a dense single-base row (multi-base / indel /
- * complex keys, insertion table, soft-clip accumulators).  96 bytes. */
+ * complex keys, insertion table, soft-clip accumulators).  160 bytes. */
 enum { RV_EV_NI = 0,    /* nonInsertionVariants[pos][key]   (parseCigar.cpp:884-937, :1036-1082) */
        RV_EV_IN = 1,    /* insertionVariants[pos][key]      (parseCigar.cpp:1427-1463) */
        RV_EV_SC5 = 2,   /* softClips5End[pos]               (parseCigar.cpp:1197-1217) */
@@ -154,7 +160,7 @@ typedef struct rv_event {
   int32_t aux0;        /* soft clips: remaining clip length m ; TTREF: pstd|qstd<<1 of the insertion */
   int32_t aux1;        /* soft clips: number of high-quality bases kept (n_hi) */
   int32_t aux2;        /* soft clips: read offset of the base nearest the junction */
-  char key[48];
+  char key[RV_EVENT_KEY_MAX];
 } rv_event;
 
 /* One accumulator in the reference's own field set (include/Variation.h:12-82) for the host-side
@@ -175,7 +181,7 @@ typedef struct rv_patch_entry {
                       single-base key `key` no longer exists at this position */
   uint8_t keylen;
   uint8_t pad[2];
-  char key[48];
+  char key[RV_PATCH_KEY_MAX];
   rv_variation v;
 } rv_patch_entry;
 

@@ -79,7 +79,7 @@ class Event(C.Structure):
                 ("kind", C.c_uint8), ("flags", C.c_uint8), ("tp", C.c_int32), ("nm", C.c_int32),
                 ("qsum", C.c_int32), ("qcnt", C.c_int32), ("dir", C.c_uint8), ("mapq", C.c_uint8),
                 ("keylen", C.c_uint8), ("pad", C.c_uint8), ("aux0", C.c_int32), ("aux1", C.c_int32),
-                ("aux2", C.c_int32), ("key", C.c_char * 48)]
+                ("aux2", C.c_int32), ("key", C.c_char * 112)]
 
 
 class Variant(C.Structure):

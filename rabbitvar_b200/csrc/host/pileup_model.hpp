@@ -163,6 +163,9 @@ inline void reduce_events_region(const rv_event* ev, int64_t n, const ReadBatch&
   uint32_t last_ins_read = 0xffffffffu;
   for (int64_t i = 0; i < n; ++i) {
     const rv_event& e = ev[i];
+    // a key that did not fit RV_EVENT_KEY_MAX is not scored under a wrong name: the device counted the read in
+    // n_unsupported, the observation is dropped here
+    if (e.flags & RV_EVF_KEY_TRUNC) continue;
     const bool dir = e.dir != 0;
     const double q = e.qsum / (double)e.qcnt;
     std::string key(e.key, e.keylen);

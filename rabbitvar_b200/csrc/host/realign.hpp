@@ -7,6 +7,7 @@
 // ismatch, find35match, noPassingReads, adjCnt/adjRefCnt/adjRefFactor.  Structural-variant keys (<dup..>, <inv..>)
 // never reach this path (the SV code of the reference is commented out).
 #pragma once
+#include <atomic>
 #include "pileup_model.hpp"
 #include "../kernels/rv_core.cuh"
 #include <string.h>
@@ -110,9 +111,24 @@ inline std::string find_conseq(Sclip& sc) {
     double maxQuality = 0;
     char chosen = 0;
     int totalCount = 0;
-    for (std::map<char, int>::iterator ent = nve->second.begin(); ent != nve->second.end(); ++ent) {
-      char cb = ent->first;
-      int cc = ent->second;
+    // The reference walks a robin_hood::unordered_map<char, int> here and its choice depends on the visiting order
+    // (a later base with fewer reads but a larger quality sum replaces an earlier one).  For the keys that can
+    // occur the flat map's slot order is fixed, whatever the insertion order: N, A, T, G, C (probed against the
+    // reference's own robin_hood.h 3.4.3 for every subset and insertion order: oracle/robin_hood_order.cpp).
+    // Any other IUPAC letter follows in ASCII order.
+    std::vector<std::pair<char, int> > ordered;
+    {
+      static const char RH_ORDER[] = "NATGC";
+      for (const char* o = RH_ORDER; *o; ++o) {
+        std::map<char, int>::iterator f = nve->second.find(*o);
+        if (f != nve->second.end()) ordered.push_back(*f);
+      }
+      for (std::map<char, int>::iterator ent = nve->second.begin(); ent != nve->second.end(); ++ent)
+        if (!strchr(RH_ORDER, ent->first)) ordered.push_back(*ent);
+    }
+    for (size_t oi = 0; oi < ordered.size(); ++oi) {
+      char cb = ordered[oi].first;
+      int cc = ordered[oi].second;
       totalCount += cc;
       bool hasq = sc.seq().count(pis) && sc.seq()[pis].count(cb);
       if (cc > maxCount || (hasq && sc.seq()[pis][cb].sum_q > maxQuality)) {
@@ -1056,7 +1072,17 @@ inline void realign_region(const rv_params& P, RegionPileup& R, const rvk::RefVi
   R.erased_dense.insert(V.erased_dense.begin(), V.erased_dense.end());
 }
 
-inline void fill_patch(rv_patch_entry& e, int region, int pos, int table, const std::string& key, const Variation& v) {
+// keys longer than RV_PATCH_KEY_MAX cannot travel to the scoring kernels: dropped and counted (reported by the CLI)
+inline std::atomic<long long>& dropped_patch_keys() {
+  static std::atomic<long long> n(0);
+  return n;
+}
+
+inline bool fill_patch(rv_patch_entry& e, int region, int pos, int table, const std::string& key, const Variation& v) {
+  if (key.size() > sizeof e.key) {
+    dropped_patch_keys()++;
+    return false;
+  }
   memset(&e, 0, sizeof e);
   e.region = region;
   e.pos = pos;
@@ -1066,6 +1092,7 @@ inline void fill_patch(rv_patch_entry& e, int region, int pos, int table, const 
   e.v.cnt = v.cnt; e.v.fwd = v.fwd; e.v.rev = v.rev; e.v.lo = v.lo; e.v.hi = v.hi; e.v.extracnt = v.extracnt;
   e.v.sum_tp = v.sum_tp; e.v.sum_q = v.sum_q; e.v.sum_mapq = v.sum_mapq; e.v.sum_nm = v.sum_nm;
   e.v.pstd = v.pstd; e.v.qstd = v.qstd;
+  return true;
 }
 
 // All sparse keys of the region grouped by position: non-insertion keys (table 0), tombstones of erased
@@ -1083,8 +1110,7 @@ inline void build_patch(const RegionPileup& R, std::vector<rv_patch_entry>* out)
     if (a != R.ni.end())
       for (KeyMap::const_iterator k = a->second.begin(); k != a->second.end(); ++k) {
         rv_patch_entry e;
-        fill_patch(e, R.region_idx, pos, 0, k->first, k->second);
-        out->push_back(e);
+        if (fill_patch(e, R.region_idx, pos, 0, k->first, k->second)) out->push_back(e);
       }
     for (int al = 0; al < 4; ++al) {
       char b = "ACGT"[al];
@@ -1098,8 +1124,7 @@ inline void build_patch(const RegionPileup& R, std::vector<rv_patch_entry>* out)
     if (b != R.ins.end())
       for (KeyMap::const_iterator k = b->second.begin(); k != b->second.end(); ++k) {
         rv_patch_entry e;
-        fill_patch(e, R.region_idx, pos, 1, k->first, k->second);
-        out->push_back(e);
+        if (fill_patch(e, R.region_idx, pos, 1, k->first, k->second)) out->push_back(e);
       }
   }
 }

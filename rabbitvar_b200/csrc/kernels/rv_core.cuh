@@ -109,11 +109,11 @@ struct Cigar {
 
 // Small fixed-capacity key builder (allele description strings, include/Variant.h:24-33).
 struct Key {
-  char c[48];
+  char c[RV_EVENT_KEY_MAX];
   int n;
   bool trunc;
   RV_HD void clear() { n = 0; trunc = false; }
-  RV_HD void push(char ch) { if (n < 48) c[n++] = ch; else trunc = true; }
+  RV_HD void push(char ch) { if (n < RV_EVENT_KEY_MAX) c[n++] = ch; else trunc = true; }
   RV_HD void push_int(int v) {
     char tmp[12];
     int k = 0;
@@ -126,7 +126,7 @@ struct Key {
   }
   RV_HD void insert_at(int idx, char ch) {  // std::string::insert(idx, 1, ch); idx <= n assumed
     if (idx > n) idx = n;
-    if (n >= 48) { trunc = true; return; }
+    if (n >= RV_EVENT_KEY_MAX) { trunc = true; return; }
     for (int k = n; k > idx; --k) c[k] = c[k - 1];
     c[idx] = ch;
     n++;
@@ -136,7 +136,7 @@ struct Key {
       if (c[k] == ch) { for (int j = k; j + 1 < n; ++j) c[j] = c[j + 1]; n--; return; }
   }
   RV_HD void prepend(const char* s, int len) {
-    if (n + len > 48) { trunc = true; return; }
+    if (n + len > RV_EVENT_KEY_MAX) { trunc = true; return; }
     for (int k = n - 1; k >= 0; --k) c[k + len] = c[k];
     for (int k = 0; k < len; ++k) c[k] = s[k];
     n += len;
@@ -682,7 +682,17 @@ RV_HD void emit_event(Sink& s, WalkState& w, int region_idx, uint32_t read_idx, 
   e.aux0 = aux0;
   e.aux1 = aux1;
   e.aux2 = aux2;
-  for (int k = 0; k < 48; ++k) e.key[k] = (key && k < key->n) ? key->c[k] : (char)0;
+  // (whole words: the key area is 4-byte aligned in both structs; bytes past the key are zero)
+  const int kn = key ? key->n : 0;
+  for (int k = 0; k < RV_EVENT_KEY_MAX; k += 4) {
+    uint32_t w = 0;
+    if (k < kn) {
+      for (int j = 0; j < 4; ++j)
+        if (k + j < kn) w |= (uint32_t)(uint8_t)key->c[k + j] << (8 * j);
+    }
+    *(uint32_t*)(e.key + k) = w;
+  }
+  if (key && key->trunc) s.unsupported();  // counted, never scored silently (the host stage refuses the batch)
   s.event(e);
 }
 
