@@ -28,9 +28,9 @@ def test_every_declared_symbol_is_exported(built):
 
 def test_abi_version_and_struct_sizes(built):
     L = rv.lib()
-    assert L.rv_abi_version() == 3
+    assert L.rv_abi_version() == 4
     assert C.sizeof(rv.Read) == 32          # fixed per-read header (SURVEY §8d accounting)
-    assert C.sizeof(rv.Event) == 96
+    assert C.sizeof(rv.Event) == 160     # 48 fixed bytes + RV_EVENT_KEY_MAX
     assert C.sizeof(rv.Region) == 40
     assert C.sizeof(rv.Variant) == 152
 
