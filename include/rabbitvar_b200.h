@@ -28,7 +28,7 @@ extern "C" {
 #define RV_ERR_ARG (-1)
 #define RV_ERR_CUDA (-2)
 #define RV_ERR_NOMEM (-3)
-#define RV_ERR_OVERFLOW (-4) /* event buffer / CIGAR op table / halo exceeded: raise the limits in rv_limits */
+#define RV_ERR_OVERFLOW (-4) /* event / variant / patch buffer exceeded: raise the limits in rv_limits */
 #define RV_ERR_STATE (-5)
 
 typedef struct rv_ctx rv_ctx;
@@ -254,10 +254,15 @@ typedef struct rv_pileup_stats {
   int64_t n_reads_kept;     /* pairs that passed every read filter */
   int64_t n_aligned_bases;  /* M/=/X bases of kept reads (the throughput unit) */
   int64_t n_events;
-  int64_t n_overflow;       /* dropped observations (halo / op-table / event-buffer overflow) */
+  int64_t n_overflow;       /* events that did not fit limits.max_events (rv_pileup then returns RV_ERR_OVERFLOW) */
   int64_t n_unsupported;    /* reads that hit a corner the device path refuses (counted, not guessed) */
   int64_t n_walk_items;     /* work items that took the exact CIGAR walk (rv_walk_kernel) ... */
   int64_t n_walk_full;      /* ... of which the whole read was walked (the rest: soft clips of a plain read only) */
+  int64_t n_clipped;        /* soft-clip re-extension / deletion / look-ahead coverage observations that fell outside
+                               [start - halo, end + halo] and were dropped (raise limits.halo for long reads); the
+                               matched bases themselves are only ever counted inside the region (parseCigar.cpp:884) */
+  int64_t n_score_unsupported; /* positions where createInsertion would edit the neighbouring position's reference
+                               allele (ToVarsBuilder.cpp:405-415): counted by the last scoring call */
 } rv_pileup_stats;
 int rv_get_pileup_stats(rv_ctx* ctx, rv_pileup_stats* out);
 /* maxReadLength per region after the pileup (parseCigar.cpp:598-601). */

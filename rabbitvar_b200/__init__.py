@@ -96,7 +96,8 @@ class Variant(C.Structure):
 class PileupStats(C.Structure):
     _fields_ = [("n_items", C.c_int64), ("n_reads_kept", C.c_int64), ("n_aligned_bases", C.c_int64),
                 ("n_events", C.c_int64), ("n_overflow", C.c_int64), ("n_unsupported", C.c_int64),
-                ("n_walk_items", C.c_int64), ("n_walk_full", C.c_int64)]
+                ("n_walk_items", C.c_int64), ("n_walk_full", C.c_int64), ("n_clipped", C.c_int64),
+                ("n_score_unsupported", C.c_int64)]
 
 
 class Timing(C.Structure):

@@ -25,6 +25,7 @@ struct ReadBatch {
   int32_t max_ref_span;
   ReadBatch() : max_ref_span(0) {}
   void clear() { reads.clear(); pool.clear(); max_ref_span = 0; }
+  void swap(ReadBatch& o) { reads.swap(o.reads); pool.swap(o.pool); std::swap(max_ref_span, o.max_ref_span); }
   rv_read_batch view() const {
     rv_read_batch b;
     b.n_reads = (int64_t)reads.size();
@@ -125,6 +126,34 @@ inline int64_t append_batch(ReadBatch& a, const ReadBatch& b) {
   }
   if (b.max_ref_span > a.max_ref_span) a.max_ref_span = b.max_ref_span;
   return off;
+}
+
+// Region descriptors against reads [r0, r1) of the batch only (one fetched span of one sample; the batch may hold
+// several spans / samples one after the other, each sorted by position).
+inline void make_regions_range(const ReadBatch& b, const std::vector<RegionSpec>& specs, int32_t chr_len, int32_t ref_ext,
+                               int32_t nucl_ext, int64_t r0, int64_t r1, std::vector<rv_region>* out) {
+  out->clear();
+  for (size_t i = 0; i < specs.size(); ++i) {
+    rv_region r;
+    r.start = specs[i].start;
+    r.end = specs[i].end;
+    int lo = r.start - nucl_ext - ref_ext;
+    if (lo < 1) lo = 1;
+    int hi = r.end + nucl_ext + ref_ext;
+    if (hi > chr_len) hi = chr_len;
+    r.ref_lo = lo;
+    r.ref_hi = hi - 17;
+    r.chr_len = chr_len;
+    r.max_read_len_in = 0;
+    const int64_t want_lo = (int64_t)r.start - 1 - b.max_ref_span;
+    int64_t a = r0, z = r1;
+    while (a < z) { const int64_t m = (a + z) / 2; if ((int64_t)b.reads[(size_t)m].pos - 1 < want_lo) a = m + 1; else z = m; }
+    r.read_lo = a;
+    a = r0; z = r1;
+    while (a < z) { const int64_t m = (a + z) / 2; if (b.reads[(size_t)m].pos - 1 < r.end) a = m + 1; else z = m; }
+    r.read_hi = a < r.read_lo ? r.read_lo : a;
+    out->push_back(r);
+  }
 }
 
 // Fills rv_region entries for regions (all on one contig, any order) against a loaded batch.

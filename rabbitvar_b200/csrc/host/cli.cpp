@@ -2,15 +2,15 @@
 // for the pileup-and-score path (reference src/Launcher.cpp:295-496 cmdParse, src/RegionBuilder.cpp:45-109
 // buildRegions, :179-200 buildRegionFromConfiguration, src/modes/simpleMode.cpp:210-387 SimpleMode::process).
 //
-// The OpenMP region loop of the reference becomes region batches sharded over GPUs: the ordered region
-// list is cut into contiguous blocks, block g goes to GPU g (one host thread + one rv_ctx per GPU), and the
-// host concatenates the TSV blocks in region order (replaces the `omp critical` write, simpleMode.cpp:339).
+// The OpenMP region loop of the reference becomes the three-stage job pipeline of file_pipeline.hpp: --th decode
+// threads (BGZF inflate + BAM parse, one file handle each) feed GPU worker contexts on --gpus devices, the host
+// concatenates the jobs' TSV in region order (replaces the `omp critical` write, simpleMode.cpp:339).
 // No collective sits on the path.
 //
 // Supported: simple mode (-b one BAM) and paired somatic mode (-b 'tumor.bam|normal.bam', somaticMode.cpp), -R or
 // -i BED with -c/-S/-E/-g, the scoring/filter flags below.
 #include "../../../include/rabbitvar_b200.h"
-#include "pipeline.hpp"
+#include "file_pipeline.hpp"
 #include <thread>
 #include <fstream>
 #include <sstream>
@@ -23,7 +23,8 @@ struct Cli {
   std::string fasta, bam, bam2, region, bed, out = "./out.txt", sample, delim = "\t";
   int c_col = 2, S_col = 6, E_col = 7, g_col = 12;  // DEFAULT_BED_ROW_FORMAT (Launcher.cpp:21), 0-based after -1
   bool c_set = false, S_set = false, E_set = false, g_set = false, zero_based = false;
-  int nucl_ext = 0, ref_ext = 1200, gpus = 1, threads = 1, batch_regions = 256;
+  int nucl_ext = 0, ref_ext = 1200, gpus = 1, threads = 1, batch_regions = 256, halo = 512, workers = 3, job_mb = 24;
+  bool auto_resize = false, threads_set = false, decode_only = false;
   rv_params P;
 };
 
@@ -32,7 +33,7 @@ static void usage() {
           "usage: rabbitvar_b200 -G ref.fa -b in.bam (-R chr:start-end | -i regions.bed -c 1 -S 2 -E 3 -g 4) [options]\n"
           "  -N name  -f freq  -k 0|1  -3  -u  --UN  -p  -t  --fisher  -q phred  -m mismatches  -X ext  -P pos  -r minr\n"
           "  -B minbias  -Q mapq  -o qratio  -O mapq  -V lofreq  -M minmatch  -T trim  -F hexfilter  -x extend  -Y refext\n"
-          "  -z  --th n  --gpus n  --out file\n");
+          "  -z  --auto_resize  --th n  --gpus n  --workers n (GPU contexts per device)  --halo n  --out file\n");
 }
 
 static bool parse(int argc, char** argv, Cli& c) {
@@ -85,10 +86,15 @@ static bool parse(int argc, char** argv, Cli& c) {
     else if (a == "-F" || a == "--Filter") c.P.samfilter = (int)strtol(val().c_str(), NULL, 16);
     else if (a == "-x" || a == "--numcl_extend") c.nucl_ext = atoi(val().c_str());
     else if (a == "-Y" || a == "--ref-extension") c.ref_ext = atoi(val().c_str());
-    else if (a == "--th") c.threads = std::max(1, atoi(val().c_str()));
+    else if (a == "--th") { c.threads = std::max(1, atoi(val().c_str())); c.threads_set = true; }
+    else if (a == "--halo") c.halo = std::max(64, atoi(val().c_str()));
+    else if (a == "--workers") c.workers = std::max(1, atoi(val().c_str()));
+    else if (a == "--job-mb") c.job_mb = std::max(1, atoi(val().c_str()));
+    else if (a == "--auto_resize") c.auto_resize = true;
+    else if (a == "--decode-only") c.decode_only = true;
     else if (a == "--gpus") c.gpus = std::max(1, atoi(val().c_str()));
     else if (a == "--batch-regions") c.batch_regions = std::max(1, atoi(val().c_str()));
-    else if (a == "--auto_resize" || a == "-y" || a == "--verbose" || a == "--chimeric" || a == "--deldupvar") {}
+    else if (a == "-y" || a == "--verbose" || a == "--chimeric" || a == "--deldupvar") {}
     else if (a == "-Z" || a == "--downsample") {
       // recordPreprocessor.cpp:133 drops records by rand(): "random and non-reproducible" (Launcher.cpp:355)
       fprintf(stderr, "-Z (random downsampling) is not supported: its output is not reproducible by definition\n");
@@ -171,110 +177,22 @@ static bool build_regions(const Cli& c, const rvio::BamHeader& hdr, std::vector<
     if (c.zero_based && ts < te) ts++;
     r.start = ts;
     r.end = te;
+    // --auto_resize: RegionBuilder::AdjustRegionSize (RegionBuilder.cpp:16-38, REGION_SIZE_MAX 10000) — literal: the
+    // pieces are [s, s+10000], [s+10000, s+20000], ...: neighbouring pieces share their boundary position
+    if (c.auto_resize && r.end - r.start > 10000) {
+      int s0 = r.start;
+      while (r.end - s0 > 10000) {
+        RegionSpec piece = r;
+        piece.start = s0;
+        piece.end = s0 + 10000;
+        out->push_back(piece);
+        s0 += 10000;
+      }
+      r.start = s0;
+    }
     out->push_back(r);
   }
   return true;
-}
-
-struct Block {
-  std::vector<RegionSpec> specs;  // same contig, ascending
-  std::string tsv;
-  int64_t bases = 0, reads = 0, lines = 0;
-  int64_t cov_sum[2] = {0, 0}, cov_pos[2] = {0, 0};
-  double pileup_ms = 0, score_ms = 0;
-  std::string err;
-};
-
-static void worker(const Cli& c, int device, std::vector<Block*> blocks) {
-  rvio::BamReader bam;
-  rvio::BaiIndex bai;
-  rvio::Fasta fa;
-  if (!bam.open(c.bam) || !bai.load(c.bam + ".bai") || !fa.open(c.fasta)) {
-    for (Block* b : blocks) b->err = "cannot open BAM/BAI/FASTA";
-    return;
-  }
-  const bool somatic = !c.bam2.empty();
-  rvio::BamReader bamN;
-  rvio::BaiIndex baiN;
-  if (somatic && (!bamN.open(c.bam2) || !baiN.load(c.bam2 + ".bai"))) {
-    for (Block* b : blocks) b->err = "cannot open the second BAM/BAI";
-    return;
-  }
-  rv_ctx* ctx = NULL;
-  rv_limits L;
-  rv_default_limits(&L);
-  int64_t cap_reads = 0, cap_bytes = 0, cap_pos = 0, cap_ref = 0;
-  for (Block* blk : blocks) {
-    try {
-      const std::string& chr = blk->specs[0].chr;
-      int tid = bam.header().tid_of(chr);
-      if (tid < 0) { blk->err = "contig not in BAM: " + chr; continue; }
-      int32_t chr_len = bam.header().lens[tid];
-      int32_t smin = blk->specs[0].start, smax = blk->specs[0].end;
-      for (auto& s : blk->specs) { smin = std::min(smin, s.start); smax = std::max(smax, s.end); }
-      ReadBatch batch;
-      load_span(bam, bai, tid, smin, smax, &batch);
-      std::vector<rv_region> regs;
-      make_regions(batch, blk->specs, chr_len, c.ref_ext, c.nucl_ext, &regs);
-      if (somatic) {  // the same tiles of the normal sample follow the tumor's (one_region_run_somt)
-        int tidN = bamN.header().tid_of(chr);
-        if (tidN < 0) { blk->err = "contig not in the second BAM: " + chr; continue; }
-        ReadBatch batchN;
-        load_span(bamN, baiN, tidN, smin, smax, &batchN);
-        std::vector<rv_region> regsN;
-        make_regions(batchN, blk->specs, chr_len, c.ref_ext, c.nucl_ext, &regsN);
-        const int64_t off = append_batch(batch, batchN);
-        for (auto& r : regsN) { r.read_lo += off; r.read_hi += off; regs.push_back(r); }
-      }
-      int32_t ref_lo = std::max(1, smin - c.ref_ext - c.nucl_ext - 100);
-      int32_t ref_hi = std::min(chr_len, smax + c.ref_ext + c.nucl_ext + 100);
-      std::string refseq;
-      fa.fetch(chr, ref_lo, ref_hi, &refseq);
-      for (auto& ch : refseq) ch = (char)toupper((unsigned char)ch);
-      int64_t npos = 0;
-      for (auto& r : regs) npos += r.end - r.start + 1 + 2 * L.halo;
-      if (!ctx || (int64_t)batch.reads.size() > cap_reads || (int64_t)batch.pool.size() > cap_bytes || npos > cap_pos ||
-          (int64_t)refseq.size() > cap_ref) {
-        if (ctx) rv_destroy(ctx);
-        cap_reads = std::max<int64_t>(cap_reads, (int64_t)batch.reads.size() * 5 / 4 + 1024);
-        cap_bytes = std::max<int64_t>(cap_bytes, (int64_t)batch.pool.size() * 5 / 4 + 4096);
-        cap_pos = std::max<int64_t>(cap_pos, npos * 5 / 4 + 1024);
-        cap_ref = std::max<int64_t>(cap_ref, (int64_t)refseq.size() * 5 / 4 + 1024);
-        L.max_reads = cap_reads;
-        L.max_read_bytes = cap_bytes;
-        L.max_positions = cap_pos;
-        L.max_regions = (int32_t)std::max<size_t>(regs.size(), (size_t)c.batch_regions * (somatic ? 2 : 1)) + 1;
-        L.max_events = std::max<int64_t>(1 << 16, cap_reads * 4);
-        L.max_variants = (somatic ? 3 : 1) * cap_pos + 1024;
-        L.max_patch = std::max<int64_t>(1 << 16, cap_reads);
-        L.max_ref_bases = cap_ref;
-        int rc = rv_create(&ctx, device, &c.P, &L);
-        if (rc != RV_OK) {
-          blk->err = std::string("rv_create: ") + (ctx ? rv_last_error(ctx) : "no CUDA device (there is no CPU path)");
-          if (ctx) rv_destroy(ctx);
-          ctx = NULL;
-          continue;
-        }
-      }
-      std::vector<std::string> genes;
-      for (auto& s : blk->specs) genes.push_back(s.gene);
-      BatchTiming tm;
-      int rc = somatic ? run_batch_somatic(ctx, c.P, batch, regs, genes, refseq, ref_lo, c.sample, chr, 3, L.halo, &blk->tsv, &tm, &blk->err)
-                       : run_batch_simple(ctx, c.P, batch, regs, genes, refseq, ref_lo, c.sample, chr, 3, L.halo, &blk->tsv, &tm, &blk->err);
-      if (rc != RV_OK) continue;
-      blk->bases = tm.stats.n_aligned_bases;
-      blk->reads = tm.stats.n_reads_kept;
-      blk->lines = tm.n_lines;
-      for (int k = 0; k < 2; ++k) { blk->cov_sum[k] = tm.cov_sum[k]; blk->cov_pos[k] = tm.cov_pos[k]; }
-      blk->pileup_ms = tm.pileup_kernel_ms;
-      blk->score_ms = tm.score_kernel_ms;
-      if (tm.stats.n_unsupported)
-        fprintf(stderr, "[warn] %lld reads hit a corner the device path refuses (see DESIGN.md)\n", (long long)tm.stats.n_unsupported);
-    } catch (const std::exception& e) {
-      blk->err = e.what();
-    }
-  }
-  if (ctx) rv_destroy(ctx);
 }
 
 int main(int argc, char** argv) {
@@ -294,51 +212,49 @@ int main(int argc, char** argv) {
     return 1;
   }
   int ndev = rv_device_count();
-  if (ndev <= 0) {
+  if (ndev <= 0 && !c.decode_only) {
     fprintf(stderr, "rabbitvar_b200: no CUDA device visible; this build has no CPU path\n");
     return 3;
   }
-  c.gpus = std::min(c.gpus, ndev);
-  // blocks: consecutive regions of one contig, at most batch_regions each (a tile is the parity unit;
-  // blocks never split a region)
-  std::vector<Block> blocks;
-  for (size_t i = 0; i < specs.size();) {
-    Block b;
-    size_t j = i;
-    while (j < specs.size() && specs[j].chr == specs[i].chr && (int)(j - i) < c.batch_regions) b.specs.push_back(specs[j++]);
-    blocks.push_back(b);
-    i = j;
-  }
-  std::vector<std::vector<Block*> > per_gpu(c.gpus);
-  for (size_t i = 0; i < blocks.size(); ++i) per_gpu[i * c.gpus / blocks.size()].push_back(&blocks[i]);
-  std::vector<std::thread> th;
-  for (int g = 0; g < c.gpus; ++g) th.emplace_back(worker, std::cref(c), g, per_gpu[g]);
-  for (auto& t : th) t.join();
+  FileRunConfig fc;
+  fc.fasta = c.fasta; fc.bam = c.bam; fc.bam2 = c.bam2; fc.sample = c.sample;
+  fc.P = c.P;
+  fc.ref_ext = c.ref_ext; fc.nucl_ext = c.nucl_ext;
+  fc.decode_threads = c.threads;                 // --th, default 1 like the reference (Launcher.cpp:474)
+  fc.gpus = c.decode_only ? 1 : std::min(c.gpus, ndev);
+  fc.decode_only = c.decode_only;
+  fc.workers_per_gpu = c.workers;
+  fc.max_regions_per_job = c.batch_regions;
+  fc.job_bytes = (int64_t)c.job_mb << 20;
+  fc.halo = c.halo;
+  std::string tsv;
+  FileRunStats st;
+  std::vector<std::string> errors;
+  int rc = run_files(fc, specs, &tsv, &st, &errors);
+  for (size_t i = 0; i < errors.size(); ++i) fprintf(stderr, "[error] %s\n", errors[i].c_str());
+  if (rc == 1) return 1;
   FILE* out = fopen(c.out.c_str(), "wb");
   if (!out) { fprintf(stderr, "open file: %s error!\n", c.out.c_str()); return 1; }
-  int64_t bases = 0, lines = 0;
-  double kms = 0;
-  int rc = 0;
-  for (auto& b : blocks) {
-    if (!b.err.empty()) { fprintf(stderr, "[error] %s\n", b.err.c_str()); rc = 2; }
-    fwrite(b.tsv.data(), 1, b.tsv.size(), out);
-    bases += b.bases;
-    lines += b.lines;
-    kms += b.pileup_ms + b.score_ms;
-  }
+  fwrite(tsv.data(), 1, tsv.size(), out);
   fclose(out);
   if (!c.bam2.empty()) {  // SomaticMode::process, somaticMode.cpp:916-929: average coverages (both over the tumor's sites)
-    int64_t ts = 0, tp = 0, ns = 0;
-    for (auto& b : blocks) { ts += b.cov_sum[0]; tp += b.cov_pos[0]; ns += b.cov_sum[1]; }
     FILE* info = fopen((c.out + ".info").c_str(), "wb");
     if (info) {
-      const std::string s = std::to_string(ts / (double)tp) + "\n" + std::to_string(ns / (double)tp) + "\n";
+      const std::string s = std::to_string(st.cov_sum[0] / (double)st.cov_pos[0]) + "\n" + std::to_string(st.cov_sum[1] / (double)st.cov_pos[0]) + "\n";
       fwrite(s.data(), 1, s.size(), info);
       fclose(info);
     }
   }
-  printf("[info] output file name: %s\n[info] regions: %zu blocks: %zu gpus: %d aligned bases: %lld variant lines: %lld kernel ms: %.3f\n",
-         c.out.c_str(), specs.size(), blocks.size(), c.gpus, (long long)bases, (long long)lines, kms);
+  if (st.n_unsupported)
+    fprintf(stderr, "[warn] %lld reads hit a corner the device path refuses (see DESIGN.md): their observations are missing\n", (long long)st.n_unsupported);
+  if (st.dropped_keys)
+    fprintf(stderr, "[warn] %lld allele keys longer than %d characters were dropped by the host stage\n", (long long)st.dropped_keys, RV_PATCH_KEY_MAX);
+  if (st.n_clipped)
+    fprintf(stderr, "[warn] %lld observations fell outside the table halo of %d positions and were dropped (--halo)\n", (long long)st.n_clipped, c.halo);
+  printf("[info] output file name: %s\n[info] regions: %zu jobs: %lld gpus: %d x %d contexts, decode threads: %d, aligned bases: %lld variant lines: %lld "
+         "kernel ms: %.3f, decode thread-ms %.0f, gpu-worker thread-ms %.0f, launches %lld\n",
+         c.out.c_str(), specs.size(), (long long)st.n_jobs, fc.gpus, fc.workers_per_gpu, fc.decode_threads, (long long)st.bases, (long long)st.lines,
+         st.pileup_kernel_ms + st.score_kernel_ms, st.decode_thread_ms, st.gpu_worker_ms, (long long)st.launches);
   printf("total time: %f s \n", (now_ms() - t0) / 1000.0);
   return rc;
 }

@@ -43,6 +43,7 @@ static const int GATHER_TILE = 256;
 struct DevStats {
   unsigned long long n_items, n_kept, n_bases, n_events, n_overflow, n_unsupported, n_variants, n_score_unsupported;
   unsigned long long n_walk_items, n_walk_full;
+  unsigned long long n_clipped;  // observations outside [start - halo, end + halo]: dropped, like the gather path clips
 };
 
 // Gather descriptor of one (region, read) work item whose rewritten CIGAR is [H][S] M [S][H] and whose matched
@@ -97,7 +98,7 @@ struct DeviceSink {
   uint32_t* covtab;
   double goodq;
   int goodq_i;  // ceil(goodq): integer qualities compare against it
-  int kept_bases, n_kept, n_unsup, n_over, n_ev;
+  int kept_bases, n_kept, n_unsup, n_over, n_ev, n_clip;
   uint32_t* pend_row;
   uint32_t pend_old, pend_mine;
   bool pend;
@@ -112,7 +113,7 @@ struct DeviceSink {
   }
   __device__ __forceinline__ bool idx_of(int pos, int* idx) {
     int i = pos - first_pos;
-    if (i < 0 || i >= n_pos) { n_over++; return false; }
+    if (i < 0 || i >= n_pos) { n_clip++; return false; }
     *idx = i;
     return true;
   }
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
   pr.m_start = pr.m_len = pr.rp0 = 0;
   DeviceSink s;
   s.a = &a;
-  s.kept_bases = s.n_kept = s.n_unsup = s.n_over = s.n_ev = 0;
+  s.kept_bases = s.n_kept = s.n_unsup = s.n_over = s.n_ev = s.n_clip = 0;
   s.mute = false;
   s.pend = false;
   s.goodq = a.P.goodq;
@@ -433,7 +434,7 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(128, MIN_CTAS) rv_walk_kernel(PileupArgs a) {
   const unsigned long long n_full = a.walk_count[0], n = n_full + a.walk_count[1];
-  unsigned long long over = 0, unsup = 0, full = 0;
+  unsigned long long over = 0, unsup = 0, full = 0, clip = 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) a.stats->n_walk_items = n;
   const int lane = threadIdx.x & 31;
   for (;;) {
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) rv_walk_kernel(PileupArgs a) {
     DeviceSink s;
     s.a = &a;
     s.bind(dr, a.counts, a.cov);
-    s.kept_bases = s.n_kept = s.n_unsup = s.n_over = s.n_ev = 0;
+    s.kept_bases = s.n_kept = s.n_unsup = s.n_over = s.n_ev = s.n_clip = 0;
     s.goodq = a.P.goodq;
     s.goodq_i = iceil(a.P.goodq);
     s.pend = false;
@@ -477,7 +478,9 @@ __global__ void __launch_bounds__(128, MIN_CTAS) rv_walk_kernel(PileupArgs a) {
     s.resolve();
     over += s.n_over;
     unsup += s.n_unsup;
+    clip += s.n_clip;
   }
+  if (clip) atomicAdd(&a.stats->n_clipped, clip);
   if (over) atomicAdd(&a.stats->n_overflow, over);
   if (unsup) atomicAdd(&a.stats->n_unsupported, unsup);
   if (full) atomicAdd(&a.stats->n_walk_full, full);
@@ -2168,7 +2171,7 @@ int rv_pileup(rv_ctx* ctx) {
   // the patch list stays attached until rv_set_regions / the next rv_apply_patch: a caller that
   // re-runs the same resident batch may score against it again
   ctx->tables_fetched = false;
-  if (ctx->h_stats.n_overflow) return fail(ctx, RV_ERR_OVERFLOW, "pileup dropped observations (halo/event buffer too small)");
+  if (ctx->h_stats.n_overflow) return fail(ctx, RV_ERR_OVERFLOW, "pileup dropped events (limits.max_events too small)");
   return RV_OK;
 }
 
@@ -2182,6 +2185,8 @@ int rv_get_pileup_stats(rv_ctx* ctx, rv_pileup_stats* o) {
   o->n_unsupported = (int64_t)ctx->h_stats.n_unsupported;
   o->n_walk_items = (int64_t)ctx->h_stats.n_walk_items;
   o->n_walk_full = (int64_t)ctx->h_stats.n_walk_full;
+  o->n_clipped = (int64_t)ctx->h_stats.n_clipped;
+  o->n_score_unsupported = (int64_t)ctx->h_stats.n_score_unsupported;
   return RV_OK;
 }
 
