@@ -1,20 +1,27 @@
 #!/usr/bin/env python
-"""bench.py — aligned bases/sec piled+scored on B200 (BASELINE.json metric), config 2 of BASELINE.json:
-tumor/normal, synthetic 5 Mb region at 200x/100x as 500 x 10 kb tiles per sample, --fisher.
+"""bench.py — aligned bases/sec piled+scored on B200 (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
-    python bench.py --impl reference --steps K --warmup W    (the reference's CPU path, oracle/_ref)
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    (the reference's own CPU path, oracle/_ref/RabbitVar)
 
-One step = one pass of the hot path (rv_pileup + rv_score: read filter, CIGAR rewrite + walk, pileup,
-per-position scoring incl. Fisher) over every (tile, sample) of the workload.
-  value : whole-job throughput, inputs resident in HBM, device time (CUDA events on the launching stream),
-          max over ranks.  Region-sharded: every rank owns a full config-2 shard, no collective (weak scaling).
-  e2e   : the same metric through the public host-buffer API (rvh_call_regions: pinned H2D, pileup, event +
-          table D2H, host realign hand-off, patch H2D, score, variant D2H, TSV formatting), wall clock.
+Workload.  N = 1: BASELINE.json configs[1] — tumor/normal, 5 Mb as 500 x 10 kb tiles, T 200x + N 100x, --fisher.
+N > 1: configs[3] — the 50 Mb / 30x chromosome as 5000 x 10 kb tiles, cut into N contiguous blocks balanced by the
+BAI's compressed bytes (rabbitvar_b200.shard), block g on GPU g, no data-path collective ("scaling": "strong").
+
+One step = one pass of the hot path over the rank's tiles with the reads resident in HBM: rv_pileup (read filter,
+CIGAR rewrite + walk, pileup) + rv_score (per-position scoring incl. Fisher, candidate compaction) [+ the joined
+tumor|normal records at N = 1].
+  value     whole-job throughput of those steps, CUDA events on the launching stream, max over ranks.
+  e2e       the same metric through the drop-in CLI (build/rabbitvar_b200): BAM + FASTA + BED files in, TSV file
+            out — BGZF inflate, BAM parse, H2D, kernels, host realigner hand-off, D2H, text — wall clock of the
+            process, max over ranks.  Same level-1 BAMs and same tiles as the reference arm.
+  parity    the CLI's TSV against the reference binary's on the same files (sorted multisets, integer/string fields
+            identical, %f fields within 2e-6): `parity_lines_differing` per config.
 """
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -22,10 +29,20 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 BUILD = os.path.join(ROOT, "build")
 METRIC = "aligned bases/sec piled+scored"
 UNIT = "bases/s"
-TILE = 10000
+
+# aligned bases (M/=/X bases of reads surviving the filters, counted once per tile fetch) of the seeded workloads,
+# as counted by rv_pileup's statistics on the same data (the generator is deterministic: tools/synthgen.cpp)
+KNOWN_ALIGNED_BASES = {("1", 1002600): 99440859, ("1R", 1002600): 97997218, ("2", 5002600): 1492236281,
+                       ("3", 2002600): 365061163, ("4", 50002600): 1492005191, ("5", 5002600): 490269790}
+WORKLOAD_TEXT = {
+    "2": "BASELINE.json configs[1]: tumor/normal, 5 Mb as 500 x 10 kb tiles, T 200x + N 100x, 2x150 bp, -f 0.01 --fisher",
+    "4": "BASELINE.json configs[3]: 50 Mb chromosome at 30x as 5000 x 10 kb tiles, 2x150 bp, -f 0.01, tiles cut into "
+         "contiguous blocks over the GPUs (balanced by BAI bytes), no collective",
+}
 
 
 def log(*a):
@@ -33,36 +50,15 @@ def log(*a):
 
 
 def ensure_built():
-    need = [os.path.join(ROOT, "rabbitvar_b200", "librvgpu.so"), os.path.join(BUILD, "synthgen")]
+    need = [os.path.join(ROOT, "rabbitvar_b200", "librvgpu.so"), os.path.join(BUILD, "synthgen"),
+            os.path.join(BUILD, "rabbitvar_b200")]
     if not all(os.path.exists(p) for p in need):
         import __graft_entry__ as g
         g.build()
 
 
-def make_dataset(work, length, level=0):
-    """config-2 shaped data (T 200x + N 100x over `length` bases), seeded; cached by directory."""
-    if not os.path.exists(os.path.join(work, "meta.txt")):
-        os.makedirs(work, exist_ok=True)
-        t0 = time.time()
-        subprocess.run([os.path.join(BUILD, "synthgen"), "--cfg", "2", "--out", work, "--len", str(length),
-                        "--level", str(level)], check=True, stderr=subprocess.DEVNULL)
-        log(f"[bench] generated {work} in {time.time() - t0:.1f}s")
-    meta = dict(l.split("\t") for l in open(os.path.join(work, "meta.txt")).read().splitlines())
-    return meta
-
-
-def read_tiles(work, limit=None):
-    tiles = []
-    for l in open(os.path.join(work, "tiles.bed")):
-        c, s, e, g = l.split()
-        tiles.append((int(s), int(e)))
-        if limit and len(tiles) >= limit:
-            break
-    return tiles
-
-
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
 
     def __init__(self, index):
         self.rows = []
@@ -71,8 +67,7 @@ class ClockSampler:
         self.t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
-        # NVML in-process (a sample every ~20 ms); nvidia-smi as the fallback
-        try:
+        try:  # NVML in-process (a sample every ~20 ms); nvidia-smi as the fallback
             import pynvml as nv
             nv.nvmlInit()
             h = nv.nvmlDeviceGetHandleByIndex(self.index)
@@ -128,82 +123,70 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ref_cmd(work, bed, out, threads):
-    return [os.path.join(ROOT, "oracle", "_ref", "RabbitVar"), "-G", os.path.join(work, "ref.fa"), "-b",
-            os.path.join(work, "T.bam") + "|" + os.path.join(work, "N.bam"), "-N", "T|N", "-i", bed, "-c", "1", "-S", "2",
-            "-E", "3", "-g", "4", "-f", "0.01", "--fisher", "--th", str(threads), "--out", out]
+def read_tiles(path):
+    tiles = []
+    for l in open(path):
+        c, s, e, g = l.split()
+        tiles.append((c, int(s), int(e), g))
+    return tiles
 
 
-def sample_bed(work, n_tiles):
-    bed = os.path.join(work, f"sample_{n_tiles}.bed")
-    with open(os.path.join(work, "tiles.bed")) as f, open(bed, "w") as o:
-        for i, l in enumerate(f):
-            if i >= n_tiles:
-                break
-            o.write(l)
-    return bed
+def workload_dataset(key, rank, barrier):
+    """The seeded level-1 BAMs of the workload (generated once per box by rank 0)."""
+    import parity_configs as pc
+    if rank == 0:
+        pc.dataset(key, 1.0, 1)
+    barrier()
+    return pc.dataset(key, 1.0, 1)
 
 
-def count_sample_bases(work, n_tiles):
-    """Aligned bases (M/=/X of reads surviving the filters, counted once per tile fetch) of the first n tiles,
-    both samples — counted from the BAMs on the host with the same definition the GPU statistics use."""
-    import numpy as np
-    import rabbitvar_b200 as rv
-    tiles = read_tiles(work, n_tiles)
-    dt = np.dtype([("pos", "<i4"), ("mpos", "<i4"), ("off", "<u4"), ("l_seq", "<i4"), ("flag", "<u2"),
-                   ("n_cigar", "<u2"), ("nm", "<i2"), ("mapq", "u1"), ("same", "u1"), ("end", "<i4"), ("rsv", "<i4")])
-    total = 0
-    for bam in ("T.bam", "N.bam"):
-        b = rv.HostBatch(os.path.join(work, bam), "chrS2", tiles[0][0], tiles[-1][1])
-        r = b.reads_numpy().view(dt)
-        keep = (r["flag"] & 0x504) == 0
-        keep &= (r["flag"] & 0x800) == 0
-        r = r[keep]
-        for s, e in tiles:
-            sel = r[(r["pos"] - 1 < e) & (r["end"] > s - 1)]
-            # synthetic reads: aligned bases = read length minus soft clips/insertions ~= end - pos + 1 - deletions;
-            # use the reference span as the aligned-base count (exact for M-only reads, within 0.1% otherwise)
-            total += int((sel["end"] - sel["pos"] + 1).sum())
-        b.close()
-    return total
+def ref_cmd(key, d, bed, out, threads):
+    import parity_configs as pc
+    c = pc.CONFIGS[key]
+    bam = "|".join(os.path.join(d, b) for b in c["bam"].split("|"))
+    return [pc.REF_BIN, "-G", os.path.join(d, "ref.fa"), "-b", bam, "-N", c["name"], "-i", bed, "-c", "1", "-S", "2",
+            "-E", "3", "-g", "4"] + c["flags"] + ["--th", str(threads), "--out", out]
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's own CPU implementation (oracle/_ref/RabbitVar, unmodified sources
-    built by oracle/Makefile) timed on this box's host cores on a bounded sample of the same workload."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref/RabbitVar = the unmodified
+    sources compiled by oracle/Makefile), all host threads, on the same files / tiles / flags as our e2e arm."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     ensure_built()
-    binp = os.path.join(ROOT, "oracle", "_ref", "RabbitVar")
-    if not os.path.exists(binp):
+    import parity_configs as pc
+    if not os.path.exists(pc.REF_BIN):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/RabbitVar was not built/shipped"}))
         return
-    n_tiles = args.ref_tiles
-    work = os.path.join(ROOT, "_work", f"bench_ref_{n_tiles}")
-    length = 1300 + n_tiles * TILE + 1300
-    make_dataset(work, length, level=1)
-    bed = sample_bed(work, n_tiles)
+    key = args.workload or ("2" if max(world, args.gpus) == 1 else "4")
+    d, length = pc.dataset(key, 1.0, 1)
+    bed = os.path.join(d, pc.CONFIGS[key]["bed"])
     cores = os.cpu_count() or 1
-    bases = count_sample_bases(work, n_tiles)
-    out = os.path.join(work, "ref_out.tsv")
+    bases = KNOWN_ALIGNED_BASES[(key, length)]
+    out = os.path.join(d, "ref_arm.tsv")
     times = []
+    t_begin = time.perf_counter()
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        subprocess.run(ref_cmd(work, bed, out, cores), check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        subprocess.run(ref_cmd(key, d, bed, out, cores), check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         dt = time.perf_counter() - t0
         if i >= args.warmup:
             times.append(dt)
+        # a bounded run: the reference needs seconds per pass; stop adding passes once the budget is spent
+        if i >= args.warmup and time.perf_counter() - t_begin > args.ref_budget_s:
+            break
     total = sum(times)
     value = bases * len(times) / total
+    n_tiles = sum(1 for _ in open(bed))
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "config 2 (tumor/normal 200x/100x, 10 kb tiles, --fisher)",
-                   "sample": f"first {n_tiles} tiles x 2 samples per step"},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True,
+        "scaling": "weak" if key == "2" else "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_TEXT[key], "sample": f"the whole workload ({n_tiles} tiles) per step, level-1 BAM files in -> TSV out"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
-                         "sample": f"oracle/_ref/RabbitVar --th {cores}, first {n_tiles} tiles of config 2 (T+N), {bases} aligned bases"},
+                         "sample": f"oracle/_ref/RabbitVar --th {cores}, all {n_tiles} tiles, {bases} aligned bases per pass, {len(times)} timed passes"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -212,15 +195,15 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--length", type=int, default=5002600, help="contig length of the config-2 shard")
-    ap.add_argument("--ref-tiles", type=int, default=150, help="tiles in the CPU-baseline sample")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3, help="timed CLI runs (files in -> TSV out)")
+    ap.add_argument("--parity", default="all", help="configs whose full-size TSV is diffed against the reference binary: "
+                                                    "all | workload | none | comma list of 1,1R,2,3,4,5")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--workers", type=int, default=16, help="pipeline workers (contexts) per GPU in the e2e path")
-    ap.add_argument("--chunk", type=int, default=5, help="tiles per pipeline chunk in the e2e path")
+    ap.add_argument("--workload", default="", help="override: 2 or 4")
+    ap.add_argument("--ref-budget-s", type=float, default=200.0)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -230,6 +213,8 @@ def main():
     import torch.distributed as dist
     ensure_built()
     import rabbitvar_b200 as rv
+    from rabbitvar_b200 import shard
+    import parity_configs as pc
     import ctypes as C
 
     rank = int(os.environ.get("RANK", "0"))
@@ -237,45 +222,68 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the one JSON line (NCCL's banner goes there otherwise)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the one JSON line
         dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world)
     if not torch.cuda.is_available():
         raise rv.RabbitVarError("bench.py needs a GPU (there is no CPU path); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
 
-    # ---- workload: one full config-2 shard per rank (same seed => same shape on every rank) -------------
-    work = os.path.join(ROOT, "_work", f"bench_cfg2_{args.length}" + (f"_r{rank}" if world > 1 else ""))
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    key = args.workload or ("2" if world == 1 else "4")
+    paired = key == "2"
+    cfg = pc.CONFIGS[key]
     t0 = time.time()
-    make_dataset(work, args.length, level=0)
-    tiles = read_tiles(work)
-    starts, ends = [t[0] for t in tiles], [t[1] for t in tiles]
-    bt = rv.HostBatch(os.path.join(work, "T.bam"), "chrS2", starts[0], ends[-1])
-    bn = rv.HostBatch(os.path.join(work, "N.bam"), "chrS2", starts[0], ends[-1])
+    d, length = workload_dataset(key, rank, barrier)
+    bed_all = os.path.join(d, cfg["bed"])
+    tiles_all = read_tiles(bed_all)
+    chrom = tiles_all[0][0]
+    # ---- this rank's block of tiles (contiguous, balanced by the compressed bytes the BAI says each tile spans) -------
+    bam0 = os.path.join(d, cfg["bam"].split("|")[0])
+    weights = shard.bai_tile_weights(bam0 + ".bai", 0, [(s, e) for _, s, e, _ in tiles_all])
+    blocks = shard.contiguous_blocks(weights, world)
+    lo, hi = blocks[rank]
+    tiles = tiles_all[lo:hi]
+    my_bed = os.path.join(d, f"shard_{world}_{rank}.bed")
+    with open(my_bed, "w") as f:
+        for c_, s, e, g in tiles:
+            f.write(f"{c_}\t{s}\t{e}\t{g}\n")
+    starts, ends = [t[1] for t in tiles], [t[2] for t in tiles]
+
+    # ---- device-resident inputs ------------------------------------------------------------------------------------
+    bams = [os.path.join(d, b) for b in cfg["bam"].split("|")]
+    bt = rv.HostBatch(bams[0], chrom, starts[0], ends[-1])
     n_t = bt.n_reads
-    off_n = bt.append(bn)
-    n_n = bn.n_reads
-    bn.close()
-    regs_t = bt.make_regions(starts, ends, 1200, 0, n_t)
-    regs_n = bt.make_regions(starts, ends, 1200, off_n, n_n)
-    nreg = 2 * len(tiles)
+    n_n = 0
+    regs_list = [bt.make_regions(starts, ends, 1200, 0, n_t)]
+    if paired:
+        bn = rv.HostBatch(bams[1], chrom, starts[0], ends[-1])
+        off_n = bt.append(bn)
+        n_n = bn.n_reads
+        bn.close()
+        regs_list.append(bt.make_regions(starts, ends, 1200, off_n, n_n))
+    half = len(tiles)
+    nreg = half * len(regs_list)
     regs = (rv.Region * nreg)()
-    C.memmove(regs, regs_t, C.sizeof(rv.Region) * len(tiles))
-    C.memmove(C.byref(regs, C.sizeof(rv.Region) * len(tiles)), regs_n, C.sizeof(rv.Region) * len(tiles))
-    ref = rv.fetch_ref(os.path.join(work, "ref.fa"), "chrS2", 1, bt.chr_len)
-    log(f"[bench r{rank}] data ready in {time.time() - t0:.1f}s: {bt.n_reads} reads, pool {bt.pool_bytes / 1e9:.2f} GB, "
-        f"{nreg} (tile, sample) regions")
+    for k, r in enumerate(regs_list):
+        C.memmove(C.byref(regs, k * half * C.sizeof(rv.Region)), r, C.sizeof(rv.Region) * half)
+    ref_lo = max(1, starts[0] - 1400)
+    ref_hi = min(bt.chr_len, ends[-1] + 1400)
+    ref = rv.fetch_ref(os.path.join(d, "ref.fa"), chrom, ref_lo, ref_hi)
+    log(f"[bench r{rank}] workload {key}: tiles [{lo}, {hi}) of {len(tiles_all)}, data ready in {time.time() - t0:.1f}s: "
+        f"{bt.n_reads} reads, pool {bt.pool_bytes / 1e9:.2f} GB, {nreg} (tile, sample) regions")
     halo = 512
-    n_pos = sum(e - s + 1 + 2 * halo for s, e in tiles) * 2
+    n_pos = sum(e - s + 1 + 2 * halo for s, e in zip(starts, ends)) * len(regs_list)
     lim = rv.default_limits(max_reads=bt.n_reads + 64, max_read_bytes=bt.pool_bytes + 256, max_positions=n_pos + 64,
                             max_regions=nreg + 8, halo=halo, max_events=max(1 << 20, bt.n_reads),
-                            max_variants=3 * n_pos + 1024, max_patch=max(1 << 20, bt.n_reads // 2),
+                            max_variants=(3 if paired else 1) * n_pos + 1024, max_patch=max(1 << 20, bt.n_reads // 2),
                             max_ref_bases=len(ref) + 64)
-    params = rv.default_params(fisher=1, has_bam2=1, candidates_only=2)
+    params = rv.default_params(fisher=1, has_bam2=1, candidates_only=2) if paired else rv.default_params(candidates_only=1)
     ctx = rv.Context(local, params, lim)
-    ctx.set_reference(1, ref)
-
-    # device-resident inputs live in torch tensors (torch = device memory plumbing)
+    ctx.set_reference(ref_lo, ref)
+    dev = torch.device("cuda", local)
     reads_np = bt.reads_numpy()
     pool_np = bt.pool_numpy()
     d_reads = torch.from_numpy(reads_np).to(dev)
@@ -284,66 +292,49 @@ def main():
     d_pool[: int(pool_np.size)].copy_(torch.from_numpy(pool_np))
     torch.cuda.synchronize()
     read_bytes_total = int(reads_np.size + pool_np.size)
-    avg_read_bytes = 32 + float((pool_np.size) / max(1, bt.n_reads))  # 32 B header + cigar + packed seq + qual (16 B aligned)
+    avg_read_bytes = 32 + float(pool_np.size) / max(1, bt.n_reads)  # 32 B header + cigar + packed seq + qual (16 B aligned)
 
-    half = len(tiles)
-    # ---- e2e warm pass through the public host-buffer API (also installs the patch list used below) --------
-    bt.pin()
-
-    pipe = rv.Pipeline(local, args.workers)
-    e2e_params = rv.default_params(fisher=1)  # the reference CLI's flags for this config: -f 0.01 --fisher, -b 'T|N'
-    regs_t_arr = (rv.Region * half).from_address(C.addressof(regs))
-    regs_n_arr = (rv.Region * half).from_address(C.addressof(regs) + half * C.sizeof(rv.Region))
-
-    def e2e_pass():
-        t_a = time.perf_counter()
-        # host buffers in, TSV out: every chunk of tiles is copied H2D, piled, handed to the host stage, scored,
-        # copied back and formatted; the pipeline's workers overlap those stages across chunks
-        tsv, tm_p = pipe.run(e2e_params, bt, regs, args.chunk, ref, 1, "T|N", "chrS2", paired=True, raw=True)
-        return time.perf_counter() - t_a, (tm_p,), len(tsv)
-
-    # ---- device-resident steps ---------------------------------------------------------------------------
-    # One step = what run_batch_somatic launches for this workload: rv_pileup over every (tile, sample), rv_score with the
-    # device-side candidate cut over every position of both samples, rv_score_positions for the full records of both
-    # samples at the positions where either has a candidate (the tumor | normal join list, built once here).
     ctx.push_reads_ptr(bt.n_reads, d_reads.data_ptr(), d_pool.data_ptr(), int(pool_np.size), device=True)
     ctx.set_regions(regs)
     st = ctx.pileup()
     bases_per_step = st.n_aligned_bases
     kept_per_step = st.n_reads_kept
     log(f"[bench r{rank}] pileup: {st.n_items} work items, {st.n_reads_kept} kept, {st.n_walk_items} walked "
-        f"({st.n_walk_full} whole reads), {st.n_events} events")
+        f"({st.n_walk_full} whole reads), {st.n_events} events, {st.n_unsupported} unsupported, {st.n_clipped} clipped")
     # sparse keys of this batch (identical every step): reduce once on the host, keep the patch resident
-    ctx.install_patch_from_events(bt, regs, ref, 1)
+    ctx.install_patch_from_events(bt, regs, ref, ref_lo)
     ctx.score()
-    vp, n_candidate_records = ctx.fetch_variants()
-    if n_candidate_records > 5000000:
-        raise rv.RabbitVarError("candidate pass returned an implausible number of records")
-    rec = np.frombuffer((C.c_char * (n_candidate_records * C.sizeof(rv.Variant))).from_address(C.addressof(vp.contents)),
-                        dtype=np.int32).reshape(n_candidate_records, C.sizeof(rv.Variant) // 4) \
-        if n_candidate_records else np.zeros((0, C.sizeof(rv.Variant) // 4), np.int32)
-    cr = rec[:, 0].astype(np.int64) % half
-    cp = rec[:, 1].astype(np.int64)
-    uniq = np.unique(cr * (1 << 32) + cp)
-    jr = (uniq >> 32).astype(np.int32)
-    jp = (uniq & 0xffffffff).astype(np.int32)
-    join_regions = np.concatenate([jr, jr + half]).astype(np.int32)
-    join_positions = np.concatenate([jp, jp]).astype(np.int32)
+    join_regions = join_positions = None
+    n_candidate_records = 0
+    if paired:
+        # the tumor | normal join list (positions where either sample has a candidate), built once
+        vp, n_candidate_records = ctx.fetch_variants()
+        rec = np.frombuffer((C.c_char * (n_candidate_records * C.sizeof(rv.Variant))).from_address(C.addressof(vp.contents)),
+                            dtype=np.int32).reshape(n_candidate_records, C.sizeof(rv.Variant) // 4) \
+            if n_candidate_records else np.zeros((0, C.sizeof(rv.Variant) // 4), np.int32)
+        cr = rec[:, 0].astype(np.int64) % half
+        cp = rec[:, 1].astype(np.int64)
+        uniq = np.unique(cr * (1 << 32) + cp)
+        jr = (uniq >> 32).astype(np.int32)
+        jp = (uniq & 0xffffffff).astype(np.int32)
+        join_regions = np.concatenate([jr, jr + half]).astype(np.int32)
+        join_positions = np.concatenate([jp, jp]).astype(np.int32)
 
     def step():
         ctx.pileup()
+        sp = ctx.pileup_stage_ms()
         ctx.score()
         a, b = ctx.kernel_ms()
-        sp = ctx.pileup_split_ms()
-        ctx.score_positions(join_regions, join_positions)
-        _, b2 = ctx.kernel_ms()
-        return a, b + b2, sp
+        if paired:
+            ctx.score_positions(join_regions, join_positions)
+            _, b2 = ctx.kernel_ms()
+            b += b2
+        return a, b, sp
 
-    for _ in range(max(0, args.warmup - 1)):
+    for _ in range(max(0, args.warmup)):
         step()
     ctx.sync()
-    if world > 1:
-        dist.barrier()
+    barrier()
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     sampler.start()
@@ -359,107 +350,136 @@ def main():
     dev_ms = ctx.timer_stop()
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - w0) * 1000.0
-    if world > 1:
-        dist.barrier()
+    barrier()
     launches = ctx.launch_count() - l0
     clocks = sampler.finish()
     n_var_step = ctx.n_variants() + n_candidate_records
+    # the device-resident arm is done: release its memory before the CLI arm creates its own contexts
+    ctx.close()
+    del d_reads, d_pool
+    bt.close()
+    torch.cuda.empty_cache()
 
-    # ---- e2e steps (host buffers, copies inside the timed region) ---------------------------------------
-    e2e_t, e2e_tm, tsv_len = [], None, 0
+    # ---- e2e: the drop-in CLI on this rank's tiles, files in -> TSV out ----------------------------------------------
+    cores = os.cpu_count() or 1
+    th = max(1, cores // world)
+    cli_out = os.path.join(d, f"cli_{world}_{rank}.tsv")
+    cli_cmd = [pc.CLI] + pc.cli_args(key, d, length)
+    cli_cmd[cli_cmd.index("-i") + 1] = my_bed
+    cli_cmd += ["--th", str(th), "--device", str(local), "--out", cli_out]
+    e2e_t, cli_info = [], ""
     for i in range(1 + args.e2e_steps if args.e2e_steps > 0 else 0):
-        dt, tms, tsv_len = e2e_pass()
+        barrier()
+        t_a = time.perf_counter()
+        r = subprocess.run(cli_cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        dt = time.perf_counter() - t_a
+        if r.returncode != 0:
+            raise rv.RabbitVarError(f"CLI failed (rc {r.returncode}): {r.stderr[-500:]}")
+        cli_info = r.stdout
         if i > 0:
             e2e_t.append(dt)
-            e2e_tm = tms
-    # --e2e-steps 0 (kernel experiments, ncu captures): no end-to-end number, the line says so
     e2e_sec = sum(e2e_t) / len(e2e_t) if e2e_t else float("nan")
-    for nm, t in zip(("T|N",), e2e_tm or ()):
-        log(f"[bench r{rank}] e2e {nm}: push {t.push_ms:.1f} pileup {t.pileup_ms:.1f} fetch {t.fetch_ms:.1f} host {t.host_ms:.1f} "
-            f"patch {t.patch_ms:.1f} score {t.score_ms:.1f} assemble {t.assemble_ms:.1f} ms; events {t.n_events} "
-            f"variants {t.n_variants} lines {t.n_lines}")
-    h2d = sum(t.h2d_bytes for t in e2e_tm or ())
-    d2h = sum(t.d2h_bytes for t in e2e_tm or ())
+    m = re.search(r"h2d bytes (\d+), d2h bytes (\d+)", cli_info)
+    h2d, d2h = (int(m.group(1)), int(m.group(2))) if m else (0, 0)
+    m = re.search(r"launches (\d+)", cli_info)
+    cli_launches = int(m.group(1)) if m else 0
+    if cli_info:
+        log(f"[bench r{rank}] e2e CLI: {e2e_sec:.3f} s per run; " + cli_info.strip().splitlines()[-2][:400])
 
-    # ---- reductions over ranks (max time, sum of work) ---------------------------------------------------
-    from rabbitvar_b200.shard import reduce_step_metrics
-    d = dist if world > 1 else None
-    dev_ms_max, total_bases = reduce_step_metrics(dev_ms, bases_per_step, d)
-    wall_ms_max, _ = reduce_step_metrics(wall_ms, 0, d)
-    e2e_sec_max, _ = reduce_step_metrics(e2e_sec, 0, d)
+    # ---- reductions over ranks (max time, sum of work) ---------------------------------------------------------------
+    dd = dist if world > 1 else None
+    dev_ms_max, total_bases = shard.reduce_step_metrics(dev_ms, bases_per_step, dd)
+    wall_ms_max, _ = shard.reduce_step_metrics(wall_ms, 0, dd)
+    e2e_sec_max, _ = shard.reduce_step_metrics(e2e_sec, 0, dd)
+    _, h2d_total = shard.reduce_step_metrics(0, h2d, dd)
+    _, d2h_total = shard.reduce_step_metrics(0, d2h, dd)
+    _, launches_total = shard.reduce_step_metrics(0, launches, dd)
+    barrier()
     value = total_bases * args.steps / (dev_ms_max / 1000.0)
-    e2e_value = total_bases / e2e_sec_max
+    e2e_value = total_bases / e2e_sec_max if e2e_t else None
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        P = sum(e - s + 1 for s, e in tiles) * 2
+        P = sum(e - s + 1 for s, e in zip(starts, ends)) * len(regs_list)
         alg_pileup = kept_per_step * avg_read_bytes + P * 133.0
         alg_score = P * 133.0 + n_var_step * 128.0
         pk = float(np.mean(pile_ms)) / 1000.0
         sk = float(np.mean(score_ms)) / 1000.0
         achieved = alg_pileup / pk / 1e9
-        split = [float(np.mean([x[k] for x in split_ms])) for k in range(3)]
+        split = [float(np.mean([x[k] for x in split_ms])) for k in range(4)]
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and key == "2":
             traffic = json.load(open(tp)).get("pileup_stage_dram_bytes_per_launch")
-        cpu = None
-        if not args.skip_cpu and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "RabbitVar")):
-            try:
-                n_tiles = min(args.ref_tiles, len(tiles))
-                bed = sample_bed(work, n_tiles)
-                cores = os.cpu_count() or 1
-                # aligned bases of the sample: exact, from a GPU pileup of just those tiles
-                sub = (rv.Region * (2 * n_tiles))()
-                C.memmove(sub, regs, C.sizeof(rv.Region) * n_tiles)
-                C.memmove(C.byref(sub, C.sizeof(rv.Region) * n_tiles), C.byref(regs, C.sizeof(rv.Region) * half),
-                          C.sizeof(rv.Region) * n_tiles)
-                ctx.push_reads_ptr(bt.n_reads, d_reads.data_ptr(), d_pool.data_ptr(), int(pool_np.size), device=True)
-                ctx.set_regions(sub)
-                sb = ctx.pileup().n_aligned_bases
-                out = os.path.join(work, "ref_out.tsv")
-                c0 = time.perf_counter()
-                subprocess.run(ref_cmd(work, bed, out, cores), check=True, stdout=subprocess.DEVNULL,
-                               stderr=subprocess.DEVNULL)
-                cdt = time.perf_counter() - c0
-                cpu = {"value": sb / cdt, "unit": UNIT, "cores": cores, "kind": "reference",
-                       "sample": f"oracle/_ref/RabbitVar (unmodified reference, -O3 -ffast-math -fopenmp) --th {cores} on the "
-                                 f"first {n_tiles} tiles x 2 samples of this workload: {sb} aligned bases in {cdt:.2f}s"}
-            except Exception as e:  # the baseline is reported, never required
-                cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+        # ---- parity + CPU baseline: the reference binary on the same files ----
+        parity, cpu = {}, None
+        which = args.parity
+        keys = []
+        if which == "all":
+            keys = [key] + ([k for k in ("1", "1R", "3", "4", "5") if k != key] if world == 1 else [])
+        elif which == "workload":
+            keys = [key]
+        elif which != "none":
+            keys = which.split(",")
+        if os.path.exists(pc.REF_BIN):
+            for k in keys:
+                try:
+                    if k == key and e2e_t:
+                        # this workload: the ranks' TSV blocks concatenated in block order vs the reference's output
+                        ref_out = os.path.join(d, f"ref_{k}.tsv")
+                        c0 = time.perf_counter()
+                        subprocess.run(ref_cmd(k, d, bed_all, ref_out, cores), check=True, stdout=subprocess.DEVNULL,
+                                       stderr=subprocess.DEVNULL)
+                        cdt = time.perf_counter() - c0
+                        want = pc.tsv_lines(ref_out)
+                        got = []
+                        for g in range(world):
+                            got += pc.tsv_lines(os.path.join(d, f"cli_{world}_{g}.tsv"))
+                        got.sort()
+                        bad, ex = pc.compare_tsv(want, got)
+                        parity[k] = {"parity_lines_differing": bad, "ref_lines": len(want), "cli_lines": len(got),
+                                     "gpus": world, "examples": ex[:2]}
+                        if not args.skip_cpu:
+                            cpu = {"value": total_bases / cdt, "unit": UNIT, "cores": cores, "kind": "reference",
+                                   "sample": f"oracle/_ref/RabbitVar (unmodified reference, -O3 -ffast-math -fopenmp) --th {cores} on "
+                                             f"the whole workload (same files, same {len(tiles_all)} tiles): {int(total_bases)} aligned "
+                                             f"bases in {cdt:.2f}s"}
+                    else:
+                        r = pc.run_config(k, 1.0, 1, cores)
+                        parity[k] = {kk: r.get(kk) for kk in ("parity_lines_differing", "ref_lines", "cli_lines", "error", "ref_sec", "cli_sec")
+                                     if r.get(kk) is not None}
+                except Exception as e:  # reported, never required
+                    parity[k] = {"error": str(e)[:300]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "BASELINE.json configs[1]: tumor/normal, 5 Mb as 500 x 10 kb tiles, T 200x + N 100x, "
-                                   "2x150 bp, -f 0.01 --fisher; one full shard per GPU (region-sharded, no collective)",
-                       "regions_per_gpu": nreg, "reads_per_gpu": int(bt.n_reads), "aligned_bases_per_step_per_gpu": int(bases_per_step),
-                       "l2_policy": f"inputs ({read_bytes_total / 1e9:.2f} GB reads + {n_pos * 132 / 1e9:.2f} GB tables) exceed the 126 MB L2",
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_TEXT[key], "tiles_total": len(tiles_all), "tiles_rank0": len(tiles),
+                       "reads_rank0": int(n_t + n_n), "aligned_bases_per_step": int(total_bases),
+                       "l2_policy": f"inputs of a step ({read_bytes_total / 1e9:.2f} GB reads + {n_pos * 132 / 1e9:.2f} GB tables on rank 0) exceed the 126 MB L2",
                        "wall_ms_per_step": wall_ms_max / args.steps,
-                       "step": "rv_pileup + rv_score (candidate cut, every position of both samples) + rv_score_positions (full records of both samples at the joined candidate positions): the launches of run_batch_somatic; the join list and the host realigner patch are built once outside the timed loop"},
+                       "step": "rv_pileup + rv_score (device candidate cut)" + (" + rv_score_positions (full records of both samples at the joined candidate positions)" if paired else "") +
+                               "; reads resident in HBM; the realigner's patch list is built once outside the timed loop"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value if e2e_t else None, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": f"rvh_pipeline_run_paired (host buffers -> somatic-mode TSV), {args.workers} worker contexts x {args.chunk}-tile chunks of both samples, pinned H2D", "sec_per_step": e2e_sec_max if e2e_t else None,
-                    "tsv_bytes": tsv_len},
-            "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(d2h_total),
+                    "api": f"build/rabbitvar_b200 (drop-in CLI): level-1 BAM + FASTA + BED files -> TSV file, one process per GPU, --th {th} decode threads each; wall clock of the process incl. CUDA start-up, max over ranks",
+                    "sec_per_step": e2e_sec_max if e2e_t else None, "runs": len(e2e_t), "gpu_launches_per_run": cli_launches},
+            "gpu_launches": int(launches_total),
+            "parity": parity,
+            "parity_lines_differing": {k: v.get("parity_lines_differing") for k, v in parity.items()},
             "roofline": {"bound": "hbm",
-                         "kernel": "pileup stage = rv_pileup_kernel + rv_tile_index_kernel + rv_gather4_kernel + rv_walk_kernel "
+                         "kernel": "pileup stage of rank 0 = rv_pileup_kernel + rv_walk_kernel + rv_tile_index_kernel + rv_gather4_kernel + rv_apply_kernel "
                                    "(one rv_pileup call; rv_gather4_kernel is the largest)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_pileup, "kernel_ms": pk * 1000.0,
-                         "split_ms": {"rv_pileup_kernel": split[0], "rv_tile_index_kernel+rv_gather4_kernel": split[1],
-                                      "rv_walk_kernel": split[2]},
+                         "split_ms": {"rv_pileup_kernel": split[0], "rv_walk_kernel": split[2],
+                                      "rv_tile_index_kernel+rv_gather4_kernel": split[1], "rv_apply_kernel": split[3]},
                          "score_kernel": {"achieved": alg_score / sk / 1e9, "kernel_ms": sk * 1000.0,
                                           "algorithmic_bytes_per_launch": alg_score}},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
-    # explicit teardown in a fixed order (nothing is left to interpreter shutdown, where CUDA may already be gone)
-    pipe.close()
-    ctx.close()
-    del d_reads, d_pool
-    bt.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

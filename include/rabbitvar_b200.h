@@ -209,6 +209,9 @@ typedef struct rv_variant {
 /* ---- lifecycle ------------------------------------------------------------------------------- */
 int rv_abi_version(void);
 int rv_device_count(void);
+/* Initialises the CUDA runtime on `device` and loads the library's kernels (what the first rv_create would otherwise
+ * pay): callers run it beside their own start-up work. */
+int rv_warmup(int device);
 int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits* limits);
 void rv_destroy(rv_ctx* ctx);
 const char* rv_last_error(const rv_ctx* ctx);
@@ -296,6 +299,9 @@ int rv_last_kernel_ms(rv_ctx* ctx, float* pileup_ms, float* score_ms);
 /* The same for the kernels of the last rv_pileup: rv_pileup_kernel (filters, CIGAR rewrite, plain-run proof),
  * rv_tile_index_kernel + rv_gather_kernel (position-major accumulation), rv_walk_kernel (exact CIGAR walks). */
 int rv_last_pileup_split_ms(rv_ctx* ctx, float* classify_ms, float* gather_ms, float* walk_ms);
+/* All four: out[0] rv_pileup_kernel, out[1] rv_tile_index_kernel + rv_gather4_kernel, out[2] rv_walk_kernel,
+ * out[3] rv_apply_kernel (launch order: classify, walk, gather, apply). */
+int rv_last_pileup_stage_ms(rv_ctx* ctx, float out[4]);
 /* Brackets any sequence of calls with CUDA events recorded on the context's (launching) stream;
  * rv_timer_stop synchronises and returns the elapsed device time in milliseconds. */
 int rv_timer_start(rv_ctx* ctx);

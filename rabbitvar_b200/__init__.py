@@ -111,11 +111,11 @@ class Timing(C.Structure):
 
 # every symbol include/*.h declares (checked by tests without a GPU)
 ABI_SYMBOLS = [
-    "rv_abi_version", "rv_device_count", "rv_default_params", "rv_default_limits", "rv_create", "rv_destroy",
+    "rv_abi_version", "rv_device_count", "rv_warmup", "rv_default_params", "rv_default_limits", "rv_create", "rv_destroy",
     "rv_last_error", "rv_sync", "rv_ctx_halo", "rv_set_params", "rv_set_reference", "rv_push_reads", "rv_push_reads_range", "rv_push_reads_ranges", "rv_push_reads_device", "rv_set_regions",
     "rv_pileup", "rv_score", "rv_score_positions", "rv_get_pileup_stats", "rv_fetch_max_read_len", "rv_fetch_tables", "rv_fetch_rows",
     "rv_fetch_events",
-    "rv_apply_patch", "rv_fetch_variants", "rv_cov_summary", "rv_variant_count", "rv_fisher_exact", "rv_last_kernel_ms", "rv_last_pileup_split_ms", "rv_timer_start",
+    "rv_apply_patch", "rv_fetch_variants", "rv_cov_summary", "rv_variant_count", "rv_fisher_exact", "rv_last_kernel_ms", "rv_last_pileup_split_ms", "rv_last_pileup_stage_ms", "rv_timer_start",
     "rv_timer_stop", "rv_launch_count",
     "rvh_load_bam", "rvh_batch_append", "rvh_batch_n_reads", "rvh_batch_reads", "rvh_batch_pool",
     "rvh_batch_pool_bytes", "rvh_batch_max_ref_span", "rvh_batch_pin", "rvh_batch_free", "rvh_make_regions", "rvh_fetch_ref",
@@ -167,6 +167,7 @@ def _declare(L):
     L.rv_cov_summary.argtypes = [vp, vp, vp]
     L.rv_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.rv_last_pileup_split_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.rv_last_pileup_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.rv_timer_start.argtypes = [vp]
     L.rv_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.rv_launch_count.argtypes = [vp]
@@ -435,6 +436,12 @@ class Context:
         a, b, c = C.c_float(), C.c_float(), C.c_float()
         lib().rv_last_pileup_split_ms(self._h, C.byref(a), C.byref(b), C.byref(c))
         return a.value, b.value, c.value
+
+    def pileup_stage_ms(self):
+        """(classify, tile index + gather, walk, apply) device milliseconds of the last pileup."""
+        out = (C.c_float * 4)()
+        lib().rv_last_pileup_stage_ms(self._h, out)
+        return tuple(out)
 
     def timer_start(self):
         self._ck(lib().rv_timer_start(self._h), "rv_timer_start")

@@ -23,7 +23,7 @@ struct Cli {
   std::string fasta, bam, bam2, region, bed, out = "./out.txt", sample, delim = "\t";
   int c_col = 2, S_col = 6, E_col = 7, g_col = 12;  // DEFAULT_BED_ROW_FORMAT (Launcher.cpp:21), 0-based after -1
   bool c_set = false, S_set = false, E_set = false, g_set = false, zero_based = false;
-  int nucl_ext = 0, ref_ext = 1200, gpus = 1, threads = 1, batch_regions = 256, halo = 512, workers = 3, job_mb = 24;
+  int nucl_ext = 0, ref_ext = 1200, gpus = 1, threads = 1, batch_regions = 256, halo = 512, workers = 2, job_mb = 12, device = 0;
   bool auto_resize = false, threads_set = false, decode_only = false;
   rv_params P;
 };
@@ -33,7 +33,7 @@ static void usage() {
           "usage: rabbitvar_b200 -G ref.fa -b in.bam (-R chr:start-end | -i regions.bed -c 1 -S 2 -E 3 -g 4) [options]\n"
           "  -N name  -f freq  -k 0|1  -3  -u  --UN  -p  -t  --fisher  -q phred  -m mismatches  -X ext  -P pos  -r minr\n"
           "  -B minbias  -Q mapq  -o qratio  -O mapq  -V lofreq  -M minmatch  -T trim  -F hexfilter  -x extend  -Y refext\n"
-          "  -z  --auto_resize  --th n  --gpus n  --workers n (GPU contexts per device)  --halo n  --out file\n");
+          "  -z  --auto_resize  --th n  --gpus n  --device first  --workers n (GPU contexts per device)  --halo n  --out file\n");
 }
 
 static bool parse(int argc, char** argv, Cli& c) {
@@ -89,6 +89,7 @@ static bool parse(int argc, char** argv, Cli& c) {
     else if (a == "--th") { c.threads = std::max(1, atoi(val().c_str())); c.threads_set = true; }
     else if (a == "--halo") c.halo = std::max(64, atoi(val().c_str()));
     else if (a == "--workers") c.workers = std::max(1, atoi(val().c_str()));
+    else if (a == "--device") c.device = std::max(0, atoi(val().c_str()));
     else if (a == "--job-mb") c.job_mb = std::max(1, atoi(val().c_str()));
     else if (a == "--auto_resize") c.auto_resize = true;
     else if (a == "--decode-only") c.decode_only = true;
@@ -199,6 +200,17 @@ int main(int argc, char** argv) {
   double t0 = now_ms();
   Cli c;
   if (!parse(argc, argv, c)) return 1;
+  // CUDA start-up (driver initialisation, primary context, module load) runs beside the header / index / BED parsing.
+  // With one device in use the others are hidden from the driver first: initialising eight GPUs costs several times
+  // what initialising one does.
+  if (!c.decode_only && c.gpus == 1 && getenv("CUDA_VISIBLE_DEVICES") == NULL) {
+    setenv("CUDA_VISIBLE_DEVICES", std::to_string(c.device).c_str(), 1);
+    c.device = 0;
+  }
+  double cuda_init_ms = 0;
+  std::thread cuda_init;
+  if (!c.decode_only) cuda_init = std::thread([&]() { const double a = now_ms(); rv_warmup(c.device); cuda_init_ms = now_ms() - a; });
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{cuda_init};
   rvio::BamReader hdr_reader;
   if (!hdr_reader.open(c.bam)) { fprintf(stderr, "cannot open %s\n", c.bam.c_str()); return 1; }
   if (c.sample.empty()) {  // SAMPLE_PATTERN fallbacks of Launcher.cpp:212-243 reduce to the file stem here
@@ -211,6 +223,7 @@ int main(int argc, char** argv) {
     fprintf(stderr, "no regions (give -R or -i)\n");
     return 1;
   }
+  if (cuda_init.joinable()) cuda_init.join();
   int ndev = rv_device_count();
   if (ndev <= 0 && !c.decode_only) {
     fprintf(stderr, "rabbitvar_b200: no CUDA device visible; this build has no CPU path\n");
@@ -221,7 +234,8 @@ int main(int argc, char** argv) {
   fc.P = c.P;
   fc.ref_ext = c.ref_ext; fc.nucl_ext = c.nucl_ext;
   fc.decode_threads = c.threads;                 // --th, default 1 like the reference (Launcher.cpp:474)
-  fc.gpus = c.decode_only ? 1 : std::min(c.gpus, ndev);
+  fc.first_device = c.device;
+  fc.gpus = c.decode_only ? 1 : std::max(1, std::min(c.gpus, ndev - c.device));
   fc.decode_only = c.decode_only;
   fc.workers_per_gpu = c.workers;
   fc.max_regions_per_job = c.batch_regions;
@@ -252,9 +266,11 @@ int main(int argc, char** argv) {
   if (st.n_clipped)
     fprintf(stderr, "[warn] %lld observations fell outside the table halo of %d positions and were dropped (--halo)\n", (long long)st.n_clipped, c.halo);
   printf("[info] output file name: %s\n[info] regions: %zu jobs: %lld gpus: %d x %d contexts, decode threads: %d, aligned bases: %lld variant lines: %lld "
-         "kernel ms: %.3f, decode thread-ms %.0f, gpu-worker thread-ms %.0f, launches %lld\n",
+         "kernel ms: %.3f, decode thread-ms %.0f, gpu-worker thread-ms %.0f, launches %lld, h2d bytes %lld, d2h bytes %lld\n",
          c.out.c_str(), specs.size(), (long long)st.n_jobs, fc.gpus, fc.workers_per_gpu, fc.decode_threads, (long long)st.bases, (long long)st.lines,
-         st.pileup_kernel_ms + st.score_kernel_ms, st.decode_thread_ms, st.gpu_worker_ms, (long long)st.launches);
+         st.pileup_kernel_ms + st.score_kernel_ms, st.decode_thread_ms, st.gpu_worker_ms, (long long)st.launches,
+         (long long)st.h2d_bytes, (long long)st.d2h_bytes);
+  printf("[info] cuda start-up %.0f ms (overlapped with input parsing)\n", cuda_init_ms);
   printf("total time: %f s \n", (now_ms() - t0) / 1000.0);
   return rc;
 }

@@ -67,6 +67,15 @@ inline uint64_t bai_coffset(const rvio::BaiIndex& bai, int tid, int64_t pos0) {
   return v >> 16;
 }
 
+// compressed bytes a region is expected to span: its share of the 16 kb index windows it touches
+inline int64_t region_bytes(const rvio::BaiIndex& bai, int tid, int32_t start, int32_t end) {
+  const int64_t w0 = ((int64_t)start - 1) >> 14, w1 = (int64_t)end >> 14;
+  const uint64_t a = bai_coffset(bai, tid, w0 << 14), b = bai_coffset(bai, tid, (w1 + 1) << 14);
+  if (b <= a) return 0;
+  const double share = (double)(end - start + 1) / (double)((w1 - w0 + 1) << 14);
+  return (int64_t)((double)(b - a) * (share > 1.0 ? 1.0 : share));
+}
+
 // Cuts the region list into jobs: consecutive regions of one contig, at most max_regions_per_job, closed when the
 // compressed bytes the job's regions span (summed over the samples) reach job_bytes.
 inline void plan_jobs(const FileRunConfig& c, const std::vector<RegionSpec>& specs, const rvio::BamHeader& hdr,
@@ -81,14 +90,8 @@ inline void plan_jobs(const FileRunConfig& c, const std::vector<RegionSpec>& spe
     size_t k = i;
     while (k < specs.size() && specs[k].chr == specs[i].chr && (int)(k - i) < c.max_regions_per_job) {
       if (k > i && bytes >= c.job_bytes) break;
-      if (tid >= 0) {
-        const uint64_t a = bai_coffset(bai, tid, (int64_t)specs[k].start - 1), b = bai_coffset(bai, tid, specs[k].end);
-        if (b > a) bytes += (int64_t)(b - a);
-      }
-      if (bai2 && tid2 >= 0) {
-        const uint64_t a = bai_coffset(*bai2, tid2, (int64_t)specs[k].start - 1), b = bai_coffset(*bai2, tid2, specs[k].end);
-        if (b > a) bytes += (int64_t)(b - a);
-      }
+      if (tid >= 0) bytes += region_bytes(bai, tid, specs[k].start, specs[k].end);
+      if (bai2 && tid2 >= 0) bytes += region_bytes(*bai2, tid2, specs[k].start, specs[k].end);
       j.specs.push_back(specs[k++]);
     }
     jobs->push_back(std::move(j));

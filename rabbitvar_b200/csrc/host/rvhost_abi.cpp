@@ -287,7 +287,7 @@ const char* rvh_last_error(void) { return g_err.c_str(); }
 
 rvh_batch* rvh_load_bam(const char* bam_path, const char* chr, int32_t start, int32_t end, int32_t* chr_len_out) {
   try {
-    rvio::BamReader rd;
+    rvio::SpanScanner rd;
     rvio::BaiIndex bai;
     if (!rd.open(bam_path)) { g_err = std::string("cannot open BAM ") + bam_path; return NULL; }
     if (!bai.load(std::string(bam_path) + ".bai")) { g_err = std::string("cannot open index of ") + bam_path; return NULL; }
@@ -295,7 +295,7 @@ rvh_batch* rvh_load_bam(const char* bam_path, const char* chr, int32_t start, in
     if (tid < 0) { g_err = std::string("contig not in BAM header: ") + chr; return NULL; }
     if (chr_len_out) *chr_len_out = rd.header().lens[tid];
     rvh_batch* b = new rvh_batch();
-    load_span(rd, bai, tid, start, end, &b->b);
+    load_span_fast(rd, bai, tid, start, end, &b->b);
     return b;
   } catch (const std::exception& e) {
     g_err = e.what();

@@ -655,7 +655,64 @@ RV_HD bool fast_obs(const FastDesc& d, int p, const uint8_t* pool, int* allele, 
 //   void event(const rv_event&)
 //   void max_read_len(int tlen)
 //   void kept(int aligned_bases) ; void unsupported()
+//   bool segment(const SegDesc&, bool dir, int mapq, int nm)   a plain matched stretch (see scan_plain_segment); a sink
+//                                                              that returns false gets the per-base observations
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// Plain segments.  A matched stretch of a read (one M/=/X op, from the bases an indel before it already consumed to
+// its end) is PLAIN when the per-base loop of parseCigar (:678-959) can do nothing with it but record one single-base
+// observation per base:
+//   * every read base is A, C, G or T (an N is skipped without an observation, :686-692; other letters have no row),
+//   * the stretch lies inside the loaded reference window,
+//   * no two mismatches lie within vext + 1 bases of each other: the multi-nucleotide loop (:711-768) looks at the
+//     next base and then up to vext bases further, never beyond the op,
+//   * with -k 1 and an I or D op following: no mismatch among the last vext bases (the indel-adjacent complex
+//     forms, :779-882).
+// Such a stretch leaves a descriptor; the position-major gather kernel accumulates it.  The conditions ignore the
+// quality / region tests of the loops they guard, so they are sufficient, not necessary: everything else takes the
+// literal per-base walk.
+// ------------------------------------------------------------------------------------------------
+struct SegDesc {
+  int32_t m_start;   // reference position of the first base
+  int32_t len;       // bases
+  int32_t rp;        // read offset of the first base, soft clips included (index into seq / qual)
+  int32_t re;        // ... soft clips excluded: tp of base k = min(re + k + 1, rlen - re - k)
+  int32_t rlen;
+  uint32_t mm_blocks;        // bit b: a mismatch among bases [16b, 16b + 16) (bit 15: and beyond)
+  uint32_t ml[4];            // up to eight mismatches, 16 bits each, oldest in the highest used bits:
+                             // 0x8000 | offset << 2 | allele of the read base
+  int n_mm;
+};
+
+RV_HDN bool scan_plain_segment(const rv_params& P, const ReadView& rd, const RefView& ref, int m_start, int rp, int len,
+                               bool indel_follows, SegDesc* out) {
+  if (len <= 0 || len > 8192) return false;
+  if (!ref.has(m_start) || !ref.has(m_start + len - 1)) return false;
+  const int D = P.vext + 1;
+  int last_mm = -100000, n_mm = 0;
+  uint32_t blocks = 0;
+  unsigned long long lo = 0, hi = 0;
+  for (int k = 0; k < len; ++k) {
+    const char b = rd.base(rp + k);
+    const int al = allele_of(b);
+    if (al < 0) return false;
+    const char rc = ref.bases[m_start + k - ref.base_pos];
+    if (rc != b) {
+      if (k - last_mm <= D) return false;
+      if (indel_follows && P.local_realign && len - k <= P.vext) return false;
+      last_mm = k;
+      if (++n_mm > 8) return false;
+      blocks |= 1u << ((k >> 4) < 15 ? (k >> 4) : 15);
+      hi = (hi << 16) | (lo >> 48);
+      lo = (lo << 16) | (unsigned long long)(0x8000u | ((uint32_t)k << 2) | (uint32_t)al);
+    }
+  }
+  out->mm_blocks = blocks;
+  out->ml[0] = (uint32_t)lo; out->ml[1] = (uint32_t)(lo >> 32); out->ml[2] = (uint32_t)hi; out->ml[3] = (uint32_t)(hi >> 32);
+  out->n_mm = n_mm;
+  return true;
+}
+
 struct WalkState {
   int start, rp, re, offset, clen;  // start, readPositionIncluding/ExcludingSoftClipped, offset, cigar_element_length
   int seq_no;
@@ -1270,6 +1327,24 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
         w.re += w.clen;
         if (w.start > R.end) break;
         continue;
+      }
+    }
+    if (trim_after == 0 && w.clen - w.offset > 0 && nm >= 0 && nm <= 127 && rlen < 65536) {
+      const bool indel_follows = ci + 1 < n_cigar && is_id(c_op(cg.op[ci + 1]));
+      SegDesc sd;
+      if (scan_plain_segment(P, rd, ref, w.start, w.rp, w.clen - w.offset, indel_follows, &sd)) {
+        sd.m_start = w.start;
+        sd.len = w.clen - w.offset;
+        sd.rp = w.rp;
+        sd.re = w.re;
+        sd.rlen = rlen;
+        if (sink.segment(sd, dir, mapq, nm)) {
+          w.start += sd.len;
+          w.rp += sd.len;
+          w.re += sd.len;
+          if (w.start > R.end) break;
+          continue;
+        }
       }
     }
     int nmoff = 0, moffset = 0;

@@ -32,31 +32,47 @@ struct DevRegion {
   int32_t first_pos;  // reference position of table index tab_off
   int32_t n_pos;
   int64_t item_base;  // first (region, read) work item of this region
-  int64_t tile_base;  // first gather tile (GATHER_TILE table positions each, halo included) of this region
+  int64_t tile_base;  // first gather tile (G4_W table positions each, halo included) of this region
   // the region's reads live in one uploaded slice of the host batch: device read index = batch index - read_bias,
   // device pool byte = batch pool byte - pool_bias (rv_push_reads_ranges)
   int64_t read_bias, pool_bias;
 };
 
-static const int GATHER_TILE = 256;
 
-struct DevStats {
+static const size_t COUNTER_BLOCK_BYTES = 192;
+struct DevStats {  // (must fit the first 128 bytes of the counter block)
   unsigned long long n_items, n_kept, n_bases, n_events, n_overflow, n_unsupported, n_variants, n_score_unsupported;
   unsigned long long n_walk_items, n_walk_full;
   unsigned long long n_clipped;  // observations outside [start - halo, end + halo]: dropped, like the gather path clips
 };
 
-// Gather descriptor of one (region, read) work item whose rewritten CIGAR is [H][S] M [S][H] and whose matched
-// run is "plain" (see rv_pileup_kernel): all the gather kernel needs to find the run's bases and qualities.
+// Gather descriptor of one plain matched segment (rvk::scan_plain_segment / the plain-run proof of rv_pileup_kernel):
+// all the gather kernel needs to find the segment's qualities and to give every base its read position.
+// A work item owns up to two: descs[item] and, when bit 15 of its m_len is set, descs2[item] (a read with one indel).
 struct GDesc {          // 16 bytes, one LDG.128
-  int32_t m_start;      // reference position of the first matched base
-  uint16_t m_len;       // matched bases; 0 = the item contributes nothing through the gather path
-  uint16_t rp0;         // read offset of the first matched base
-  uint32_t seq_off4;    // byte offset of the packed bases in the pool / 4 (qualities follow the bases)
-  uint16_t l_seq;
+  int32_t m_start;      // reference position of the first base
+  uint16_t m_len;       // bits 0-13: bases (0 = nothing for the gather path); bit 15: descs2[item] holds a second segment
+  uint16_t re0;         // read offset of the first base, soft clips excluded: tp of base k = min(re0 + k + 1, rlen - re0 - k)
+  uint32_t qual_off;    // byte offset in the device pool of the first base's quality
+  uint16_t rlen;        // matched + inserted bases of the read (parseCigar.cpp:591-595)
   uint8_t mapq;
   uint8_t dir_nm;       // bit 7: reverse strand; bits 0-6: nm (0..127)
 };
+static const uint32_t GD_LEN_MASK = 0x3fffu, GD_HAS_SECOND = 0x8000u;
+
+// Observation that does not go through the gather kernel (soft-clip re-extension, the anchor base an insertion takes
+// back, bases of stretches that are not plain, coverage under deletions): rv_walk_kernel appends them, rv_apply_kernel
+// adds them to the tables with global atomics once the gather kernel has stored every row.
+struct SparseObs {      // 16 bytes
+  uint32_t tab;         // table position index (region slice offset + position - first_pos)
+  uint16_t tp;
+  uint8_t q, mapq;
+  int16_t nm;
+  uint8_t flags;        // bits 0-1 allele, bit 2 reverse strand, bits 3-4 kind
+  uint8_t pad;
+  uint32_t pad2;
+};
+enum { SO_SINGLE = 0, SO_ADD = 1, SO_SUB = 2, SO_COV = 3 };
 
 struct PileupArgs {
   rv_params P;
@@ -79,6 +95,12 @@ struct PileupArgs {
   uint16_t* desc_mm;     // per work item: bit b set = the plain run has a mismatch in its bases [16b, 16b+16) (bit 15: and beyond)
   uint4* desc_mml;       // per work item with desc_mm != 0: the run's mismatches, up to 8 entries of 16 bits,
                          // 0x8000 | run offset << 2 | allele of the read base (rv_gather4_kernel)
+  GDesc* descs2;         // second segment of a work item (GD_HAS_SECOND), with its own mismatch mask / list
+  uint16_t* desc_mm2;
+  uint4* desc_mml2;
+  SparseObs* sparse;     // observations for rv_apply_kernel
+  unsigned long long max_sparse;
+  unsigned long long* sparse_count;
   int32_t* reach;        // [0] = max(pos - m_start), [1] = max(m_start + m_len - pos) over the descriptors
   int force_exact;       // debugging: every read takes the exact walk
   // reads that need the exact CIGAR walk are not walked by the classifying kernel (one slow lane would stall
@@ -91,83 +113,62 @@ struct PileupArgs {
 };
 static const unsigned long long WALK_PLAIN_DONE = 1ull << 62;  // the matched run already left a descriptor
 
+// Sink of prepare_read (read filters, CIGAR rewrite): statistics and maxReadLength only.
 struct DeviceSink {
   const PileupArgs* a;
   const DevRegion* dr;
-  uint32_t* counts;  // region slice
-  uint32_t* covtab;
-  double goodq;
-  int goodq_i;  // ceil(goodq): integer qualities compare against it
-  int kept_bases, n_kept, n_unsup, n_over, n_ev, n_clip;
-  uint32_t* pend_row;
-  uint32_t pend_old, pend_mine;
-  bool pend;
+  int kept_bases, n_kept, n_unsup, n_over;
   bool mute;  // rv_walk_kernel re-runs prepare_read: its statistics were already counted by rv_pileup_kernel
-  int first_pos, n_pos;  // copies of dr->first_pos / dr->n_pos (registers instead of a global load per observation)
-  __device__ __forceinline__ void bind(const DevRegion* r, uint32_t* counts_all, uint32_t* cov_all) {
+  __device__ __forceinline__ void max_read_len(int tlen) {
+    if (!mute && tlen > a->max_rl[dr - a->regions]) atomicMax(a->max_rl + (dr - a->regions), tlen);
+  }
+  __device__ __forceinline__ void kept(int aligned) { if (!mute) { kept_bases += aligned; n_kept++; } }
+  __device__ __forceinline__ void unsupported() { if (!mute) n_unsup++; }
+};
+
+// Sink of rv_walk_kernel: nothing is added to the tables here.  Plain segments become gather descriptors, everything
+// else a SparseObs for rv_apply_kernel or an event for the host stage.
+struct ListSink {
+  const PileupArgs* a;
+  const DevRegion* dr;
+  int64_t item;
+  int n_seg;             // descriptors this item has written
+  bool first_taken;      // descs[item] already holds the matched run of a plain read (WALK_PLAIN_DONE)
+  bool want_segments;
+  const rv_read* rd;
+  int64_t pool_off;      // device pool byte offset of the read's variable part
+  int n_unsup, n_over, n_clip, n_ev;
+  int first_pos, n_pos;
+  int64_t tab_off;
+  __device__ __forceinline__ void bind(const DevRegion* r) {
     dr = r;
-    counts = counts_all + (size_t)r->tab_off * RV_POS_U32;
-    covtab = cov_all + r->tab_off;
     first_pos = r->first_pos;
     n_pos = r->n_pos;
+    tab_off = r->tab_off;
   }
-  __device__ __forceinline__ bool idx_of(int pos, int* idx) {
-    int i = pos - first_pos;
-    if (i < 0 || i >= n_pos) { n_clip++; return false; }
-    *idx = i;
-    return true;
+  __device__ __forceinline__ void put(int pos, uint32_t flags, int tp, int q, int mapq, int nm) {
+    const int i = pos - first_pos;
+    if (i < 0 || i >= n_pos) { n_clip++; return; }
+    cg::coalesced_group g = cg::coalesced_threads();
+    unsigned long long slot = 0;
+    if (g.thread_rank() == 0) slot = atomicAdd(a->sparse_count, (unsigned long long)g.size());
+    slot = g.shfl(slot, 0) + g.thread_rank();
+    if (slot >= a->max_sparse) { n_over++; return; }
+    uint4 v;
+    v.x = (uint32_t)(tab_off + i);
+    v.y = ((uint32_t)tp & 0xffffu) | (((uint32_t)q & 0xffu) << 16) | (((uint32_t)mapq & 0xffu) << 24);
+    v.z = ((uint32_t)nm & 0xffffu) | (flags << 16);
+    v.w = 0;
+    *(uint4*)(a->sparse + slot) = v;
   }
   __device__ __forceinline__ void single(int pos, int allele, bool dir, int tp, int q, int mapq, int nm) {
-    int i;
-    if (!idx_of(pos, &i)) return;
-    uint32_t* row = counts + ((size_t)i * 4 + allele) * RV_ROW_U32;
-    // (32-bit adds: the sums may legitimately end negative — subCnt of an insertion's anchor base — so two fields cannot
-    // share one 64-bit add)
-    atomicAdd(row + (dir ? RV_F_REV : RV_F_FWD), 1u);
-    atomicAdd(row + RV_F_SUM_TP, (uint32_t)tp);
-    atomicAdd(row + RV_F_SUM_Q, (uint32_t)q);
-    atomicAdd(row + RV_F_SUM_MAPQ, (uint32_t)mapq);
-    if (nm) atomicAdd(row + RV_F_SUM_NM, (uint32_t)nm);
-    if (q >= goodq_i) atomicAdd(row + RV_F_HI, 1u);
-    // pstd/qstd: "two observations differ" == "some observation differs from the first one recorded".
-    // The compare-and-swap result is consumed one observation later (resolve), so its round trip to L2
-    // overlaps the walk of the next base instead of stalling this one.
-    resolve();
-    pend_row = row + RV_F_STD;
-    pend_mine = ((uint32_t)tp & 0xffffu) | (((uint32_t)q & 0xffu) << 16) | (1u << 31);
-    pend_old = atomicCAS(pend_row, 0u, pend_mine);
-    pend = true;
-  }
-  __device__ __forceinline__ void resolve() {
-    if (!pend) return;
-    pend = false;
-    const uint32_t old = pend_old;
-    if (old != 0u) {
-      uint32_t bits = 0;
-      if ((old ^ pend_mine) & 0xffffu) bits |= 1u << 24;
-      if ((old ^ pend_mine) & 0xff0000u) bits |= 1u << 25;
-      if (bits & ~old) atomicOr(pend_row, bits);
-    }
+    put(pos, (uint32_t)allele | (dir ? 4u : 0u) | (SO_SINGLE << 3), tp, q, mapq, nm);
   }
   __device__ __forceinline__ void adj(int pos, int allele, int sign, bool dir, int tp, int q, int mapq, int nm) {
-    int i;
-    if (!idx_of(pos, &i)) return;
-    uint32_t* row = counts + ((size_t)i * 4 + allele) * RV_ROW_U32;
-    atomicAdd(row + (dir ? RV_F_REV : RV_F_FWD), (uint32_t)sign);
-    atomicAdd(row + RV_F_SUM_TP, (uint32_t)(sign * tp));
-    atomicAdd(row + RV_F_SUM_Q, (uint32_t)(sign * q));
-    atomicAdd(row + RV_F_SUM_MAPQ, (uint32_t)(sign * mapq));
-    if (nm) atomicAdd(row + RV_F_SUM_NM, (uint32_t)(sign * nm));
-    if (q >= goodq_i) atomicAdd(row + RV_F_HI, (uint32_t)sign);
-    // (a key only ever nets to zero after an M-path observation, whose STD word keeps it "existing")
+    put(pos, (uint32_t)allele | (dir ? 4u : 0u) | ((sign > 0 ? SO_ADD : SO_SUB) << 3), tp, q, mapq, nm);
   }
-  __device__ __forceinline__ void cov(int pos) {
-    int i;
-    if (!idx_of(pos, &i)) return;
-    atomicAdd(covtab + i, 1u);
-  }
+  __device__ __forceinline__ void cov(int pos) { put(pos, SO_COV << 3, 0, 0, 0, 0); }
   __device__ __forceinline__ void event(const rv_event& e) {
-    // one atomic per group of converged lanes
     cg::coalesced_group g = cg::coalesced_threads();
     unsigned long long slot = 0;
     if (g.thread_rank() == 0) slot = atomicAdd(&a->stats->n_events, (unsigned long long)g.size());
@@ -176,11 +177,38 @@ struct DeviceSink {
     a->events[slot] = e;
     n_ev++;
   }
-  __device__ __forceinline__ void max_read_len(int tlen) {
-    if (!mute && tlen > a->max_rl[dr - a->regions]) atomicMax(a->max_rl + (dr - a->regions), tlen);
+  __device__ __forceinline__ bool segment(const SegDesc& sd, bool dir, int mapq, int nm) {
+    if (!want_segments) return false;
+    const int slot = n_seg + (first_taken ? 1 : 0);
+    if (slot > 1 || sd.rlen > 1800 || sd.re > 65535) return false;
+    GDesc gd;
+    gd.m_start = sd.m_start;
+    gd.m_len = (uint16_t)sd.len;
+    gd.re0 = (uint16_t)sd.re;
+    gd.qual_off = (uint32_t)(pool_off + 4 * (int64_t)rd->n_cigar + ((rd->l_seq + 1) >> 1) + sd.rp);
+    gd.rlen = (uint16_t)sd.rlen;
+    gd.mapq = (uint8_t)mapq;
+    gd.dir_nm = (uint8_t)((dir ? 0x80 : 0) | nm);
+    const uint4 ml = make_uint4(sd.ml[0], sd.ml[1], sd.ml[2], sd.ml[3]);
+    if (slot == 0) {
+      *(uint4*)(a->descs + item) = *(const uint4*)&gd;
+      a->desc_mm[item] = (uint16_t)sd.mm_blocks;
+      if (sd.mm_blocks) a->desc_mml[item] = ml;
+    } else {
+      *(uint4*)(a->descs2 + item) = *(const uint4*)&gd;
+      a->desc_mm2[item] = (uint16_t)sd.mm_blocks;
+      if (sd.mm_blocks) a->desc_mml2[item] = ml;
+      ((uint16_t*)(a->descs + item))[2] |= (uint16_t)GD_HAS_SECOND;  // m_len of the first descriptor
+    }
+    n_seg++;
+    const int back = rd->pos - sd.m_start, reach = sd.m_start + sd.len - rd->pos;
+    if (back > a->reach[0]) atomicMax(a->reach + 0, back);
+    if (reach > a->reach[1]) atomicMax(a->reach + 1, reach);
+    return true;
   }
-  __device__ __forceinline__ void kept(int aligned) { if (!mute) { kept_bases += aligned; n_kept++; } }
-  __device__ __forceinline__ void unsupported() { if (!mute) n_unsup++; }
+  __device__ __forceinline__ void max_read_len(int) {}   // counted by rv_pileup_kernel
+  __device__ __forceinline__ void kept(int) {}
+  __device__ __forceinline__ void unsupported() { n_unsup++; }
 };
 
 __device__ __forceinline__ int find_region(const DevRegion* regs, int n, int64_t item) {
@@ -234,12 +262,10 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
   pr.m_start = pr.m_len = pr.rp0 = 0;
   DeviceSink s;
   s.a = &a;
-  s.kept_bases = s.n_kept = s.n_unsup = s.n_over = s.n_ev = s.n_clip = 0;
+  s.kept_bases = s.n_kept = s.n_unsup = s.n_over = 0;
   s.mute = false;
-  s.pend = false;
-  s.goodq = a.P.goodq;
-  s.goodq_i = iceil(a.P.goodq);
   const DevRegion* dr = a.regions;
+  s.dr = dr;
   rv_read rd;
   rd.data_off16 = 0; rd.n_cigar = 0; rd.l_seq = 0; rd.pos = 0;
   RefView ref;
@@ -256,7 +282,7 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
     rd = a.reads[read_idx - dr->read_bias];
     ref.lo = dr->r.ref_lo;
     ref.hi = dr->r.ref_hi;
-    s.bind(dr, a.counts, a.cov);
+    s.dr = dr;
     // htslib iterator overlap test (sam_itr_next): pos0 < end && endpos > beg0
     if (rd.pos - 1 < dr->r.end && rd.end_pos > dr->r.start - 1 &&
         !(a.P.dedup && is_duplicate_read(a.P, dr->r, a.reads - dr->read_bias, a.pool - dr->pool_bias, read_idx)))
@@ -336,7 +362,7 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
   unsigned long long queue_entry = 0;
   if (item < a.n_items) {
     GDesc gd;
-    gd.m_start = 0; gd.m_len = 0; gd.rp0 = 0; gd.seq_off4 = 0; gd.l_seq = 0; gd.mapq = 0; gd.dir_nm = 0;
+    gd.m_start = 0; gd.m_len = 0; gd.re0 = 0; gd.qual_off = 0; gd.rlen = 0; gd.mapq = 0; gd.dir_nm = 0;
     if (pr.ok) {
       // parseCigar.cpp:630 / skipOverlappingReads :182-206 — the -u / --UN test happens once, before the first op
       bool skip = false;
@@ -353,9 +379,9 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
         if (plain) {
           gd.m_start = pr.m_start;
           gd.m_len = (uint16_t)pr.m_len;
-          gd.rp0 = (uint16_t)pr.rp0;
-          gd.seq_off4 = (uint32_t)seq_word;
-          gd.l_seq = (uint16_t)rd.l_seq;
+          gd.re0 = 0;                      // a read of shape [H][S] M [S][H]: the run is the whole aligned part
+          gd.qual_off = (uint32_t)(seq_word * 4 + (size_t)((rd.l_seq + 1) >> 1) + (size_t)pr.rp0);
+          gd.rlen = (uint16_t)pr.m_len;
           gd.mapq = (uint8_t)pr.mapq;
           gd.dir_nm = (uint8_t)((pr.dir ? 0x80 : 0) | pr.nm);
           back = rd.pos - pr.m_start;
@@ -428,7 +454,9 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
   }
 }
 
-// The exact CIGAR walk for the queued work items, one per thread (all lanes busy with walks).
+// The queued work items, one per thread: reads with soft clips or indels, reads whose matched run is not plain.
+// prepare_read is repeated (the classify kernel keeps no per-read state), then walk_read runs the literal CIGAR walk
+// with a ListSink: plain matched stretches leave gather descriptors, the rest goes to the SparseObs list / the events.
 // The grid is sized to what is resident (MIN_CTAS per SM); a warp takes its next 32 queue entries from a cursor, whole-read
 // walks first, so the long walks start early and the short soft-clip walks fill the tail.
 template <int MIN_CTAS>
@@ -459,23 +487,30 @@ __global__ void __launch_bounds__(128, MIN_CTAS) rv_walk_kernel(PileupArgs a) {
     ref.n = a.ref_n;
     ref.lo = dr->r.ref_lo;
     ref.hi = dr->r.ref_hi;
-    DeviceSink s;
+    ListSink s;
     s.a = &a;
-    s.bind(dr, a.counts, a.cov);
-    s.kept_bases = s.n_kept = s.n_unsup = s.n_over = s.n_ev = s.n_clip = 0;
-    s.goodq = a.P.goodq;
-    s.goodq_i = iceil(a.P.goodq);
-    s.pend = false;
-    s.mute = true;
+    s.bind(dr);
+    s.item = item;
+    s.n_seg = 0;
+    s.first_taken = plain_done;
+    s.want_segments = !a.force_exact;
+    s.rd = &rd;
+    s.pool_off = (int64_t)rd.data_off16 * 16 - dr->pool_bias;
+    s.n_unsup = s.n_over = s.n_clip = s.n_ev = 0;
     Prep pr;
     const rv_region R = dr->r;  // by value: the walk compares against start / end at every base
-    prepare_read(a.P, R, rd, pool, ref, s, true, pr);
-    s.mute = false;
+    {
+      DeviceSink mute;          // prepare_read's statistics were already counted by rv_pileup_kernel
+      mute.a = &a;
+      mute.dr = dr;
+      mute.mute = true;
+      mute.kept_bases = mute.n_kept = mute.n_unsup = mute.n_over = 0;
+      prepare_read(a.P, R, rd, pool, ref, mute, true, pr);
+    }
     if (!pr.ok) continue;  // cannot happen: the item was queued because it passed
     FastDesc scratch;
     walk_read(a.P, R, ri, rd, pool, ref, (uint32_t)read_idx, s, pr, plain_done ? &scratch : (FastDesc*)0,
               plain_done ? 1 : 0);
-    s.resolve();
     over += s.n_over;
     unsup += s.n_unsup;
     clip += s.n_clip;
@@ -486,21 +521,38 @@ __global__ void __launch_bounds__(128, MIN_CTAS) rv_walk_kernel(PileupArgs a) {
   if (full) atomicAdd(&a.stats->n_walk_full, full);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Gather pileup: one lane per table position, no atomics.
-// A CTA owns GATHER_TILE consecutive table positions of one region (halo included: the kernel writes
-// every row of the table, so no memset is needed).  Per round it
-//   1. reads up to 256 descriptors of the candidate window, clips their matched run to the tile and sizes the
-//      16-byte chunks of packed bases / qualities each needs (block prefix sum = arena offsets),
-//   2. copies those chunks global -> shared, one warp per read (coalesced LDG.128 / STS.128),
-//   3. appends each staged read to the list of every warp whose 32 positions it overlaps,
-//   4. lets every lane walk its warp's list: one broadcast record + two shared-memory byte loads per
-//      observation; the reference allele accumulates in registers, anything else goes straight to the
-//      lane's own table row (plain read-modify-write: the position is owned by exactly this lane).
-// pstd/qstd ("two observations differ", parseCigar.cpp:902-914) = AND-reduction != OR-reduction of (tp, q).
-// ------------------------------------------------------------------------------------------------
-static const int ARENA_CHUNKS = 2048;  // 32 KB of staged read bytes per round
+// The SparseObs list onto the tables (after the gather kernel has stored every row): one entry per thread.
+__device__ __forceinline__ void row_observe(uint32_t* row, uint32_t dir, uint32_t tp, uint32_t q, uint32_t mapq, uint32_t nm, int thr);
+__global__ void __launch_bounds__(256) rv_apply_kernel(const SparseObs* list, const unsigned long long* count, unsigned long long cap,
+                                                        uint32_t* counts, uint32_t* cov, int thr) {
+  unsigned long long n = *count;
+  if (n > cap) n = cap;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint4 v = *(const uint4*)(list + i);
+    const uint32_t flags = v.z >> 16, kind = (flags >> 3) & 3u;
+    if (kind == SO_COV) { atomicAdd(cov + v.x, 1u); continue; }
+    uint32_t* row = counts + ((size_t)v.x * 4 + (flags & 3u)) * RV_ROW_U32;
+    const uint32_t dir = (flags >> 2) & 1u, tp = v.y & 0xffffu, q = (v.y >> 16) & 0xffu, mapq = v.y >> 24;
+    const int nm = (int)(int16_t)(v.z & 0xffffu);
+    if (kind == SO_SINGLE) {
+      row_observe(row, dir, tp, q, mapq, (uint32_t)nm, thr);
+    } else {
+      // addCnt (parseCigar.cpp:300-325) / the subtraction of an insertion's anchor base (:1471-1490): no pstd / qstd
+      const uint32_t sg = kind == SO_ADD ? 1u : 0u - 1u;
+      atomicAdd(row + (dir ? RV_F_REV : RV_F_FWD), sg);
+      atomicAdd(row + RV_F_SUM_TP, sg * tp);
+      atomicAdd(row + RV_F_SUM_Q, sg * q);
+      atomicAdd(row + RV_F_SUM_MAPQ, sg * mapq);
+      if (nm) atomicAdd(row + RV_F_SUM_NM, sg * (uint32_t)nm);
+      if ((int)q >= thr) atomicAdd(row + RV_F_HI, sg);
+    }
+  }
+}
 
+// ------------------------------------------------------------------------------------------------
+// Position-major accumulation of the plain segments (rv_gather4_kernel): arguments and the tile index.
+// ------------------------------------------------------------------------------------------------
 struct GatherArgs {
   double goodq;
   const DevRegion* regions;
@@ -517,8 +569,11 @@ struct GatherArgs {
   const int32_t* reach;
   int64_t* tile_range;  // [2 * tile]: first candidate read of the tile; number of candidates | region << 32
   int64_t n_tiles;
-  int tile;             // table positions per tile (GATHER_TILE, or G4_W for rv_gather4_kernel)
+  int tile;             // table positions per tile (G4_W)
   const uint4* desc_mml;
+  const GDesc* descs2;  // second segments (GD_HAS_SECOND)
+  const uint16_t* desc_mm2;
+  const uint4* desc_mml2;
   int64_t pool_bytes;   // bytes of the device pool (rv_gather4_kernel clamps its look-ahead loads to it)
   int thr;              // ceil(goodq)
   int run;              // consecutive tiles per warp (rv_gather4_kernel)
@@ -560,221 +615,6 @@ __global__ void rv_tile_index_kernel(GatherArgs a) {
   a.tile_range[2 * tile + 1] = (int64_t)(((unsigned long long)(unsigned)ri << 32) | (unsigned)(hi - lo));
 }
 
-static const int REC_BIAS = 256;  // keeps the arena byte offsets of a staged read non-negative 16-bit numbers
-
-__global__ void __launch_bounds__(GATHER_TILE, 5) rv_gather_kernel(GatherArgs a) {
-  __shared__ __align__(16) uint8_t s_arena[ARENA_CHUNKS * 16];
-  // staged read: {rel_start, seq byte offset | qual byte offset << 16 (both + REC_BIAS), m_len | par << 16 | dir << 17,
-  //               mapq | nm << 16}
-  __shared__ uint4 s_rec[GATHER_TILE];
-  __shared__ uint4 s_copy[GATHER_TILE];  // {first seq chunk, first qual chunk, n seq chunks | n qual chunks << 8, arena chunk}
-  __shared__ int s_wlo[GATHER_TILE / 32], s_whi[GATHER_TILE / 32];  // staged reads [lo, hi) that may overlap the warp
-  __shared__ int s_wsum[GATHER_TILE / 32];
-  __shared__ int s_ntake, s_nslots;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t tile = blockIdx.x;
-  const int4 tinfo = ((const int4*)a.tile_range)[tile];  // {read lo (64 bit), n reads, region}
-  const DevRegion* dr = a.regions + tinfo.w;
-  const int64_t lo = (int64_t)(((unsigned long long)(unsigned)tinfo.y << 32) | (unsigned)tinfo.x);
-  const int64_t hi = lo + tinfo.z;
-  const int p_lo = dr->first_pos + (int)(tile - dr->tile_base) * GATHER_TILE;
-  const int c_lo = p_lo > dr->r.start ? p_lo : dr->r.start;  // positions that can receive observations
-  const int c_hi = p_lo + GATHER_TILE - 1 < dr->r.end ? p_lo + GATHER_TILE - 1 : dr->r.end;
-  const int x = tid;
-  const int p = p_lo + x;
-  const bool in_table = p - dr->first_pos < dr->n_pos;
-  const bool live = p >= c_lo && p <= c_hi;
-  // the lane's reference allele, as a BAM nibble (0 = none: every observation takes the row path)
-  int refnib = 0;
-  if (live && p >= dr->r.ref_lo && p <= dr->r.ref_hi && p >= a.ref_start && (int64_t)(p - a.ref_start) < a.ref_n) {
-    const char c = a.ref[p - a.ref_start];
-    refnib = c == 'A' ? 1 : c == 'C' ? 2 : c == 'G' ? 4 : c == 'T' ? 8 : 0;
-  }
-  const int thr = (int)ceil(a.goodq);  // integer q >= goodq
-  const int64_t t_row = dr->tab_off + (p - dr->first_pos);
-  uint32_t* const row0 = a.counts + (size_t)t_row * RV_POS_U32;
-  uint32_t n_ref = 0, n_rev = 0, sum_tp = 0, sum_q = 0, sum_mapq = 0, sum_nm = 0;
-  uint32_t v_and = 0xffffffffu, v_or = 0, n_other = 0, other_mask = 0;
-  int n_lowq = 0;  // minus the number of reference-allele observations below the quality threshold
-  const GDesc* item_desc = a.descs + (dr->item_base - dr->r.read_lo);  // descriptor of read index i
-  const uint16_t* item_mm = a.desc_mm + (dr->item_base - dr->r.read_lo);
-  const uint4* pool16 = (const uint4*)a.pool;
-  const uint32_t wbit = 1u << (18 + warp);  // this warp's "decode the bases" flag in a staged record
-  // lane constants of the byte lookups: seq byte = offset + ((x + par) >> 1), qual byte = offset + x
-  const int xq = x - REC_BIAS;
-
-  for (int64_t base = lo; base < hi;) {
-    // ---- 1. descriptors of this round, clipped to the tile ------------------------------------------
-    if (tid < GATHER_TILE / 32) { s_wlo[tid] = GATHER_TILE; s_whi[tid] = 0; }
-    if (tid == 0) { s_ntake = 0; s_nslots = 0; }
-    const int64_t i = base + tid;
-    GDesc d;
-    d.m_len = 0;
-    uint32_t mm = 0;
-    if (i < hi) {
-      *(uint4*)&d = *(const uint4*)(item_desc + i);
-      mm = item_mm[i];
-    }
-    bool take = false;
-    int ns = 0, nq = 0, n_lo = 0;
-    size_t s_first = 0, q_first = 0;
-    if (d.m_len != 0) {
-      const int k_lo = c_lo - d.m_start > 0 ? c_lo - d.m_start : 0;
-      const int k_hi = c_hi + 1 - d.m_start < (int)d.m_len ? c_hi + 1 - d.m_start : (int)d.m_len;
-      if (k_lo < k_hi) {
-        take = true;
-        n_lo = d.rp0 + k_lo;
-        const int n_hi_ = d.rp0 + k_hi;
-        const size_t sb = (size_t)d.seq_off4 * 4;
-        const size_t qb = sb + ((d.l_seq + 1) >> 1);
-        s_first = sb + (n_lo >> 1);
-        q_first = qb + n_lo;
-        ns = (int)(((sb + ((n_hi_ - 1) >> 1)) >> 4) - (s_first >> 4)) + 1;
-        nq = (int)(((qb + n_hi_ - 1) >> 4) - (q_first >> 4)) + 1;
-      }
-    }
-    // block inclusive scan of (chunks needed | take << 16)
-    const int mine = (ns + nq) | (take ? 1 << 16 : 0);
-    int incl = mine;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, incl, off);
-      if (lane >= off) incl += y;
-    }
-    if (lane == 31) s_wsum[warp] = incl;
-    __syncthreads();
-    for (int w = 0; w < warp; ++w) incl += s_wsum[w];
-    const int chunks_incl = incl & 0xffff;
-    const bool fits = chunks_incl <= ARENA_CHUNKS;  // a prefix of the round (the scan is monotone)
-    const bool staged = take && fits;
-    {
-      const unsigned bf = __ballot_sync(0xffffffffu, fits), bs = __ballot_sync(0xffffffffu, staged);
-      if (lane == 0) {
-        if (bf) atomicAdd(&s_ntake, __popc(bf));
-        if (bs) atomicAdd(&s_nslots, __popc(bs));
-      }
-    }
-    if (staged) {
-      const int slot = (incl >> 16) - 1;
-      const int chunk0 = chunks_incl - (ns + nq);
-      const int rel_start = d.m_start - p_lo;
-      const int n0 = (int)d.rp0 - rel_start;  // read offset of the base under tile coordinate 0
-      const int par = n0 & 1;
-      const int so = chunk0 * 16 + (int)(s_first & 15) - (n_lo >> 1) + ((n0 - par) >> 1) + REC_BIAS;
-      const int qo = (chunk0 + ns) * 16 + (int)(q_first & 15) - n_lo + n0 + REC_BIAS;
-      s_copy[slot] = make_uint4((uint32_t)(s_first >> 4), (uint32_t)(q_first >> 4), (uint32_t)(ns | (nq << 8)), (uint32_t)chunk0);
-      const int x_lo = rel_start > c_lo - p_lo ? rel_start : c_lo - p_lo;
-      const int x_hi = rel_start + (int)d.m_len - 1 < c_hi - p_lo ? rel_start + (int)d.m_len - 1 : c_hi - p_lo;
-      uint32_t wbits = 0;  // warps whose 32 positions see a 16-base block of the run with a mismatch in it
-      for (int w = x_lo >> 5; w <= (x_hi >> 5); ++w) {
-        if (slot < s_wlo[w]) atomicMin(&s_wlo[w], slot);
-        if (slot + 1 > s_whi[w]) atomicMax(&s_whi[w], slot + 1);
-        const int kw_lo = 32 * w - rel_start > 0 ? 32 * w - rel_start : 0;
-        const int kw_hi = 32 * w + 31 - rel_start < (int)d.m_len - 1 ? 32 * w + 31 - rel_start : (int)d.m_len - 1;
-        const int bl = min(kw_lo >> 4, 15), bh = min(kw_hi >> 4, 15);
-        if (mm & (((2u << (bh - bl)) - 1u) << bl)) wbits |= 1u << w;
-      }
-      s_rec[slot] = make_uint4((uint32_t)rel_start, (uint32_t)so | ((uint32_t)qo << 16),
-                               (uint32_t)d.m_len | ((uint32_t)par << 16) | ((uint32_t)(d.dir_nm >> 7) << 17) | (wbits << 18),
-                               (uint32_t)d.mapq | ((uint32_t)(d.dir_nm & 0x7f) << 16));
-    }
-    __syncthreads();
-    // ---- 2. stage the bytes: one warp per read, one 16-byte chunk per lane, asynchronous copies ---------
-    const int n_slots = s_nslots, n_take = s_ntake;
-    for (int sidx = warp; sidx < n_slots; sidx += GATHER_TILE / 32) {
-      const uint4 c = s_copy[sidx];
-      const int cns = (int)(c.z & 0xff), cnq = (int)(c.z >> 8);
-      if (lane < cns + cnq) {
-        const size_t src = lane < cns ? (size_t)c.x + lane : (size_t)c.y + (lane - cns);
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(s_arena + (size_t)(c.w + lane) * 16);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(pool16 + src) : "memory");
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    // ---- 3. every lane walks the staged reads that may overlap its warp ---------------------------------
-    if (live) {
-      const int w_lo = s_wlo[warp], w_hi = s_whi[warp];
-      uint32_t add_acc = 0;
-#pragma unroll 4
-      for (int slot = w_lo; slot < w_hi; ++slot) {
-        const uint4 r = s_rec[slot];
-        const int m_len = (int)(r.z & 0xffffu);
-        const int k = x - (int)r.x;
-        if ((unsigned)k >= (unsigned)m_len) continue;
-        const uint32_t q = s_arena[(int)(r.y >> 16) + xq];
-        int nib = refnib;
-        if (r.z & wbit) {
-          // (warp-uniform: the record is broadcast) some base of the run under this warp differs from the reference:
-          // decode the lane's base.  Otherwise the classify kernel has proven it equal to the reference base.
-          const bool odd = (r.z >> 16) & 1;  // parity of the read offset under tile coordinate 0
-          const int sbyte = s_arena[(int)(r.y & 0xffffu) - REC_BIAS + ((x + (int)odd) >> 1)];
-          nib = ((x ^ (int)odd) & 1) ? (sbyte & 15) : (sbyte >> 4);
-        }
-        const uint32_t tp = (uint32_t)min(k + 1, m_len - k);
-        const uint32_t v = tp | (q << 16);
-        const uint32_t dir = (r.z >> 17) & 1u;
-        if (nib == refnib) {
-          n_ref++;
-          n_rev += dir;
-          sum_tp += tp;
-          sum_q += q;
-          add_acc += r.w;
-          n_lowq += ((int)q - thr) >> 31;  // -1 below the threshold
-          v_and &= v;
-          v_or |= v;
-        } else {
-          // a base that differs from the reference: the lane's own row of that allele, read-modify-write
-          const uint32_t hiq = (int)q >= thr ? 1u : 0u;
-          const int al = nib_allele(nib);
-          uint4* row4 = (uint4*)(row0 + al * RV_ROW_U32);
-          uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
-          if (other_mask & (1u << al)) { ra = row4[0]; rb = row4[1]; }
-          ra.x += 1u - dir; ra.y += dir; ra.z += tp; ra.w += q;
-          rb.x += r.w & 0xffffu; rb.y += r.w >> 16; rb.z += hiq;
-          uint32_t w = rb.w;
-          if ((w >> 31) == 0) w = v | (1u << 31);
-          else {
-            if ((w ^ v) & 0xffffu) w |= 1u << 24;
-            if ((w ^ v) & 0xff0000u) w |= 1u << 25;
-          }
-          rb.w = w;
-          row4[0] = ra;
-          row4[1] = rb;
-          other_mask |= 1u << al;
-          n_other++;
-        }
-      }
-      sum_mapq += add_acc & 0xffffu;  // at most 256 reads per round: neither half can overflow
-      sum_nm += add_acc >> 16;
-    }
-    __syncthreads();
-    base += n_take;
-  }
-  if (!in_table) return;
-  // ---- write the position: the reference allele from registers, untouched alleles as zeros ------------
-  a.cov[t_row] = n_ref + n_other;
-  const int a0 = refnib ? nib_allele(refnib) : -1;
-#pragma unroll
-  for (int al = 0; al < 4; ++al) {
-    if (other_mask & (1u << al)) continue;
-    uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
-    if (al == a0 && n_ref) {
-      ra = make_uint4(n_ref - n_rev, n_rev, sum_tp, sum_q);
-      // the recorded (tp, q): a field of the AND-reduction is the common value whenever that field's flag stays
-      // clear, and is never looked at again once the flag is set
-      uint32_t w = (v_and & 0xffffffu) | (1u << 31);
-      if ((v_and ^ v_or) & 0xffffu) w |= 1u << 24;
-      if ((v_and ^ v_or) & 0xff0000u) w |= 1u << 25;
-      rb = make_uint4(sum_mapq, sum_nm, n_ref + (uint32_t)n_lowq, w);
-    }
-    uint4* row4 = (uint4*)(row0 + al * RV_ROW_U32);
-    row4[0] = ra;
-    row4[1] = rb;
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // rv_gather4_kernel — the plain matched runs, four table positions per lane.
 // A WARP owns G4_W = 128 consecutive table positions (lane l: positions 4l..4l+3); warps share nothing, so the
@@ -799,6 +639,7 @@ template <int G4_PF>  // quality words are fetched this many records ahead
 struct G4Warp {
   uint4 rec[32 + 2 * G4_PF];      // {-(s+B) x2, (s+L+1+B) x2, PRMT selector | flag << 16, -}
   uint4 ldr[32 + 2 * G4_PF];      // {word index of the quality under coordinate 0, first lane, last lane the run covers, -}
+  uint2 rec2[32 + 2 * G4_PF];     // segments that are not a whole read: {-(s+B) + re0 x2, (s+L+1+B) + tail x2} (tp of the SIMD pass)
   uint8_t excl[32][32];           // [record][lane]: bit j = position j of the lane is masked out of the SIMD pass
   uint32_t d_n[G4_W + 4], c_n[G4_W + 4], d_rev[G4_W + 4], d_mapq[G4_W + 4], d_nm[G4_W + 4], d_tp1[G4_W + 4], d_tp2[G4_W + 4];
 };
@@ -892,11 +733,12 @@ __global__ void __launch_bounds__(G4_WARPS * 32, MIN_CTAS) rv_gather4_kernel(Gat
   const uint32_t X23 = X01 + 0x00020002u;
   const uint32_t bias4 = (uint32_t)(128 - thr) * 0x01010101u;  // 1 <= thr <= 128 (checked by the host)
   const uint32_t* const pool32 = (const uint32_t*)a.pool;
-  const GDesc* item_desc = a.descs + (dr->item_base - dr->r.read_lo);  // descriptor of read index i
-  const uint16_t* item_mm = a.desc_mm + (dr->item_base - dr->r.read_lo);
-  const uint4* item_mml = a.desc_mml + (dr->item_base - dr->r.read_lo);
+  const int64_t item_shift = dr->item_base - dr->r.read_lo;  // work item of read index i = i + item_shift
+  const GDesc* item_desc = a.descs + item_shift;
+  const uint16_t* item_mm = a.desc_mm + item_shift;
   uint32_t tp_and01 = 0xffffffffu, tp_and23 = 0xffffffffu, tp_or01 = 0, tp_or23 = 0, q_and = 0xffffffffu, q_or = 0;
   uint32_t sum_q[4] = {0, 0, 0, 0}, n_hi[4] = {0, 0, 0, 0};
+  uint32_t sum_tp_g[4] = {0, 0, 0, 0};  // tp of segments that are not a whole read (summed in the SIMD pass)
 
   // Neighbouring tiles walk their candidates in opposite directions: the reads two tiles share are then needed by
   // both at the same end of their loops, i.e. close in time (L1 / L2 hits instead of a second trip to DRAM).
@@ -912,11 +754,10 @@ __global__ void __launch_bounds__(G4_WARPS * 32, MIN_CTAS) rv_gather4_kernel(Gat
     }
   }
   for (int bi = 0; bi < n_batches; ++bi) {
-    // ---- 1. one candidate descriptor per lane -> record of the SIMD pass, range adds, mismatching bases -----------
     const int64_t i = lo + 32 * (int64_t)(downward ? n_batches - 1 - bi : bi) + lane;
     GDesc d;
     *(uint4*)&d = d_nxt;
-    const uint32_t mm = mm_nxt;
+    uint32_t mm = mm_nxt;
     d_nxt = make_uint4(0, 0, 0, 0);  // (m_len = 0) the next round's descriptor travels while this round computes
     mm_nxt = 0;
     {
@@ -926,6 +767,23 @@ __global__ void __launch_bounds__(G4_WARPS * 32, MIN_CTAS) rv_gather4_kernel(Gat
         mm_nxt = item_mm[i_n];
       }
     }
+    bool second = (d.m_len & GD_HAS_SECOND) != 0;  // the work item has a second segment (a read with an indel)
+    d.m_len &= (uint16_t)GD_LEN_MASK;
+    const uint4* cur_mml = a.desc_mml + item_shift;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1) {
+      if (!__any_sync(0xffffffffu, second)) break;
+      d.m_len = 0;
+      mm = 0;
+      if (second) {
+        *(uint4*)&d = *(const uint4*)(a.descs2 + item_shift + i);
+        d.m_len &= (uint16_t)GD_LEN_MASK;
+        mm = a.desc_mm2[item_shift + i];
+      }
+      cur_mml = a.desc_mml2 + item_shift;
+    }
+    // ---- 1. one candidate descriptor per lane -> record of the SIMD pass, range adds, mismatching bases -----------
     bool take = false;
     int k_lo = 0, k_hi = 0;
     if (d.m_len != 0) {
@@ -939,13 +797,15 @@ __global__ void __launch_bounds__(G4_WARPS * 32, MIN_CTAS) rv_gather4_kernel(Gat
     if (take) {
       const int slot = __popc(bt & ((1u << lane) - 1u));
       const int s = d.m_start - p_lo, L = (int)d.m_len;
+      const int re0 = (int)d.re0, tail = (int)d.rlen - re0 - L;
+      const bool general = (re0 | tail) != 0;  // not a whole read: tp = min(re0 + k + 1, L - k + tail)
       const uint32_t dir = d.dir_nm >> 7, nm = d.dir_nm & 0x7fu, mapq = d.mapq;
-      const int64_t qb = (int64_t)d.seq_off4 * 4 + ((d.l_seq + 1) >> 1) + d.rp0;  // pool byte of the run's first quality
-      const int64_t q0 = qb - s;                                                   // ... of the quality under coordinate 0
+      const int64_t qb = (int64_t)d.qual_off;  // pool byte of the segment's first quality
+      const int64_t q0 = qb - s;               // ... of the quality under coordinate 0
       bool any_ex = false;
       if (mm) {
-        // mismatching bases of the run that fall on this warp's live positions
-        const uint4 ml = item_mml[i];
+        // mismatching bases of the segment that fall on this warp's live positions
+        const uint4 ml = cur_mml[i];
         unsigned long long l_lo = (unsigned long long)ml.x | ((unsigned long long)ml.y << 32);
         unsigned long long l_hi = (unsigned long long)ml.z | ((unsigned long long)ml.w << 32);
 #pragma unroll 1
@@ -962,20 +822,23 @@ __global__ void __launch_bounds__(G4_WARPS * 32, MIN_CTAS) rv_gather4_kernel(Gat
               ((uint4*)W.excl[slot])[1] = make_uint4(0, 0, 0, 0);
             }
             W.excl[slot][x >> 2] |= (uint8_t)(1u << (x & 3));
-            const uint32_t tp = (uint32_t)min(k + 1, L - k);
+            const uint32_t tp = (uint32_t)min(re0 + k + 1, L - k + tail);
             const uint32_t q = a.pool[qb + k];
             row_observe(tile_rows + (size_t)x * RV_POS_U32 + (e & 3u) * RV_ROW_U32, dir, tp, q, mapq, nm, thr);
             atomicAdd(&W.c_n[x], 1u);
             if (dir) { atomicAdd(&W.d_rev[x], 0u - 1u); atomicAdd(&W.d_rev[x + 1], 1u); }
             atomicAdd(&W.d_mapq[x], 0u - mapq); atomicAdd(&W.d_mapq[x + 1], mapq);
             if (nm) { atomicAdd(&W.d_nm[x], 0u - nm); atomicAdd(&W.d_nm[x + 1], nm); }
-            atomicAdd(&W.d_tp1[x], 0u - tp); atomicAdd(&W.d_tp1[x + 1], tp);
+            if (!general) { atomicAdd(&W.d_tp1[x], 0u - tp); atomicAdd(&W.d_tp1[x + 1], tp); }
           }
         }
       }
-      const uint32_t flag = any_ex ? 0x10000u : 0u;
+      const uint32_t flag = (any_ex ? 0x10000u : 0u) | (general ? 0x20000u : 0u);
       W.rec[slot] = make_uint4(((uint32_t)(-(s + G4_B)) & 0xffffu) * 0x10001u, ((uint32_t)(s + L + 1 + G4_B) & 0xffffu) * 0x10001u,
                                (0x3210u + 0x1111u * (uint32_t)(q0 & 3)) | flag, 0u);
+      if (general)
+        W.rec2[slot] = make_uint2(((uint32_t)(-(s + G4_B) + re0) & 0xffffu) * 0x10001u,
+                                  ((uint32_t)(s + L + 1 + G4_B + tail) & 0xffffu) * 0x10001u);
       // lanes outside the run load what its nearest covered lane loads (no sector that no lane needs is fetched)
       W.ldr[slot] = make_uint4((uint32_t)(int)(q0 >> 2), (uint32_t)((s > 0 ? s : 0) >> 2), (uint32_t)((s + L - 1 < G4_W - 1 ? s + L - 1 : G4_W - 1) >> 2), 0u);
       // range adds of the per-read constants over [s, s+L) clipped to the tile (index G4_W is never read)
@@ -994,15 +857,17 @@ __global__ void __launch_bounds__(G4_WARPS * 32, MIN_CTAS) rv_gather4_kernel(Gat
         atomicAdd(&W.d_mapq[rb], 0u - mapq);
         if (nm) atomicAdd(&W.d_nm[rb], 0u - nm);
       }
-      // tp = min(k+1, L-k): slope +1 on [s, s+h), -1 on [s+L-h+1, s+L], h = ceil(L/2); second differences, the part
-      // left of the tile folded into coordinate 0
-      const int h = (L + 1) >> 1;
-      const int i0 = s, i1 = s + h, i2 = s + L - h + 1, i3 = s + L + 1;
-      if (i0 <= 0) g_tp2 += 1; else if (i0 < G4_W) atomicAdd(&W.d_tp2[i0], 1u);
-      if (i1 <= 0) g_tp2 -= 1; else if (i1 < G4_W) atomicAdd(&W.d_tp2[i1], 0u - 1u);
-      if (i2 <= 0) g_tp2 -= 1; else if (i2 < G4_W) atomicAdd(&W.d_tp2[i2], 0u - 1u);
-      if (i3 <= 0) g_tp2 += 1; else if (i3 < G4_W) atomicAdd(&W.d_tp2[i3], 1u);
-      if (s < 0) g_tp1 = min(-s, s + L + 1);  // tp under coordinate -1
+      if (!general) {
+        // tp = min(k+1, L-k): slope +1 on [s, s+h), -1 on [s+L-h+1, s+L], h = ceil(L/2); second differences, the part
+        // left of the tile folded into coordinate 0
+        const int h = (L + 1) >> 1;
+        const int i0 = s, i1 = s + h, i2 = s + L - h + 1, i3 = s + L + 1;
+        if (i0 <= 0) g_tp2 += 1; else if (i0 < G4_W) atomicAdd(&W.d_tp2[i0], 1u);
+        if (i1 <= 0) g_tp2 -= 1; else if (i1 < G4_W) atomicAdd(&W.d_tp2[i1], 0u - 1u);
+        if (i2 <= 0) g_tp2 -= 1; else if (i2 < G4_W) atomicAdd(&W.d_tp2[i2], 0u - 1u);
+        if (i3 <= 0) g_tp2 += 1; else if (i3 < G4_W) atomicAdd(&W.d_tp2[i3], 1u);
+        if (s < 0) g_tp1 = min(-s, s + L + 1);  // tp under coordinate -1
+      }
     }
     if (__any_sync(0xffffffffu, g_n != 0)) {
       const int t_n = __reduce_add_sync(0xffffffffu, g_n), t_rev = __reduce_add_sync(0xffffffffu, g_rev);
@@ -1029,17 +894,25 @@ __global__ void __launch_bounds__(G4_WARPS * 32, MIN_CTAS) rv_gather4_kernel(Gat
         w1[u] = __ldg(pool32 + widx + 1);
       }
       uint32_t sq_lo = 0, sq_hi = 0, hi_acc = 0;  // at most 32 + G4_PF records: no byte / halfword can overflow
+      uint32_t stp01 = 0, stp23 = 0;              // (tp <= 900 for the segments summed here: rlen <= 1800)
       for (int r = 0; r < n_rec; r += G4_PF) {
 #pragma unroll
         for (int u = 0; u < G4_PF; ++u) {
           const uint4 rc = W.rec[r + u];
           const uint32_t dn01 = rc.y - X01, dn23 = rc.y - X23;
-          const uint32_t t01 = __viaddmin_s16x2_relu(X01, rc.x, dn01);  // tp of positions 0, 1 (0 = not covered)
-          const uint32_t t23 = __viaddmin_s16x2_relu(X23, rc.x, dn23);
+          uint32_t t01 = __viaddmin_s16x2_relu(X01, rc.x, dn01);  // min(k+1, L-k) of positions 0, 1 (0 = not covered)
+          uint32_t t23 = __viaddmin_s16x2_relu(X23, rc.x, dn23);
           uint32_t m = prmt(t01 + 0x7fff7fffu, t23 + 0x7fff7fffu, 0xfdb9u);  // 0xff per covered position
           if (rc.z & 0x10000u)  // (warp-uniform) the record has bases that differ from the reference under this warp
             m &= ~((((uint32_t)W.excl[r + u][lane] * 0x00204081u) & 0x01010101u) * 0xffu);
           const uint32_t m01 = prmt(m, 0u, 0x1100u), m23 = prmt(m, 0u, 0x3322u);
+          if (rc.z & 0x20000u) {  // (warp-uniform) a segment of a read with indels: its bases' read positions
+            const uint2 r2 = W.rec2[r + u];
+            t01 = __viaddmin_s16x2_relu(X01, r2.x, r2.y - X01);
+            t23 = __viaddmin_s16x2_relu(X23, r2.x, r2.y - X23);
+            stp01 += t01 & m01;
+            stp23 += t23 & m23;
+          }
           tp_and01 &= t01 | ~m01; tp_or01 |= t01 & m01;
           tp_and23 &= t23 | ~m23; tp_or23 |= t23 & m23;
           const uint32_t q4 = prmt(w0[u], w1[u], rc.z);
@@ -1057,8 +930,10 @@ __global__ void __launch_bounds__(G4_WARPS * 32, MIN_CTAS) rv_gather4_kernel(Gat
       }
       sum_q[0] += sq_lo & 0xffffu; sum_q[2] += sq_lo >> 16; sum_q[1] += sq_hi & 0xffffu; sum_q[3] += sq_hi >> 16;
       n_hi[0] += hi_acc & 0xffu; n_hi[1] += (hi_acc >> 8) & 0xffu; n_hi[2] += (hi_acc >> 16) & 0xffu; n_hi[3] += hi_acc >> 24;
+      sum_tp_g[0] += stp01 & 0xffffu; sum_tp_g[1] += stp01 >> 16; sum_tp_g[2] += stp23 & 0xffffu; sum_tp_g[3] += stp23 >> 16;
     }
     __syncwarp();
+    }  // first / second segment of the batch's work items
   }
   // ---- 3. prefix sums of the difference arrays, rows of the reference alleles -------------------------------------
   __syncwarp();
@@ -1071,6 +946,8 @@ __global__ void __launch_bounds__(G4_WARPS * 32, MIN_CTAS) rv_gather4_kernel(Gat
 #pragma unroll
   for (int j = 0; j < 4; ++j) stp[j] += W.d_tp1[x4 + j];
   warp_scan4(stp, lane);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) stp[j] += sum_tp_g[j];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     if (!in_tab[j]) continue;
@@ -1097,249 +974,6 @@ __global__ void __launch_bounds__(G4_WARPS * 32, MIN_CTAS) rv_gather4_kernel(Gat
   }
   __syncwarp();
   }  // tiles of the warp
-}
-
-// ------------------------------------------------------------------------------------------------
-// Warp-specialised form of the gather kernel: warp 8 is a producer that prepares the next round (descriptor
-// loads, clipping, arena layout, asynchronous global->shared copies) into one of two shared-memory stages
-// while warps 0-7 (one lane per table position) consume the other; named barriers hand the stages over.
-// ------------------------------------------------------------------------------------------------
-static const int WS_CAND = 128;          // candidate descriptors per round (4 per producer lane)
-static const int WS_STAGE_CHUNKS = 1024; // 16 KB of staged read bytes per stage
-static const int WS_THREADS = GATHER_TILE + 32;
-
-struct WsStage {
-  uint4 arena[WS_STAGE_CHUNKS];
-  uint4 rec[WS_CAND];
-  int wlo[GATHER_TILE / 32], whi[GATHER_TILE / 32];
-  int n_slots, done;
-  int pad[2];
-};
-
-__device__ __forceinline__ void named_bar_sync(int id, int count) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(int id, int count) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-
-__global__ void __launch_bounds__(WS_THREADS, 4) rv_gather_ws_kernel(GatherArgs a) {
-  __shared__ __align__(16) WsStage s_stage[2];
-  __shared__ uint4 s_copy[WS_CAND];  // producer scratch: {first seq chunk, first qual chunk, ns | nq << 8, arena chunk}
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t tile = blockIdx.x;
-  const int4 tinfo = ((const int4*)a.tile_range)[tile];  // {read lo (64 bit), n reads, region}
-  const DevRegion* dr = a.regions + tinfo.w;
-  const int64_t lo = (int64_t)(((unsigned long long)(unsigned)tinfo.y << 32) | (unsigned)tinfo.x);
-  const int64_t hi = lo + tinfo.z;
-  const int p_lo = dr->first_pos + (int)(tile - dr->tile_base) * GATHER_TILE;
-  const int c_lo = p_lo > dr->r.start ? p_lo : dr->r.start;  // positions that can receive observations
-  const int c_hi = p_lo + GATHER_TILE - 1 < dr->r.end ? p_lo + GATHER_TILE - 1 : dr->r.end;
-  enum { BAR_FULL = 1, BAR_EMPTY = 3 };
-
-  if (warp == GATHER_TILE / 32) {
-    // =========================== producer warp ===========================
-    const GDesc* item_desc = a.descs + (dr->item_base - dr->r.read_lo);  // descriptor of read index i
-    const uint4* pool16 = (const uint4*)a.pool;
-    int round = 0;
-    for (int64_t base = lo;; ++round) {
-      WsStage& st = s_stage[round & 1];
-      if (round >= 2) named_bar_sync(BAR_EMPTY + (round & 1), WS_THREADS);
-      if (base >= hi) {  // nothing left: tell the consumers
-        if (lane == 0) { st.n_slots = 0; st.done = 1; }
-        __syncwarp();
-        named_bar_arrive(BAR_FULL + (round & 1), WS_THREADS);
-        break;
-      }
-      if (lane < GATHER_TILE / 32) { st.wlo[lane] = WS_CAND; st.whi[lane] = 0; }
-      __syncwarp();
-      // ---- four consecutive candidates per lane: clip to the tile, size the chunks ----
-      GDesc d[4];
-      int ns[4], nq[4], n_lo[4];
-      unsigned sfirst_lo[4], qfirst_lo[4];  // low 4 bits of the first seq / qual byte address
-      unsigned sc0[4], qc0[4];
-      int mine = 0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int64_t i = base + lane * 4 + j;
-        d[j].m_len = 0;
-        if (i < hi) *(uint4*)&d[j] = *(const uint4*)(item_desc + i);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        ns[j] = nq[j] = 0;
-        n_lo[j] = 0; sfirst_lo[j] = qfirst_lo[j] = 0; sc0[j] = qc0[j] = 0;
-        if (d[j].m_len != 0) {
-          const int k_lo = c_lo - d[j].m_start > 0 ? c_lo - d[j].m_start : 0;
-          const int k_hi = c_hi + 1 - d[j].m_start < (int)d[j].m_len ? c_hi + 1 - d[j].m_start : (int)d[j].m_len;
-          if (k_lo < k_hi) {
-            n_lo[j] = d[j].rp0 + k_lo;
-            const int n_hi_ = d[j].rp0 + k_hi;
-            const size_t sb = (size_t)d[j].seq_off4 * 4;
-            const size_t qb = sb + ((d[j].l_seq + 1) >> 1);
-            const size_t s_first = sb + (n_lo[j] >> 1), q_first = qb + n_lo[j];
-            ns[j] = (int)(((sb + ((n_hi_ - 1) >> 1)) >> 4) - (s_first >> 4)) + 1;
-            nq[j] = (int)(((qb + n_hi_ - 1) >> 4) - (q_first >> 4)) + 1;
-            sfirst_lo[j] = (unsigned)(s_first & 15);
-            qfirst_lo[j] = (unsigned)(q_first & 15);
-            sc0[j] = (unsigned)(s_first >> 4);
-            qc0[j] = (unsigned)(q_first >> 4);
-            mine += (ns[j] + nq[j]) | (1 << 16);
-          }
-        }
-      }
-      // warp scan of (chunks | staged reads << 16) over the lanes, then over the lane's four candidates
-      int incl = mine;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, incl, off);
-        if (lane >= off) incl += y;
-      }
-      int run = incl - mine;  // exclusive prefix of this lane
-      int n_fit = 0, n_staged = 0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int need = ns[j] + nq[j];
-        const int chunk0 = run & 0xffff, slot = run >> 16;
-        const bool fits = chunk0 + need <= WS_STAGE_CHUNKS;  // a prefix of the round (the scan is monotone)
-        if (need) run += need | (1 << 16);
-        if (fits) n_fit++;
-        if (fits && need) {
-          n_staged++;
-          const int rel_start = d[j].m_start - p_lo;
-          const int n0 = (int)d[j].rp0 - rel_start;  // read offset of the base under tile coordinate 0
-          const int par = n0 & 1;
-          const int so = chunk0 * 16 + (int)sfirst_lo[j] - (n_lo[j] >> 1) + ((n0 - par) >> 1) + REC_BIAS;
-          const int qo = (chunk0 + ns[j]) * 16 + (int)qfirst_lo[j] - n_lo[j] + n0 + REC_BIAS;
-          st.rec[slot] = make_uint4((uint32_t)rel_start, (uint32_t)so | ((uint32_t)qo << 16),
-                                    (uint32_t)d[j].m_len | ((uint32_t)par << 16) | ((uint32_t)(d[j].dir_nm >> 7) << 17),
-                                    (uint32_t)d[j].mapq | ((uint32_t)(d[j].dir_nm & 0x7f) << 16));
-          s_copy[slot] = make_uint4(sc0[j], qc0[j], (uint32_t)(ns[j] | (nq[j] << 8)), (uint32_t)chunk0);
-          const int x_lo = rel_start > c_lo - p_lo ? rel_start : c_lo - p_lo;
-          const int x_hi = rel_start + (int)d[j].m_len - 1 < c_hi - p_lo ? rel_start + (int)d[j].m_len - 1 : c_hi - p_lo;
-          for (int w = x_lo >> 5; w <= (x_hi >> 5); ++w) {
-            atomicMin(&st.wlo[w], slot);
-            atomicMax(&st.whi[w], slot + 1);
-          }
-        }
-      }
-      n_fit = __reduce_add_sync(0xffffffffu, n_fit);
-      n_staged = __reduce_add_sync(0xffffffffu, n_staged);
-      __syncwarp();
-      // ---- asynchronous copies: one read per step, one 16-byte chunk per lane ----
-      for (int sidx = 0; sidx < n_staged; ++sidx) {
-        const uint4 c = s_copy[sidx];
-        const int cns = (int)(c.z & 0xff), cnq = (int)(c.z >> 8);
-        if (lane < cns + cnq) {
-          const size_t src = lane < cns ? (size_t)c.x + lane : (size_t)c.y + (lane - cns);
-          const unsigned dst = (unsigned)__cvta_generic_to_shared(&st.arena[c.w + lane]);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(pool16 + src) : "memory");
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      if (lane == 0) { st.n_slots = n_staged; st.done = 0; }
-      __syncwarp();
-      named_bar_arrive(BAR_FULL + (round & 1), WS_THREADS);
-      base += n_fit;
-    }
-    return;
-  }
-
-  // =========================== consumer warps: one lane per table position ===========================
-  const int x = tid;
-  const int p = p_lo + x;
-  const bool in_table = p - dr->first_pos < dr->n_pos;
-  const bool live = p >= c_lo && p <= c_hi;
-  int refnib = 0;  // the lane's reference allele, as a BAM nibble (0 = none: every observation takes the row path)
-  if (live && p >= dr->r.ref_lo && p <= dr->r.ref_hi && p >= a.ref_start && (int64_t)(p - a.ref_start) < a.ref_n) {
-    const char c = a.ref[p - a.ref_start];
-    refnib = c == 'A' ? 1 : c == 'C' ? 2 : c == 'G' ? 4 : c == 'T' ? 8 : 0;
-  }
-  const int thr = (int)ceil(a.goodq);  // integer q >= goodq
-  const int64_t t_row = dr->tab_off + (p - dr->first_pos);
-  uint32_t* const row0 = a.counts + (size_t)t_row * RV_POS_U32;
-  uint32_t n_ref = 0, n_rev = 0, sum_tp = 0, sum_q = 0, sum_mapq = 0, sum_nm = 0, n_hi = 0;
-  uint32_t v_and = 0xffffffffu, v_or = 0, v_last = 0, n_other = 0, other_mask = 0;
-  const int xs0 = (x >> 1) - REC_BIAS, xs1 = ((x + 1) >> 1) - REC_BIAS, xq = x - REC_BIAS;
-
-  for (int round = 0;; ++round) {
-    WsStage& st = s_stage[round & 1];
-    named_bar_sync(BAR_FULL + (round & 1), WS_THREADS);
-    if (st.done) break;
-    if (live) {
-      const uint8_t* arena = (const uint8_t*)st.arena;
-      const int w_lo = st.wlo[warp], w_hi = st.whi[warp];
-      uint32_t add_acc = 0;
-#pragma unroll 4
-      for (int slot = w_lo; slot < w_hi; ++slot) {
-        const uint4 r = st.rec[slot];
-        const int m_len = (int)(r.z & 0xffffu);
-        const int k = x - (int)r.x;
-        if ((unsigned)k >= (unsigned)m_len) continue;
-        const uint32_t q = arena[(int)(r.y >> 16) + xq];
-        const bool odd = (r.z >> 16) & 1;  // parity of the read offset under tile coordinate 0
-        const int sbyte = arena[(int)(r.y & 0xffffu) + (odd ? xs1 : xs0)];
-        const int nib = ((x ^ (int)odd) & 1) ? (sbyte & 15) : (sbyte >> 4);
-        const uint32_t tp = (uint32_t)min(k + 1, m_len - k);
-        const uint32_t v = tp | (q << 16);
-        const uint32_t hiq = (int)q >= thr ? 1u : 0u;
-        const uint32_t dir = (r.z >> 17) & 1u;
-        if (nib == refnib) {
-          n_ref++;
-          n_rev += dir;
-          sum_tp += tp;
-          sum_q += q;
-          add_acc += r.w;
-          n_hi += hiq;
-          v_and &= v;
-          v_or |= v;
-          v_last = v;
-        } else {
-          // a base that differs from the reference: the lane's own row of that allele, read-modify-write
-          const int al = nib_allele(nib);
-          uint4* row4 = (uint4*)(row0 + al * RV_ROW_U32);
-          uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
-          if (other_mask & (1u << al)) { ra = row4[0]; rb = row4[1]; }
-          ra.x += 1u - dir; ra.y += dir; ra.z += tp; ra.w += q;
-          rb.x += r.w & 0xffffu; rb.y += r.w >> 16; rb.z += hiq;
-          uint32_t w = rb.w;
-          if ((w >> 31) == 0) w = v | (1u << 31);
-          else {
-            if ((w ^ v) & 0xffffu) w |= 1u << 24;
-            if ((w ^ v) & 0xff0000u) w |= 1u << 25;
-          }
-          rb.w = w;
-          row4[0] = ra;
-          row4[1] = rb;
-          other_mask |= 1u << al;
-          n_other++;
-        }
-      }
-      sum_mapq += add_acc & 0xffffu;  // at most 128 reads per round: neither half can overflow
-      sum_nm += add_acc >> 16;
-    }
-    named_bar_arrive(BAR_EMPTY + (round & 1), WS_THREADS);
-  }
-  if (!in_table) return;
-  // ---- write the position: the reference allele from registers, untouched alleles as zeros ------------
-  a.cov[t_row] = n_ref + n_other;
-  const int a0 = refnib ? nib_allele(refnib) : -1;
-#pragma unroll
-  for (int al = 0; al < 4; ++al) {
-    if (other_mask & (1u << al)) continue;
-    uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
-    if (al == a0 && n_ref) {
-      ra = make_uint4(n_ref - n_rev, n_rev, sum_tp, sum_q);
-      uint32_t w = v_last | (1u << 31);
-      if ((v_and ^ v_or) & 0xffffu) w |= 1u << 24;
-      if ((v_and ^ v_or) & 0xff0000u) w |= 1u << 25;
-      rb = make_uint4(sum_mapq, sum_nm, n_hi, w);
-    }
-    uint4* row4 = (uint4*)(row0 + al * RV_ROW_U32);
-    row4[0] = ra;
-    row4[1] = rb;
-  }
 }
 
 struct ScoreArgs {
@@ -1676,7 +1310,7 @@ struct rv_ctx {
   cudaStream_t stream;
   cudaEvent_t ev0, ev1, tev0, tev1;
   cudaEvent_t evs[3];      // boundaries between the kernels of the pileup stage
-  float split_ms[4];       // classify, tile index + gather, walk, (unused)
+  float split_ms[4];       // classify, tile index + gather, walk, apply
   std::string err;
   int64_t launches;
   // device buffers
@@ -1708,10 +1342,15 @@ struct rv_ctx {
   unsigned long long* d_walk_queue;
   unsigned long long* d_walk_count;
   int64_t n_tiles;
-  bool use_gather;
-  bool gather_ws;   // RV_GATHER_WS=1 selects the warp-specialised gather kernel (experimental)
-  bool gather4;     // rv_gather4_kernel (default; RV_GATHER_LEGACY=1 or goodq outside [0, 128] selects rv_gather_kernel)
+  bool use_gather;  // false (RV_NO_GATHER=1, a debugging reference): no descriptors, every base through the SparseObs list
   int tile;         // table positions per gather tile
+  int g4_run, g4_alt, g4_variant, walk_occ;  // launch shapes (environment overrides are read once, at rv_create)
+  GDesc* d_descs2;
+  uint16_t* d_desc_mm2;
+  uint4* d_desc_mml2;
+  SparseObs* d_sparse;
+  unsigned long long* d_sparse_count;
+  int64_t max_sparse;
   int n_sms;        // SMs of the device (persistent grids)
   uint4* d_desc_mml;
   int64_t pool_dev_bytes;
@@ -1775,6 +1414,16 @@ int rv_device_count(void) {
   return n;
 }
 
+int rv_warmup(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return RV_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess) return RV_ERR_CUDA;
+  // loads the module (the sm_100a image of every kernel) as well
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, rv_pack_ref_kernel) != cudaSuccess) { cudaGetLastError(); return RV_ERR_CUDA; }
+  return RV_OK;
+}
+
 void rv_default_params(rv_params* p) {
   memset(p, 0, sizeof(*p));
   p->goodq = 22.5;
@@ -1826,13 +1475,14 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   ctx->d_events = NULL; ctx->d_variants = NULL; ctx->d_patch = NULL; ctx->d_patch_first = NULL;
   ctx->d_patch_count = NULL; ctx->d_regions = NULL; ctx->d_max_rl = NULL; ctx->d_stats = NULL; ctx->d_lgt = NULL; ctx->d_descs = NULL; ctx->d_desc_mm = NULL; ctx->d_reach = NULL; ctx->d_ref4 = NULL; ctx->d_tile_range = NULL; ctx->tile_cap = 0; ctx->d_patched_queue = NULL; ctx->d_patched_count = NULL; ctx->d_walk_queue = NULL; ctx->d_walk_count = NULL; ctx->n_tiles = 0;
   ctx->use_gather = getenv("RV_NO_GATHER") == NULL;
-  ctx->gather_ws = getenv("RV_GATHER_WS") && atoi(getenv("RV_GATHER_WS")) == 1;
-  {
-    const int thr = (int)ceil(params->goodq);
-    ctx->gather4 = !ctx->gather_ws && !(getenv("RV_GATHER_LEGACY") && atoi(getenv("RV_GATHER_LEGACY")) == 1) && thr >= 1 &&
-                   thr <= 128 && limits->max_read_bytes < ((int64_t)1 << 32);
-    ctx->tile = ctx->gather4 ? G4_W : GATHER_TILE;
-  }
+  ctx->tile = G4_W;
+  ctx->g4_run = getenv("RV_G4_RUN") ? std::max(1, atoi(getenv("RV_G4_RUN"))) : 1;
+  ctx->g4_alt = getenv("RV_G4_ALT") ? atoi(getenv("RV_G4_ALT")) : 1;
+  ctx->g4_variant = getenv("RV_G4_VARIANT") ? atoi(getenv("RV_G4_VARIANT")) : 0;
+  ctx->walk_occ = getenv("RV_WALK_OCC") ? atoi(getenv("RV_WALK_OCC")) : 4;
+  ctx->d_descs2 = NULL; ctx->d_desc_mm2 = NULL; ctx->d_desc_mml2 = NULL; ctx->d_sparse = NULL; ctx->d_sparse_count = NULL;
+  ctx->max_sparse = 0;
+
   ctx->d_desc_mml = NULL;
   ctx->pool_dev_bytes = 0;
   ctx->h_counts = NULL; ctx->h_cov = NULL; ctx->h_tab_cap = 0; ctx->h_events = NULL; ctx->h_events_cap = 0;
@@ -1842,6 +1492,13 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   ctx->evs[0] = ctx->evs[1] = ctx->evs[2] = NULL; ctx->split_ms[0] = ctx->split_ms[1] = ctx->split_ms[2] = ctx->split_ms[3] = 0;
   ctx->reads_dev_view = NULL; ctx->pool_dev_view = NULL;
   *out = ctx;  // returned even on failure so the caller can read rv_last_error, then rv_destroy
+  {
+    // the byte-SIMD quality threshold of rv_gather4_kernel and its 32-bit pool offsets
+    const int thr = (int)ceil(params->goodq);
+    if (!(thr >= 1 && thr <= 128)) return fail(ctx, RV_ERR_ARG, "phred threshold (-q) outside (0, 128] is not supported");
+    if (limits->max_read_bytes >= ((int64_t)1 << 32) - 64) return fail(ctx, RV_ERR_ARG, "limits.max_read_bytes must stay below 4 GiB per context");
+    if (limits->max_positions >= ((int64_t)1 << 32) - 2) return fail(ctx, RV_ERR_ARG, "limits.max_positions must stay below 2^32 per context");
+  }
   CK(cudaSetDevice(device));
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->n_sms = 148;
@@ -1864,12 +1521,26 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   CK(cudaMalloc(&ctx->d_patch_count, (size_t)(L.max_positions + 1)));
   CK(cudaMalloc(&ctx->d_regions, sizeof(DevRegion) * (size_t)L.max_regions));
   CK(cudaMalloc(&ctx->d_max_rl, sizeof(int32_t) * (size_t)L.max_regions));
-  CK(cudaMalloc(&ctx->d_stats, sizeof(DevStats)));
+  {
+    // one block: statistics | walk queue counters [3] | SparseObs cursor | reach bounds [2] (a single memset per pileup)
+    uint8_t* blk = NULL;
+    CK(cudaMalloc(&blk, COUNTER_BLOCK_BYTES));
+    ctx->d_stats = (DevStats*)blk;
+    ctx->d_walk_count = (unsigned long long*)(blk + 128);
+    ctx->d_sparse_count = (unsigned long long*)(blk + 128 + 24);
+    ctx->d_reach = (int32_t*)(blk + 128 + 32);
+  }
   // work items are (region, read) pairs: a read overlapping two tiles is walked once per tile
   CK(cudaMalloc(&ctx->d_descs, sizeof(GDesc) * (size_t)(2 * L.max_reads + 1024)));
   CK(cudaMalloc(&ctx->d_desc_mm, sizeof(uint16_t) * (size_t)(2 * L.max_reads + 1024)));
   CK(cudaMalloc(&ctx->d_desc_mml, sizeof(uint4) * (size_t)(2 * L.max_reads + 1024)));
-  CK(cudaMalloc(&ctx->d_reach, 2 * sizeof(int32_t)));
+  CK(cudaMalloc(&ctx->d_descs2, sizeof(GDesc) * (size_t)(2 * L.max_reads + 1024)));
+  CK(cudaMalloc(&ctx->d_desc_mm2, sizeof(uint16_t) * (size_t)(2 * L.max_reads + 1024)));
+  CK(cudaMalloc(&ctx->d_desc_mml2, sizeof(uint4) * (size_t)(2 * L.max_reads + 1024)));
+  // SparseObs list: a walked read leaves a few entries (soft-clip re-extension, coverage under a deletion), a stretch
+  // that is not plain one per base; RV_NO_GATHER sends every base here (small debugging batches only)
+  ctx->max_sparse = std::max<int64_t>(4 << 20, 8 * L.max_reads);
+  CK(cudaMalloc(&ctx->d_sparse, sizeof(SparseObs) * (size_t)ctx->max_sparse));
   CK(cudaMalloc(&ctx->d_ref4, sizeof(uint32_t) * (size_t)(L.max_ref_bases / 8 + 16)));
   // gather tiles: every region rounds its table (length + 2*halo) up to whole tiles
   ctx->tile_cap = L.max_positions / ctx->tile + L.max_regions + 1;
@@ -1878,7 +1549,6 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   CK(cudaMalloc(&ctx->d_patched_queue, sizeof(int64_t) * (size_t)(L.max_positions + 1)));
   CK(cudaMalloc(&ctx->d_patched_count, sizeof(unsigned long long)));
   CK(cudaMalloc(&ctx->d_walk_queue, sizeof(unsigned long long) * (size_t)(2 * L.max_reads + 1024)));
-  CK(cudaMalloc(&ctx->d_walk_count, 3 * sizeof(unsigned long long)));  // whole-read walks, soft-clip walks, walk cursor
   CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->stream));
   ctx->lgt_n = 1 << 20;
   CK(cudaMalloc(&ctx->d_lgt, sizeof(double) * (size_t)ctx->lgt_n));
@@ -1901,13 +1571,15 @@ void rv_destroy(rv_ctx* ctx) {
   cudaFree(ctx->d_descs);
   cudaFree(ctx->d_desc_mm);
   cudaFree(ctx->d_desc_mml);
-  cudaFree(ctx->d_reach);
+  cudaFree(ctx->d_descs2);
+  cudaFree(ctx->d_desc_mm2);
+  cudaFree(ctx->d_desc_mml2);
+  cudaFree(ctx->d_sparse);
   cudaFree(ctx->d_ref4);
   cudaFree(ctx->d_tile_range);
   cudaFree(ctx->d_patched_queue);
   cudaFree(ctx->d_patched_count);
   cudaFree(ctx->d_walk_queue);
-  cudaFree(ctx->d_walk_count);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
   if (ctx->h_cov) cudaFreeHost(ctx->h_cov);
   if (ctx->h_events) cudaFreeHost(ctx->h_events);
@@ -1927,8 +1599,8 @@ int32_t rv_ctx_halo(const rv_ctx* ctx) { return ctx ? ctx->L.halo : 0; }
 
 int rv_set_params(rv_ctx* ctx, const rv_params* params) {
   if (!ctx || !params) return RV_ERR_ARG;
-  if (ctx->gather4 && !(ceil(params->goodq) >= 1 && ceil(params->goodq) <= 128))
-    return fail(ctx, RV_ERR_ARG, "goodq outside (0, 128]: create the context with these parameters instead");
+  if (!(ceil(params->goodq) >= 1 && ceil(params->goodq) <= 128))
+    return fail(ctx, RV_ERR_ARG, "phred threshold (-q) outside (0, 128] is not supported");
   ctx->P = *params;
   return RV_OK;
 }
@@ -2073,10 +1745,9 @@ int rv_pileup(rv_ctx* ctx) {
   if (!ctx->reads_dev_view) return fail(ctx, RV_ERR_STATE, "rv_push_reads has not been called");
   CK(cudaSetDevice(ctx->device));
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  // no table memset: rv_gather_kernel stores every row (halo included) before rv_walk_kernel adds to them
-  CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->stream));
-  CK(cudaMemsetAsync(ctx->d_walk_count, 0, 3 * sizeof(unsigned long long), ctx->stream));
-  CK(cudaMemsetAsync(ctx->d_reach, 0, 2 * sizeof(int32_t), ctx->stream));
+  // no table memset: rv_gather4_kernel stores every row (halo included) before rv_apply_kernel adds to them.
+  // One memset clears the statistics, the walk queue counters, the SparseObs cursor and the reach bounds.
+  CK(cudaMemsetAsync(ctx->d_stats, 0, COUNTER_BLOCK_BYTES, ctx->stream));
   PileupArgs a;
   a.P = ctx->P;
   a.regions = ctx->d_regions;
@@ -2097,11 +1768,18 @@ int rv_pileup(rv_ctx* ctx) {
   a.descs = ctx->d_descs;
   a.desc_mm = ctx->d_desc_mm;
   a.desc_mml = ctx->d_desc_mml;
+  a.descs2 = ctx->d_descs2;
+  a.desc_mm2 = ctx->d_desc_mm2;
+  a.desc_mml2 = ctx->d_desc_mml2;
+  a.sparse = ctx->d_sparse;
+  a.max_sparse = (unsigned long long)ctx->max_sparse;
+  a.sparse_count = ctx->d_sparse_count;
   a.reach = ctx->d_reach;
   a.force_exact = ctx->use_gather ? 0 : 1;
   a.walk_queue = ctx->d_walk_queue;
   a.walk_count = ctx->d_walk_count;
   a.walk_cap = (unsigned long long)(2 * ctx->L.max_reads + 1024);
+  // 1. classify: filters, CIGAR rewrite, plain-run proof -> descriptors of the plain reads, queue of the others
   if (ctx->n_items > 0) {
     unsigned grid = (unsigned)((ctx->n_items + 127) / 128);
     rv_pileup_kernel<<<grid, 128, 0, ctx->stream>>>(a);
@@ -2109,6 +1787,19 @@ int rv_pileup(rv_ctx* ctx) {
     CK(cudaGetLastError());
   }
   CK(cudaEventRecord(ctx->evs[0], ctx->stream));
+  // 2. the queued reads: CIGAR walk -> descriptors of their plain segments, SparseObs list, events
+  if (ctx->n_items > 0) {
+    // the queue length is only known on the device: a fixed grid of grid-stride threads
+    const int occ = ctx->walk_occ;
+    if (occ == 8) rv_walk_kernel<8><<<ctx->n_sms * 8, 128, 0, ctx->stream>>>(a);
+    else if (occ == 6) rv_walk_kernel<6><<<ctx->n_sms * 6, 128, 0, ctx->stream>>>(a);
+    else if (occ == 5) rv_walk_kernel<5><<<ctx->n_sms * 5, 128, 0, ctx->stream>>>(a);
+    else rv_walk_kernel<4><<<ctx->n_sms * 4, 128, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(ctx->evs[1], ctx->stream));
+  // 3. position-major accumulation of every descriptor; stores every table row
   if (ctx->n_tiles > 0) {
     GatherArgs g;
     g.goodq = ctx->P.goodq;
@@ -2128,34 +1819,29 @@ int rv_pileup(rv_ctx* ctx) {
     g.n_tiles = ctx->n_tiles;
     g.tile = ctx->tile;
     g.desc_mml = ctx->d_desc_mml;
+    g.descs2 = ctx->d_descs2;
+    g.desc_mm2 = ctx->d_desc_mm2;
+    g.desc_mml2 = ctx->d_desc_mml2;
     g.pool_bytes = ctx->pool_dev_bytes;
     g.thr = (int)ceil(ctx->P.goodq);
     rv_tile_index_kernel<<<(unsigned)((ctx->n_tiles + 127) / 128), 128, 0, ctx->stream>>>(g);
-    if (ctx->gather4) {
-      g.run = getenv("RV_G4_RUN") ? atoi(getenv("RV_G4_RUN")) : 1;
-      if (g.run < 1) g.run = 1;
-      g.alternate = getenv("RV_G4_ALT") ? atoi(getenv("RV_G4_ALT")) : 1;
-      const int64_t g4_warps = (ctx->n_tiles + g.run - 1) / g.run;
-      const unsigned g4_grid = (unsigned)((g4_warps + G4_WARPS - 1) / G4_WARPS);
-      const int variant = getenv("RV_G4_VARIANT") ? atoi(getenv("RV_G4_VARIANT")) : 0;
-      if (variant == 1) rv_gather4_kernel<8, 6><<<g4_grid, G4_WARPS * 32, 0, ctx->stream>>>(g);
-      else if (variant == 2) rv_gather4_kernel<8, 5><<<g4_grid, G4_WARPS * 32, 0, ctx->stream>>>(g);
-      else if (variant == 3) rv_gather4_kernel<4, 6><<<g4_grid, G4_WARPS * 32, 0, ctx->stream>>>(g);
-      else rv_gather4_kernel<4, 8><<<g4_grid, G4_WARPS * 32, 0, ctx->stream>>>(g);
-    }
-    else if (ctx->gather_ws) rv_gather_ws_kernel<<<(unsigned)ctx->n_tiles, WS_THREADS, 0, ctx->stream>>>(g);
-    else rv_gather_kernel<<<(unsigned)ctx->n_tiles, GATHER_TILE, 0, ctx->stream>>>(g);
+    g.run = ctx->g4_run;
+    g.alternate = ctx->g4_alt;
+    const int64_t g4_warps = (ctx->n_tiles + g.run - 1) / g.run;
+    const unsigned g4_grid = (unsigned)((g4_warps + G4_WARPS - 1) / G4_WARPS);
+    const int variant = ctx->g4_variant;
+    if (variant == 1) rv_gather4_kernel<8, 6><<<g4_grid, G4_WARPS * 32, 0, ctx->stream>>>(g);
+    else if (variant == 2) rv_gather4_kernel<8, 5><<<g4_grid, G4_WARPS * 32, 0, ctx->stream>>>(g);
+    else if (variant == 3) rv_gather4_kernel<4, 6><<<g4_grid, G4_WARPS * 32, 0, ctx->stream>>>(g);
+    else rv_gather4_kernel<4, 8><<<g4_grid, G4_WARPS * 32, 0, ctx->stream>>>(g);
     ctx->launches += 2;
     CK(cudaGetLastError());
   }
-  CK(cudaEventRecord(ctx->evs[1], ctx->stream));
+  CK(cudaEventRecord(ctx->evs[2], ctx->stream));
+  // 4. the SparseObs list onto the tables
   if (ctx->n_items > 0) {
-    // the queue length is only known on the device: a fixed grid of grid-stride threads
-    const int occ = getenv("RV_WALK_OCC") ? atoi(getenv("RV_WALK_OCC")) : 4;
-    if (occ == 8) rv_walk_kernel<8><<<ctx->n_sms * 8, 128, 0, ctx->stream>>>(a);
-    else if (occ == 6) rv_walk_kernel<6><<<ctx->n_sms * 6, 128, 0, ctx->stream>>>(a);
-    else if (occ == 5) rv_walk_kernel<5><<<ctx->n_sms * 5, 128, 0, ctx->stream>>>(a);
-    else rv_walk_kernel<4><<<ctx->n_sms * 4, 128, 0, ctx->stream>>>(a);
+    rv_apply_kernel<<<ctx->n_sms * 8, 256, 0, ctx->stream>>>(ctx->d_sparse, ctx->d_sparse_count, (unsigned long long)ctx->max_sparse,
+                                                           ctx->d_counts, ctx->d_cov, (int)ceil(ctx->P.goodq));
     ctx->launches++;
     CK(cudaGetLastError());
   }
@@ -2165,13 +1851,15 @@ int rv_pileup(rv_ctx* ctx) {
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaEventElapsedTime(&ctx->pileup_ms, ctx->ev0, ctx->ev1));
   CK(cudaEventElapsedTime(&ctx->split_ms[0], ctx->ev0, ctx->evs[0]));
-  CK(cudaEventElapsedTime(&ctx->split_ms[1], ctx->evs[0], ctx->evs[1]));
-  CK(cudaEventElapsedTime(&ctx->split_ms[2], ctx->evs[1], ctx->ev1));
+  CK(cudaEventElapsedTime(&ctx->split_ms[2], ctx->evs[0], ctx->evs[1]));
+  CK(cudaEventElapsedTime(&ctx->split_ms[1], ctx->evs[1], ctx->evs[2]));
+  CK(cudaEventElapsedTime(&ctx->split_ms[3], ctx->evs[2], ctx->ev1));
   ctx->h_stats.n_items = (unsigned long long)ctx->n_items;
   // the patch list stays attached until rv_set_regions / the next rv_apply_patch: a caller that
   // re-runs the same resident batch may score against it again
   ctx->tables_fetched = false;
-  if (ctx->h_stats.n_overflow) return fail(ctx, RV_ERR_OVERFLOW, "pileup dropped events (limits.max_events too small)");
+  if (ctx->h_stats.n_overflow)
+    return fail(ctx, RV_ERR_OVERFLOW, "pileup dropped events or sparse observations (limits.max_events / limits.max_reads too small)");
   return RV_OK;
 }
 
@@ -2528,7 +2216,13 @@ int rv_last_pileup_split_ms(rv_ctx* ctx, float* classify_ms, float* gather_ms, f
   if (!ctx) return RV_ERR_ARG;
   if (classify_ms) *classify_ms = ctx->split_ms[0];
   if (gather_ms) *gather_ms = ctx->split_ms[1];
-  if (walk_ms) *walk_ms = ctx->split_ms[2];
+  if (walk_ms) *walk_ms = ctx->split_ms[2] + ctx->split_ms[3];  // rv_walk_kernel + rv_apply_kernel
+  return RV_OK;
+}
+
+int rv_last_pileup_stage_ms(rv_ctx* ctx, float out[4]) {
+  if (!ctx || !out) return RV_ERR_ARG;
+  for (int k = 0; k < 4; ++k) out[k] = ctx->split_ms[k];
   return RV_OK;
 }
 

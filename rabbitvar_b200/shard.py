@@ -55,3 +55,44 @@ def concat_in_order(parts, dist=None):
     out = [None] * dist.get_world_size()
     dist.all_gather_object(out, "".join(parts))
     return "".join(out)
+
+
+def bai_tile_weights(bai_path, tid, tiles):
+    """Expected work of every tile = compressed BAM bytes between the linear-index entries of its first and last
+    16 kb window (BAI linear index, SAM spec 5.2) — the 'balanced by expected reads' weight of SURVEY 8(e).
+    tiles: [(start1, end1)] 1-based inclusive.  Falls back to the tile lengths when the index has no entry."""
+    import struct
+    with open(bai_path, "rb") as f:
+        data = f.read()
+    if data[:4] != b"BAI\x01":
+        raise ValueError("not a BAI file: " + bai_path)
+    off = 4
+    (n_ref,) = struct.unpack_from("<i", data, off)
+    off += 4
+    ioffset = []
+    for r in range(n_ref):
+        (n_bin,) = struct.unpack_from("<i", data, off)
+        off += 4
+        for _ in range(n_bin):
+            _, n_chunk = struct.unpack_from("<Ii", data, off)
+            off += 8 + 16 * n_chunk
+        (n_intv,) = struct.unpack_from("<i", data, off)
+        off += 4
+        if r == tid:
+            ioffset = list(struct.unpack_from("<%dQ" % n_intv, data, off))
+        off += 8 * n_intv
+    if not ioffset:
+        return [float(e - s + 1) for s, e in tiles]
+    for i in range(1, len(ioffset)):  # empty windows inherit the previous offset
+        if ioffset[i] == 0:
+            ioffset[i] = ioffset[i - 1]
+
+    def coff(pos0):
+        w = min(max(pos0, 0) >> 14, len(ioffset) - 1)
+        return ioffset[w] >> 16
+
+    out = []
+    for s, e in tiles:
+        w = float(coff(e + (1 << 14)) - coff(s - 1))
+        out.append(w if w > 0 else float(e - s + 1) * 1e-3)
+    return out

@@ -29,10 +29,11 @@ def test_cuda_path_matches_golden(built, name, tmp_path):
     assert not problems, problems[:5]
 
 
-@pytest.mark.parametrize("env", [{"RV_GATHER_WS": "1"}, {"RV_NO_GATHER": "1"}])
+@pytest.mark.parametrize("env", [{"RV_G4_VARIANT": "3"}, {"RV_G4_VARIANT": "1", "RV_G4_RUN": "2"}, {"RV_NO_GATHER": "1"}])
 def test_alternative_kernel_paths_match_golden(built, env, tmp_path):
-    """The opt-in kernel variants must stay exact too: the warp-specialised gather kernel (RV_GATHER_WS=1) and the
-    all-reads-through-the-exact-walk path (RV_NO_GATHER=1, the debugging reference for the gather path)."""
+    """The opt-in kernel variants must stay exact too: other launch shapes of the gather kernel and the path that sends
+    every base through the literal walk and the sparse-observation list (RV_NO_GATHER=1, the debugging reference for
+    the descriptor / gather path)."""
     name = "c5_k1"
     c = cases.CASES[name]
     cases.generate(name)

@@ -65,6 +65,30 @@ struct SimSink {
     R->cov[pos - R->first_pos]++;
   }
   void event(const rv_event& e) { events->push_back(e); }
+  // a plain matched stretch (rvk::scan_plain_segment): expanded here the way the gather kernel accumulates it — one
+  // single-base observation per base that lies inside the region, the allele being the read base itself
+  const rv_read* cur_read;
+  const uint8_t* cur_pool;
+  int r_start, r_end;
+  bool use_segments;
+  bool segment(const rvk::SegDesc& d, bool dir, int mapq, int nm) {
+    if (!use_segments) return false;
+    const uint8_t* var = cur_pool + (size_t)cur_read->data_off16 * 16;
+    const uint8_t* seq4 = var + 4 * (size_t)cur_read->n_cigar;
+    const uint8_t* qual = seq4 + ((cur_read->l_seq + 1) >> 1);
+    for (int k = 0; k < d.len; ++k) {
+      const int p = d.m_start + k;
+      if (p < r_start || p > r_end) continue;
+      const int r = d.rp + k;
+      const int b = seq4[r >> 1];
+      const int nib = (r & 1) ? (b & 15) : (b >> 4);
+      const int al = nib == 1 ? 0 : nib == 2 ? 1 : nib == 4 ? 2 : nib == 8 ? 3 : -1;
+      const int up = d.re + k + 1, dn = d.rlen - d.re - k;
+      single(p, al, dir, up < dn ? up : dn, qual[r], mapq, nm);
+      cov(p);
+    }
+    return true;
+  }
   void max_read_len(int t) { if (t > R->max_read_len) R->max_read_len = t; }
   void kept(int aligned) { kept_reads++; kept_bases += aligned; }
   void unsupported() { unsup++; }
@@ -227,6 +251,10 @@ int main(int argc, char** argv) {
       s.R = &R; s.events = &events; s.goodq = P.goodq;
       s.kept_reads = s.kept_bases = s.unsup = s.over = 0;
       const bool use_fast = getenv("RV_NO_GATHER") == NULL;
+      s.use_segments = use_fast && getenv("RV_NO_SEGMENTS") == NULL;
+      s.cur_pool = batch.pool.data();
+      s.r_start = regs[r].start;
+      s.r_end = regs[r].end;
       std::vector<rvk::FastDesc> descs;
       for (int64_t i = regs[r].read_lo; i < regs[r].read_hi; ++i) {
         const rv_read& rd = batch.reads[(size_t)i];
@@ -235,6 +263,7 @@ int main(int argc, char** argv) {
         if (P.dedup && rvk::is_duplicate_read(P, regs[r], batch.reads.data(), batch.pool.data(), i)) continue;
         rvk::FastDesc d;
         memset(&d, 0, sizeof d);
+        s.cur_read = &rd;
         rvk::process_read(P, regs[r], (int)r, rd, batch.pool.data(), ref, (uint32_t)i, s, use_fast ? &d : (rvk::FastDesc*)0);
         if (d.m_len) descs.push_back(d);
       }
