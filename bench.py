@@ -384,7 +384,7 @@ def main():
     m = re.search(r"launches (\d+)", cli_info)
     cli_launches = int(m.group(1)) if m else 0
     if cli_info:
-        log(f"[bench r{rank}] e2e CLI: {e2e_sec:.3f} s per run; " + cli_info.strip().splitlines()[-2][:400])
+        log(f"[bench r{rank}] e2e CLI: {e2e_sec:.3f} s per run; " + " | ".join(cli_info.strip().splitlines()[-3:])[:900])
 
     # ---- reductions over ranks (max time, sum of work) ---------------------------------------------------------------
     dd = dist if world > 1 else None

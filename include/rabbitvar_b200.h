@@ -82,6 +82,8 @@ typedef struct rv_limits {
   int64_t max_variants;     /* scored variant records per batch */
   int64_t max_patch;        /* patch entries per batch */
   int64_t max_ref_bases;    /* reference bases resident */
+  int64_t max_sparse_obs;   /* observations of the walked reads that do not travel as gather descriptors (soft-clip
+                               re-extension, stretches that are not plain, every base under -T): 0 = 8 x max_reads */
 } rv_limits;
 
 void rv_default_limits(rv_limits* l);

@@ -55,7 +55,8 @@ class Params(C.Structure):
 class Limits(C.Structure):
     _fields_ = [("max_reads", C.c_int64), ("max_read_bytes", C.c_int64), ("max_positions", C.c_int64),
                 ("max_regions", C.c_int32), ("halo", C.c_int32), ("max_events", C.c_int64),
-                ("max_variants", C.c_int64), ("max_patch", C.c_int64), ("max_ref_bases", C.c_int64)]
+                ("max_variants", C.c_int64), ("max_patch", C.c_int64), ("max_ref_bases", C.c_int64),
+                ("max_sparse_obs", C.c_int64)]
 
 
 class Read(C.Structure):

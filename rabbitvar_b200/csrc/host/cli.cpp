@@ -223,19 +223,15 @@ int main(int argc, char** argv) {
     fprintf(stderr, "no regions (give -R or -i)\n");
     return 1;
   }
-  if (cuda_init.joinable()) cuda_init.join();
-  int ndev = rv_device_count();
-  if (ndev <= 0 && !c.decode_only) {
-    fprintf(stderr, "rabbitvar_b200: no CUDA device visible; this build has no CPU path\n");
-    return 3;
-  }
+  const double t_parsed = now_ms();
+  // (the decode threads start right away; the GPU workers wait for the CUDA start-up inside rv_create)
   FileRunConfig fc;
   fc.fasta = c.fasta; fc.bam = c.bam; fc.bam2 = c.bam2; fc.sample = c.sample;
   fc.P = c.P;
   fc.ref_ext = c.ref_ext; fc.nucl_ext = c.nucl_ext;
   fc.decode_threads = c.threads;                 // --th, default 1 like the reference (Launcher.cpp:474)
   fc.first_device = c.device;
-  fc.gpus = c.decode_only ? 1 : std::max(1, std::min(c.gpus, ndev - c.device));
+  fc.gpus = std::max(1, c.gpus);
   fc.decode_only = c.decode_only;
   fc.workers_per_gpu = c.workers;
   fc.max_regions_per_job = c.batch_regions;
@@ -245,6 +241,12 @@ int main(int argc, char** argv) {
   FileRunStats st;
   std::vector<std::string> errors;
   int rc = run_files(fc, specs, &tsv, &st, &errors);
+  const double t_ran = now_ms();
+  if (cuda_init.joinable()) cuda_init.join();
+  if (!c.decode_only && rv_device_count() <= 0) {
+    fprintf(stderr, "rabbitvar_b200: no CUDA device visible; this build has no CPU path\n");
+    return 3;
+  }
   for (size_t i = 0; i < errors.size(); ++i) fprintf(stderr, "[error] %s\n", errors[i].c_str());
   if (rc == 1) return 1;
   FILE* out = fopen(c.out.c_str(), "wb");
@@ -270,7 +272,8 @@ int main(int argc, char** argv) {
          c.out.c_str(), specs.size(), (long long)st.n_jobs, fc.gpus, fc.workers_per_gpu, fc.decode_threads, (long long)st.bases, (long long)st.lines,
          st.pileup_kernel_ms + st.score_kernel_ms, st.decode_thread_ms, st.gpu_worker_ms, (long long)st.launches,
          (long long)st.h2d_bytes, (long long)st.d2h_bytes);
-  printf("[info] cuda start-up %.0f ms (overlapped with input parsing)\n", cuda_init_ms);
+  printf("[info] timeline ms: inputs parsed %.0f, cuda start-up %.0f (beside the decode threads), pipeline done %.0f, output written %.0f\n",
+         t_parsed - t0, cuda_init_ms, t_ran - t0, now_ms() - t0);
   printf("total time: %f s \n", (now_ms() - t0) / 1000.0);
   return rc;
 }

@@ -174,7 +174,8 @@ inline bool limits_fit(const rv_limits& have, const rv_limits& need) {
   return have.max_reads >= need.max_reads && have.max_read_bytes >= need.max_read_bytes &&
          have.max_positions >= need.max_positions && have.max_regions >= need.max_regions &&
          have.max_events >= need.max_events && have.max_variants >= need.max_variants &&
-         have.max_patch >= need.max_patch && have.max_ref_bases >= need.max_ref_bases && have.halo == need.halo;
+         have.max_patch >= need.max_patch && have.max_ref_bases >= need.max_ref_bases && have.halo == need.halo &&
+         have.max_sparse_obs >= need.max_sparse_obs;
 }
 
 // Runs every region of `specs` (input order is output order).  Returns 0, or 2 when a job failed (its regions print
@@ -245,7 +246,9 @@ inline int run_files(const FileRunConfig& c, const std::vector<RegionSpec>& spec
   for (int w = 0; w < n_gpu_workers; ++w)
     threads.emplace_back([&, w]() {
       host_threads_override() = host_thr;
-      const int device = c.first_device + w % std::max(1, c.gpus);
+      int n_dev = rv_device_count();  // (waits for the CUDA start-up the caller began)
+      if (n_dev <= 0) n_dev = 1;
+      const int device = (c.first_device + w % std::max(1, c.gpus)) % n_dev;
       rv_ctx* ctx = NULL;
       rv_limits have;
       rv_default_limits(&have);
@@ -296,6 +299,7 @@ inline int run_files(const FileRunConfig& c, const std::vector<RegionSpec>& spec
               if (rc == RV_OK) { job.err.clear(); break; }
               if (rc != RV_ERR_OVERFLOW) break;
               need.max_events *= 4; need.max_variants *= 2; need.max_patch *= 4;
+              need.max_sparse_obs = std::max<int64_t>(4 << 20, 8 * need.max_reads) << (4 * (attempt + 1));
             }
           } catch (const std::exception& e) {
             job.err = e.what();

@@ -45,7 +45,8 @@ static bool limits_cover(const rv_limits& have, const rv_limits& need) {
   return have.max_reads >= need.max_reads && have.max_read_bytes >= need.max_read_bytes &&
          have.max_positions >= need.max_positions && have.max_regions >= need.max_regions &&
          have.max_events >= need.max_events && have.max_variants >= need.max_variants &&
-         have.max_patch >= need.max_patch && have.max_ref_bases >= need.max_ref_bases && have.halo == need.halo;
+         have.max_patch >= need.max_patch && have.max_ref_bases >= need.max_ref_bases && have.halo == need.halo &&
+         have.max_sparse_obs >= need.max_sparse_obs;
 }
 
 extern "C" {

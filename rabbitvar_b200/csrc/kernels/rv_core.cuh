@@ -24,6 +24,13 @@
 #define RV_KEEP_REG(x) ((void)0)
 #endif
 
+// "any lane of the warp" on the device (every lane of the warp must be there), the value itself on the host
+#if defined(__CUDA_ARCH__)
+#define RV_WARP_ANY(x) (__syncwarp(), __any_sync(0xffffffffu, (x)))
+#else
+#define RV_WARP_ANY(x) (x)
+#endif
+
 namespace rvk {
 
 enum { OP_M = 0, OP_I = 1, OP_D = 2, OP_N = 3, OP_S = 4, OP_H = 5, OP_P = 6, OP_EQ = 7, OP_X = 8, OP_B = 9 };
@@ -655,8 +662,10 @@ RV_HD bool fast_obs(const FastDesc& d, int p, const uint8_t* pool, int* allele, 
 //   void event(const rv_event&)
 //   void max_read_len(int tlen)
 //   void kept(int aligned_bases) ; void unsupported()
-//   bool segment(const SegDesc&, bool dir, int mapq, int nm)   a plain matched stretch (see scan_plain_segment); a sink
-//                                                              that returns false gets the per-base observations
+//   bool scan_segment(P, rd, ref, m_start, rp, len, indel_follows, SegDesc*)   is the stretch plain? (scan_plain_segment,
+//                                                              or a faster equivalent; false = take the per-base walk)
+//   bool segment(const SegDesc&, bool dir, int mapq, int nm)   a plain matched stretch; a sink that returns false gets
+//                                                              the per-base observations
 // ------------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------------
 // Plain segments.  A matched stretch of a read (one M/=/X op, from the bases an indel before it already consumed to
@@ -952,9 +961,11 @@ RV_HDN void prepare_read(const rv_params& P, const rv_region& R, const rv_read& 
 
 // plain_hint: 1 = the matched run was already proven plain (warp-cooperative scan in the kernel),
 // 0 = proven not plain, -1 = decide here with the scalar scan.
+// has_work: on the device ALL lanes of a warp call walk_read together; a lane without a read passes false.
 template <class Sink>
 RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, const rv_read& rdh, const uint8_t* pool,
-                      const RefView& ref, uint32_t read_idx, Sink& sink, Prep& pr, FastDesc* fast, int plain_hint) {
+                      const RefView& ref, uint32_t read_idx, Sink& sink, Prep& pr, FastDesc* fast, int plain_hint,
+                      bool has_work = true) {
   Cigar& cg = pr.cg;
   const uint8_t* var = pool + (size_t)rdh.data_off16 * 16;
   ReadView rd;
@@ -978,7 +989,11 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
   const bool paired_same = (rdh.flag & 1) && rdh.mate_same_tid;
 
   bool need_break = true;
-  for (int ci = 0; ci < n_cigar; ++ci) {
+  int ci = 0;
+  // One CIGAR op per round.  On the device the rounds are warp-synchronous: the 32 lanes (32 reads) enter every round
+  // together, so lanes whose op is of the same kind run its loops side by side instead of one after the other
+  // (independent thread scheduling never brings lanes back together inside a loop they entered at different times).
+  auto op_step = [&]() -> bool {  // true = the read is finished
     // :630-634 / skipOverlappingReads :182-206 — only evaluated before the first op
     if (need_break) {
       bool skip = false;
@@ -992,7 +1007,7 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
         else ov = w.start >= mate_start && mate_start <= rec_end;
         if (ov) skip = true;
       }
-      if (skip) break;
+      if (skip) return true;
     }
     need_break = false;
     int c_operator = c_op(cg.op[ci]);
@@ -1003,7 +1018,7 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
       sink.unsupported();
       w.start += w.clen;
       w.offset = 0;
-      continue;
+      return false;
     }
     if (c_operator == OP_S) {
       // ---- process_softclip :1112-1301 -----------------------------------------------------------
@@ -1063,16 +1078,16 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
       w.rp += w.clen;
       w.offset = 0;
       w.start = position;
-      continue;
+      return false;
     }
-    if (c_operator == OP_H) { w.offset = 0; continue; }
+    if (c_operator == OP_H) { w.offset = 0; return false; }
 
     if (c_operator == OP_I) {
       // ---- process_insertion :1303-1523 ----------------------------------------------------------
       w.offset = 0;
       if ((n_cigar > ci + 1 && c_op(cg.op[ci + 1]) == OP_N) || (ci > 0 && c_op(cg.op[ci - 1]) == OP_N)) {
         w.rp += w.clen;
-        continue;
+        return false;
       }
       Key key;
       key.clear();
@@ -1087,7 +1102,7 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
       bool combo = P.local_realign && n_cigar > ci + 2 && c_len(cg.op[ci + 1]) <= P.vext &&
                    c_op(cg.op[ci + 1]) == OP_M && is_id(c_op(cg.op[ci + 2]));
       if (combo) {
-        if (ci + 3 >= n_cigar) { sink.unsupported(); return; }
+        if (ci + 3 >= n_cigar) { sink.unsupported(); return true; }
         combo = !is_id(c_op(cg.op[ci + 3]));
       }
       if (combo) {
@@ -1184,16 +1199,16 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
       w.rp += w.clen + w.offset + multoffp;
       w.re += w.clen + w.offset + multoffp;
       w.start += w.offset + multoffs;
-      continue;
+      return false;
     }
 
     if (c_operator == OP_D) {
       // ---- process_deletion :1525-1727 -----------------------------------------------------------
       w.offset = 0;
-      if (ci + 1 >= n_cigar) { sink.unsupported(); return; }  // reads cigar[ci+1] unconditionally (A-6)
+      if (ci + 1 >= n_cigar) { sink.unsupported(); return true; }  // reads cigar[ci+1] unconditionally (A-6)
       if (c_op(cg.op[ci + 1]) == OP_N || (ci > 1 && c_op(cg.op[ci - 1]) == OP_N)) {
         w.rp += w.clen;
-        continue;
+        return false;
       }
       Key key;
       key.clear();
@@ -1207,7 +1222,7 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
       bool combo = P.local_realign && n_cigar > ci + 2 && c_len(cg.op[ci + 1]) <= P.vext &&
                    c_op(cg.op[ci + 1]) == OP_M && is_id(c_op(cg.op[ci + 2]));
       if (combo) {
-        if (ci + 3 >= n_cigar) { sink.unsupported(); return; }
+        if (ci + 3 >= n_cigar) { sink.unsupported(); return true; }
         combo = !is_id(c_op(cg.op[ci + 3]));
       }
       if (combo) {
@@ -1292,7 +1307,7 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
       w.start += w.clen + w.offset + multoffs;
       w.rp += w.offset + multoffp;
       w.re += w.offset + multoffp;
-      continue;
+      return false;
     }
 
     // ---- match part :675-959 ------------------------------------------------------------------------
@@ -1325,14 +1340,14 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
         w.start += w.clen;
         w.rp += w.clen;
         w.re += w.clen;
-        if (w.start > R.end) break;
-        continue;
+        if (w.start > R.end) return true;
+        return false;
       }
     }
     if (trim_after == 0 && w.clen - w.offset > 0 && nm >= 0 && nm <= 127 && rlen < 65536) {
       const bool indel_follows = ci + 1 < n_cigar && is_id(c_op(cg.op[ci + 1]));
       SegDesc sd;
-      if (scan_plain_segment(P, rd, ref, w.start, w.rp, w.clen - w.offset, indel_follows, &sd)) {
+      if (sink.scan_segment(P, rd, ref, w.start, w.rp, w.clen - w.offset, indel_follows, &sd)) {
         sd.m_start = w.start;
         sd.len = w.clen - w.offset;
         sd.rp = w.rp;
@@ -1342,8 +1357,8 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
           w.start += sd.len;
           w.rp += sd.len;
           w.re += sd.len;
-          if (w.start > R.end) break;
-          continue;
+          if (w.start > R.end) return true;
+          return false;
         }
       }
     }
@@ -1552,7 +1567,15 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
       w.start += moffset;
       w.re += moffset;
     }
-    if (w.start > R.end) break;
+    if (w.start > R.end) return true;
+    return false;
+  };
+  bool active = has_work && n_cigar > 0;
+  while (RV_WARP_ANY(active)) {
+    if (active) {
+      if (op_step()) active = false;
+      else if (++ci >= n_cigar) active = false;
+    }
   }
 }
 

@@ -126,6 +126,95 @@ struct DeviceSink {
   __device__ __forceinline__ void unsupported() { if (!mute) n_unsup++; }
 };
 
+__device__ __forceinline__ int nib_allele(int nib) { return (nib >> 1) - (nib >> 3); }  // 1,2,4,8 -> 0,1,2,3
+
+// bit 0 of every nibble = OR of the nibble's four bits
+__device__ __forceinline__ uint32_t nib_any(uint32_t x) { return (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u; }
+
+// The nibble-SIMD plain-run proof.  The matched stretch [rp0, rp0 + ml) of a read is compared with the reference 8
+// bases per step: BAM's 4-bit bases XOR the 4-bit reference (funnel-shifted to the read's phase) give one mismatch flag
+// per nibble; shifted copies of the flag word, carried across words, prove that no two mismatches lie within D = vext + 1
+// bases, i.e. that no base of the stretch can start a multi-nucleotide key (parseCigar.cpp:711-768).  Read bases other
+// than A, C, G, T make the stretch not plain.  Returns bad == 0 (more than eight mismatches are left to the caller);
+// mismatches are listed as 0x8000 | offset << 2 | allele, 16 bits each, the newest in the low bits.
+// sq: the read's packed bases (word 0 = bases 0..7); E0: reference-slice index of read base 0 (>= 0).
+struct PlainScan {
+  uint32_t mm_blocks;
+  unsigned long long ml_lo, ml_hi;
+  int ml_n;
+  uint32_t special;  // a read base that is not A, C, G, T was seen
+};
+__device__ __forceinline__ bool simd_plain_scan(const uint32_t* sq, const uint32_t* ref4, int E0, int rp0, int ml, int D,
+                                                PlainScan* out) {
+  const int w_first = rp0 >> 3, w_last = (rp0 + ml - 1) >> 3;
+  const int e = E0 + 8 * w_first;
+  const int sh = (e & 7) * 4;
+  const uint32_t* rw = ref4 + (e >> 3);
+  uint32_t r_lo = rw[0];
+  uint32_t prev = 0, bad = 0, seen = 0, spec = 0, mm_blocks = 0;
+  unsigned long long ml_lo = 0, ml_hi = 0;
+  int ml_n = 0;
+  for (int wi = w_first; wi <= w_last; ++wi) {
+    const uint32_t r_hi = *++rw;
+    const uint32_t rf = __funnelshift_l(r_hi, r_lo, sh);
+    r_lo = r_hi;
+    const uint32_t b8 = __byte_perm(sq[wi], 0, 0x0123);  // base 8*wi in the top nibble
+    uint32_t vm = 0xffffffffu;
+    if (wi == w_first) vm >>= 4 * (rp0 & 7);
+    if (wi == w_last) {
+      const int hi = ((rp0 + ml - 1) & 7) + 1;
+      if (hi < 8) vm &= ~(0xffffffffu >> (4 * hi));
+    }
+    const uint32_t nz = nib_any(b8 ^ rf) & vm;
+    // read bases other than A, C, G, T (N included): zero nibble, or more than one bit in the nibble
+    const uint32_t special = (~nib_any(b8) | nib_any(b8 & (b8 - 0x11111111u))) & 0x11111111u & vm;
+    uint32_t near;
+    if (D == 3) {
+      near = nz & (__funnelshift_r(nz, prev, 4) | __funnelshift_r(nz, prev, 8) | __funnelshift_r(nz, prev, 12));
+    } else if (D <= 7) {
+      near = 0;
+      for (int d = 1; d <= D; ++d) near |= nz & __funnelshift_r(nz, prev, 4 * d);
+    } else {
+      near = (nz & (nz - 1)) | ((nz && seen) ? 1u : 0u);  // conservative: any two mismatches in the stretch
+      seen |= nz;
+    }
+    bad |= near | special;
+    spec |= special;
+    prev = nz;
+    if (nz) {  // 16-base blocks of the stretch this word's mismatches may lie in (a word touches at most two)
+      const int k_lo = 8 * wi - rp0 > 0 ? 8 * wi - rp0 : 0;
+      const int k_hi = 8 * wi + 7 - rp0 < ml - 1 ? 8 * wi + 7 - rp0 : ml - 1;
+      mm_blocks |= (1u << min(k_lo >> 4, 15)) | (1u << min(k_hi >> 4, 15));
+      for (uint32_t z = nz; z;) {  // the mismatches themselves: base 8*wi + i has its flag at bit 28 - 4i
+        const int i = __clz(z) >> 2;
+        z &= ~(0x10000000u >> (4 * i));
+        const uint32_t en = 0x8000u | ((uint32_t)(8 * wi + i - rp0) << 2) | ((uint32_t)nib_allele((b8 >> (28 - 4 * i)) & 15u) & 3u);
+        ml_hi = (ml_hi << 16) | (ml_lo >> 48);
+        ml_lo = (ml_lo << 16) | en;
+        ml_n++;
+      }
+    }
+  }
+  out->mm_blocks = mm_blocks;
+  out->ml_lo = ml_lo;
+  out->ml_hi = ml_hi;
+  out->ml_n = ml_n;
+  out->special = spec;
+  return bad == 0;
+}
+// is any listed mismatch among the first `head` or the last `tail` bases of a stretch of ml bases?
+__device__ __forceinline__ bool mismatch_near_ends(const PlainScan& ps, int ml, int head, int tail) {
+  unsigned long long lo = ps.ml_lo, hi = ps.ml_hi;
+  const int n = ps.ml_n < 8 ? ps.ml_n : 8;
+  for (int j = 0; j < n; ++j) {
+    const int k = (int)((lo >> 2) & 0x1fffu);
+    if (k < head || k >= ml - tail) return true;
+    lo = (lo >> 16) | (hi << 48);
+    hi >>= 16;
+  }
+  return ps.ml_n > 8;  // more mismatches than the list holds: unknown, say yes
+}
+
 // Sink of rv_walk_kernel: nothing is added to the tables here.  Plain segments become gather descriptors, everything
 // else a SparseObs for rv_apply_kernel or an event for the host stage.
 struct ListSink {
@@ -177,6 +266,23 @@ struct ListSink {
     a->events[slot] = e;
     n_ev++;
   }
+  // scan_plain_segment with the nibble-SIMD proof (8 bases per step against the 4-bit reference)
+  __device__ __forceinline__ bool scan_segment(const rv_params& P, const ReadView& rv, const RefView& ref, int m_start, int rp, int len,
+                                               bool indel_follows, SegDesc* out) {
+    if (!want_segments || len <= 0 || len > 8192) return false;
+    const int E0 = m_start - rp - a->ref_start;
+    const int64_t w_lo = ref.lo > a->ref_start ? ref.lo : a->ref_start;
+    const int64_t w_hi = (int64_t)ref.hi < a->ref_start + a->ref_n - 1 ? (int64_t)ref.hi : a->ref_start + a->ref_n - 1;
+    if (E0 < 0 || m_start < w_lo || (int64_t)m_start + len - 1 > w_hi) return false;
+    PlainScan ps;
+    if (!simd_plain_scan((const uint32_t*)rv.seq4, a->ref4, E0, rp, len, P.vext + 1, &ps) || ps.ml_n > 8) return false;
+    if (indel_follows && P.local_realign && mismatch_near_ends(ps, len, 0, P.vext)) return false;
+    out->mm_blocks = ps.mm_blocks;
+    out->ml[0] = (uint32_t)ps.ml_lo; out->ml[1] = (uint32_t)(ps.ml_lo >> 32);
+    out->ml[2] = (uint32_t)ps.ml_hi; out->ml[3] = (uint32_t)(ps.ml_hi >> 32);
+    out->n_mm = ps.ml_n;
+    return true;
+  }
   __device__ __forceinline__ bool segment(const SegDesc& sd, bool dir, int mapq, int nm) {
     if (!want_segments) return false;
     const int slot = n_seg + (first_taken ? 1 : 0);
@@ -221,10 +327,6 @@ __device__ __forceinline__ int find_region(const DevRegion* regs, int n, int64_t
   return lo;
 }
 
-__device__ __forceinline__ int nib_allele(int nib) { return (nib >> 1) - (nib >> 3); }  // 1,2,4,8 -> 0,1,2,3
-
-// bit 0 of every nibble = OR of the nibble's four bits
-__device__ __forceinline__ uint32_t nib_any(uint32_t x) { return (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u; }
 
 // 4-bit packing of the reference slice (one thread per 8 bases)
 __global__ void rv_pack_ref_kernel(const char* ref, int64_t n, uint32_t* out, int64_t n_words) {
@@ -244,204 +346,140 @@ __global__ void rv_pack_ref_kernel(const char* ref, int64_t n, uint32_t* out, in
   out[w] = v;
 }
 
-// One (region, read) pair per thread, three stages:
-//   1. per thread : read filters, CIGAR rewrite rules, clean-up (prepare_read)
-//   2. per thread : the matched run of a fast-shaped read is compared with the reference 8 bases per step: the
-//                   BAM 4-bit bases XOR the 4-bit reference give one mismatch flag per nibble; shifted copies
-//                   of the flag word (carried across words) prove that no two mismatches lie within vext+1
-//                   bases, i.e. that no base of the run can start a multi-nucleotide key
-//                   (parseCigar.cpp:711-768).  Such a "plain" run only leaves a GDesc for the gather kernel.
-//   3. per thread : everything that needs the exact CIGAR walk (soft clips, indels, non-plain runs, reads with N
-//                   or IUPAC bases) is appended to the walk queue
+static const unsigned long long WALK_COUNT_STATS = 1ull << 61;  // the walk kernel's prepare_read counts the read's statistics
+
+// rv_pileup_kernel — classify.  One (region, read) pair per thread.
+//   * the record filters of RecordPreprocessor::next_record (recordPreprocessor.cpp:121-176, -t included);
+//   * a read whose CIGAR is one M op over the whole read — the bulk of any data set — is handled here completely:
+//     NM filter, the plain-run proof over the read, and the observation that CigarModifier (cigarModifier.cpp:365-377)
+//     leaves such a read alone when its first three and last three bases equal the reference (with them inside the loaded
+//     window the two mismatch walks, :412-439 and :529-568, stop after three matches with nothing to clip).  The
+//     remaining tests of parseCigar's preamble (:584-603) are applied and a plain read leaves its gather descriptor;
+//   * every other read (soft clips, indels, hard clips, mismatching ends, N bases, clustered mismatches) is appended
+//     to the walk queue: rv_walk_kernel runs prepare_read + walk_read on it.
 __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
-  int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  Prep pr;
-  pr.ok = false;
-  pr.fast_shape = false;
-  pr.m_start = pr.m_len = pr.rp0 = 0;
-  DeviceSink s;
-  s.a = &a;
-  s.kept_bases = s.n_kept = s.n_unsup = s.n_over = 0;
-  s.mute = false;
-  const DevRegion* dr = a.regions;
-  s.dr = dr;
-  rv_read rd;
-  rd.data_off16 = 0; rd.n_cigar = 0; rd.l_seq = 0; rd.pos = 0;
-  RefView ref;
-  ref.bases = a.ref;
-  ref.base_pos = a.ref_start;
-  ref.n = a.ref_n;
-  ref.lo = 1;
-  ref.hi = 0;
-  int64_t read_idx = 0;
-  if (item < a.n_items) {
-    const int ri = find_region(a.regions, a.n_regions, item);
-    dr = a.regions + ri;
-    read_idx = dr->r.read_lo + (item - dr->item_base);
-    rd = a.reads[read_idx - dr->read_bias];
-    ref.lo = dr->r.ref_lo;
-    ref.hi = dr->r.ref_hi;
-    s.dr = dr;
-    // htslib iterator overlap test (sam_itr_next): pos0 < end && endpos > beg0
-    if (rd.pos - 1 < dr->r.end && rd.end_pos > dr->r.start - 1 &&
-        !(a.P.dedup && is_duplicate_read(a.P, dr->r, a.reads - dr->read_bias, a.pool - dr->pool_bias, read_idx)))
-      prepare_read(a.P, dr->r, rd, a.pool - dr->pool_bias, ref, s, true, pr);
-  }
-  // ---- stage 2: warp-cooperative plain-run proof ------------------------------------------------------
-  // u32 index of the packed bases in the DEVICE pool
-  const size_t seq_word = (size_t)(((int64_t)rd.data_off16 * 16 - dr->pool_bias) >> 2) + rd.n_cigar;
-  int E0 = 0;  // reference-slice index of read base 0
-  bool cand = pr.ok && pr.fast_shape && !a.force_exact;
-  if (cand) {
-    E0 = pr.m_start - pr.rp0 - a.ref_start;
-    const int64_t w_lo = ref.lo > a.ref_start ? ref.lo : a.ref_start;
-    const int64_t w_hi = (int64_t)ref.hi < a.ref_start + a.ref_n - 1 ? (int64_t)ref.hi : a.ref_start + a.ref_n - 1;
-    cand = pr.m_len > 0 && E0 >= 0 && pr.m_start >= w_lo && (int64_t)pr.m_start + pr.m_len - 1 <= w_hi && pr.nm >= 0 &&
-           pr.nm <= 127 && pr.mapq <= 255 && pr.m_len <= 8192;
-  }
-  bool plain = cand;
-  uint32_t mm_blocks = 0;
-  unsigned long long ml_lo = 0, ml_hi = 0;  // the run's mismatches, 16 bits each (newest in the low bits)
-  int ml_n = 0;
-  if (cand) {
-    const int D = a.P.vext + 1;
-    const uint32_t* sq = (const uint32_t*)a.pool + seq_word;
-    const int rp0 = pr.rp0, ml = pr.m_len;
-    const int w_first = rp0 >> 3, w_last = (rp0 + ml - 1) >> 3;
-    const int e = E0 + 8 * w_first;
-    const int sh = (e & 7) * 4;
-    const uint32_t* rw = a.ref4 + (e >> 3);
-    uint32_t r_lo = rw[0];
-    uint32_t prev = 0, bad = 0, seen = 0;
-    for (int wi = w_first; wi <= w_last; ++wi) {
-      const uint32_t r_hi = *++rw;
-      const uint32_t rf = __funnelshift_l(r_hi, r_lo, sh);
-      r_lo = r_hi;
-      const uint32_t b8 = __byte_perm(sq[wi], 0, 0x0123);  // base 8*wi in the top nibble
-      uint32_t vm = 0xffffffffu;
-      if (wi == w_first) vm >>= 4 * (rp0 & 7);
-      if (wi == w_last) {
-        const int hi = ((rp0 + ml - 1) & 7) + 1;
-        if (hi < 8) vm &= ~(0xffffffffu >> (4 * hi));
-      }
-      const uint32_t nz = nib_any(b8 ^ rf) & vm;
-      // read bases other than A, C, G, T (N included): zero nibble, or more than one bit in the nibble
-      const uint32_t special = (~nib_any(b8) | nib_any(b8 & (b8 - 0x11111111u))) & 0x11111111u & vm;
-      uint32_t near;
-      if (D == 3) {
-        near = nz & (__funnelshift_r(nz, prev, 4) | __funnelshift_r(nz, prev, 8) | __funnelshift_r(nz, prev, 12));
-      } else if (D <= 7) {
-        near = 0;
-        for (int d = 1; d <= D; ++d) near |= nz & __funnelshift_r(nz, prev, 4 * d);
-      } else {
-        near = (nz & (nz - 1)) | ((nz && seen) ? 1u : 0u);  // conservative: any two mismatches in the run
-        seen |= nz;
-      }
-      bad |= near | special;
-      prev = nz;
-      if (nz) {  // 16-base blocks of the run this word's mismatches may lie in (a word touches at most two)
-        const int k_lo = 8 * wi - rp0 > 0 ? 8 * wi - rp0 : 0;
-        const int k_hi = 8 * wi + 7 - rp0 < ml - 1 ? 8 * wi + 7 - rp0 : ml - 1;
-        mm_blocks |= (1u << min(k_lo >> 4, 15)) | (1u << min(k_hi >> 4, 15));
-        for (uint32_t z = nz; z;) {  // the mismatches themselves: base 8*wi + i has its flag at bit 28 - 4i
-          const int i = __clz(z) >> 2;
-          z &= ~(0x10000000u >> (4 * i));
-          const uint32_t e = 0x8000u | ((uint32_t)(8 * wi + i - rp0) << 2) | ((uint32_t)nib_allele((b8 >> (28 - 4 * i)) & 15u) & 3u);
-          ml_hi = (ml_hi << 16) | (ml_lo >> 48);
-          ml_lo = (ml_lo << 16) | e;
-          ml_n++;
-        }
-      }
-    }
-    plain = bad == 0 && ml_n <= 8;
-  }
-  // ---- stage 3: descriptor for plain matched runs; everything else is queued for rv_walk_kernel -----
+  int kept = 0, kept_bases = 0;
   int back = 0, reach = 0;
-  int queue_kind = -1;  // 0: whole-read walk, 1: soft clips of a plain read
+  bool queue = false;
   unsigned long long queue_entry = 0;
   if (item < a.n_items) {
+    const int ri = find_region(a.regions, a.n_regions, item);
+    const DevRegion* dr = a.regions + ri;
+    const int64_t read_idx = dr->r.read_lo + (item - dr->item_base);
+    const rv_read rd = a.reads[read_idx - dr->read_bias];
     GDesc gd;
     gd.m_start = 0; gd.m_len = 0; gd.re0 = 0; gd.qual_off = 0; gd.rlen = 0; gd.mapq = 0; gd.dir_nm = 0;
-    if (pr.ok) {
-      // parseCigar.cpp:630 / skipOverlappingReads :182-206 — the -u / --UN test happens once, before the first op
-      bool skip = false;
-      const bool paired_same = (rd.flag & 1) && rd.mate_same_tid;
-      if (a.P.uniq_u && paired_same && !pr.dir && pr.position >= rd.mpos) skip = true;
-      if (!skip && a.P.uniq_un && (rd.flag & 1) && paired_same) {
-        const int ref_len = pr.rec_ref_len;
-        // start == position before the first op, so the "position < mate_start" arm can never hold
-        if (pr.position >= rd.mpos && pr.position <= rd.mpos + ref_len - 1) skip = true;
+    uint32_t mm_blocks = 0;
+    bool store_ml = false;
+    PlainScan ps;
+    ps.ml_lo = ps.ml_hi = 0;
+    // htslib iterator overlap test (sam_itr_next): pos0 < end && endpos > beg0; then recordPreprocessor.cpp:121-146
+    bool pass = rd.pos - 1 < dr->r.end && rd.end_pos > dr->r.start - 1 && (rd.flag & a.P.samfilter) == 0 &&
+                (int)rd.mapq >= a.P.mapping_quality && rd.l_seq != 1 && rd.n_cigar > 0;
+    if (pass && a.P.dedup && is_duplicate_read(a.P, dr->r, a.reads - dr->read_bias, a.pool - dr->pool_bias, read_idx)) pass = false;
+    if (pass) {
+      const int64_t pool_off = (int64_t)rd.data_off16 * 16 - dr->pool_bias;  // device pool byte of the read's variable part
+      const uint32_t c0 = *(const uint32_t*)(a.pool + pool_off);
+      bool simple = rd.n_cigar == 1 && c_op(c0) == OP_M && c_len(c0) == rd.l_seq && rd.l_seq >= 8 && rd.l_seq <= 8192 &&
+                    !a.force_exact && a.P.trim_bases_after == 0;
+      int nm = 0;
+      if (simple) {  // parseCigar.cpp:514-534 with no indel bases
+        if (rd.nm >= 0) { nm = rd.nm; if (nm > a.P.mismatch) { pass = false; simple = false; } }
+        else if (rd.flag & 4) { pass = false; simple = false; }
+        if (nm > 127) simple = false;
       }
-      bool queue = false;
-      unsigned long long entry = (unsigned long long)item;
-      if (!skip) {
-        if (plain) {
-          gd.m_start = pr.m_start;
-          gd.m_len = (uint16_t)pr.m_len;
-          gd.re0 = 0;                      // a read of shape [H][S] M [S][H]: the run is the whole aligned part
-          gd.qual_off = (uint32_t)(seq_word * 4 + (size_t)((rd.l_seq + 1) >> 1) + (size_t)pr.rp0);
-          gd.rlen = (uint16_t)pr.m_len;
-          gd.mapq = (uint8_t)pr.mapq;
-          gd.dir_nm = (uint8_t)((pr.dir ? 0x80 : 0) | pr.nm);
-          back = rd.pos - pr.m_start;
-          reach = pr.m_start + pr.m_len - rd.pos;
-          // ops other than M/H (soft clips) still need the walk
-          bool only_mh = true;
-          for (int k = 0; k < pr.n_cigar; ++k) {
-            const int o = c_op(pr.cg.op[k]);
-            if (o != OP_M && o != OP_H) only_mh = false;
+      if (simple) {
+        const int ml = rd.l_seq;
+        const int E0 = rd.pos - a.ref_start;
+        const int64_t w_lo = dr->r.ref_lo > a.ref_start ? dr->r.ref_lo : a.ref_start;
+        const int64_t w_hi = (int64_t)dr->r.ref_hi < a.ref_start + a.ref_n - 1 ? (int64_t)dr->r.ref_hi : a.ref_start + a.ref_n - 1;
+        simple = E0 >= 0 && rd.pos >= w_lo && (int64_t)rd.pos + ml - 1 <= w_hi;
+        if (simple) {
+          const uint32_t* sq = (const uint32_t*)(a.pool + pool_off) + 1;
+          const bool plain = simd_plain_scan(sq, a.ref4, E0, 0, ml, a.P.vext + 1, &ps) && ps.ml_n <= 8;
+          // CigarModifier leaves the read alone only with clean ends (-k 1); a base that is not A/C/G/T anywhere sends
+          // the read to the literal path as well
+          const bool ends_dirty = a.P.local_realign && (ps.special != 0 || mismatch_near_ends(ps, ml, 3, 3));
+          if (ends_dirty) simple = false;
+          else {
+            // the rest of parseCigar's preamble for an unchanged "<l_seq>M": -M, maxReadLength, supplementary (:591-603)
+            if (a.P.minmatch != 0 && ml < a.P.minmatch) pass = false;
+            else {
+              if (ml > a.max_rl[ri]) atomicMax(a.max_rl + ri, ml);
+              if (rd.flag & 2048) pass = false;
+              else {
+                kept = 1;
+                kept_bases = ml;
+                // parseCigar.cpp:630 / skipOverlappingReads :182-206 — the -u / --UN test happens once, before the first op
+                const bool dir = (rd.flag & 16) != 0;
+                const bool paired_same = (rd.flag & 1) && rd.mate_same_tid;
+                bool skip = a.P.uniq_u && paired_same && !dir && rd.pos >= rd.mpos;
+                if (!skip && a.P.uniq_un && paired_same && rd.pos >= rd.mpos && rd.pos <= rd.mpos + ml - 1) skip = true;
+                if (!skip) {
+                  if (plain) {
+                    gd.m_start = rd.pos;
+                    gd.m_len = (uint16_t)ml;
+                    gd.re0 = 0;
+                    gd.qual_off = (uint32_t)(pool_off + 4 + ((ml + 1) >> 1));
+                    gd.rlen = (uint16_t)ml;
+                    gd.mapq = rd.mapq;
+                    gd.dir_nm = (uint8_t)((dir ? 0x80 : 0) | nm);
+                    mm_blocks = ps.mm_blocks;
+                    store_ml = mm_blocks != 0;
+                    reach = ml;
+                  } else {  // clustered mismatches away from the ends: the literal walk (statistics are counted already)
+                    queue = true;
+                    queue_entry = (unsigned long long)item;
+                  }
+                }
+              }
+            }
           }
-          if (!only_mh) { queue = true; entry |= WALK_PLAIN_DONE; }
-        } else {
-          queue = true;
         }
       }
-      if (queue) {
-        queue_kind = (entry & WALK_PLAIN_DONE) ? 1 : 0;
-        queue_entry = entry;
+      if (pass && !simple && !kept) {
+        queue = true;
+        queue_entry = (unsigned long long)item | WALK_COUNT_STATS;
       }
     }
     *(uint4*)(a.descs + item) = *(const uint4*)&gd;
     a.desc_mm[item] = (uint16_t)mm_blocks;
-    if (mm_blocks && plain)
-      a.desc_mml[item] = make_uint4((uint32_t)ml_lo, (uint32_t)(ml_lo >> 32), (uint32_t)ml_hi, (uint32_t)(ml_hi >> 32));
+    if (store_ml)
+      a.desc_mml[item] = make_uint4((uint32_t)ps.ml_lo, (uint32_t)(ps.ml_lo >> 32), (uint32_t)ps.ml_hi, (uint32_t)(ps.ml_hi >> 32));
   }
   // ---- statistics and the candidate-window bounds of the gather kernel: one atomic per warp / block ----
-  unsigned long long kept = s.n_kept, bases = s.kept_bases, unsup = s.n_unsup, over = s.n_over;
+  unsigned long long w_kept = kept, w_bases = kept_bases;
   for (int off = 16; off > 0; off >>= 1) {
-    kept += __shfl_down_sync(0xffffffffu, kept, off);
-    bases += __shfl_down_sync(0xffffffffu, bases, off);
-    unsup += __shfl_down_sync(0xffffffffu, unsup, off);
-    over += __shfl_down_sync(0xffffffffu, over, off);
+    w_kept += __shfl_down_sync(0xffffffffu, w_kept, off);
+    w_bases += __shfl_down_sync(0xffffffffu, w_bases, off);
     back = max(back, __shfl_down_sync(0xffffffffu, back, off));
     reach = max(reach, __shfl_down_sync(0xffffffffu, reach, off));
   }
-  // queue slots: one atomic per CTA and kind, entries of a CTA stay together in item order, so that neighbouring
-  // lanes of rv_walk_kernel walk neighbouring reads (same indel site, same CIGAR shape: the lanes stay in step)
-  __shared__ unsigned long long sh[4];
-  __shared__ unsigned s_qcnt[2][4];
-  __shared__ unsigned long long s_qbase[2];
-  const unsigned b0 = __ballot_sync(0xffffffffu, queue_kind == 0), b1 = __ballot_sync(0xffffffffu, queue_kind == 1);
-  if (lane == 0) { s_qcnt[0][threadIdx.x >> 5] = __popc(b0); s_qcnt[1][threadIdx.x >> 5] = __popc(b1); }
-  if (threadIdx.x < 4) sh[threadIdx.x] = 0;
+  // queue slots: one atomic per CTA, entries of a CTA stay together in item order, so that neighbouring lanes of
+  // rv_walk_kernel walk neighbouring reads (same indel site, same CIGAR shape: the lanes stay in step)
+  __shared__ unsigned long long sh[2];
+  __shared__ unsigned s_qcnt[4];
+  __shared__ unsigned long long s_qbase;
+  const unsigned b0 = __ballot_sync(0xffffffffu, queue);
+  if (lane == 0) s_qcnt[threadIdx.x >> 5] = __popc(b0);
+  if (threadIdx.x < 2) sh[threadIdx.x] = 0;
   __syncthreads();
-  if (threadIdx.x < 2) {
-    const unsigned tot = s_qcnt[threadIdx.x][0] + s_qcnt[threadIdx.x][1] + s_qcnt[threadIdx.x][2] + s_qcnt[threadIdx.x][3];
-    s_qbase[threadIdx.x] = tot ? atomicAdd(a.walk_count + threadIdx.x, (unsigned long long)tot) : 0ull;
+  if (threadIdx.x == 0) {
+    const unsigned tot = s_qcnt[0] + s_qcnt[1] + s_qcnt[2] + s_qcnt[3];
+    s_qbase = tot ? atomicAdd(a.walk_count, (unsigned long long)tot) : 0ull;
   }
   __syncthreads();
-  if (queue_kind >= 0) {
-    unsigned long long slot = s_qbase[queue_kind];
-    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) slot += s_qcnt[queue_kind][w];
-    slot += __popc((queue_kind ? b1 : b0) & ((1u << lane) - 1u));
-    a.walk_queue[queue_kind ? a.walk_cap - 1 - slot : slot] = queue_entry;
+  if (queue) {
+    unsigned long long slot = s_qbase;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) slot += s_qcnt[w];
+    slot += __popc(b0 & ((1u << lane) - 1u));
+    a.walk_queue[slot] = queue_entry;
   }
   if (lane == 0) {
-    if (kept) atomicAdd(&sh[0], kept);
-    if (bases) atomicAdd(&sh[1], bases);
-    if (unsup) atomicAdd(&sh[2], unsup);
-    if (over) atomicAdd(&sh[3], over);
+    if (w_kept) atomicAdd(&sh[0], w_kept);
+    if (w_bases) atomicAdd(&sh[1], w_bases);
     if (back > a.reach[0]) atomicMax(a.reach + 0, back);
     if (reach > a.reach[1]) atomicMax(a.reach + 1, reach);
   }
@@ -449,21 +487,19 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
   if (threadIdx.x == 0) {
     if (sh[0]) atomicAdd(&a.stats->n_kept, sh[0]);
     if (sh[1]) atomicAdd(&a.stats->n_bases, sh[1]);
-    if (sh[2]) atomicAdd(&a.stats->n_unsupported, sh[2]);
-    if (sh[3]) atomicAdd(&a.stats->n_overflow, sh[3]);
   }
 }
 
-// The queued work items, one per thread: reads with soft clips or indels, reads whose matched run is not plain.
-// prepare_read is repeated (the classify kernel keeps no per-read state), then walk_read runs the literal CIGAR walk
-// with a ListSink: plain matched stretches leave gather descriptors, the rest goes to the SparseObs list / the events.
-// The grid is sized to what is resident (MIN_CTAS per SM); a warp takes its next 32 queue entries from a cursor, whole-read
-// walks first, so the long walks start early and the short soft-clip walks fill the tail.
+// rv_walk_kernel — the queued reads, one per thread: prepare_read (parseCigar's preamble: NM filter, every CigarModifier
+// rule, clean-up, the clip / length / supplementary filters), then walk_read with a ListSink: plain matched stretches
+// leave gather descriptors, the rest goes to the SparseObs list / the events.  All 32 lanes of a warp go through
+// walk_read together (its CIGAR-op rounds are warp-synchronous).  The grid is sized to what is resident (MIN_CTAS per
+// SM); a warp takes its next 32 queue entries from a cursor.
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(128, MIN_CTAS) rv_walk_kernel(PileupArgs a) {
-  const unsigned long long n_full = a.walk_count[0], n = n_full + a.walk_count[1];
-  unsigned long long over = 0, unsup = 0, full = 0, clip = 0;
-  if (blockIdx.x == 0 && threadIdx.x == 0) a.stats->n_walk_items = n;
+  const unsigned long long n = a.walk_count[0];
+  unsigned long long over = 0, unsup = 0, clip = 0, kept = 0, bases = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { a.stats->n_walk_items = n; a.stats->n_walk_full = n; }
   const int lane = threadIdx.x & 31;
   for (;;) {
     unsigned long long q0 = 0;
@@ -471,15 +507,15 @@ __global__ void __launch_bounds__(128, MIN_CTAS) rv_walk_kernel(PileupArgs a) {
     q0 = __shfl_sync(0xffffffffu, q0, 0);
     if (q0 >= n) break;
     const unsigned long long q = q0 + lane;
-    if (q >= n) continue;
-    const unsigned long long entry = a.walk_queue[q < n_full ? q : a.walk_cap - 1 - (q - n_full)];
-    const int64_t item = (int64_t)(entry & ~WALK_PLAIN_DONE);
-    const bool plain_done = (entry & WALK_PLAIN_DONE) != 0;
-    if (!plain_done) full++;
+    bool work = q < n;
+    const unsigned long long entry = work ? a.walk_queue[q] : 0ull;
+    const int64_t item = (int64_t)(entry & ~(WALK_COUNT_STATS | WALK_PLAIN_DONE));
     const int ri = find_region(a.regions, a.n_regions, item);
     const DevRegion* dr = a.regions + ri;
     const int64_t read_idx = dr->r.read_lo + (item - dr->item_base);
-    const rv_read rd = a.reads[read_idx - dr->read_bias];
+    rv_read rd;
+    if (work) rd = a.reads[read_idx - dr->read_bias];
+    else { rd.pos = 0; rd.mpos = 0; rd.data_off16 = 0; rd.l_seq = 0; rd.flag = 0; rd.n_cigar = 0; rd.nm = 0; rd.mapq = 0; rd.mate_same_tid = 0; rd.end_pos = 0; rd.mtid = 0; }
     const uint8_t* pool = a.pool - dr->pool_bias;
     RefView ref;
     ref.bases = a.ref;
@@ -492,25 +528,29 @@ __global__ void __launch_bounds__(128, MIN_CTAS) rv_walk_kernel(PileupArgs a) {
     s.bind(dr);
     s.item = item;
     s.n_seg = 0;
-    s.first_taken = plain_done;
+    s.first_taken = false;
     s.want_segments = !a.force_exact;
     s.rd = &rd;
     s.pool_off = (int64_t)rd.data_off16 * 16 - dr->pool_bias;
     s.n_unsup = s.n_over = s.n_clip = s.n_ev = 0;
     Prep pr;
+    pr.ok = false;
+    pr.n_cigar = 0;
     const rv_region R = dr->r;  // by value: the walk compares against start / end at every base
-    {
-      DeviceSink mute;          // prepare_read's statistics were already counted by rv_pileup_kernel
-      mute.a = &a;
-      mute.dr = dr;
-      mute.mute = true;
-      mute.kept_bases = mute.n_kept = mute.n_unsup = mute.n_over = 0;
-      prepare_read(a.P, R, rd, pool, ref, mute, true, pr);
+    if (work) {
+      DeviceSink ps;
+      ps.a = &a;
+      ps.dr = dr;
+      ps.mute = (entry & WALK_COUNT_STATS) == 0;  // counted by rv_pileup_kernel already
+      ps.kept_bases = ps.n_kept = ps.n_unsup = ps.n_over = 0;
+      prepare_read(a.P, R, rd, pool, ref, ps, false, pr);
+      kept += ps.n_kept;
+      bases += ps.kept_bases;
+      unsup += ps.n_unsup;
     }
-    if (!pr.ok) continue;  // cannot happen: the item was queued because it passed
-    FastDesc scratch;
-    walk_read(a.P, R, ri, rd, pool, ref, (uint32_t)read_idx, s, pr, plain_done ? &scratch : (FastDesc*)0,
-              plain_done ? 1 : 0);
+    work = work && pr.ok;
+    __syncwarp();
+    walk_read(a.P, R, ri, rd, pool, ref, (uint32_t)read_idx, s, pr, (FastDesc*)0, 0, work);
     over += s.n_over;
     unsup += s.n_unsup;
     clip += s.n_clip;
@@ -518,7 +558,8 @@ __global__ void __launch_bounds__(128, MIN_CTAS) rv_walk_kernel(PileupArgs a) {
   if (clip) atomicAdd(&a.stats->n_clipped, clip);
   if (over) atomicAdd(&a.stats->n_overflow, over);
   if (unsup) atomicAdd(&a.stats->n_unsupported, unsup);
-  if (full) atomicAdd(&a.stats->n_walk_full, full);
+  if (kept) atomicAdd(&a.stats->n_kept, kept);
+  if (bases) atomicAdd(&a.stats->n_bases, bases);
 }
 
 // The SparseObs list onto the tables (after the gather kernel has stored every row): one entry per thread.
@@ -1539,7 +1580,8 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   CK(cudaMalloc(&ctx->d_desc_mml2, sizeof(uint4) * (size_t)(2 * L.max_reads + 1024)));
   // SparseObs list: a walked read leaves a few entries (soft-clip re-extension, coverage under a deletion), a stretch
   // that is not plain one per base; RV_NO_GATHER sends every base here (small debugging batches only)
-  ctx->max_sparse = std::max<int64_t>(4 << 20, 8 * L.max_reads);
+  ctx->max_sparse = L.max_sparse_obs > 0 ? L.max_sparse_obs : std::max<int64_t>(4 << 20, 8 * L.max_reads);
+  if (ctx->max_sparse > ((int64_t)1 << 31)) return fail(ctx, RV_ERR_ARG, "limits.max_sparse_obs too large");
   CK(cudaMalloc(&ctx->d_sparse, sizeof(SparseObs) * (size_t)ctx->max_sparse));
   CK(cudaMalloc(&ctx->d_ref4, sizeof(uint32_t) * (size_t)(L.max_ref_bases / 8 + 16)));
   // gather tiles: every region rounds its table (length + 2*halo) up to whole tiles

@@ -71,6 +71,10 @@ struct SimSink {
   const uint8_t* cur_pool;
   int r_start, r_end;
   bool use_segments;
+  bool scan_segment(const rv_params& P, const rvk::ReadView& rd, const rvk::RefView& ref, int m_start, int rp, int len,
+                    bool indel_follows, rvk::SegDesc* out) {
+    return use_segments && rvk::scan_plain_segment(P, rd, ref, m_start, rp, len, indel_follows, out);
+  }
   bool segment(const rvk::SegDesc& d, bool dir, int mapq, int nm) {
     if (!use_segments) return false;
     const uint8_t* var = cur_pool + (size_t)cur_read->data_off16 * 16;

@@ -1,7 +1,10 @@
-set -x
-for env in "RV_G4_VARIANT=0 RV_WALK_OCC=4" "RV_G4_VARIANT=3 RV_WALK_OCC=8" "RV_G4_VARIANT=1 RV_WALK_OCC=6"; do
-  env $env python bench.py --steps 6 --warmup 3 --e2e-steps 0 --skip-cpu 2>/dev/null | tail -1 | python -c "
-import json,sys; d=json.load(sys.stdin); print('$env', d['ms_per_step'], d['roofline']['split_ms'])"
-done
-ncu --set full --clock-control none --import-source on -k regex:"rv_walk|rv_gather4|rv_apply" -s 9 -c 3 -o gpurun_out/prof_r2_a python bench.py --steps 1 --warmup 3 --e2e-steps 0 --skip-cpu > gpurun_out/ncu_a.log 2>&1
-tail -3 gpurun_out/ncu_a.log
+python tools/parity_configs.py --configs 1,2 2>&1 | grep -v "^    " | tail -3
+cd _work/parity_c1_1002600_l1
+for i in 1 2; do ( time ../../build/rabbitvar_b200 -G ref.fa -b S.bam -N S -i tiles.bed -c 1 -S 2 -E 3 -g 4 --th 16 --out /tmp/x.tsv ) 2>&1 | grep -E "timeline|real|total"; done
+cd ../parity_c2_5002600_l1
+for w in 2 3; do ( time ../../build/rabbitvar_b200 -G ref.fa -b "T.bam|N.bam" -N "T|N" -i tiles.bed -c 1 -S 2 -E 3 -g 4 --fisher --th 16 --workers $w --out /tmp/x.tsv ) 2>&1 | grep -E "timeline|real|total|jobs"; done
+python - <<'PY'
+import torch, subprocess, time
+x = torch.zeros(1<<28, device="cuda"); torch.cuda.synchronize()
+t=time.time(); r=subprocess.run(["../../build/rabbitvar_b200","-G","ref.fa","-b","T.bam|N.bam","-N","T|N","-i","tiles.bed","-c","1","-S","2","-E","3","-g","4","--fisher","--th","16","--out","/tmp/x.tsv"],capture_output=True,text=True); print("with a torch parent holding the GPU:", time.time()-t); print(r.stdout[-400:])
+PY
