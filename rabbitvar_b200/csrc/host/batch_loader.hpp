@@ -86,8 +86,8 @@ inline void append_raw_record(ReadBatch& out, const rvio::RawRecord& r) {
   const size_t off = (out.pool.size() + 15) & ~(size_t)15;
   if ((off >> 4) > (size_t)0xffffffffu) throw std::runtime_error("read batch pool exceeds 64 GiB: use smaller region blocks");
   h.data_off16 = (uint32_t)(off / 16);
-  out.pool.resize(off + bytes);
-  if (bytes) memcpy(out.pool.data() + off, r.cigar_bytes(), bytes);
+  if (out.pool.size() != off) out.pool.resize(off);  // (padding of the previous record)
+  out.pool.insert(out.pool.end(), r.cigar_bytes(), r.cigar_bytes() + bytes);
   const int span = h.end_pos - r.pos();
   if (span > out.max_ref_span) out.max_ref_span = span;
   out.reads.push_back(h);

@@ -128,6 +128,20 @@ inline void decode_job(const FileRunConfig& c, SampleFiles* samples, int n_sampl
     clusters.back().members.push_back(order[oi]);
   }
   job->batch.clear();
+  {  // room for the job's reads up front: deflate shrinks BAM payloads ~3.5x, a record is ~300 bytes
+    int64_t cbytes = 0;
+    for (int s = 0; s < n_samples; ++s) {
+      const int tid_s = samples[s].scan.header().tid_of(chr);
+      if (tid_s < 0) continue;
+      for (size_t ci = 0; ci < clusters.size(); ++ci) {
+        const uint64_t a = bai_coffset(*samples[s].bai, tid_s, (int64_t)clusters[ci].lo - 1), b = bai_coffset(*samples[s].bai, tid_s, (int64_t)clusters[ci].hi + (1 << 14));
+        if (b > a) cbytes += (int64_t)(b - a);
+      }
+    }
+    cbytes = std::min<int64_t>(cbytes, (int64_t)1 << 30);
+    job->batch.pool.reserve((size_t)(cbytes * 4));
+    job->batch.reads.reserve((size_t)(cbytes * 4 / 250));
+  }
   job->regs.assign(job->specs.size() * (size_t)n_samples, rv_region());
   int32_t smin = job->specs[0].start, smax = job->specs[0].end;
   for (size_t i = 0; i < job->specs.size(); ++i) { smin = std::min(smin, job->specs[i].start); smax = std::max(smax, job->specs[i].end); }

@@ -10,6 +10,7 @@
 // Header-only, C++11, depends on zlib only.
 #pragma once
 #include <zlib.h>
+#include "fast_inflate.hpp"
 #include <fcntl.h>
 #include <unistd.h>
 #include <sys/stat.h>
@@ -22,6 +23,7 @@
 #include <map>
 #include <algorithm>
 #include <stdexcept>
+#include <memory>
 
 namespace rvio {
 
@@ -676,19 +678,19 @@ class SpanScanner {
     if (!bai.start_offset(tid, beg0, &voff)) return;
     caddr_ = voff >> 16;
     cbuf_lo_ = cbuf_hi_ = caddr_;
-    ubuf_.clear();
+    usize_ = 0;
     size_t cur = (size_t)(voff & 0xffff);
     bool first = true, eof = false;
     for (;;) {
       // complete records available at ubuf_[cur..]?
-      while (ubuf_.size() >= cur + 4) {
+      while (usize_ >= cur + 4) {
         int32_t bs;
-        memcpy(&bs, ubuf_.data() + cur, 4);
+        memcpy(&bs, ubuf_.get() + cur, 4);
         if (bs < 32) throw std::runtime_error("bam: record shorter than its fixed part");
         if (bs > (64 << 20)) throw std::runtime_error("bam: implausible record size");
-        if (ubuf_.size() < cur + 4 + (size_t)bs) break;
+        if (usize_ < cur + 4 + (size_t)bs) break;
         RawRecord r;
-        r.core = ubuf_.data() + cur + 4;
+        r.core = ubuf_.get() + cur + 4;
         r.block_size = bs;
         if (r.l_seq() < 0 || (size_t)r.l_qname() + r.tail_bytes() > (size_t)bs - 32)
           throw std::runtime_error("bam: record fields exceed its size");
@@ -697,18 +699,19 @@ class SpanScanner {
         cur += 4 + (size_t)bs;
       }
       if (eof) {
-        if (ubuf_.size() > cur) throw std::runtime_error("bam: truncated record at end of file");
+        if (usize_ > cur) throw std::runtime_error("bam: truncated record at end of file");
         return;
       }
       // drop what has been consumed, then append the next block
-      if (cur > (size_t)(1 << 20) || cur == ubuf_.size()) {
-        ubuf_.erase(ubuf_.begin(), ubuf_.begin() + (std::ptrdiff_t)cur);
+      if (!first && (cur > (size_t)(1 << 20) || cur == usize_)) {
+        memmove(ubuf_.get(), ubuf_.get() + cur, usize_ - cur);
+        usize_ -= cur;
         cur = 0;
       }
       if (!append_block(&eof)) eof = true;
       if (first) {
         first = false;
-        if (cur > ubuf_.size()) throw std::runtime_error("bam: index offset beyond its block");
+        if (cur > usize_) throw std::runtime_error("bam: index offset beyond its block");
       }
     }
   }
@@ -758,17 +761,27 @@ class SpanScanner {
     memcpy(&isize, def + remain - 4, 4);
     if (isize > (uint32_t)BGZF_MAX_BLOCK) throw std::runtime_error("bgzf: bad isize");
     if (isize) {
-      const size_t at = ubuf_.size();
-      ubuf_.resize(at + isize);
-      inflateReset(&zs_);
-      zs_.next_in = (Bytef*)def;
-      zs_.avail_in = (uInt)(remain - 8);
-      zs_.next_out = ubuf_.data() + at;
-      zs_.avail_out = isize;
-      const int rc = inflate(&zs_, Z_FINISH);
-      if (rc != Z_STREAM_END || zs_.total_out != isize) throw std::runtime_error("bgzf: inflate failed");
-      if (check_crc_ && (uint32_t)crc32(crc32(0L, Z_NULL, 0), ubuf_.data() + at, isize) != crc_want)
-        throw std::runtime_error("bgzf: CRC mismatch");
+      const size_t at = usize_;
+      if (at + isize > ucap_) {  // (no zero-fill: the decoder overwrites every byte it reports)
+        const size_t cap = std::max<size_t>(2 * ucap_, at + isize + (size_t)(4 << 20));
+        std::unique_ptr<uint8_t[]> nb(new uint8_t[cap]);
+        if (at) memcpy(nb.get(), ubuf_.get(), at);
+        ubuf_.swap(nb);
+        ucap_ = cap;
+      }
+      // the block decoder of fast_inflate.hpp; zlib only when it refuses a stream (never seen on a BGZF file)
+      if (!fast_) fast_.reset(new FastInflate());
+      if (fast_->inflate(def, (size_t)(remain - 8), ubuf_.get() + at, isize) != (long)isize) {
+        inflateReset(&zs_);
+        zs_.next_in = (Bytef*)def;
+        zs_.avail_in = (uInt)(remain - 8);
+        zs_.next_out = ubuf_.get() + at;
+        zs_.avail_out = isize;
+        const int rc = inflate(&zs_, Z_FINISH);
+        if (rc != Z_STREAM_END || zs_.total_out != isize) throw std::runtime_error("bgzf: inflate failed");
+      }
+      if (check_crc_ && fast_crc32(ubuf_.get() + at, isize) != crc_want) throw std::runtime_error("bgzf: CRC mismatch");
+      usize_ = at + isize;
     }
     caddr_ += (uint64_t)bsize;
     return true;
@@ -778,7 +791,10 @@ class SpanScanner {
   BamHeader hdr_;
   z_stream zs_;
   bool zinit_, check_crc_;
-  std::vector<uint8_t> cbuf_, ubuf_;
+  std::unique_ptr<FastInflate> fast_;
+  std::vector<uint8_t> cbuf_;
+  std::unique_ptr<uint8_t[]> ubuf_;  // inflated stream, sliding
+  size_t usize_ = 0, ucap_ = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
