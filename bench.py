@@ -300,7 +300,7 @@ def main():
     bases_per_step = st.n_aligned_bases
     kept_per_step = st.n_reads_kept
     log(f"[bench r{rank}] pileup: {st.n_items} work items, {st.n_reads_kept} kept, {st.n_walk_items} walked "
-        f"({st.n_walk_full} whole reads), {st.n_events} events, {st.n_unsupported} unsupported, {st.n_clipped} clipped")
+        f"({st.n_walk_segments} plain segments, {st.n_sparse_obs} sparse observations), {st.n_events} events, {st.n_unsupported} unsupported, {st.n_clipped} clipped")
     # sparse keys of this batch (identical every step): reduce once on the host, keep the patch resident
     ctx.install_patch_from_events(bt, regs, ref, ref_lo)
     ctx.score()

@@ -268,6 +268,8 @@ typedef struct rv_pileup_stats {
                                matched bases themselves are only ever counted inside the region (parseCigar.cpp:884) */
   int64_t n_score_unsupported; /* positions where createInsertion would edit the neighbouring position's reference
                                allele (ToVarsBuilder.cpp:405-415): counted by the last scoring call */
+  int64_t n_sparse_obs;     /* observations of walked reads added with global atomics (rv_apply_kernel) ... */
+  int64_t n_walk_segments;  /* ... and plain matched stretches of walked reads handed to the gather kernel instead */
 } rv_pileup_stats;
 int rv_get_pileup_stats(rv_ctx* ctx, rv_pileup_stats* out);
 /* maxReadLength per region after the pileup (parseCigar.cpp:598-601). */

@@ -98,7 +98,7 @@ class PileupStats(C.Structure):
     _fields_ = [("n_items", C.c_int64), ("n_reads_kept", C.c_int64), ("n_aligned_bases", C.c_int64),
                 ("n_events", C.c_int64), ("n_overflow", C.c_int64), ("n_unsupported", C.c_int64),
                 ("n_walk_items", C.c_int64), ("n_walk_full", C.c_int64), ("n_clipped", C.c_int64),
-                ("n_score_unsupported", C.c_int64)]
+                ("n_score_unsupported", C.c_int64), ("n_sparse_obs", C.c_int64), ("n_walk_segments", C.c_int64)]
 
 
 class Timing(C.Structure):

@@ -722,6 +722,146 @@ RV_HDN bool scan_plain_segment(const rv_params& P, const ReadView& rd, const Ref
   return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// 4-bit reference packing and the nibble-SIMD plain-stretch proof (device: rv_pileup_kernel, rv_walk_kernel; host: the
+// single-stepping test tool checks it against scan_plain_segment on every stretch).
+// Packed reference: base e of the slice in bits 28 - 4 * (e & 7) of word e >> 3, BAM codes A=1 C=2 G=4 T=8, other=15,
+// beyond the slice 0.
+// ------------------------------------------------------------------------------------------------
+RV_HD uint32_t rv_funnel_l(uint32_t lo, uint32_t hi, int s) {  // upper 32 bits of (hi:lo) << s, 0 <= s < 32
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(lo, hi, s);
+#else
+  return s ? (hi << s) | (lo >> (32 - s)) : hi;
+#endif
+}
+RV_HD uint32_t rv_funnel_r(uint32_t lo, uint32_t hi, int s) {  // lower 32 bits of (hi:lo) >> s
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, s);
+#else
+  return s ? (lo >> s) | (hi << (32 - s)) : lo;
+#endif
+}
+RV_HD uint32_t rv_bswap32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(v, 0, 0x0123);
+#else
+  return (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24);
+#endif
+}
+RV_HD int rv_clz32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return __clz((int)v);
+#else
+  return v ? __builtin_clz(v) : 32;
+#endif
+}
+RV_HD uint32_t pack_ref8(const char* ref, int64_t n, int64_t w) {  // word w of the packed slice
+  uint32_t v = 0;
+  for (int i = 0; i < 8; ++i) {
+    const int64_t e = w * 8 + i;
+    uint32_t code = 0;  // beyond the slice: equal to no read base
+    if (e < n) {
+      const char c = ref[e];
+      code = c == 'A' ? 1u : c == 'C' ? 2u : c == 'G' ? 4u : c == 'T' ? 8u : 15u;
+    }
+    v |= code << (28 - 4 * i);
+  }
+  return v;
+}
+RV_HD int nib_allele(int nib) { return (nib >> 1) - (nib >> 3); }  // 1,2,4,8 -> 0,1,2,3
+
+// bit 0 of every nibble = OR of the nibble's four bits
+RV_HD uint32_t nib_any(uint32_t x) { return (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u; }
+
+// The nibble-SIMD plain-run proof.  The matched stretch [rp0, rp0 + ml) of a read is compared with the reference 8
+// bases per step: BAM's 4-bit bases XOR the 4-bit reference (funnel-shifted to the read's phase) give one mismatch flag
+// per nibble; shifted copies of the flag word, carried across words, prove that no two mismatches lie within D = vext + 1
+// bases, i.e. that no base of the stretch can start a multi-nucleotide key (parseCigar.cpp:711-768).  Read bases other
+// than A, C, G, T make the stretch not plain.  Returns bad == 0 (more than eight mismatches are left to the caller);
+// mismatches are listed as 0x8000 | offset << 2 | allele, 16 bits each, the newest in the low bits.
+// sq: the read's packed bases (word 0 = bases 0..7); E0: reference-slice index of read base 0 (>= 0).
+struct PlainScan {
+  uint32_t mm_blocks;
+  unsigned long long ml_lo, ml_hi;
+  int ml_n;
+  uint32_t special;  // a read base that is not A, C, G, T was seen
+};
+RV_HD bool simd_plain_scan(const uint32_t* sq, const uint32_t* ref4, int E0, int rp0, int ml, int D,
+                                                PlainScan* out) {
+  const int w_first = rp0 >> 3, w_last = (rp0 + ml - 1) >> 3;
+  const int e = E0 + 8 * w_first;
+  const int sh = (e & 7) * 4;
+  const uint32_t* rw = ref4 + (e >> 3);
+  uint32_t r_lo = rw[0];
+  uint32_t prev = 0, bad = 0, seen = 0, spec = 0, mm_blocks = 0;
+  unsigned long long ml_lo = 0, ml_hi = 0;
+  int ml_n = 0;
+  for (int wi = w_first; wi <= w_last; ++wi) {
+    const uint32_t r_hi = *++rw;
+    const uint32_t rf = rv_funnel_l(r_hi, r_lo, sh);
+    r_lo = r_hi;
+    const uint32_t b8 = rv_bswap32(sq[wi]);  // base 8*wi in the top nibble
+    uint32_t vm = 0xffffffffu;
+    if (wi == w_first) vm >>= 4 * (rp0 & 7);
+    if (wi == w_last) {
+      const int hi = ((rp0 + ml - 1) & 7) + 1;
+      if (hi < 8) vm &= ~(0xffffffffu >> (4 * hi));
+    }
+    const uint32_t nz = nib_any(b8 ^ rf) & vm;
+    // read bases other than A, C, G, T (N included): zero nibble, or more than one bit in the nibble
+    // (the nibble-wise x & (x - 1) borrows out of a zero nibble: nibbles outside the stretch are forced to 1 first, so
+    // that a zero there — padding, or the byte that follows the packed bases — cannot taint its neighbour)
+    const uint32_t b8s = (b8 & vm) | (0x11111111u & ~vm);
+    const uint32_t special = (~nib_any(b8s) | nib_any(b8s & (b8s - 0x11111111u))) & 0x11111111u & vm;
+    uint32_t near;
+    if (D == 3) {
+      near = nz & (rv_funnel_r(nz, prev, 4) | rv_funnel_r(nz, prev, 8) | rv_funnel_r(nz, prev, 12));
+    } else if (D <= 7) {
+      near = 0;
+      for (int d = 1; d <= D; ++d) near |= nz & rv_funnel_r(nz, prev, 4 * d);
+    } else {
+      near = (nz & (nz - 1)) | ((nz && seen) ? 1u : 0u);  // conservative: any two mismatches in the stretch
+      seen |= nz;
+    }
+    bad |= near | special;
+    spec |= special;
+    prev = nz;
+    if (nz) {  // 16-base blocks of the stretch this word's mismatches may lie in (a word touches at most two)
+      const int k_lo = 8 * wi - rp0 > 0 ? 8 * wi - rp0 : 0;
+      const int k_hi = 8 * wi + 7 - rp0 < ml - 1 ? 8 * wi + 7 - rp0 : ml - 1;
+      mm_blocks |= (1u << ((k_lo >> 4) < 15 ? (k_lo >> 4) : 15)) | (1u << ((k_hi >> 4) < 15 ? (k_hi >> 4) : 15));
+      for (uint32_t z = nz; z;) {  // the mismatches themselves: base 8*wi + i has its flag at bit 28 - 4i
+        const int i = rv_clz32(z) >> 2;
+        z &= ~(0x10000000u >> (4 * i));
+        const uint32_t en = 0x8000u | ((uint32_t)(8 * wi + i - rp0) << 2) | ((uint32_t)nib_allele((b8 >> (28 - 4 * i)) & 15u) & 3u);
+        ml_hi = (ml_hi << 16) | (ml_lo >> 48);
+        ml_lo = (ml_lo << 16) | en;
+        ml_n++;
+      }
+    }
+  }
+  out->mm_blocks = mm_blocks;
+  out->ml_lo = ml_lo;
+  out->ml_hi = ml_hi;
+  out->ml_n = ml_n;
+  out->special = spec;
+  return bad == 0;
+}
+// is any listed mismatch among the first `head` or the last `tail` bases of a stretch of ml bases?
+RV_HD bool mismatch_near_ends(const PlainScan& ps, int ml, int head, int tail) {
+  unsigned long long lo = ps.ml_lo, hi = ps.ml_hi;
+  const int n = ps.ml_n < 8 ? ps.ml_n : 8;
+  for (int j = 0; j < n; ++j) {
+    const int k = (int)((lo >> 2) & 0x1fffu);
+    if (k < head || k >= ml - tail) return true;
+    lo = (lo >> 16) | (hi << 48);
+    hi >>= 16;
+  }
+  return ps.ml_n > 8;  // more mismatches than the list holds: unknown, say yes
+}
+
+
 struct WalkState {
   int start, rp, re, offset, clen;  // start, readPositionIncluding/ExcludingSoftClipped, offset, cigar_element_length
   int seq_no;

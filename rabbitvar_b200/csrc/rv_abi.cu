@@ -44,6 +44,8 @@ struct DevStats {  // (must fit the first 128 bytes of the counter block)
   unsigned long long n_items, n_kept, n_bases, n_events, n_overflow, n_unsupported, n_variants, n_score_unsupported;
   unsigned long long n_walk_items, n_walk_full;
   unsigned long long n_clipped;  // observations outside [start - halo, end + halo]: dropped, like the gather path clips
+  unsigned long long n_sparse;   // SparseObs entries the walk kernel left for rv_apply_kernel
+  unsigned long long n_segments; // gather descriptors written by the walk kernel
 };
 
 // Gather descriptor of one plain matched segment (rvk::scan_plain_segment / the plain-run proof of rv_pileup_kernel):
@@ -125,95 +127,6 @@ struct DeviceSink {
   __device__ __forceinline__ void kept(int aligned) { if (!mute) { kept_bases += aligned; n_kept++; } }
   __device__ __forceinline__ void unsupported() { if (!mute) n_unsup++; }
 };
-
-__device__ __forceinline__ int nib_allele(int nib) { return (nib >> 1) - (nib >> 3); }  // 1,2,4,8 -> 0,1,2,3
-
-// bit 0 of every nibble = OR of the nibble's four bits
-__device__ __forceinline__ uint32_t nib_any(uint32_t x) { return (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u; }
-
-// The nibble-SIMD plain-run proof.  The matched stretch [rp0, rp0 + ml) of a read is compared with the reference 8
-// bases per step: BAM's 4-bit bases XOR the 4-bit reference (funnel-shifted to the read's phase) give one mismatch flag
-// per nibble; shifted copies of the flag word, carried across words, prove that no two mismatches lie within D = vext + 1
-// bases, i.e. that no base of the stretch can start a multi-nucleotide key (parseCigar.cpp:711-768).  Read bases other
-// than A, C, G, T make the stretch not plain.  Returns bad == 0 (more than eight mismatches are left to the caller);
-// mismatches are listed as 0x8000 | offset << 2 | allele, 16 bits each, the newest in the low bits.
-// sq: the read's packed bases (word 0 = bases 0..7); E0: reference-slice index of read base 0 (>= 0).
-struct PlainScan {
-  uint32_t mm_blocks;
-  unsigned long long ml_lo, ml_hi;
-  int ml_n;
-  uint32_t special;  // a read base that is not A, C, G, T was seen
-};
-__device__ __forceinline__ bool simd_plain_scan(const uint32_t* sq, const uint32_t* ref4, int E0, int rp0, int ml, int D,
-                                                PlainScan* out) {
-  const int w_first = rp0 >> 3, w_last = (rp0 + ml - 1) >> 3;
-  const int e = E0 + 8 * w_first;
-  const int sh = (e & 7) * 4;
-  const uint32_t* rw = ref4 + (e >> 3);
-  uint32_t r_lo = rw[0];
-  uint32_t prev = 0, bad = 0, seen = 0, spec = 0, mm_blocks = 0;
-  unsigned long long ml_lo = 0, ml_hi = 0;
-  int ml_n = 0;
-  for (int wi = w_first; wi <= w_last; ++wi) {
-    const uint32_t r_hi = *++rw;
-    const uint32_t rf = __funnelshift_l(r_hi, r_lo, sh);
-    r_lo = r_hi;
-    const uint32_t b8 = __byte_perm(sq[wi], 0, 0x0123);  // base 8*wi in the top nibble
-    uint32_t vm = 0xffffffffu;
-    if (wi == w_first) vm >>= 4 * (rp0 & 7);
-    if (wi == w_last) {
-      const int hi = ((rp0 + ml - 1) & 7) + 1;
-      if (hi < 8) vm &= ~(0xffffffffu >> (4 * hi));
-    }
-    const uint32_t nz = nib_any(b8 ^ rf) & vm;
-    // read bases other than A, C, G, T (N included): zero nibble, or more than one bit in the nibble
-    const uint32_t special = (~nib_any(b8) | nib_any(b8 & (b8 - 0x11111111u))) & 0x11111111u & vm;
-    uint32_t near;
-    if (D == 3) {
-      near = nz & (__funnelshift_r(nz, prev, 4) | __funnelshift_r(nz, prev, 8) | __funnelshift_r(nz, prev, 12));
-    } else if (D <= 7) {
-      near = 0;
-      for (int d = 1; d <= D; ++d) near |= nz & __funnelshift_r(nz, prev, 4 * d);
-    } else {
-      near = (nz & (nz - 1)) | ((nz && seen) ? 1u : 0u);  // conservative: any two mismatches in the stretch
-      seen |= nz;
-    }
-    bad |= near | special;
-    spec |= special;
-    prev = nz;
-    if (nz) {  // 16-base blocks of the stretch this word's mismatches may lie in (a word touches at most two)
-      const int k_lo = 8 * wi - rp0 > 0 ? 8 * wi - rp0 : 0;
-      const int k_hi = 8 * wi + 7 - rp0 < ml - 1 ? 8 * wi + 7 - rp0 : ml - 1;
-      mm_blocks |= (1u << min(k_lo >> 4, 15)) | (1u << min(k_hi >> 4, 15));
-      for (uint32_t z = nz; z;) {  // the mismatches themselves: base 8*wi + i has its flag at bit 28 - 4i
-        const int i = __clz(z) >> 2;
-        z &= ~(0x10000000u >> (4 * i));
-        const uint32_t en = 0x8000u | ((uint32_t)(8 * wi + i - rp0) << 2) | ((uint32_t)nib_allele((b8 >> (28 - 4 * i)) & 15u) & 3u);
-        ml_hi = (ml_hi << 16) | (ml_lo >> 48);
-        ml_lo = (ml_lo << 16) | en;
-        ml_n++;
-      }
-    }
-  }
-  out->mm_blocks = mm_blocks;
-  out->ml_lo = ml_lo;
-  out->ml_hi = ml_hi;
-  out->ml_n = ml_n;
-  out->special = spec;
-  return bad == 0;
-}
-// is any listed mismatch among the first `head` or the last `tail` bases of a stretch of ml bases?
-__device__ __forceinline__ bool mismatch_near_ends(const PlainScan& ps, int ml, int head, int tail) {
-  unsigned long long lo = ps.ml_lo, hi = ps.ml_hi;
-  const int n = ps.ml_n < 8 ? ps.ml_n : 8;
-  for (int j = 0; j < n; ++j) {
-    const int k = (int)((lo >> 2) & 0x1fffu);
-    if (k < head || k >= ml - tail) return true;
-    lo = (lo >> 16) | (hi << 48);
-    hi >>= 16;
-  }
-  return ps.ml_n > 8;  // more mismatches than the list holds: unknown, say yes
-}
 
 // Sink of rv_walk_kernel: nothing is added to the tables here.  Plain segments become gather descriptors, everything
 // else a SparseObs for rv_apply_kernel or an event for the host stage.
@@ -332,17 +245,7 @@ __device__ __forceinline__ int find_region(const DevRegion* regs, int n, int64_t
 __global__ void rv_pack_ref_kernel(const char* ref, int64_t n, uint32_t* out, int64_t n_words) {
   int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= n_words) return;
-  uint32_t v = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int64_t e = w * 8 + i;
-    uint32_t code = 0;  // beyond the slice: equal to no read base
-    if (e < n) {
-      const char c = ref[e];
-      code = c == 'A' ? 1u : c == 'C' ? 2u : c == 'G' ? 4u : c == 'T' ? 8u : 15u;
-    }
-    v |= code << (28 - 4 * i);
-  }
+  const uint32_t v = pack_ref8(ref, n, w);
   out[w] = v;
 }
 
@@ -498,7 +401,7 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(128, MIN_CTAS) rv_walk_kernel(PileupArgs a) {
   const unsigned long long n = a.walk_count[0];
-  unsigned long long over = 0, unsup = 0, clip = 0, kept = 0, bases = 0;
+  unsigned long long over = 0, unsup = 0, clip = 0, kept = 0, bases = 0, segs = 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) { a.stats->n_walk_items = n; a.stats->n_walk_full = n; }
   const int lane = threadIdx.x & 31;
   for (;;) {
@@ -554,7 +457,9 @@ __global__ void __launch_bounds__(128, MIN_CTAS) rv_walk_kernel(PileupArgs a) {
     over += s.n_over;
     unsup += s.n_unsup;
     clip += s.n_clip;
+    segs += s.n_seg;
   }
+  if (segs) atomicAdd(&a.stats->n_segments, segs);
   if (clip) atomicAdd(&a.stats->n_clipped, clip);
   if (over) atomicAdd(&a.stats->n_overflow, over);
   if (unsup) atomicAdd(&a.stats->n_unsupported, unsup);
@@ -565,8 +470,9 @@ __global__ void __launch_bounds__(128, MIN_CTAS) rv_walk_kernel(PileupArgs a) {
 // The SparseObs list onto the tables (after the gather kernel has stored every row): one entry per thread.
 __device__ __forceinline__ void row_observe(uint32_t* row, uint32_t dir, uint32_t tp, uint32_t q, uint32_t mapq, uint32_t nm, int thr);
 __global__ void __launch_bounds__(256) rv_apply_kernel(const SparseObs* list, const unsigned long long* count, unsigned long long cap,
-                                                        uint32_t* counts, uint32_t* cov, int thr) {
+                                                        uint32_t* counts, uint32_t* cov, int thr, DevStats* stats) {
   unsigned long long n = *count;
+  if (blockIdx.x == 0 && threadIdx.x == 0) stats->n_sparse = n;
   if (n > cap) n = cap;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * blockDim.x) {
@@ -1883,7 +1789,7 @@ int rv_pileup(rv_ctx* ctx) {
   // 4. the SparseObs list onto the tables
   if (ctx->n_items > 0) {
     rv_apply_kernel<<<ctx->n_sms * 8, 256, 0, ctx->stream>>>(ctx->d_sparse, ctx->d_sparse_count, (unsigned long long)ctx->max_sparse,
-                                                           ctx->d_counts, ctx->d_cov, (int)ceil(ctx->P.goodq));
+                                                           ctx->d_counts, ctx->d_cov, (int)ceil(ctx->P.goodq), ctx->d_stats);
     ctx->launches++;
     CK(cudaGetLastError());
   }
@@ -1917,6 +1823,8 @@ int rv_get_pileup_stats(rv_ctx* ctx, rv_pileup_stats* o) {
   o->n_walk_full = (int64_t)ctx->h_stats.n_walk_full;
   o->n_clipped = (int64_t)ctx->h_stats.n_clipped;
   o->n_score_unsupported = (int64_t)ctx->h_stats.n_score_unsupported;
+  o->n_sparse_obs = (int64_t)ctx->h_stats.n_sparse;
+  o->n_walk_segments = (int64_t)ctx->h_stats.n_segments;
   return RV_OK;
 }
 

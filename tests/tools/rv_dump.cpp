@@ -31,7 +31,10 @@ struct SimSink {
     if (!R->in_table(pos)) { over++; return false; }
     return true;
   }
+  long n_direct = 0, n_adj = 0, n_cov = 0, n_segbases = 0;
+  bool in_segment = false;
   void single(int pos, int allele, bool dir, int tp, int q, int mapq, int nm) {
+    if (!in_segment) n_direct++;
     if (getenv("RV_DEBUG_POS") && atoi(getenv("RV_DEBUG_POS")) == pos) fprintf(stderr, "single pos %d al %d dir %d tp %d q %d mapq %d nm %d\n", pos, allele, dir, tp, q, mapq, nm);
     if (!idx(pos)) return;
     uint32_t* row = R->row(pos, allele);
@@ -50,6 +53,7 @@ struct SimSink {
     }
   }
   void adj(int pos, int allele, int sign, bool dir, int tp, int q, int mapq, int nm) {
+    n_adj++;
     if (getenv("RV_DEBUG_POS") && atoi(getenv("RV_DEBUG_POS")) == pos) fprintf(stderr, "adj pos %d al %d sign %d dir %d tp %d q %d\n", pos, allele, sign, dir, tp, q);
     if (!idx(pos)) return;
     uint32_t* row = R->row(pos, allele);
@@ -61,6 +65,7 @@ struct SimSink {
     if ((double)q >= goodq) row[RV_F_HI] += (uint32_t)sign;
   }
   void cov(int pos) {
+    if (!in_segment) n_cov++;
     if (!idx(pos)) return;
     R->cov[pos - R->first_pos]++;
   }
@@ -73,13 +78,38 @@ struct SimSink {
   bool use_segments;
   bool scan_segment(const rv_params& P, const rvk::ReadView& rd, const rvk::RefView& ref, int m_start, int rp, int len,
                     bool indel_follows, rvk::SegDesc* out) {
-    return use_segments && rvk::scan_plain_segment(P, rd, ref, m_start, rp, len, indel_follows, out);
+    if (!use_segments) return false;
+    const bool plain = rvk::scan_plain_segment(P, rd, ref, m_start, rp, len, indel_follows, out);
+    if (ref4) {  // cross-check: the nibble-SIMD proof the kernels use must decide (and list) the same
+      bool simd = false;
+      rvk::PlainScan ps;
+      const int E0 = m_start - rp - ref.base_pos;
+      const int64_t w_lo = ref.lo > ref.base_pos ? ref.lo : ref.base_pos;
+      const int64_t w_hi = (int64_t)ref.hi < ref.base_pos + ref.n - 1 ? (int64_t)ref.hi : ref.base_pos + ref.n - 1;
+      if (len > 0 && len <= 8192 && E0 >= 0 && m_start >= w_lo && (int64_t)m_start + len - 1 <= w_hi && ((uintptr_t)rd.seq4 & 3) == 0) {
+        simd = rvk::simd_plain_scan((const uint32_t*)rd.seq4, ref4, E0, rp, len, P.vext + 1, &ps) && ps.ml_n <= 8;
+        if (simd && indel_follows && P.local_realign && rvk::mismatch_near_ends(ps, len, 0, P.vext)) simd = false;
+      }
+      n_scan++;
+      if (simd != plain && getenv("RV_SCAN_DEBUG"))
+        fprintf(stderr, "scan diff: pos %d rp %d len %d indel_follows %d plain %d simd %d n_mm scalar %d simd %d E0 %d\n", m_start, rp, len, (int)indel_follows,
+                (int)plain, (int)simd, plain ? out->n_mm : -1, ps.ml_n, E0);
+      if (simd != plain) n_scan_diff++;
+      else if (plain && ((ps.mm_blocks != 0) != (out->mm_blocks != 0) || (uint32_t)ps.ml_lo != out->ml[0] || (uint32_t)(ps.ml_lo >> 32) != out->ml[1] ||
+                         (uint32_t)ps.ml_hi != out->ml[2] || (uint32_t)(ps.ml_hi >> 32) != out->ml[3]))
+        n_scan_diff++;
+    }
+    return plain;
   }
+  const uint32_t* ref4 = NULL;
+  long n_scan = 0, n_scan_diff = 0;
   bool segment(const rvk::SegDesc& d, bool dir, int mapq, int nm) {
     if (!use_segments) return false;
     const uint8_t* var = cur_pool + (size_t)cur_read->data_off16 * 16;
     const uint8_t* seq4 = var + 4 * (size_t)cur_read->n_cigar;
     const uint8_t* qual = seq4 + ((cur_read->l_seq + 1) >> 1);
+    in_segment = true;
+    n_segbases += d.len;
     for (int k = 0; k < d.len; ++k) {
       const int p = d.m_start + k;
       if (p < r_start || p > r_end) continue;
@@ -91,6 +121,7 @@ struct SimSink {
       single(p, al, dir, up < dn ? up : dn, qual[r], mapq, nm);
       cov(p);
     }
+    in_segment = false;
     return true;
   }
   void max_read_len(int t) { if (t > R->max_read_len) R->max_read_len = t; }
@@ -240,6 +271,9 @@ int main(int argc, char** argv) {
     ref.bases = refseq.data();
     ref.base_pos = ref_lo;
     ref.n = (int64_t)refseq.size();
+    std::vector<uint32_t> ref4((size_t)ref.n / 8 + 16);
+    for (size_t w = 0; w < ref4.size(); ++w) ref4[w] = rvk::pack_ref8(refseq.data(), ref.n, (int64_t)w);
+    long n_scan = 0, n_scan_diff = 0;
     for (size_t r = 0; r < regs.size(); ++r) {
       RegionPileup& R = rp[r];
       R.region_idx = (int)r;
@@ -256,6 +290,7 @@ int main(int argc, char** argv) {
       s.kept_reads = s.kept_bases = s.unsup = s.over = 0;
       const bool use_fast = getenv("RV_NO_GATHER") == NULL;
       s.use_segments = use_fast && getenv("RV_NO_SEGMENTS") == NULL;
+      s.ref4 = ref4.data();
       s.cur_pool = batch.pool.data();
       s.r_start = regs[r].start;
       s.r_end = regs[r].end;
@@ -268,7 +303,9 @@ int main(int argc, char** argv) {
         rvk::FastDesc d;
         memset(&d, 0, sizeof d);
         s.cur_read = &rd;
-        rvk::process_read(P, regs[r], (int)r, rd, batch.pool.data(), ref, (uint32_t)i, s, use_fast ? &d : (rvk::FastDesc*)0);
+        // RV_SIM_NO_FASTDESC=1: every read goes the way rv_walk_kernel takes (plain stretches through scan_segment)
+        static const bool no_fastdesc = getenv("RV_SIM_NO_FASTDESC") != NULL;
+        rvk::process_read(P, regs[r], (int)r, rd, batch.pool.data(), ref, (uint32_t)i, s, (use_fast && !no_fastdesc) ? &d : (rvk::FastDesc*)0);
         if (d.m_len) descs.push_back(d);
       }
       // the gather kernel's work, position by position
@@ -284,7 +321,11 @@ int main(int argc, char** argv) {
       }
       st.n_reads_kept += s.kept_reads; st.n_aligned_bases += s.kept_bases;
       st.n_unsupported += s.unsup; st.n_overflow += s.over;
+      n_scan += s.n_scan; n_scan_diff += s.n_scan_diff;
+      if (getenv("RV_SCAN_DEBUG")) fprintf(stderr, "region %zu: per-base singles %ld, adj %ld, cov %ld, segment bases %ld\n", r, s.n_direct, s.n_adj, s.n_cov, s.n_segbases);
     }
+    fprintf(stderr, "rv_dump[sim]: %ld stretches scanned, %ld where the nibble-SIMD proof and the scalar scan disagree\n", n_scan, n_scan_diff);
+    if (n_scan_diff) return 4;
     st.n_events = (int64_t)events.size();
   } else {
     rv_limits L;

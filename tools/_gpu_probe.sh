@@ -1,10 +1,5 @@
-python tools/parity_configs.py --configs 1,2 2>&1 | grep -v "^    " | tail -3
-cd _work/parity_c1_1002600_l1
-for i in 1 2; do ( time ../../build/rabbitvar_b200 -G ref.fa -b S.bam -N S -i tiles.bed -c 1 -S 2 -E 3 -g 4 --th 16 --out /tmp/x.tsv ) 2>&1 | grep -E "timeline|real|total"; done
-cd ../parity_c2_5002600_l1
-for w in 2 3; do ( time ../../build/rabbitvar_b200 -G ref.fa -b "T.bam|N.bam" -N "T|N" -i tiles.bed -c 1 -S 2 -E 3 -g 4 --fisher --th 16 --workers $w --out /tmp/x.tsv ) 2>&1 | grep -E "timeline|real|total|jobs"; done
-python - <<'PY'
-import torch, subprocess, time
-x = torch.zeros(1<<28, device="cuda"); torch.cuda.synchronize()
-t=time.time(); r=subprocess.run(["../../build/rabbitvar_b200","-G","ref.fa","-b","T.bam|N.bam","-N","T|N","-i","tiles.bed","-c","1","-S","2","-E","3","-g","4","--fisher","--th","16","--out","/tmp/x.tsv"],capture_output=True,text=True); print("with a torch parent holding the GPU:", time.time()-t); print(r.stdout[-400:])
-PY
+python bench.py --steps 4 --warmup 3 --e2e-steps 0 --parity none --skip-cpu 2> gpurun_out/bench_f.err | tail -1 | python -c "
+import json,sys; d=json.load(sys.stdin); print(d['ms_per_step'], d['roofline']['split_ms'])"
+grep pileup: gpurun_out/bench_f.err
+ncu --set full --clock-control none --import-source on -k regex:"rv_walk|rv_apply|rv_pileup_kernel" -s 9 -c 3 -o gpurun_out/prof_r2_b python bench.py --steps 1 --warmup 3 --e2e-steps 0 --parity none --skip-cpu > gpurun_out/ncu_b.log 2>&1
+tail -2 gpurun_out/ncu_b.log
