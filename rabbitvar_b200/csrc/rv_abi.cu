@@ -75,6 +75,7 @@ struct SparseObs {      // 16 bytes
   uint32_t pad2;
 };
 enum { SO_SINGLE = 0, SO_ADD = 1, SO_SUB = 2, SO_COV = 3 };
+static const int SPARSE_CHUNK = 32;  // (tab == 0xffffffff marks an unused slot of a chunk)
 
 struct PileupArgs {
   rv_params P;
@@ -148,13 +149,17 @@ struct ListSink {
     n_pos = r->n_pos;
     tab_off = r->tab_off;
   }
+  // list slots are reserved SPARSE_CHUNK at a time per lane (one atomic on the shared cursor per chunk, nothing to
+  // wait for in between); what a lane has left over when the kernel ends is filled with no-op entries (flush)
+  unsigned long long slot_next, slot_end;
   __device__ __forceinline__ void put(int pos, uint32_t flags, int tp, int q, int mapq, int nm) {
     const int i = pos - first_pos;
     if (i < 0 || i >= n_pos) { n_clip++; return; }
-    cg::coalesced_group g = cg::coalesced_threads();
-    unsigned long long slot = 0;
-    if (g.thread_rank() == 0) slot = atomicAdd(a->sparse_count, (unsigned long long)g.size());
-    slot = g.shfl(slot, 0) + g.thread_rank();
+    if (slot_next == slot_end) {
+      slot_next = atomicAdd(a->sparse_count, (unsigned long long)SPARSE_CHUNK);
+      slot_end = slot_next + SPARSE_CHUNK;
+    }
+    const unsigned long long slot = slot_next++;
     if (slot >= a->max_sparse) { n_over++; return; }
     uint4 v;
     v.x = (uint32_t)(tab_off + i);
@@ -162,6 +167,10 @@ struct ListSink {
     v.z = ((uint32_t)nm & 0xffffu) | (flags << 16);
     v.w = 0;
     *(uint4*)(a->sparse + slot) = v;
+  }
+  __device__ __forceinline__ void flush() {
+    for (; slot_next < slot_end; ++slot_next)
+      if (slot_next < a->max_sparse) *(uint4*)(a->sparse + slot_next) = make_uint4(0xffffffffu, 0u, 0u, 0u);
   }
   __device__ __forceinline__ void single(int pos, int allele, bool dir, int tp, int q, int mapq, int nm) {
     put(pos, (uint32_t)allele | (dir ? 4u : 0u) | (SO_SINGLE << 3), tp, q, mapq, nm);
@@ -404,6 +413,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) rv_walk_kernel(PileupArgs a) {
   unsigned long long over = 0, unsup = 0, clip = 0, kept = 0, bases = 0, segs = 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) { a.stats->n_walk_items = n; a.stats->n_walk_full = n; }
   const int lane = threadIdx.x & 31;
+  unsigned long long slot_next = 0, slot_end = 0;  // this lane's reserved stretch of the SparseObs list
   for (;;) {
     unsigned long long q0 = 0;
     if (lane == 0) q0 = atomicAdd(a.walk_count + 2, 32ull);
@@ -436,6 +446,8 @@ __global__ void __launch_bounds__(128, MIN_CTAS) rv_walk_kernel(PileupArgs a) {
     s.rd = &rd;
     s.pool_off = (int64_t)rd.data_off16 * 16 - dr->pool_bias;
     s.n_unsup = s.n_over = s.n_clip = s.n_ev = 0;
+    s.slot_next = slot_next;
+    s.slot_end = slot_end;
     Prep pr;
     pr.ok = false;
     pr.n_cigar = 0;
@@ -458,7 +470,11 @@ __global__ void __launch_bounds__(128, MIN_CTAS) rv_walk_kernel(PileupArgs a) {
     unsup += s.n_unsup;
     clip += s.n_clip;
     segs += s.n_seg;
+    slot_next = s.slot_next;
+    slot_end = s.slot_end;
   }
+  for (; slot_next < slot_end; ++slot_next)  // unused slots of the last chunk
+    if (slot_next < a.max_sparse) *(uint4*)(a.sparse + slot_next) = make_uint4(0xffffffffu, 0u, 0u, 0u);
   if (segs) atomicAdd(&a.stats->n_segments, segs);
   if (clip) atomicAdd(&a.stats->n_clipped, clip);
   if (over) atomicAdd(&a.stats->n_overflow, over);
@@ -477,6 +493,7 @@ __global__ void __launch_bounds__(256) rv_apply_kernel(const SparseObs* list, co
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * blockDim.x) {
     const uint4 v = *(const uint4*)(list + i);
+    if (v.x == 0xffffffffu) continue;  // unused slot of a lane's chunk
     const uint32_t flags = v.z >> 16, kind = (flags >> 3) & 3u;
     if (kind == SO_COV) { atomicAdd(cov + v.x, 1u); continue; }
     uint32_t* row = counts + ((size_t)v.x * 4 + (flags & 3u)) * RV_ROW_U32;
@@ -589,6 +606,7 @@ struct G4Warp {
   uint2 rec2[32 + 2 * G4_PF];     // segments that are not a whole read: {-(s+B) + re0 x2, (s+L+1+B) + tail x2} (tp of the SIMD pass)
   uint8_t excl[32][32];           // [record][lane]: bit j = position j of the lane is masked out of the SIMD pass
   uint32_t d_n[G4_W + 4], c_n[G4_W + 4], d_rev[G4_W + 4], d_mapq[G4_W + 4], d_nm[G4_W + 4], d_tp1[G4_W + 4], d_tp2[G4_W + 4];
+  uint32_t g_tp[G4_W];            // sum of tp of the segments that are not a whole read (each lane owns its four)
 };
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t c) {
@@ -673,6 +691,7 @@ __global__ void __launch_bounds__(G4_WARPS * 32, MIN_CTAS) rv_gather4_kernel(Gat
   for (int i = lane; i < G4_W + 4; i += 32) {
     W.d_n[i] = 0; W.c_n[i] = 0; W.d_rev[i] = 0; W.d_mapq[i] = 0; W.d_nm[i] = 0; W.d_tp1[i] = 0; W.d_tp2[i] = 0;
   }
+  for (int i = lane; i < G4_W; i += 32) W.g_tp[i] = 0;
   __threadfence();  // the zero rows are in place before any lane's atomics on them
   __syncwarp();
   // ---- lane constants of the SIMD pass
@@ -685,7 +704,6 @@ __global__ void __launch_bounds__(G4_WARPS * 32, MIN_CTAS) rv_gather4_kernel(Gat
   const uint16_t* item_mm = a.desc_mm + item_shift;
   uint32_t tp_and01 = 0xffffffffu, tp_and23 = 0xffffffffu, tp_or01 = 0, tp_or23 = 0, q_and = 0xffffffffu, q_or = 0;
   uint32_t sum_q[4] = {0, 0, 0, 0}, n_hi[4] = {0, 0, 0, 0};
-  uint32_t sum_tp_g[4] = {0, 0, 0, 0};  // tp of segments that are not a whole read (summed in the SIMD pass)
 
   // Neighbouring tiles walk their candidates in opposite directions: the reads two tiles share are then needed by
   // both at the same end of their loops, i.e. close in time (L1 / L2 hits instead of a second trip to DRAM).
@@ -877,7 +895,9 @@ __global__ void __launch_bounds__(G4_WARPS * 32, MIN_CTAS) rv_gather4_kernel(Gat
       }
       sum_q[0] += sq_lo & 0xffffu; sum_q[2] += sq_lo >> 16; sum_q[1] += sq_hi & 0xffffu; sum_q[3] += sq_hi >> 16;
       n_hi[0] += hi_acc & 0xffu; n_hi[1] += (hi_acc >> 8) & 0xffu; n_hi[2] += (hi_acc >> 16) & 0xffu; n_hi[3] += hi_acc >> 24;
-      sum_tp_g[0] += stp01 & 0xffffu; sum_tp_g[1] += stp01 >> 16; sum_tp_g[2] += stp23 & 0xffffu; sum_tp_g[3] += stp23 >> 16;
+      if (stp01 | stp23) {
+        W.g_tp[x4] += stp01 & 0xffffu; W.g_tp[x4 + 1] += stp01 >> 16; W.g_tp[x4 + 2] += stp23 & 0xffffu; W.g_tp[x4 + 3] += stp23 >> 16;
+      }
     }
     __syncwarp();
     }  // first / second segment of the batch's work items
@@ -894,7 +914,7 @@ __global__ void __launch_bounds__(G4_WARPS * 32, MIN_CTAS) rv_gather4_kernel(Gat
   for (int j = 0; j < 4; ++j) stp[j] += W.d_tp1[x4 + j];
   warp_scan4(stp, lane);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) stp[j] += sum_tp_g[j];
+  for (int j = 0; j < 4; ++j) stp[j] += W.g_tp[x4 + j];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     if (!in_tab[j]) continue;
@@ -1425,7 +1445,7 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   ctx->tile = G4_W;
   ctx->g4_run = getenv("RV_G4_RUN") ? std::max(1, atoi(getenv("RV_G4_RUN"))) : 1;
   ctx->g4_alt = getenv("RV_G4_ALT") ? atoi(getenv("RV_G4_ALT")) : 1;
-  ctx->g4_variant = getenv("RV_G4_VARIANT") ? atoi(getenv("RV_G4_VARIANT")) : 0;
+  ctx->g4_variant = getenv("RV_G4_VARIANT") ? atoi(getenv("RV_G4_VARIANT")) : 4;  // <4, 7>: 72 registers, fewest spills
   ctx->walk_occ = getenv("RV_WALK_OCC") ? atoi(getenv("RV_WALK_OCC")) : 4;
   ctx->d_descs2 = NULL; ctx->d_desc_mm2 = NULL; ctx->d_desc_mml2 = NULL; ctx->d_sparse = NULL; ctx->d_sparse_count = NULL;
   ctx->max_sparse = 0;
@@ -1781,6 +1801,7 @@ int rv_pileup(rv_ctx* ctx) {
     if (variant == 1) rv_gather4_kernel<8, 6><<<g4_grid, G4_WARPS * 32, 0, ctx->stream>>>(g);
     else if (variant == 2) rv_gather4_kernel<8, 5><<<g4_grid, G4_WARPS * 32, 0, ctx->stream>>>(g);
     else if (variant == 3) rv_gather4_kernel<4, 6><<<g4_grid, G4_WARPS * 32, 0, ctx->stream>>>(g);
+    else if (variant == 4) rv_gather4_kernel<4, 7><<<g4_grid, G4_WARPS * 32, 0, ctx->stream>>>(g);
     else rv_gather4_kernel<4, 8><<<g4_grid, G4_WARPS * 32, 0, ctx->stream>>>(g);
     ctx->launches += 2;
     CK(cudaGetLastError());
