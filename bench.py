@@ -192,67 +192,17 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours")
-    ap.add_argument("--e2e-steps", type=int, default=3, help="timed CLI runs (files in -> TSV out)")
-    ap.add_argument("--parity", default="all", help="configs whose full-size TSV is diffed against the reference binary: "
-                                                    "all | workload | none | comma list of 1,1R,2,3,4,5")
-    ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--workload", default="", help="override: 2 or 4")
-    ap.add_argument("--ref-budget-s", type=float, default=200.0)
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference_arm(args)
-
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    ensure_built()
-    import rabbitvar_b200 as rv
-    from rabbitvar_b200 import shard
-    import parity_configs as pc
+def measure_resident(rv, torch, key, d, tiles, local, steps, warmup, barrier, rank):
+    """The device-resident arm: reads of `tiles` resident in HBM, `steps` timed passes of rv_pileup + rv_score
+    (+ the joined tumor|normal records for the paired workload), CUDA events on the context's stream."""
     import ctypes as C
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the one JSON line
-        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world)
-    if not torch.cuda.is_available():
-        raise rv.RabbitVarError("bench.py needs a GPU (there is no CPU path); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    key = args.workload or ("2" if world == 1 else "4")
-    paired = key == "2"
+    import numpy as np
+    import parity_configs as pc
     cfg = pc.CONFIGS[key]
-    t0 = time.time()
-    d, length = workload_dataset(key, rank, barrier)
-    bed_all = os.path.join(d, cfg["bed"])
-    tiles_all = read_tiles(bed_all)
-    chrom = tiles_all[0][0]
-    # ---- this rank's block of tiles (contiguous, balanced by the compressed bytes the BAI says each tile spans) -------
-    bam0 = os.path.join(d, cfg["bam"].split("|")[0])
-    weights = shard.bai_tile_weights(bam0 + ".bai", 0, [(s, e) for _, s, e, _ in tiles_all])
-    blocks = shard.contiguous_blocks(weights, world)
-    lo, hi = blocks[rank]
-    tiles = tiles_all[lo:hi]
-    my_bed = os.path.join(d, f"shard_{world}_{rank}.bed")
-    with open(my_bed, "w") as f:
-        for c_, s, e, g in tiles:
-            f.write(f"{c_}\t{s}\t{e}\t{g}\n")
+    paired = key == "2"
+    chrom = tiles[0][0]
     starts, ends = [t[1] for t in tiles], [t[2] for t in tiles]
-
-    # ---- device-resident inputs ------------------------------------------------------------------------------------
+    t0 = time.time()
     bams = [os.path.join(d, b) for b in cfg["bam"].split("|")]
     bt = rv.HostBatch(bams[0], chrom, starts[0], ends[-1])
     n_t = bt.n_reads
@@ -272,7 +222,7 @@ def main():
     ref_lo = max(1, starts[0] - 1400)
     ref_hi = min(bt.chr_len, ends[-1] + 1400)
     ref = rv.fetch_ref(os.path.join(d, "ref.fa"), chrom, ref_lo, ref_hi)
-    log(f"[bench r{rank}] workload {key}: tiles [{lo}, {hi}) of {len(tiles_all)}, data ready in {time.time() - t0:.1f}s: "
+    log(f"[bench r{rank}] workload {key}: {len(tiles)} tiles, data ready in {time.time() - t0:.1f}s: "
         f"{bt.n_reads} reads, pool {bt.pool_bytes / 1e9:.2f} GB, {nreg} (tile, sample) regions")
     halo = 512
     n_pos = sum(e - s + 1 + 2 * halo for s, e in zip(starts, ends)) * len(regs_list)
@@ -331,7 +281,7 @@ def main():
             b += b2
         return a, b, sp
 
-    for _ in range(max(0, args.warmup)):
+    for _ in range(max(0, warmup)):
         step()
     ctx.sync()
     barrier()
@@ -342,7 +292,7 @@ def main():
     pile_ms, score_ms, split_ms = [], [], []
     ctx.timer_start()
     w0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         a, b, sp = step()
         pile_ms.append(a)
         score_ms.append(b)
@@ -359,6 +309,79 @@ def main():
     del d_reads, d_pool
     bt.close()
     torch.cuda.empty_cache()
+
+    P = sum(e - s + 1 for s, e in zip(starts, ends)) * len(regs_list)
+    return {"dev_ms": dev_ms, "wall_ms": wall_ms, "bases": bases_per_step, "kept": kept_per_step, "launches": launches,
+            "clocks": clocks, "n_var": n_var_step, "pile_ms": pile_ms, "score_ms": score_ms, "split_ms": split_ms,
+            "avg_read_bytes": avg_read_bytes, "read_bytes_total": read_bytes_total, "n_pos": n_pos, "P": P,
+            "reads": int(n_t + n_n), "paired": paired}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--e2e-steps", type=int, default=3, help="timed CLI runs (files in -> TSV out)")
+    ap.add_argument("--parity", default="all", help="configs whose full-size TSV is diffed against the reference binary: "
+                                                    "all | workload | none | comma list of 1,1R,2,3,4,5")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--no-scaling-base", dest="scaling_base", action="store_false",
+                    help="N = 1: skip the single-GPU measurement of the multi-GPU workload (configs[3])")
+    ap.add_argument("--workload", default="", help="override: 2 or 4")
+    ap.add_argument("--ref-budget-s", type=float, default=200.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    ensure_built()
+    import rabbitvar_b200 as rv
+    from rabbitvar_b200 import shard
+    import parity_configs as pc
+    import ctypes as C
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the one JSON line
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world)
+    if not torch.cuda.is_available():
+        raise rv.RabbitVarError("bench.py needs a GPU (there is no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    key = args.workload or ("2" if world == 1 else "4")
+    paired = key == "2"
+    cfg = pc.CONFIGS[key]
+    t0 = time.time()
+    d, length = workload_dataset(key, rank, barrier)
+    bed_all = os.path.join(d, cfg["bed"])
+    tiles_all = read_tiles(bed_all)
+    chrom = tiles_all[0][0]
+    # ---- this rank's block of tiles (contiguous, balanced by the compressed bytes the BAI says each tile spans) -------
+    bam0 = os.path.join(d, cfg["bam"].split("|")[0])
+    weights = shard.bai_tile_weights(bam0 + ".bai", 0, [(s, e) for _, s, e, _ in tiles_all])
+    blocks = shard.contiguous_blocks(weights, world)
+    lo, hi = blocks[rank]
+    tiles = tiles_all[lo:hi]
+    my_bed = os.path.join(d, f"shard_{world}_{rank}.bed")
+    with open(my_bed, "w") as f:
+        for c_, s, e, g in tiles:
+            f.write(f"{c_}\t{s}\t{e}\t{g}\n")
+    # ---- device-resident arm ----------------------------------------------------------------------------------------
+    R = measure_resident(rv, torch, key, d, tiles, local, args.steps, args.warmup, barrier, rank)
+    dev_ms, wall_ms, bases_per_step, kept_per_step, launches, clocks = R["dev_ms"], R["wall_ms"], R["bases"], R["kept"], R["launches"], R["clocks"]
+    n_var_step, pile_ms, score_ms, split_ms = R["n_var"], R["pile_ms"], R["score_ms"], R["split_ms"]
+    avg_read_bytes, read_bytes_total, n_pos = R["avg_read_bytes"], R["read_bytes_total"], R["n_pos"]
 
     # ---- e2e: the drop-in CLI on this rank's tiles, files in -> TSV out ----------------------------------------------
     cores = os.cpu_count() or 1
@@ -386,6 +409,22 @@ def main():
     if cli_info:
         log(f"[bench r{rank}] e2e CLI: {e2e_sec:.3f} s per run; " + " | ".join(cli_info.strip().splitlines()[-3:])[:900])
 
+    # ---- N = 1: the multi-GPU workload (configs[3]) on this one GPU, so that the strong-scaling series of the N > 1
+    # runs has its own single-GPU point (the N = 1 headline above is configs[1]) --------------------------------------
+    scaling_base = None
+    if world == 1 and key == "2" and args.scaling_base:
+        try:
+            d4, _ = pc.dataset("4", 1.0, 1)
+            tiles4 = read_tiles(os.path.join(d4, pc.CONFIGS["4"]["bed"]))
+            R4 = measure_resident(rv, torch, "4", d4, tiles4, local, max(3, args.steps // 3), 2, barrier, rank)
+            alg4 = R4["kept"] * R4["avg_read_bytes"] + R4["P"] * 133.0
+            pk4 = float(np.mean(R4["pile_ms"])) / 1000.0
+            scaling_base = {"workload": WORKLOAD_TEXT["4"], "n_gpus": 1, "value": R4["bases"] * len(R4["pile_ms"]) / (R4["dev_ms"] / 1000.0),
+                            "ms_per_step": R4["dev_ms"] / len(R4["pile_ms"]), "aligned_bases_per_step": int(R4["bases"]),
+                            "pileup_stage_ms": pk4 * 1000.0, "pileup_roofline_frac": alg4 / pk4 / 1e9 / measured_peak()[0]}
+        except Exception as e:  # reported, never required
+            scaling_base = {"error": str(e)[:300]}
+
     # ---- reductions over ranks (max time, sum of work) ---------------------------------------------------------------
     dd = dist if world > 1 else None
     dev_ms_max, total_bases = shard.reduce_step_metrics(dev_ms, bases_per_step, dd)
@@ -400,7 +439,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        P = sum(e - s + 1 for s, e in zip(starts, ends)) * len(regs_list)
+        P = R["P"]
         alg_pileup = kept_per_step * avg_read_bytes + P * 133.0
         alg_score = P * 133.0 + n_var_step * 128.0
         pk = float(np.mean(pile_ms)) / 1000.0
@@ -455,7 +494,7 @@ def main():
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": WORKLOAD_TEXT[key], "tiles_total": len(tiles_all), "tiles_rank0": len(tiles),
-                       "reads_rank0": int(n_t + n_n), "aligned_bases_per_step": int(total_bases),
+                       "reads_rank0": R["reads"], "aligned_bases_per_step": int(total_bases),
                        "l2_policy": f"inputs of a step ({read_bytes_total / 1e9:.2f} GB reads + {n_pos * 132 / 1e9:.2f} GB tables on rank 0) exceed the 126 MB L2",
                        "wall_ms_per_step": wall_ms_max / args.steps,
                        "step": "rv_pileup + rv_score (device candidate cut)" + (" + rv_score_positions (full records of both samples at the joined candidate positions)" if paired else "") +
@@ -465,6 +504,7 @@ def main():
                     "api": f"build/rabbitvar_b200 (drop-in CLI): level-1 BAM + FASTA + BED files -> TSV file, one process per GPU, --th {th} decode threads each; wall clock of the process incl. CUDA start-up, max over ranks",
                     "sec_per_step": e2e_sec_max if e2e_t else None, "runs": len(e2e_t), "gpu_launches_per_run": cli_launches},
             "gpu_launches": int(launches_total),
+            "strong_scaling_base": scaling_base,
             "parity": parity,
             "parity_lines_differing": {k: v.get("parity_lines_differing") for k, v in parity.items()},
             "roofline": {"bound": "hbm",

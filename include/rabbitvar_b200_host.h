@@ -75,6 +75,23 @@ int rvh_pipeline_run_paired(rvh_pipeline* p, const rv_params* params, const rvh_
 int64_t rvh_pipeline_launch_count(const rvh_pipeline* p);
 const char* rvh_last_error(void);
 
+/* The loader's block decoder and checksum (csrc/io/fast_inflate.hpp), exposed so that they can be checked against
+ * zlib from outside: one raw-DEFLATE stream (a BGZF block's payload) in, bytes out.  Returns the number of bytes
+ * written, -1 when the stream is malformed or does not fit out_cap. */
+int64_t rvh_inflate_block(const uint8_t* in, int64_t in_len, uint8_t* out, int64_t out_cap);
+uint32_t rvh_crc32(const uint8_t* buf, int64_t n);
+
+/* Files in, TSV text out: the region loop of the reference's CLI (Launcher.cpp / simpleMode.cpp:210-387 /
+ * somaticMode.cpp:860-930) for a list of regions of one or more contigs — parallel BGZF/BAM decode threads feeding GPU
+ * worker contexts (csrc/host/file_pipeline.hpp).  bam2 = NULL or "" selects the single-sample mode.  Regions are
+ * (chr[i], start[i], end[i], gene[i]), 1-based inclusive.  tsv_out is malloc'ed by the library: free it with
+ * rvh_free.  Returns 0, 2 when some regions failed (see rvh_last_error), 3 without a CUDA device. */
+int rvh_run_files(const rv_params* params, const char* fasta, const char* bam, const char* bam2, const char* sample,
+                  int32_t n_regions, const char* const* chr, const int32_t* start, const int32_t* end,
+                  const char* const* gene, int32_t decode_threads, int32_t gpus, int32_t first_device,
+                  char** tsv_out, int64_t* tsv_len, double* cov_info /* [4]: sum T, sites T, sum N, sites N; may be NULL */);
+void rvh_free(void* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -122,6 +122,7 @@ ABI_SYMBOLS = [
     "rvh_batch_pool_bytes", "rvh_batch_max_ref_span", "rvh_batch_pin", "rvh_batch_free", "rvh_make_regions", "rvh_fetch_ref",
     "rvh_call_regions", "rvh_install_patch", "rvh_last_error",
     "rvh_pipeline_create", "rvh_pipeline_destroy", "rvh_pipeline_run", "rvh_pipeline_run_paired", "rvh_pipeline_launch_count",
+    "rvh_inflate_block", "rvh_crc32", "rvh_run_files", "rvh_free",
 ]
 
 
@@ -129,6 +130,14 @@ def _declare(L):
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     L.rv_abi_version.restype = C.c_int
     L.rv_device_count.restype = C.c_int
+    L.rvh_inflate_block.argtypes = [vp, i64, vp, i64]
+    L.rvh_inflate_block.restype = i64
+    L.rvh_crc32.argtypes = [vp, i64]
+    L.rvh_crc32.restype = C.c_uint32
+    L.rvh_run_files.argtypes = [C.POINTER(Params), C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, i32, C.POINTER(C.c_char_p),
+                                C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_char_p), i32, i32, i32, C.POINTER(vp),
+                                C.POINTER(i64), C.POINTER(C.c_double)]
+    L.rvh_free.argtypes = [vp]
     L.rv_default_params.argtypes = [C.POINTER(Params)]
     L.rv_default_limits.argtypes = [C.POINTER(Limits)]
     L.rv_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(Params), C.POINTER(Limits)]
@@ -499,3 +508,32 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def inflate_block(data, out_len):
+    """One raw-DEFLATE stream through the loader's own decoder (csrc/io/fast_inflate.hpp). None when it refuses."""
+    buf = C.create_string_buffer(max(1, out_len))
+    n = lib().rvh_inflate_block(C.cast(C.c_char_p(data), C.c_void_p), len(data), C.cast(buf, C.c_void_p), out_len)
+    return None if n < 0 else buf.raw[:n]
+
+
+def crc32(data):
+    return lib().rvh_crc32(C.cast(C.c_char_p(data), C.c_void_p), len(data))
+
+
+def run_files(params, fasta, bam, regions, bam2=None, sample="S", decode_threads=4, gpus=1, first_device=0):
+    """Files in, TSV text out (rvh_run_files).  regions: [(chr, start1, end1, gene)].  Returns (rc, text, cov_info)."""
+    n = len(regions)
+    chr_a = (C.c_char_p * n)(*[r[0].encode() for r in regions])
+    gene_a = (C.c_char_p * n)(*[(r[3] if len(r) > 3 else r[0]).encode() for r in regions])
+    st = (C.c_int32 * n)(*[r[1] for r in regions])
+    en = (C.c_int32 * n)(*[r[2] for r in regions])
+    out, olen = C.c_void_p(), C.c_int64()
+    cov = (C.c_double * 4)()
+    rc = lib().rvh_run_files(C.byref(params), os.fsencode(fasta), os.fsencode(bam), os.fsencode(bam2) if bam2 else None,
+                             sample.encode(), n, chr_a, st, en, gene_a, decode_threads, gpus, first_device, C.byref(out),
+                             C.byref(olen), cov)
+    text = C.string_at(out, olen.value).decode() if out.value else ""
+    if out.value:
+        lib().rvh_free(out)
+    return rc, text, tuple(cov)

@@ -237,6 +237,7 @@ int main(int argc, char** argv) {
   fc.max_regions_per_job = c.batch_regions;
   fc.job_bytes = (int64_t)c.job_mb << 20;
   fc.halo = c.halo;
+  fc.keep_contexts = true;  // the process exits right after the run
   std::string tsv;
   FileRunStats st;
   std::vector<std::string> errors;
@@ -275,5 +276,8 @@ int main(int argc, char** argv) {
   printf("[info] timeline ms: inputs parsed %.0f, cuda start-up %.0f (beside the decode threads), pipeline done %.0f, output written %.0f\n",
          t_parsed - t0, cuda_init_ms, t_ran - t0, now_ms() - t0);
   printf("total time: %f s \n", (now_ms() - t0) / 1000.0);
-  return rc;
+  // the output is on disk: leave without tearing the CUDA context down (hundreds of milliseconds of cudaFree)
+  fflush(stdout);
+  fflush(stderr);
+  _exit(rc);
 }

@@ -38,6 +38,7 @@ struct FileRunConfig {
   int cluster_gap = 2000;
   int halo = 512;
   bool verbose = false;
+  bool keep_contexts = false;  // do not rv_destroy the worker contexts at the end (a CLI about to exit)
   bool decode_only = false;  // measurement aid: run the decode stage alone (no device needed), print nothing
 };
 
@@ -330,7 +331,10 @@ inline int run_files(const FileRunConfig& c, const std::vector<RegionSpec>& spec
         }
         cv_slot.notify_all();
       }
-      if (ctx) { launches += rv_launch_count(ctx); rv_destroy(ctx); }
+      if (ctx) {
+        launches += rv_launch_count(ctx);
+        if (!c.keep_contexts) rv_destroy(ctx);
+      }
     });
   for (size_t i = 0; i < threads.size(); ++i) threads[i].join();
   int rc = 0;

@@ -1,6 +1,6 @@
 // rvhost_abi.cpp — C ABI over the host side of the path (include/rabbitvar_b200_host.h).
 #include "../../../include/rabbitvar_b200_host.h"
-#include "pipeline.hpp"
+#include "file_pipeline.hpp"
 #include <array>
 #include <atomic>
 #include <map>
@@ -285,6 +285,59 @@ int rvh_pipeline_run_paired(rvh_pipeline* p, const rv_params* params, const rvh_
 }
 
 const char* rvh_last_error(void) { return g_err.c_str(); }
+
+int64_t rvh_inflate_block(const uint8_t* in, int64_t in_len, uint8_t* out, int64_t out_cap) {
+  if (!in || !out || in_len < 0 || out_cap < 0) return -1;
+  static thread_local std::unique_ptr<rvio::FastInflate> fi;
+  if (!fi) fi.reset(new rvio::FastInflate());
+  return (int64_t)fi->inflate(in, (size_t)in_len, out, (size_t)out_cap);
+}
+uint32_t rvh_crc32(const uint8_t* buf, int64_t n) { return rvio::fast_crc32(buf, (size_t)(n < 0 ? 0 : n)); }
+
+int rvh_run_files(const rv_params* params, const char* fasta, const char* bam, const char* bam2, const char* sample,
+                  int32_t n_regions, const char* const* chr, const int32_t* start, const int32_t* end,
+                  const char* const* gene, int32_t decode_threads, int32_t gpus, int32_t first_device,
+                  char** tsv_out, int64_t* tsv_len, double* cov_info) {
+  if (!params || !fasta || !bam || !tsv_out || !tsv_len || n_regions < 0 || (n_regions && (!chr || !start || !end))) return RV_ERR_ARG;
+  try {
+    FileRunConfig fc;
+    fc.fasta = fasta;
+    fc.bam = bam;
+    fc.bam2 = bam2 ? bam2 : "";
+    fc.sample = sample ? sample : "";
+    fc.P = *params;
+    fc.P.candidates_only = fc.P.pileup ? 0 : 1;
+    fc.decode_threads = decode_threads > 0 ? decode_threads : 1;
+    fc.gpus = gpus > 0 ? gpus : 1;
+    fc.first_device = first_device > 0 ? first_device : 0;
+    std::vector<RegionSpec> specs((size_t)n_regions);
+    for (int i = 0; i < n_regions; ++i) {
+      specs[(size_t)i].chr = chr[i];
+      specs[(size_t)i].start = start[i];
+      specs[(size_t)i].end = end[i];
+      specs[(size_t)i].gene = gene && gene[i] ? gene[i] : chr[i];
+    }
+    std::string tsv;
+    FileRunStats st;
+    std::vector<std::string> errors;
+    int rc = run_files(fc, specs, &tsv, &st, &errors);
+    g_err.clear();
+    for (size_t i = 0; i < errors.size(); ++i) g_err += errors[i] + "\n";
+    if (rc == 2 && rv_device_count() <= 0) rc = 3;
+    char* out = (char*)malloc(tsv.size() + 1);
+    if (!out) return RV_ERR_NOMEM;
+    memcpy(out, tsv.data(), tsv.size());
+    out[tsv.size()] = 0;
+    *tsv_out = out;
+    *tsv_len = (int64_t)tsv.size();
+    if (cov_info) { cov_info[0] = (double)st.cov_sum[0]; cov_info[1] = (double)st.cov_pos[0]; cov_info[2] = (double)st.cov_sum[1]; cov_info[3] = (double)st.cov_pos[1]; }
+    return rc;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return RV_ERR_STATE;
+  }
+}
+void rvh_free(void* p) { free(p); }
 
 rvh_batch* rvh_load_bam(const char* bam_path, const char* chr, int32_t start, int32_t end, int32_t* chr_len_out) {
   try {

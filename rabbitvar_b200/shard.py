@@ -58,8 +58,8 @@ def concat_in_order(parts, dist=None):
 
 
 def bai_tile_weights(bai_path, tid, tiles):
-    """Expected work of every tile = compressed BAM bytes between the linear-index entries of its first and last
-    16 kb window (BAI linear index, SAM spec 5.2) — the 'balanced by expected reads' weight of SURVEY 8(e).
+    """Expected work of every tile = its share of the compressed BAM bytes of the 16 kb index windows it touches
+    (BAI linear index, SAM spec 5.2) — the 'balanced by expected reads' weight of SURVEY 8(e).
     tiles: [(start1, end1)] 1-based inclusive.  Falls back to the tile lengths when the index has no entry."""
     import struct
     with open(bai_path, "rb") as f:
@@ -87,12 +87,23 @@ def bai_tile_weights(bai_path, tid, tiles):
         if ioffset[i] == 0:
             ioffset[i] = ioffset[i - 1]
 
-    def coff(pos0):
-        w = min(max(pos0, 0) >> 14, len(ioffset) - 1)
-        return ioffset[w] >> 16
+    def coff(w):
+        return ioffset[min(max(w, 0), len(ioffset) - 1)] >> 16
 
+    # bytes of window w: up to the next window's first offset; the last window gets the mean of the others
+    n_w = len(ioffset)
+    wbytes = [max(0, coff(w + 1) - coff(w)) for w in range(n_w)]
+    filled = [b for b in wbytes[:-1] if b > 0]
+    if n_w:
+        wbytes[-1] = sum(filled) / len(filled) if filled else 0.0
     out = []
     for s, e in tiles:
-        w = float(coff(e + (1 << 14)) - coff(s - 1))
-        out.append(w if w > 0 else float(e - s + 1) * 1e-3)
+        w0, w1 = max(s - 1, 0) >> 14, max(e - 1, 0) >> 14
+        total = 0.0
+        for w in range(w0, w1 + 1):
+            if w >= n_w:
+                break
+            lo, hi = max(s - 1, w << 14), min(e, (w + 1) << 14)  # the tile's share of the window
+            total += wbytes[w] * max(0, hi - lo) / 16384.0
+        out.append(total if total > 0 else float(e - s + 1) * 1e-3)
     return out

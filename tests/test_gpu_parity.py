@@ -246,3 +246,53 @@ def test_paired_pipeline_matches_reference_output(built):
         bad = [(w, g) for w, g in zip(want, got) if w != g and not _tsv_equal(w, g)]
         assert not bad, bad[:3]
     bt.close()
+
+
+@pytest.mark.parametrize("key,scale", [("1", 0.2), ("1R", 0.1), ("2", 0.1), ("3", 0.1), ("4", 0.02), ("5", 0.1)])
+def test_baseline_config_slice_matches_reference_binary(built, ref_tools, key, scale):
+    """Every BASELINE.json config, same flags as tools/parity_configs.py runs them at full size (bench.py does, and
+    records `parity_lines_differing`), here on a slice (>= 1 Mb for config 4): the drop-in CLI — parallel decode,
+    GPU pipeline — against the reference binary built by oracle/Makefile, TSV as sorted multisets."""
+    if ref_tools is None:
+        pytest.skip("oracle/_ref did not travel to this box")
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import parity_configs as pc
+    r = pc.run_config(key, scale, 1, 4)
+    assert not r.get("error"), r
+    assert r["ref_lines"] > 0 and r["cli_lines"] == r["ref_lines"], r
+    assert r["parity_lines_differing"] == 0, r["examples"][:3]
+    if key == "2":
+        assert r["info_equal"]
+
+
+def test_tile_blocks_concatenate_to_the_whole_run(built, tmp_path):
+    """The multi-GPU split of bench.py (config 4: contiguous blocks of the tile list, one CLI process per block, text
+    concatenated in block order) on one GPU: the blocks' TSV must add up to the TSV of the undivided run, and
+    rvh_run_files (the CLI's loop behind the C ABI) must return the same text."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import parity_configs as pc
+    import rabbitvar_b200 as rv
+    from rabbitvar_b200 import shard
+    d, length = pc.dataset("4", 0.02)
+    args = pc.cli_args("4", d, length)
+    bed = args[args.index("-i") + 1]
+    tiles = [l.split() for l in open(bed)]
+    whole = str(tmp_path / "whole.tsv")
+    run([pc.CLI] + args + ["--th", "4", "--out", whole])
+    w = shard.bai_tile_weights(os.path.join(d, "S.bam.bai"), 0, [(int(t[1]), int(t[2])) for t in tiles])
+    parts = []
+    for g, (lo, hi) in enumerate(shard.contiguous_blocks(w, 3)):
+        sub = str(tmp_path / f"b{g}.bed")
+        with open(sub, "w") as f:
+            f.writelines("\t".join(t) + "\n" for t in tiles[lo:hi])
+        a = list(args)
+        a[a.index("-i") + 1] = sub
+        out = str(tmp_path / f"b{g}.tsv")
+        run([pc.CLI] + a + ["--th", "2", "--out", out])
+        parts.append(open(out).read())
+    assert "".join(parts) == open(whole).read()
+    rc, text, _ = rv.run_files(rv.default_params(), os.path.join(d, "ref.fa"), os.path.join(d, "S.bam"),
+                               [(t[0], int(t[1]), int(t[2]), t[3]) for t in tiles], sample="S", decode_threads=3)
+    assert rc == 0 and text == open(whole).read()

@@ -50,3 +50,43 @@ def test_fixed_point_formatter_matches_libc(tmp_path):
     subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(cases.ROOT, "tests", "tools", "fmt_test.cpp")], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-500:]
+
+
+def test_block_decoder_and_crc_match_zlib(built):
+    """The loader's own raw-DEFLATE decoder and CRC-32 (csrc/io/fast_inflate.hpp) against zlib: streams of every block
+    type (stored, fixed, dynamic), sizes from empty to several blocks, literal- and match-heavy payloads, and every
+    BGZF block of a synthetic BAM.  Truncated input and a too-small output buffer must be refused, not overrun."""
+    import random
+    import struct
+    import zlib
+    import rabbitvar_b200 as rv
+    rnd = random.Random(5)
+    payloads = [b"", b"A", bytes(rnd.getrandbits(8) for _ in range(5000)), bytes(rnd.choice(b"ACGT") for _ in range(70000)),
+                bytes([37]) * 66000, b"".join(bytes([rnd.choice((37, 37, 37, 30, 25, 12))]) for _ in range(40000)),
+                bytes((i * 7 + (i >> 5)) & 255 for i in range(200000))]
+    n = 0
+    for data in payloads:
+        assert rv.crc32(data) == zlib.crc32(data)
+        for level in (0, 1, 6, 9):
+            for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE):
+                co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+                comp = co.compress(data) + co.flush()
+                assert rv.inflate_block(comp, len(data)) == data
+                if len(data) > 100:
+                    assert rv.inflate_block(comp, len(data) - 1) is None          # output too small
+                    assert rv.inflate_block(comp[: len(comp) // 2], len(data)) != data  # truncated input
+                n += 1
+    assert n == len(payloads) * 16
+    # every BGZF block of a BAM written by the generator
+    d = cases.generate("c1_k1")
+    raw = open(os.path.join(d, "S.bam"), "rb").read()
+    p, blocks = 0, 0
+    while p + 18 <= len(raw):
+        bsize = struct.unpack_from("<H", raw, p + 16)[0] + 1
+        crc, isize = struct.unpack_from("<II", raw, p + bsize - 8)
+        want = zlib.decompress(raw[p + 18: p + bsize - 8], -15)
+        got = rv.inflate_block(raw[p + 18: p + bsize - 8], isize)
+        assert got == want and rv.crc32(got) == crc
+        p += bsize
+        blocks += 1
+    assert blocks > 10

@@ -9,7 +9,7 @@ import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from rabbitvar_b200.shard import concat_in_order, contiguous_blocks, reduce_step_metrics  # noqa: E402
+from rabbitvar_b200.shard import bai_tile_weights, concat_in_order, contiguous_blocks, reduce_step_metrics  # noqa: E402
 
 
 def test_blocks_cover_in_order_and_balance():
@@ -60,3 +60,17 @@ def test_two_rank_gloo_reduction_and_ordered_concat():
     assert u == (5 * 3 + 15) * 1000      # sum over ranks == whole job
     assert text == "".join(f"tile{i}\n" for i in range(20))  # rank order == tile order
     assert blk0[0] == 0
+
+
+def test_bai_weights_follow_the_read_density(built):
+    """bai_tile_weights: compressed bytes per tile from the BAI linear index — the weights bench.py cuts the tile list
+    with (contiguous_blocks).  A region without reads weighs (almost) nothing, equal tiles of a uniform BAM weigh alike."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    d = cases.generate("c2_somatic_bed_k0")
+    tiles = [(int(l.split()[1]), int(l.split()[2])) for l in open(os.path.join(d, "tiles.bed"))]
+    w = bai_tile_weights(os.path.join(d, "T.bam.bai"), 0, tiles + [(100, 900)])
+    assert len(w) == len(tiles) + 1 and all(x > 0 for x in w)
+    assert w[-1] < 0.2 * max(w[:-1])                       # 800 bp against 10 kb tiles
+    blocks = contiguous_blocks(w[:-1], 2)
+    assert blocks[0][1] == blocks[1][0] and abs((blocks[0][1] - blocks[0][0]) - (blocks[1][1] - blocks[1][0])) <= 1
