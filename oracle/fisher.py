@@ -7,8 +7,9 @@ samtools/htslib HEAD), so the arithmetic is restated from the published algorith
     hypergeo     = exp(lbinom(n1_,n11) + lbinom(n-n1_,n_1-n11) - lbinom(n,n_1))
 incremental ratio updates between exact re-evaluations at every 11th step, tails summed while
 p < 0.99999999 q, boundary term added when p < 1.00000001 q, two = min(1, left + right).
-PARITY UNPINNED by the reference's own tests (it has none); pinned instead against
-scipy.stats.fisher_exact in tests/test_fisher.py.
+The reference's own tests do not pin these values (it has none); they are pinned against the exact integer
+evaluation of the same procedure (oracle/fisher_exact_rational.py, tests/golden/fisher_exact.tsv.gz) at 1e-12 and
+cross-checked with scipy.stats.fisher_exact in tests/test_fisher.py.
 """
 from math import exp, lgamma
 

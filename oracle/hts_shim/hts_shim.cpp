@@ -11,8 +11,8 @@
 //   * sam_itr_querys("chr:b-e")  -> records with tid==chr, pos < e, bam_endpos > b-1, file order
 //   * fai_fetch("chr:b-e")       -> 1-based inclusive, clipped to contig, malloc'ed
 //   * kt_fisher_exact            -> htslib kfunc.c (un-vendored, unpinned: install.sh:40 clones
-//                                   HEAD); restated from the published algorithm — PARITY UNPINNED,
-//                                   cross-checked against scipy.stats.fisher_exact in tests/.
+//                                   HEAD); restated from the published algorithm and pinned against
+//                                   its exact integer evaluation (oracle/fisher_exact_rational.py).
 #include "htslib/sam.h"
 #include "htslib/faidx.h"
 #include "htslib/kfunc.h"

@@ -1,4 +1,7 @@
-"""Fisher exact test: the oracle restatement is pinned against scipy; the CUDA kernel against the oracle."""
+"""Fisher exact test.  Pin: exact integer / rational evaluation of the published kt_fisher_exact procedure
+(oracle/fisher_exact_rational.py -> tests/golden/fisher_exact.tsv.gz, 10 160 tables incl. exact ties and margins up to
+10 000).  Against it, at 1e-12 (n <= 100) / 1e-10 (n <= 1200) / 1e-9 relative: the double-precision restatement oracle/fisher.py, the
+kt_fisher_exact the reference binary links (oracle/hts_shim), and the CUDA kernel.  scipy stays as a second opinion."""
 import os
 import sys
 
@@ -42,3 +45,68 @@ def test_cuda_fisher_matches_oracle(built):
         for x, y in zip(want, g):
             assert y == pytest.approx(x, rel=1e-9, abs=1e-300), (a, b, c, d)
     ctx.close()
+
+
+def _golden_fisher():
+    import gzip
+    rows = []
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "fisher_exact.tsv.gz"), "rt") as f:
+        for l in f:
+            t = l.split("\t")
+            rows.append((tuple(int(x) for x in t[:4]), tuple(float(x) for x in t[4:7])))
+    return rows
+
+
+def _tol(tab):
+    # the double-precision evaluations go through exp(sum of lgamma): their relative error grows with |log p|, i.e. with
+    # the table's size (~ n * 1e-16 * a few); the exact vectors show it directly
+    n = sum(tab)
+    return 1e-12 if n <= 100 else 1e-10 if n <= 1200 else 1e-9
+
+
+def test_golden_fisher_file_is_the_exact_procedure():
+    """The committed vectors are what oracle/fisher_exact_rational.py computes (spot-check: every 37th table)."""
+    import fisher_exact_rational as ex
+    rows = _golden_fisher()
+    assert len(rows) >= 10000 and [r[0] for r in rows] == ex.tables()
+    for tab, want in rows[::37]:
+        got = tuple(float(x) for x in ex.exact_fisher(*tab))
+        assert got == want, tab
+
+
+def test_oracle_fisher_matches_exact_rational():
+    for tab, want in _golden_fisher():
+        got = oracle_fisher.kt_fisher_exact(*tab)
+        for x, y in zip(want, got):
+            assert y == pytest.approx(x, rel=_tol(tab), abs=1e-300), (tab, want, got)
+
+
+def test_reference_side_shim_fisher_matches_exact_rational(tmp_path):
+    """oracle/hts_shim's kt_fisher_exact — the function the compiled reference (oracle/_ref) calls, i.e. the source of the
+    Fisher columns in every golden TSV — against the exact vectors."""
+    import ctypes as C
+    import subprocess
+    so = str(tmp_path / "libshim.so")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-std=gnu++11", "-O2", "-shared", "-fPIC", "-I" + os.path.join(ROOT, "oracle", "hts_shim"),
+                    os.path.join(ROOT, "oracle", "hts_shim", "hts_shim.cpp"), "-o", so, "-lz"], check=True)
+    L = C.CDLL(so)
+    L.kt_fisher_exact.restype = C.c_double
+    L.kt_fisher_exact.argtypes = [C.c_int] * 4 + [C.POINTER(C.c_double)] * 3
+    for tab, want in _golden_fisher():
+        l, r, t = C.c_double(), C.c_double(), C.c_double()
+        L.kt_fisher_exact(*tab, C.byref(l), C.byref(r), C.byref(t))
+        for x, y in zip(want, (l.value, r.value, t.value)):
+            assert y == pytest.approx(x, rel=_tol(tab), abs=1e-300), (tab, want)
+
+
+@pytest.mark.gpu
+def test_cuda_fisher_matches_exact_rational(built):
+    import rabbitvar_b200 as rv
+    rows = _golden_fisher()
+    ctx = rv.Context(0)
+    got = ctx.fisher_exact(np.array([r[0] for r in rows], dtype=np.int32))
+    ctx.close()
+    for (tab, want), g in zip(rows, got):
+        for x, y in zip(want, g):
+            assert y == pytest.approx(x, rel=_tol(tab), abs=1e-300), (tab, want, tuple(g))
