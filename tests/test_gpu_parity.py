@@ -296,3 +296,27 @@ def test_tile_blocks_concatenate_to_the_whole_run(built, tmp_path):
     rc, text, _ = rv.run_files(rv.default_params(), os.path.join(d, "ref.fa"), os.path.join(d, "S.bam"),
                                [(t[0], int(t[1]), int(t[2]), t[3]) for t in tiles], sample="S", decode_threads=3)
     assert rc == 0 and text == open(whole).read()
+
+
+def test_reference_binary_with_compiled_binding(built, ref_tools, tmp_path):
+    """oracle/_ref/RabbitVar_b200 = the reference's own Launcher / RegionBuilder / CLI objects linked with
+    oracle/ref_binding/simple_mode_b200.cpp in place of src/modes/simpleMode.cpp: its SimpleMode::process hands the
+    regions to rvh_run_files (the C ABI).  Same flags, same files: its TSV must equal the stock reference binary's."""
+    if ref_tools is None:
+        pytest.skip("oracle/_ref did not travel to this box")
+    bound = os.path.join(ROOT, "oracle", "_ref", "RabbitVar_b200")
+    if not os.path.exists(bound):
+        pytest.skip("oracle/_ref/RabbitVar_b200 was not built")
+    d = cases.generate("c5_k1")
+    bed = str(tmp_path / "two.bed")
+    with open(bed, "w") as f:
+        f.write("chrS5\t1301\t6300\tg1\nchrS5\t6301\t11300\tg2\n")
+    args = ["-G", os.path.join(d, "ref.fa"), "-b", os.path.join(d, "S.bam"), "-N", "S", "-i", bed, "-c", "1", "-S", "2", "-E", "3",
+            "-g", "4", "-f", "0.01", "-3", "-u", "--fisher", "--th", "2"]
+    want_f, got_f = str(tmp_path / "ref.tsv"), str(tmp_path / "bound.tsv")
+    run([ref_tools["RabbitVar"]] + args + ["--out", want_f])
+    run([bound] + args + ["--out", got_f])
+    want, got = _tsv_lines(open(want_f).read()), _tsv_lines(open(got_f).read())
+    assert len(want) > 20 and len(got) == len(want)
+    bad = [(w, g) for w, g in zip(want, got) if w != g and not _tsv_equal(w, g)]
+    assert not bad, bad[:3]
