@@ -23,7 +23,7 @@ struct Cli {
   std::string fasta, bam, bam2, region, bed, out = "./out.txt", sample, delim = "\t";
   int c_col = 2, S_col = 6, E_col = 7, g_col = 12;  // DEFAULT_BED_ROW_FORMAT (Launcher.cpp:21), 0-based after -1
   bool c_set = false, S_set = false, E_set = false, g_set = false, zero_based = false;
-  int nucl_ext = 0, ref_ext = 1200, gpus = 1, threads = 1, batch_regions = 256, halo = 512, workers = 2, job_mb = 12, device = 0;
+  int nucl_ext = 0, ref_ext = 1200, gpus = 1, threads = 1, batch_regions = 256, halo = 512, workers = 4, job_mb = 12, device = 0;
   bool auto_resize = false, threads_set = false, decode_only = false;
   rv_params P;
 };
