@@ -42,6 +42,10 @@ WORKLOAD_TEXT = {
     "2": "BASELINE.json configs[1]: tumor/normal, 5 Mb as 500 x 10 kb tiles, T 200x + N 100x, 2x150 bp, -f 0.01 --fisher",
     "4": "BASELINE.json configs[3]: 50 Mb chromosome at 30x as 5000 x 10 kb tiles, 2x150 bp, -f 0.01, tiles cut into "
          "contiguous blocks over the GPUs (balanced by BAI bytes), no collective",
+    # --workload 1|3|5: the other configs through the same two arms (profiles/r02_bench_config*.json)
+    "1": "BASELINE.json configs[0]: single sample, 1 Mb as 100 x 10 kb tiles at 100x, 2x150 bp, -f 0.01",
+    "3": "BASELINE.json configs[2]: deep panel, 500 amplicons x 200 bp at 5000x, -f 0.005",
+    "5": "BASELINE.json configs[4]: indel / soft-clip heavy, 5 Mb as 500 x 10 kb tiles at 100x, -3 -u",
 }
 
 
@@ -230,7 +234,11 @@ def measure_resident(rv, torch, key, d, tiles, local, steps, warmup, barrier, ra
                             max_regions=nreg + 8, halo=halo, max_events=max(1 << 20, bt.n_reads),
                             max_variants=(3 if paired else 1) * n_pos + 1024, max_patch=max(1 << 20, bt.n_reads // 2),
                             max_ref_bases=len(ref) + 64)
-    params = rv.default_params(fisher=1, has_bam2=1, candidates_only=2) if paired else rv.default_params(candidates_only=1)
+    if paired:
+        params = rv.default_params(fisher=1, has_bam2=1, candidates_only=2)
+    else:
+        extra = {"3": dict(freq=0.005), "5": dict(move3=1, uniq_u=1)}.get(key, {})
+        params = rv.default_params(candidates_only=1, **extra)
     ctx = rv.Context(local, params, lim)
     ctx.set_reference(ref_lo, ref)
     dev = torch.device("cuda", local)
@@ -329,7 +337,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--no-scaling-base", dest="scaling_base", action="store_false",
                     help="N = 1: skip the single-GPU measurement of the multi-GPU workload (configs[3])")
-    ap.add_argument("--workload", default="", help="override: 2 or 4")
+    ap.add_argument("--workload", default="", help="override the workload: 1, 2, 3, 4 or 5 (BASELINE config number)")
     ap.add_argument("--ref-budget-s", type=float, default=200.0)
     args = ap.parse_args()
     if args.impl == "reference":

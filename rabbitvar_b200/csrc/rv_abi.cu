@@ -1802,7 +1802,6 @@ int rv_pileup(rv_ctx* ctx) {
     else if (variant == 2) rv_gather4_kernel<8, 5><<<g4_grid, G4_WARPS * 32, 0, ctx->stream>>>(g);
     else if (variant == 3) rv_gather4_kernel<4, 6><<<g4_grid, G4_WARPS * 32, 0, ctx->stream>>>(g);
     else if (variant == 4) rv_gather4_kernel<4, 7><<<g4_grid, G4_WARPS * 32, 0, ctx->stream>>>(g);
-    else rv_gather4_kernel<4, 8><<<g4_grid, G4_WARPS * 32, 0, ctx->stream>>>(g);
     ctx->launches += 2;
     CK(cudaGetLastError());
   }
