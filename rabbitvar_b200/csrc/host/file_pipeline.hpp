@@ -35,7 +35,7 @@ struct FileRunConfig {
   int workers_per_gpu = 3;
   int max_regions_per_job = 256;
   int64_t job_bytes = 24 << 20;  // compressed bytes (all samples) a job aims for
-  int cluster_gap = 2000;
+  int cluster_gap = 16384;  // (one index window: a scan starts at its window's first record anyway)
   int halo = 512;
   bool verbose = false;
   bool keep_contexts = false;  // do not rv_destroy the worker contexts at the end (a CLI about to exit)
@@ -68,17 +68,17 @@ inline uint64_t bai_coffset(const rvio::BaiIndex& bai, int tid, int64_t pos0) {
   return v >> 16;
 }
 
-// compressed bytes a region is expected to span: its share of the 16 kb index windows it touches
-inline int64_t region_bytes(const rvio::BaiIndex& bai, int tid, int32_t start, int32_t end) {
-  const int64_t w0 = ((int64_t)start - 1) >> 14, w1 = (int64_t)end >> 14;
+// compressed bytes of the 16 kb index windows [w0, w1] of `tid`
+inline int64_t window_bytes(const rvio::BaiIndex& bai, int tid, int64_t w0, int64_t w1) {
+  if (w1 < w0) return 0;
   const uint64_t a = bai_coffset(bai, tid, w0 << 14), b = bai_coffset(bai, tid, (w1 + 1) << 14);
-  if (b <= a) return 0;
-  const double share = (double)(end - start + 1) / (double)((w1 - w0 + 1) << 14);
-  return (int64_t)((double)(b - a) * (share > 1.0 ? 1.0 : share));
+  return b > a ? (int64_t)(b - a) : 0;
 }
 
 // Cuts the region list into jobs: consecutive regions of one contig, at most max_regions_per_job, closed when the
-// compressed bytes the job's regions span (summed over the samples) reach job_bytes.
+// compressed bytes of the index windows the job's regions touch (each window once, summed over the samples) reach
+// job_bytes.  Counting windows rather than region lengths keeps a panel of short amplicons on a deep BAM from
+// collapsing into a few huge jobs: an amplicon's reads are all of its window's bytes.
 inline void plan_jobs(const FileRunConfig& c, const std::vector<RegionSpec>& specs, const rvio::BamHeader& hdr,
                       const rvio::BaiIndex& bai, const rvio::BamHeader* hdr2, const rvio::BaiIndex* bai2,
                       std::vector<FileJob>* jobs) {
@@ -87,12 +87,17 @@ inline void plan_jobs(const FileRunConfig& c, const std::vector<RegionSpec>& spe
     FileJob j;
     const int tid = hdr.tid_of(specs[i].chr);
     const int tid2 = hdr2 ? hdr2->tid_of(specs[i].chr) : -1;
-    int64_t bytes = 0;
+    int64_t bytes = 0, w_done = -1;  // windows up to w_done are counted (regions of a job mostly ascend)
     size_t k = i;
     while (k < specs.size() && specs[k].chr == specs[i].chr && (int)(k - i) < c.max_regions_per_job) {
       if (k > i && bytes >= c.job_bytes) break;
-      if (tid >= 0) bytes += region_bytes(bai, tid, specs[k].start, specs[k].end);
-      if (bai2 && tid2 >= 0) bytes += region_bytes(*bai2, tid2, specs[k].start, specs[k].end);
+      int64_t w0 = ((int64_t)specs[k].start - 1) >> 14, w1 = (int64_t)specs[k].end >> 14;
+      if (w0 < 0) w0 = 0;
+      if (w1 < w_done - 64 || w0 > w_done) w_done = w0 - 1;  // a jump backwards / a gap: start counting afresh
+      if (w0 <= w_done) w0 = w_done + 1;
+      if (tid >= 0) bytes += window_bytes(bai, tid, w0, w1);
+      if (bai2 && tid2 >= 0) bytes += window_bytes(*bai2, tid2, w0, w1);
+      if (w1 > w_done) w_done = w1;
       j.specs.push_back(specs[k++]);
     }
     jobs->push_back(std::move(j));
