@@ -8,6 +8,8 @@
 #pragma once
 #include "../../../include/rabbitvar_b200.h"
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #if defined(__CUDACC__)
 #define RV_HD __host__ __device__ __forceinline__
@@ -662,8 +664,8 @@ RV_HD bool fast_obs(const FastDesc& d, int p, const uint8_t* pool, int* allele, 
 //   void event(const rv_event&)
 //   void max_read_len(int tlen)
 //   void kept(int aligned_bases) ; void unsupported()
-//   bool scan_segment(P, rd, ref, m_start, rp, len, indel_follows, SegDesc*)   is the stretch plain? (scan_plain_segment,
-//                                                              or a faster equivalent; false = take the per-base walk)
+//   int scan_segment(P, rd, ref, m_start, rp, len, indel_follows, SegDesc*)    scan_plain_segment or a faster equivalent:
+//                                                              0 = take the per-base walk, 1 = plain, 2 = splittable
 //   bool segment(const SegDesc&, bool dir, int mapq, int nm)   a plain matched stretch; a sink that returns false gets
 //                                                              the per-base observations
 // ------------------------------------------------------------------------------------------------
@@ -691,35 +693,80 @@ struct SegDesc {
   uint32_t ml[4];            // up to eight mismatches, 16 bits each, oldest in the highest used bits:
                              // 0x8000 | offset << 2 | allele of the read base
   int n_mm;
+  int p_first, p_last;       // scan result 2 (splittable): offsets of the first / last base the literal walk must see
 };
+// Result of a stretch scan: 0 = take the literal walk for all of it, 1 = plain, 2 = plain apart from the bases
+// [p_first - (vext + 1), p_last]: what lies before and after that range is plain on its own (split_plain_stretch).
+// A base is flagged when it is not A/C/G/T, when it is a mismatch (or such a base) within vext + 1 bases after another
+// one — the second element of a close pair; the first lies at most vext + 1 before it — or, with an indel following
+// under -k 1, a mismatch among the last vext bases.  The multi-nucleotide loop started at the first element of a pair
+// ends at its last flagged element (nothing within vext + 1 after it mismatches), so the literal walk of
+// [p_first - (vext + 1), p_last] is self-contained.
 
-RV_HDN bool scan_plain_segment(const rv_params& P, const ReadView& rd, const RefView& ref, int m_start, int rp, int len,
-                               bool indel_follows, SegDesc* out) {
-  if (len <= 0 || len > 8192) return false;
-  if (!ref.has(m_start) || !ref.has(m_start + len - 1)) return false;
+RV_HDN int scan_plain_segment(const rv_params& P, const ReadView& rd, const RefView& ref, int m_start, int rp, int len,
+                              bool indel_follows, SegDesc* out) {
+  if (len <= 0 || len > 8192) return 0;
+  if (!ref.has(m_start) || !ref.has(m_start + len - 1)) return 0;
   const int D = P.vext + 1;
-  int last_mm = -100000, n_mm = 0;
+  int last_mm = -100000, n_mm = 0, p_first = -1, p_last = -1;
   uint32_t blocks = 0;
   unsigned long long lo = 0, hi = 0;
   for (int k = 0; k < len; ++k) {
     const char b = rd.base(rp + k);
     const int al = allele_of(b);
-    if (al < 0) return false;
     const char rc = ref.bases[m_start + k - ref.base_pos];
-    if (rc != b) {
-      if (k - last_mm <= D) return false;
-      if (indel_follows && P.local_realign && len - k <= P.vext) return false;
+    if (al < 0 || rc != b) {
+      bool flag = al < 0 || k - last_mm <= D || (indel_follows && P.local_realign && len - k <= P.vext);
       last_mm = k;
-      if (++n_mm > 8) return false;
-      blocks |= 1u << ((k >> 4) < 15 ? (k >> 4) : 15);
-      hi = (hi << 16) | (lo >> 48);
-      lo = (lo << 16) | (unsigned long long)(0x8000u | ((uint32_t)k << 2) | (uint32_t)al);
+      if (flag) {
+        if (p_first < 0) p_first = k;
+        p_last = k;
+      }
+      if (al >= 0) {
+        if (++n_mm > 8) return 0;
+        blocks |= 1u << ((k >> 4) < 15 ? (k >> 4) : 15);
+        hi = (hi << 16) | (lo >> 48);
+        lo = (lo << 16) | (unsigned long long)(0x8000u | ((uint32_t)k << 2) | (uint32_t)al);
+      }
     }
   }
   out->mm_blocks = blocks;
   out->ml[0] = (uint32_t)lo; out->ml[1] = (uint32_t)(lo >> 32); out->ml[2] = (uint32_t)hi; out->ml[3] = (uint32_t)(hi >> 32);
   out->n_mm = n_mm;
-  return true;
+  out->p_first = p_first;
+  out->p_last = p_last;
+  if (p_first < 0) return 1;
+  return D <= 7 ? 2 : 0;
+}
+
+// The mismatch list of the sub-stretch [k0, k1) of a scanned stretch (entries re-based to k0).
+RV_HDN void sub_mismatch_list(const SegDesc& full, int k0, int k1, SegDesc* out) {
+  unsigned long long lo = (unsigned long long)full.ml[0] | ((unsigned long long)full.ml[1] << 32);
+  unsigned long long hi = (unsigned long long)full.ml[2] | ((unsigned long long)full.ml[3] << 32);
+  // entries are stored newest (largest offset) in the low bits: collect, then re-insert oldest first
+  uint32_t e[8];
+  int n = 0;
+  for (int j = 0; j < full.n_mm && j < 8; ++j) {
+    e[n++] = (uint32_t)lo & 0xffffu;
+    lo = (lo >> 16) | (hi << 48);
+    hi >>= 16;
+  }
+  unsigned long long olo = 0, ohi = 0;
+  uint32_t blocks = 0;
+  int m = 0;
+  for (int j = n - 1; j >= 0; --j) {
+    const int k = (int)((e[j] >> 2) & 0x1fffu);
+    if (k < k0 || k >= k1) continue;
+    const int kk = k - k0;
+    blocks |= 1u << ((kk >> 4) < 15 ? (kk >> 4) : 15);
+    ohi = (ohi << 16) | (olo >> 48);
+    olo = (olo << 16) | (unsigned long long)(0x8000u | ((uint32_t)kk << 2) | (e[j] & 3u));
+    m++;
+  }
+  out->mm_blocks = blocks;
+  out->ml[0] = (uint32_t)olo; out->ml[1] = (uint32_t)(olo >> 32); out->ml[2] = (uint32_t)ohi; out->ml[3] = (uint32_t)(ohi >> 32);
+  out->n_mm = m;
+  out->p_first = out->p_last = -1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -747,6 +794,13 @@ RV_HD uint32_t rv_bswap32(uint32_t v) {
   return __byte_perm(v, 0, 0x0123);
 #else
   return (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24);
+#endif
+}
+RV_HD int rv_ctz32(uint32_t v) {  // v != 0
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)v) - 1;
+#else
+  return __builtin_ctz(v);
 #endif
 }
 RV_HD int rv_clz32(uint32_t v) {
@@ -786,6 +840,7 @@ struct PlainScan {
   unsigned long long ml_lo, ml_hi;
   int ml_n;
   uint32_t special;  // a read base that is not A, C, G, T was seen
+  int p_first, p_last;  // offsets of the first / last flagged base (see scan_plain_segment), -1 = none
 };
 RV_HD bool simd_plain_scan(const uint32_t* sq, const uint32_t* ref4, int E0, int rp0, int ml, int D,
                                                 PlainScan* out) {
@@ -796,7 +851,7 @@ RV_HD bool simd_plain_scan(const uint32_t* sq, const uint32_t* ref4, int E0, int
   uint32_t r_lo = rw[0];
   uint32_t prev = 0, bad = 0, seen = 0, spec = 0, mm_blocks = 0;
   unsigned long long ml_lo = 0, ml_hi = 0;
-  int ml_n = 0;
+  int ml_n = 0, p_first = -1, p_last = -1;
   for (int wi = w_first; wi <= w_last; ++wi) {
     const uint32_t r_hi = *++rw;
     const uint32_t rf = rv_funnel_l(r_hi, r_lo, sh);
@@ -814,24 +869,34 @@ RV_HD bool simd_plain_scan(const uint32_t* sq, const uint32_t* ref4, int E0, int
     // that a zero there — padding, or the byte that follows the packed bases — cannot taint its neighbour)
     const uint32_t b8s = (b8 & vm) | (0x11111111u & ~vm);
     const uint32_t special = (~nib_any(b8s) | nib_any(b8s & (b8s - 0x11111111u))) & 0x11111111u & vm;
+    // close pairs: a mismatch — or a base that is not A/C/G/T, which the multi-nucleotide loop would take in as well —
+    // within D bases after another one
+    const uint32_t nzs = nz | special;
     uint32_t near;
     if (D == 3) {
-      near = nz & (rv_funnel_r(nz, prev, 4) | rv_funnel_r(nz, prev, 8) | rv_funnel_r(nz, prev, 12));
+      near = nzs & (rv_funnel_r(nzs, prev, 4) | rv_funnel_r(nzs, prev, 8) | rv_funnel_r(nzs, prev, 12));
     } else if (D <= 7) {
       near = 0;
-      for (int d = 1; d <= D; ++d) near |= nz & rv_funnel_r(nz, prev, 4 * d);
+      for (int d = 1; d <= D; ++d) near |= nzs & rv_funnel_r(nzs, prev, 4 * d);
     } else {
-      near = (nz & (nz - 1)) | ((nz && seen) ? 1u : 0u);  // conservative: any two mismatches in the stretch
-      seen |= nz;
+      near = (nzs & (nzs - 1)) | ((nzs && seen) ? 1u : 0u);  // conservative: any two mismatches in the stretch
+      seen |= nzs;
     }
-    bad |= near | special;
+    const uint32_t flagged = near | special;
+    if (flagged) {  // base 8*wi + i has its flag at bit 28 - 4i
+      const int f_lo = 8 * wi + (rv_clz32(flagged) >> 2) - rp0;
+      const int f_hi = 8 * wi + 7 - (rv_ctz32(flagged) >> 2) - rp0;
+      if (p_first < 0) p_first = f_lo;
+      p_last = f_hi;
+    }
+    bad |= flagged;
     spec |= special;
-    prev = nz;
-    if (nz) {  // 16-base blocks of the stretch this word's mismatches may lie in (a word touches at most two)
+    prev = nzs;
+    if (nz & ~special) {  // 16-base blocks of the stretch this word's mismatches may lie in (a word touches at most two)
       const int k_lo = 8 * wi - rp0 > 0 ? 8 * wi - rp0 : 0;
       const int k_hi = 8 * wi + 7 - rp0 < ml - 1 ? 8 * wi + 7 - rp0 : ml - 1;
       mm_blocks |= (1u << ((k_lo >> 4) < 15 ? (k_lo >> 4) : 15)) | (1u << ((k_hi >> 4) < 15 ? (k_hi >> 4) : 15));
-      for (uint32_t z = nz; z;) {  // the mismatches themselves: base 8*wi + i has its flag at bit 28 - 4i
+      for (uint32_t z = nz & ~special; z;) {  // the A/C/G/T mismatches themselves: base 8*wi + i has its flag at bit 28 - 4i
         const int i = rv_clz32(z) >> 2;
         z &= ~(0x10000000u >> (4 * i));
         const uint32_t en = 0x8000u | ((uint32_t)(8 * wi + i - rp0) << 2) | ((uint32_t)nib_allele((b8 >> (28 - 4 * i)) & 15u) & 3u);
@@ -846,6 +911,8 @@ RV_HD bool simd_plain_scan(const uint32_t* sq, const uint32_t* ref4, int E0, int
   out->ml_hi = ml_hi;
   out->ml_n = ml_n;
   out->special = spec;
+  out->p_first = p_first;
+  out->p_last = p_last;
   return bad == 0;
 }
 // is any listed mismatch among the first `head` or the last `tail` bases of a stretch of ml bases?
@@ -861,6 +928,27 @@ RV_HD bool mismatch_near_ends(const PlainScan& ps, int ml, int head, int tail) {
   return ps.ml_n > 8;  // more mismatches than the list holds: unknown, say yes
 }
 
+
+// scan_plain_segment's verdict from the nibble-SIMD proof (the caller has checked the window and E0 >= 0)
+RV_HD int simd_scan_kind(const rv_params& P, const uint32_t* sq, const uint32_t* ref4, int E0, int rp, int len, bool indel_follows,
+                         PlainScan* ps) {
+  const bool clean = simd_plain_scan(sq, ref4, E0, rp, len, P.vext + 1, ps);
+  if (ps->ml_n > 8) return 0;
+  if (indel_follows && P.local_realign) {  // mismatches among the last vext bases are flagged as well
+    unsigned long long lo = ps->ml_lo, hi = ps->ml_hi;
+    for (int j = 0; j < ps->ml_n; ++j) {
+      const int k = (int)((lo >> 2) & 0x1fffu);
+      if (len - k <= P.vext) {
+        if (ps->p_first < 0 || k < ps->p_first) ps->p_first = k;
+        if (k > ps->p_last) ps->p_last = k;
+      }
+      lo = (lo >> 16) | (hi << 48);
+      hi >>= 16;
+    }
+  }
+  if (clean && ps->p_first < 0) return 1;
+  return P.vext + 1 <= 7 ? 2 : 0;
+}
 
 struct WalkState {
   int start, rp, re, offset, clen;  // start, readPositionIncluding/ExcludingSoftClipped, offset, cigar_element_length
@@ -1484,12 +1572,17 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
         return false;
       }
     }
+    int loop_from = w.offset, loop_end = w.clen;  // the per-base loop below covers [loop_from, loop_end) of the op
+    SegDesc suffix;             // a plain tail of the stretch, emitted once the loop has reached it
+    bool have_suffix = false;
     if (trim_after == 0 && w.clen - w.offset > 0 && nm >= 0 && nm <= 127 && rlen < 65536) {
       const bool indel_follows = ci + 1 < n_cigar && is_id(c_op(cg.op[ci + 1]));
+      const int len = w.clen - w.offset;
       SegDesc sd;
-      if (sink.scan_segment(P, rd, ref, w.start, w.rp, w.clen - w.offset, indel_follows, &sd)) {
+      const int kind = sink.scan_segment(P, rd, ref, w.start, w.rp, len, indel_follows, &sd);
+      if (kind == 1) {
         sd.m_start = w.start;
-        sd.len = w.clen - w.offset;
+        sd.len = len;
         sd.rp = w.rp;
         sd.re = w.re;
         sd.rlen = rlen;
@@ -1499,6 +1592,43 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
           w.re += sd.len;
           if (w.start > R.end) return true;
           return false;
+        }
+      } else if (kind == 2) {
+        // plain apart from [p_first - (vext + 1), p_last]: what lies before and after goes to the gather kernel, the
+        // literal loop only sees the flagged bases and the vext + 1 before them (stretches under 16 bases are not worth
+        // a descriptor)
+        int kp = sd.p_first - (vext + 1), ks = sd.p_last + 1;
+#if !defined(__CUDA_ARCH__)
+        if (getenv("RV_SPLIT_DEBUG")) fprintf(stderr, "split: start %d rp %d len %d flagged [%d,%d] n_mm %d\n", w.start, w.rp, len, sd.p_first, sd.p_last, sd.n_mm);
+#endif
+        if (kp < 16) kp = 0;
+        if (len - ks < 16) ks = len;
+        if (ks < len) {
+          sub_mismatch_list(sd, ks, len, &suffix);
+          suffix.m_start = w.start + ks;
+          suffix.len = len - ks;
+          suffix.rp = w.rp + ks;
+          suffix.re = w.re + ks;
+          suffix.rlen = rlen;
+        }
+        if (kp > 0) {
+          SegDesc pre;
+          sub_mismatch_list(sd, 0, kp, &pre);
+          pre.m_start = w.start;
+          pre.len = kp;
+          pre.rp = w.rp;
+          pre.re = w.re;
+          pre.rlen = rlen;
+          if (sink.segment(pre, dir, mapq, nm)) {
+            w.start += kp;
+            w.rp += kp;
+            w.re += kp;
+            loop_from += kp;  // (w.offset itself keeps its value: the op after a folded indel starts from it)
+          }
+        }
+        if (ks < len) {  // (emitted after the loop: its bases record nm minus what the loop folded into keys, quirk A-8)
+          have_suffix = true;
+          loop_end = w.clen - (len - ks);
         }
       }
     }
@@ -1510,7 +1640,8 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
     WordCache c_seq, c_qual, c_ref;
     c_seq.tag = c_qual.tag = c_ref.tag = 0;
     c_seq.w = c_qual.w = c_ref.w = 0;
-    for (int i = w.offset; i < w.clen; i++) {
+    for (;;) {
+    for (int i = loop_from; i < loop_end; i++) {
       bool trim = false;
       if (trim_after != 0) trim = !dir ? (w.rp > trim_after) : (tlen - w.rp > trim_after);
       char ch1_, rc_;  // rc_: reference base at w.start, 0 outside the loaded window
@@ -1700,6 +1831,19 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
       w.start++;
       w.rp++;
       w.re++;
+    }
+    if (!have_suffix) break;
+    // the loop stopped at the suffix' first base (no multi-nucleotide key reaches into it): hand the rest over, or walk
+    // it literally after all when the sink has no room for another descriptor
+    have_suffix = false;
+    if (nm - nmoff >= 0 && sink.segment(suffix, dir, mapq, nm - nmoff)) {
+      w.start += suffix.len;
+      w.rp += suffix.len;
+      w.re += suffix.len;
+      break;
+    }
+    loop_from = loop_end;
+    loop_end = w.clen;
     }
     if (moffset != 0) {
       w.offset = moffset;

@@ -189,21 +189,23 @@ struct ListSink {
     n_ev++;
   }
   // scan_plain_segment with the nibble-SIMD proof (8 bases per step against the 4-bit reference)
-  __device__ __forceinline__ bool scan_segment(const rv_params& P, const ReadView& rv, const RefView& ref, int m_start, int rp, int len,
-                                               bool indel_follows, SegDesc* out) {
-    if (!want_segments || len <= 0 || len > 8192) return false;
+  __device__ __forceinline__ int scan_segment(const rv_params& P, const ReadView& rv, const RefView& ref, int m_start, int rp, int len,
+                                              bool indel_follows, SegDesc* out) {
+    if (!want_segments || len <= 0 || len > 8192) return 0;
     const int E0 = m_start - rp - a->ref_start;
     const int64_t w_lo = ref.lo > a->ref_start ? ref.lo : a->ref_start;
     const int64_t w_hi = (int64_t)ref.hi < a->ref_start + a->ref_n - 1 ? (int64_t)ref.hi : a->ref_start + a->ref_n - 1;
-    if (E0 < 0 || m_start < w_lo || (int64_t)m_start + len - 1 > w_hi) return false;
+    if (E0 < 0 || m_start < w_lo || (int64_t)m_start + len - 1 > w_hi) return 0;
     PlainScan ps;
-    if (!simd_plain_scan((const uint32_t*)rv.seq4, a->ref4, E0, rp, len, P.vext + 1, &ps) || ps.ml_n > 8) return false;
-    if (indel_follows && P.local_realign && mismatch_near_ends(ps, len, 0, P.vext)) return false;
+    const int kind = simd_scan_kind(P, (const uint32_t*)rv.seq4, a->ref4, E0, rp, len, indel_follows, &ps);
+    if (kind == 0) return 0;
     out->mm_blocks = ps.mm_blocks;
     out->ml[0] = (uint32_t)ps.ml_lo; out->ml[1] = (uint32_t)(ps.ml_lo >> 32);
     out->ml[2] = (uint32_t)ps.ml_hi; out->ml[3] = (uint32_t)(ps.ml_hi >> 32);
     out->n_mm = ps.ml_n;
-    return true;
+    out->p_first = ps.p_first;
+    out->p_last = ps.p_last;
+    return kind;
   }
   __device__ __forceinline__ bool segment(const SegDesc& sd, bool dir, int mapq, int nm) {
     if (!want_segments) return false;

@@ -76,31 +76,35 @@ struct SimSink {
   const uint8_t* cur_pool;
   int r_start, r_end;
   bool use_segments;
-  bool scan_segment(const rv_params& P, const rvk::ReadView& rd, const rvk::RefView& ref, int m_start, int rp, int len,
-                    bool indel_follows, rvk::SegDesc* out) {
-    if (!use_segments) return false;
-    const bool plain = rvk::scan_plain_segment(P, rd, ref, m_start, rp, len, indel_follows, out);
+  int scan_segment(const rv_params& P, const rvk::ReadView& rd, const rvk::RefView& ref, int m_start, int rp, int len,
+                   bool indel_follows, rvk::SegDesc* out) {
+    if (!use_segments) return 0;
+    const int kind = rvk::scan_plain_segment(P, rd, ref, m_start, rp, len, indel_follows, out);
     if (ref4) {  // cross-check: the nibble-SIMD proof the kernels use must decide (and list) the same
-      bool simd = false;
+      int simd = 0;
       rvk::PlainScan ps;
+      ps.p_first = ps.p_last = -1;
       const int E0 = m_start - rp - ref.base_pos;
       const int64_t w_lo = ref.lo > ref.base_pos ? ref.lo : ref.base_pos;
       const int64_t w_hi = (int64_t)ref.hi < ref.base_pos + ref.n - 1 ? (int64_t)ref.hi : ref.base_pos + ref.n - 1;
-      if (len > 0 && len <= 8192 && E0 >= 0 && m_start >= w_lo && (int64_t)m_start + len - 1 <= w_hi && ((uintptr_t)rd.seq4 & 3) == 0) {
-        simd = rvk::simd_plain_scan((const uint32_t*)rd.seq4, ref4, E0, rp, len, P.vext + 1, &ps) && ps.ml_n <= 8;
-        if (simd && indel_follows && P.local_realign && rvk::mismatch_near_ends(ps, len, 0, P.vext)) simd = false;
-      }
+      if (len > 0 && len <= 8192 && E0 >= 0 && m_start >= w_lo && (int64_t)m_start + len - 1 <= w_hi && ((uintptr_t)rd.seq4 & 3) == 0)
+        simd = rvk::simd_scan_kind(P, (const uint32_t*)rd.seq4, ref4, E0, rp, len, indel_follows, &ps);
       n_scan++;
-      if (simd != plain && getenv("RV_SCAN_DEBUG"))
-        fprintf(stderr, "scan diff: pos %d rp %d len %d indel_follows %d plain %d simd %d n_mm scalar %d simd %d E0 %d\n", m_start, rp, len, (int)indel_follows,
-                (int)plain, (int)simd, plain ? out->n_mm : -1, ps.ml_n, E0);
-      if (simd != plain) n_scan_diff++;
-      else if (plain && ((ps.mm_blocks != 0) != (out->mm_blocks != 0) || (uint32_t)ps.ml_lo != out->ml[0] || (uint32_t)(ps.ml_lo >> 32) != out->ml[1] ||
-                         (uint32_t)ps.ml_hi != out->ml[2] || (uint32_t)(ps.ml_hi >> 32) != out->ml[3]))
+      bool same = simd == kind;
+      if (same && kind != 0)
+        same = (ps.mm_blocks != 0) == (out->mm_blocks != 0) && (uint32_t)ps.ml_lo == out->ml[0] && (uint32_t)(ps.ml_lo >> 32) == out->ml[1] &&
+               (uint32_t)ps.ml_hi == out->ml[2] && (uint32_t)(ps.ml_hi >> 32) == out->ml[3] && ps.p_first == out->p_first && ps.p_last == out->p_last;
+      if (!same) {
         n_scan_diff++;
+        if (getenv("RV_SCAN_DEBUG"))
+          fprintf(stderr, "scan diff: pos %d rp %d len %d indel_follows %d scalar %d simd %d n_mm %d/%d flagged [%d,%d]/[%d,%d]\n", m_start, rp, len,
+                  (int)indel_follows, kind, simd, out->n_mm, ps.ml_n, out->p_first, out->p_last, ps.p_first, ps.p_last);
+      }
+      if (kind == 2) n_split++;
     }
-    return plain;
+    return kind;
   }
+  long n_split = 0;
   const uint32_t* ref4 = NULL;
   long n_scan = 0, n_scan_diff = 0;
   bool segment(const rvk::SegDesc& d, bool dir, int mapq, int nm) {
@@ -110,6 +114,8 @@ struct SimSink {
     const uint8_t* qual = seq4 + ((cur_read->l_seq + 1) >> 1);
     in_segment = true;
     n_segbases += d.len;
+    if (getenv("RV_DEBUG_POS") && atoi(getenv("RV_DEBUG_POS")) >= d.m_start && atoi(getenv("RV_DEBUG_POS")) < d.m_start + d.len)
+      fprintf(stderr, "segment start %d len %d rp %d re %d rlen %d dir %d nm %d n_mm %d read pos %d\n", d.m_start, d.len, d.rp, d.re, d.rlen, (int)dir, nm, d.n_mm, cur_read->pos);
     for (int k = 0; k < d.len; ++k) {
       const int p = d.m_start + k;
       if (p < r_start || p > r_end) continue;
@@ -273,7 +279,7 @@ int main(int argc, char** argv) {
     ref.n = (int64_t)refseq.size();
     std::vector<uint32_t> ref4((size_t)ref.n / 8 + 16);
     for (size_t w = 0; w < ref4.size(); ++w) ref4[w] = rvk::pack_ref8(refseq.data(), ref.n, (int64_t)w);
-    long n_scan = 0, n_scan_diff = 0;
+    long n_scan = 0, n_scan_diff = 0, n_split = 0;
     for (size_t r = 0; r < regs.size(); ++r) {
       RegionPileup& R = rp[r];
       R.region_idx = (int)r;
@@ -321,10 +327,10 @@ int main(int argc, char** argv) {
       }
       st.n_reads_kept += s.kept_reads; st.n_aligned_bases += s.kept_bases;
       st.n_unsupported += s.unsup; st.n_overflow += s.over;
-      n_scan += s.n_scan; n_scan_diff += s.n_scan_diff;
+      n_scan += s.n_scan; n_scan_diff += s.n_scan_diff; n_split += s.n_split;
       if (getenv("RV_SCAN_DEBUG")) fprintf(stderr, "region %zu: per-base singles %ld, adj %ld, cov %ld, segment bases %ld\n", r, s.n_direct, s.n_adj, s.n_cov, s.n_segbases);
     }
-    fprintf(stderr, "rv_dump[sim]: %ld stretches scanned, %ld where the nibble-SIMD proof and the scalar scan disagree\n", n_scan, n_scan_diff);
+    fprintf(stderr, "rv_dump[sim]: %ld stretches scanned (%ld split around a cluster), %ld where the nibble-SIMD proof and the scalar scan disagree\n", n_scan, n_split, n_scan_diff);
     if (n_scan_diff) return 4;
     st.n_events = (int64_t)events.size();
   } else {
