@@ -91,11 +91,7 @@ int rvh_run_files(const rv_params* params, const char* fasta, const char* bam, c
                   const char* const* gene, int32_t decode_threads, int32_t gpus, int32_t first_device,
                   char** tsv_out, int64_t* tsv_len, double* cov_info /* [4]: sum T, sites T, sum N, sites N; may be NULL */);
 void rvh_free(void* p);
-/* Page-locks / unlocks a host buffer for the copy engine (cudaHostRegister): the file pipeline pins a decoded job's
- * buffers right before their upload.  Returns 0, or a negative rv error when the runtime refuses (the copy then simply
- * takes the pageable path). */
-int rvh_host_register(const void* p, int64_t bytes);
-int rvh_host_unregister(const void* p);
+
 
 #ifdef __cplusplus
 }

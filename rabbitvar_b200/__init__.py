@@ -122,7 +122,7 @@ ABI_SYMBOLS = [
     "rvh_batch_pool_bytes", "rvh_batch_max_ref_span", "rvh_batch_pin", "rvh_batch_free", "rvh_make_regions", "rvh_fetch_ref",
     "rvh_call_regions", "rvh_install_patch", "rvh_last_error",
     "rvh_pipeline_create", "rvh_pipeline_destroy", "rvh_pipeline_run", "rvh_pipeline_run_paired", "rvh_pipeline_launch_count",
-    "rvh_inflate_block", "rvh_crc32", "rvh_run_files", "rvh_free", "rvh_host_register", "rvh_host_unregister",
+    "rvh_inflate_block", "rvh_crc32", "rvh_run_files", "rvh_free",
 ]
 
 

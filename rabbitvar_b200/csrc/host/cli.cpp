@@ -238,7 +238,6 @@ int main(int argc, char** argv) {
   fc.job_bytes = (int64_t)c.job_mb << 20;
   fc.halo = c.halo;
   fc.keep_contexts = true;  // the process exits right after the run
-  fc.pin_jobs = getenv("RV_PIN_JOBS") ? atoi(getenv("RV_PIN_JOBS")) != 0 : false;
   std::string tsv;
   FileRunStats st;
   std::vector<std::string> errors;

@@ -18,7 +18,6 @@
 // panel BED on a deep BAM does not pull the inter-region gaps into memory (the reference fetches per region).
 #pragma once
 #include "pipeline.hpp"
-#include "../../../include/rabbitvar_b200_host.h"
 #include <atomic>
 #include <condition_variable>
 #include <deque>
@@ -39,7 +38,6 @@ struct FileRunConfig {
   int cluster_gap = 16384;  // (one index window: a scan starts at its window's first record anyway)
   int halo = 512;
   bool verbose = false;
-  bool pin_jobs = false;       // cudaHostRegister a job's read buffers around its upload
   bool keep_contexts = false;  // do not rv_destroy the worker contexts at the end (a CLI about to exit)
   bool decode_only = false;  // measurement aid: run the decode stage alone (no device needed), print nothing
 };
@@ -314,17 +312,6 @@ inline int run_files(const FileRunConfig& c, const std::vector<RegionSpec>& spec
               }
               std::vector<std::string> genes;
               for (size_t i = 0; i < job.specs.size(); ++i) genes.push_back(job.specs[i].gene);
-              // page-lock the job's buffers for the upload (DMA straight from them instead of the driver's staged copy)
-              const bool pin = c.pin_jobs && attempt == 0 && !job.batch.reads.empty();
-              bool pinned_r = false, pinned_p = false;
-              if (pin) {
-                pinned_r = rvh_host_register(job.batch.reads.data(), (int64_t)(job.batch.reads.size() * sizeof(rv_read))) == RV_OK;
-                pinned_p = rvh_host_register(job.batch.pool.data(), (int64_t)job.batch.pool.size()) == RV_OK;
-              }
-              struct Unpin {
-                const void *a, *b;
-                ~Unpin() { if (a) rvh_host_unregister(a); if (b) rvh_host_unregister(b); }
-              } unpin{pinned_r ? (const void*)job.batch.reads.data() : NULL, pinned_p ? (const void*)job.batch.pool.data() : NULL};
               job.tsv.clear();
               job.err.clear();
               const int rc = somatic ? run_batch_somatic(ctx, c.P, job.batch, job.regs, genes, job.refseq, job.ref_lo, c.sample, job.specs[0].chr, 3, c.halo, &job.tsv, &job.tm, &job.err)

@@ -338,16 +338,7 @@ int rvh_run_files(const rv_params* params, const char* fasta, const char* bam, c
   }
 }
 void rvh_free(void* p) { free(p); }
-int rvh_host_register(const void* p, int64_t bytes) {
-  if (!p || bytes <= 0) return RV_ERR_ARG;
-  if (cudaHostRegister((void*)p, (size_t)bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return RV_ERR_CUDA; }
-  return RV_OK;
-}
-int rvh_host_unregister(const void* p) {
-  if (!p) return RV_ERR_ARG;
-  if (cudaHostUnregister((void*)p) != cudaSuccess) { cudaGetLastError(); return RV_ERR_CUDA; }
-  return RV_OK;
-}
+
 
 rvh_batch* rvh_load_bam(const char* bam_path, const char* chr, int32_t start, int32_t end, int32_t* chr_len_out) {
   try {
