@@ -218,6 +218,11 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
 void rv_destroy(rv_ctx* ctx);
 const char* rv_last_error(const rv_ctx* ctx);
 int rv_sync(rv_ctx* ctx);
+/* Lazy mode (off by default): rv_pileup / rv_score / rv_score_positions only enqueue their kernels — no stream
+ * synchronisation, no read-back of the statistics.  The host's view is settled by rv_sync or by the first call that
+ * reads a result (rv_get_pileup_stats, rv_fetch_*, rv_variant_count, rv_last_*_ms), which then also returns the
+ * RV_ERR_OVERFLOW the enqueuing call could not report.  For callers that run several batches' kernels back to back. */
+int rv_set_lazy(rv_ctx* ctx, int on);
 /* Table halo (limits.halo) of the context, and replacement of its parameter block between batches. */
 int32_t rv_ctx_halo(const rv_ctx* ctx);
 int rv_set_params(rv_ctx* ctx, const rv_params* params);

@@ -113,7 +113,7 @@ class Timing(C.Structure):
 # every symbol include/*.h declares (checked by tests without a GPU)
 ABI_SYMBOLS = [
     "rv_abi_version", "rv_device_count", "rv_warmup", "rv_default_params", "rv_default_limits", "rv_create", "rv_destroy",
-    "rv_last_error", "rv_sync", "rv_ctx_halo", "rv_set_params", "rv_set_reference", "rv_push_reads", "rv_push_reads_range", "rv_push_reads_ranges", "rv_push_reads_device", "rv_set_regions",
+    "rv_last_error", "rv_sync", "rv_set_lazy", "rv_ctx_halo", "rv_set_params", "rv_set_reference", "rv_push_reads", "rv_push_reads_range", "rv_push_reads_ranges", "rv_push_reads_device", "rv_set_regions",
     "rv_pileup", "rv_score", "rv_score_positions", "rv_get_pileup_stats", "rv_fetch_max_read_len", "rv_fetch_tables", "rv_fetch_rows",
     "rv_fetch_events",
     "rv_apply_patch", "rv_fetch_variants", "rv_cov_summary", "rv_variant_count", "rv_fisher_exact", "rv_last_kernel_ms", "rv_last_pileup_split_ms", "rv_last_pileup_stage_ms", "rv_timer_start",
@@ -405,6 +405,13 @@ class Context:
 
     def sync(self):
         self._ck(lib().rv_sync(self._h), "rv_sync")
+
+    def set_lazy(self, on):
+        self._ck(lib().rv_set_lazy(self._h, 1 if on else 0), "rv_set_lazy")
+
+    def pileup_enqueue(self):
+        """rv_pileup without reading the statistics back (lazy mode keeps it free of host synchronisation)."""
+        self._ck(lib().rv_pileup(self._h), "rv_pileup")
 
     def fetch_variants(self):
         p = C.POINTER(Variant)()

@@ -1277,7 +1277,7 @@ struct rv_ctx {
   rv_params P;
   rv_limits L;
   cudaStream_t stream;
-  cudaEvent_t ev0, ev1, tev0, tev1;
+  cudaEvent_t ev0, ev1, tev0, tev1, pev0, pev1;  // ev: scoring calls, pev: rv_pileup, tev: rv_timer_*
   cudaEvent_t evs[3];      // boundaries between the kernels of the pileup stage
   float split_ms[4];       // classify, tile index + gather, walk, apply
   std::string err;
@@ -1348,6 +1348,10 @@ struct rv_ctx {
   size_t h_variants_cap;
   int32_t* h_max_rl;
   DevStats h_stats;
+  bool lazy;     // rv_set_lazy: rv_pileup / rv_score enqueue only; results are settled at rv_sync or by the first getter
+  bool unsettled;
+  bool unsettled_pileup;
+  std::vector<int64_t> keep_list;  // rv_score_positions' position list while its upload may still be in flight
   float pileup_ms, score_ms;
 };
 
@@ -1373,9 +1377,43 @@ static int fail(rv_ctx* c, int code, const std::string& msg) {
       return fail(ctx, RV_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
   } while (0)
 
+// Lazy mode: brings the host's view (statistics, maxReadLength, kernel times, variant count) up to date with what has
+// been enqueued.  Returns the error a non-lazy rv_pileup / rv_score would have returned.
+static int settle(rv_ctx* ctx) {
+  if (!ctx->unsettled) return RV_OK;
+  ctx->unsettled = false;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(&ctx->h_stats, ctx->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, ctx->stream));
+  if (ctx->unsettled_pileup)
+    CK(cudaMemcpyAsync(ctx->h_max_rl, ctx->d_max_rl, sizeof(int32_t) * ctx->regions.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->h_stats.n_items = (unsigned long long)ctx->n_items;
+  if (ctx->unsettled_pileup) {
+    ctx->unsettled_pileup = false;
+    CK(cudaEventElapsedTime(&ctx->pileup_ms, ctx->pev0, ctx->pev1));
+    CK(cudaEventElapsedTime(&ctx->split_ms[0], ctx->pev0, ctx->evs[0]));
+    CK(cudaEventElapsedTime(&ctx->split_ms[2], ctx->evs[0], ctx->evs[1]));
+    CK(cudaEventElapsedTime(&ctx->split_ms[1], ctx->evs[1], ctx->evs[2]));
+    CK(cudaEventElapsedTime(&ctx->split_ms[3], ctx->evs[2], ctx->pev1));
+  }
+  CK(cudaEventElapsedTime(&ctx->score_ms, ctx->ev0, ctx->ev1));
+  if (ctx->h_stats.n_overflow)
+    return fail(ctx, RV_ERR_OVERFLOW, "pileup dropped events or sparse observations (limits.max_events / limits.max_reads too small)");
+  if (ctx->h_stats.n_variants > (unsigned long long)ctx->L.max_variants)
+    return fail(ctx, RV_ERR_OVERFLOW, "more variants than limits.max_variants");
+  return RV_OK;
+}
+
 extern "C" {
 
 int rv_abi_version(void) { return RV_ABI_VERSION; }
+
+int rv_set_lazy(rv_ctx* ctx, int on) {
+  if (!ctx) return RV_ERR_ARG;
+  const int rc = settle(ctx);
+  ctx->lazy = on != 0;
+  return rc;
+}
 
 int rv_device_count(void) {
   int n = 0;
@@ -1436,6 +1474,9 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return RV_ERR_CUDA;
   rv_ctx* ctx = new rv_ctx();
   memset((void*)&ctx->h_stats, 0, sizeof(ctx->h_stats));
+  ctx->lazy = false;
+  ctx->unsettled = false;
+  ctx->unsettled_pileup = false;
   ctx->device = device;
   ctx->P = *params;
   ctx->L = *limits;
@@ -1476,6 +1517,8 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   CK(cudaEventCreate(&ctx->ev1));
   CK(cudaEventCreate(&ctx->tev0));
   CK(cudaEventCreate(&ctx->tev1));
+  CK(cudaEventCreate(&ctx->pev0));
+  CK(cudaEventCreate(&ctx->pev1));
   for (int k = 0; k < 3; ++k) CK(cudaEventCreate(&ctx->evs[k]));
   const rv_limits& L = ctx->L;
   CK(cudaMalloc(&ctx->d_reads, sizeof(rv_read) * (size_t)L.max_reads));
@@ -1561,6 +1604,8 @@ void rv_destroy(rv_ctx* ctx) {
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->tev0) cudaEventDestroy(ctx->tev0);
   if (ctx->tev1) cudaEventDestroy(ctx->tev1);
+  if (ctx->pev0) cudaEventDestroy(ctx->pev0);
+  if (ctx->pev1) cudaEventDestroy(ctx->pev1);
   for (int k = 0; k < 3; ++k) if (ctx->evs[k]) cudaEventDestroy(ctx->evs[k]);
   delete ctx;
 }
@@ -1577,6 +1622,7 @@ int rv_set_params(rv_ctx* ctx, const rv_params* params) {
 
 int rv_sync(rv_ctx* ctx) {
   if (!ctx) return RV_ERR_ARG;
+  { const int rcs = settle(ctx); if (rcs != RV_OK) return rcs; }
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   return RV_OK;
@@ -1714,7 +1760,8 @@ int rv_pileup(rv_ctx* ctx) {
   if (ctx->regions.empty()) return fail(ctx, RV_ERR_STATE, "rv_set_regions has not been called");
   if (!ctx->reads_dev_view) return fail(ctx, RV_ERR_STATE, "rv_push_reads has not been called");
   CK(cudaSetDevice(ctx->device));
-  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  if (!ctx->lazy && ctx->unsettled) { const int rcs = settle(ctx); if (rcs != RV_OK) return rcs; }
+  CK(cudaEventRecord(ctx->pev0, ctx->stream));
   // no table memset: rv_gather4_kernel stores every row (halo included) before rv_apply_kernel adds to them.
   // One memset clears the statistics, the walk queue counters, the SparseObs cursor and the reach bounds.
   CK(cudaMemsetAsync(ctx->d_stats, 0, COUNTER_BLOCK_BYTES, ctx->stream));
@@ -1815,15 +1862,20 @@ int rv_pileup(rv_ctx* ctx) {
     ctx->launches++;
     CK(cudaGetLastError());
   }
-  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaEventRecord(ctx->pev1, ctx->stream));
+  ctx->tables_fetched = false;
+  if (ctx->lazy) {
+    ctx->unsettled = ctx->unsettled_pileup = true;
+    return RV_OK;
+  }
   CK(cudaMemcpyAsync(&ctx->h_stats, ctx->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_max_rl, ctx->d_max_rl, sizeof(int32_t) * ctx->regions.size(), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  CK(cudaEventElapsedTime(&ctx->pileup_ms, ctx->ev0, ctx->ev1));
-  CK(cudaEventElapsedTime(&ctx->split_ms[0], ctx->ev0, ctx->evs[0]));
+  CK(cudaEventElapsedTime(&ctx->pileup_ms, ctx->pev0, ctx->pev1));
+  CK(cudaEventElapsedTime(&ctx->split_ms[0], ctx->pev0, ctx->evs[0]));
   CK(cudaEventElapsedTime(&ctx->split_ms[2], ctx->evs[0], ctx->evs[1]));
   CK(cudaEventElapsedTime(&ctx->split_ms[1], ctx->evs[1], ctx->evs[2]));
-  CK(cudaEventElapsedTime(&ctx->split_ms[3], ctx->evs[2], ctx->ev1));
+  CK(cudaEventElapsedTime(&ctx->split_ms[3], ctx->evs[2], ctx->pev1));
   ctx->h_stats.n_items = (unsigned long long)ctx->n_items;
   // the patch list stays attached until rv_set_regions / the next rv_apply_patch: a caller that
   // re-runs the same resident batch may score against it again
@@ -1835,6 +1887,7 @@ int rv_pileup(rv_ctx* ctx) {
 
 int rv_get_pileup_stats(rv_ctx* ctx, rv_pileup_stats* o) {
   if (!ctx || !o) return RV_ERR_ARG;
+  { const int rcs = settle(ctx); if (rcs != RV_OK) return rcs; }
   o->n_items = (int64_t)ctx->h_stats.n_items;
   o->n_reads_kept = (int64_t)ctx->h_stats.n_kept;
   o->n_aligned_bases = (int64_t)ctx->h_stats.n_bases;
@@ -1852,6 +1905,7 @@ int rv_get_pileup_stats(rv_ctx* ctx, rv_pileup_stats* o) {
 
 int rv_fetch_max_read_len(rv_ctx* ctx, const int32_t** out, int32_t* n) {
   if (!ctx || !out || !n) return RV_ERR_ARG;
+  { const int rcs = settle(ctx); if (rcs != RV_OK) return rcs; }
   *out = ctx->h_max_rl;
   *n = (int32_t)ctx->regions.size();
   return RV_OK;
@@ -1923,6 +1977,7 @@ int rv_fetch_rows(rv_ctx* ctx, const int32_t* region, const int32_t* pos, int64_
 
 int rv_fetch_events(rv_ctx* ctx, const rv_event** events, int64_t* n_events) {
   if (!ctx || !events || !n_events) return RV_ERR_ARG;
+  { const int rcs = settle(ctx); if (rcs != RV_OK) return rcs; }
   CK(cudaSetDevice(ctx->device));
   size_t n = (size_t)std::min<unsigned long long>(ctx->h_stats.n_events, (unsigned long long)ctx->L.max_events);
   if (n > ctx->h_events_cap) {
@@ -2044,6 +2099,7 @@ int rv_score(rv_ctx* ctx) {
   if (!ctx) return RV_ERR_ARG;
   if (ctx->regions.empty()) return fail(ctx, RV_ERR_STATE, "rv_set_regions has not been called");
   CK(cudaSetDevice(ctx->device));
+  if (!ctx->lazy && ctx->unsettled) { const int rcs = settle(ctx); if (rcs != RV_OK) return rcs; }
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   CK(cudaMemsetAsync(&ctx->d_stats->n_variants, 0, 2 * sizeof(unsigned long long), ctx->stream));
   ScoreArgs a;
@@ -2068,6 +2124,7 @@ int rv_score(rv_ctx* ctx) {
     }
   }
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (ctx->lazy) { ctx->unsettled = true; return RV_OK; }
   CK(cudaMemcpyAsync(&ctx->h_stats.n_variants, &ctx->d_stats->n_variants, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaEventElapsedTime(&ctx->score_ms, ctx->ev0, ctx->ev1));
@@ -2080,7 +2137,8 @@ int rv_score_positions(rv_ctx* ctx, const int32_t* region, const int32_t* pos, i
   if (!ctx || n < 0 || (n && (!region || !pos))) return RV_ERR_ARG;
   if (ctx->regions.empty()) return fail(ctx, RV_ERR_STATE, "rv_set_regions has not been called");
   CK(cudaSetDevice(ctx->device));
-  std::vector<int64_t> tab((size_t)n);
+  std::vector<int64_t>& tab = ctx->keep_list;
+  tab.resize((size_t)n);
   for (int64_t i = 0; i < n; ++i) {
     const int r = region[i];
     if (r < 0 || r >= (int)ctx->regions.size()) return fail(ctx, RV_ERR_ARG, "rv_score_positions: bad region");
@@ -2103,8 +2161,9 @@ int rv_score_positions(rv_ctx* ctx, const int32_t* region, const int32_t* pos, i
     CK(cudaGetLastError());
   }
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (ctx->lazy) { ctx->unsettled = true; return RV_OK; }  // (`tab` lives in the context)
   CK(cudaMemcpyAsync(&ctx->h_stats.n_variants, &ctx->d_stats->n_variants, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));  // also keeps `tab` alive until the copy has been consumed
+  CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaEventElapsedTime(&ctx->score_ms, ctx->ev0, ctx->ev1));
   if (ctx->h_stats.n_variants > (unsigned long long)ctx->L.max_variants)
     return fail(ctx, RV_ERR_OVERFLOW, "more variants than limits.max_variants");
@@ -2113,6 +2172,7 @@ int rv_score_positions(rv_ctx* ctx, const int32_t* region, const int32_t* pos, i
 
 int rv_fetch_variants(rv_ctx* ctx, const rv_variant** variants, int64_t* n_variants) {
   if (!ctx || !variants || !n_variants) return RV_ERR_ARG;
+  { const int rcs = settle(ctx); if (rcs != RV_OK) return rcs; }
   CK(cudaSetDevice(ctx->device));
   size_t n = (size_t)ctx->h_stats.n_variants;
   if (n > ctx->h_variants_cap) {
@@ -2155,7 +2215,11 @@ int rv_cov_summary(rv_ctx* ctx, int64_t* sum, int64_t* covered) {
   return RV_OK;
 }
 
-int64_t rv_variant_count(const rv_ctx* ctx) { return ctx ? (int64_t)ctx->h_stats.n_variants : 0; }
+int64_t rv_variant_count(const rv_ctx* ctx) {
+  if (!ctx) return 0;
+  settle(const_cast<rv_ctx*>(ctx));
+  return (int64_t)ctx->h_stats.n_variants;
+}
 
 int rv_fisher_exact(rv_ctx* ctx, const int32_t* tables, int64_t n, double* out) {
   if (!ctx || (!tables && n) || (!out && n) || n < 0) return RV_ERR_ARG;
@@ -2179,6 +2243,7 @@ int rv_fisher_exact(rv_ctx* ctx, const int32_t* tables, int64_t n, double* out) 
 
 int rv_last_kernel_ms(rv_ctx* ctx, float* pileup_ms, float* score_ms) {
   if (!ctx) return RV_ERR_ARG;
+  { const int rcs = settle(ctx); if (rcs != RV_OK) return rcs; }
   if (pileup_ms) *pileup_ms = ctx->pileup_ms;
   if (score_ms) *score_ms = ctx->score_ms;
   return RV_OK;
@@ -2186,6 +2251,7 @@ int rv_last_kernel_ms(rv_ctx* ctx, float* pileup_ms, float* score_ms) {
 
 int rv_last_pileup_split_ms(rv_ctx* ctx, float* classify_ms, float* gather_ms, float* walk_ms) {
   if (!ctx) return RV_ERR_ARG;
+  { const int rcs = settle(ctx); if (rcs != RV_OK) return rcs; }
   if (classify_ms) *classify_ms = ctx->split_ms[0];
   if (gather_ms) *gather_ms = ctx->split_ms[1];
   if (walk_ms) *walk_ms = ctx->split_ms[2] + ctx->split_ms[3];  // rv_walk_kernel + rv_apply_kernel
@@ -2194,6 +2260,7 @@ int rv_last_pileup_split_ms(rv_ctx* ctx, float* classify_ms, float* gather_ms, f
 
 int rv_last_pileup_stage_ms(rv_ctx* ctx, float out[4]) {
   if (!ctx || !out) return RV_ERR_ARG;
+  { const int rcs = settle(ctx); if (rcs != RV_OK) return rcs; }
   for (int k = 0; k < 4; ++k) out[k] = ctx->split_ms[k];
   return RV_OK;
 }

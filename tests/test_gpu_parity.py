@@ -175,6 +175,58 @@ def test_pileup_is_deterministic_and_additive(built):
     ctx.close()
 
 
+def test_lazy_mode_gives_the_settled_results(built):
+    """rv_set_lazy: rv_pileup / rv_score only enqueue; the first getter settles.  Statistics, variant records and
+    the overflow error must be those of the settled calls."""
+    import ctypes as C
+    import rabbitvar_b200 as rv
+    d = cases.generate("c1_k1")
+    bam, fa = os.path.join(d, "S.bam"), os.path.join(d, "ref.fa")
+    b = rv.HostBatch(bam, "chrS1", 1301, 21300)
+    ref = rv.fetch_ref(fa, "chrS1", 1, b.chr_len)
+    lim = rv.default_limits(max_reads=b.n_reads + 16, max_read_bytes=b.pool_bytes + 64, max_ref_bases=len(ref) + 16)
+    ctx = rv.Context(0, rv.default_params(candidates_only=1), lim)
+    ctx.set_reference(1, ref)
+    ctx.push_reads(b)
+    regs = b.make_regions([1301], [21300])
+    ctx.set_regions(regs)
+    st = ctx.pileup()
+    ctx.score()
+    vp, n = ctx.fetch_variants()
+    want = bytes((C.c_char * (n * C.sizeof(rv.Variant))).from_address(C.addressof(vp.contents)))
+    assert n > 0
+    ctx.set_lazy(True)
+    for _ in range(3):
+        ctx.pileup_enqueue()
+        ctx.score()
+    assert ctx.n_variants() == n
+    vp, n2 = ctx.fetch_variants()
+    got = bytes((C.c_char * (n2 * C.sizeof(rv.Variant))).from_address(C.addressof(vp.contents)))
+    st2 = rv.PileupStats()
+    rv.lib().rv_get_pileup_stats(ctx._h, C.byref(st2))
+    assert (st2.n_aligned_bases, st2.n_reads_kept, st2.n_events) == (st.n_aligned_bases, st.n_reads_kept, st.n_events)
+    a, bms = ctx.kernel_ms()
+    assert a > 0 and bms > 0
+    ctx.set_lazy(False)
+    ctx.close()
+    assert n2 == n and sorted(got[i:i + C.sizeof(rv.Variant)] for i in range(0, len(got), C.sizeof(rv.Variant))) == \
+        sorted(want[i:i + C.sizeof(rv.Variant)] for i in range(0, len(want), C.sizeof(rv.Variant)))
+    # an overflow the enqueuing call could not report comes back from the settling call
+    lim2 = rv.default_limits(max_reads=b.n_reads + 16, max_read_bytes=b.pool_bytes + 64, max_ref_bases=len(ref) + 16,
+                             max_variants=4)
+    ctx = rv.Context(0, rv.default_params(candidates_only=1), lim2)
+    ctx.set_reference(1, ref)
+    ctx.push_reads(b)
+    ctx.set_regions(regs)
+    ctx.set_lazy(True)
+    ctx.pileup_enqueue()
+    ctx.score()
+    with pytest.raises(rv.RabbitVarError):
+        ctx.sync()
+    ctx.close()
+    b.close()
+
+
 def test_pipeline_equals_single_call(built):
     """rvh_pipeline_run (chunks of tiles on several worker contexts, ranged read uploads) must print exactly what one
     rvh_call_regions over all tiles prints."""
