@@ -127,6 +127,10 @@ typedef struct rv_region {
  * = 132 bytes.  Row layout of one allele: */
 enum { RV_F_FWD = 0, RV_F_REV = 1, RV_F_SUM_TP = 2, RV_F_SUM_Q = 3, RV_F_SUM_MAPQ = 4, RV_F_SUM_NM = 5,
        RV_F_HI = 6, RV_F_STD = 7 /* bits 0-15 first tp, 16-23 first q, 24 pstd, 25 qstd */ };
+/* PRECONDITION of pstd / qstd: no base quality of 0.  The reference sets the flags when two observations that follow
+ * each other in BAM order differ and the earlier one is non-zero (parseCigar.cpp:902-914); with tp >= 1 and q >= 1 that
+ * is "not all observations are equal", which is what the tables hold (order-free).  A Phred-0 base that precedes the
+ * others in BAM order would leave the reference's flag unset where this library sets it. */
 #define RV_ROW_U32 8
 #define RV_POS_U32 (4 * RV_ROW_U32)
 

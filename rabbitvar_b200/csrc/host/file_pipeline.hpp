@@ -156,7 +156,10 @@ inline void decode_job(const FileRunConfig& c, SampleFiles* samples, int n_sampl
     if (tid_s < 0) { job->err = "contig not in the second BAM: " + chr; return; }
     for (size_t ci = 0; ci < clusters.size(); ++ci) {
       const int64_t r0 = (int64_t)job->batch.reads.size();
-      load_span_fast(samples[s].scan, *samples[s].bai, tid_s, clusters[ci].lo, clusters[ci].hi, &job->batch);
+      // (the margin: reads that overlap no region of the span but pass an indel found just outside one — the realigner's
+      //  noPassingReads looks them up, VariationRealigner.cpp:1447-1490; no region's read slice includes them)
+      load_span_fast(samples[s].scan, *samples[s].bai, tid_s, std::max(1, clusters[ci].lo - c.halo),
+                     std::min(job->chr_len, clusters[ci].hi + c.halo), &job->batch);
       const int64_t r1 = (int64_t)job->batch.reads.size();
       std::vector<RegionSpec> sub;
       for (size_t m = 0; m < clusters[ci].members.size(); ++m) sub.push_back(job->specs[clusters[ci].members[m]]);

@@ -532,12 +532,19 @@ struct Realigner {
     int cnt = 0, midcnt = 0;
     const int dlen = end - start;
     const uint32_t dlenqr = ((uint32_t)dlen << 4) | 2u;
-    // reads are sorted by start: only those starting in [start - longest reference span, end] can overlap
+    // reads are sorted by start: only those starting in [start - longest reference span, end] can overlap.  The
+    // region's slice [read_lo, read_hi) ends at the region's own end; an indel beyond it (the reads that carry it overlap
+    // the region, the reads that pass it need not) is looked up in the rest of the sorted run the slice belongs to —
+    // the neighbouring tiles' reads of the same sample and the margin the loader reads beyond the span.
+    const int64_t n_all = (int64_t)batch->reads.size();
     int64_t i0 = read_lo, z = read_hi;
     const int64_t want = (int64_t)start - 1 - batch->max_ref_span;
     while (i0 < z) { const int64_t m = (i0 + z) / 2; if ((int64_t)batch->reads[(size_t)m].pos - 1 < want) i0 = m + 1; else z = m; }
-    for (int64_t i = i0; i < read_hi; ++i) {
+    if (i0 == read_lo && read_lo < n_all)
+      while (i0 > 0 && batch->reads[(size_t)i0 - 1].pos <= batch->reads[(size_t)i0].pos && (int64_t)batch->reads[(size_t)i0 - 1].pos - 1 >= want) --i0;
+    for (int64_t i = i0; i < n_all; ++i) {
       const rv_read& rd = batch->reads[(size_t)i];
+      if (i >= read_hi && i > 0 && rd.pos < batch->reads[(size_t)i - 1].pos) break;  // the next span / sample begins
       if (rd.pos - 1 >= end) break;
       if (!(rd.pos - 1 < end && rd.end_pos > start - 1)) continue;  // sam_itr_querys("chr:start-end")
       const uint32_t* cg = batch->cigar((size_t)i);

@@ -2,6 +2,7 @@
 import os
 
 import numpy as np
+import pytest
 
 import cases
 import rabbitvar_b200 as rv
@@ -90,3 +91,84 @@ def test_block_decoder_and_crc_match_zlib(built):
         p += bsize
         blocks += 1
     assert blocks > 10
+
+
+def _python_bam_records(path):
+    """An independent BAM reader for the test below: Python's gzip module (multi-member = BGZF) and the record layout
+    of the SAM/BAM specification section 4.2, nothing from the repo's C++ reader."""
+    import gzip
+    import struct
+    raw = gzip.open(path, "rb").read()
+    assert raw[:4] == b"BAM\1"
+    l_text, = struct.unpack_from("<i", raw, 4)
+    o = 8 + l_text
+    n_ref, = struct.unpack_from("<i", raw, o)
+    o += 4
+    refs = []
+    for _ in range(n_ref):
+        l_name, = struct.unpack_from("<i", raw, o)
+        name = raw[o + 4:o + 4 + l_name - 1].decode()
+        l_ref, = struct.unpack_from("<i", raw, o + 4 + l_name)
+        refs.append((name, l_ref))
+        o += 8 + l_name
+    recs = []
+    while o < len(raw):
+        bs, = struct.unpack_from("<i", raw, o)
+        tid, pos, l_qname, mapq, _bin, n_cigar, flag, l_seq, mtid, mpos, _tlen = struct.unpack_from("<iiBBHHHiiii", raw, o + 4)
+        p = o + 36 + l_qname
+        cigar = struct.unpack_from("<%dI" % n_cigar, raw, p)
+        tail = raw[p:p + 4 * n_cigar + (l_seq + 1) // 2 + l_seq]  # cigar | packed bases | qualities
+        ref_len = sum(c >> 4 for c in cigar if (c & 15) in (0, 2, 3, 7, 8))
+        a = p + len(tail)
+        end = o + 4 + bs
+        nm = -1
+        while a < end:  # the aux fields, for NM
+            tag, ty = raw[a:a + 2], raw[a + 2:a + 3]
+            a += 3
+            size = {b"A": 1, b"c": 1, b"C": 1, b"s": 2, b"S": 2, b"i": 4, b"I": 4, b"f": 4}.get(ty)
+            if size is not None:
+                if tag == b"NM":
+                    nm = int.from_bytes(raw[a:a + size], "little", signed=ty in (b"c", b"s", b"i"))
+                a += size
+            elif ty in (b"Z", b"H"):
+                a = raw.index(b"\0", a) + 1
+            elif ty == b"B":
+                sub = raw[a:a + 1]
+                cnt, = struct.unpack_from("<i", raw, a + 1)
+                a += 5 + cnt * {b"c": 1, b"C": 1, b"s": 2, b"S": 2, b"i": 4, b"I": 4, b"f": 4}[sub]
+            else:
+                raise AssertionError("aux type %r" % ty)
+        recs.append(dict(tid=tid, pos=pos, mpos=mpos, flag=flag, l_seq=l_seq, n_cigar=n_cigar, mapq=mapq, mtid=mtid,
+                         end=pos + (ref_len if ref_len else 1), nm=nm, tail=tail))
+        o = end
+    return refs, recs
+
+
+@pytest.mark.parametrize("name,bam,chrom", [("c5_k1", "S.bam", "chrS5"), ("edge_nh_k1", "S.bam", None)])
+def test_loader_matches_an_independent_python_reader(built, name, bam, chrom):
+    """rvh_load_bam (BAI query, the repo's inflate, record decode, pool layout) against a reader written from the BAM
+    specification with Python's gzip + struct: every field of every record, the cigar | bases | qualities bytes, and
+    htslib's overlap rule on a sub-range served through the index."""
+    d = cases.generate(name)
+    refs, recs = _python_bam_records(os.path.join(d, bam))
+    chrom = chrom or refs[0][0]
+    tid = [r[0] for r in refs].index(chrom)
+    dt = np.dtype([("pos", "<i4"), ("mpos", "<i4"), ("off", "<u4"), ("l_seq", "<i4"), ("flag", "<u2"),
+                   ("n_cigar", "<u2"), ("nm", "<i2"), ("mapq", "u1"), ("same", "u1"), ("end", "<i4"), ("mtid", "<i4")])
+    length = refs[tid][1]
+    mine = [r for r in recs if r["tid"] == tid]
+    mid, last = mine[len(mine) // 2]["pos"] + 1, mine[-1]["pos"] + 1
+    for lo, hi in ((1, length), (mid, mid + 700), (last + 3, min(length, last + 40)), (mine[0]["pos"] + 1, mine[0]["pos"] + 1)):
+        b = rv.HostBatch(os.path.join(d, bam), chrom, lo, hi)
+        assert b.chr_len == length
+        got = b.reads_numpy().view(dt)
+        pool = b.pool_numpy()
+        want = [r for r in recs if r["tid"] == tid and r["pos"] < hi and r["end"] > lo - 1]  # 0-based pos < end, endpos > beg
+        assert len(got) == len(want) > 0
+        for g, w in zip(got, want):
+            assert (g["pos"], g["mpos"], g["flag"], g["l_seq"], g["n_cigar"], g["mapq"], g["end"], g["nm"]) == \
+                (w["pos"] + 1, w["mpos"] + 1, w["flag"], w["l_seq"], w["n_cigar"], w["mapq"], w["end"], w["nm"])
+            assert g["same"] == (1 if w["tid"] == w["mtid"] else 0) and g["mtid"] == w["mtid"]
+            o = int(g["off"]) * 16
+            assert pool[o:o + len(w["tail"])].tobytes() == w["tail"]
+        b.close()
