@@ -23,7 +23,7 @@ struct Cli {
   std::string fasta, bam, bam2, region, bed, out = "./out.txt", sample, delim = "\t";
   int c_col = 2, S_col = 6, E_col = 7, g_col = 12;  // DEFAULT_BED_ROW_FORMAT (Launcher.cpp:21), 0-based after -1
   bool c_set = false, S_set = false, E_set = false, g_set = false, zero_based = false;
-  int nucl_ext = 0, ref_ext = 1200, gpus = 1, threads = 1, batch_regions = 256, halo = 512, workers = 4, job_mb = 12, device = 0;
+  int nucl_ext = 0, ref_ext = 1200, gpus = 1, threads = 1, batch_regions = 256, halo = 512, workers = 4, job_mb = 12, device = 0, inflight_gb = 6;
   bool auto_resize = false, threads_set = false, decode_only = false;
   rv_params P;
 };
@@ -33,7 +33,7 @@ static void usage() {
           "usage: rabbitvar_b200 -G ref.fa -b in.bam (-R chr:start-end | -i regions.bed -c 1 -S 2 -E 3 -g 4) [options]\n"
           "  -N name  -f freq  -k 0|1  -3  -u  --UN  -p  -t  --fisher  -q phred  -m mismatches  -X ext  -P pos  -r minr\n"
           "  -B minbias  -Q mapq  -o qratio  -O mapq  -V lofreq  -M minmatch  -T trim  -F hexfilter  -x extend  -Y refext\n"
-          "  -z  --auto_resize  --th n  --gpus n  --device first  --workers n (GPU contexts per device)  --halo n  --out file\n");
+          "  -z  --auto_resize  --th n  --gpus n  --device first  --workers n (GPU contexts per device)  --halo n  --job-mb n  --inflight-gb n (decoded input held ahead of the GPU)  --out file\n");
 }
 
 static bool parse(int argc, char** argv, Cli& c) {
@@ -91,6 +91,7 @@ static bool parse(int argc, char** argv, Cli& c) {
     else if (a == "--workers") c.workers = std::max(1, atoi(val().c_str()));
     else if (a == "--device") c.device = std::max(0, atoi(val().c_str()));
     else if (a == "--job-mb") c.job_mb = std::max(1, atoi(val().c_str()));
+    else if (a == "--inflight-gb") c.inflight_gb = std::max(0, atoi(val().c_str()));
     else if (a == "--auto_resize") c.auto_resize = true;
     else if (a == "--decode-only") c.decode_only = true;
     else if (a == "--gpus") c.gpus = std::max(1, atoi(val().c_str()));
@@ -236,6 +237,7 @@ int main(int argc, char** argv) {
   fc.workers_per_gpu = c.workers;
   fc.max_regions_per_job = c.batch_regions;
   fc.job_bytes = (int64_t)c.job_mb << 20;
+  fc.inflight_bytes = (int64_t)c.inflight_gb << 30;  // decoded input the decode threads may run ahead of the GPU workers
   fc.halo = c.halo;
   fc.keep_contexts = true;  // the process exits right after the run
   std::string tsv;
@@ -273,6 +275,10 @@ int main(int argc, char** argv) {
          c.out.c_str(), specs.size(), (long long)st.n_jobs, fc.gpus, fc.workers_per_gpu, fc.decode_threads, (long long)st.bases, (long long)st.lines,
          st.pileup_kernel_ms + st.score_kernel_ms, st.decode_thread_ms, st.gpu_worker_ms, (long long)st.launches,
          (long long)st.h2d_bytes, (long long)st.d2h_bytes);
+  printf("[info] gpu-worker thread-ms by stage: contexts %.0f, upload %.0f, pileup %.0f, fetch %.0f, host stage %.0f, patch %.0f, score %.0f, "
+         "records + TSV %.0f; first job decoded at %.0f ms, last at %.0f ms, first job taken by a GPU worker at %.0f ms\n",
+         st.stage_ms[0], st.stage_ms[1], st.stage_ms[2], st.stage_ms[3], st.stage_ms[4], st.stage_ms[5], st.stage_ms[6], st.stage_ms[7],
+         st.first_job_ready_ms, st.last_decode_done_ms, st.first_gpu_job_start_ms);
   printf("[info] timeline ms: inputs parsed %.0f, cuda start-up %.0f (beside the decode threads), pipeline done %.0f, output written %.0f\n",
          t_parsed - t0, cuda_init_ms, t_ran - t0, now_ms() - t0);
   printf("total time: %f s \n", (now_ms() - t0) / 1000.0);

@@ -37,6 +37,9 @@ struct FileRunConfig {
   int64_t job_bytes = 24 << 20;  // compressed bytes (all samples) a job aims for
   int cluster_gap = 16384;  // (one index window: a scan starts at its window's first record anyway)
   int halo = 512;
+  // decoded jobs waiting for a GPU worker are bounded by their bytes, not their number: while CUDA starts up (0.5-2 s
+  // of a process's life) the decode threads should be able to run through a whole panel / exome sized input
+  int64_t inflight_bytes = (int64_t)6 << 30;
   bool verbose = false;
   bool keep_contexts = false;  // do not rv_destroy the worker contexts at the end (a CLI about to exit)
   bool decode_only = false;  // measurement aid: run the decode stage alone (no device needed), print nothing
@@ -48,6 +51,10 @@ struct FileRunStats {
   double pileup_kernel_ms = 0, score_kernel_ms = 0;
   double decode_thread_ms = 0, gpu_worker_ms = 0;  // summed over threads
   int64_t h2d_bytes = 0, d2h_bytes = 0, launches = 0;
+  // gpu-worker time by stage, summed over the worker threads: context creation, read upload, pileup, event / row
+  // fetch, host stage (reduce + realigner), patch upload, scoring, record fetch + TSV assembly
+  double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double first_job_ready_ms = 0, first_gpu_job_start_ms = 0, last_decode_done_ms = 0;  // since run_files began
 };
 
 struct FileJob {
@@ -59,6 +66,7 @@ struct FileJob {
   std::string tsv, err;
   BatchTiming tm;
   bool done = false;
+  int64_t held_bytes = 0;  // decoded inputs this job holds until a GPU worker has taken them
 };
 
 // compressed offset at which the scan for `pos0` of `tid` starts (a monotone proxy for "where in the file")
@@ -220,13 +228,17 @@ inline int run_files(const FileRunConfig& c, const std::vector<RegionSpec>& spec
   const int n_jobs = (int)jobs.size();
   const int n_gpu_workers = std::max(1, c.gpus * c.workers_per_gpu);
   const int n_decode = std::max(1, std::min(c.decode_threads, n_jobs));
-  // decoded-but-unprocessed jobs are bounded (memory): a decode thread waits for a slot
-  const int max_inflight = n_decode + 2 * n_gpu_workers;
+  // decoded-but-unprocessed jobs are bounded (memory): a decode thread waits for a slot once more than min_inflight
+  // jobs are out and the decoded bytes held exceed c.inflight_bytes
+  const int min_inflight = n_decode + 2 * n_gpu_workers;
+  int64_t held_bytes = 0;
   std::mutex mu;
   std::condition_variable cv_ready, cv_slot;
   std::deque<int> ready;
   int inflight = 0, next_job = 0, decoders_left = n_decode;
-  std::atomic<long long> dec_us(0), gpu_us(0), launches(0);
+  std::atomic<long long> dec_us(0), gpu_us(0), launches(0), create_us(0);
+  const double t_begin = now_ms();
+  std::atomic<long long> first_ready_us(-1), first_gpu_us(-1), last_dec_us(0);
   std::vector<std::thread> threads;
   for (int d = 0; d < n_decode; ++d)
     threads.emplace_back([&, d]() {
@@ -240,7 +252,7 @@ inline int run_files(const FileRunConfig& c, const std::vector<RegionSpec>& spec
         int ji;
         {
           std::unique_lock<std::mutex> lk(mu);
-          cv_slot.wait(lk, [&]() { return inflight < max_inflight || next_job >= n_jobs; });
+          cv_slot.wait(lk, [&]() { return inflight < min_inflight || held_bytes < c.inflight_bytes || next_job >= n_jobs; });
           if (next_job >= n_jobs) break;
           ji = next_job++;
           inflight++;
@@ -254,7 +266,16 @@ inline int run_files(const FileRunConfig& c, const std::vector<RegionSpec>& spec
         }
         dec_us += (long long)((now_ms() - t0) * 1000.0);
         {
+          const long long t_us = (long long)((now_ms() - t_begin) * 1000.0);
+          long long none = -1;
+          first_ready_us.compare_exchange_strong(none, t_us);
+          long long prev = last_dec_us.load();
+          while (prev < t_us && !last_dec_us.compare_exchange_weak(prev, t_us)) {}
+        }
+        job.held_bytes = (int64_t)(job.batch.pool.capacity() + job.batch.reads.capacity() * sizeof(rv_read) + job.refseq.capacity());
+        {
           std::lock_guard<std::mutex> lk(mu);
+          held_bytes += job.held_bytes;
           ready.push_back(ji);
         }
         cv_ready.notify_one();
@@ -269,9 +290,10 @@ inline int run_files(const FileRunConfig& c, const std::vector<RegionSpec>& spec
   for (int w = 0; w < n_gpu_workers; ++w)
     threads.emplace_back([&, w]() {
       host_threads_override() = host_thr;
-      int n_dev = rv_device_count();  // (waits for the CUDA start-up the caller began)
+      int n_dev = rv_device_count();
       if (n_dev <= 0) n_dev = 1;
       const int device = (c.first_device + w % std::max(1, c.gpus)) % n_dev;
+      if (!c.decode_only) rv_warmup(device);  // (waits for the CUDA start-up the caller began on another thread)
       rv_ctx* ctx = NULL;
       rv_limits have;
       rv_default_limits(&have);
@@ -285,6 +307,10 @@ inline int run_files(const FileRunConfig& c, const std::vector<RegionSpec>& spec
           ready.pop_front();
         }
         const double t0 = now_ms();
+        {
+          long long none = -1;
+          first_gpu_us.compare_exchange_strong(none, (long long)((t0 - t_begin) * 1000.0));
+        }
         FileJob& job = jobs[(size_t)ji];
         if (job.err.empty() && c.decode_only) {
           job.tm = BatchTiming();
@@ -304,7 +330,9 @@ inline int run_files(const FileRunConfig& c, const std::vector<RegionSpec>& spec
                 L.max_variants = (somatic ? 3 : 1) * L.max_positions + 1024;
                 L.max_regions = std::max(L.max_regions, c.max_regions_per_job * n_samples + 8);
                 if (L.max_read_bytes >= ((int64_t)1 << 32) - 4096) L.max_read_bytes = need.max_read_bytes;
+                const double tc = now_ms();
                 const int rc = rv_create(&ctx, device, &c.P, &L);
+                create_us += (long long)((now_ms() - tc) * 1000.0);
                 if (rc != RV_OK) {
                   job.err = std::string("rv_create: ") + (ctx ? rv_last_error(ctx) : "no CUDA device (there is no CPU path)");
                   if (ctx) rv_destroy(ctx);
@@ -336,6 +364,7 @@ inline int run_files(const FileRunConfig& c, const std::vector<RegionSpec>& spec
         {
           std::lock_guard<std::mutex> lk(mu);
           inflight--;
+          held_bytes -= job.held_bytes;
         }
         cv_slot.notify_all();
       }
@@ -367,12 +396,19 @@ inline int run_files(const FileRunConfig& c, const std::vector<RegionSpec>& spec
     st->score_kernel_ms += job.tm.score_kernel_ms;
     st->h2d_bytes += job.tm.h2d_bytes;
     st->d2h_bytes += job.tm.d2h_bytes;
+    st->stage_ms[1] += job.tm.push_ms; st->stage_ms[2] += job.tm.pileup_ms; st->stage_ms[3] += job.tm.fetch_ms;
+    st->stage_ms[4] += job.tm.host_ms; st->stage_ms[5] += job.tm.patch_ms; st->stage_ms[6] += job.tm.score_ms;
+    st->stage_ms[7] += job.tm.assemble_ms;
     for (int k = 0; k < 2; ++k) { st->cov_sum[k] += job.tm.cov_sum[k]; st->cov_pos[k] += job.tm.cov_pos[k]; }
   }
   st->n_jobs = n_jobs;
   st->decode_thread_ms = dec_us.load() / 1000.0;
   st->gpu_worker_ms = gpu_us.load() / 1000.0;
   st->launches = launches.load();
+  st->stage_ms[0] = create_us.load() / 1000.0;
+  st->first_job_ready_ms = first_ready_us.load() / 1000.0;
+  st->first_gpu_job_start_ms = first_gpu_us.load() / 1000.0;
+  st->last_decode_done_ms = last_dec_us.load() / 1000.0;
   st->dropped_keys = dropped_patch_keys().load();
   return rc;
 }

@@ -1348,6 +1348,7 @@ struct rv_ctx {
   size_t h_variants_cap;
   int32_t* h_max_rl;
   DevStats h_stats;
+  uint8_t* d_arena;  // the one device allocation the buffers above are carved from
   bool lazy;     // rv_set_lazy: rv_pileup / rv_score enqueue only; results are settled at rv_sync or by the first getter
   bool unsettled;
   bool unsettled_pileup;
@@ -1494,6 +1495,7 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   ctx->max_sparse = 0;
 
   ctx->d_desc_mml = NULL;
+  ctx->d_arena = NULL;
   ctx->pool_dev_bytes = 0;
   ctx->h_counts = NULL; ctx->h_cov = NULL; ctx->h_tab_cap = 0; ctx->h_events = NULL; ctx->h_events_cap = 0;
   ctx->h_variants = NULL; ctx->h_variants_cap = 0; ctx->h_max_rl = NULL; ctx->h_rows = NULL; ctx->h_rows_cap = 0; ctx->d_scratch = NULL; ctx->scratch_cap = 0;
@@ -1521,50 +1523,71 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   CK(cudaEventCreate(&ctx->pev1));
   for (int k = 0; k < 3; ++k) CK(cudaEventCreate(&ctx->evs[k]));
   const rv_limits& L = ctx->L;
-  CK(cudaMalloc(&ctx->d_reads, sizeof(rv_read) * (size_t)L.max_reads));
-  CK(cudaMalloc(&ctx->d_pool, (size_t)L.max_read_bytes + 64));  // the gather kernel copies whole 16-byte chunks
-  CK(cudaMalloc(&ctx->d_ref, (size_t)L.max_ref_bases));
-  CK(cudaMalloc(&ctx->d_counts, sizeof(uint32_t) * RV_POS_U32 * (size_t)(L.max_positions + 1)));
-  CK(cudaMalloc(&ctx->d_cov, sizeof(uint32_t) * (size_t)(L.max_positions + 1)));
-  CK(cudaMalloc(&ctx->d_events, sizeof(rv_event) * (size_t)L.max_events));
-  CK(cudaMalloc(&ctx->d_variants, sizeof(rv_variant) * (size_t)L.max_variants));
-  CK(cudaMalloc(&ctx->d_patch, sizeof(rv_patch_entry) * (size_t)L.max_patch));
-  CK(cudaMalloc(&ctx->d_patch_first, sizeof(uint32_t) * (size_t)(L.max_positions + 1)));
-  CK(cudaMalloc(&ctx->d_patch_count, (size_t)(L.max_positions + 1)));
-  CK(cudaMalloc(&ctx->d_regions, sizeof(DevRegion) * (size_t)L.max_regions));
-  CK(cudaMalloc(&ctx->d_max_rl, sizeof(int32_t) * (size_t)L.max_regions));
-  {
-    // one block: statistics | walk queue counters [3] | SparseObs cursor | reach bounds [2] (a single memset per pileup)
-    uint8_t* blk = NULL;
-    CK(cudaMalloc(&blk, COUNTER_BLOCK_BYTES));
-    ctx->d_stats = (DevStats*)blk;
-    ctx->d_walk_count = (unsigned long long*)(blk + 128);
-    ctx->d_sparse_count = (unsigned long long*)(blk + 128 + 24);
-    ctx->d_reach = (int32_t*)(blk + 128 + 32);
-  }
-  // work items are (region, read) pairs: a read overlapping two tiles is walked once per tile
-  CK(cudaMalloc(&ctx->d_descs, sizeof(GDesc) * (size_t)(2 * L.max_reads + 1024)));
-  CK(cudaMalloc(&ctx->d_desc_mm, sizeof(uint16_t) * (size_t)(2 * L.max_reads + 1024)));
-  CK(cudaMalloc(&ctx->d_desc_mml, sizeof(uint4) * (size_t)(2 * L.max_reads + 1024)));
-  CK(cudaMalloc(&ctx->d_descs2, sizeof(GDesc) * (size_t)(2 * L.max_reads + 1024)));
-  CK(cudaMalloc(&ctx->d_desc_mm2, sizeof(uint16_t) * (size_t)(2 * L.max_reads + 1024)));
-  CK(cudaMalloc(&ctx->d_desc_mml2, sizeof(uint4) * (size_t)(2 * L.max_reads + 1024)));
-  // SparseObs list: a walked read leaves a few entries (soft-clip re-extension, coverage under a deletion), a stretch
-  // that is not plain one per base; RV_NO_GATHER sends every base here (small debugging batches only)
+  // Every device buffer of the context is carved out of ONE allocation: cudaMalloc takes a device-wide lock, and the
+  // ~30 calls a context used to make cost 100-400 ms of a short process's life when four worker threads created
+  // their contexts side by side (measured through the drop-in CLI on BASELINE configs[1]).
   ctx->max_sparse = L.max_sparse_obs > 0 ? L.max_sparse_obs : std::max<int64_t>(4 << 20, 8 * L.max_reads);
   if (ctx->max_sparse > ((int64_t)1 << 31)) return fail(ctx, RV_ERR_ARG, "limits.max_sparse_obs too large");
-  CK(cudaMalloc(&ctx->d_sparse, sizeof(SparseObs) * (size_t)ctx->max_sparse));
-  CK(cudaMalloc(&ctx->d_ref4, sizeof(uint32_t) * (size_t)(L.max_ref_bases / 8 + 16)));
-  // gather tiles: every region rounds its table (length + 2*halo) up to whole tiles
-  ctx->tile_cap = L.max_positions / ctx->tile + L.max_regions + 1;
-  CK(cudaMalloc(&ctx->d_tile_range, 2 * sizeof(int64_t) * (size_t)ctx->tile_cap));
-  // positions queued for the general scoring kernel (patched positions, screened candidates): at most every position
-  CK(cudaMalloc(&ctx->d_patched_queue, sizeof(int64_t) * (size_t)(L.max_positions + 1)));
-  CK(cudaMalloc(&ctx->d_patched_count, sizeof(unsigned long long)));
-  CK(cudaMalloc(&ctx->d_walk_queue, sizeof(unsigned long long) * (size_t)(2 * L.max_reads + 1024)));
-  CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->stream));
+  ctx->tile_cap = L.max_positions / ctx->tile + L.max_regions + 1;  // every region rounds its table up to whole tiles
   ctx->lgt_n = 1 << 20;
-  CK(cudaMalloc(&ctx->d_lgt, sizeof(double) * (size_t)ctx->lgt_n));
+  const size_t n_items_cap = (size_t)(2 * L.max_reads + 1024);  // work items are (region, read) pairs
+  {
+    size_t total = 0;
+    uint8_t* base = NULL;
+    for (int pass = 0; pass < 2; ++pass) {
+      size_t off = 0;
+      auto carve = [&](auto** p, size_t bytes) {
+        if (pass == 1) *p = reinterpret_cast<std::remove_reference_t<decltype(**p)>*>(base + off);
+        off += (bytes + 255) & ~(size_t)255;
+      };
+      carve(&ctx->d_reads, sizeof(rv_read) * (size_t)L.max_reads);
+      carve(&ctx->d_pool, (size_t)L.max_read_bytes + 64);  // the gather kernel's look-ahead loads
+      carve(&ctx->d_ref, (size_t)L.max_ref_bases);
+      carve(&ctx->d_counts, sizeof(uint32_t) * RV_POS_U32 * (size_t)(L.max_positions + 1));
+      carve(&ctx->d_cov, sizeof(uint32_t) * (size_t)(L.max_positions + 1));
+      carve(&ctx->d_events, sizeof(rv_event) * (size_t)L.max_events);
+      carve(&ctx->d_variants, sizeof(rv_variant) * (size_t)L.max_variants);
+      carve(&ctx->d_patch, sizeof(rv_patch_entry) * (size_t)L.max_patch);
+      carve(&ctx->d_patch_first, sizeof(uint32_t) * (size_t)(L.max_positions + 1));
+      carve(&ctx->d_patch_count, (size_t)(L.max_positions + 1));
+      carve(&ctx->d_regions, sizeof(DevRegion) * (size_t)L.max_regions);
+      carve(&ctx->d_max_rl, sizeof(int32_t) * (size_t)L.max_regions);
+      // one block: statistics | walk queue counters [3] | SparseObs cursor | reach bounds [2] (a single memset per pileup)
+      uint8_t* blk = NULL;
+      carve(&blk, COUNTER_BLOCK_BYTES);
+      if (pass == 1) {
+        ctx->d_stats = (DevStats*)blk;
+        ctx->d_walk_count = (unsigned long long*)(blk + 128);
+        ctx->d_sparse_count = (unsigned long long*)(blk + 128 + 24);
+        ctx->d_reach = (int32_t*)(blk + 128 + 32);
+      }
+      carve(&ctx->d_descs, sizeof(GDesc) * n_items_cap);
+      carve(&ctx->d_desc_mm, sizeof(uint16_t) * n_items_cap);
+      carve(&ctx->d_desc_mml, sizeof(uint4) * n_items_cap);
+      carve(&ctx->d_descs2, sizeof(GDesc) * n_items_cap);
+      carve(&ctx->d_desc_mm2, sizeof(uint16_t) * n_items_cap);
+      carve(&ctx->d_desc_mml2, sizeof(uint4) * n_items_cap);
+      // SparseObs list: a walked read leaves a few entries (soft-clip re-extension, coverage under a deletion), a stretch
+      // that is not plain one per base; RV_NO_GATHER sends every base here (small debugging batches only)
+      carve(&ctx->d_sparse, sizeof(SparseObs) * (size_t)ctx->max_sparse);
+      carve(&ctx->d_ref4, sizeof(uint32_t) * (size_t)(L.max_ref_bases / 8 + 16));
+      carve(&ctx->d_tile_range, 2 * sizeof(int64_t) * (size_t)ctx->tile_cap);
+      // positions queued for the general scoring kernel (patched positions, screened candidates): at most every position
+      carve(&ctx->d_patched_queue, sizeof(int64_t) * (size_t)(L.max_positions + 1));
+      carve(&ctx->d_patched_count, sizeof(unsigned long long));
+      carve(&ctx->d_walk_queue, sizeof(unsigned long long) * n_items_cap);
+      carve(&ctx->d_lgt, sizeof(double) * (size_t)ctx->lgt_n);
+      if (pass == 0) {
+        total = off;
+        if (cudaMalloc(&base, total) != cudaSuccess) {
+          cudaGetLastError();
+          return fail(ctx, RV_ERR_NOMEM, "out of device memory: the context's limits need " + std::to_string(total >> 20) + " MiB");
+        }
+        ctx->d_arena = base;
+      }
+    }
+  }
+  CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->stream));
   rv_lgamma_table_kernel<<<(ctx->lgt_n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_lgt, ctx->lgt_n);
   ctx->launches++;
   CK(cudaGetLastError());
@@ -1576,23 +1599,8 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
 void rv_destroy(rv_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaFree(ctx->d_reads); cudaFree(ctx->d_pool); cudaFree(ctx->d_ref); cudaFree(ctx->d_counts); cudaFree(ctx->d_cov);
-  cudaFree(ctx->d_events); cudaFree(ctx->d_variants); cudaFree(ctx->d_patch); cudaFree(ctx->d_patch_first);
-  cudaFree(ctx->d_patch_count); cudaFree(ctx->d_regions); cudaFree(ctx->d_max_rl); cudaFree(ctx->d_stats);
-  cudaFree(ctx->d_lgt);
+  cudaFree(ctx->d_arena);  // every device buffer but the scratch
   cudaFree(ctx->d_scratch);
-  cudaFree(ctx->d_descs);
-  cudaFree(ctx->d_desc_mm);
-  cudaFree(ctx->d_desc_mml);
-  cudaFree(ctx->d_descs2);
-  cudaFree(ctx->d_desc_mm2);
-  cudaFree(ctx->d_desc_mml2);
-  cudaFree(ctx->d_sparse);
-  cudaFree(ctx->d_ref4);
-  cudaFree(ctx->d_tile_range);
-  cudaFree(ctx->d_patched_queue);
-  cudaFree(ctx->d_patched_count);
-  cudaFree(ctx->d_walk_queue);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
   if (ctx->h_cov) cudaFreeHost(ctx->h_cov);
   if (ctx->h_events) cudaFreeHost(ctx->h_events);
