@@ -67,6 +67,7 @@ struct FileJob {
   BatchTiming tm;
   bool done = false;
   int64_t held_bytes = 0;  // decoded inputs this job holds until a GPU worker has taken them
+  int64_t planned_bytes = 0;  // compressed bytes the planner counted for the job
 };
 
 // compressed offset at which the scan for `pos0` of `tid` starts (a monotone proxy for "where in the file")
@@ -108,6 +109,7 @@ inline void plan_jobs(const FileRunConfig& c, const std::vector<RegionSpec>& spe
       if (w1 > w_done) w_done = w1;
       j.specs.push_back(specs[k++]);
     }
+    j.planned_bytes = bytes;
     jobs->push_back(std::move(j));
     i = k;
   }
@@ -156,6 +158,10 @@ inline void decode_job(const FileRunConfig& c, SampleFiles* samples, int n_sampl
     job->batch.pool.reserve((size_t)(cbytes * 4));
     job->batch.reads.reserve((size_t)(cbytes * 4 / 250));
   }
+  // one allocation for the pool instead of a doubling series (untouched reserve costs address space only): a level-1
+  // BAM inflates ~3.5x, and cigar | bases | qualities are ~0.8 of a record
+  job->batch.pool.reserve((size_t)std::min<int64_t>(job->planned_bytes * 4 + (1 << 20), (int64_t)3 << 30));
+  job->batch.reads.reserve((size_t)std::min<int64_t>(job->planned_bytes / 40 + 1024, (int64_t)1 << 24));
   job->regs.assign(job->specs.size() * (size_t)n_samples, rv_region());
   int32_t smin = job->specs[0].start, smax = job->specs[0].end;
   for (size_t i = 0; i < job->specs.size(); ++i) { smin = std::min(smin, job->specs[i].start); smax = std::max(smax, job->specs[i].end); }
@@ -272,7 +278,7 @@ inline int run_files(const FileRunConfig& c, const std::vector<RegionSpec>& spec
           long long prev = last_dec_us.load();
           while (prev < t_us && !last_dec_us.compare_exchange_weak(prev, t_us)) {}
         }
-        job.held_bytes = (int64_t)(job.batch.pool.capacity() + job.batch.reads.capacity() * sizeof(rv_read) + job.refseq.capacity());
+        job.held_bytes = (int64_t)(job.batch.pool.size() + job.batch.reads.size() * sizeof(rv_read) + job.refseq.size());
         {
           std::lock_guard<std::mutex> lk(mu);
           held_bytes += job.held_bytes;
