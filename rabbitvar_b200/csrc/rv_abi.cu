@@ -609,6 +609,7 @@ struct G4Warp {
   uint8_t excl[32][32];           // [record][lane]: bit j = position j of the lane is masked out of the SIMD pass
   uint32_t d_n[G4_W + 4], c_n[G4_W + 4], d_rev[G4_W + 4], d_mapq[G4_W + 4], d_nm[G4_W + 4], d_tp1[G4_W + 4], d_tp2[G4_W + 4];
   uint32_t g_tp[G4_W];            // sum of tp of the segments that are not a whole read (each lane owns its four)
+  int8_t refal_s[G4_W];           // reference allele of every position of the tile (-1 = none)
 };
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t c) {
@@ -670,31 +671,34 @@ __global__ void __launch_bounds__(G4_WARPS * 32, MIN_CTAS) rv_gather4_kernel(Gat
   const int64_t t_row0 = dr->tab_off + (p_lo - dr->first_pos);
   uint32_t* const tile_rows = a.counts + (size_t)t_row0 * RV_POS_U32;
   // ---- the lane's four positions: table / live flags, reference alleles; rows the atomics may land in start at zero
-  int refal[4];
-  bool in_tab[4], live[4];
+  // (kept in shared memory, not in registers: the pass below needs every register it can get)
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int p = p_lo + x4 + j;
-    in_tab[j] = p - dr->first_pos < dr->n_pos;
-    live[j] = p >= c_lo && p <= c_hi;
-    refal[j] = -1;
-    if (live[j] && p >= dr->r.ref_lo && p <= dr->r.ref_hi && p >= a.ref_start && (int64_t)(p - a.ref_start) < a.ref_n) {
+    int ral = -1;
+    if (p >= c_lo && p <= c_hi && p >= dr->r.ref_lo && p <= dr->r.ref_hi && p >= a.ref_start && (int64_t)(p - a.ref_start) < a.ref_n) {
       const char c = a.ref[p - a.ref_start];
-      refal[j] = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
+      ral = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
     }
-  }
-  {
-    // every row of the tile starts at zero (512 contiguous bytes per store instruction); the rows of the reference
-    // alleles are written again at the end, the others only ever receive the atomics of mismatching bases
-    const int n_in = dr->n_pos - (p_lo - dr->first_pos) < G4_W ? dr->n_pos - (p_lo - dr->first_pos) : G4_W;
-    uint4* blk = (uint4*)tile_rows;
-    for (int c = lane; c < n_in * (RV_POS_U32 / 4); c += 32) blk[c] = make_uint4(0, 0, 0, 0);
+    W.refal_s[x4 + j] = (int8_t)ral;
   }
   for (int i = lane; i < G4_W + 4; i += 32) {
     W.d_n[i] = 0; W.c_n[i] = 0; W.d_rev[i] = 0; W.d_mapq[i] = 0; W.d_nm[i] = 0; W.d_tp1[i] = 0; W.d_tp2[i] = 0;
   }
   for (int i = lane; i < G4_W; i += 32) W.g_tp[i] = 0;
-  __threadfence();  // the zero rows are in place before any lane's atomics on them
+  __syncwarp();
+  {
+    const int n_in = dr->n_pos - (p_lo - dr->first_pos) < G4_W ? dr->n_pos - (p_lo - dr->first_pos) : G4_W;
+    // Every byte of the tile's rows is stored exactly once.  Now: zeros into the rows of the alleles that are not the
+    // reference's (they only ever receive the atomics of bases that differ from the reference: from the lanes of this
+    // warp below, from rv_apply_kernel later).  At the end of the tile: the reference allele's row.  Whole 32-byte
+    // sectors both times, so the two partial writes of a line cost DRAM what one full write does.
+    uint4* blk = (uint4*)tile_rows;
+    for (int c = lane; c < n_in * (RV_POS_U32 / 4); c += 32)
+      if (((c >> 1) & 3) != (int)W.refal_s[c >> 3]) blk[c] = make_uint4(0, 0, 0, 0);
+  }
+  // the zero rows are in place before any lane's atomics on them: the warp barrier orders the lanes' memory accesses
+  // (a device-wide fence here made every tile wait for the acknowledgement of its stores)
   __syncwarp();
   // ---- lane constants of the SIMD pass
   const uint32_t X01 = (uint32_t)(x4 + 1 + G4_B) | ((uint32_t)(x4 + 2 + G4_B) << 16);
@@ -917,13 +921,18 @@ __global__ void __launch_bounds__(G4_WARPS * 32, MIN_CTAS) rv_gather4_kernel(Gat
   warp_scan4(stp, lane);
 #pragma unroll
   for (int j = 0; j < 4; ++j) stp[j] += W.g_tp[x4 + j];
+  uint32_t cn[4];
+  int refal[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { cn[j] = W.c_n[x4 + j]; refal[j] = (int)W.refal_s[x4 + j]; }
+  __syncwarp();  // the difference arrays are dead: their memory now stages the tile's reference-allele rows
+  uint4* const st_rows = (uint4*)&W;  // [128][2]: first / second half of the position's reference-allele row (ends before W.refal_s)
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    if (!in_tab[j]) continue;
     const int x = x4 + j;
-    a.cov[t_row0 + x] = live[j] ? cnt[j] : 0u;
-    if (refal[j] < 0) continue;
-    const uint32_t n_ref = cnt[j] - W.c_n[x];
+    const int p = p_lo + x;
+    if (p - dr->first_pos < dr->n_pos) a.cov[t_row0 + x] = (p >= c_lo && p <= c_hi) ? cnt[j] : 0u;
+    const uint32_t n_ref = refal[j] < 0 ? 0u : cnt[j] - cn[j];
     uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
     if (n_ref) {
       const uint32_t t_and = ((j & 2) ? tp_and23 : tp_and01) >> (16 * (j & 1)) & 0xffffu;
@@ -935,10 +944,17 @@ __global__ void __launch_bounds__(G4_WARPS * 32, MIN_CTAS) rv_gather4_kernel(Gat
       ra = make_uint4(n_ref - rev[j], rev[j], stp[j], sum_q[j]);
       rb = make_uint4(smq[j], snm[j], n_hi[j], w);
     }
-    if (n_ref) {  // (the row is zero already)
-      uint4* row4 = (uint4*)(tile_rows + (size_t)x * RV_POS_U32 + refal[j] * RV_ROW_U32);
-      row4[0] = ra;
-      row4[1] = rb;
+    st_rows[2 * x] = ra;
+    st_rows[2 * x + 1] = rb;
+  }
+  __syncwarp();
+  {
+    // the reference alleles' rows (zeros where no read matched): two lanes per row, i.e. whole 32-byte sectors
+    const int n_in = dr->n_pos - (p_lo - dr->first_pos) < G4_W ? dr->n_pos - (p_lo - dr->first_pos) : G4_W;
+    uint4* blk = (uint4*)tile_rows;
+    for (int c = lane; c < n_in * 2; c += 32) {
+      const int x = c >> 1, al = (int)W.refal_s[x];
+      if (al >= 0) blk[x * (RV_POS_U32 / 4) + al * 2 + (c & 1)] = st_rows[c];
     }
   }
   __syncwarp();
@@ -1100,39 +1116,67 @@ __global__ void __launch_bounds__(SCORE_BLOCK, 4) rv_score_kernel(ScoreArgs a) {
   }
 }
 
-// Candidate mode (rv_params.candidates_only, simple-mode and paired-mode output): one position per thread, integer
-// work only.  A position can print something only if one of its non-reference alleles has hicnt >= minr (a
+// Candidate mode (rv_params.candidates_only, simple-mode and paired-mode output): integer work only.  A position can print something only if one of its non-reference alleles has hicnt >= minr (a
 // necessary condition of Variant::isGoodVar, include/Variant.h:205-231); those positions, and the positions with
 // patch entries, are queued for the general scoring kernel.  Everything else ends here after one pass over its row.
+// Layout of the pass: a CTA owns 256 consecutive table positions.  Phase 1, one position per thread: region, reference
+// allele, patch flag, coverage -> one byte of shared memory.  Phase 2, eight lanes per position: lane s loads bytes
+// [16 s, 16 s + 16) of the position's 128-byte row block, so a warp's load instruction covers 512 contiguous bytes (the
+// one-thread-per-position form touched 32 lines per instruction and ran at half the HBM rate); the eight 16-byte parts
+// are combined with one shuffle and two ballots.
 __global__ void __launch_bounds__(256) rv_score_screen_kernel(ScoreArgs a) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= a.n_positions) return;
-  const int ri = find_region_by_tab(a.regions, a.n_regions, t);
-  const DevRegion* dr = a.regions + ri;
-  const int pos = dr->first_pos + (int)(t - dr->tab_off);
-  if (pos < dr->r.start || pos > dr->r.end) return;
-  bool queue = (a.patch_first ? a.patch_first[t] : 0u) != 0;
-  if (!queue) {
-    const uint4* r4 = (const uint4*)(a.counts + (size_t)t * RV_POS_U32);
-    int refal = -1;
-    if (pos >= dr->r.ref_lo && pos <= dr->r.ref_hi && pos >= a.ref_start && (int64_t)(pos - a.ref_start) < a.ref_n)
-      refal = allele_of(a.ref[pos - a.ref_start]);
-    uint32_t any = 0;
-    bool possible = false;
-#pragma unroll
-    for (int al = 0; al < 4; ++al) {
-      const uint4 x = r4[2 * al], y = r4[2 * al + 1];
-      const uint32_t ex = x.x | x.y | x.z | x.w | y.x | y.y | y.z | y.w;
-      any |= ex;
-      if (al != refal && ex && x.x + x.y != 0 && (int)y.z >= a.P.minr) possible = true;  // fwd + rev, hicnt
+  __shared__ uint8_t s_meta[256];  // bits 0-2: reference allele + 1 (0 = none), 3: inside the region, 4: has patch entries, 5: coverage != 0
+  const int64_t base = (int64_t)blockIdx.x * 256;
+  {
+    const int64_t t = base + threadIdx.x;
+    uint32_t m = 0;
+    if (t < a.n_positions) {
+      const int ri = find_region_by_tab(a.regions, a.n_regions, t);
+      const DevRegion* dr = a.regions + ri;
+      const int pos = dr->first_pos + (int)(t - dr->tab_off);
+      if (pos >= dr->r.start && pos <= dr->r.end) {
+        m = 8u;
+        if (pos >= dr->r.ref_lo && pos <= dr->r.ref_hi && pos >= a.ref_start && (int64_t)(pos - a.ref_start) < a.ref_n)
+          m |= (uint32_t)(allele_of(a.ref[pos - a.ref_start]) + 1);
+        if ((a.patch_first ? a.patch_first[t] : 0u) != 0) m |= 16u;
+        if (a.cov[t] != 0) m |= 32u;
+      }
     }
-    queue = any && a.cov[t] != 0 && possible;
+    s_meta[threadIdx.x] = (uint8_t)m;
   }
-  if (queue) {
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 7, grp = lane >> 3;
+  const int w0 = warp * 32;  // the warp's 32 positions: eight rounds of four
+  uint4 v[8];
+  uint32_t meta[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int k = w0 + it * 4 + grp;
+    meta[it] = s_meta[k];
+    // rows are read only where they can matter: inside the region, covered, not queued already
+    v[it] = (meta[it] & (8u | 16u | 32u)) == (8u | 32u) ? __ldg((const uint4*)(a.counts + (size_t)(base + k) * RV_POS_U32) + sub)
+                                                        : make_uint4(0, 0, 0, 0);
+  }
+  uint32_t qmask = 0;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const uint4 x = v[it];
+    const uint32_t ex = x.x | x.y | x.z | x.w;
+    // even lanes hold {fwd, rev, sum tp, sum q} of allele sub / 2, odd lanes {sum mapq, sum nm, hicnt, std}
+    const uint32_t ex_o = __shfl_xor_sync(0xffffffffu, ex, 1);
+    const uint32_t hi_o = __shfl_xor_sync(0xffffffffu, x.z, 1);
+    const int refal = (int)(meta[it] & 7u) - 1;
+    const bool possible = (sub & 1) == 0 && (sub >> 1) != refal && (ex | ex_o) != 0 && x.x + x.y != 0 && (int)hi_o >= a.P.minr;
+    const unsigned b_pos = __ballot_sync(0xffffffffu, possible);
+    const bool dec = (meta[it] & 8u) && ((meta[it] & 16u) || ((b_pos >> (8 * grp)) & 0xffu) != 0);  // (possible implies a non-zero row; coverage is in the load condition)
+    const unsigned b = __ballot_sync(0xffffffffu, dec && sub == 0);
+    qmask |= ((b & 1u) | ((b >> 7) & 2u) | ((b >> 14) & 4u) | ((b >> 21) & 8u)) << (4 * it);
+  }
+  if ((qmask >> lane) & 1u) {
     cg::coalesced_group g = cg::coalesced_threads();
     unsigned long long slot = 0;
     if (g.thread_rank() == 0) slot = atomicAdd(a.patched_count, (unsigned long long)g.size());
-    a.patched_queue[g.shfl(slot, 0) + g.thread_rank()] = t;
+    a.patched_queue[g.shfl(slot, 0) + g.thread_rank()] = base + w0 + lane;
   }
 }
 

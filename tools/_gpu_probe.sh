@@ -1,11 +1,7 @@
-python tools/parity_configs.py --configs 2,1 --scale 1.0 2>&1 | grep -v "^    " | tail -1
-ls _work
-cd _work/parity_c2_5002600_l1
-run() { ../../build/rabbitvar_b200 -G ref.fa -b "T.bam|N.bam" -N "T|N" -i tiles.bed -c 1 -S 2 -E 3 -g 4 --fisher --out /tmp/x.tsv "$@" | grep -E "timeline" | sed -e 's/\[info\] //'; }
-head -2 tiles.bed > /tmp/two.bed
-echo "== two tiles, th 1 (CUDA start-up without decode threads beside it)"
-for i in 1 2 3 4 5 6; do ../../build/rabbitvar_b200 -G ref.fa -b "T.bam|N.bam" -N "T|N" -i /tmp/two.bed -c 1 -S 2 -E 3 -g 4 --fisher --out /tmp/y.tsv --th 1 | grep timeline; done
-echo "== full, th 16"
-for i in 1 2 3 4 5 6; do run --th 16; done
-echo "== full, th 8"
-for i in 1 2 3; do run --th 8; done
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -2
+for v in 4 3; do for k in 2 4; do
+  RV_G4_VARIANT=$v python bench.py --workload $k --steps 10 --warmup 3 --e2e-steps 0 --parity none --skip-cpu --no-scaling-base 2> gpurun_out/tmp.err | tail -1 | python -c "
+import json,sys; d=json.load(sys.stdin); print('variant $v config $k', d['ms_per_step'], d['value'], d['roofline']['frac'], d['roofline'].get('split_ms'), d['roofline']['score_kernel']['kernel_ms'])"
+  grep "pileup:" gpurun_out/tmp.err
+done; done
+python tools/parity_configs.py --configs 1,2,3,5 2>&1 | grep -v "^    " | tail -1
