@@ -118,7 +118,7 @@ struct Cigar {
 
 // Small fixed-capacity key builder (allele description strings, include/Variant.h:24-33).
 struct Key {
-  char c[RV_EVENT_KEY_MAX];
+  alignas(4) char c[RV_EVENT_KEY_MAX];
   int n;
   bool trunc;
   RV_HD void clear() { n = 0; trunc = false; }
@@ -981,8 +981,8 @@ RV_HD void emit_event(Sink& s, WalkState& w, int region_idx, uint32_t read_idx, 
   for (int k = 0; k < RV_EVENT_KEY_MAX; k += 4) {
     uint32_t w = 0;
     if (k < kn) {
-      for (int j = 0; j < 4; ++j)
-        if (k + j < kn) w |= (uint32_t)(uint8_t)key->c[k + j] << (8 * j);
+      w = *(const uint32_t*)(key->c + k);  // (little endian on both sides; bytes past the key's end are masked off)
+      if (kn - k < 4) w &= (1u << (8 * (kn - k))) - 1u;
     }
     *(uint32_t*)(e.key + k) = w;
   }
