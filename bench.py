@@ -440,12 +440,14 @@ def main():
 
     # ---- N = 1: the multi-GPU workload (configs[3]) on this one GPU, so that the strong-scaling series of the N > 1
     # runs has its own single-GPU point (the N = 1 headline above is configs[1]) --------------------------------------
+    # N > 1: rank 0 measures the same single-GPU point inside the run (the other ranks wait in the reductions below), so
+    # that the line carries both ends of its strong-scaling claim.
     scaling_base = None
-    if world == 1 and key == "2" and args.scaling_base:
+    if args.scaling_base and ((world == 1 and key == "2") or (world > 1 and key == "4" and rank == 0)):
         try:
-            d4, _ = pc.dataset("4", 1.0, 1)
+            d4, _ = pc.dataset("4", 1.0, 1) if world == 1 else (d, length)
             tiles4 = read_tiles(os.path.join(d4, pc.CONFIGS["4"]["bed"]))
-            R4 = measure_resident(rv, torch, "4", d4, tiles4, local, max(3, args.steps // 3), 2, barrier, rank)
+            R4 = measure_resident(rv, torch, "4", d4, tiles4, local, max(3, args.steps // 3), 3, (lambda: None) if world > 1 else barrier, rank)
             alg4 = R4["kept"] * R4["avg_read_bytes"] + R4["P"] * 133.0
             pk4 = float(np.mean(R4["pile_ms"])) / 1000.0
             scaling_base = {"workload": WORKLOAD_TEXT["4"], "n_gpus": 1, "value": R4["bases"] * len(R4["pile_ms"]) / (R4["dev_ms"] / 1000.0),
