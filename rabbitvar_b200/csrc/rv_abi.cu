@@ -81,6 +81,7 @@ struct PileupArgs {
   rv_params P;
   const DevRegion* regions;
   int n_regions;
+  const int32_t* itemblk_region;  // region of work item 128 b
   int64_t n_items;
   const rv_read* reads;
   const uint8_t* pool;
@@ -250,6 +251,13 @@ __device__ __forceinline__ int find_region(const DevRegion* regs, int n, int64_t
   }
   return lo;
 }
+// The same for a work item at or after the one whose region r0 is known (lane 0 of the warp searched for the warp's first
+// item): consecutive items are in the same region or the next, the search over thousands of regions is the exception.
+__device__ __forceinline__ int find_region_near(const DevRegion* regs, int n, int64_t item, int r0) {
+  if (r0 + 1 >= n || regs[r0 + 1].item_base > item) return r0;
+  if (r0 + 2 >= n || regs[r0 + 2].item_base > item) return r0 + 1;
+  return find_region(regs, n, item);
+}
 
 
 // 4-bit packing of the reference slice (one thread per 8 bases)
@@ -278,8 +286,9 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
   int back = 0, reach = 0;
   bool queue = false;
   unsigned long long queue_entry = 0;
+  const int r_first = a.itemblk_region[blockIdx.x];  // (blockDim.x == 128) region of the CTA's first item
   if (item < a.n_items) {
-    const int ri = find_region(a.regions, a.n_regions, item);
+    const int ri = find_region_near(a.regions, a.n_regions, item, r_first);
     const DevRegion* dr = a.regions + ri;
     const int64_t read_idx = dr->r.read_lo + (item - dr->item_base);
     const rv_read rd = a.reads[read_idx - dr->read_bias];
@@ -488,7 +497,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) rv_walk_kernel(PileupArgs a) {
 // The SparseObs list onto the tables (after the gather kernel has stored every row): one entry per thread.
 __device__ __forceinline__ void row_observe(uint32_t* row, uint32_t dir, uint32_t tp, uint32_t q, uint32_t mapq, uint32_t nm, int thr);
 __global__ void __launch_bounds__(256) rv_apply_kernel(const SparseObs* list, const unsigned long long* count, unsigned long long cap,
-                                                        uint32_t* counts, uint32_t* cov, int thr, DevStats* stats) {
+                                                        uint32_t* counts, uint32_t* cov, uint8_t* touched, int thr, DevStats* stats) {
   unsigned long long n = *count;
   if (blockIdx.x == 0 && threadIdx.x == 0) stats->n_sparse = n;
   if (n > cap) n = cap;
@@ -499,6 +508,7 @@ __global__ void __launch_bounds__(256) rv_apply_kernel(const SparseObs* list, co
     const uint32_t flags = v.z >> 16, kind = (flags >> 3) & 3u;
     if (kind == SO_COV) { atomicAdd(cov + v.x, 1u); continue; }
     uint32_t* row = counts + ((size_t)v.x * 4 + (flags & 3u)) * RV_ROW_U32;
+    touched[v.x] = 1;  // (whichever allele: the screen pass then looks at the position's rows)
     const uint32_t dir = (flags >> 2) & 1u, tp = v.y & 0xffffu, q = (v.y >> 16) & 0xffu, mapq = v.y >> 24;
     const int nm = (int)(int16_t)(v.z & 0xffffu);
     if (kind == SO_SINGLE) {
@@ -544,6 +554,7 @@ struct GatherArgs {
   int thr;              // ceil(goodq)
   int run;              // consecutive tiles per warp (rv_gather4_kernel)
   int alternate;        // odd tiles walk their candidates downward
+  uint8_t* touched;     // [table position]: set where a base that differs from the reference was added
 };
 
 __device__ __forceinline__ int find_region_by_tile(const DevRegion* regs, int n, int64_t tile) {
@@ -696,6 +707,7 @@ __global__ void __launch_bounds__(G4_WARPS * 32, MIN_CTAS) rv_gather4_kernel(Gat
     uint4* blk = (uint4*)tile_rows;
     for (int c = lane; c < n_in * (RV_POS_U32 / 4); c += 32)
       if (((c >> 1) & 3) != (int)W.refal_s[c >> 3]) blk[c] = make_uint4(0, 0, 0, 0);
+    for (int x = lane; x < n_in; x += 32) a.touched[t_row0 + x] = 0;
   }
   // the zero rows are in place before any lane's atomics on them: the warp barrier orders the lanes' memory accesses
   // (a device-wide fence here made every tile wait for the acknowledgement of its stores)
@@ -796,6 +808,7 @@ __global__ void __launch_bounds__(G4_WARPS * 32, MIN_CTAS) rv_gather4_kernel(Gat
             const uint32_t tp = (uint32_t)min(re0 + k + 1, L - k + tail);
             const uint32_t q = a.pool[qb + k];
             row_observe(tile_rows + (size_t)x * RV_POS_U32 + (e & 3u) * RV_ROW_U32, dir, tp, q, mapq, nm, thr);
+            a.touched[t_row0 + x] = 1;
             atomicAdd(&W.c_n[x], 1u);
             if (dir) { atomicAdd(&W.d_rev[x], 0u - 1u); atomicAdd(&W.d_rev[x + 1], 1u); }
             atomicAdd(&W.d_mapq[x], 0u - mapq); atomicAdd(&W.d_mapq[x + 1], mapq);
@@ -974,6 +987,8 @@ struct ScoreArgs {
   const rv_patch_entry* patch;
   const uint32_t* patch_first;
   const uint8_t* patch_count;
+  const uint8_t* touched;
+  const int32_t* tabblk_region;  // region of table position 256 b
   rv_variant* variants;
   unsigned long long max_variants;
   const double* lgt;
@@ -1005,6 +1020,11 @@ __device__ __forceinline__ int find_region_by_tab(const DevRegion* regs, int n, 
     else hi = mid - 1;
   }
   return lo;
+}
+__device__ __forceinline__ int find_region_by_tab_near(const DevRegion* regs, int n, int64_t t, int r0) {  // see find_region_near
+  if (r0 + 1 >= n || regs[r0 + 1].tab_off > t) return r0;
+  if (r0 + 2 >= n || regs[r0 + 2].tab_off > t) return r0 + 1;
+  return find_region_by_tab(regs, n, t);
 }
 
 // Scoring, ToVarsBuilder::process, in two kernels:
@@ -1119,64 +1139,63 @@ __global__ void __launch_bounds__(SCORE_BLOCK, 4) rv_score_kernel(ScoreArgs a) {
 // Candidate mode (rv_params.candidates_only, simple-mode and paired-mode output): integer work only.  A position can print something only if one of its non-reference alleles has hicnt >= minr (a
 // necessary condition of Variant::isGoodVar, include/Variant.h:205-231); those positions, and the positions with
 // patch entries, are queued for the general scoring kernel.  Everything else ends here after one pass over its row.
-// Layout of the pass: a CTA owns 256 consecutive table positions.  Phase 1, one position per thread: region, reference
-// allele, patch flag, coverage -> one byte of shared memory.  Phase 2, eight lanes per position: lane s loads bytes
-// [16 s, 16 s + 16) of the position's 128-byte row block, so a warp's load instruction covers 512 contiguous bytes (the
-// one-thread-per-position form touched 32 lines per instruction and ran at half the HBM rate); the eight 16-byte parts
-// are combined with one shuffle and two ballots.
+// Layout of the pass: a warp owns 32 consecutive table positions.  Phase 1, one position per lane: region, reference allele,
+// patch flag, coverage, and the pileup's `touched` byte (some allele other than the reference's was observed there: without
+// it the rows cannot hold a candidate, and they are not read — one byte instead of 128 per position).  Phase 2 visits only
+// the positions that need their rows, four per round, EIGHT LANES PER POSITION: lane s loads bytes [16 s, 16 s + 16) of the
+// position's 128-byte row block (whole lines per load instruction; one thread per position touched 32 lines per
+// instruction and ran at half the HBM rate), the eight 16-byte parts are combined with one shuffle pair and a ballot.
 __global__ void __launch_bounds__(256) rv_score_screen_kernel(ScoreArgs a) {
-  __shared__ uint8_t s_meta[256];  // bits 0-2: reference allele + 1 (0 = none), 3: inside the region, 4: has patch entries, 5: coverage != 0
-  const int64_t base = (int64_t)blockIdx.x * 256;
-  {
-    const int64_t t = base + threadIdx.x;
-    uint32_t m = 0;
-    if (t < a.n_positions) {
-      const int ri = find_region_by_tab(a.regions, a.n_regions, t);
-      const DevRegion* dr = a.regions + ri;
-      const int pos = dr->first_pos + (int)(t - dr->tab_off);
-      if (pos >= dr->r.start && pos <= dr->r.end) {
-        m = 8u;
-        if (pos >= dr->r.ref_lo && pos <= dr->r.ref_hi && pos >= a.ref_start && (int64_t)(pos - a.ref_start) < a.ref_n)
-          m |= (uint32_t)(allele_of(a.ref[pos - a.ref_start]) + 1);
-        if ((a.patch_first ? a.patch_first[t] : 0u) != 0) m |= 16u;
-        if (a.cov[t] != 0) m |= 32u;
-      }
+  const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+  const int64_t w_base = (int64_t)blockIdx.x * 256 + (threadIdx.x & ~31);  // the warp's first position
+  const int64_t t = w_base + lane;
+  // bits 0-2: reference allele + 1 (0 = none), 3: inside the region, 4: has patch entries, 5: coverage != 0, 6: touched
+  uint32_t m = 0;
+  const int r_first = a.tabblk_region[blockIdx.x];  // (blockDim.x == 256) region of the CTA's first position
+  if (t < a.n_positions) {
+    const int ri = find_region_by_tab_near(a.regions, a.n_regions, t, r_first);
+    const DevRegion* dr = a.regions + ri;
+    const int pos = dr->first_pos + (int)(t - dr->tab_off);
+    if (pos >= dr->r.start && pos <= dr->r.end) {
+      m = 8u;
+      if (pos >= dr->r.ref_lo && pos <= dr->r.ref_hi && pos >= a.ref_start && (int64_t)(pos - a.ref_start) < a.ref_n)
+        m |= (uint32_t)(allele_of(a.ref[pos - a.ref_start]) + 1);
+      if ((a.patch_first ? a.patch_first[t] : 0u) != 0) m |= 16u;
+      if (a.cov[t] != 0) m |= 32u;
+      if (a.touched[t]) m |= 64u;
     }
-    s_meta[threadIdx.x] = (uint8_t)m;
   }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 7, grp = lane >> 3;
-  const int w0 = warp * 32;  // the warp's 32 positions: eight rounds of four
-  uint4 v[8];
-  uint32_t meta[8];
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int k = w0 + it * 4 + grp;
-    meta[it] = s_meta[k];
-    // rows are read only where they can matter: inside the region, covered, not queued already
-    v[it] = (meta[it] & (8u | 16u | 32u)) == (8u | 32u) ? __ldg((const uint4*)(a.counts + (size_t)(base + k) * RV_POS_U32) + sub)
-                                                        : make_uint4(0, 0, 0, 0);
-  }
-  uint32_t qmask = 0;
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const uint4 x = v[it];
+  // positions with patch entries are queued as they are; rows are read where they can matter: inside the region, covered,
+  // not queued already, touched
+  unsigned qmask = __ballot_sync(0xffffffffu, (m & (8u | 16u)) == (8u | 16u));
+  const unsigned need = __ballot_sync(0xffffffffu, (m & (8u | 16u | 32u | 64u)) == (8u | 32u | 64u));
+  const int n_need = __popc(need);
+  for (int r = 0; 4 * r < n_need; ++r) {
+    const int idx = 4 * r + grp;
+    const bool valid = idx < n_need;
+    const int k = valid ? (int)__fns(need, 0u, idx + 1) : 0;  // the group's position: the idx-th one that needs its rows
+    const uint32_t mk = __shfl_sync(0xffffffffu, m, k);
+    uint4 x = make_uint4(0, 0, 0, 0);
+    if (valid) x = __ldg((const uint4*)(a.counts + (size_t)(w_base + k) * RV_POS_U32) + sub);
     const uint32_t ex = x.x | x.y | x.z | x.w;
     // even lanes hold {fwd, rev, sum tp, sum q} of allele sub / 2, odd lanes {sum mapq, sum nm, hicnt, std}
     const uint32_t ex_o = __shfl_xor_sync(0xffffffffu, ex, 1);
     const uint32_t hi_o = __shfl_xor_sync(0xffffffffu, x.z, 1);
-    const int refal = (int)(meta[it] & 7u) - 1;
-    const bool possible = (sub & 1) == 0 && (sub >> 1) != refal && (ex | ex_o) != 0 && x.x + x.y != 0 && (int)hi_o >= a.P.minr;
+    const int refal = (int)(mk & 7u) - 1;
+    const bool possible = valid && (sub & 1) == 0 && (sub >> 1) != refal && (ex | ex_o) != 0 && x.x + x.y != 0 && (int)hi_o >= a.P.minr;
     const unsigned b_pos = __ballot_sync(0xffffffffu, possible);
-    const bool dec = (meta[it] & 8u) && ((meta[it] & 16u) || ((b_pos >> (8 * grp)) & 0xffu) != 0);  // (possible implies a non-zero row; coverage is in the load condition)
-    const unsigned b = __ballot_sync(0xffffffffu, dec && sub == 0);
-    qmask |= ((b & 1u) | ((b >> 7) & 2u) | ((b >> 14) & 4u) | ((b >> 21) & 8u)) << (4 * it);
+    // the group leaders' verdicts, as bits at their positions
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int kg = __shfl_sync(0xffffffffu, k, 8 * g);
+      if ((b_pos >> (8 * g)) & 0xffu) qmask |= 1u << kg;
+    }
   }
   if ((qmask >> lane) & 1u) {
     cg::coalesced_group g = cg::coalesced_threads();
     unsigned long long slot = 0;
     if (g.thread_rank() == 0) slot = atomicAdd(a.patched_count, (unsigned long long)g.size());
-    a.patched_queue[g.shfl(slot, 0) + g.thread_rank()] = base + w0 + lane;
+    a.patched_queue[g.shfl(slot, 0) + g.thread_rank()] = t;
   }
 }
 
@@ -1334,6 +1353,10 @@ struct rv_ctx {
   int64_t ref_n;
   uint32_t* d_counts;
   uint32_t* d_cov;
+  int32_t* d_tabblk_region;   // region of table position 256 b (b = block): the kernels start from it instead of searching thousands of regions
+  int32_t* d_itemblk_region;  // region of work item 128 b
+  std::vector<int32_t> h_blk_region;
+  uint8_t* d_touched;  // per table position: a row of an allele other than the reference's has received something (rv_score_screen_kernel reads rows only there)
   rv_event* d_events;
   rv_variant* d_variants;
   rv_patch_entry* d_patch;
@@ -1589,6 +1612,9 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
       carve(&ctx->d_ref, (size_t)L.max_ref_bases);
       carve(&ctx->d_counts, sizeof(uint32_t) * RV_POS_U32 * (size_t)(L.max_positions + 1));
       carve(&ctx->d_cov, sizeof(uint32_t) * (size_t)(L.max_positions + 1));
+      carve(&ctx->d_touched, (size_t)(L.max_positions + 4));
+      carve(&ctx->d_tabblk_region, sizeof(int32_t) * (size_t)(L.max_positions / 256 + 4));
+      carve(&ctx->d_itemblk_region, sizeof(int32_t) * (size_t)(n_items_cap / 128 + 4));
       carve(&ctx->d_events, sizeof(rv_event) * (size_t)L.max_events);
       carve(&ctx->d_variants, sizeof(rv_variant) * (size_t)L.max_variants);
       carve(&ctx->d_patch, sizeof(rv_patch_entry) * (size_t)L.max_patch);
@@ -1801,6 +1827,25 @@ int rv_set_regions(rv_ctx* ctx, const rv_region* regs, int32_t n) {
   if (n) {
     CK(cudaMemcpyAsync(ctx->d_regions, ctx->regions.data(), sizeof(DevRegion) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_max_rl, ctx->h_max_rl, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    {
+      // region of the first position of every 256-position block / of the first item of every 128-item block: the last
+      // region whose base is <= it (what the binary searches of the kernels return)
+      const size_t nb_tab = (size_t)(tab / 256 + 1), nb_item = (size_t)(items / 128 + 1);
+      std::vector<int32_t>& h = ctx->h_blk_region;
+      h.resize(nb_tab + nb_item);
+      int r = 0;
+      for (size_t b = 0; b < nb_tab; ++b) {
+        while (r + 1 < n && ctx->regions[(size_t)r + 1].tab_off <= (int64_t)b * 256) ++r;
+        h[b] = r;
+      }
+      r = 0;
+      for (size_t b = 0; b < nb_item; ++b) {
+        while (r + 1 < n && ctx->regions[(size_t)r + 1].item_base <= (int64_t)b * 128) ++r;
+        h[nb_tab + b] = r;
+      }
+      CK(cudaMemcpyAsync(ctx->d_tabblk_region, h.data(), sizeof(int32_t) * nb_tab, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(ctx->d_itemblk_region, h.data() + nb_tab, sizeof(int32_t) * nb_item, cudaMemcpyHostToDevice, ctx->stream));
+    }
     // the async copies above read host vectors: make sure they are consumed before the caller can mutate them
     CK(cudaStreamSynchronize(ctx->stream));
   }
@@ -1820,6 +1865,7 @@ int rv_pileup(rv_ctx* ctx) {
   PileupArgs a;
   a.P = ctx->P;
   a.regions = ctx->d_regions;
+  a.itemblk_region = ctx->d_itemblk_region;
   a.n_regions = (int)ctx->regions.size();
   a.n_items = ctx->n_items;
   a.reads = ctx->reads_dev_view;
@@ -1896,6 +1942,7 @@ int rv_pileup(rv_ctx* ctx) {
     rv_tile_index_kernel<<<(unsigned)((ctx->n_tiles + 127) / 128), 128, 0, ctx->stream>>>(g);
     g.run = ctx->g4_run;
     g.alternate = ctx->g4_alt;
+    g.touched = ctx->d_touched;
     const int64_t g4_warps = (ctx->n_tiles + g.run - 1) / g.run;
     const unsigned g4_grid = (unsigned)((g4_warps + G4_WARPS - 1) / G4_WARPS);
     const int variant = ctx->g4_variant;
@@ -1910,7 +1957,7 @@ int rv_pileup(rv_ctx* ctx) {
   // 4. the SparseObs list onto the tables
   if (ctx->n_items > 0) {
     rv_apply_kernel<<<ctx->n_sms * 8, 256, 0, ctx->stream>>>(ctx->d_sparse, ctx->d_sparse_count, (unsigned long long)ctx->max_sparse,
-                                                           ctx->d_counts, ctx->d_cov, (int)ceil(ctx->P.goodq), ctx->d_stats);
+                                                           ctx->d_counts, ctx->d_cov, ctx->d_touched, (int)ceil(ctx->P.goodq), ctx->d_stats);
     ctx->launches++;
     CK(cudaGetLastError());
   }
@@ -2138,6 +2185,8 @@ static void fill_score_args(rv_ctx* ctx, ScoreArgs& a) {
   a.patch = ctx->d_patch;
   a.patch_first = ctx->have_patch ? ctx->d_patch_first : NULL;
   a.patch_count = ctx->d_patch_count;
+  a.touched = ctx->d_touched;
+  a.tabblk_region = ctx->d_tabblk_region;
   a.variants = ctx->d_variants;
   a.max_variants = (unsigned long long)ctx->L.max_variants;
   a.lgt = ctx->d_lgt;
