@@ -39,7 +39,7 @@ struct DevRegion {
 };
 
 
-static const size_t COUNTER_BLOCK_BYTES = 192;
+static const size_t COUNTER_BLOCK_BYTES = 256;
 struct DevStats {  // (must fit the first 128 bytes of the counter block)
   unsigned long long n_items, n_kept, n_bases, n_events, n_overflow, n_unsupported, n_variants, n_score_unsupported;
   unsigned long long n_walk_items, n_walk_full;
@@ -111,10 +111,16 @@ struct PileupArgs {
   // its 31 neighbours): their work item goes to this queue and rv_walk_kernel runs them densely packed
   // Whole-read walks fill the queue from the front, soft-clip-only walks (WALK_PLAIN_DONE) from the back, so that the
   // lanes of a warp of rv_walk_kernel run the same kind of walk side by side.
-  unsigned long long* walk_queue;   // item | WALK_PLAIN_DONE
-  unsigned long long* walk_count;   // [0] whole-read entries, [1] soft-clip-only entries
+  unsigned long long* walk_queue;   // item | flags | class << WALK_CLASS_SHIFT, in item order (rv_pileup_kernel)
+  unsigned long long* walk_queue2;  // the same entries grouped by class (rv_walk_sort_kernel): what rv_walk_kernel reads
+  unsigned long long* walk_count;   // [0] entries, [2] the walk kernel's cursor, [8..11] entries per class, [12..15] sort cursors
   unsigned long long walk_cap;
 };
+// Classes of queued reads by CIGAR shape (the lanes of a warp of rv_walk_kernel should run the same code: the kernel is
+// bound by instruction fetch): 0 = one M op (dirty ends, mismatch clusters, N bases), 1 = soft clips + one M, 2 = one
+// insertion or deletion (+ soft clips), 3 = everything else.  Walked in the order 3, 2, 0, 1 (longest first).
+static const int WALK_CLASS_SHIFT = 58;
+static const unsigned long long WALK_ITEM_MASK = (1ull << WALK_CLASS_SHIFT) - 1ull;
 static const unsigned long long WALK_PLAIN_DONE = 1ull << 62;  // the matched run already left a descriptor
 
 // Sink of prepare_read (read filters, CIGAR rewrite): statistics and maxReadLength only.
@@ -354,7 +360,7 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
                     reach = ml;
                   } else {  // clustered mismatches away from the ends: the literal walk (statistics are counted already)
                     queue = true;
-                    queue_entry = (unsigned long long)item;
+                    queue_entry = (unsigned long long)item;  // (class 0)
                   }
                 }
               }
@@ -364,7 +370,21 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
       }
       if (pass && !simple && !kept) {
         queue = true;
-        queue_entry = (unsigned long long)item | WALK_COUNT_STATS;
+        int cls = 3;
+        if (rd.n_cigar == 1) cls = 0;
+        else if (rd.n_cigar <= 6) {
+          const uint32_t* cg = (const uint32_t*)(a.pool + pool_off);
+          int n_indel = 0, n_other = 0, n_m = 0;
+          for (int k = 0; k < (int)rd.n_cigar; ++k) {
+            const int op = c_op(cg[k]);
+            if (op == OP_M) n_m++;
+            else if (op == OP_I || op == OP_D) n_indel++;
+            else if (op != OP_S) n_other++;
+          }
+          if (n_other == 0 && n_indel == 0 && n_m == 1) cls = 1;
+          else if (n_other == 0 && n_indel == 1 && n_m == 2) cls = 2;
+        }
+        queue_entry = (unsigned long long)item | WALK_COUNT_STATS | ((unsigned long long)cls << WALK_CLASS_SHIFT);
       }
     }
     *(uint4*)(a.descs + item) = *(const uint4*)&gd;
@@ -383,17 +403,20 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
   // queue slots: one atomic per CTA, entries of a CTA stay together in item order, so that neighbouring lanes of
   // rv_walk_kernel walk neighbouring reads (same indel site, same CIGAR shape: the lanes stay in step)
   __shared__ unsigned long long sh[2];
-  __shared__ unsigned s_qcnt[4];
+  __shared__ unsigned s_qcnt[4], s_cls[4];
   __shared__ unsigned long long s_qbase;
   const unsigned b0 = __ballot_sync(0xffffffffu, queue);
   if (lane == 0) s_qcnt[threadIdx.x >> 5] = __popc(b0);
   if (threadIdx.x < 2) sh[threadIdx.x] = 0;
+  if (threadIdx.x < 4) s_cls[threadIdx.x] = 0;
   __syncthreads();
+  if (queue) atomicAdd(&s_cls[(queue_entry >> WALK_CLASS_SHIFT) & 3ull], 1u);
   if (threadIdx.x == 0) {
     const unsigned tot = s_qcnt[0] + s_qcnt[1] + s_qcnt[2] + s_qcnt[3];
     s_qbase = tot ? atomicAdd(a.walk_count, (unsigned long long)tot) : 0ull;
   }
   __syncthreads();
+  if (threadIdx.x < 4 && s_cls[threadIdx.x]) atomicAdd(a.walk_count + 8 + threadIdx.x, (unsigned long long)s_cls[threadIdx.x]);
   if (queue) {
     unsigned long long slot = s_qbase;
     for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) slot += s_qcnt[w];
@@ -410,6 +433,42 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
   if (threadIdx.x == 0) {
     if (sh[0]) atomicAdd(&a.stats->n_kept, sh[0]);
     if (sh[1]) atomicAdd(&a.stats->n_bases, sh[1]);
+  }
+}
+
+// Groups the walk queue by class (stable inside a chunk of 256 entries, chunks in arbitrary order: neighbouring reads —
+// same indel site, same CIGAR shape — stay together).  Class c starts at the sum of the counts of the classes walked
+// before it.
+__global__ void __launch_bounds__(256) rv_walk_sort_kernel(PileupArgs a) {
+  const unsigned long long n = a.walk_count[0];
+  const unsigned long long n3 = a.walk_count[8 + 3], n2 = a.walk_count[8 + 2], n0 = a.walk_count[8 + 0];
+  __shared__ unsigned s_cnt[4];
+  __shared__ unsigned long long s_base[4];
+  const int lane = threadIdx.x & 31;
+  for (unsigned long long start = (unsigned long long)blockIdx.x * 256; start < n; start += (unsigned long long)gridDim.x * 256) {
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned long long q = start + threadIdx.x;
+    const bool have = q < n;
+    const unsigned long long e = have ? a.walk_queue[q] : 0ull;
+    const int c = have ? (int)((e >> WALK_CLASS_SHIFT) & 3ull) : -1;
+    unsigned rank = 0, wbase = 0;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const unsigned mk = __ballot_sync(0xffffffffu, c == cc);
+      unsigned wb = 0;
+      if (lane == 0 && mk) wb = atomicAdd(&s_cnt[cc], (unsigned)__popc(mk));
+      wb = __shfl_sync(0xffffffffu, wb, 0);
+      if (c == cc) { rank = __popc(mk & ((1u << lane) - 1u)); wbase = wb; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      const unsigned long long off = threadIdx.x == 3 ? 0ull : threadIdx.x == 2 ? n3 : threadIdx.x == 0 ? n3 + n2 : n3 + n2 + n0;
+      s_base[threadIdx.x] = off + (s_cnt[threadIdx.x] ? atomicAdd(a.walk_count + 12 + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]) : 0ull);
+    }
+    __syncthreads();
+    if (have) a.walk_queue2[s_base[c] + wbase + rank] = e;
+    __syncthreads();
   }
 }
 
@@ -432,8 +491,8 @@ __global__ void __launch_bounds__(128, MIN_CTAS) rv_walk_kernel(PileupArgs a) {
     if (q0 >= n) break;
     const unsigned long long q = q0 + lane;
     bool work = q < n;
-    const unsigned long long entry = work ? a.walk_queue[q] : 0ull;
-    const int64_t item = (int64_t)(entry & ~(WALK_COUNT_STATS | WALK_PLAIN_DONE));
+    const unsigned long long entry = work ? a.walk_queue2[q] : 0ull;
+    const int64_t item = (int64_t)(entry & WALK_ITEM_MASK);
     const int ri = find_region(a.regions, a.n_regions, item);
     const DevRegion* dr = a.regions + ri;
     const int64_t read_idx = dr->r.read_lo + (item - dr->item_base);
@@ -1376,6 +1435,8 @@ struct rv_ctx {
   int64_t* d_patched_queue;
   unsigned long long* d_patched_count;
   unsigned long long* d_walk_queue;
+  unsigned long long* d_walk_queue2;  // grouped by class (rv_walk_sort_kernel)
+  bool walk_sort;
   unsigned long long* d_walk_count;
   int64_t n_tiles;
   bool use_gather;  // false (RV_NO_GATHER=1, a debugging reference): no descriptors, every base through the SparseObs list
@@ -1558,6 +1619,7 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
   ctx->g4_alt = getenv("RV_G4_ALT") ? atoi(getenv("RV_G4_ALT")) : 1;
   ctx->g4_variant = getenv("RV_G4_VARIANT") ? atoi(getenv("RV_G4_VARIANT")) : 4;  // <4, 7>: 72 registers, fewest spills
   ctx->walk_occ = getenv("RV_WALK_OCC") ? atoi(getenv("RV_WALK_OCC")) : 4;
+  ctx->walk_sort = getenv("RV_NO_WALK_SORT") == NULL;
   ctx->d_descs2 = NULL; ctx->d_desc_mm2 = NULL; ctx->d_desc_mml2 = NULL; ctx->d_sparse = NULL; ctx->d_sparse_count = NULL;
   ctx->max_sparse = 0;
 
@@ -1646,6 +1708,7 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
       carve(&ctx->d_patched_queue, sizeof(int64_t) * (size_t)(L.max_positions + 1));
       carve(&ctx->d_patched_count, sizeof(unsigned long long));
       carve(&ctx->d_walk_queue, sizeof(unsigned long long) * n_items_cap);
+      carve(&ctx->d_walk_queue2, sizeof(unsigned long long) * n_items_cap);
       carve(&ctx->d_lgt, sizeof(double) * (size_t)ctx->lgt_n);
       if (pass == 0) {
         total = off;
@@ -1892,6 +1955,7 @@ int rv_pileup(rv_ctx* ctx) {
   a.reach = ctx->d_reach;
   a.force_exact = ctx->use_gather ? 0 : 1;
   a.walk_queue = ctx->d_walk_queue;
+  a.walk_queue2 = ctx->walk_sort ? ctx->d_walk_queue2 : ctx->d_walk_queue;
   a.walk_count = ctx->d_walk_count;
   a.walk_cap = (unsigned long long)(2 * ctx->L.max_reads + 1024);
   // 1. classify: filters, CIGAR rewrite, plain-run proof -> descriptors of the plain reads, queue of the others
@@ -1905,6 +1969,10 @@ int rv_pileup(rv_ctx* ctx) {
   // 2. the queued reads: CIGAR walk -> descriptors of their plain segments, SparseObs list, events
   if (ctx->n_items > 0) {
     // the queue length is only known on the device: a fixed grid of grid-stride threads
+    if (ctx->walk_sort) {
+      rv_walk_sort_kernel<<<ctx->n_sms * 2, 256, 0, ctx->stream>>>(a);
+      ctx->launches++;
+    }
     const int occ = ctx->walk_occ;
     if (occ == 8) rv_walk_kernel<8><<<ctx->n_sms * 8, 128, 0, ctx->stream>>>(a);
     else if (occ == 6) rv_walk_kernel<6><<<ctx->n_sms * 6, 128, 0, ctx->stream>>>(a);
