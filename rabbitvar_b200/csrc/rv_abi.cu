@@ -39,7 +39,7 @@ struct DevRegion {
 };
 
 
-static const size_t COUNTER_BLOCK_BYTES = 256;
+static const size_t COUNTER_BLOCK_BYTES = 320;
 struct DevStats {  // (must fit the first 128 bytes of the counter block)
   unsigned long long n_items, n_kept, n_bases, n_events, n_overflow, n_unsupported, n_variants, n_score_unsupported;
   unsigned long long n_walk_items, n_walk_full;
@@ -113,13 +113,15 @@ struct PileupArgs {
   // lanes of a warp of rv_walk_kernel run the same kind of walk side by side.
   unsigned long long* walk_queue;   // item | flags | class << WALK_CLASS_SHIFT, in item order (rv_pileup_kernel)
   unsigned long long* walk_queue2;  // the same entries grouped by class (rv_walk_sort_kernel): what rv_walk_kernel reads
-  unsigned long long* walk_count;   // [0] entries, [2] the walk kernel's cursor, [8..11] entries per class, [12..15] sort cursors
+  unsigned long long* walk_count;   // [0] entries, [2] the walk kernel's cursor, [8..15] entries per class, [16..23] sort cursors
   unsigned long long walk_cap;
 };
 // Classes of queued reads by CIGAR shape (the lanes of a warp of rv_walk_kernel should run the same code: the kernel is
-// bound by instruction fetch): 0 = one M op (dirty ends, mismatch clusters, N bases), 1 = soft clips + one M, 2 = one
-// insertion or deletion (+ soft clips), 3 = everything else.  Walked in the order 3, 2, 0, 1 (longest first).
-static const int WALK_CLASS_SHIFT = 58;
+// bound by instruction fetch): 0 = one M op (dirty ends, mismatch clusters, N bases), 1 = S M, 2 = M S, 3 = S M S,
+// 4 = M D M, 5 = M I M, 6 = one insertion or deletion with soft clips, 7 = everything else.  Walked from 7 down to 0
+// (longest first).
+static const int WALK_CLASSES = 8;
+static const int WALK_CLASS_SHIFT = 57;
 static const unsigned long long WALK_ITEM_MASK = (1ull << WALK_CLASS_SHIFT) - 1ull;
 static const unsigned long long WALK_PLAIN_DONE = 1ull << 62;  // the matched run already left a descriptor
 
@@ -370,19 +372,23 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
       }
       if (pass && !simple && !kept) {
         queue = true;
-        int cls = 3;
+        int cls = 7;
         if (rd.n_cigar == 1) cls = 0;
         else if (rd.n_cigar <= 6) {
           const uint32_t* cg = (const uint32_t*)(a.pool + pool_off);
-          int n_indel = 0, n_other = 0, n_m = 0;
+          int n_ins = 0, n_del = 0, n_other = 0, n_m = 0, n_clip = 0;
           for (int k = 0; k < (int)rd.n_cigar; ++k) {
             const int op = c_op(cg[k]);
             if (op == OP_M) n_m++;
-            else if (op == OP_I || op == OP_D) n_indel++;
-            else if (op != OP_S) n_other++;
+            else if (op == OP_I) n_ins++;
+            else if (op == OP_D) n_del++;
+            else if (op == OP_S) n_clip++;
+            else n_other++;
           }
-          if (n_other == 0 && n_indel == 0 && n_m == 1) cls = 1;
-          else if (n_other == 0 && n_indel == 1 && n_m == 2) cls = 2;
+          if (n_other == 0 && n_ins + n_del == 0 && n_m == 1)
+            cls = n_clip == 2 ? 3 : c_op(cg[0]) == OP_S ? 1 : 2;
+          else if (n_other == 0 && n_ins + n_del == 1 && n_m == 2)
+            cls = n_clip ? 6 : n_del ? 4 : 5;
         }
         queue_entry = (unsigned long long)item | WALK_COUNT_STATS | ((unsigned long long)cls << WALK_CLASS_SHIFT);
       }
@@ -403,20 +409,20 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
   // queue slots: one atomic per CTA, entries of a CTA stay together in item order, so that neighbouring lanes of
   // rv_walk_kernel walk neighbouring reads (same indel site, same CIGAR shape: the lanes stay in step)
   __shared__ unsigned long long sh[2];
-  __shared__ unsigned s_qcnt[4], s_cls[4];
+  __shared__ unsigned s_qcnt[4], s_cls[WALK_CLASSES];
   __shared__ unsigned long long s_qbase;
   const unsigned b0 = __ballot_sync(0xffffffffu, queue);
   if (lane == 0) s_qcnt[threadIdx.x >> 5] = __popc(b0);
   if (threadIdx.x < 2) sh[threadIdx.x] = 0;
-  if (threadIdx.x < 4) s_cls[threadIdx.x] = 0;
+  if (threadIdx.x < WALK_CLASSES) s_cls[threadIdx.x] = 0;
   __syncthreads();
-  if (queue) atomicAdd(&s_cls[(queue_entry >> WALK_CLASS_SHIFT) & 3ull], 1u);
+  if (queue) atomicAdd(&s_cls[(queue_entry >> WALK_CLASS_SHIFT) & (unsigned long long)(WALK_CLASSES - 1)], 1u);
   if (threadIdx.x == 0) {
     const unsigned tot = s_qcnt[0] + s_qcnt[1] + s_qcnt[2] + s_qcnt[3];
     s_qbase = tot ? atomicAdd(a.walk_count, (unsigned long long)tot) : 0ull;
   }
   __syncthreads();
-  if (threadIdx.x < 4 && s_cls[threadIdx.x]) atomicAdd(a.walk_count + 8 + threadIdx.x, (unsigned long long)s_cls[threadIdx.x]);
+  if (threadIdx.x < WALK_CLASSES && s_cls[threadIdx.x]) atomicAdd(a.walk_count + 8 + threadIdx.x, (unsigned long long)s_cls[threadIdx.x]);
   if (queue) {
     unsigned long long slot = s_qbase;
     for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) slot += s_qcnt[w];
@@ -441,31 +447,34 @@ __global__ void __launch_bounds__(128) rv_pileup_kernel(PileupArgs a) {
 // before it.
 __global__ void __launch_bounds__(256) rv_walk_sort_kernel(PileupArgs a) {
   const unsigned long long n = a.walk_count[0];
-  const unsigned long long n3 = a.walk_count[8 + 3], n2 = a.walk_count[8 + 2], n0 = a.walk_count[8 + 0];
-  __shared__ unsigned s_cnt[4];
-  __shared__ unsigned long long s_base[4];
+  __shared__ unsigned s_cnt[WALK_CLASSES];
+  __shared__ unsigned long long s_base[WALK_CLASSES], s_off[WALK_CLASSES];
+  if (threadIdx.x == 0) {  // class c starts after the classes walked before it (7, 6, ... c + 1)
+    unsigned long long off = 0;
+    for (int c = WALK_CLASSES - 1; c >= 0; --c) { s_off[c] = off; off += a.walk_count[8 + c]; }
+  }
   const int lane = threadIdx.x & 31;
   for (unsigned long long start = (unsigned long long)blockIdx.x * 256; start < n; start += (unsigned long long)gridDim.x * 256) {
-    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x < WALK_CLASSES) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const unsigned long long q = start + threadIdx.x;
     const bool have = q < n;
     const unsigned long long e = have ? a.walk_queue[q] : 0ull;
-    const int c = have ? (int)((e >> WALK_CLASS_SHIFT) & 3ull) : -1;
+    const int c = have ? (int)((e >> WALK_CLASS_SHIFT) & (unsigned long long)(WALK_CLASSES - 1)) : -1;
     unsigned rank = 0, wbase = 0;
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
+    for (int cc = 0; cc < WALK_CLASSES; ++cc) {
       const unsigned mk = __ballot_sync(0xffffffffu, c == cc);
+      if (mk == 0) continue;
       unsigned wb = 0;
-      if (lane == 0 && mk) wb = atomicAdd(&s_cnt[cc], (unsigned)__popc(mk));
+      if (lane == 0) wb = atomicAdd(&s_cnt[cc], (unsigned)__popc(mk));
       wb = __shfl_sync(0xffffffffu, wb, 0);
       if (c == cc) { rank = __popc(mk & ((1u << lane) - 1u)); wbase = wb; }
     }
     __syncthreads();
-    if (threadIdx.x < 4) {
-      const unsigned long long off = threadIdx.x == 3 ? 0ull : threadIdx.x == 2 ? n3 : threadIdx.x == 0 ? n3 + n2 : n3 + n2 + n0;
-      s_base[threadIdx.x] = off + (s_cnt[threadIdx.x] ? atomicAdd(a.walk_count + 12 + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]) : 0ull);
-    }
+    if (threadIdx.x < WALK_CLASSES)
+      s_base[threadIdx.x] = s_off[threadIdx.x] +
+                            (s_cnt[threadIdx.x] ? atomicAdd(a.walk_count + 16 + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]) : 0ull);
     __syncthreads();
     if (have) a.walk_queue2[s_base[c] + wbase + rank] = e;
     __syncthreads();
