@@ -660,6 +660,10 @@ RV_HD bool fast_obs(const FastDesc& d, int p, const uint8_t* pool, int* allele, 
 // Sink concept:
 //   void single(int pos, int allele, bool dir, int tp, int q, int mapq, int nm)   M-path obs, single base key
 //   void adj(int pos, int allele, int sign, bool dir, int tp, int q, int mapq, int nm)  addCnt / subtraction
+//   void sub_anchor(int pos, int allele, bool dir, int tp, int q, int mapq, int nm)   the anchor base an insertion takes back,
+//        parseCigar.cpp:1471-1490: only `if (tv != NULL)`, i.e. if this or an EARLIER read of the region (BAM order) has
+//        created the (position, base) entry.  Always true without -T (the read's own M loop has just done it); with -T the
+//        anchor can be a trimmed base, so the sinks defer the subtraction until every row's first contributor is known.
 //   void cov(int pos)                                                               refCoverage[pos]++
 //   void event(const rv_event&)
 //   void max_read_len(int tlen)
@@ -1411,7 +1415,7 @@ RV_HDN void walk_read(const rv_params& P, const rv_region& R, int region_idx, co
         int index = w.rp - 1 - (w.start - 1 - inspos);
         if (inspos > position && has_eq(ref, inspos, rd.base(index))) {
           int al = allele_of(rd.base(index));
-          if (al >= 0) sink.adj(inspos, al, -1, dir, tp, rd.q(index), mapq, nm - nmoff);
+          if (al >= 0) sink.sub_anchor(inspos, al, dir, tp, rd.q(index), mapq, nm - nmoff);
           else sink.unsupported();
         }
         // :1497-1515 — insertion right behind a leading S/H: one extra reference observation

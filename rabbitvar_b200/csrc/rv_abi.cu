@@ -161,6 +161,7 @@ struct ListSink {
   // list slots are reserved SPARSE_CHUNK at a time per lane (one atomic on the shared cursor per chunk, nothing to
   // wait for in between); what a lane has left over when the kernel ends is filled with no-op entries (flush)
   unsigned long long slot_next, slot_end;
+  uint32_t ridx1;  // -T only: the read's index in the batch + 1 (BAM order inside a region), 0 otherwise; travels with every entry
   __device__ __forceinline__ void put(int pos, uint32_t flags, int tp, int q, int mapq, int nm) {
     const int i = pos - first_pos;
     if (i < 0 || i >= n_pos) { n_clip++; return; }
@@ -174,7 +175,7 @@ struct ListSink {
     v.x = (uint32_t)(tab_off + i);
     v.y = ((uint32_t)tp & 0xffffu) | (((uint32_t)q & 0xffu) << 16) | (((uint32_t)mapq & 0xffu) << 24);
     v.z = ((uint32_t)nm & 0xffffu) | (flags << 16);
-    v.w = 0;
+    v.w = ridx1;
     *(uint4*)(a->sparse + slot) = v;
   }
   __device__ __forceinline__ void flush() {
@@ -186,6 +187,9 @@ struct ListSink {
   }
   __device__ __forceinline__ void adj(int pos, int allele, int sign, bool dir, int tp, int q, int mapq, int nm) {
     put(pos, (uint32_t)allele | (dir ? 4u : 0u) | ((sign > 0 ? SO_ADD : SO_SUB) << 3), tp, q, mapq, nm);
+  }
+  __device__ __forceinline__ void sub_anchor(int pos, int allele, bool dir, int tp, int q, int mapq, int nm) {
+    put(pos, (uint32_t)allele | (dir ? 4u : 0u) | (SO_SUB << 3), tp, q, mapq, nm);  // (-T: applied by the second apply pass)
   }
   __device__ __forceinline__ void cov(int pos) { put(pos, SO_COV << 3, 0, 0, 0, 0); }
   __device__ __forceinline__ void event(const rv_event& e) {
@@ -527,6 +531,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) rv_walk_kernel(PileupArgs a) {
     s.n_unsup = s.n_over = s.n_clip = s.n_ev = 0;
     s.slot_next = slot_next;
     s.slot_end = slot_end;
+    s.ridx1 = a.P.trim_bases_after != 0 ? (uint32_t)read_idx + 1u : 0u;
     Prep pr;
     pr.ok = false;
     pr.n_cigar = 0;
@@ -564,17 +569,27 @@ __global__ void __launch_bounds__(128, MIN_CTAS) rv_walk_kernel(PileupArgs a) {
 
 // The SparseObs list onto the tables (after the gather kernel has stored every row): one entry per thread.
 __device__ __forceinline__ void row_observe(uint32_t* row, uint32_t dir, uint32_t tp, uint32_t q, uint32_t mapq, uint32_t nm, int thr);
+// -T (pass != 0): the subtraction of an insertion's anchor base applies only if this or an earlier read created the row
+// (see the Sink concept in rv_core.cuh).  Pass 1 applies everything else and records every row's first contributor
+// (atomicMin of the read index), pass 2 — a second launch — applies the subtractions whose read is not before it.
 __global__ void __launch_bounds__(256) rv_apply_kernel(const SparseObs* list, const unsigned long long* count, unsigned long long cap,
-                                                        uint32_t* counts, uint32_t* cov, uint8_t* touched, int thr, DevStats* stats) {
+                                                        uint32_t* counts, uint32_t* cov, uint8_t* touched, int thr, DevStats* stats,
+                                                        uint32_t* first_read, int pass) {
   unsigned long long n = *count;
-  if (blockIdx.x == 0 && threadIdx.x == 0) stats->n_sparse = n;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && pass != 2) stats->n_sparse = n;
   if (n > cap) n = cap;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * blockDim.x) {
     const uint4 v = *(const uint4*)(list + i);
     if (v.x == 0xffffffffu) continue;  // unused slot of a lane's chunk
     const uint32_t flags = v.z >> 16, kind = (flags >> 3) & 3u;
-    if (kind == SO_COV) { atomicAdd(cov + v.x, 1u); continue; }
+    if (kind == SO_COV) { if (pass != 2) atomicAdd(cov + v.x, 1u); continue; }
+    if (pass == 1) {
+      if (kind == SO_SUB) continue;
+      if (v.w) atomicMin(first_read + (size_t)v.x * 4 + (flags & 3u), v.w - 1u);
+    } else if (pass == 2) {
+      if (kind != SO_SUB || !v.w || first_read[(size_t)v.x * 4 + (flags & 3u)] > v.w - 1u) continue;
+    }
     uint32_t* row = counts + ((size_t)v.x * 4 + (flags & 3u)) * RV_ROW_U32;
     touched[v.x] = 1;  // (whichever allele: the screen pass then looks at the position's rows)
     const uint32_t dir = (flags >> 2) & 1u, tp = v.y & 0xffffu, q = (v.y >> 16) & 0xffu, mapq = v.y >> 24;
@@ -1486,6 +1501,7 @@ struct rv_ctx {
   int32_t* h_max_rl;
   DevStats h_stats;
   uint8_t* d_arena;  // the one device allocation the buffers above are carved from
+  uint32_t* d_first_read;  // -T only: [position][allele] lowest read index that added to the row (allocated on first use)
   bool lazy;     // rv_set_lazy: rv_pileup / rv_score enqueue only; results are settled at rv_sync or by the first getter
   bool unsettled;
   bool unsettled_pileup;
@@ -1634,6 +1650,7 @@ int rv_create(rv_ctx** out, int device, const rv_params* params, const rv_limits
 
   ctx->d_desc_mml = NULL;
   ctx->d_arena = NULL;
+  ctx->d_first_read = NULL;
   ctx->pool_dev_bytes = 0;
   ctx->h_counts = NULL; ctx->h_cov = NULL; ctx->h_tab_cap = 0; ctx->h_events = NULL; ctx->h_events_cap = 0;
   ctx->h_variants = NULL; ctx->h_variants_cap = 0; ctx->h_max_rl = NULL; ctx->h_rows = NULL; ctx->h_rows_cap = 0; ctx->d_scratch = NULL; ctx->scratch_cap = 0;
@@ -1742,6 +1759,7 @@ void rv_destroy(rv_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaFree(ctx->d_arena);  // every device buffer but the scratch
+  cudaFree(ctx->d_first_read);
   cudaFree(ctx->d_scratch);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
   if (ctx->h_cov) cudaFreeHost(ctx->h_cov);
@@ -2033,9 +2051,24 @@ int rv_pileup(rv_ctx* ctx) {
   CK(cudaEventRecord(ctx->evs[2], ctx->stream));
   // 4. the SparseObs list onto the tables
   if (ctx->n_items > 0) {
-    rv_apply_kernel<<<ctx->n_sms * 8, 256, 0, ctx->stream>>>(ctx->d_sparse, ctx->d_sparse_count, (unsigned long long)ctx->max_sparse,
-                                                           ctx->d_counts, ctx->d_cov, ctx->d_touched, (int)ceil(ctx->P.goodq), ctx->d_stats);
-    ctx->launches++;
+    if (ctx->P.trim_bases_after == 0) {
+      rv_apply_kernel<<<ctx->n_sms * 8, 256, 0, ctx->stream>>>(ctx->d_sparse, ctx->d_sparse_count, (unsigned long long)ctx->max_sparse,
+                                                             ctx->d_counts, ctx->d_cov, ctx->d_touched, (int)ceil(ctx->P.goodq), ctx->d_stats,
+                                                             (uint32_t*)0, 0);
+      ctx->launches++;
+    } else {
+      // -T: first contributor of every row, then the conditional subtractions (two launches; the array exists only in this mode)
+      const size_t need = sizeof(uint32_t) * 4 * (size_t)(ctx->L.max_positions + 1);
+      if (!ctx->d_first_read) {
+        if (cudaMalloc(&ctx->d_first_read, need) != cudaSuccess) { cudaGetLastError(); return fail(ctx, RV_ERR_NOMEM, "out of device memory (-T: first contributor per row)"); }
+      }
+      CK(cudaMemsetAsync(ctx->d_first_read, 0xff, sizeof(uint32_t) * 4 * (size_t)ctx->n_positions, ctx->stream));
+      for (int pass = 1; pass <= 2; ++pass)
+        rv_apply_kernel<<<ctx->n_sms * 8, 256, 0, ctx->stream>>>(ctx->d_sparse, ctx->d_sparse_count, (unsigned long long)ctx->max_sparse,
+                                                               ctx->d_counts, ctx->d_cov, ctx->d_touched, (int)ceil(ctx->P.goodq), ctx->d_stats,
+                                                               ctx->d_first_read, pass);
+      ctx->launches += 2;
+    }
     CK(cudaGetLastError());
   }
   CK(cudaEventRecord(ctx->pev1, ctx->stream));

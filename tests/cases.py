@@ -50,6 +50,13 @@ CASES = {
                             "--seed", "41"], chrom="chrS5", region="1301-9300",
                        ref_args=_simple("chrS5", "1301-9300", ["-3", "-u"]), dump_args=["--three", "1", "--u", "1"],
                        stages="CRV", exact_stages=["C.", "R.", "V."]),
+    # -T 80 on the same data: reads are cut after 80 bases, so an insertion's anchor base can be a trimmed one and its
+    # subtraction from the reference allele depends on an EARLIER read having created the entry (parseCigar.cpp:1474-1476)
+    "edge_nh_T80_k1": dict(gen=["--cfg", "5", "--len", "10600", "--depth", "80", "--nbase-frac", "0.3", "--hardclip-frac", "0.2",
+                                "--seed", "41"], chrom="chrS5", region="1301-9300",
+                           ref_args=_simple("chrS5", "1301-9300", ["-3", "-u", "-T", "80"]),
+                           dump_args=["--three", "1", "--u", "1", "--T", "80"],
+                           stages="CRV", exact_stages=["C.", "R.", "V."]),
     # cfg 3: deep amplicon panel, low VAF, BED input (4-column BED => simple mode)
     "c3_k0": dict(gen=["--cfg", "3", "--len", "14600", "--depth", "2000", "--amplicons", "3"], chrom="chrS3",
                   bed="panel.bed", ref_args=_bed("chrS3", "panel.bed", ["-f", "0.005", "-k", "0"]),

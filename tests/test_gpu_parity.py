@@ -69,7 +69,7 @@ def _tsv_equal(a, b):
 
 
 @pytest.mark.parametrize("name", ["c1_k0", "c1_k1", "c5_k0", "c5_k1", "c3_k0", "c2_pileup_k0", "dedup_t", "dedup_t_F500",
-                                  "c5_un_k1", "edge_nh_k1"])
+                                  "c5_un_k1", "edge_nh_k1", "edge_nh_T80_k1"])
 def test_cli_tsv_matches_reference_output(built, name, tmp_path):
     """End to end through the drop-in CLI: same flags as the reference, same TSV (sorted multiset of lines;
     %f-printed doubles may differ in the last printed digit when the oracle's -ffast-math quotient is off by an ulp)."""

@@ -35,6 +35,7 @@ struct SimSink {
   bool in_segment = false;
   void single(int pos, int allele, bool dir, int tp, int q, int mapq, int nm) {
     if (!in_segment) n_direct++;
+    note_contributor(pos, allele);
     if (getenv("RV_DEBUG_POS") && atoi(getenv("RV_DEBUG_POS")) == pos) fprintf(stderr, "single pos %d al %d dir %d tp %d q %d mapq %d nm %d\n", pos, allele, dir, tp, q, mapq, nm);
     if (!idx(pos)) return;
     uint32_t* row = R->row(pos, allele);
@@ -52,8 +53,36 @@ struct SimSink {
       if (((old >> 16) & 0xffu) != ((uint32_t)q & 0xffu)) row[RV_F_STD] |= 1u << 25;
     }
   }
+  // -T: the anchor subtraction is conditional on the row's first contributor (Sink concept, rv_core.cuh); the device defers
+  // it to a second pass over the observation list, and so does this harness
+  int trim = 0;
+  uint32_t cur_ridx = 0;
+  std::map<std::pair<int, int>, uint32_t> first_read;
+  struct Deferred { int pos, allele; bool dir; int tp, q, mapq, nm; uint32_t ridx; };
+  std::vector<Deferred> deferred;
+  void note_contributor(int pos, int allele) {
+    if (!trim) return;
+    std::map<std::pair<int, int>, uint32_t>::iterator it = first_read.find(std::make_pair(pos, allele));
+    if (it == first_read.end()) first_read[std::make_pair(pos, allele)] = cur_ridx;
+    else if (cur_ridx < it->second) it->second = cur_ridx;
+  }
+  void sub_anchor(int pos, int allele, bool dir, int tp, int q, int mapq, int nm) {
+    if (!trim) { adj(pos, allele, -1, dir, tp, q, mapq, nm); return; }
+    Deferred d = {pos, allele, dir, tp, q, mapq, nm, cur_ridx};
+    deferred.push_back(d);
+  }
+  void apply_deferred() {
+    for (size_t k = 0; k < deferred.size(); ++k) {
+      const Deferred& d = deferred[k];
+      std::map<std::pair<int, int>, uint32_t>::const_iterator it = first_read.find(std::make_pair(d.pos, d.allele));
+      if (it != first_read.end() && it->second <= d.ridx) adj(d.pos, d.allele, -1, d.dir, d.tp, d.q, d.mapq, d.nm);
+    }
+    deferred.clear();
+    first_read.clear();
+  }
   void adj(int pos, int allele, int sign, bool dir, int tp, int q, int mapq, int nm) {
     n_adj++;
+    if (sign > 0) note_contributor(pos, allele);
     if (getenv("RV_DEBUG_POS") && atoi(getenv("RV_DEBUG_POS")) == pos) fprintf(stderr, "adj pos %d al %d sign %d dir %d tp %d q %d\n", pos, allele, sign, dir, tp, q);
     if (!idx(pos)) return;
     uint32_t* row = R->row(pos, allele);
@@ -293,6 +322,7 @@ int main(int argc, char** argv) {
       ref.hi = regs[r].ref_hi;
       SimSink s;
       s.R = &R; s.events = &events; s.goodq = P.goodq;
+      s.trim = P.trim_bases_after;
       s.kept_reads = s.kept_bases = s.unsup = s.over = 0;
       const bool use_fast = getenv("RV_NO_GATHER") == NULL;
       s.use_segments = use_fast && getenv("RV_NO_SEGMENTS") == NULL;
@@ -309,11 +339,13 @@ int main(int argc, char** argv) {
         rvk::FastDesc d;
         memset(&d, 0, sizeof d);
         s.cur_read = &rd;
+        s.cur_ridx = (uint32_t)i;
         // RV_SIM_NO_FASTDESC=1: every read goes the way rv_walk_kernel takes (plain stretches through scan_segment)
         static const bool no_fastdesc = getenv("RV_SIM_NO_FASTDESC") != NULL;
         rvk::process_read(P, regs[r], (int)r, rd, batch.pool.data(), ref, (uint32_t)i, s, (use_fast && !no_fastdesc) ? &d : (rvk::FastDesc*)0);
         if (d.m_len) descs.push_back(d);
       }
+      s.apply_deferred();
       // the gather kernel's work, position by position
       for (size_t k = 0; k < descs.size(); ++k) {
         const rvk::FastDesc& d = descs[k];
