@@ -1222,63 +1222,105 @@ __global__ void __launch_bounds__(SCORE_BLOCK, 4) rv_score_kernel(ScoreArgs a) {
 // Candidate mode (rv_params.candidates_only, simple-mode and paired-mode output): integer work only.  A position can print something only if one of its non-reference alleles has hicnt >= minr (a
 // necessary condition of Variant::isGoodVar, include/Variant.h:205-231); those positions, and the positions with
 // patch entries, are queued for the general scoring kernel.  Everything else ends here after one pass over its row.
-// Layout of the pass: a warp owns 32 consecutive table positions.  Phase 1, one position per lane: region, reference allele,
-// patch flag, coverage, and the pileup's `touched` byte (some allele other than the reference's was observed there: without
-// it the rows cannot hold a candidate, and they are not read — one byte instead of 128 per position).  Phase 2 visits only
-// the positions that need their rows, four per round, EIGHT LANES PER POSITION: lane s loads bytes [16 s, 16 s + 16) of the
-// position's 128-byte row block (whole lines per load instruction; one thread per position touched 32 lines per
-// instruction and ran at half the HBM rate), the eight 16-byte parts are combined with one shuffle pair and a ballot.
+// Layout of the pass: a warp owns 128 consecutive table positions.
+//   A. four positions per lane, two vector loads: patch flags and the pileup's `touched` bytes (some allele other than the
+//      reference's was observed there).  A position with neither can print nothing and ends here: no region lookup, no
+//      reference base, no coverage, and above all none of its 128 bytes of rows (6 % of the positions go on at 30x, 30 % at
+//      300x).
+//   B. the positions that go on, one per lane (32 per round): region, reference allele, coverage.  Patched ones are queued as
+//      they are.
+//   C. the others' rows, four positions per round, EIGHT LANES PER POSITION: lane s loads bytes [16 s, 16 s + 16) of the
+//      position's 128-byte row block (whole lines per load instruction; one thread per position touched 32 lines per
+//      instruction and ran at half the HBM rate), the eight 16-byte parts are combined with one shuffle pair and a ballot.
 __global__ void __launch_bounds__(256) rv_score_screen_kernel(ScoreArgs a) {
   const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
-  const int64_t w_base = (int64_t)blockIdx.x * 256 + (threadIdx.x & ~31);  // the warp's first position
-  const int64_t t = w_base + lane;
-  // bits 0-2: reference allele + 1 (0 = none), 3: inside the region, 4: has patch entries, 5: coverage != 0, 6: touched
-  uint32_t m = 0;
-  const int r_first = a.tabblk_region[blockIdx.x];  // (blockDim.x == 256) region of the CTA's first position
-  if (t < a.n_positions) {
-    const int ri = find_region_by_tab_near(a.regions, a.n_regions, t, r_first);
-    const DevRegion* dr = a.regions + ri;
-    const int pos = dr->first_pos + (int)(t - dr->tab_off);
-    if (pos >= dr->r.start && pos <= dr->r.end) {
-      m = 8u;
-      if (pos >= dr->r.ref_lo && pos <= dr->r.ref_hi && pos >= a.ref_start && (int64_t)(pos - a.ref_start) < a.ref_n)
-        m |= (uint32_t)(allele_of(a.ref[pos - a.ref_start]) + 1);
-      if ((a.patch_first ? a.patch_first[t] : 0u) != 0) m |= 16u;
-      if (a.cov[t] != 0) m |= 32u;
-      if (a.touched[t]) m |= 64u;
+  const int64_t w_base = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 128;  // the warp's first position
+  if (w_base >= a.n_positions) return;  // (whole warps; the kernel has no CTA barrier)
+  // ---- A
+  unsigned m4[4];  // m4[j]: lanes whose position 4 * lane + j goes on
+  {
+    const int64_t t4 = w_base + 4 * lane;
+    uint32_t tw = 0;
+    uint4 pf = make_uint4(0, 0, 0, 0);
+    if (t4 + 3 < a.n_positions) {
+      tw = *(const uint32_t*)(a.touched + t4);
+      if (a.patch_first) pf = *(const uint4*)(a.patch_first + t4);
+    } else {
+      if (t4 + 0 < a.n_positions) { tw |= (uint32_t)a.touched[t4 + 0]; if (a.patch_first) pf.x = a.patch_first[t4 + 0]; }
+      if (t4 + 1 < a.n_positions) { tw |= (uint32_t)a.touched[t4 + 1] << 8; if (a.patch_first) pf.y = a.patch_first[t4 + 1]; }
+      if (t4 + 2 < a.n_positions) { tw |= (uint32_t)a.touched[t4 + 2] << 16; if (a.patch_first) pf.z = a.patch_first[t4 + 2]; }
     }
+    m4[0] = __ballot_sync(0xffffffffu, (tw & 0x000000ffu) || pf.x);
+    m4[1] = __ballot_sync(0xffffffffu, (tw & 0x0000ff00u) || pf.y);
+    m4[2] = __ballot_sync(0xffffffffu, (tw & 0x00ff0000u) || pf.z);
+    m4[3] = __ballot_sync(0xffffffffu, (tw & 0xff000000u) || pf.w);
   }
-  // positions with patch entries are queued as they are; rows are read where they can matter: inside the region, covered,
-  // not queued already, touched
-  unsigned qmask = __ballot_sync(0xffffffffu, (m & (8u | 16u)) == (8u | 16u));
-  const unsigned need = __ballot_sync(0xffffffffu, (m & (8u | 16u | 32u | 64u)) == (8u | 32u | 64u));
-  const int n_need = __popc(need);
-  for (int r = 0; 4 * r < n_need; ++r) {
-    const int idx = 4 * r + grp;
-    const bool valid = idx < n_need;
-    const int k = valid ? (int)__fns(need, 0u, idx + 1) : 0;  // the group's position: the idx-th one that needs its rows
-    const uint32_t mk = __shfl_sync(0xffffffffu, m, k);
-    uint4 x = make_uint4(0, 0, 0, 0);
-    if (valid) x = __ldg((const uint4*)(a.counts + (size_t)(w_base + k) * RV_POS_U32) + sub);
-    const uint32_t ex = x.x | x.y | x.z | x.w;
-    // even lanes hold {fwd, rev, sum tp, sum q} of allele sub / 2, odd lanes {sum mapq, sum nm, hicnt, std}
-    const uint32_t ex_o = __shfl_xor_sync(0xffffffffu, ex, 1);
-    const uint32_t hi_o = __shfl_xor_sync(0xffffffffu, x.z, 1);
-    const int refal = (int)(mk & 7u) - 1;
-    const bool possible = valid && (sub & 1) == 0 && (sub >> 1) != refal && (ex | ex_o) != 0 && x.x + x.y != 0 && (int)hi_o >= a.P.minr;
-    const unsigned b_pos = __ballot_sync(0xffffffffu, possible);
-    // the group leaders' verdicts, as bits at their positions
+  const int c0 = __popc(m4[0]), c1 = __popc(m4[1]), c2 = __popc(m4[2]), total = c0 + c1 + c2 + __popc(m4[3]);
+  const int r_first = a.tabblk_region[w_base >> 8];  // region of a position at or before the warp's first
+  for (int r0 = 0; r0 < total; r0 += 32) {
+    // ---- B: this lane's position of the round
+    int off = -1;  // position - w_base
+    {
+      int kk = r0 + lane;
+      if (kk < total) {
+        int j = 0;
+        unsigned mk = m4[0];
+        if (kk >= c0) { kk -= c0; j = 1; mk = m4[1];
+          if (kk >= c1) { kk -= c1; j = 2; mk = m4[2];
+            if (kk >= c2) { kk -= c2; j = 3; mk = m4[3]; } } }
+        off = 4 * (int)__fns(mk, 0u, kk + 1) + j;
+      }
+    }
+    // bits 0-2: reference allele + 1 (0 = none), 3: inside the region, 4: has patch entries, 5: coverage != 0, 6: touched
+    uint32_t m = 0;
+    const int64_t t = w_base + (off < 0 ? 0 : off);
+    if (off >= 0) {
+      const int ri = find_region_by_tab_near(a.regions, a.n_regions, t, r_first);
+      const DevRegion* dr = a.regions + ri;
+      const int pos = dr->first_pos + (int)(t - dr->tab_off);
+      if (pos >= dr->r.start && pos <= dr->r.end) {
+        m = 8u;
+        if (pos >= dr->r.ref_lo && pos <= dr->r.ref_hi && pos >= a.ref_start && (int64_t)(pos - a.ref_start) < a.ref_n)
+          m |= (uint32_t)(allele_of(a.ref[pos - a.ref_start]) + 1);
+        if ((a.patch_first ? a.patch_first[t] : 0u) != 0) m |= 16u;
+        if (a.cov[t] != 0) m |= 32u;
+        if (a.touched[t]) m |= 64u;
+      }
+    }
+    // positions with patch entries are queued as they are; rows are read where they can matter: inside the region, covered,
+    // not queued already, touched
+    unsigned qmask = __ballot_sync(0xffffffffu, (m & (8u | 16u)) == (8u | 16u));
+    const unsigned need = __ballot_sync(0xffffffffu, (m & (8u | 16u | 32u | 64u)) == (8u | 32u | 64u));
+    const int n_need = __popc(need);
+    // ---- C
+    for (int r = 0; 4 * r < n_need; ++r) {
+      const int idx = 4 * r + grp;
+      const bool valid = idx < n_need;
+      const int k = valid ? (int)__fns(need, 0u, idx + 1) : 0;  // the lane (of B) whose position this group reads
+      const uint32_t mk = __shfl_sync(0xffffffffu, m, k);
+      const int offk = __shfl_sync(0xffffffffu, off, k);
+      uint4 x = make_uint4(0, 0, 0, 0);
+      if (valid) x = __ldg((const uint4*)(a.counts + (size_t)(w_base + offk) * RV_POS_U32) + sub);
+      const uint32_t ex = x.x | x.y | x.z | x.w;
+      // even lanes hold {fwd, rev, sum tp, sum q} of allele sub / 2, odd lanes {sum mapq, sum nm, hicnt, std}
+      const uint32_t ex_o = __shfl_xor_sync(0xffffffffu, ex, 1);
+      const uint32_t hi_o = __shfl_xor_sync(0xffffffffu, x.z, 1);
+      const int refal = (int)(mk & 7u) - 1;
+      const bool possible = valid && (sub & 1) == 0 && (sub >> 1) != refal && (ex | ex_o) != 0 && x.x + x.y != 0 && (int)hi_o >= a.P.minr;
+      const unsigned b_pos = __ballot_sync(0xffffffffu, possible);
+      // the group leaders' verdicts, as bits at their lanes of B
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int kg = __shfl_sync(0xffffffffu, k, 8 * g);
-      if ((b_pos >> (8 * g)) & 0xffu) qmask |= 1u << kg;
+      for (int g = 0; g < 4; ++g) {
+        const int kg = __shfl_sync(0xffffffffu, k, 8 * g);
+        if ((b_pos >> (8 * g)) & 0xffu) qmask |= 1u << kg;
+      }
     }
-  }
-  if ((qmask >> lane) & 1u) {
-    cg::coalesced_group g = cg::coalesced_threads();
-    unsigned long long slot = 0;
-    if (g.thread_rank() == 0) slot = atomicAdd(a.patched_count, (unsigned long long)g.size());
-    a.patched_queue[g.shfl(slot, 0) + g.thread_rank()] = t;
+    if ((qmask >> lane) & 1u) {
+      cg::coalesced_group g = cg::coalesced_threads();
+      unsigned long long slot = 0;
+      if (g.thread_rank() == 0) slot = atomicAdd(a.patched_count, (unsigned long long)g.size());
+      a.patched_queue[g.shfl(slot, 0) + g.thread_rank()] = t;
+    }
   }
 }
 
@@ -2318,7 +2360,7 @@ int rv_score(rv_ctx* ctx) {
   if (ctx->n_positions > 0) {
     CK(cudaMemsetAsync(ctx->d_patched_count, 0, sizeof(unsigned long long), ctx->stream));
     if (ctx->P.candidates_only && !ctx->P.pileup) {
-      rv_score_screen_kernel<<<(unsigned)((ctx->n_positions + 255) / 256), 256, 0, ctx->stream>>>(a);
+      rv_score_screen_kernel<<<(unsigned)((ctx->n_positions + 1023) / 1024), 256, 0, ctx->stream>>>(a);
       rv_score_patched_kernel<<<148 * 8, 128, 0, ctx->stream>>>(a);
       ctx->launches += 2;
       CK(cudaGetLastError());
