@@ -1621,9 +1621,17 @@ int rv_warmup(int device) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return RV_ERR_CUDA;
   if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess) return RV_ERR_CUDA;
-  // loads the module (the sm_100a image of every kernel) as well
+  // With lazy module loading (the CUDA 12 default) a kernel's image is loaded at its first launch — under a lock, in the
+  // middle of the first jobs.  Asking for the attributes of the kernels a run uses loads them here, on the caller's
+  // warm-up thread, beside the decode threads.
   cudaFuncAttributes fa;
-  if (cudaFuncGetAttributes(&fa, rv_pack_ref_kernel) != cudaSuccess) { cudaGetLastError(); return RV_ERR_CUDA; }
+  const void* used[] = {(const void*)rv_pack_ref_kernel, (const void*)rv_pileup_kernel, (const void*)rv_walk_sort_kernel,
+                        (const void*)rv_walk_kernel<4>, (const void*)rv_tile_index_kernel, (const void*)rv_gather4_kernel<4, 7>,
+                        (const void*)rv_apply_kernel, (const void*)rv_score_screen_kernel, (const void*)rv_score_patched_kernel,
+                        (const void*)rv_score_list_kernel, (const void*)rv_lgamma_table_kernel, (const void*)rv_gather_rows_kernel,
+                        (const void*)rv_patch_scatter_kernel, (const void*)rv_cov_scatter_kernel, (const void*)rv_cov_summary_kernel};
+  for (size_t k = 0; k < sizeof(used) / sizeof(used[0]); ++k)
+    if (cudaFuncGetAttributes(&fa, used[k]) != cudaSuccess) { cudaGetLastError(); return RV_ERR_CUDA; }
   return RV_OK;
 }
 
