@@ -47,6 +47,7 @@ struct DevStats {  // (must fit the first 128 bytes of the counter block)
   unsigned long long n_sparse;   // SparseObs entries the walk kernel left for rv_apply_kernel
   unsigned long long n_segments; // gather descriptors written by the walk kernel
 };
+static_assert(sizeof(DevStats) <= 128, "DevStats must fit the first 128 bytes of the counter block");
 
 // Gather descriptor of one plain matched segment (rvk::scan_plain_segment / the plain-run proof of rv_pileup_kernel):
 // all the gather kernel needs to find the segment's qualities and to give every base its read position.
