@@ -415,12 +415,23 @@ def main():
     cli_out = os.path.join(d, f"cli_{world}_{rank}.tsv")
     cli_cmd = [pc.CLI] + pc.cli_args(key, d, length)
     cli_cmd[cli_cmd.index("-i") + 1] = my_bed
-    cli_cmd += ["--th", str(th), "--device", str(local), "--out", cli_out]
+    # the CLI process sees this rank's GPU only: a fresh process initialises every device it can see, and eight cost
+    # several times what one does (the CLI does the same cut by itself; here it is explicit and independent of the
+    # launcher's CUDA_VISIBLE_DEVICES)
+    cli_env = dict(os.environ)
+    vis = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+    if not vis:
+        cli_env["CUDA_VISIBLE_DEVICES"], cli_dev = str(local), 0
+    elif local < len(vis):
+        cli_env["CUDA_VISIBLE_DEVICES"], cli_dev = vis[local], 0
+    else:
+        cli_dev = local
+    cli_cmd += ["--th", str(th), "--device", str(cli_dev), "--out", cli_out]
     e2e_t, cli_info, cli_startup = [], "", []
     for i in range(1 + args.e2e_steps if args.e2e_steps > 0 else 0):
         barrier()
         t_a = time.perf_counter()
-        r = subprocess.run(cli_cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        r = subprocess.run(cli_cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=cli_env)
         dt = time.perf_counter() - t_a
         if r.returncode != 0:
             raise rv.RabbitVarError(f"CLI failed (rc {r.returncode}): {r.stderr[-500:]}")

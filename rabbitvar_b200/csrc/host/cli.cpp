@@ -204,9 +204,25 @@ int main(int argc, char** argv) {
   // CUDA start-up (driver initialisation, primary context, module load) runs beside the header / index / BED parsing.
   // With one device in use the others are hidden from the driver first: initialising eight GPUs costs several times
   // what initialising one does.
-  if (!c.decode_only && c.gpus == 1 && getenv("CUDA_VISIBLE_DEVICES") == NULL) {
-    setenv("CUDA_VISIBLE_DEVICES", std::to_string(c.device).c_str(), 1);
-    c.device = 0;
+  // (--device counts within CUDA_VISIBLE_DEVICES when a launcher has set one — torchrun jobs usually run with all eight
+  // listed —, so the entry it names is the one kept)
+  if (!c.decode_only && c.gpus == 1) {
+    const char* vis = getenv("CUDA_VISIBLE_DEVICES");
+    if (vis == NULL) {
+      setenv("CUDA_VISIBLE_DEVICES", std::to_string(c.device).c_str(), 1);
+      c.device = 0;
+    } else {
+      std::vector<std::string> ids;
+      std::string cur;
+      for (const char* p = vis;; ++p) {
+        if (*p == ',' || *p == 0) { ids.push_back(cur); cur.clear(); if (*p == 0) break; }
+        else if (*p != ' ') cur += *p;
+      }
+      if (ids.size() > 1 && c.device >= 0 && (size_t)c.device < ids.size() && !ids[c.device].empty()) {
+        setenv("CUDA_VISIBLE_DEVICES", ids[c.device].c_str(), 1);
+        c.device = 0;
+      }
+    }
   }
   double cuda_init_ms = 0;
   std::thread cuda_init;
