@@ -571,7 +571,11 @@ def main():
                          "split_ms": {"rv_pileup_kernel": split[0], "rv_walk_kernel": split[2],
                                       "rv_tile_index_kernel+rv_gather4_kernel": split[1], "rv_apply_kernel": split[3]},
                          "score_kernel": {"achieved": alg_score / sk / 1e9, "kernel_ms": sk * 1000.0,
-                                          "algorithmic_bytes_per_launch": alg_score}},
+                                          "algorithmic_bytes_per_launch": alg_score,
+                                          "note": "SURVEY 8d counts every table row once (133 B per position); the screen kernel reads the "
+                                                  "1 B per position touched map and the rows of touched / patched positions only, so at "
+                                                  "low depth 'achieved' (algorithmic bytes / time) can exceed the HBM peak: it is not a "
+                                                  "bandwidth"}},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
