@@ -5,8 +5,9 @@
 // decoder is written for that one job — whole blocks, input and output both in memory, sizes known up front:
 //   * a 64-bit bit buffer refilled with one unaligned 8-byte load, at most once per literal/length + distance pair;
 //   * one table look-up per codeword in the common case: 11-bit primary table for literal/length codes, 8-bit for
-//     distance codes, second-level tables behind the longer codes; an entry carries the symbol's base value, its
-//     codeword length and its number of extra bits;
+//     distance codes, second-level tables behind the longer codes; an entry carries the symbol's base value, the
+//     bits to drop for it (codeword + extra bits: ONE shift of the bit buffer on the decode loop's dependency chain,
+//     the extra bits are cut out of a saved copy beside it) and its number of extra bits;
 //   * matches copied eight bytes at a time (byte-wise only for distances < 8);
 //   * a careful loop (byte-wise refill, every store bounds-checked) for the last few hundred bytes of a block.
 // CRC-32 (IEEE 802.3, the gzip polynomial) by carry-less multiplication (PCLMULQDQ folding, Gopal et al., "Fast CRC
@@ -68,8 +69,10 @@ class FastInflate {
 
  private:
   enum { LL_BITS = 11, D_BITS = 8, LL_SIZE = 2048 + 1024, D_SIZE = 256 + 512 };
-  // table entry: bits 0-3 codeword length still to consume, 4-7 extra bits (or sub-table index bits for a pointer),
-  // 8 literal, 9 sub-table pointer, 10 end of block, 11 invalid; 16-31 base value / literal / sub-table start
+  // table entry: bits 0-5 bits to drop = codeword length still to consume + extra bits (<= 28; bits 6-7 are zero, so
+  // the low byte is the shift count), 8 literal, 9 sub-table pointer, 10 end of block, 11 invalid, 12-15 extra bits
+  // (or sub-table index bits for a pointer); 16-31 base value / literal / sub-table start.  The precode table of
+  // read_dynamic_tables has the codeword length in its low bits and no extra bits.
   enum { F_LIT = 1u << 8, F_SUB = 1u << 9, F_EOB = 1u << 10, F_BAD = 1u << 11 };
 
   const uint8_t *in_, *in_end_;
@@ -157,7 +160,7 @@ class FastInflate {
       if (!sub_len[p]) continue;
       const int sz = 1 << sub_len[p];
       if (sub_next + sz > tab_size) return false;
-      tab[p] = F_SUB | ((uint32_t)sub_len[p] << 4) | (uint32_t)tbits | ((uint32_t)sub_next << 16);
+      tab[p] = F_SUB | ((uint32_t)sub_len[p] << 12) | (uint32_t)tbits | ((uint32_t)sub_next << 16);
       for (int i = 0; i < sz; ++i) tab[sub_next + i] = F_BAD | 1u;
       sub_next += sz;
     }
@@ -169,22 +172,22 @@ class FastInflate {
       if (litlen) {
         if (s < 256) e = F_LIT | ((uint32_t)s << 16);
         else if (s == 256) e = F_EOB;
-        else if (s < 286) e = ((uint32_t)len_extra[s - 257] << 4) | ((uint32_t)len_base[s - 257] << 16);
+        else if (s < 286) e = ((uint32_t)len_extra[s - 257] << 12) | (uint32_t)len_extra[s - 257] | ((uint32_t)len_base[s - 257] << 16);
         else e = F_BAD;
       } else {
-        if (s < 30) e = ((uint32_t)dist_extra[s] << 4) | ((uint32_t)dist_base[s] << 16);
+        if (s < 30) e = ((uint32_t)dist_extra[s] << 12) | (uint32_t)dist_extra[s] | ((uint32_t)dist_base[s] << 16);
         else e = F_BAD;
       }
       if (l <= tbits) {
-        e |= (uint32_t)l;
+        e += (uint32_t)l;  // (bits to drop: extra bits + codeword)
         const unsigned r = reverse_bits(c, l);
         for (unsigned i = r; i < (unsigned)primary; i += 1u << l) tab[i] = e;
       } else {
         const unsigned prefix = reverse_bits(c >> (l - tbits), tbits);
         const uint32_t pe = tab[prefix];
-        const int sb = (int)((pe >> 4) & 15), start = (int)(pe >> 16);
+        const int sb = (int)((pe >> 12) & 15), start = (int)(pe >> 16);
         const int rl = l - tbits;
-        e |= (uint32_t)rl;
+        e += (uint32_t)rl;
         const unsigned r = reverse_bits(c & ((1u << rl) - 1u), rl);
         for (unsigned i = r; i < (1u << sb); i += 1u << rl) tab[start + i] = e;
       }
@@ -260,6 +263,12 @@ class FastInflate {
   static inline uint64_t load64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
   static inline void store64(uint8_t* p, uint64_t v) { memcpy(p, &v, 8); }
 
+  // the extra bits of a symbol whose entry is e, out of the bit buffer as it was before the symbol was dropped
+  static inline unsigned extra_of(uint64_t saved, uint32_t e) {
+    const unsigned tot = e & 63u, xb = (e >> 12) & 15u;
+    return (unsigned)((saved & (((uint64_t)1 << tot) - 1u)) >> (tot - xb));
+  }
+
   bool coded_block(const uint32_t* lt, const uint32_t* dt) {
     const uint64_t ll_mask = (1u << LL_BITS) - 1, d_mask = (1u << D_BITS) - 1;
     // ---- fast loop: >= 16 input bytes and >= 280 output bytes of slack, so neither needs a check inside ----
@@ -271,33 +280,31 @@ class FastInflate {
       uint32_t e = lt[bitbuf_ & ll_mask];
       if (e & F_SUB) {
         drop(LL_BITS);
-        e = lt[(e >> 16) + (bitbuf_ & ((1u << ((e >> 4) & 15)) - 1u))];
+        e = lt[(e >> 16) + (bitbuf_ & ((1u << ((e >> 12) & 15)) - 1u))];
       }
-      drop(e & 15);
+      uint64_t saved = bitbuf_;
+      drop(e & 63u);  // codeword and extra bits in one shift
       if (e & F_LIT) {
         *out_++ = (uint8_t)(e >> 16);
         // more literals from the same refill (primary-table hits only, <= 11 bits each)
         while (bits_ >= 11 && ((e = lt[bitbuf_ & ll_mask]) & F_LIT)) {
-          drop(e & 15);
+          drop(e & 63u);
           *out_++ = (uint8_t)(e >> 16);
         }
         continue;
       }
       if (e & (F_EOB | F_BAD)) return (e & F_EOB) != 0;
       {
-        const unsigned xb = (e >> 4) & 15;
-        const unsigned len = (e >> 16) + (unsigned)(bitbuf_ & ((1u << xb) - 1u));
-        drop(xb);
+        const unsigned len = (e >> 16) + extra_of(saved, e);
         uint32_t de = dt[bitbuf_ & d_mask];
         if (de & F_SUB) {
           drop(D_BITS);
-          de = dt[(de >> 16) + (bitbuf_ & ((1u << ((de >> 4) & 15)) - 1u))];
+          de = dt[(de >> 16) + (bitbuf_ & ((1u << ((de >> 12) & 15)) - 1u))];
         }
         if (de & F_BAD) return false;
-        drop(de & 15);
-        const unsigned dxb = (de >> 4) & 15;
-        const unsigned dist = (de >> 16) + (unsigned)(bitbuf_ & ((1u << dxb) - 1u));
-        drop(dxb);
+        saved = bitbuf_;
+        drop(de & 63u);
+        const unsigned dist = (de >> 16) + extra_of(saved, de);
         if (dist > (size_t)(out_ - out_begin_)) return false;
         uint8_t* dst = out_;
         const uint8_t* src = out_ - dist;
@@ -326,9 +333,10 @@ class FastInflate {
       uint32_t e = lt[bitbuf_ & ll_mask];
       if (e & F_SUB) {
         drop(LL_BITS);
-        e = lt[(e >> 16) + (bitbuf_ & ((1u << ((e >> 4) & 15)) - 1u))];
+        e = lt[(e >> 16) + (bitbuf_ & ((1u << ((e >> 12) & 15)) - 1u))];
       }
-      drop(e & 15);
+      uint64_t saved = bitbuf_;
+      drop(e & 63u);
       if (e & F_LIT) {
         if (out_ >= out_end_) return false;
         *out_++ = (uint8_t)(e >> 16);
@@ -336,20 +344,17 @@ class FastInflate {
       }
       if (e & F_EOB) return true;
       if (e & F_BAD) return false;
-      const unsigned xb = (e >> 4) & 15;
-      const unsigned len = (e >> 16) + (unsigned)(bitbuf_ & ((1u << xb) - 1u));
-      drop(xb);
+      const unsigned len = (e >> 16) + extra_of(saved, e);
       need(32);
       uint32_t de = dt[bitbuf_ & d_mask];
       if (de & F_SUB) {
         drop(D_BITS);
-        de = dt[(de >> 16) + (bitbuf_ & ((1u << ((de >> 4) & 15)) - 1u))];
+        de = dt[(de >> 16) + (bitbuf_ & ((1u << ((de >> 12) & 15)) - 1u))];
       }
       if (de & F_BAD) return false;
-      drop(de & 15);
-      const unsigned dxb = (de >> 4) & 15;
-      const unsigned dist = (de >> 16) + (unsigned)(bitbuf_ & ((1u << dxb) - 1u));
-      drop(dxb);
+      saved = bitbuf_;
+      drop(de & 63u);
+      const unsigned dist = (de >> 16) + extra_of(saved, de);
       if (dist > (size_t)(out_ - out_begin_) || len > (size_t)(out_end_ - out_)) return false;
       const uint8_t* src = out_ - dist;
       for (unsigned k = 0; k < len; ++k) out_[k] = src[k];
