@@ -113,10 +113,12 @@ class FastInflate {
     return true;
   }
 
-  static inline unsigned reverse_bits(unsigned v, int n) {
-    unsigned r = 0;
-    for (int i = 0; i < n; ++i) { r = (r << 1) | (v & 1); v >>= 1; }
-    return r;
+  static inline unsigned reverse_bits(unsigned v, int n) {  // the low n (1..16) bits of v, reversed
+    v = ((v & 0x5555u) << 1) | ((v >> 1) & 0x5555u);
+    v = ((v & 0x3333u) << 2) | ((v >> 2) & 0x3333u);
+    v = ((v & 0x0f0fu) << 4) | ((v >> 4) & 0x0f0fu);
+    v = ((v & 0x00ffu) << 8) | ((v >> 8) & 0x00ffu);
+    return v >> (16 - n);
   }
 
   // canonical Huffman decode table from code lengths (RFC 1951 3.2.2); false for an over-subscribed code.
@@ -139,55 +141,56 @@ class FastInflate {
       next_code[l] = code;
     }
     const int primary = 1 << tbits;
-    for (int i = 0; i < primary; ++i) tab[i] = F_BAD | 1u;
-    int sub_next = primary;  // next free slot for second-level tables
-    // second-level tables: one per distinct tbits-bit prefix of the codes longer than tbits; sized by the longest
-    // code that shares the prefix.  Pass 1: longest length per prefix.
-    uint8_t sub_len[1 << LL_BITS];
-    memset(sub_len, 0, (size_t)primary);
-    {
-      unsigned nc[16];
-      memcpy(nc, next_code, sizeof nc);
-      for (int s = 0; s < n; ++s) {
-        const int l = lens[s];
-        if (l <= tbits) { if (l) nc[l]++; continue; }
-        const unsigned c = nc[l]++;
-        const unsigned prefix = reverse_bits(c >> (l - tbits), tbits);
-        if (l - tbits > sub_len[prefix]) sub_len[prefix] = (uint8_t)(l - tbits);
-      }
-    }
-    for (int p = 0; p < primary; ++p) {
-      if (!sub_len[p]) continue;
-      const int sz = 1 << sub_len[p];
-      if (sub_next + sz > tab_size) return false;
-      tab[p] = F_SUB | ((uint32_t)sub_len[p] << 12) | (uint32_t)tbits | ((uint32_t)sub_next << 16);
-      for (int i = 0; i < sz; ++i) tab[sub_next + i] = F_BAD | 1u;
-      sub_next += sz;
-    }
-    for (int s = 0; s < n; ++s) {
-      const int l = lens[s];
-      if (!l) continue;
-      const unsigned c = next_code[l]++;
-      uint32_t e;
+    // the entry of symbol s without its codeword length
+    auto entry_of = [&](int s) -> uint32_t {
       if (litlen) {
-        if (s < 256) e = F_LIT | ((uint32_t)s << 16);
-        else if (s == 256) e = F_EOB;
-        else if (s < 286) e = ((uint32_t)len_extra[s - 257] << 12) | (uint32_t)len_extra[s - 257] | ((uint32_t)len_base[s - 257] << 16);
-        else e = F_BAD;
-      } else {
-        if (s < 30) e = ((uint32_t)dist_extra[s] << 12) | (uint32_t)dist_extra[s] | ((uint32_t)dist_base[s] << 16);
-        else e = F_BAD;
+        if (s < 256) return F_LIT | ((uint32_t)s << 16);
+        if (s == 256) return F_EOB;
+        if (s < 286) return ((uint32_t)len_extra[s - 257] << 12) | (uint32_t)len_extra[s - 257] | ((uint32_t)len_base[s - 257] << 16);
+        return F_BAD;
       }
-      if (l <= tbits) {
-        e += (uint32_t)l;  // (bits to drop: extra bits + codeword)
-        const unsigned r = reverse_bits(c, l);
-        for (unsigned i = r; i < (unsigned)primary; i += 1u << l) tab[i] = e;
-      } else {
+      if (s < 30) return ((uint32_t)dist_extra[s] << 12) | (uint32_t)dist_extra[s] | ((uint32_t)dist_base[s] << 16);
+      return F_BAD;
+    };
+    // symbols ordered by codeword length, then by symbol: the order canonical codewords are handed out in
+    uint16_t first[17], put[16], sorted[288 + 32];
+    first[1] = 0;
+    for (int l = 1; l <= 15; ++l) { first[l + 1] = (uint16_t)(first[l] + count[l]); put[l] = first[l]; }
+    for (int s = 0; s < n; ++s)
+      if (lens[s]) sorted[put[lens[s]]++] = (uint16_t)s;
+    // Primary table by doubling: after the codewords of l bits are in place (one store each, at their bit-reversed
+    // value) the 2^l entries so far are copied behind themselves; a slot no codeword reaches stays invalid.
+    tab[0] = F_BAD | 1u;
+    for (int l = 1; l <= tbits; ++l) {
+      const int half = 1 << (l - 1);
+      memcpy(tab + half, tab, (size_t)half * sizeof(uint32_t));
+      unsigned c = next_code[l];
+      for (int k = first[l]; k < first[l + 1]; ++k, ++c) tab[reverse_bits(c, l)] = entry_of(sorted[k]) + (uint32_t)l;
+    }
+    // Second-level tables: one per distinct tbits-bit prefix of the codes longer than tbits, sized by the longest code
+    // that shares the prefix — lengths ascend in `sorted`, so the last pointer written for a prefix carries it.
+    int sub_next = primary;  // next free slot
+    for (int l = tbits + 1; l <= 15; ++l) {
+      unsigned c = next_code[l];
+      for (int k = first[l]; k < first[l + 1]; ++k, ++c)
+        tab[reverse_bits(c >> (l - tbits), tbits)] = F_SUB | ((uint32_t)(l - tbits) << 12) | (uint32_t)tbits;  // (start 0 = not placed yet)
+    }
+    for (int l = tbits + 1; l <= 15; ++l) {
+      unsigned c = next_code[l];
+      for (int k = first[l]; k < first[l + 1]; ++k, ++c) {
         const unsigned prefix = reverse_bits(c >> (l - tbits), tbits);
-        const uint32_t pe = tab[prefix];
-        const int sb = (int)((pe >> 12) & 15), start = (int)(pe >> 16);
-        const int rl = l - tbits;
-        e += (uint32_t)rl;
+        uint32_t pe = tab[prefix];
+        const int sb = (int)((pe >> 12) & 15);
+        if ((pe >> 16) == 0) {
+          const int sz = 1 << sb;
+          if (sub_next + sz > tab_size) return false;
+          pe |= (uint32_t)sub_next << 16;
+          tab[prefix] = pe;
+          for (int i = 0; i < sz; ++i) tab[sub_next + i] = F_BAD | 1u;
+          sub_next += sz;
+        }
+        const int start = (int)(pe >> 16), rl = l - tbits;
+        const uint32_t e = entry_of(sorted[k]) + (uint32_t)rl;  // (bits to drop: extra bits + the rest of the codeword)
         const unsigned r = reverse_bits(c & ((1u << rl) - 1u), rl);
         for (unsigned i = r; i < (1u << sb); i += 1u << rl) tab[start + i] = e;
       }
