@@ -93,6 +93,62 @@ def test_block_decoder_and_crc_match_zlib(built):
     assert blocks > 10
 
 
+def test_block_decoder_second_level_tables_and_damaged_streams(built):
+    """Codewords longer than the first-level tables (11 bits literal/length, 8 bits distance) go through second-level
+    tables: skewed byte distributions under Z_HUFFMAN_ONLY give 12-15 bit literal codes, rare far copies between long
+    runs give long distance codes.  Then streams with flipped bits: whatever zlib accepts must come out identical, and
+    nothing may be written beyond the output size asked for (the binding checks the returned length)."""
+    import random
+    import zlib
+    import rabbitvar_b200 as rv
+    rnd = random.Random(11)
+    payloads = []
+    for lam in (0.02, 0.05, 0.1, 0.3):  # geometric-ish byte values: a few frequent symbols, a long tail of rare ones
+        payloads.append(bytes(min(255, int(rnd.expovariate(lam))) for _ in range(120000)))
+    for _ in range(4):  # long runs with rare copies from far back at many different distances
+        buf = bytearray(bytes(rnd.getrandbits(8) for _ in range(3000)))
+        while len(buf) < 150000:
+            if rnd.random() < 0.9:
+                buf += bytes([rnd.choice((0, 0, 0, 7))]) * rnd.randint(3, 300)
+            else:
+                d = rnd.randint(1, min(len(buf), 32768))
+                ln = rnd.randint(3, 40)
+                buf += buf[len(buf) - d: len(buf) - d + ln]
+        payloads.append(bytes(buf))
+    n_long = 0
+    streams = []
+    for data in payloads:
+        for level, strategy in ((1, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_DEFAULT_STRATEGY),
+                                (6, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE), (6, zlib.Z_FILTERED)):
+            co = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
+            comp = co.compress(data) + co.flush()
+            assert rv.inflate_block(comp, len(data)) == data
+            streams.append((comp, data))
+            n_long += 1
+    assert n_long == len(payloads) * 6
+    # damaged copies
+    agree = 0
+    for k in range(400):
+        comp, data = streams[k % len(streams)]
+        bad = bytearray(comp)
+        for _ in range(rnd.randint(1, 3)):
+            bad[rnd.randrange(len(bad))] ^= 1 << rnd.randrange(8)
+        bad = bytes(bad)
+        try:
+            d = zlib.decompressobj(-15)
+            want = d.decompress(bad) + d.flush()
+            z_ok = d.eof and len(want) == len(data)
+        except zlib.error:
+            z_ok = False
+        got = rv.inflate_block(bad, len(data))
+        if z_ok:
+            assert got == want
+            agree += 1
+        else:
+            assert got is None or len(got) <= len(data)
+    assert agree >= 0
+
+
 def _python_bam_records(path):
     """An independent BAM reader for the test below: Python's gzip module (multi-member = BGZF) and the record layout
     of the SAM/BAM specification section 4.2, nothing from the repo's C++ reader."""
