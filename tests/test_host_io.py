@@ -228,3 +228,109 @@ def test_loader_matches_an_independent_python_reader(built, name, bam, chrom):
             o = int(g["off"]) * 16
             assert pool[o:o + len(w["tail"])].tobytes() == w["tail"]
         b.close()
+
+
+def _reg2bin(beg, end):
+    """SAM specification section 5.3 (C code of the specification, restated): bin of the 0-based half-open [beg, end)."""
+    end -= 1
+    if beg >> 14 == end >> 14:
+        return ((1 << 15) - 1) // 7 + (beg >> 14)
+    if beg >> 17 == end >> 17:
+        return ((1 << 12) - 1) // 7 + (beg >> 17)
+    if beg >> 20 == end >> 20:
+        return ((1 << 9) - 1) // 7 + (beg >> 20)
+    if beg >> 23 == end >> 23:
+        return ((1 << 6) - 1) // 7 + (beg >> 23)
+    if beg >> 26 == end >> 26:
+        return ((1 << 3) - 1) // 7 + (beg >> 26)
+    return 0
+
+
+@pytest.mark.parametrize("name,bam", [("c5_k1", "S.bam"), ("c1_k1", "S.bam")])
+def test_bai_written_by_the_generator_follows_the_specification(built, name, bam):
+    """The .bai the loader's queries rest on is written by the repo's own code (tools/synthgen via csrc/io/bamio.hpp), so
+    a reader and a writer that agree with each other but not with the format would go unnoticed.  Here the index is
+    parsed from the SAM specification's section 5.2 layout with struct, the records and their virtual offsets come from a
+    BGZF walk with zlib, and the two must fit: every record lies inside a chunk of the bin reg2bin() gives it (the bin
+    field of the record says the same), and the linear index holds, per 16 kb window, the virtual offset of the first
+    record that overlaps it."""
+    import struct
+    import zlib
+    d = cases.generate(name)
+    raw = open(os.path.join(d, bam), "rb").read()
+    # BGZF walk: uncompressed stream + where each block starts in both coordinates
+    blocks, data, p = [], bytearray(), 0
+    while p + 18 <= len(raw):
+        bsize = struct.unpack_from("<H", raw, p + 16)[0] + 1
+        blocks.append((p, len(data)))
+        data += zlib.decompress(raw[p + 18: p + bsize - 8], -15)
+        p += bsize
+    data = bytes(data)
+    ustarts = [u for _, u in blocks]
+
+    def voffset(u):  # virtual offset of uncompressed position u
+        import bisect
+        i = bisect.bisect_right(ustarts, u) - 1
+        while i + 1 < len(blocks) and blocks[i + 1][1] == u:  # an empty block: the position belongs to the next one
+            i += 1
+        return (blocks[i][0] << 16) | (u - blocks[i][1])
+
+    assert data[:4] == b"BAM\1"
+    l_text, = struct.unpack_from("<i", data, 4)
+    o = 8 + l_text
+    n_ref, = struct.unpack_from("<i", data, o)
+    o += 4
+    for _ in range(n_ref):
+        l_name, = struct.unpack_from("<i", data, o)
+        o += 8 + l_name
+    recs = []
+    while o < len(data):
+        bs, = struct.unpack_from("<i", data, o)
+        tid, pos, l_qname, mapq, bin_, n_cigar, flag, l_seq = struct.unpack_from("<iiBBHHHi", data, o + 4)
+        cigar = struct.unpack_from("<%dI" % n_cigar, data, o + 36 + l_qname)
+        ref_len = sum(c >> 4 for c in cigar if (c & 15) in (0, 2, 3, 7, 8))
+        end = pos + (ref_len if ref_len and not flag & 4 else 1)
+        recs.append((tid, pos, end, bin_, voffset(o), o, o + 4 + bs))
+        o += 4 + bs
+    assert len(recs) > 100
+    # the index, section 5.2
+    bai = open(os.path.join(d, bam + ".bai"), "rb").read()
+    assert bai[:4] == b"BAI\1"
+    n, = struct.unpack_from("<i", bai, 4)
+    assert n == n_ref
+    q = 8
+    index = []
+    for _ in range(n):
+        n_bin, = struct.unpack_from("<i", bai, q)
+        q += 4
+        bins = {}
+        for _ in range(n_bin):
+            b, n_chunk = struct.unpack_from("<Ii", bai, q)
+            q += 8
+            bins[b] = [struct.unpack_from("<QQ", bai, q + 16 * k) for k in range(n_chunk)]
+            q += 16 * n_chunk
+        n_intv, = struct.unpack_from("<i", bai, q)
+        q += 4
+        lin = list(struct.unpack_from("<%dQ" % n_intv, bai, q))
+        q += 8 * n_intv
+        index.append((bins, lin))
+    assert q == len(bai) or q + 8 == len(bai)  # (optional n_no_coor)
+    first_in_window = {}
+    cstart = {c: u for c, u in blocks}
+
+    def upos(v):  # uncompressed position of a virtual offset (the end of a block and the start of the next are one place)
+        return cstart[v >> 16] + (v & 0xffff)
+
+    for tid, pos, end, bin_, v0, u0, u1 in recs:
+        if tid < 0:
+            continue
+        want_bin = _reg2bin(pos, end)
+        assert bin_ == want_bin
+        bins, lin = index[tid]
+        assert want_bin in bins
+        assert any(upos(c0) <= u0 and u1 <= upos(c1) for c0, c1 in bins[want_bin]), (tid, pos, hex(v0), bins[want_bin][:3])
+        for w in range(pos >> 14, ((end - 1) >> 14) + 1):
+            first_in_window.setdefault((tid, w), v0)
+    for (tid, w), v in first_in_window.items():
+        lin = index[tid][1]
+        assert w < len(lin) and lin[w] == v, (tid, w, hex(lin[w]) if w < len(lin) else None, hex(v))
