@@ -205,23 +205,27 @@ int main(int argc, char** argv) {
   // With one device in use the others are hidden from the driver first: initialising eight GPUs costs several times
   // what initialising one does.
   // (--device counts within CUDA_VISIBLE_DEVICES when a launcher has set one — torchrun jobs usually run with all eight
-  // listed —, so the entry it names is the one kept)
-  if (!c.decode_only && c.gpus == 1) {
+  // listed —, so the entries [device, device + gpus) of that list are the ones kept)
+  if (!c.decode_only && c.gpus >= 1 && c.device >= 0) {
     const char* vis = getenv("CUDA_VISIBLE_DEVICES");
+    std::vector<std::string> ids;
     if (vis == NULL) {
-      setenv("CUDA_VISIBLE_DEVICES", std::to_string(c.device).c_str(), 1);
-      c.device = 0;
+      for (int k = 0; k < c.device + c.gpus; ++k) ids.push_back(std::to_string(k));
     } else {
-      std::vector<std::string> ids;
       std::string cur;
       for (const char* p = vis;; ++p) {
         if (*p == ',' || *p == 0) { ids.push_back(cur); cur.clear(); if (*p == 0) break; }
         else if (*p != ' ') cur += *p;
       }
-      if (ids.size() > 1 && c.device >= 0 && (size_t)c.device < ids.size() && !ids[c.device].empty()) {
-        setenv("CUDA_VISIBLE_DEVICES", ids[c.device].c_str(), 1);
-        c.device = 0;
-      }
+    }
+    std::string keep;
+    for (size_t k = (size_t)c.device; k < ids.size() && k < (size_t)(c.device + c.gpus); ++k) {
+      if (ids[k].empty()) { keep.clear(); break; }
+      keep += (keep.empty() ? "" : ",") + ids[k];
+    }
+    if (!keep.empty()) {
+      setenv("CUDA_VISIBLE_DEVICES", keep.c_str(), 1);
+      c.device = 0;
     }
   }
   double cuda_init_ms = 0;
