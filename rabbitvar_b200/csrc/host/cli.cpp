@@ -206,7 +206,7 @@ int main(int argc, char** argv) {
   // what initialising one does.
   // (--device counts within CUDA_VISIBLE_DEVICES when a launcher has set one — torchrun jobs usually run with all eight
   // listed —, so the entries [device, device + gpus) of that list are the ones kept)
-  if (!c.decode_only && c.gpus >= 1 && c.device >= 0) {
+  if (c.gpus >= 1 && c.device >= 0) {
     const char* vis = getenv("CUDA_VISIBLE_DEVICES");
     std::vector<std::string> ids;
     if (vis == NULL) {
@@ -299,6 +299,7 @@ int main(int argc, char** argv) {
          "records + TSV %.0f; first job decoded at %.0f ms, last at %.0f ms, first job taken by a GPU worker at %.0f ms\n",
          st.stage_ms[0], st.stage_ms[1], st.stage_ms[2], st.stage_ms[3], st.stage_ms[4], st.stage_ms[5], st.stage_ms[6], st.stage_ms[7],
          st.first_job_ready_ms, st.last_decode_done_ms, st.first_gpu_job_start_ms);
+  printf("[info] CUDA_VISIBLE_DEVICES of this run: %s\n", getenv("CUDA_VISIBLE_DEVICES") ? getenv("CUDA_VISIBLE_DEVICES") : "(unset)");
   printf("[info] timeline ms: inputs parsed %.0f, cuda start-up %.0f (beside the decode threads), pipeline done %.0f, output written %.0f\n",
          t_parsed - t0, cuda_init_ms, t_ran - t0, now_ms() - t0);
   printf("total time: %f s \n", (now_ms() - t0) / 1000.0);

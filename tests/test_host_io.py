@@ -334,3 +334,22 @@ def test_bai_written_by_the_generator_follows_the_specification(built, name, bam
     for (tid, w), v in first_in_window.items():
         lin = index[tid][1]
         assert w < len(lin) and lin[w] == v, (tid, w, hex(lin[w]) if w < len(lin) else None, hex(v))
+
+
+def test_cli_narrows_the_visible_devices(built):
+    """`--device d --gpus n` keeps the entries [d, d + n) of CUDA_VISIBLE_DEVICES (or of 0, 1, 2, ... when it is unset)
+    before CUDA starts: a fresh process initialises every device it can see.  Checked on the decode-only path, which
+    needs no GPU."""
+    import subprocess
+    d = cases.generate("c1_k1")
+    cli = os.path.join(cases.ROOT, "build", "rabbitvar_b200")
+    base = [cli, "-G", os.path.join(d, "ref.fa"), "-b", os.path.join(d, "S.bam"), "-R", "chrS1:1301-2300", "--decode-only",
+            "--out", os.path.join(d, "narrow.tsv")]
+    for vis, dev, gpus, want in (("0,1,2,3", 1, 2, "1,2"), ("0,1,2,3", 3, 1, "3"), ("GPU-aa, GPU-bb", 1, 1, "GPU-bb"),
+                                 (None, 2, 1, "2"), (None, 0, 2, "0,1"), ("5", 0, 1, "5"), ("0,1", 1, 4, "1")):
+        env = {k: v for k, v in os.environ.items() if k != "CUDA_VISIBLE_DEVICES"}
+        if vis is not None:
+            env["CUDA_VISIBLE_DEVICES"] = vis
+        r = subprocess.run(base + ["--device", str(dev), "--gpus", str(gpus)], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr[-300:]
+        assert f"CUDA_VISIBLE_DEVICES of this run: {want}\n" in r.stdout, (vis, dev, gpus, r.stdout[-400:])
